@@ -1,0 +1,306 @@
+"""ctypes front-end of the CPU oracle (oracle/_build/liborb_oracle.so).
+
+TEST INFRASTRUCTURE ONLY — see oracle/orb_oracle.h.  Importable from tests/, __graft_entry__.smoke()
+and bench.py's cpu_baseline / --impl reference legs; never from orb_slam_2_ros_b200/.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "liborb_oracle.so")
+
+KP_DTYPE = np.dtype(
+    [("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+     ("octave", "<i4"), ("class_id", "<i4")]
+)
+TOP2_DTYPE = np.dtype([("best_dist", "<i4"), ("best_idx", "<i4"), ("second_dist", "<i4"), ("second_idx", "<i4")])
+
+MODE_TRACK_LAST = 0
+MODE_LOCAL_POINTS = 1
+
+
+class SearchParams(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("th_dist", C.c_int32), ("nn_ratio", C.c_float),
+                ("check_orientation", C.c_int32)]
+
+
+class StereoParams(C.Structure):
+    _fields_ = [("bf", C.c_float), ("b", C.c_float)]
+
+
+def build(force=False):
+    """Compile the oracle with the committed Makefile (gcc only, a few seconds)."""
+    srcs = [os.path.join(_HERE, f) for f in
+            ("orb_oracle_extract.cpp", "orb_oracle_match.cpp", "orb_oracle.h", "orb_pattern_31.inc", "Makefile")]
+    if (not force) and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in srcs):
+        return _SO
+    subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        vp, i32, f32 = C.c_void_p, C.c_int32, C.c_float
+        L.orc_extractor_create.restype = vp
+        L.orc_extractor_create.argtypes = [i32, f32, i32, i32, i32]
+        L.orc_extractor_destroy.argtypes = [vp]
+        L.orc_extractor_tables.argtypes = [vp] + [vp] * 6
+        L.orc_extract.argtypes = [vp, vp, i32, i32, i32, vp, vp, i32]
+        L.orc_level_dims.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32)]
+        L.orc_get_level.argtypes = [vp, i32, vp]
+        L.orc_get_blurred.argtypes = [vp, i32, vp]
+        L.orc_raw_corner_count.argtypes = [vp, i32]
+        L.orc_get_raw_corners.argtypes = [vp, i32, vp, i32]
+        L.orc_level_kp_count.argtypes = [vp, i32]
+        L.orc_get_level_kps.argtypes = [vp, i32, vp, i32]
+        L.orc_get_stats.argtypes = [vp, vp]
+        L.orc_count_near_half_taps.argtypes = [vp, f32]
+        L.orc_resize_linear_u8.argtypes = [vp, i32, i32, i32, vp, i32, i32, i32]
+        L.orc_border_reflect101.argtypes = [vp, i32, i32, i32, vp, i32, i32]
+        L.orc_fast9_16.argtypes = [vp, i32, i32, i32, i32, i32, vp, i32]
+        L.orc_gaussian7x7_s2.argtypes = [vp, i32, i32, i32, vp, i32]
+        L.orc_fast_atan2.restype = f32
+        L.orc_fast_atan2.argtypes = [f32, f32]
+        L.orc_cv_round_f.argtypes = [f32]
+        L.orc_ic_angle.restype = f32
+        L.orc_ic_angle.argtypes = [vp, i32]
+        L.orc_brief_descriptor.argtypes = [vp, i32, f32, vp]
+        L.orc_descriptor_distance.argtypes = [vp, vp]
+        L.orc_hamming_top2.argtypes = [vp, i32, vp, i32, vp]
+        L.orc_hamming_top2_csr.argtypes = [vp, i32, vp, vp, vp, vp]
+        L.orc_grid_create.restype = vp
+        L.orc_grid_create.argtypes = [vp, i32, f32, f32, f32, f32]
+        L.orc_grid_destroy.argtypes = [vp]
+        L.orc_grid_query.argtypes = [vp, f32, f32, f32, i32, i32, vp, i32]
+        L.orc_search_by_projection_ex.argtypes = [C.POINTER(SearchParams), vp, vp, vp, vp, i32, vp, i32] + [vp] * 13
+        L.orc_match_bruteforce.argtypes = [vp, vp, i32, vp, vp, i32, i32, f32, i32, vp]
+        L.orc_stereo_match.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, C.POINTER(StereoParams), vp, vp, vp]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _u8(a):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    return a
+
+
+class Extractor:
+    """Oracle ORBextractor (reference ORBextractor.cc:416-479, 1083-1149)."""
+
+    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+        self.nfeatures, self.nlevels = nfeatures, nlevels
+        self._h = lib().orc_extractor_create(nfeatures, scale_factor, nlevels, ini_th, min_th)
+        sc = np.zeros(nlevels, np.float32); isc = sc.copy(); s2 = sc.copy(); is2 = sc.copy()
+        per = np.zeros(nlevels, np.int32); um = np.zeros(16, np.int32)
+        lib().orc_extractor_tables(self._h, _p(sc), _p(isc), _p(s2), _p(is2), _p(per), _p(um))
+        self.scale_factors, self.inv_scale_factors = sc, isc
+        self.level_sigma2, self.inv_level_sigma2 = s2, is2
+        self.features_per_level, self.umax = per, um
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_extractor_destroy(self._h)
+            self._h = None
+
+    def extract(self, img):
+        img = _u8(img)
+        h, w = img.shape
+        cap = self.nfeatures + 8 * self.nlevels + 64
+        while True:
+            kps = np.zeros(cap, KP_DTYPE)
+            desc = np.zeros((cap, 32), np.uint8)
+            n = lib().orc_extract(self._h, _p(img), w, h, img.strides[0], _p(kps), _p(desc), cap)
+            if n <= -1000000:
+                raise ValueError("image too small for the reference cell grid")
+            if n < 0:
+                cap = -n
+                continue
+            return kps[:n].copy(), desc[:n].copy()
+
+    def level_dims(self, l):
+        w, h = C.c_int32(), C.c_int32()
+        lib().orc_level_dims(self._h, l, C.byref(w), C.byref(h))
+        return w.value, h.value
+
+    def level(self, l):
+        """Bordered pyramid buffer of level l: (h+38, w+38)."""
+        w, h = self.level_dims(l)
+        out = np.zeros((h + 38, w + 38), np.uint8)
+        lib().orc_get_level(self._h, l, _p(out))
+        return out
+
+    def blurred(self, l):
+        w, h = self.level_dims(l)
+        out = np.zeros((h, w), np.uint8)
+        if lib().orc_get_blurred(self._h, l, _p(out)) != 0:
+            return None
+        return out
+
+    def raw_corners(self, l):
+        n = lib().orc_raw_corner_count(self._h, l)
+        out = np.zeros(n, KP_DTYPE)
+        lib().orc_get_raw_corners(self._h, l, _p(out), n)
+        return out
+
+    def level_kps(self, l):
+        n = lib().orc_level_kp_count(self._h, l)
+        out = np.zeros(n, KP_DTYPE)
+        lib().orc_get_level_kps(self._h, l, _p(out), n)
+        return out
+
+    def stats(self):
+        s = np.zeros((self.nlevels, 4), np.int32)
+        lib().orc_get_stats(self._h, _p(s))
+        return s
+
+    def near_half_taps(self):
+        return lib().orc_count_near_half_taps(self._h, 1e-4)
+
+
+# ---- primitives -------------------------------------------------------------------------------------
+def resize_linear(src, dw, dh):
+    src = _u8(src)
+    dst = np.zeros((dh, dw), np.uint8)
+    lib().orc_resize_linear_u8(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(dst), dw, dh, dw)
+    return dst
+
+
+def border_reflect101(src, b=19):
+    src = _u8(src)
+    h, w = src.shape
+    dst = np.zeros((h + 2 * b, w + 2 * b), np.uint8)
+    lib().orc_border_reflect101(_p(src), w, h, src.strides[0], _p(dst), b, w + 2 * b)
+    return dst
+
+
+def fast(img, threshold, nms=True):
+    img = _u8(img)
+    h, w = img.shape
+    cap = max(16, w * h)
+    out = np.zeros(cap, KP_DTYPE)
+    n = lib().orc_fast9_16(_p(img), w, h, img.strides[0], threshold, int(nms), _p(out), cap)
+    return out[:n].copy()
+
+
+def gaussian_blur(src):
+    src = _u8(src)
+    h, w = src.shape
+    dst = np.zeros((h, w), np.uint8)
+    lib().orc_gaussian7x7_s2(_p(src), w, h, src.strides[0], _p(dst), w)
+    return dst
+
+
+def fast_atan2(y, x):
+    return lib().orc_fast_atan2(float(y), float(x))
+
+
+def ic_angle(img, x, y):
+    img = _u8(img)
+    ptr = img.ctypes.data + y * img.strides[0] + x
+    return lib().orc_ic_angle(C.c_void_p(ptr), img.strides[0])
+
+
+def brief_descriptor(img, x, y, angle_deg):
+    img = _u8(img)
+    ptr = img.ctypes.data + y * img.strides[0] + x
+    d = np.zeros(32, np.uint8)
+    lib().orc_brief_descriptor(C.c_void_p(ptr), img.strides[0], float(angle_deg), _p(d))
+    return d
+
+
+# ---- matcher -----------------------------------------------------------------------------------------
+def descriptor_distance(a, b):
+    return lib().orc_descriptor_distance(_p(_u8(a)), _p(_u8(b)))
+
+
+def hamming_top2(q, db):
+    q, db = _u8(q), _u8(db)
+    out = np.zeros(len(q), TOP2_DTYPE)
+    lib().orc_hamming_top2(_p(q), len(q), _p(db), len(db), _p(out))
+    return out
+
+
+def hamming_top2_csr(q, db, off, idx):
+    q, db = _u8(q), _u8(db)
+    off = np.ascontiguousarray(off, np.int32); idx = np.ascontiguousarray(idx, np.int32)
+    out = np.zeros(len(q), TOP2_DTYPE)
+    lib().orc_hamming_top2_csr(_p(q), len(q), _p(db), _p(off), _p(idx), _p(out))
+    return out
+
+
+class Grid:
+    """Frame::mGrid (reference Frame.cc:239-256) + GetFeaturesInArea (Frame.cc:354-412)."""
+
+    def __init__(self, kps_un, min_x, min_y, max_x, max_y):
+        self.kps = np.ascontiguousarray(kps_un, KP_DTYPE)
+        self._h = lib().orc_grid_create(_p(self.kps), len(self.kps), min_x, min_y, max_x, max_y)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_grid_destroy(self._h)
+            self._h = None
+
+    def query(self, x, y, r, min_level=-1, max_level=-1):
+        out = np.zeros(max(1, len(self.kps)), np.int32)
+        n = lib().orc_grid_query(self._h, x, y, r, min_level, max_level, _p(out), len(out))
+        return out[:n].copy()
+
+
+def search_by_projection(mode, grid, desc, u_right, taken, q_u, q_v, q_radius, q_min_level, q_max_level, q_desc,
+                         q_ur=None, q_er_max=None, q_angle=None, q_valid=None, q_obs=None, th_dist=100,
+                         nn_ratio=0.9, check_orientation=True):
+    """Returns (nmatches, match_of_query, target_query); `taken` (uint8[n]) is updated in place."""
+    n, nq = len(grid.kps), len(q_u)
+    f = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
+    i = lambda a: None if a is None else np.ascontiguousarray(a, np.int32)
+    b = lambda a: None if a is None else np.ascontiguousarray(a, np.uint8)
+    desc, q_desc = _u8(desc), _u8(q_desc)
+    u_right, q_u, q_v, q_radius, q_ur, q_er_max, q_angle = map(f, (u_right, q_u, q_v, q_radius, q_ur, q_er_max, q_angle))
+    q_min_level, q_max_level = i(q_min_level), i(q_max_level)
+    q_valid, q_obs = b(q_valid), b(q_obs)
+    if q_angle is None:
+        q_angle = np.zeros(nq, np.float32)
+    if u_right is not None and (q_ur is None or q_er_max is None):
+        raise ValueError("q_ur and q_er_max are required with u_right")
+    assert taken.dtype == np.uint8 and taken.flags.c_contiguous
+    prm = SearchParams(mode, th_dist, nn_ratio, int(check_orientation))
+    moq = np.zeros(nq, np.int32)
+    tq = np.zeros(n, np.int32)
+    nm = lib().orc_search_by_projection_ex(C.byref(prm), grid._h, _p(grid.kps), _p(desc), _p(u_right), n, _p(taken),
+                                           nq, _p(q_u), _p(q_v), _p(q_radius), _p(q_min_level), _p(q_max_level),
+                                           _p(q_desc), _p(q_ur), _p(q_er_max), _p(q_angle), _p(q_valid), _p(q_obs),
+                                           _p(moq), _p(tq))
+    return nm, moq, tq
+
+
+def match_bruteforce(desc1, angle1, desc2, angle2, th_dist=50, nn_ratio=0.6, check_orientation=True):
+    desc1, desc2 = _u8(desc1), _u8(desc2)
+    angle1 = np.ascontiguousarray(angle1, np.float32); angle2 = np.ascontiguousarray(angle2, np.float32)
+    m = np.zeros(len(desc1), np.int32)
+    nm = lib().orc_match_bruteforce(_p(desc1), _p(angle1), len(desc1), _p(desc2), _p(angle2), len(desc2), th_dist,
+                                    nn_ratio, int(check_orientation), _p(m))
+    return nm, m
+
+
+def stereo_match(ex_left, ex_right, kps_l, desc_l, kps_r, desc_r, bf, b):
+    kps_l = np.ascontiguousarray(kps_l, KP_DTYPE); kps_r = np.ascontiguousarray(kps_r, KP_DTYPE)
+    desc_l, desc_r = _u8(desc_l), _u8(desc_r)
+    n = len(kps_l)
+    ur = np.zeros(n, np.float32); depth = np.zeros(n, np.float32); sad = np.zeros(n, np.int32)
+    prm = StereoParams(bf, b)
+    kept = lib().orc_stereo_match(ex_left._h, ex_right._h, _p(kps_l), _p(desc_l), n, _p(kps_r), _p(desc_r), len(kps_r),
+                                  C.byref(prm), _p(ur), _p(depth), _p(sad))
+    return kept, ur, depth, sad

@@ -1,0 +1,403 @@
+/*
+ * orb_oracle_match.cpp — CPU ORACLE (test infrastructure, never shipped / never on the product path).
+ *
+ * Restates the matcher and stereo parts of the hot path:
+ *     /root/reference/orb_slam2/src/ORBmatcher.cc   (cited as OM:<line>)
+ *     /root/reference/orb_slam2/src/Frame.cc        (cited as FR:<line>)
+ * The reference routines walk Frame / MapPoint objects; the oracle takes the same data as flat arrays
+ * (what each loop actually reads), keeps the loop order, the comparison operators (< vs <=), the
+ * int/float promotion of every test and the sequential "already matched" dependency.
+ */
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <utility>
+#include <vector>
+
+#include "orb_oracle.h"
+
+extern "C" {
+const uint8_t* orc__level_ptr(void* p, int l, int* w, int* h, int* stride);
+int orc__nlevels(void* p);
+float orc__scale(void* p, int l);
+float orc__inv_scale(void* p, int l);
+}
+
+namespace {
+
+const int TH_HIGH = 100;     // OM:37
+const int TH_LOW = 50;       // OM:38
+const int HISTO_LENGTH = 30; // OM:39
+const int GRID_COLS = 64;    // Frame.h:38
+const int GRID_ROWS = 48;    // Frame.h:37
+
+// OM:1649-1665 — 256-bit Hamming distance, SWAR population count on 8 x 32-bit words
+inline int descriptor_distance(const uint8_t* a, const uint8_t* b) {
+    uint32_t wa[8], wb[8];
+    memcpy(wa, a, 32);
+    memcpy(wb, b, 32);
+    int dist = 0;
+    for (int i = 0; i < 8; ++i) {
+        uint32_t v = wa[i] ^ wb[i];
+        v -= (v >> 1) & 0x55555555u;                          // 2-bit sums
+        v = (v & 0x33333333u) + ((v >> 2) & 0x33333333u);     // 4-bit sums
+        v = (v + (v >> 4)) & 0x0F0F0F0Fu;                     // 8-bit sums
+        dist += (int)((v * 0x01010101u) >> 24);               // add the four bytes
+    }
+    return dist;
+}
+
+struct Grid {
+    float min_x, min_y, max_x, max_y, inv_w, inv_h;
+    const orc_kp* kps; int n;
+    std::vector<int32_t> cell[GRID_COLS][GRID_ROWS];
+};
+
+// OM:1603-1644
+void three_maxima(const std::vector<int>* histo, int L, int& ind1, int& ind2, int& ind3) {
+    int max1 = 0, max2 = 0, max3 = 0;
+    for (int i = 0; i < L; ++i) {
+        const int s = (int)histo[i].size();
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+    else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+}
+
+inline int rot_bin(float a_query, float a_target) {  // OM:1436-1441
+    const float factor = 1.0f / HISTO_LENGTH;
+    float rot = a_query - a_target;
+    if (rot < 0.0) rot += 360.0f;
+    int bin = (int)roundf(rot * factor);
+    if (bin == HISTO_LENGTH) bin = 0;
+    return bin;
+}
+
+}  // namespace
+
+extern "C" {
+
+int orc_descriptor_distance(const uint8_t* a, const uint8_t* b) { return descriptor_distance(a, b); }
+
+void orc_hamming_top2(const uint8_t* q, int nq, const uint8_t* db, int ndb, orc_top2* out) {
+    for (int i = 0; i < nq; ++i) {
+        int best = 256, best_idx = -1, second = 256, second_idx = -1;
+        const uint8_t* dq = q + (size_t)i * 32;
+        for (int j = 0; j < ndb; ++j) {
+            const int d = descriptor_distance(dq, db + (size_t)j * 32);
+            if (d < best) { second = best; second_idx = best_idx; best = d; best_idx = j; }
+            else if (d < second) { second = d; second_idx = j; }
+        }
+        out[i] = {best, best_idx, second, second_idx};
+    }
+}
+
+void orc_hamming_top2_csr(const uint8_t* q, int nq, const uint8_t* db, const int32_t* off, const int32_t* idx,
+                          orc_top2* out) {
+    for (int i = 0; i < nq; ++i) {
+        int best = 256, best_idx = -1, second = 256, second_idx = -1;
+        const uint8_t* dq = q + (size_t)i * 32;
+        for (int c = off[i]; c < off[i + 1]; ++c) {
+            const int j = idx[c];
+            const int d = descriptor_distance(dq, db + (size_t)j * 32);
+            if (d < best) { second = best; second_idx = best_idx; best = d; best_idx = j; }
+            else if (d < second) { second = d; second_idx = j; }
+        }
+        out[i] = {best, best_idx, second, second_idx};
+    }
+}
+
+// FR:239-256, 415-425
+void* orc_grid_create(const orc_kp* kps, int n, float min_x, float min_y, float max_x, float max_y) {
+    Grid* g = new Grid;
+    g->min_x = min_x; g->min_y = min_y; g->max_x = max_x; g->max_y = max_y;
+    g->inv_w = (float)GRID_COLS / (max_x - min_x);  // FR:162
+    g->inv_h = (float)GRID_ROWS / (max_y - min_y);  // FR:163
+    g->kps = kps; g->n = n;
+    for (int i = 0; i < n; ++i) {
+        int px = (int)roundf((kps[i].x - min_x) * g->inv_w);
+        int py = (int)roundf((kps[i].y - min_y) * g->inv_h);
+        if (px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS) continue;
+        g->cell[px][py].push_back(i);
+    }
+    return g;
+}
+void orc_grid_destroy(void* g) { delete (Grid*)g; }
+
+// FR:354-412
+static void grid_query(const Grid* g, float x, float y, float r, int minLevel, int maxLevel, std::vector<int32_t>& out) {
+    out.clear();
+    const int nMinCellX = std::max(0, (int)floorf((x - g->min_x - r) * g->inv_w));
+    if (nMinCellX >= GRID_COLS) return;
+    const int nMaxCellX = std::min(GRID_COLS - 1, (int)ceilf((x - g->min_x + r) * g->inv_w));
+    if (nMaxCellX < 0) return;
+    const int nMinCellY = std::max(0, (int)floorf((y - g->min_y - r) * g->inv_h));
+    if (nMinCellY >= GRID_ROWS) return;
+    const int nMaxCellY = std::min(GRID_ROWS - 1, (int)ceilf((y - g->min_y + r) * g->inv_h));
+    if (nMaxCellY < 0) return;
+    const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+    for (int ix = nMinCellX; ix <= nMaxCellX; ++ix)
+        for (int iy = nMinCellY; iy <= nMaxCellY; ++iy)
+            for (int32_t id : g->cell[ix][iy]) {
+                const orc_kp& kp = g->kps[id];
+                if (bCheckLevels) {
+                    if (kp.octave < minLevel) continue;
+                    if (maxLevel >= 0 && kp.octave > maxLevel) continue;
+                }
+                const float dx = kp.x - x, dy = kp.y - y;
+                if (fabsf(dx) < r && fabsf(dy) < r) out.push_back(id);
+            }
+}
+
+int orc_grid_query(void* g, float x, float y, float r, int minLevel, int maxLevel, int32_t* out, int cap) {
+    std::vector<int32_t> v;
+    grid_query((Grid*)g, x, y, r, minLevel, maxLevel, v);
+    int n = std::min((int)v.size(), cap);
+    memcpy(out, v.data(), (size_t)n * 4);
+    return (int)v.size();
+}
+
+/* OM:1330-1472 (TRACK_LAST) and OM:45-129 (LOCAL_POINTS); q_obs[i] = query map point has Observations()>0
+ * (only then does its assignment block later queries, OM:1405-1407 / OM:87-89).
+ * target_query[n] (out): final owner (query index) of each target keypoint, -1 = none. */
+int orc_search_by_projection_ex(const orc_search_params* prm, void* grid, const orc_kp* kps_un,
+                                const uint8_t* desc, const float* u_right, int n, uint8_t* taken, int nq,
+                                const float* q_u, const float* q_v, const float* q_radius,
+                                const int32_t* q_min_level, const int32_t* q_max_level, const uint8_t* q_desc,
+                                const float* q_ur, const float* q_er_max, const float* q_angle,
+                                const uint8_t* q_valid, const uint8_t* q_obs, int32_t* match_of_query,
+                                int32_t* target_query) {
+    const Grid* g = (const Grid*)grid;
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    std::vector<int32_t> owner(n, -1);
+    std::vector<int32_t> cand;
+    for (int i = 0; i < nq; ++i) {
+        match_of_query[i] = -1;
+        if (q_valid && !q_valid[i]) continue;
+        grid_query(g, q_u[i], q_v[i], q_radius[i], q_min_level[i], q_max_level[i], cand);
+        if (cand.empty()) continue;
+        const uint8_t* dq = q_desc + (size_t)i * 32;
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        for (int32_t idx : cand) {
+            if (taken[idx]) continue;
+            if (u_right && u_right[idx] > 0) {
+                const float er = fabsf(q_ur[i] - u_right[idx]);
+                if (er > q_er_max[i]) continue;
+            }
+            const int dist = descriptor_distance(dq, desc + (size_t)idx * 32);
+            if (prm->mode == ORC_MODE_LOCAL_POINTS) {
+                if (dist < bestDist) {
+                    bestDist2 = bestDist; bestDist = dist;
+                    bestLevel2 = bestLevel; bestLevel = kps_un[idx].octave;
+                    bestIdx = idx;
+                } else if (dist < bestDist2) {
+                    bestLevel2 = kps_un[idx].octave;
+                    bestDist2 = dist;
+                }
+            } else {
+                if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+            }
+        }
+        if (bestDist <= prm->th_dist) {
+            if (prm->mode == ORC_MODE_LOCAL_POINTS) {
+                if (bestLevel == bestLevel2 && (float)bestDist > prm->nn_ratio * (float)bestDist2) continue;
+            }
+            match_of_query[i] = bestIdx;
+            owner[bestIdx] = i;
+            if (!q_obs || q_obs[i]) taken[bestIdx] = 1;
+            nmatches++;
+            if (prm->mode == ORC_MODE_TRACK_LAST && prm->check_orientation)
+                rotHist[rot_bin(q_angle[i], kps_un[bestIdx].angle)].push_back(bestIdx);
+        }
+    }
+    if (prm->mode == ORC_MODE_TRACK_LAST && prm->check_orientation) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int b = 0; b < HISTO_LENGTH; ++b) {
+            if (b == ind1 || b == ind2 || b == ind3) continue;
+            for (int idx : rotHist[b]) { owner[idx] = -1; nmatches--; }
+        }
+    }
+    if (target_query) memcpy(target_query, owner.data(), (size_t)n * 4);
+    // per-query view after the rotation filter
+    for (int i = 0; i < nq; ++i)
+        if (match_of_query[i] >= 0 && owner[match_of_query[i]] != i) {
+            // removed by the rotation filter, or overwritten by a later query (only when q_obs==0)
+            if (owner[match_of_query[i]] == -1) match_of_query[i] = -1;
+        }
+    return nmatches;
+}
+
+int orc_search_by_projection(const orc_search_params* prm, void* grid, const orc_kp* kps_un, const uint8_t* desc,
+                             const float* u_right, int n, uint8_t* taken, int nq, const float* q_u,
+                             const float* q_v, const float* q_radius, const int32_t* q_min_level,
+                             const int32_t* q_max_level, const uint8_t* q_desc, const float* q_ur,
+                             const float* q_er_max, const float* q_angle, const uint8_t* q_valid,
+                             int32_t* match_of_query) {
+    return orc_search_by_projection_ex(prm, grid, kps_un, desc, u_right, n, taken, nq, q_u, q_v, q_radius,
+                                       q_min_level, q_max_level, q_desc, q_ur, q_er_max, q_angle, q_valid,
+                                       nullptr, match_of_query, nullptr);
+}
+
+/* OM:196-252 applied to a single vocabulary node that holds every keypoint of both frames:
+ * queries = frame 1 in index order, candidates = frame 2 in index order, already-matched targets skipped
+ * (OM:210-211), accept best<=th_dist && (float)best < ratio*(float)second (OM:229-231), rotation
+ * histogram on angle1-angle2 (OM:239-248), three-maxima filter (OM:268-285).
+ * match12[i] = index in frame 2 or -1.  Returns nmatches. */
+int orc_match_bruteforce(const uint8_t* desc1, const float* angle1, int n1, const uint8_t* desc2,
+                         const float* angle2, int n2, int th_dist, float nn_ratio, int check_orientation,
+                         int32_t* match12) {
+    std::vector<int32_t> owner(n2, -1);
+    std::vector<int> rotHist[HISTO_LENGTH];
+    int nmatches = 0;
+    for (int i = 0; i < n1; ++i) {
+        match12[i] = -1;
+        int best1 = 256, bestIdx = -1, best2 = 256;
+        const uint8_t* d1 = desc1 + (size_t)i * 32;
+        for (int j = 0; j < n2; ++j) {
+            if (owner[j] >= 0) continue;
+            const int dist = descriptor_distance(d1, desc2 + (size_t)j * 32);
+            if (dist < best1) { best2 = best1; best1 = dist; bestIdx = j; }
+            else if (dist < best2) { best2 = dist; }
+        }
+        if (best1 <= th_dist) {
+            if ((float)best1 < nn_ratio * (float)best2) {
+                owner[bestIdx] = i;
+                match12[i] = bestIdx;
+                if (check_orientation) rotHist[rot_bin(angle1[i], angle2[bestIdx])].push_back(bestIdx);
+                nmatches++;
+            }
+        }
+    }
+    if (check_orientation) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int b = 0; b < HISTO_LENGTH; ++b) {
+            if (b == ind1 || b == ind2 || b == ind3) continue;
+            for (int idx : rotHist[b]) { match12[owner[idx]] = -1; owner[idx] = -1; nmatches--; }
+        }
+    }
+    return nmatches;
+}
+
+/* FR:502-676 */
+int orc_stereo_match(void* exL, void* exR, const orc_kp* kpsL, const uint8_t* descL, int N, const orc_kp* kpsR,
+                     const uint8_t* descR, int Nr, const orc_stereo_params* prm, float* mvuRight, float* mvDepth,
+                     int32_t* best_sad) {
+    for (int i = 0; i < N; ++i) { mvuRight[i] = -1.0f; mvDepth[i] = -1.0f; if (best_sad) best_sad[i] = -1; }
+    const int thOrbDist = (TH_HIGH + TH_LOW) / 2;
+    int w0, h0, s0;
+    orc__level_ptr(exL, 0, &w0, &h0, &s0);
+    const int nRows = h0;
+    const float mbf = prm->bf, mb = prm->b;
+
+    std::vector<std::vector<int>> vRowIndices(nRows);
+    for (int iR = 0; iR < Nr; ++iR) {
+        const float kpY = kpsR[iR].y;
+        const float r = 2.0f * orc__scale(exL, kpsR[iR].octave);
+        const int maxr = (int)ceilf(kpY + r);
+        const int minr = (int)floorf(kpY - r);
+        for (int yi = minr; yi <= maxr; ++yi)
+            if (yi >= 0 && yi < nRows) vRowIndices[yi].push_back(iR);  // guard: the reference indexes unchecked
+    }
+    const float minZ = mb, minD = 0, maxD = mbf / minZ;
+    std::vector<std::pair<int, int>> vDistIdx;
+    for (int iL = 0; iL < N; ++iL) {
+        const orc_kp& kpL = kpsL[iL];
+        const int levelL = kpL.octave;
+        const float vL = kpL.y, uL = kpL.x;
+        const int row = (int)vL;
+        if (row < 0 || row >= nRows) continue;
+        const std::vector<int>& vCandidates = vRowIndices[row];
+        if (vCandidates.empty()) continue;
+        const float minU = uL - maxD, maxU = uL - minD;
+        if (maxU < 0) continue;
+        int bestDist = TH_HIGH;
+        int bestIdxR = 0;
+        const uint8_t* dL = descL + (size_t)iL * 32;
+        for (int iR : vCandidates) {
+            const orc_kp& kpR = kpsR[iR];
+            if (kpR.octave < levelL - 1 || kpR.octave > levelL + 1) continue;
+            const float uR = kpR.x;
+            if (uR >= minU && uR <= maxU) {
+                const int dist = descriptor_distance(dL, descR + (size_t)iR * 32);
+                if (dist < bestDist) { bestDist = dist; bestIdxR = iR; }
+            }
+        }
+        if (bestDist < thOrbDist) {
+            const float uR0 = kpsR[bestIdxR].x;
+            const float scaleFactor = orc__inv_scale(exL, kpL.octave);
+            const float scaleduL = roundf(kpL.x * scaleFactor);
+            const float scaledvL = roundf(kpL.y * scaleFactor);
+            const float scaleduR0 = roundf(uR0 * scaleFactor);
+            const int w = 5;
+            int lw, lh, ls, rw, rh, rs;
+            const uint8_t* PL = orc__level_ptr(exL, kpL.octave, &lw, &lh, &ls);
+            const uint8_t* PR = orc__level_ptr(exR, kpL.octave, &rw, &rh, &rs);
+            const int y0 = (int)(scaledvL - w), xl0 = (int)(scaleduL - w);
+            float IL[11][11];
+            {
+                const float c = (float)PL[(size_t)(y0 + w) * ls + xl0 + w];
+                for (int yy = 0; yy < 11; ++yy)
+                    for (int xx = 0; xx < 11; ++xx) IL[yy][xx] = (float)PL[(ptrdiff_t)(y0 + yy) * ls + xl0 + xx] - c;
+            }
+            int bestDistS = INT_MAX;
+            int bestincR = 0;
+            const int L = 5;
+            float vDists[2 * 5 + 1];
+            const float iniu = scaleduR0 + L - w;
+            const float endu = scaleduR0 + L + w + 1;
+            if (iniu < 0 || endu >= rw) continue;
+            for (int incR = -L; incR <= +L; ++incR) {
+                const int xr0 = (int)(scaleduR0 + incR - w);
+                const float c = (float)PR[(ptrdiff_t)(y0 + w) * rs + xr0 + w];
+                double acc = 0;  // cv::norm(NORM_L1) accumulates CV_32F in double; all terms are small integers
+                for (int yy = 0; yy < 11; ++yy)
+                    for (int xx = 0; xx < 11; ++xx) {
+                        const float ir = (float)PR[(ptrdiff_t)(y0 + yy) * rs + xr0 + xx] - c;
+                        acc += fabs((double)(IL[yy][xx] - ir));
+                    }
+                float dist = (float)acc;
+                if (dist < bestDistS) { bestDistS = (int)dist; bestincR = incR; }
+                vDists[L + incR] = dist;
+            }
+            if (best_sad) best_sad[iL] = bestDistS;
+            if (bestincR == -L || bestincR == L) continue;
+            const float dist1 = vDists[L + bestincR - 1];
+            const float dist2 = vDists[L + bestincR];
+            const float dist3 = vDists[L + bestincR + 1];
+            const float deltaR = (dist1 - dist3) / (2.0f * (dist1 + dist3 - 2.0f * dist2));
+            if (deltaR < -1 || deltaR > 1) continue;
+            float bestuR = orc__scale(exL, kpL.octave) * ((float)scaleduR0 + (float)bestincR + deltaR);
+            float disparity = (uL - bestuR);
+            if (disparity >= minD && disparity < maxD) {
+                if (disparity <= 0) {
+                    disparity = 0.01;
+                    bestuR = uL - 0.01;
+                }
+                mvDepth[iL] = mbf / disparity;
+                mvuRight[iL] = bestuR;
+                vDistIdx.push_back(std::pair<int, int>(bestDistS, iL));
+            }
+        }
+    }
+    if (vDistIdx.empty()) return 0;  // guard: the reference reads vDistIdx[0] of an empty vector here
+    std::sort(vDistIdx.begin(), vDistIdx.end());
+    const float median = vDistIdx[vDistIdx.size() / 2].first;
+    const float thDist = 1.5f * 1.4f * median;
+    int kept = (int)vDistIdx.size();
+    for (int i = (int)vDistIdx.size() - 1; i >= 0; --i) {
+        if (vDistIdx[i].first < thDist) break;
+        mvuRight[vDistIdx[i].second] = -1;
+        mvDepth[vDistIdx[i].second] = -1;
+        kept--;
+    }
+    return kept;
+}
+
+}  // extern "C"
