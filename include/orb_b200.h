@@ -1,0 +1,179 @@
+/*
+ * orb_b200.h — C ABI of liborb_b200.so: the B200-native (sm_100a) ORB front-end of ORB-SLAM2.
+ *
+ * This is the drop-in boundary for the hot path of wjjcdy/orb_slam_2_ros.  The reference has no FFI
+ * layer; the replaced surface is the C++ class surface of two translation units plus one Frame method:
+ *
+ *   ORBextractor::ORBextractor(...)            orb_slam2/include/ORBextractor.h:51-52   -> orb_create
+ *   ORBextractor::operator()(img,mask,kps,desc) ORBextractor.h:59-61, ORBextractor.cc:1083 -> orb_extract
+ *   ORBextractor getters                        ORBextractor.h:63-83                      -> orb_get_tables
+ *   ORBextractor::mvImagePyramid (public data)  ORBextractor.h:85                         -> orb_pyramid_level
+ *   ORBmatcher::DescriptorDistance + best/2nd   ORBmatcher.cc:1649-1665, 202-227          -> orb_hamming_top2*
+ *   ORBmatcher::SearchByProjection (Frame/Last) ORBmatcher.cc:45-129, 1330-1472           -> orb_search_by_projection
+ *   ORBmatcher::SearchByBoW inner loop          ORBmatcher.cc:196-252                     -> orb_match_bruteforce
+ *   Frame::ComputeStereoMatches                 Frame.cc:502-676                          -> orb_stereo_match
+ *
+ * INTEGRATION.md shows the C++ shims (ORBextractor.cc / ORBmatcher.cc / Frame.cc replacements) that bind
+ * these entry points with the reference's own signatures.
+ *
+ * Conventions: every function returns an int status (ORB_OK == 0, negative = error, never throws, never
+ * aborts); orb_last_error() gives a thread-local message.  Outputs are caller-allocated with explicit
+ * capacities.  Pointers are HOST pointers unless the parameter name starts with d_ (device pointer on the
+ * context's device).  One CUDA stream per context; distinct contexts may be used concurrently from
+ * different threads (the reference runs the left/right extractors on two threads, Frame.cc:79-82); one
+ * context must not be used by two threads at once.  There is no CPU fallback: without a CUDA device
+ * every compute entry point returns ORB_ERR_NO_DEVICE.
+ */
+#ifndef ORB_B200_H
+#define ORB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    ORB_OK = 0,
+    ORB_ERR_INVALID = -1,   /* bad argument (NULL, sizes, unsupported dims)                 */
+    ORB_ERR_CUDA = -2,      /* CUDA runtime error, see orb_last_error()                      */
+    ORB_ERR_CAPACITY = -3,  /* caller buffer / context capacity too small                    */
+    ORB_ERR_NO_DEVICE = -4, /* no CUDA device visible                                        */
+    ORB_ERR_TOO_SMALL = -5  /* image too small for the reference's 30-px cell grid           */
+};
+
+/* bit-compatible with cv::KeyPoint (28 bytes): pt.x, pt.y, size, angle, response, octave, class_id */
+typedef struct {
+    float x, y;
+    float size;
+    float angle;
+    float response;
+    int32_t octave;
+    int32_t class_id;
+} orb_kp;
+
+/* best / second-best of one query (ORBmatcher.cc:217-226 update rule). idx == -1, dist == 256 when absent. */
+typedef struct {
+    int32_t best_dist;
+    int32_t second_dist;
+    int64_t best_idx;
+    int64_t second_idx;
+} orb_top2;
+
+typedef struct orb_ctx orb_ctx; /* one ORBextractor instance (tables + device arena + stream) */
+typedef struct orb_db orb_db;   /* a device-resident shard of a descriptor database            */
+
+/* ---- library ---------------------------------------------------------------------------------- */
+const char* orb_last_error(void);
+int orb_device_count(void);
+int orb_version(void);
+
+/* ---- extractor (ORBextractor.cc) ---------------------------------------------------------------- */
+/* max_batch: frames processed per launch group (arena is sized for it; larger batches are chunked). */
+int orb_create(orb_ctx** ctx, int nfeatures, float scale_factor, int nlevels, int ini_th_fast, int min_th_fast,
+               int device, int max_batch);
+void orb_destroy(orb_ctx* ctx);
+/* arrays of nlevels entries (any may be NULL): mvScaleFactor, mvInvScaleFactor, mvLevelSigma2,
+ * mvInvLevelSigma2, mnFeaturesPerLevel */
+int orb_get_tables(orb_ctx* ctx, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
+                   int32_t* features_per_level);
+int orb_max_keypoints(orb_ctx* ctx); /* upper bound of keypoints per frame (sum of N_l + 3 per level ...) */
+
+/* operator(): one host image (any row stride) -> host keypoints + descriptors. *n_out = count. */
+int orb_extract(orb_ctx* ctx, const uint8_t* img, int w, int h, size_t stride, orb_kp* kps, uint8_t* desc32,
+                int cap, int* n_out);
+/* nframes host images of identical size; outputs are [nframes][cap] / [nframes][cap][32]. */
+int orb_extract_batch(orb_ctx* ctx, const uint8_t* imgs, int nframes, int w, int h, size_t row_stride,
+                      size_t frame_stride, orb_kp* kps, uint8_t* desc32, int cap, int32_t* n_out);
+/* Same with DEVICE pointers, asynchronous on the context stream (no host synchronisation): the form a
+ * GPU-resident caller (and bench.py's device-resident leg) uses.  nframes <= max_batch. */
+int orb_extract_batch_device(orb_ctx* ctx, const uint8_t* d_imgs, int nframes, int w, int h, size_t row_stride,
+                             size_t frame_stride, orb_kp* d_kps, uint8_t* d_desc32, int cap, int32_t* d_n_out);
+/* stream plumbing: adopt an external cudaStream_t (e.g. torch's current stream) / wait for the context */
+int orb_set_stream(orb_ctx* ctx, void* cuda_stream);
+int orb_sync(orb_ctx* ctx);
+/* kernels launched by this context so far (the bench's gpu_launches counter) */
+int64_t orb_launch_count(orb_ctx* ctx);
+
+/* mvImagePyramid[level] of frame `frame` of the last extract call: interior size via orb_level_dims;
+ * orb_pyramid_level copies the BORDERED buffer ((w+38) x (h+38), reflect-101 border, like the Mat the
+ * reference's ROI lives in) to host memory with row stride dst_stride. */
+int orb_level_dims(orb_ctx* ctx, int level, int* w, int* h);
+int orb_pyramid_level(orb_ctx* ctx, int frame, int level, uint8_t* dst, size_t dst_stride);
+
+/* stage taps of the last call, for parity tests (host outputs) */
+int orb_debug_blurred(orb_ctx* ctx, int frame, int level, uint8_t* dst, size_t dst_stride); /* w x h */
+/* corners before the quadtree, level coordinates relative to the 16-px border (vToDistributeKeys,
+ * ORBextractor.cc:856-859), sorted in the reference's (cell row, cell col, y, x) order. returns count via *n */
+int orb_debug_raw_corners(orb_ctx* ctx, int frame, int level, float* xyr /* [cap][3] */, int cap, int* n);
+/* per-level count of quadtree cuts that fell inside a group of equal-size nodes (where the reference's own
+ * result depends on heap addresses, ORBextractor.cc:705-708,752-755; see DESIGN.md pin (ii)) */
+int orb_debug_tie_counts(orb_ctx* ctx, int frame, int32_t* ties /* [nlevels] */);
+
+/* ---- Hamming search (ORBmatcher.cc) --------------------------------------------------------------- */
+/* brute force, host buffers: every query against db[0..ndb) */
+int orb_hamming_top2(int device, const uint8_t* q, int nq, const uint8_t* db, int64_t ndb, orb_top2* out);
+
+/* device-resident database shard (config 5: map-wide relocalisation-scale search).
+ * index_base = global index of the shard's first row; results carry global indices. */
+int orb_db_create(orb_db** db, int device, int64_t capacity_rows, int64_t index_base);
+void orb_db_destroy(orb_db* db);
+int orb_db_add(orb_db* db, const uint8_t* desc32, int64_t nrows);          /* host rows, appended */
+int orb_db_add_device(orb_db* db, const uint8_t* d_desc32, int64_t nrows); /* device rows, appended */
+int64_t orb_db_size(orb_db* db);
+int orb_db_set_stream(orb_db* db, void* cuda_stream);
+int orb_db_query_top2(orb_db* db, const uint8_t* q, int nq, orb_top2* out);              /* host q / out */
+int orb_db_query_top2_device(orb_db* db, const uint8_t* d_q, int nq, orb_top2* d_out);   /* async */
+int64_t orb_db_launch_count(orb_db* db);
+/* exact merge of per-shard results (after an all-gather): parts is [nparts][nq]; best = min distance,
+ * lowest global index on ties; second = second smallest of the union. */
+int orb_top2_merge(const orb_top2* parts, int nparts, int nq, orb_top2* out);
+
+/* ---- windowed search with the sequential "already matched" rule ------------------------------------ */
+enum {
+    ORB_MODE_TRACK_LAST = 0,  /* ORBmatcher.cc:1330-1472: best only, <= th_dist, rotation histogram      */
+    ORB_MODE_LOCAL_POINTS = 1 /* ORBmatcher.cc:45-129: best/second, same-octave ratio test, no histogram */
+};
+typedef struct {
+    int32_t mode;
+    int32_t th_dist;           /* TH_HIGH (100) or ORBdist                                  */
+    float nn_ratio;            /* mfNNratio                                                 */
+    int32_t check_orientation; /* mbCheckOrientation                                        */
+    float min_x, min_y, max_x, max_y; /* Frame::mnMinX.. (image bounds, Frame.cc:472-500)   */
+} orb_search_params;
+
+/*
+ * Target frame: kps_un[n] (Frame::mvKeysUn), desc[n][32], u_right[n] (Frame::mvuRight; NULL = mono).
+ * taken[n] in/out: target already holds a map point with Observations()>0.
+ * Queries in the reference's loop order: projected position (q_u,q_v), window radius, octave band for
+ * GetFeaturesInArea (Frame.cc:354-412), descriptor, predicted right coordinate + tolerance (NULL when
+ * u_right is NULL), angle for the rotation histogram, q_valid (NULL = all), q_obs (query's map point has
+ * Observations()>0, NULL = all).  Outputs: match_of_query[nq] (target index or -1), target_query[n]
+ * (final owner of each target = final Frame::mvpMapPoints, may be NULL), *nmatches.
+ */
+int orb_search_by_projection(int device, const orb_search_params* prm, const orb_kp* kps_un, const uint8_t* desc,
+                             const float* u_right, int n, uint8_t* taken, int nq, const float* q_u,
+                             const float* q_v, const float* q_radius, const int32_t* q_min_level,
+                             const int32_t* q_max_level, const uint8_t* q_desc, const float* q_ur,
+                             const float* q_er_max, const float* q_angle, const uint8_t* q_valid,
+                             const uint8_t* q_obs, int32_t* match_of_query, int32_t* target_query, int* nmatches);
+
+/* SearchByBoW inner loop (ORBmatcher.cc:196-252) over one node holding all keypoints of both frames:
+ * queries = frame 1 in order, skip already-matched targets, best <= th_dist and best < ratio*second,
+ * rotation histogram + three-maxima filter.  match12[n1] = index in frame 2 or -1. */
+int orb_match_bruteforce(int device, const uint8_t* desc1, const float* angle1, int n1, const uint8_t* desc2,
+                         const float* angle2, int n2, int th_dist, float nn_ratio, int check_orientation,
+                         int32_t* match12, int* nmatches);
+
+/* ---- stereo (Frame::ComputeStereoMatches, Frame.cc:502-676) ------------------------------------------ */
+/* ctx_left / ctx_right hold the pyramids of the last single-frame extract of the left / right image.
+ * Outputs u_right[nl] (mvuRight), depth[nl] (mvDepth), -1 = no match. */
+int orb_stereo_match(orb_ctx* ctx_left, orb_ctx* ctx_right, const orb_kp* kps_l, const uint8_t* desc_l, int nl,
+                     const orb_kp* kps_r, const uint8_t* desc_r, int nr, float bf, float b, float* u_right,
+                     float* depth, int* nmatches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORB_B200_H */

@@ -76,6 +76,9 @@ int orc_cv_round_f(float v);
 float orc_ic_angle(const uint8_t* center, int stride);
 void orc_brief_descriptor(const uint8_t* center, int stride, float angle_deg, uint8_t* desc32);
 
+/* pin (iii): steering coefficients for the n consecutive fp32 bit patterns starting at first_bits */
+void orc_sincos_range(uint32_t first_bits, long long n, float* a, float* b);
+
 /* ---------------- matcher (ORBmatcher.cc) ---------------- */
 int orc_descriptor_distance(const uint8_t* a, const uint8_t* b);
 /* brute-force best / second-best of every query against db[0..ndb) in index order

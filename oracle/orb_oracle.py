@@ -74,6 +74,7 @@ def lib():
         L.orc_ic_angle.restype = f32
         L.orc_ic_angle.argtypes = [vp, i32]
         L.orc_brief_descriptor.argtypes = [vp, i32, f32, vp]
+        L.orc_sincos_range.argtypes = [C.c_uint32, C.c_longlong, vp, vp]
         L.orc_descriptor_distance.argtypes = [vp, vp]
         L.orc_hamming_top2.argtypes = [vp, i32, vp, i32, vp]
         L.orc_hamming_top2_csr.argtypes = [vp, i32, vp, vp, vp, vp]
@@ -219,6 +220,12 @@ def brief_descriptor(img, x, y, angle_deg):
     d = np.zeros(32, np.uint8)
     lib().orc_brief_descriptor(C.c_void_p(ptr), img.strides[0], float(angle_deg), _p(d))
     return d
+
+
+def sincos_range(first_bits, n):
+    a = np.zeros(n, np.float32); b = np.zeros(n, np.float32)
+    lib().orc_sincos_range(first_bits, n, _p(a), _p(b))
+    return a, b
 
 
 # ---- matcher -----------------------------------------------------------------------------------------

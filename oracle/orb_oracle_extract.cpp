@@ -677,6 +677,17 @@ int orc_cv_round_f(float v) { return cv_round(v); }
 float orc_ic_angle(const uint8_t* c, int stride) { return ic_angle(c, stride); }
 void orc_brief_descriptor(const uint8_t* c, int stride, float angle, uint8_t* d) { brief_descriptor(c, stride, angle, d, nullptr); }
 
+// pin (iii) checker: a=(float)cos((double)x), b=(float)sin((double)x) for n consecutive fp32 bit patterns
+void orc_sincos_range(uint32_t first_bits, long long n, float* a, float* b) {
+    for (long long i = 0; i < n; ++i) {
+        uint32_t bits = first_bits + (uint32_t)i;
+        float x;
+        memcpy(&x, &bits, 4);
+        a[i] = (float)cos((double)x);
+        b[i] = (float)sin((double)x);
+    }
+}
+
 // accessors used by the stereo oracle (orb_oracle_match.cpp)
 const uint8_t* orc__level_ptr(void* p, int l, int* w, int* h, int* stride) {
     Extractor* ex = (Extractor*)p;

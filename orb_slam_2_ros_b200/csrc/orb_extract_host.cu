@@ -1,0 +1,450 @@
+// orb_extract_host.cu — host side of the extractor C ABI (include/orb_b200.h): context, tables, geometry,
+// device arena and the orb_extract* entry points.  Mirrors the reference constructor
+// (orb_slam2/src/ORBextractor.cc:416-479) and ComputePyramid's size rules (:1152-1165).
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "orb_internal.cuh"
+
+static thread_local char g_err[512] = "";
+
+void orb_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* orb_last_error(void) { return g_err; }
+extern "C" int orb_version(void) { return 100; }
+extern "C" int orb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+namespace {
+
+inline int cv_round_f(float v) { return (int)lrintf(v); }  // cvRound: half-to-even
+inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+void free_geometry_buffers(orb_ctx* c) {
+    cudaFree(c->d_in); cudaFree(c->d_pyr); cudaFree(c->d_blur); cudaFree(c->d_corners); cudaFree(c->d_node_of_key);
+    cudaFree(c->d_corner_count); cudaFree(c->d_kept); cudaFree(c->d_kept_count); cudaFree(c->d_taps);
+    cudaFree(c->d_blur_tile_base); cudaFree(c->d_kps_out); cudaFree(c->d_desc_out); cudaFree(c->d_n_out);
+    cudaFreeHost(c->h_kps); cudaFreeHost(c->h_desc); cudaFreeHost(c->h_n); cudaFreeHost(c->h_in);
+    c->d_in = c->d_pyr = c->d_blur = nullptr; c->d_corners = nullptr; c->d_node_of_key = nullptr;
+    c->d_corner_count = c->d_kept_count = nullptr; c->d_kept = nullptr; c->d_taps = nullptr;
+    c->d_blur_tile_base = nullptr; c->d_kps_out = nullptr; c->d_desc_out = nullptr; c->d_n_out = nullptr;
+    c->h_kps = nullptr; c->h_desc = nullptr; c->h_n = nullptr; c->h_in = nullptr;
+    c->in_bytes = c->h_in_bytes = 0; c->out_cap = 0;
+    c->have_geom = false;
+}
+
+// resize(INTER_LINEAR) tap tables of one axis (OpenCV resize.cpp, 8u fixed-point path)
+void make_taps(int sn, int dn, bool vertical, ResizeTap* out) {
+    const double scale = 1.0 / ((double)dn / (double)sn);
+    for (int d = 0; d < dn; ++d) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int s = (int)floorf(f);
+        f -= (float)s;
+        int s0, s1;
+        if (!vertical) {
+            if (s < 0) { s = 0; f = 0.f; }
+            if (s >= sn - 1) { s = sn - 1; f = 0.f; }
+            s0 = s; s1 = std::min(s + 1, sn - 1);
+        } else {  // rows are clipped, the weights are kept
+            s0 = std::min(std::max(s, 0), sn - 1);
+            s1 = std::min(std::max(s + 1, 0), sn - 1);
+        }
+        out[d].s0 = (unsigned short)s0; out[d].s1 = (unsigned short)s1;
+        out[d].c0 = (short)cv_round_f((1.f - f) * 2048.f);
+        out[d].c1 = (short)cv_round_f(f * 2048.f);
+    }
+}
+
+// (re)build everything that depends on the image size
+int build_geometry(orb_ctx* c, int w, int h) {
+    if (c->have_geom && c->g.w == w && c->g.h == h) return ORB_OK;
+    ORB_CUDA(cudaStreamSynchronize(c->stream));
+    free_geometry_buffers(c);
+    Geometry& g = c->g;
+    memset(&g, 0, sizeof(g));
+    g.nlevels = c->nlevels; g.w = w; g.h = h; g.ini_th = c->ini_th; g.min_th = c->min_th;
+    const int F = c->max_batch;
+    long long pyr_off = 0, blur_off = 0, corner_off = 0;
+    int cells = 0, kp_slots = 0, taps = 0, max_node_cap = 0;
+    for (int l = 0; l < g.nlevels; ++l) {
+        LevelGeom& L = g.lv[l];
+        L.w = cv_round_f((float)w * c->inv_scale[l]);  // ORBextractor.cc:1159
+        L.h = cv_round_f((float)h * c->inv_scale[l]);
+        if (L.w > 4096 + 32 || L.h > 4096 + 32) { orb_set_error("image larger than 4128 px is not supported"); return ORB_ERR_INVALID; }
+        L.pitch = (int)round_up(L.w + 2 * ORB_EDGE, 64);
+        L.rows = L.h + 2 * ORB_EDGE;
+        L.frame_stride = (long long)L.pitch * L.rows;
+        L.base = pyr_off; pyr_off += L.frame_stride * F;
+        L.bpitch = (int)round_up(L.w, 64);
+        L.bframe_stride = (long long)L.bpitch * L.h;
+        L.bbase = blur_off; blur_off += L.bframe_stride * F;
+        // cell grid, ORBextractor.cc:801-817 (float arithmetic as in the reference)
+        L.maxBX = L.w - ORB_EDGE + 3; L.maxBY = L.h - ORB_EDGE + 3;
+        const float width = (float)(L.maxBX - ORB_MINB), height = (float)(L.maxBY - ORB_MINB);
+        L.nCols = (int)(width / 30.f); L.nRows = (int)(height / 30.f);
+        if (L.nCols <= 0 || L.nRows <= 0) {
+            orb_set_error("level %d (%dx%d) is smaller than one 30-px cell: the reference divides by zero here", l, L.w, L.h);
+            return ORB_ERR_TOO_SMALL;
+        }
+        L.wCell = (int)ceilf(width / L.nCols); L.hCell = (int)ceilf(height / L.nRows);
+        L.cell_base = cells; cells += L.nCols * L.nRows;
+        if (L.nCols * L.nRows > 4096) { orb_set_error("more than 4096 cells per level is not supported"); return ORB_ERR_INVALID; }
+        L.quota = c->quota[l];
+        // quadtree roots, ORBextractor.cc:566-568
+        L.nIni = (int)roundf((float)(L.maxBX - ORB_MINB) / (L.maxBY - ORB_MINB));
+        if (L.nIni <= 0) { orb_set_error("level %d is taller than 2x its width: the reference divides by zero here", l); return ORB_ERR_TOO_SMALL; }
+        L.hX = (float)(L.maxBX - ORB_MINB) / L.nIni;
+        // worst case of NMS survivors: one per 2x2 block of every cell's evaluated area
+        long long cc = 0;
+        for (int i = 0; i < L.nRows; ++i) {
+            const int iniY = ORB_MINB + i * L.hCell;
+            if (iniY >= L.maxBY - 3) continue;
+            const int ch = std::min(iniY + L.hCell + 6, L.maxBY) - iniY;
+            for (int j = 0; j < L.nCols; ++j) {
+                const int iniX = ORB_MINB + j * L.wCell;
+                if (iniX >= L.maxBX - 6) continue;
+                const int cw = std::min(iniX + L.wCell + 6, L.maxBX) - iniX;
+                if (cw < 7 || ch < 7) continue;
+                cc += (long long)((cw - 6 + 1) / 2) * ((ch - 6 + 1) / 2);
+            }
+        }
+        L.corner_cap = (int)round_up((size_t)std::max<long long>(cc, 8), 8);
+        L.corner_base = corner_off; corner_off += (long long)L.corner_cap * F;
+        L.node_cap = (int)round_up((size_t)std::max(L.quota + 3, 4 * L.nIni) + L.nIni + 8, 8);
+        max_node_cap = std::max(max_node_cap, L.node_cap);
+        L.kp_base = kp_slots; kp_slots += L.node_cap;
+        L.xtab = taps; taps += L.w;
+        L.ytab = taps; taps += L.h;
+        L.scale = c->scale[l];
+        L.size = (float)(int)(ORB_PATCH * c->scale[l]);  // ORBextractor.cc:874
+    }
+    if (max_node_cap > 65535) { orb_set_error("nfeatures too large"); return ORB_ERR_INVALID; }
+    if ((size_t)max_node_cap * 80 > 200 * 1024) { orb_set_error("nfeatures too large for the quadtree kernel"); return ORB_ERR_INVALID; }
+    g.total_cells = cells; g.total_kp_slots = kp_slots; g.max_node_cap = max_node_cap;
+    g.pyr_frame_total = pyr_off / F;
+    // resize taps
+    std::vector<ResizeTap> h_taps(taps);
+    for (int l = 1; l < g.nlevels; ++l) {
+        make_taps(g.lv[l - 1].w, g.lv[l].w, false, h_taps.data() + g.lv[l].xtab);
+        make_taps(g.lv[l - 1].h, g.lv[l].h, true, h_taps.data() + g.lv[l].ytab);
+    }
+    int tile_base[ORB_MAX_LEVELS];
+    c->blur_tiles = orb_blur_tile_bases(g, tile_base);
+
+    c->pyr_bytes = (size_t)pyr_off; c->blur_bytes = (size_t)blur_off; c->corner_elems = (size_t)corner_off;
+    ORB_CUDA(cudaMalloc(&c->d_pyr, c->pyr_bytes + 256));
+    ORB_CUDA(cudaMalloc(&c->d_blur, c->blur_bytes + 256));
+    ORB_CUDA(cudaMalloc(&c->d_corners, c->corner_elems * sizeof(unsigned long long)));
+    ORB_CUDA(cudaMalloc(&c->d_node_of_key, c->corner_elems * sizeof(unsigned short)));
+    ORB_CUDA(cudaMalloc(&c->d_corner_count, sizeof(int) * 2 * (size_t)F * g.nlevels));
+    ORB_CUDA(cudaMalloc(&c->d_kept, sizeof(unsigned long long) * (size_t)F * kp_slots));
+    ORB_CUDA(cudaMalloc(&c->d_kept_count, sizeof(int) * (size_t)F * g.nlevels));
+    ORB_CUDA(cudaMalloc(&c->d_taps, sizeof(ResizeTap) * (size_t)std::max(taps, 1)));
+    ORB_CUDA(cudaMalloc(&c->d_blur_tile_base, sizeof(int) * ORB_MAX_LEVELS));
+    ORB_CUDA(cudaMemcpyAsync(c->d_taps, h_taps.data(), sizeof(ResizeTap) * taps, cudaMemcpyHostToDevice, c->stream));
+    ORB_CUDA(cudaMemcpyAsync(c->d_blur_tile_base, tile_base, sizeof(int) * g.nlevels, cudaMemcpyHostToDevice, c->stream));
+    ORB_CUDA(cudaMemsetAsync(c->d_pyr, 0, c->pyr_bytes + 256, c->stream));
+    ORB_CUDA(cudaMemsetAsync(c->d_blur, 0, c->blur_bytes + 256, c->stream));
+    ORB_CUDA(cudaMemsetAsync(c->d_kept_count, 0, sizeof(int) * (size_t)F * g.nlevels, c->stream));
+    ORB_CUDA(cudaStreamSynchronize(c->stream));
+    c->have_geom = true;
+    c->last_frames = 0;
+    return ORB_OK;
+}
+
+int ensure_staging(orb_ctx* c, int cap) {
+    const int F = c->max_batch;
+    const size_t in_bytes = (size_t)F * c->g.w * c->g.h;
+    if (c->in_bytes < in_bytes) {
+        cudaFree(c->d_in); cudaFreeHost(c->h_in);
+        c->d_in = nullptr; c->h_in = nullptr;
+        ORB_CUDA(cudaMalloc(&c->d_in, in_bytes));
+        ORB_CUDA(cudaMallocHost(&c->h_in, in_bytes));
+        c->in_bytes = c->h_in_bytes = in_bytes;
+    }
+    if (c->out_cap < cap) {
+        cudaFree(c->d_kps_out); cudaFree(c->d_desc_out); cudaFree(c->d_n_out);
+        cudaFreeHost(c->h_kps); cudaFreeHost(c->h_desc); cudaFreeHost(c->h_n);
+        c->d_kps_out = nullptr; c->d_desc_out = nullptr; c->d_n_out = nullptr;
+        c->h_kps = nullptr; c->h_desc = nullptr; c->h_n = nullptr;
+        ORB_CUDA(cudaMalloc(&c->d_kps_out, sizeof(orb_kp) * (size_t)F * cap));
+        ORB_CUDA(cudaMalloc(&c->d_desc_out, (size_t)32 * F * cap));
+        ORB_CUDA(cudaMalloc(&c->d_n_out, sizeof(int) * F));
+        ORB_CUDA(cudaMallocHost(&c->h_kps, sizeof(orb_kp) * (size_t)F * cap));
+        ORB_CUDA(cudaMallocHost(&c->h_desc, (size_t)32 * F * cap));
+        ORB_CUDA(cudaMallocHost(&c->h_n, sizeof(int) * F));
+        c->out_cap = cap;
+    }
+    return ORB_OK;
+}
+
+int check_device() {
+    if (orb_device_count() <= 0) {
+        orb_set_error("no CUDA device visible: liborb_b200 has no CPU fallback");
+        return ORB_ERR_NO_DEVICE;
+    }
+    return ORB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int orb_create(orb_ctx** out, int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th, int device,
+               int max_batch) {
+    if (!out) return ORB_ERR_INVALID;
+    *out = nullptr;
+    if (nfeatures <= 0 || nlevels <= 0 || nlevels > ORB_MAX_LEVELS || !(scale_factor > 1.0f) || ini_th <= 0 ||
+        min_th <= 0 || ini_th > 254 || min_th > ini_th || max_batch <= 0 || max_batch > 65535) {
+        orb_set_error("orb_create: invalid parameters");
+        return ORB_ERR_INVALID;
+    }
+    orb_ctx* c = new orb_ctx;
+    c->device = device; c->nfeatures = nfeatures; c->nlevels = nlevels; c->ini_th = ini_th; c->min_th = min_th;
+    c->scale_factor = scale_factor;  // stored as double like the reference member (ORBextractor.h:99)
+    c->max_batch = max_batch;
+    // ORBextractor.cc:423-455
+    c->scale[0] = 1.f; c->sigma2[0] = 1.f;
+    for (int i = 1; i < nlevels; ++i) {
+        c->scale[i] = (float)(c->scale[i - 1] * c->scale_factor);
+        c->sigma2[i] = c->scale[i] * c->scale[i];
+    }
+    for (int i = 0; i < nlevels; ++i) { c->inv_scale[i] = 1.f / c->scale[i]; c->inv_sigma2[i] = 1.f / c->sigma2[i]; }
+    const float factor = (float)(1.0f / c->scale_factor);
+    float desired = nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nlevels));
+    int sum = 0;
+    for (int l = 0; l < nlevels - 1; ++l) {
+        c->quota[l] = cv_round_f(desired);
+        sum += c->quota[l];
+        desired *= factor;
+    }
+    c->quota[nlevels - 1] = std::max(nfeatures - sum, 0);
+    // device side is created lazily so that a context can be constructed (and its tables read) without a GPU
+    *out = c;
+    return ORB_OK;
+}
+
+static int ensure_device(orb_ctx* c) {
+    int rc = check_device();
+    if (rc != ORB_OK) return rc;
+    ORB_CUDA(cudaSetDevice(c->device));
+    if (!c->stream) {
+        ORB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    return ORB_OK;
+}
+
+void orb_destroy(orb_ctx* c) {
+    if (!c) return;
+    if (orb_device_count() > 0) {
+        cudaSetDevice(c->device);
+        if (c->stream) cudaStreamSynchronize(c->stream);
+        free_geometry_buffers(c);
+        if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    }
+    delete c;
+}
+
+int orb_get_tables(orb_ctx* c, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2, int32_t* per_level) {
+    if (!c) return ORB_ERR_INVALID;
+    for (int i = 0; i < c->nlevels; ++i) {
+        if (scale) scale[i] = c->scale[i];
+        if (inv_scale) inv_scale[i] = c->inv_scale[i];
+        if (sigma2) sigma2[i] = c->sigma2[i];
+        if (inv_sigma2) inv_sigma2[i] = c->inv_sigma2[i];
+        if (per_level) per_level[i] = c->quota[i];
+    }
+    return ORB_OK;
+}
+
+int orb_max_keypoints(orb_ctx* c) {
+    if (!c) return ORB_ERR_INVALID;
+    // list length after DistributeOctTree <= max(N_l + 2, 4 * nIni); nIni <= 16 for any sane aspect ratio
+    int tot = 0;
+    for (int l = 0; l < c->nlevels; ++l) tot += std::max(c->quota[l] + 3, 64);
+    return tot;
+}
+
+int orb_set_stream(orb_ctx* c, void* s) {
+    if (!c) return ORB_ERR_INVALID;
+    int rc = ensure_device(c);
+    if (rc != ORB_OK) return rc;
+    ORB_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->own_stream) { cudaStreamDestroy(c->stream); c->own_stream = false; }
+    c->stream = (cudaStream_t)s;
+    if (!c->stream) {
+        ORB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    return ORB_OK;
+}
+
+int orb_sync(orb_ctx* c) {
+    if (!c) return ORB_ERR_INVALID;
+    if (!c->stream) return ORB_OK;
+    ORB_CUDA(cudaSetDevice(c->device));
+    ORB_CUDA(cudaStreamSynchronize(c->stream));
+    return ORB_OK;
+}
+
+int64_t orb_launch_count(orb_ctx* c) { return c ? c->launches : 0; }
+
+int orb_extract_batch_device(orb_ctx* c, const uint8_t* d_imgs, int nframes, int w, int h, size_t row_stride,
+                             size_t frame_stride, orb_kp* d_kps, uint8_t* d_desc, int cap, int32_t* d_n_out) {
+    if (!c || !d_imgs || !d_kps || !d_desc || !d_n_out || nframes < 0 || cap <= 0) return ORB_ERR_INVALID;
+    if (nframes == 0 || w <= 0 || h <= 0) return ORB_OK;  // empty image => silent return (ORBextractor.cc:1086)
+    if (nframes > c->max_batch) { orb_set_error("nframes %d > max_batch %d", nframes, c->max_batch); return ORB_ERR_CAPACITY; }
+    if (row_stride < (size_t)w) return ORB_ERR_INVALID;
+    int rc = ensure_device(c);
+    if (rc != ORB_OK) return rc;
+    rc = build_geometry(c, w, h);
+    if (rc != ORB_OK) return rc;
+    c->last_frames = nframes;
+    return orb_launch_extract(c, d_imgs, nframes, row_stride, frame_stride, d_kps, d_desc, cap, d_n_out);
+}
+
+int orb_extract_batch(orb_ctx* c, const uint8_t* imgs, int nframes, int w, int h, size_t row_stride, size_t frame_stride,
+                      orb_kp* kps, uint8_t* desc, int cap, int32_t* n_out) {
+    if (!c || !n_out || nframes < 0 || cap < 0) return ORB_ERR_INVALID;
+    for (int f = 0; f < nframes; ++f) n_out[f] = 0;
+    if (nframes == 0 || !imgs || w <= 0 || h <= 0) return ORB_OK;  // ORBextractor.cc:1086-1087
+    if (!kps || !desc || cap == 0 || row_stride < (size_t)w) return ORB_ERR_INVALID;
+    int rc = ensure_device(c);
+    if (rc != ORB_OK) return rc;
+    rc = build_geometry(c, w, h);
+    if (rc != ORB_OK) return rc;
+    const int dcap = std::min(cap, c->g.total_kp_slots);
+    rc = ensure_staging(c, std::max(dcap, c->out_cap));
+    if (rc != ORB_OK) return rc;
+    const int ocap = c->out_cap;
+    int status = ORB_OK;
+    for (int f0 = 0; f0 < nframes; f0 += c->max_batch) {
+        const int F = std::min(c->max_batch, nframes - f0);
+        // host -> pinned staging (tight rows) -> device
+        for (int f = 0; f < F; ++f) {
+            const uint8_t* src = imgs + (size_t)(f0 + f) * frame_stride;
+            uint8_t* dst = c->h_in + (size_t)f * w * h;
+            if (row_stride == (size_t)w) memcpy(dst, src, (size_t)w * h);
+            else for (int y = 0; y < h; ++y) memcpy(dst + (size_t)y * w, src + (size_t)y * row_stride, w);
+        }
+        ORB_CUDA(cudaMemcpyAsync(c->d_in, c->h_in, (size_t)F * w * h, cudaMemcpyHostToDevice, c->stream));
+        c->last_frames = F;
+        rc = orb_launch_extract(c, c->d_in, F, (size_t)w, (size_t)w * h, c->d_kps_out, c->d_desc_out, ocap, c->d_n_out);
+        if (rc != ORB_OK) return rc;
+        ORB_CUDA(cudaMemcpyAsync(c->h_n, c->d_n_out, sizeof(int) * F, cudaMemcpyDeviceToHost, c->stream));
+        ORB_CUDA(cudaStreamSynchronize(c->stream));
+        // copy back only what was produced
+        for (int f = 0; f < F; ++f) {
+            const int n = c->h_n[f];
+            n_out[f0 + f] = n;
+            if (n > cap || n > ocap) {
+                orb_set_error("frame %d produced %d keypoints, capacity %d", f0 + f, n, cap);
+                status = ORB_ERR_CAPACITY;
+            }
+        }
+        for (int f = 0; f < F; ++f) {
+            const int n = std::min(std::min(c->h_n[f], cap), ocap);
+            if (n <= 0) continue;
+            ORB_CUDA(cudaMemcpyAsync(c->h_kps + (size_t)f * ocap, c->d_kps_out + (size_t)f * ocap, sizeof(orb_kp) * n,
+                                     cudaMemcpyDeviceToHost, c->stream));
+            ORB_CUDA(cudaMemcpyAsync(c->h_desc + (size_t)f * ocap * 32, c->d_desc_out + (size_t)f * ocap * 32, (size_t)32 * n,
+                                     cudaMemcpyDeviceToHost, c->stream));
+        }
+        ORB_CUDA(cudaStreamSynchronize(c->stream));
+        for (int f = 0; f < F; ++f) {
+            const int n = std::min(std::min(c->h_n[f], cap), ocap);
+            if (n <= 0) continue;
+            memcpy(kps + (size_t)(f0 + f) * cap, c->h_kps + (size_t)f * ocap, sizeof(orb_kp) * n);
+            memcpy(desc + (size_t)(f0 + f) * cap * 32, c->h_desc + (size_t)f * ocap * 32, (size_t)32 * n);
+        }
+    }
+    return status;
+}
+
+int orb_extract(orb_ctx* c, const uint8_t* img, int w, int h, size_t stride, orb_kp* kps, uint8_t* desc, int cap,
+                int* n_out) {
+    if (!n_out) return ORB_ERR_INVALID;
+    int32_t n = 0;
+    const int rc = orb_extract_batch(c, img, (img && w > 0 && h > 0) ? 1 : 0, w, h, stride, (size_t)stride * h, kps, desc,
+                                     cap, &n);
+    *n_out = n;
+    return rc;
+}
+
+int orb_level_dims(orb_ctx* c, int level, int* w, int* h) {
+    if (!c || !c->have_geom || level < 0 || level >= c->nlevels) return ORB_ERR_INVALID;
+    if (w) *w = c->g.lv[level].w;
+    if (h) *h = c->g.lv[level].h;
+    return ORB_OK;
+}
+
+int orb_pyramid_level(orb_ctx* c, int frame, int level, uint8_t* dst, size_t dst_stride) {
+    if (!c || !c->have_geom || !dst || level < 0 || level >= c->nlevels || frame < 0 || frame >= c->last_frames)
+        return ORB_ERR_INVALID;
+    const LevelGeom& L = c->g.lv[level];
+    const int bw = L.w + 2 * ORB_EDGE;
+    if (dst_stride < (size_t)bw) return ORB_ERR_INVALID;
+    ORB_CUDA(cudaSetDevice(c->device));
+    ORB_CUDA(cudaMemcpy2DAsync(dst, dst_stride, c->d_pyr + L.base + (long long)frame * L.frame_stride, L.pitch, bw, L.rows,
+                               cudaMemcpyDeviceToHost, c->stream));
+    ORB_CUDA(cudaStreamSynchronize(c->stream));
+    return ORB_OK;
+}
+
+int orb_debug_blurred(orb_ctx* c, int frame, int level, uint8_t* dst, size_t dst_stride) {
+    if (!c || !c->have_geom || !dst || level < 0 || level >= c->nlevels || frame < 0 || frame >= c->last_frames)
+        return ORB_ERR_INVALID;
+    const LevelGeom& L = c->g.lv[level];
+    if (dst_stride < (size_t)L.w) return ORB_ERR_INVALID;
+    ORB_CUDA(cudaSetDevice(c->device));
+    ORB_CUDA(cudaMemcpy2DAsync(dst, dst_stride, c->d_blur + L.bbase + (long long)frame * L.bframe_stride, L.bpitch, L.w, L.h,
+                               cudaMemcpyDeviceToHost, c->stream));
+    ORB_CUDA(cudaStreamSynchronize(c->stream));
+    return ORB_OK;
+}
+
+int orb_debug_raw_corners(orb_ctx* c, int frame, int level, float* xyr, int cap, int* n_out) {
+    if (!c || !c->have_geom || !n_out || level < 0 || level >= c->nlevels || frame < 0 || frame >= c->last_frames)
+        return ORB_ERR_INVALID;
+    const LevelGeom& L = c->g.lv[level];
+    ORB_CUDA(cudaSetDevice(c->device));
+    int n = 0;
+    ORB_CUDA(cudaMemcpyAsync(&n, c->d_corner_count + frame * c->nlevels + level, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    ORB_CUDA(cudaStreamSynchronize(c->stream));
+    n = std::min(n, L.corner_cap);
+    *n_out = n;
+    if (!xyr || n == 0) return ORB_OK;
+    std::vector<unsigned long long> rec(n);
+    ORB_CUDA(cudaMemcpyAsync(rec.data(), c->d_corners + L.corner_base + (long long)frame * L.corner_cap,
+                             sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost, c->stream));
+    ORB_CUDA(cudaStreamSynchronize(c->stream));
+    std::sort(rec.begin(), rec.end(), [](unsigned long long a, unsigned long long b) { return corner_order(a) < corner_order(b); });
+    for (int i = 0; i < std::min(n, cap); ++i) {
+        xyr[3 * i] = (float)corner_x(rec[i]); xyr[3 * i + 1] = (float)corner_y(rec[i]); xyr[3 * i + 2] = (float)corner_score(rec[i]);
+    }
+    return n > cap ? ORB_ERR_CAPACITY : ORB_OK;
+}
+
+int orb_debug_tie_counts(orb_ctx* c, int frame, int32_t* ties /*[nlevels]*/) {
+    if (!c || !c->have_geom || !ties || frame < 0 || frame >= c->last_frames) return ORB_ERR_INVALID;
+    ORB_CUDA(cudaSetDevice(c->device));
+    ORB_CUDA(cudaMemcpyAsync(ties, c->d_corner_count + (size_t)c->max_batch * c->nlevels + frame * c->nlevels,
+                             sizeof(int) * c->nlevels, cudaMemcpyDeviceToHost, c->stream));
+    ORB_CUDA(cudaStreamSynchronize(c->stream));
+    return ORB_OK;
+}
+
+}  // extern "C"

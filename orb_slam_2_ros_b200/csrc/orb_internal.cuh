@@ -1,0 +1,109 @@
+// orb_internal.cuh — shared declarations of liborb_b200 (sm_100a).  Not a public header.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+
+#include "../../include/orb_b200.h"
+
+#define ORB_MAX_LEVELS 12
+#define ORB_EDGE 19        // EDGE_THRESHOLD   (reference ORBextractor.cc:72)
+#define ORB_MINB 16        // EDGE_THRESHOLD-3 (reference ORBextractor.cc:801)
+#define ORB_HALF_PATCH 15  // reference ORBextractor.cc:71
+#define ORB_PATCH 31       // reference ORBextractor.cc:70
+
+// thread-local error string ---------------------------------------------------------------------------
+void orb_set_error(const char* fmt, ...);
+
+#define ORB_CUDA(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            orb_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return ORB_ERR_CUDA;                                                               \
+        }                                                                                      \
+    } while (0)
+
+// per-level geometry, passed BY VALUE to kernels (lives in the constant bank) ---------------------------
+struct LevelGeom {
+    int w, h;                  // interior size of mvImagePyramid[l]
+    int pitch, rows;           // bordered buffer: pitch bytes per row, rows = h + 38
+    long long base;            // byte offset of frame 0 of this level in the pyramid arena
+    long long frame_stride;    // pitch * rows
+    int bpitch;                // blurred buffer pitch (w x h, no border)
+    long long bbase, bframe_stride;
+    int nCols, nRows, wCell, hCell, maxBX, maxBY;  // cell grid (reference ORBextractor.cc:801-817)
+    int cell_base;             // number of cells in levels < l
+    int quota;                 // mnFeaturesPerLevel[l]
+    int nIni;                  // quadtree roots (reference ORBextractor.cc:566)
+    float hX;
+    int corner_cap;            // worst-case number of NMS survivors of this level
+    long long corner_base;     // element offset (u64 records) of frame 0 / this level in the corner arena
+    int node_cap;              // max quadtree list length (+ slack)
+    int kp_base;               // offset of this level's slots in a frame's kept-keypoint array
+    int xtab, ytab;            // offsets into the resize tables (entries of ResizeTap)
+    float scale;               // mvScaleFactor[l]
+    float size;                // (float)(int)(PATCH_SIZE * scale)
+};
+
+struct Geometry {
+    int nlevels, w, h;
+    int ini_th, min_th;
+    int total_cells, total_kp_slots, max_node_cap, max_tile_bytes;
+    long long pyr_frame_total;   // not used for addressing (level-major layout), informational
+    LevelGeom lv[ORB_MAX_LEVELS];
+};
+
+struct ResizeTap {  // one destination coordinate of resize(INTER_LINEAR): two source taps + Q11 weights
+    unsigned short s0, s1;
+    short c0, c1;
+};
+
+// 64-bit corner record: max() over records picks the reference's winner inside a quadtree node:
+//   hi 32 bits = score << 24 | (0xFFFFFF - order)   order = (cell index << 12 | y_in_cell << 6 | x_in_cell)
+//   lo 32 bits = x | y << 16     (x, y relative to the 16-px border == vToDistributeKeys coordinates)
+__host__ __device__ inline unsigned long long corner_pack(int x, int y, int score, int order) {
+    return ((unsigned long long)(((unsigned)score << 24) | (0xFFFFFFu - (unsigned)order)) << 32) |
+           (unsigned)(x | (y << 16));
+}
+__host__ __device__ inline int corner_x(unsigned long long r) { return (int)(r & 0xFFFF); }
+__host__ __device__ inline int corner_y(unsigned long long r) { return (int)((r >> 16) & 0xFFFF); }
+__host__ __device__ inline int corner_score(unsigned long long r) { return (int)(r >> 56); }
+__host__ __device__ inline int corner_order(unsigned long long r) { return (int)(0xFFFFFFu - ((r >> 32) & 0xFFFFFFu)); }
+
+struct orb_ctx {
+    int device = 0;
+    int nfeatures = 0, nlevels = 0, ini_th = 0, min_th = 0;
+    double scale_factor = 0;
+    float scale[ORB_MAX_LEVELS], inv_scale[ORB_MAX_LEVELS], sigma2[ORB_MAX_LEVELS], inv_sigma2[ORB_MAX_LEVELS];
+    int quota[ORB_MAX_LEVELS];
+    int max_batch = 1;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    long long launches = 0;
+    // geometry-dependent state (rebuilt when the image size changes)
+    bool have_geom = false;
+    Geometry g;
+    int last_frames = 0;
+    uint8_t* d_in = nullptr;  size_t in_bytes = 0;      // staging of host input frames
+    uint8_t* d_pyr = nullptr; size_t pyr_bytes = 0;     // bordered pyramids, level-major
+    uint8_t* d_blur = nullptr; size_t blur_bytes = 0;   // blurred levels
+    unsigned long long* d_corners = nullptr; size_t corner_elems = 0;
+    unsigned short* d_node_of_key = nullptr;
+    int* d_corner_count = nullptr;                      // [2][max_batch][nlevels]: corner counts, tie-at-cut counts
+    unsigned long long* d_kept = nullptr;               // [max_batch][total_kp_slots]
+    int* d_kept_count = nullptr;                        // [max_batch][nlevels]
+    ResizeTap* d_taps = nullptr;
+    int* d_blur_tile_base = nullptr; int blur_tiles = 0;
+    orb_kp* d_kps_out = nullptr; uint8_t* d_desc_out = nullptr; int* d_n_out = nullptr; int out_cap = 0;
+    orb_kp* h_kps = nullptr; uint8_t* h_desc = nullptr; int* h_n = nullptr; uint8_t* h_in = nullptr;  // pinned
+    size_t h_in_bytes = 0;
+};
+
+// kernels' launchers (orb_extract_kernels.cu)
+int orb_blur_tile_bases(const Geometry& g, int* bases);
+int orb_fast_smem_bytes();
+int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int nframes, size_t row_stride, size_t frame_stride,
+                       orb_kp* d_kps, uint8_t* d_desc, int cap, int* d_n_out);

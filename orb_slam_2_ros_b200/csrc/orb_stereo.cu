@@ -1,0 +1,216 @@
+// orb_stereo.cu — Frame::ComputeStereoMatches (reference orb_slam2/src/Frame.cc:502-676) on the device.
+//
+// One warp per left keypoint: (1) row-band candidate search — a right keypoint is a candidate iff the left
+// row lies in [floor(y-2s), ceil(y+2s)] (the vRowIndices table, Frame.cc:519-529), octave within +-1 and
+// uR in [uL-maxD, uL]; minimum Hamming distance below TH_HIGH, lowest right index on ties (the table is
+// filled in ascending iR order); (2) if < (TH_HIGH+TH_LOW)/2: 11x11 centre-subtracted L1 patch distance
+// over 11 horizontal shifts in pyramid level kpL.octave (exact in integers), parabola sub-pixel fit and
+// depth in separately-rounded fp32.  A second kernel applies the median cut (Frame.cc:662-675).
+#include <algorithm>
+#include <vector>
+
+#include "orb_internal.cuh"
+
+namespace {
+
+#define TH_HIGH 100
+#define TH_LOW 50
+
+struct StereoScales { float scale[ORB_MAX_LEVELS]; float inv_scale[ORB_MAX_LEVELS]; };
+
+__device__ __forceinline__ int dist256s(const uint4* a, const uint4* b) {
+    const uint4 a0 = a[0], a1 = a[1], b0 = b[0], b1 = b[1];
+    return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+           __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+__global__ void __launch_bounds__(256)
+stereo_match_kernel(const uint8_t* __restrict__ pyrL, const uint8_t* __restrict__ pyrR, const orb_kp* __restrict__ kpsL,
+                    const uint8_t* __restrict__ descL, int N, const orb_kp* __restrict__ kpsR,
+                    const uint8_t* __restrict__ descR, int Nr, float mbf, float mb, const StereoScales sc,
+                    float* __restrict__ uRight, float* __restrict__ depth, int* __restrict__ sad,
+                    const __grid_constant__ Geometry g) {
+    const int lane = threadIdx.x & 31;
+    const int iL = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (iL >= N) return;
+    if (lane == 0) { uRight[iL] = -1.0f; depth[iL] = -1.0f; sad[iL] = -1; }
+    const orb_kp kpL = kpsL[iL];
+    const int levelL = kpL.octave;
+    const float vL = kpL.y, uL = kpL.x;
+    const int row = (int)vL;
+    const int nRows = g.lv[0].h;
+    if (row < 0 || row >= nRows) return;
+    const float maxD = __fdiv_rn(mbf, mb);   // minZ = mb, maxD = mbf/minZ   (Frame.cc:532-534)
+    const float minU = __fsub_rn(uL, maxD), maxU = uL;
+    if (maxU < 0) return;
+    const uint4* dL = reinterpret_cast<const uint4*>(descL + (size_t)iL * 32);
+    unsigned best = 0xFFFFFFFFu;
+    for (int iR = lane; iR < Nr; iR += 32) {
+        const orb_kp kpR = kpsR[iR];
+        const float r = __fmul_rn(2.0f, sc.scale[kpR.octave]);
+        const int maxr = (int)ceilf(__fadd_rn(kpR.y, r)), minr = (int)floorf(__fsub_rn(kpR.y, r));
+        if (row < minr || row > maxr) continue;
+        if (kpR.octave < levelL - 1 || kpR.octave > levelL + 1) continue;
+        if (kpR.x >= minU && kpR.x <= maxU) {
+            const int d = dist256s(dL, reinterpret_cast<const uint4*>(descR + (size_t)iR * 32));
+            if (d < TH_HIGH) best = min(best, ((unsigned)d << 16) | (unsigned)iR);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (best == 0xFFFFFFFFu) return;
+    const int bestDist = (int)(best >> 16), bestIdxR = (int)(best & 0xFFFFu);
+    if (bestDist >= (TH_HIGH + TH_LOW) / 2) return;
+
+    // ---- sub-pixel refinement by correlation (Frame.cc:588-659) ----
+    const float uR0 = kpsR[bestIdxR].x;
+    const float sf = sc.inv_scale[levelL];
+    const float scaleduL = roundf(__fmul_rn(kpL.x, sf));
+    const float scaledvL = roundf(__fmul_rn(kpL.y, sf));
+    const float scaleduR0 = roundf(__fmul_rn(uR0, sf));
+    const int w = 5, Lh = 5;
+    const LevelGeom& G = g.lv[levelL];
+    const float iniu = __fsub_rn(__fadd_rn(scaleduR0, (float)Lh), (float)w);
+    const float endu = __fadd_rn(__fadd_rn(__fadd_rn(scaleduR0, (float)Lh), (float)w), 1.0f);
+    if (iniu < 0 || endu >= (float)G.w) return;
+    const int y0 = (int)(scaledvL - w), xl0 = (int)(scaleduL - w), xr0 = (int)(scaleduR0 - w);
+    const uint8_t* PL = pyrL + G.base + (long long)ORB_EDGE * G.pitch + ORB_EDGE;  // frame 0 interior
+    const uint8_t* PR = pyrR + G.base + (long long)ORB_EDGE * G.pitch + ORB_EDGE;
+    const int cL = PL[(long long)(y0 + w) * G.pitch + xl0 + w];
+    // each lane owns up to 4 of the 121 patch pixels
+    int il[4], py[4], px[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int p = lane + 32 * k;
+        py[k] = p / 11; px[k] = p - py[k] * 11;
+        il[k] = (p < 121) ? (int)PL[(long long)(y0 + py[k]) * G.pitch + xl0 + px[k]] - cL : 0;
+    }
+    int bestSad = 0x7FFFFFFF, bestinc = 0;
+    int d_prev = 0, d_at_best_m1 = 0, d_at_best = 0, d_at_best_p1 = 0;
+    bool want_next = false;
+    for (int inc = -Lh; inc <= Lh; ++inc) {
+        const int cR = PR[(long long)(y0 + w) * G.pitch + xr0 + inc + w];
+        int s = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int p = lane + 32 * k;
+            if (p < 121) s += abs(il[k] - ((int)PR[(long long)(y0 + py[k]) * G.pitch + xr0 + inc + px[k]] - cR));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (want_next) { d_at_best_p1 = s; want_next = false; }
+        if (s < bestSad) { bestSad = s; bestinc = inc; d_at_best_m1 = d_prev; d_at_best = s; want_next = true; }
+        d_prev = s;
+    }
+    if (lane != 0) return;
+    sad[iL] = -2 - bestSad;  // provisional: reached refinement but (so far) no match; decoded by the host / median kernel
+    if (bestinc == -Lh || bestinc == Lh) return;
+    const float dist1 = (float)d_at_best_m1, dist2 = (float)d_at_best, dist3 = (float)d_at_best_p1;
+    const float deltaR = __fdiv_rn(__fsub_rn(dist1, dist3),
+                                   __fmul_rn(2.0f, __fsub_rn(__fadd_rn(dist1, dist3), __fmul_rn(2.0f, dist2))));
+    if (deltaR < -1 || deltaR > 1) return;
+    float bestuR = __fmul_rn(sc.scale[levelL], __fadd_rn(__fadd_rn(scaleduR0, (float)bestinc), deltaR));
+    float disparity = __fsub_rn(uL, bestuR);
+    if (disparity >= 0 && disparity < maxD) {
+        if (disparity <= 0) {
+            disparity = 0.01f;                       // float disparity = 0.01 (double literal)
+            bestuR = (float)((double)uL - 0.01);     // bestuR = uL - 0.01 (evaluated in double)
+        }
+        depth[iL] = __fdiv_rn(mbf, disparity);
+        uRight[iL] = bestuR;
+        sad[iL] = bestSad;
+    }
+}
+
+// median cut (Frame.cc:662-675): thDist = 1.5f*1.4f*median of the kept SADs, drop everything >= thDist
+__global__ void __launch_bounds__(1024)
+stereo_median_kernel(int N, float* uRight, float* depth, const int* __restrict__ sad, int* nkept_out) {
+    __shared__ int s_count, s_median, s_removed;
+    if (threadIdx.x == 0) { s_count = 0; s_median = -1; s_removed = 0; }
+    __syncthreads();
+    int local = 0;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) local += (sad[i] >= 0);
+    atomicAdd(&s_count, local);
+    __syncthreads();
+    const int count = s_count;
+    if (count == 0) { if (threadIdx.x == 0) *nkept_out = 0; return; }
+    const int target = count / 2;
+    // element of rank `target` in (sad, index) order
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const int si = sad[i];
+        if (si < 0) continue;
+        int rank = 0;
+        for (int j = 0; j < N; ++j) {
+            const int sj = sad[j];
+            rank += (sj >= 0) && (sj < si || (sj == si && j < i));
+        }
+        if (rank == target) s_median = si;
+    }
+    __syncthreads();
+    const float thDist = __fmul_rn(1.5f * 1.4f, (float)s_median);
+    int removed = 0;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const int si = sad[i];
+        if (si >= 0 && !((float)si < thDist)) { uRight[i] = -1.0f; depth[i] = -1.0f; removed++; }
+    }
+    atomicAdd(&s_removed, removed);
+    __syncthreads();
+    if (threadIdx.x == 0) *nkept_out = count - s_removed;
+}
+
+}  // namespace
+
+extern "C" int orb_stereo_match(orb_ctx* cl, orb_ctx* cr, const orb_kp* kps_l, const uint8_t* desc_l, int nl,
+                                const orb_kp* kps_r, const uint8_t* desc_r, int nr, float bf, float b, float* u_right,
+                                float* depth, int* nmatches) {
+    if (!cl || !cr || nl < 0 || nr < 0 || !nmatches || (nl && (!kps_l || !desc_l || !u_right || !depth)) ||
+        (nr && (!kps_r || !desc_r)))
+        return ORB_ERR_INVALID;
+    *nmatches = 0;
+    for (int i = 0; i < nl; ++i) { u_right[i] = -1.0f; depth[i] = -1.0f; }
+    if (!cl->have_geom || !cr->have_geom || cl->last_frames < 1 || cr->last_frames < 1) {
+        orb_set_error("orb_stereo_match: both contexts must hold an extracted frame");
+        return ORB_ERR_INVALID;
+    }
+    if (cl->device != cr->device || cl->g.w != cr->g.w || cl->g.h != cr->g.h || cl->nlevels != cr->nlevels ||
+        cl->max_batch != cr->max_batch) {
+        orb_set_error("orb_stereo_match: left/right contexts differ in device, image size, levels or max_batch");
+        return ORB_ERR_INVALID;
+    }
+    if (nl == 0 || nr == 0) return ORB_OK;
+    if (nr > 65535) { orb_set_error("orb_stereo_match: more than 65535 right keypoints"); return ORB_ERR_CAPACITY; }
+    for (int i = 0; i < nl; ++i) if (kps_l[i].octave < 0 || kps_l[i].octave >= cl->nlevels) return ORB_ERR_INVALID;
+    for (int i = 0; i < nr; ++i) if (kps_r[i].octave < 0 || kps_r[i].octave >= cl->nlevels) return ORB_ERR_INVALID;
+    ORB_CUDA(cudaSetDevice(cl->device));
+    ORB_CUDA(cudaStreamSynchronize(cr->stream));  // the right pyramid must be complete; work runs on the left stream
+    cudaStream_t st = cl->stream;
+    orb_kp *d_kl = nullptr, *d_kr = nullptr; uint8_t *d_dl = nullptr, *d_dr = nullptr;
+    float *d_ur = nullptr, *d_dep = nullptr; int *d_sad = nullptr, *d_nk = nullptr;
+    int rc = ORB_OK;
+#define ST_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { orb_set_error("%s -> %s", #x, cudaGetErrorString(e_)); rc = ORB_ERR_CUDA; goto done; } } while (0)
+    ST_CUDA(cudaMalloc(&d_kl, sizeof(orb_kp) * nl)); ST_CUDA(cudaMalloc(&d_kr, sizeof(orb_kp) * nr));
+    ST_CUDA(cudaMalloc(&d_dl, (size_t)32 * nl)); ST_CUDA(cudaMalloc(&d_dr, (size_t)32 * nr));
+    ST_CUDA(cudaMalloc(&d_ur, sizeof(float) * nl)); ST_CUDA(cudaMalloc(&d_dep, sizeof(float) * nl));
+    ST_CUDA(cudaMalloc(&d_sad, sizeof(int) * nl)); ST_CUDA(cudaMalloc(&d_nk, sizeof(int)));
+    ST_CUDA(cudaMemcpyAsync(d_kl, kps_l, sizeof(orb_kp) * nl, cudaMemcpyHostToDevice, st));
+    ST_CUDA(cudaMemcpyAsync(d_kr, kps_r, sizeof(orb_kp) * nr, cudaMemcpyHostToDevice, st));
+    ST_CUDA(cudaMemcpyAsync(d_dl, desc_l, (size_t)32 * nl, cudaMemcpyHostToDevice, st));
+    ST_CUDA(cudaMemcpyAsync(d_dr, desc_r, (size_t)32 * nr, cudaMemcpyHostToDevice, st));
+    {
+        StereoScales sc;
+        for (int l = 0; l < ORB_MAX_LEVELS; ++l) { sc.scale[l] = l < cl->nlevels ? cl->scale[l] : 1.f; sc.inv_scale[l] = l < cl->nlevels ? cl->inv_scale[l] : 1.f; }
+        stereo_match_kernel<<<(nl + 7) / 8, 256, 0, st>>>(cl->d_pyr, cr->d_pyr, d_kl, d_dl, nl, d_kr, d_dr, nr, bf, b, sc, d_ur, d_dep,
+                                                         d_sad, cl->g);
+        stereo_median_kernel<<<1, 1024, 0, st>>>(nl, d_ur, d_dep, d_sad, d_nk);
+        cl->launches += 2;
+    }
+    ST_CUDA(cudaGetLastError());
+    ST_CUDA(cudaMemcpyAsync(u_right, d_ur, sizeof(float) * nl, cudaMemcpyDeviceToHost, st));
+    ST_CUDA(cudaMemcpyAsync(depth, d_dep, sizeof(float) * nl, cudaMemcpyDeviceToHost, st));
+    ST_CUDA(cudaMemcpyAsync(nmatches, d_nk, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ST_CUDA(cudaStreamSynchronize(st));
+done:
+    cudaFree(d_kl); cudaFree(d_kr); cudaFree(d_dl); cudaFree(d_dr); cudaFree(d_ur); cudaFree(d_dep); cudaFree(d_sad); cudaFree(d_nk);
+    return rc;
+#undef ST_CUDA
+}

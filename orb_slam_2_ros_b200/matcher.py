@@ -1,0 +1,116 @@
+"""ORBmatcher — host-side mirror of ORB_SLAM2::ORBmatcher (reference orb_slam2/include/ORBmatcher.h:37-103)
+over the C ABI.  The reference methods take Frame / KeyFrame / MapPoint objects; here the same routines take
+the arrays those objects hold (what each loop reads), see include/orb_b200.h."""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import KP_DTYPE, TOP2_DTYPE, SearchParams, check, lib, ptr
+
+TH_HIGH = 100      # ORBmatcher.cc:37
+TH_LOW = 50        # ORBmatcher.cc:38
+HISTO_LENGTH = 30  # ORBmatcher.cc:39
+MODE_TRACK_LAST, MODE_LOCAL_POINTS = 0, 1
+
+
+def _f(a): return None if a is None else np.ascontiguousarray(a, np.float32)
+def _i(a): return None if a is None else np.ascontiguousarray(a, np.int32)
+def _b(a): return None if a is None else np.ascontiguousarray(a, np.uint8)
+
+
+class ORBmatcher:
+    TH_HIGH, TH_LOW, HISTO_LENGTH = TH_HIGH, TH_LOW, HISTO_LENGTH
+
+    def __init__(self, nnratio=0.6, checkOri=True, device=0):
+        self.mfNNratio, self.mbCheckOrientation, self.device = nnratio, checkOri, device
+
+    @staticmethod
+    def DescriptorDistance(a, b, device=0):
+        """ORBmatcher.cc:1649-1665.  Computed on the device like everything else (one 1x1 search)."""
+        out = hamming_top2(np.asarray(a, np.uint8).reshape(1, 32), np.asarray(b, np.uint8).reshape(1, 32), device)
+        return int(out["best_dist"][0])
+
+    def SearchByProjection(self, mode, kps_un, desc, bounds, taken, q_u, q_v, q_radius, q_min_level, q_max_level,
+                           q_desc, u_right=None, q_ur=None, q_er_max=None, q_angle=None, q_valid=None, q_obs=None,
+                           th_dist=TH_HIGH):
+        """ORBmatcher.cc:45-129 (mode LOCAL_POINTS) / :1330-1472 (mode TRACK_LAST).
+        Returns (nmatches, match_of_query[nq], target_query[n]); `taken` (uint8[n]) is updated in place."""
+        kps_un = np.ascontiguousarray(kps_un, KP_DTYPE)
+        n, nq = len(kps_un), len(q_u)
+        desc, q_desc = _b(desc), _b(q_desc)
+        u_right, q_u, q_v, q_radius, q_ur, q_er_max, q_angle = map(_f, (u_right, q_u, q_v, q_radius, q_ur, q_er_max, q_angle))
+        q_min_level, q_max_level, q_valid, q_obs = _i(q_min_level), _i(q_max_level), _b(q_valid), _b(q_obs)
+        assert taken.dtype == np.uint8 and taken.flags.c_contiguous and len(taken) == n
+        prm = SearchParams(mode, th_dist, self.mfNNratio, int(self.mbCheckOrientation), *map(float, bounds))
+        moq = np.full(nq, -1, np.int32); tq = np.full(n, -1, np.int32); nm = C.c_int32(0)
+        check(lib().orb_search_by_projection(self.device, C.byref(prm), ptr(kps_un), ptr(desc), ptr(u_right), n, ptr(taken), nq,
+                                             ptr(q_u), ptr(q_v), ptr(q_radius), ptr(q_min_level), ptr(q_max_level), ptr(q_desc),
+                                             ptr(q_ur), ptr(q_er_max), ptr(q_angle), ptr(q_valid), ptr(q_obs), ptr(moq), ptr(tq),
+                                             C.byref(nm)))
+        return nm.value, moq, tq
+
+    def MatchBruteForce(self, desc1, angle1, desc2, angle2, th_dist=TH_LOW):
+        """SearchByBoW inner loop (ORBmatcher.cc:196-252) over one node holding both frames' keypoints."""
+        desc1, desc2, angle1, angle2 = _b(desc1), _b(desc2), _f(angle1), _f(angle2)
+        m = np.full(len(desc1), -1, np.int32); nm = C.c_int32(0)
+        check(lib().orb_match_bruteforce(self.device, ptr(desc1), ptr(angle1), len(desc1), ptr(desc2), ptr(angle2), len(desc2),
+                                         th_dist, self.mfNNratio, int(self.mbCheckOrientation), ptr(m), C.byref(nm)))
+        return nm.value, m
+
+
+def hamming_top2(q, db, device=0):
+    """Brute-force best / second-best (ORBmatcher.cc:202-227 update rule) of each query over db (host arrays)."""
+    q, db = _b(q), _b(db)
+    out = np.zeros(len(q), TOP2_DTYPE)
+    check(lib().orb_hamming_top2(device, ptr(q), len(q), ptr(db), len(db), ptr(out)))
+    return out
+
+
+def top2_merge(parts):
+    """parts: TOP2_DTYPE [nparts, nq] (e.g. the all-gathered per-shard results) -> merged [nq]."""
+    parts = np.ascontiguousarray(parts, TOP2_DTYPE)
+    nparts, nq = parts.shape
+    out = np.zeros(nq, TOP2_DTYPE)
+    check(lib().orb_top2_merge(ptr(parts), nparts, nq, ptr(out)))
+    return out
+
+
+class DescriptorDB:
+    """One device-resident shard of a descriptor database (BASELINE config 5)."""
+
+    def __init__(self, capacity_rows, index_base=0, device=0):
+        self._h = C.c_void_p()
+        check(lib().orb_db_create(C.byref(self._h), device, capacity_rows, index_base))
+        self.device, self.index_base = device, index_base
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().orb_db_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def add(self, desc):
+        desc = _b(desc)
+        check(lib().orb_db_add(self._h, ptr(desc), len(desc)))
+
+    def add_device(self, d_ptr, nrows):
+        check(lib().orb_db_add_device(self._h, C.c_void_p(d_ptr), nrows))
+
+    def __len__(self):
+        return lib().orb_db_size(self._h)
+
+    def set_stream(self, handle):
+        check(lib().orb_db_set_stream(self._h, C.c_void_p(handle)))
+
+    def query_top2(self, q):
+        q = _b(q)
+        out = np.zeros(len(q), TOP2_DTYPE)
+        check(lib().orb_db_query_top2(self._h, ptr(q), len(q), ptr(out)))
+        return out
+
+    def query_top2_device(self, d_q, nq, d_out):
+        check(lib().orb_db_query_top2_device(self._h, C.c_void_p(d_q), nq, C.c_void_p(d_out)))
+
+    def launch_count(self):
+        return lib().orb_db_launch_count(self._h)

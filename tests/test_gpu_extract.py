@@ -1,0 +1,154 @@
+"""GPU parity: the CUDA extractor (through the C ABI) against the CPU oracle and the committed golden vectors.
+Bit-exact on keypoint coordinates, octaves, responses, sizes, descriptors, pyramid, blur and raw corners;
+the float angle is compared bit-exactly too (tolerance allowed by north_star: 1e-4 rad)."""
+import glob
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from orb_slam_2_ros_b200 import synth
+
+pytestmark = pytest.mark.gpu
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def assert_kps_equal(a, b, what=""):
+    assert len(a) == len(b), "%s count %d vs %d" % (what, len(a), len(b))
+    for f in ("x", "y", "size", "response", "octave", "class_id"):
+        assert np.array_equal(a[f].view(np.uint32), b[f].view(np.uint32)), "%s field %s" % (what, f)
+    ang_bad = int((a["angle"].view(np.uint32) != b["angle"].view(np.uint32)).sum())
+    if ang_bad:   # report, then apply the stated tolerance (1e-4 rad)
+        d = np.abs(a["angle"].astype(np.float64) - b["angle"].astype(np.float64))
+        d = np.minimum(d, 360 - d)
+        assert np.deg2rad(d.max()) < 1e-4, "%s angle off by %g deg" % (what, d.max())
+    return ang_bad
+
+
+@pytest.fixture(scope="module")
+def ORB():
+    from orb_slam_2_ros_b200 import ORBextractor
+    return ORBextractor
+
+
+CASES = [(0, 640, 480, 1000, 8), (1, 640, 480, 1000, 8), (2, 640, 480, 1000, 8), (3, 752, 480, 1000, 8),
+         (4, 1241, 376, 2000, 8), (5, 640, 480, 1200, 8), (6, 320, 240, 500, 6), (7, 160, 120, 300, 4),
+         (8, 645, 487, 1000, 8)]
+
+
+@pytest.mark.parametrize("seed,w,h,nf,nl", CASES)
+def test_extract_matches_oracle_all_stages(oracle, ORB, seed, w, h, nf, nl):
+    img = synth.synth_frame(seed, w, h)
+    ex = ORB(nf, 1.2, nl, 20, 7)
+    kps, desc = ex(img)
+    oex = oracle.Extractor(nf, 1.2, nl, 20, 7)
+    okps, odesc = oex.extract(img)
+    # stage by stage first, so a failure points at the first wrong stage
+    for l in range(nl):
+        assert ex.level_dims(l) == oex.level_dims(l)
+        assert np.array_equal(ex.pyramid_level_bordered(l), oex.level(l)), "pyramid level %d" % l
+    for l in range(nl):
+        raw = ex.debug_raw_corners(l)
+        oraw = oex.raw_corners(l)
+        oraw = np.stack([oraw["x"], oraw["y"], oraw["response"]], 1) if len(oraw) else np.zeros((0, 3), np.float32)
+        assert raw.shape == oraw.shape, "raw corner count level %d: %s vs %s" % (l, raw.shape, oraw.shape)
+        assert np.array_equal(raw, oraw), "raw corners level %d" % l
+    for l in range(nl):
+        ob = oex.blurred(l)
+        if ob is not None:
+            assert np.array_equal(ex.debug_blurred(l), ob), "blur level %d" % l
+    assert_kps_equal(kps, okps, "final")
+    flips = int(np.unpackbits(desc ^ odesc).sum())
+    assert flips == 0, "%d descriptor bit flips" % flips
+    assert np.array_equal(ex.debug_tie_counts(), oex.stats()[:, 2])
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
+def test_extract_matches_golden(ORB, path):
+    g = np.load(path)
+    w, h, nf, nl = int(g["w"]), int(g["h"]), int(g["nfeatures"]), int(g["nlevels"])
+    img = synth.synth_frame(int(g["seed"]), w, h)
+    assert sha(img) == str(g["image_sha"])
+    ex = ORB(nf, 1.2, nl, 20, 7)
+    kps, desc = ex(img)
+    assert_kps_equal(kps, g["kps"], "golden")
+    assert np.array_equal(desc, g["desc"])
+    for l in range(nl):
+        assert sha(ex.pyramid_level_bordered(l)) == str(g["L%d_bordered_sha" % l])
+        if str(g["L%d_blurred_sha" % l]):
+            assert sha(ex.debug_blurred(l)) == str(g["L%d_blurred_sha" % l])
+
+
+def test_batch_equals_single_and_strided_input(oracle, ORB):
+    imgs = synth.synth_batch(100, 6, 640, 480, unique=3)
+    exb = ORB(1000, max_batch=4)      # 6 frames through a 4-frame arena: two chunks
+    res = exb.extract_batch(imgs)
+    oex = oracle.Extractor(1000)
+    for f in range(6):
+        ok, od = oex.extract(imgs[f])
+        assert_kps_equal(res[f][0], ok, "frame %d" % f)
+        assert np.array_equal(res[f][1], od)
+    # a non-contiguous (strided) single image, like a cv::Mat ROI
+    big = np.zeros((500, 700), np.uint8)
+    big[10:490, 30:670] = imgs[1]
+    k, d = exb(big[10:490, 30:670])
+    ok, od = oex.extract(imgs[1])
+    assert_kps_equal(k, ok, "strided")
+    assert np.array_equal(d, od)
+
+
+def test_edge_cases(oracle, ORB):
+    ex = ORB(500)
+    k, d = ex(np.zeros((0, 0), np.uint8))                 # empty image => silent return (ORBextractor.cc:1086)
+    assert len(k) == 0 and d.shape == (0, 32)
+    k, d = ex(np.full((480, 640), 90, np.uint8))          # flat image: no corner at any threshold
+    assert len(k) == 0
+    # image size change on the same context (arena rebuild)
+    img = synth.synth_frame(9, 320, 240)
+    k, d = ex(img)
+    ok, od = oracle.Extractor(500).extract(img)
+    assert_kps_equal(k, ok, "resized ctx")
+    assert np.array_equal(d, od)
+    # too small for the reference's cell grid: explicit error instead of the reference's division by zero
+    from orb_slam_2_ros_b200 import _lib
+    with pytest.raises(_lib.OrbError) as ei:
+        ex(synth.synth_frame(1, 160, 120))
+    assert ei.value.code == _lib.ORB_ERR_TOO_SMALL
+    # mvImagePyramid is public API (ORBextractor.h:85): interior ROI with step w+38
+    ex(synth.synth_frame(0))
+    pyr = ex.mvImagePyramid
+    assert pyr[0].shape == (480, 640) and pyr[0].strides[0] == 640 + 38
+    assert np.array_equal(pyr[0], synth.synth_frame(0))
+
+
+def test_noise_image_many_corners(oracle, ORB):
+    """Pure noise: tens of thousands of raw corners per level, quota-limited everywhere (deep quadtree)."""
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, (480, 640), dtype=np.uint8)
+    k, d = ORB(1000)(img)
+    ok, od = oracle.Extractor(1000).extract(img)
+    assert_kps_equal(k, ok, "noise")
+    assert np.array_equal(d, od)
+
+
+def test_sincos_pin_sampled(oracle):
+    """pin (iii): (float)cos((double)x), (float)sin((double)x) on the device equal the host libm on sampled
+    ranges of fp32 bit patterns in [0, 2*pi] (the exhaustive sweep is tools/check_sincos_exhaustive.py)."""
+    import ctypes as C
+    from orb_slam_2_ros_b200 import _lib
+    L = _lib.lib()
+    hi = np.array([6.2831855], np.float32).view(np.uint32)[0]
+    rng = np.random.default_rng(0)
+    starts = [0, 1, int(hi) - 200000] + [int(s) for s in rng.integers(0x30000000, int(hi) - 200000, size=12)]
+    for s in starts:
+        n = 200000
+        a = np.zeros(n, np.float32); b = np.zeros(n, np.float32)
+        _lib.check(L.orb_debug_sincos_range(0, C.c_uint32(s), n, _lib.ptr(a), _lib.ptr(b)))
+        oa, ob = oracle.sincos_range(s, n)
+        assert np.array_equal(a.view(np.uint32), oa.view(np.uint32)), "cos mismatch in range %x" % s
+        assert np.array_equal(b.view(np.uint32), ob.view(np.uint32)), "sin mismatch in range %x" % s

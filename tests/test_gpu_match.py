@@ -1,0 +1,200 @@
+"""GPU parity: Hamming search, windowed / brute-force matching and stereo matching (through the C ABI) against
+the CPU oracle.  All integer / index results are compared bit-exactly; the stereo floats bit-exactly too."""
+import numpy as np
+import pytest
+
+from orb_slam_2_ros_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _same_top2(gpu, ora, base=0):
+    assert np.array_equal(gpu["best_dist"], ora["best_dist"])
+    assert np.array_equal(gpu["second_dist"], ora["second_dist"])
+    assert np.array_equal(gpu["best_idx"], np.where(ora["best_idx"] >= 0, ora["best_idx"].astype(np.int64) + base, -1))
+    assert np.array_equal(gpu["second_idx"], np.where(ora["second_idx"] >= 0, ora["second_idx"].astype(np.int64) + base, -1))
+
+
+@pytest.mark.parametrize("nq,ndb", [(700, 5000), (1, 1), (3, 2), (1500, 777), (2100, 40000), (5, 0), (64, 100001)])
+def test_hamming_top2_vs_oracle(oracle, nq, ndb):
+    from orb_slam_2_ros_b200 import hamming_top2
+    rng = np.random.default_rng(nq * 31 + ndb)
+    db = rng.integers(0, 256, (ndb, 32), dtype=np.uint8)
+    q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
+    if ndb >= 100:   # exact duplicates, near duplicates and ties
+        db[ndb // 2] = db[3]; db[ndb - 1] = db[3]
+        q[0] = db[3]
+        q[min(1, nq - 1)] = db[10] ^ np.uint8(1)
+        db[50:60] = db[50]
+        q[min(2, nq - 1)] = db[50]
+    _same_top2(hamming_top2(q, db), oracle.hamming_top2(q, db))
+
+
+def test_db_shards_merge(oracle):
+    """Config-5 shape in miniature: a database sharded into 3 device-resident shards, replicated queries,
+    per-shard top-2, exact merge == single-database oracle; planted queries find their rows."""
+    from orb_slam_2_ros_b200 import DescriptorDB, top2_merge
+    total, nq = 30000, 400
+    db = synth.synth_descriptors(99, 0, total)
+    q, planted, flips = synth.synth_queries(99, total, nq)
+    bounds = [0, 9000, 21000, total]
+    parts = []
+    for s in range(3):
+        shard = DescriptorDB(bounds[s + 1] - bounds[s], index_base=bounds[s])
+        # counter-based generator: the shard builds its own slice
+        shard.add(synth.synth_descriptors(99, bounds[s], bounds[s + 1] - bounds[s]))
+        assert len(shard) == bounds[s + 1] - bounds[s]
+        parts.append(shard.query_top2(q))
+        shard.close()
+    merged = top2_merge(np.stack(parts))
+    _same_top2(merged, oracle.hamming_top2(q, db))
+    ok = planted >= 0
+    assert np.array_equal(merged["best_idx"][ok], planted[ok])
+    assert np.array_equal(merged["best_dist"][ok], flips[ok])
+
+
+@pytest.fixture(scope="module")
+def frame_pair(oracle):
+    a = synth.synth_frame(40)
+    b = synth.shifted_frame(a, 3, -2, 40)
+    ex = oracle.Extractor(1000)
+    ka, da = ex.extract(a)
+    kb, db = ex.extract(b)
+    return ka, da, kb, db, ex.scale_factors.copy()
+
+
+@pytest.mark.parametrize("variant", ["mono", "stereo", "nonblocking", "backward_levels"])
+def test_search_by_projection_track_last(oracle, frame_pair, variant):
+    """ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) (ORBmatcher.cc:1330-1472)."""
+    from orb_slam_2_ros_b200 import ORBmatcher
+    from orb_slam_2_ros_b200.matcher import MODE_TRACK_LAST
+    ka, da, kb, db, sf = frame_pair
+    rng = np.random.default_rng(3)
+    n, nq = len(kb), len(ka)
+    q_u = (ka["x"] + np.float32(3)).astype(np.float32); q_v = (ka["y"] - np.float32(2)).astype(np.float32)
+    th = 15.0 if variant != "stereo" else 7.0
+    q_radius = (np.float32(th) * sf[ka["octave"]]).astype(np.float32)
+    if variant == "backward_levels":
+        q_min, q_max = np.zeros(nq, np.int32), ka["octave"].astype(np.int32)
+    else:
+        q_min, q_max = ka["octave"] - 1, ka["octave"] + 1
+    q_valid = (rng.random(nq) > 0.1).astype(np.uint8)
+    q_obs = None
+    u_right = q_ur = q_er = None
+    if variant == "stereo":
+        u_right = np.where(rng.random(n) < 0.7, kb["x"] - rng.uniform(1, 40, n), -1).astype(np.float32)
+        q_ur = (q_u - rng.uniform(1, 40, nq)).astype(np.float32)
+        q_er = q_radius.copy()
+    if variant == "nonblocking":
+        q_obs = (rng.random(nq) > 0.5).astype(np.uint8)
+    taken0 = (rng.random(n) < 0.05).astype(np.uint8)
+    bounds = (0.0, 0.0, 640.0, 480.0)
+    t_o, t_g = taken0.copy(), taken0.copy()
+    grid = oracle.Grid(kb, *bounds)
+    nm_o, moq_o, tq_o = oracle.search_by_projection(oracle.MODE_TRACK_LAST, grid, db, u_right, t_o, q_u, q_v, q_radius, q_min,
+                                                    q_max, da, q_ur, q_er, ka["angle"], q_valid, q_obs, th_dist=100,
+                                                    nn_ratio=0.9, check_orientation=True)
+    nm_g, moq_g, tq_g = ORBmatcher(0.9, True).SearchByProjection(MODE_TRACK_LAST, kb, db, bounds, t_g, q_u, q_v, q_radius, q_min,
+                                                                 q_max, da, u_right, q_ur, q_er, ka["angle"], q_valid, q_obs,
+                                                                 th_dist=100)
+    assert nm_o > 100, "test input produced too few matches (%d)" % nm_o
+    assert nm_g == nm_o
+    assert np.array_equal(moq_g, moq_o)
+    assert np.array_equal(tq_g, tq_o)
+    assert np.array_equal(t_g, t_o)
+
+
+def test_search_by_projection_local_points(oracle, frame_pair):
+    """ORBmatcher::SearchByProjection(Frame&, vpMapPoints, th) (ORBmatcher.cc:45-129): best/second, same-octave ratio."""
+    from orb_slam_2_ros_b200 import ORBmatcher
+    from orb_slam_2_ros_b200.matcher import MODE_LOCAL_POINTS
+    ka, da, kb, db, sf = frame_pair
+    rng = np.random.default_rng(4)
+    n, nq = len(kb), len(ka)
+    q_u = (ka["x"] + np.float32(3) + rng.uniform(-1, 1, nq)).astype(np.float32)
+    q_v = (ka["y"] - np.float32(2) + rng.uniform(-1, 1, nq)).astype(np.float32)
+    r = np.where(rng.random(nq) < 0.5, 2.5, 4.0).astype(np.float32) * np.float32(3.0)   # RadiusByViewingCos * th
+    q_radius = (r * sf[ka["octave"]]).astype(np.float32)
+    q_min, q_max = ka["octave"] - 1, ka["octave"]
+    taken0 = np.zeros(n, np.uint8)
+    bounds = (0.0, 0.0, 640.0, 480.0)
+    t_o, t_g = taken0.copy(), taken0.copy()
+    grid = oracle.Grid(kb, *bounds)
+    for ratio in (0.8, 0.6):
+        nm_o, moq_o, tq_o = oracle.search_by_projection(oracle.MODE_LOCAL_POINTS, grid, db, None, t_o, q_u, q_v, q_radius, q_min,
+                                                        q_max, da, th_dist=100, nn_ratio=ratio, check_orientation=False)
+        nm_g, moq_g, tq_g = ORBmatcher(ratio, False).SearchByProjection(MODE_LOCAL_POINTS, kb, db, bounds, t_g, q_u, q_v, q_radius,
+                                                                      q_min, q_max, da, th_dist=100)
+        assert nm_g == nm_o and nm_o > 50
+        assert np.array_equal(moq_g, moq_o) and np.array_equal(tq_g, tq_o) and np.array_equal(t_g, t_o)
+
+
+def test_grid_window_order(oracle, frame_pair):
+    """GetFeaturesInArea candidate ORDER (ix, iy, insertion) decides ties: check through equal-distance candidates."""
+    from orb_slam_2_ros_b200 import ORBmatcher
+    from orb_slam_2_ros_b200.matcher import MODE_TRACK_LAST
+    _, _, kb, db, _ = frame_pair
+    n = len(kb)
+    same = np.tile(db[0], (n, 1))              # every target has the same descriptor: all distances tie
+    q_u = kb["x"][:300].copy(); q_v = kb["y"][:300].copy()
+    q_radius = np.full(300, 40, np.float32)
+    q_min = np.full(300, -1, np.int32); q_max = np.full(300, -1, np.int32)
+    bounds = (0.0, 0.0, 640.0, 480.0)
+    t_o, t_g = np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+    grid = oracle.Grid(kb, *bounds)
+    nm_o, moq_o, tq_o = oracle.search_by_projection(oracle.MODE_TRACK_LAST, grid, same, None, t_o, q_u, q_v, q_radius, q_min, q_max,
+                                                    same[:300], q_angle=np.zeros(300, np.float32), check_orientation=False)
+    nm_g, moq_g, tq_g = ORBmatcher(0.9, False).SearchByProjection(MODE_TRACK_LAST, kb, same, bounds, t_g, q_u, q_v, q_radius, q_min,
+                                                                  q_max, same[:300], q_angle=np.zeros(300, np.float32))
+    assert nm_g == nm_o == 300
+    assert np.array_equal(moq_g, moq_o) and np.array_equal(tq_g, tq_o)
+
+
+@pytest.mark.parametrize("ratio,th", [(0.6, 50), (0.9, 100)])
+def test_match_bruteforce(oracle, frame_pair, ratio, th):
+    from orb_slam_2_ros_b200 import ORBmatcher
+    ka, da, kb, db, _ = frame_pair
+    nm_o, m_o = oracle.match_bruteforce(da, ka["angle"], db, kb["angle"], th, ratio, True)
+    nm_g, m_g = ORBmatcher(ratio, True).MatchBruteForce(da, ka["angle"], db, kb["angle"], th)
+    assert nm_o > 50
+    assert nm_g == nm_o and np.array_equal(m_g, m_o)
+
+
+def test_match_bruteforce_collisions(oracle):
+    """Many queries compete for few targets: exercises the masked fallback scan of the resolve kernel."""
+    from orb_slam_2_ros_b200 import ORBmatcher
+    rng = np.random.default_rng(11)
+    base = rng.integers(0, 256, (6, 32), dtype=np.uint8)
+    d2 = np.concatenate([base[rng.integers(0, 6, 40)] ^ (rng.random((40, 32)) < 0.02).astype(np.uint8),
+                         rng.integers(0, 256, (25, 32), dtype=np.uint8)])
+    d1 = base[rng.integers(0, 6, 300)] ^ (rng.random((300, 32)) < 0.03).astype(np.uint8)
+    a1 = rng.uniform(0, 360, 300).astype(np.float32); a2 = rng.uniform(0, 360, len(d2)).astype(np.float32)
+    for ratio in (0.95, 1.5):
+        nm_o, m_o = oracle.match_bruteforce(d1, a1, d2, a2, 100, ratio, False)
+        nm_g, m_g = ORBmatcher(ratio, False).MatchBruteForce(d1, a1, d2, a2, 100)
+        assert nm_g == nm_o and np.array_equal(m_g, m_o)
+    # fewer targets than the top-K list length
+    nm_o, m_o = oracle.match_bruteforce(d1, a1, d2[:3], a2[:3], 100, 1.5, False)
+    nm_g, m_g = ORBmatcher(1.5, False).MatchBruteForce(d1, a1, d2[:3], a2[:3], 100)
+    assert nm_g == nm_o and np.array_equal(m_g, m_o)
+
+
+def test_stereo_matches(oracle):
+    """Frame::ComputeStereoMatches (Frame.cc:502-676) on a KITTI-shape pair, nFeatures=2000."""
+    from orb_slam_2_ros_b200 import ORBextractor, compute_stereo_matches
+    left, right, _ = synth.synth_stereo_pair(2)
+    bf, fx = np.float32(386.1448), np.float32(718.856)
+    b = np.float32(bf / fx)
+    exl, exr = ORBextractor(2000), ORBextractor(2000)
+    kl, dl = exl(left)
+    kr, dr = exr(right)
+    oel, oer = oracle.Extractor(2000), oracle.Extractor(2000)
+    okl, odl = oel.extract(left)
+    okr, odr = oer.extract(right)
+    assert np.array_equal(dl, odl) and np.array_equal(dr, odr)
+    kept_o, ur_o, dep_o, _ = oracle.stereo_match(oel, oer, okl, odl, okr, odr, float(bf), float(b))
+    kept_g, ur_g, dep_g = compute_stereo_matches(exl, exr, kl, dl, kr, dr, float(bf), float(b))
+    assert kept_o > 200, "stereo test input too weak (%d matches)" % kept_o
+    assert kept_g == kept_o
+    assert np.array_equal(ur_g.view(np.uint32), ur_o.view(np.uint32))
+    assert np.array_equal(dep_g.view(np.uint32), dep_o.view(np.uint32))
