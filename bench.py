@@ -1,0 +1,436 @@
+#!/usr/bin/env python
+"""bench.py — headline measurement of the B200-native ORB front-end.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference ...                     (the CPU restatement on the host cores)
+
+One "step" = one pass of the extractor hot path (pyramid -> per-cell FAST -> quadtree -> blur -> orientation
++ rBRIEF) over one batch of synthetic 640x480 frames per GPU (BASELINE config 1's shape and parameters,
+batched the way config 4 shards frames).  The JSON line also carries the second half of BASELINE's metric —
+Hamming compares/s of the map-wide top-2 search (config 5: 2000 queries x a 10 M-row database sharded over
+the ranks with an all-gather + merge) — under "hamming".
+
+Timed regions:
+  value   frames already in HBM, outputs stay in HBM (orb_extract_batch_device), CUDA events, max over ranks
+  e2e     HOST buffers in, HOST keypoints/descriptors out through the public call (ORBextractor.extract_batch
+          -> orb_extract_batch): pinned staging, H2D, kernels, D2H inside the timed region
+  roofline    per-stage CUDA-event times recorded by the library inside the timed region of `value`
+  cpu_baseline  oracle/ (the CPU restatement = checker) timed on all host cores on a bounded sample
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+W, H, NFEAT, NLEVELS, SCALE, INI_TH, MIN_TH = 640, 480, 1000, 8, 1.2, 20, 7
+METRIC = "ORB extract frames/s @640x480 1k feat"
+NQ = 2000
+DB_SEED = 7
+
+
+# ---------------------------------------------------------------------------------------------------------
+# algorithmic bytes per frame, unfused-stage model of SURVEY.md §8(d) (stated in DESIGN.md §Roofline)
+# ---------------------------------------------------------------------------------------------------------
+def level_dims(w, h, nlevels=NLEVELS, scale=SCALE):
+    sf = [np.float32(1.0)]
+    for _ in range(1, nlevels):
+        sf.append(np.float32(np.float64(sf[-1]) * np.float64(scale)))
+    out = []
+    for l in range(nlevels):
+        inv = np.float32(1.0) / sf[l]
+        out.append((int(np.rint(np.float32(w) * inv)), int(np.rint(np.float32(h) * inv))))
+    return out
+
+
+def algorithmic_bytes(w, h):
+    dims = level_dims(w, h)
+    px = [a * b for a, b in dims]
+    bordered = [(a + 38) * (b + 38) for a, b in dims]
+    return {
+        "pyramid": px[0] + sum(px[:-1]) + sum(bordered),  # read L0, read levels 0..6, write bordered levels
+        "fast_cells": sum(px),                             # read every level once
+        "blur": 2 * sum(px),                               # read + write every level
+    }
+
+
+# ---------------------------------------------------------------------------------------------------------
+def clocks_sampler(stop, out, gpu_index):
+    q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    try:
+        p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                              "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+    except OSError:
+        return
+    out["proc"] = p
+    for line in p.stdout:
+        if stop.is_set():
+            break
+        f = [x.strip() for x in line.split(",")]
+        if len(f) >= 6:
+            out.setdefault("rows", []).append(f)
+    p.kill()
+
+
+def summarize_clocks(rows):
+    if not rows:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+    sm = sorted(int(r[0]) for r in rows if r[0].isdigit())
+    mx = [int(r[1]) for r in rows if r[1].isdigit()]
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in rows)]
+    return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+            "samples": len(rows)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU restatement (oracle/) on the host cores: cpu_baseline leg and the --impl reference arm
+# ---------------------------------------------------------------------------------------------------------
+def cpu_extract_throughput(frames, threads, repeat=1):
+    """frames: uint8 [n, H, W]; every thread owns one oracle extractor and takes frames round-robin."""
+    from oracle import orb_oracle
+    exs = [orb_oracle.Extractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH) for _ in range(threads)]
+    counts = [0] * threads
+
+    def work(t):
+        for _ in range(repeat):
+            for i in range(t, len(frames), threads):
+                k, _d = exs[t].extract(frames[i])
+                counts[t] += 1
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    t0 = time.perf_counter()
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    dt = time.perf_counter() - t0
+    return sum(counts) / dt, dt, sum(counts)
+
+
+def cpu_hamming_throughput(q, db, threads):
+    from oracle import orb_oracle
+    parts = np.array_split(np.arange(len(q)), threads)
+
+    def work(t):
+        if len(parts[t]):
+            orb_oracle.hamming_top2(q[parts[t]], db)
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    t0 = time.perf_counter()
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    dt = time.perf_counter() - t0
+    return len(q) * len(db) / dt, dt
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU path.  Its own translation units need OpenCV C++ headers that this
+    image lacks, so the arm times oracle/'s restatement (kind "port") on all host cores."""
+    if rank != 0:
+        return
+    from orb_slam_2_ros_b200 import synth
+    threads = os.cpu_count() or 1
+    sample = max(threads, min(args.ref_frames, 4 * threads))
+    frames = synth.synth_batch(0, sample, W, H, unique=min(16, sample))
+    for _ in range(args.warmup):
+        cpu_extract_throughput(frames[:threads], threads)
+    t_total, n_total = 0.0, 0
+    for _ in range(args.steps):
+        _fps, dt, n = cpu_extract_throughput(frames, threads)
+        t_total += dt
+        n_total += n
+    fps = n_total / t_total
+    # Hamming sample: 256 queries x 400k rows per step
+    from orb_slam_2_ros_b200 import synth as S
+    db = S.synth_descriptors(DB_SEED, 0, 400000)
+    q, _, _ = S.synth_queries(DB_SEED, 400000, 256)
+    cps, hdt = cpu_hamming_throughput(q, db, threads)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "ORBextractor 640x480 nFeatures=1000 8 levels 1.2 20/7 (BASELINE config 1 shape), "
+                               "%d frames per step on %d host threads" % (sample, threads)},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                         "sample": "%d synthetic frames per step, one oracle extractor per thread" % sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "hamming": {"metric": "Hamming compares/s", "value": cps, "unit": "compares/s", "cores": threads, "kind": "port",
+                    "sample": "256 queries x 400000 rows, reference bit-hack DescriptorDistance, %.2f s" % hdt},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=512, help="frames per step per GPU (512 x 640x480 = 157 MB > L2)")
+    ap.add_argument("--db-rows", type=int, default=10_000_000, help="total database rows of the Hamming leg")
+    ap.add_argument("--ref-frames", type=int, default=64)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-hamming", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product has no CPU path); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if args.warmup < 3:
+        args.warmup = 3  # timing rule: W >= 3
+
+    import __graft_entry__ as entry
+    if not os.path.exists(os.path.join(ROOT, "orb_slam_2_ros_b200", "lib", "liborb_b200.so")):
+        if rank == 0:
+            entry.build()
+        if world > 1:
+            dist.barrier()
+    from orb_slam_2_ros_b200 import DescriptorDB, ORBextractor, synth, top2_merge
+    from orb_slam_2_ros_b200._lib import KP_DTYPE, TOP2_DTYPE
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    B = args.batch
+    # ---- synthetic frames: every rank its own contiguous block of seeds (config 4's sharding) ----
+    frames_np = synth.synth_batch(1000 * rank, B, W, H, unique=16)
+    h_frames = torch.from_numpy(frames_np).pin_memory()
+    d_frames = h_frames.to(dev, non_blocking=False)
+    ex = ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=local_rank, max_batch=B)
+    cap = ex.max_keypoints
+    d_kps = torch.zeros((B, cap, KP_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+    d_desc = torch.zeros((B, cap, 32), dtype=torch.uint8, device=dev)
+    d_n = torch.zeros(B, dtype=torch.int32, device=dev)
+    stream = torch.cuda.Stream(dev)        # a real (non-null) stream shared by torch's events and the library
+    torch.cuda.set_stream(stream)
+    ex.set_stream(stream.cuda_stream)
+
+    def step_device():
+        ex.extract_batch_device(d_frames.data_ptr(), B, W, H, W, W * H, d_kps.data_ptr(), d_desc.data_ptr(), cap, d_n.data_ptr())
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    ex.profile_enable(True)
+    ex.profile_read(reset=True)
+    launches0 = ex.launch_count()
+    stop, clk = threading.Event(), {}
+    sampler = threading.Thread(target=clocks_sampler, args=(stop, clk, local_rank), daemon=True)
+    sampler.start()
+    time.sleep(0.25)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(stream)
+    barrier()
+    ms_dev = max_over_ranks(e0.elapsed_time(e1))
+    stage_ms, prof_calls, prof_frames = ex.profile_read(reset=True)
+    ex.profile_enable(False)
+    launches = ex.launch_count() - launches0
+    n_kp = int(d_n.sum().item())
+    value = world * B * args.steps / (ms_dev * 1e-3)
+
+    # ---- e2e: host frames -> host keypoints + descriptors through the public call ----
+    kps_h = np.zeros((B, cap), KP_DTYPE)
+    desc_h = np.zeros((B, cap, 32), np.uint8)
+    n_h = np.zeros(B, np.int32)
+    from orb_slam_2_ros_b200._lib import check, lib, ptr
+
+    def step_e2e():
+        check(lib().orb_extract_batch(ex._h, h_frames.data_ptr(), B, W, H, W, W * H, ptr(kps_h), ptr(desc_h), cap, ptr(n_h)))
+
+    for _ in range(min(args.warmup, 3)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    t_e2e = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * B * args.steps / t_e2e
+    h2d = B * W * H
+    d2h = int(n_h.sum()) * (KP_DTYPE.itemsize + 32) + 4 * B
+    stop.set()
+
+    # ---- Hamming leg: 2000 queries x db_rows rows sharded contiguously over the ranks ----
+    ham = None
+    if not args.no_hamming:
+        rows_total = args.db_rows
+        per = (rows_total + world - 1) // world
+        r0, r1 = min(rank * per, rows_total), min((rank + 1) * per, rows_total)
+        db = DescriptorDB(max(r1 - r0, 1), index_base=r0, device=local_rank)
+        chunk = 1 << 20
+        for s in range(r0, r1, chunk):
+            db.add(synth.synth_descriptors(DB_SEED, s, min(chunk, r1 - s)))
+        q_np, planted, _flips = synth.synth_queries(DB_SEED, rows_total, NQ)
+        d_q = torch.from_numpy(q_np).to(dev)
+        d_top = torch.zeros((NQ, TOP2_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+        gathered = torch.zeros((world, NQ, TOP2_DTYPE.itemsize), dtype=torch.uint8, device=dev) if world > 1 else None
+        db.set_stream(stream.cuda_stream)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+        def step_hamming():
+            db.query_top2_device(d_q.data_ptr(), NQ, d_top.data_ptr())
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, d_top)   # 2000 x 24 B per rank over NCCL / NVLink
+
+        for _ in range(args.warmup):
+            step_hamming()
+        barrier()
+        db.profile_enable(True)
+        db.profile_read(reset=True)
+        hl0 = db.launch_count()
+        tot = 0.0
+        hsteps = max(3, min(args.steps, 10))
+        for _ in range(hsteps):
+            flush.zero_()                                       # L2 flush between timed iterations
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            step_hamming()
+            b.record(stream)
+            torch.cuda.synchronize()
+            tot += max_over_ranks(a.elapsed_time(b))
+        s_ms, m_ms, calls = db.profile_read(reset=True)
+        db.profile_enable(False)
+        hl = db.launch_count() - hl0
+        # result check: merged top-1 of the planted queries must be the planted row
+        parts = gathered.cpu().numpy().view(TOP2_DTYPE).reshape(world, NQ) if world > 1 else \
+            d_top.cpu().numpy().view(TOP2_DTYPE).reshape(1, NQ)
+        merged = top2_merge(parts)
+        ok = int((merged["best_idx"][planted >= 0] == planted[planted >= 0]).sum())
+        import ctypes
+        issue = ctypes.c_double(0)
+        check(lib().orb_bench_issue_rate(local_rank, 0, 2000, ctypes.byref(issue)))
+        popc_rate = issue.value * 1e9                           # measured POPC issue rate of this GPU (register-only)
+        check(lib().orb_bench_issue_rate(local_rank, 1, 2000, ctypes.byref(issue)))
+        cmp_rate = issue.value * 1e9                            # register-only 256-bit compare + top-2 update rate
+        peak_cmp = popc_rate / 8.0                              # 8 x popc.b32 per 256-bit compare
+        kern_cps = NQ * (r1 - r0) / (s_ms / max(calls, 1) * 1e-3) if s_ms > 0 else 0.0
+        ham = {
+            "metric": "Hamming compares/s", "value": NQ * rows_total * hsteps / (tot * 1e-3), "unit": "compares/s",
+            "scaling": "strong", "steps": hsteps, "ms_per_step": tot / hsteps,
+            "config": {"workload": "%d queries x %d-row descriptor DB sharded over %d GPU(s), top-2 + all-gather merge"
+                                   % (NQ, rows_total, world), "l2": "flushed between timed iterations"},
+            "planted_top1_found": "%d/%d" % (ok, int((planted >= 0).sum())),
+            "roofline": {"bound": "popc", "achieved": kern_cps / 1e9, "peak": peak_cmp / 1e9, "unit": "Gcompare/s",
+                         "frac": kern_cps / peak_cmp if peak_cmp else None,
+                         "peak_source": "measured POPC issue rate of this GPU / 8 popc per compare (orb_bench_issue_rate kind 0)",
+                         "popc_per_s": popc_rate, "register_only_compare_per_s": cmp_rate,
+                         "kernel": "hamming_top2_kernel", "avg_launch_ms": s_ms / max(calls, 1)},
+            "gpu_launches": int(hl),
+        }
+
+    sampler.join(timeout=2.0)
+    if clk.get("proc"):
+        clk["proc"].kill()
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        hbm_peak, peak_src = (peaks["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs") if "hbm_gbs" in peaks else (6650.0, "fallback")
+        ab = algorithmic_bytes(W, H)
+        per_call = {k: v / max(prof_calls, 1) for k, v in stage_ms.items()}
+        stages = {}
+        for k in ("pyramid", "fast_cells", "blur"):
+            gbs = ab[k] * B / (per_call[k] * 1e-3) / 1e9 if per_call[k] > 0 else 0.0
+            stages[k] = {"ms": per_call[k], "alg_bytes": ab[k] * B, "gbs": gbs, "frac": gbs / hbm_peak}
+        for k in ("quadtree", "orient_describe"):
+            stages[k] = {"ms": per_call[k]}
+        dom = max(("pyramid", "fast_cells", "blur", "quadtree", "orient_describe"), key=lambda k: per_call[k])
+        total_alg = sum(ab.values()) * B
+        sum_ms = sum(per_call.values())
+        if dom in ab:
+            roof = {"bound": "hbm", "achieved": stages[dom]["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": stages[dom]["frac"],
+                    "traffic": None, "kernel": dom, "peak_source": peak_src, "avg_launch_ms": per_call[dom]}
+        else:
+            # the dominant stage moves no image-sized data: report the whole step against the unfused-stage byte model
+            gbs = total_alg / (sum_ms * 1e-3) / 1e9
+            roof = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None,
+                    "kernel": dom + " (latency-bound stage; achieved = all stages' algorithmic bytes / step time)",
+                    "peak_source": peak_src, "avg_launch_ms": per_call[dom]}
+        roof["stages"] = stages
+        roof["step_alg_bytes"] = total_alg
+        roof["step_gbs"] = total_alg / (ms_dev / args.steps * 1e-3) / 1e9
+
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            threads = os.cpu_count() or 1
+            sample = frames_np[:max(threads, 16)]
+            fps1, dt1, n1 = cpu_extract_throughput(sample[:threads], threads)      # calibration pass (also warm-up)
+            repeat = max(1, int(args.cpu_seconds * fps1 / len(sample)))
+            fps, dt, n = cpu_extract_throughput(sample, threads, repeat=repeat)
+            cpu = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                   "sample": "%d extractions of %d distinct synthetic frames in %.1f s, one oracle extractor per thread" % (n, len(sample), dt)}
+        line = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "ORBextractor 640x480 nFeatures=1000 8 levels 1.2 20/7 (BASELINE config 1), batch of %d frames "
+                                   "per GPU per step" % B, "frames_per_step_per_gpu": B, "keypoints_per_step_per_gpu": n_kp,
+                       "l2": "inputs larger than L2 (%d MB of frames + %d MB pyramid arena per step)" % (B * W * H >> 20, (B * 1158012) >> 20),
+                       "parallelism": "frames sharded over %d GPU(s), no collective" % world},
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "roofline": roof,
+            "cpu_baseline": cpu,
+            "hamming": ham,
+            "clocks": summarize_clocks(clk.get("rows")),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -96,6 +96,13 @@ int orb_sync(orb_ctx* ctx);
 /* kernels launched by this context so far (the bench's gpu_launches counter) */
 int64_t orb_launch_count(orb_ctx* ctx);
 
+/* per-stage device timers (CUDA events on the context stream, recorded around every stage of every extract
+ * call while enabled; reading never blocks the stream).  stage_ms[ORB_NUM_STAGES] = accumulated milliseconds of
+ * {pyramid, FAST cells, quadtree, blur, orientation+descriptors}; *calls / *frames = batches / frames covered. */
+#define ORB_NUM_STAGES 5
+int orb_profile_enable(orb_ctx* ctx, int enable);
+int orb_profile_read(orb_ctx* ctx, double* stage_ms, int64_t* calls, int64_t* frames, int reset);
+
 /* mvImagePyramid[level] of frame `frame` of the last extract call: interior size via orb_level_dims;
  * orb_pyramid_level copies the BORDERED buffer ((w+38) x (h+38), reflect-101 border, like the Mat the
  * reference's ROI lives in) to host memory with row stride dst_stride. */
@@ -126,6 +133,9 @@ int orb_db_set_stream(orb_db* db, void* cuda_stream);
 int orb_db_query_top2(orb_db* db, const uint8_t* q, int nq, orb_top2* out);              /* host q / out */
 int orb_db_query_top2_device(orb_db* db, const uint8_t* d_q, int nq, orb_top2* d_out);   /* async */
 int64_t orb_db_launch_count(orb_db* db);
+/* device timers of the search and merge kernels (accumulated ms over *calls queries), like orb_profile_read */
+int orb_db_profile_enable(orb_db* db, int enable);
+int orb_db_profile_read(orb_db* db, double* search_ms, double* merge_ms, int64_t* calls, int reset);
 /* exact merge of per-shard results (after an all-gather): parts is [nparts][nq]; best = min distance,
  * lowest global index on ties; second = second smallest of the union. */
 int orb_top2_merge(const orb_top2* parts, int nparts, int nq, orb_top2* out);

@@ -200,6 +200,20 @@ int check_device() {
 
 }  // namespace
 
+int orb_profile_harvest(orb_ctx* c, int slot) {
+    cudaEvent_t* ev = c->prof_ev[slot];
+    ORB_CUDA(cudaEventSynchronize(ev[ORB_NSTAGES]));
+    for (int s = 0; s < ORB_NSTAGES; ++s) {
+        float ms = 0.f;
+        ORB_CUDA(cudaEventElapsedTime(&ms, ev[s], ev[s + 1]));
+        c->prof_ms[s] += ms;
+    }
+    c->prof_calls++;
+    c->prof_total_frames += c->prof_frames[slot];
+    c->prof_pending[slot] = false;
+    return ORB_OK;
+}
+
 extern "C" {
 
 int orb_create(orb_ctx** out, int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th, int device,
@@ -253,6 +267,9 @@ void orb_destroy(orb_ctx* c) {
         cudaSetDevice(c->device);
         if (c->stream) cudaStreamSynchronize(c->stream);
         free_geometry_buffers(c);
+        if (c->prof_ev[0][0])
+            for (int r = 0; r < ORB_PROF_RING; ++r)
+                for (int s = 0; s <= ORB_NSTAGES; ++s) cudaEventDestroy(c->prof_ev[r][s]);
         if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     }
     delete c;
@@ -301,6 +318,32 @@ int orb_sync(orb_ctx* c) {
 }
 
 int64_t orb_launch_count(orb_ctx* c) { return c ? c->launches : 0; }
+
+int orb_profile_enable(orb_ctx* c, int enable) {
+    if (!c) return ORB_ERR_INVALID;
+    int rc = ensure_device(c);
+    if (rc != ORB_OK) return rc;
+    if (enable && !c->prof_ev[0][0]) {
+        for (int r = 0; r < ORB_PROF_RING; ++r)
+            for (int s = 0; s <= ORB_NSTAGES; ++s) ORB_CUDA(cudaEventCreate(&c->prof_ev[r][s]));
+    }
+    c->profile = enable != 0;
+    return ORB_OK;
+}
+
+int orb_profile_read(orb_ctx* c, double* stage_ms, int64_t* calls, int64_t* frames, int reset) {
+    if (!c) return ORB_ERR_INVALID;
+    if (c->prof_ev[0][0]) {
+        ORB_CUDA(cudaSetDevice(c->device));
+        for (int r = 0; r < ORB_PROF_RING; ++r)
+            if (c->prof_pending[r]) { int rc = orb_profile_harvest(c, r); if (rc != ORB_OK) return rc; }
+    }
+    if (stage_ms) for (int s = 0; s < ORB_NSTAGES; ++s) stage_ms[s] = c->prof_ms[s];
+    if (calls) *calls = c->prof_calls;
+    if (frames) *frames = c->prof_total_frames;
+    if (reset) { for (int s = 0; s < ORB_NSTAGES; ++s) c->prof_ms[s] = 0; c->prof_calls = 0; c->prof_total_frames = 0; }
+    return ORB_OK;
+}
 
 int orb_extract_batch_device(orb_ctx* c, const uint8_t* d_imgs, int nframes, int w, int h, size_t row_stride,
                              size_t frame_stride, orb_kp* d_kps, uint8_t* d_desc, int cap, int32_t* d_n_out) {

@@ -694,8 +694,19 @@ int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int F, size_t row_stri
                        orb_kp* d_kps, uint8_t* d_desc, int cap, int* d_n_out) {
     const Geometry& g = c->g;
     cudaStream_t st = c->stream;
+    cudaEvent_t* ev = nullptr;
+    if (c->profile) {
+        const int slot = c->prof_head;
+        if (c->prof_pending[slot]) { int rc = orb_profile_harvest(c, slot); if (rc != ORB_OK) return rc; }
+        ev = c->prof_ev[slot];
+        c->prof_frames[slot] = F;
+        c->prof_pending[slot] = true;
+        c->prof_head = (slot + 1) % ORB_PROF_RING;
+    }
+#define ORB_STAGE_MARK(i) do { if (ev) ORB_CUDA(cudaEventRecord(ev[i], st)); } while (0)
     ORB_CUDA(cudaMemsetAsync(c->d_corner_count, 0, sizeof(int) * 2 * (size_t)c->max_batch * g.nlevels, st));
     int* d_tie = c->d_corner_count + (size_t)c->max_batch * g.nlevels;  // second half: tie-at-cut counters
+    ORB_STAGE_MARK(0);
     {   // K1
         const LevelGeom& L = g.lv[0];
         dim3 blk(64, 4), grd((L.pitch / 4 + 63) / 64, (L.rows + 3) / 4, F);
@@ -708,26 +719,32 @@ int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int F, size_t row_stri
             c->launches++;
         }
     }
+    ORB_STAGE_MARK(1);
     {   // K2
         const size_t smem = 66 * FAST_TP + 62 * FAST_SP + 3600 * 2 + 900 * 8;
         fast_cells_kernel<<<dim3(g.total_cells, F), FAST_THREADS, smem, st>>>(c->d_pyr, c->d_corners, c->d_corner_count, g);
         c->launches++;
     }
+    ORB_STAGE_MARK(2);
     {   // K3
         const size_t smem = (size_t)g.max_node_cap * 80;
         quadtree_kernel<<<dim3(g.nlevels, F), QT_THREADS, smem, st>>>(c->d_corners, c->d_corner_count, c->d_node_of_key,
                                                                        c->d_kept, c->d_kept_count, d_tie, g);
         c->launches++;
     }
+    ORB_STAGE_MARK(3);
     {   // K5
         blur_kernel<<<dim3(c->blur_tiles, F), BL_THREADS, 0, st>>>(c->d_pyr, c->d_blur, c->d_blur_tile_base, g);
         c->launches++;
     }
+    ORB_STAGE_MARK(4);
     {   // K4 + K6
         orient_describe_kernel<<<dim3((g.total_kp_slots + OD_WARPS - 1) / OD_WARPS, F), OD_WARPS * 32, 0, st>>>(
             c->d_pyr, c->d_blur, c->d_kept, c->d_kept_count, d_kps, d_desc, cap, d_n_out, g);
         c->launches++;
     }
+    ORB_STAGE_MARK(5);
+#undef ORB_STAGE_MARK
     ORB_CUDA(cudaGetLastError());
     return ORB_OK;
 }

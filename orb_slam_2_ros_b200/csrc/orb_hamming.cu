@@ -147,7 +147,8 @@ __global__ void compare_peak_kernel(unsigned* out, int iters, unsigned seed) {
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            a.x += 0x9E3779B9u; b.w ^= a.x;   // cheap row change so nothing is hoisted
+            // every word of the row changes every iteration (8 extra IADD on the ALU pipe), so no popc is hoisted
+            a.x += 0x9E3779B9u; a.y += a.x; a.z += a.y; a.w += a.z; b.x += a.w; b.y += b.x; b.z += b.y; b.w += b.z;
             const unsigned key = ((unsigned)hamming256(a, b, q) << HT_IDX_BITS) | (unsigned)(i * 8 + u);
             k2 = min(k2, max(key, k1));
             k1 = min(k1, key);
@@ -188,7 +189,27 @@ struct orb_db {
     uint2* d_partial = nullptr; size_t partial_elems = 0;
     uint8_t* d_q = nullptr; orb_top2* d_out = nullptr; int q_cap = 0;
     long long launches = 0;
+    // CUDA-event timers of {search kernel, merge kernel}: ring of event triples, harvested lazily
+    bool profile = false;
+    cudaEvent_t prof_ev[ORB_PROF_RING][3] = {};
+    bool prof_pending[ORB_PROF_RING] = {};
+    int prof_head = 0;
+    double prof_ms[2] = {0, 0};
+    long long prof_calls = 0;
 };
+
+static int db_harvest(orb_db* db, int slot) {
+    cudaEvent_t* ev = db->prof_ev[slot];
+    ORB_CUDA(cudaEventSynchronize(ev[2]));
+    for (int s = 0; s < 2; ++s) {
+        float ms = 0.f;
+        ORB_CUDA(cudaEventElapsedTime(&ms, ev[s], ev[s + 1]));
+        db->prof_ms[s] += ms;
+    }
+    db->prof_calls++;
+    db->prof_pending[slot] = false;
+    return ORB_OK;
+}
 
 static int db_launch(orb_db* db, const uint8_t* d_q, int nq, orb_top2* d_out) {
     if (nq == 0) return ORB_OK;
@@ -200,6 +221,15 @@ static int db_launch(orb_db* db, const uint8_t* d_q, int nq, orb_top2* d_out) {
         ORB_CUDA(cudaMalloc(&db->d_partial, need * sizeof(uint2)));
         db->partial_elems = need;
     }
+    cudaEvent_t* ev = nullptr;
+    if (db->profile) {
+        const int slot = db->prof_head;
+        if (db->prof_pending[slot]) { int rc = db_harvest(db, slot); if (rc != ORB_OK) return rc; }
+        ev = db->prof_ev[slot];
+        db->prof_pending[slot] = true;
+        db->prof_head = (slot + 1) % ORB_PROF_RING;
+        ORB_CUDA(cudaEventRecord(ev[0], db->stream));
+    }
     if (db->n > 0) {
         dim3 grid(p.nsplit, p.grid_y);
         if (p.qpt == 2)
@@ -210,9 +240,11 @@ static int db_launch(orb_db* db, const uint8_t* d_q, int nq, orb_top2* d_out) {
                                                                        p.rows_per_split, db->d_partial, p.nq_pad);
         db->launches++;
     }
+    if (ev) ORB_CUDA(cudaEventRecord(ev[1], db->stream));
     hamming_merge_kernel<<<(nq + 127) / 128, 128, 0, db->stream>>>(db->d_partial, db->n > 0 ? p.nsplit : 0, nq, p.nq_pad,
                                                                   p.rows_per_split, db->index_base, d_out);
     db->launches++;
+    if (ev) ORB_CUDA(cudaEventRecord(ev[2], db->stream));
     ORB_CUDA(cudaGetLastError());
     return ORB_OK;
 }
@@ -243,6 +275,9 @@ void orb_db_destroy(orb_db* db) {
     cudaSetDevice(db->device);
     if (db->stream) cudaStreamSynchronize(db->stream);
     cudaFree(db->d_rows); cudaFree(db->d_partial); cudaFree(db->d_q); cudaFree(db->d_out);
+    if (db->prof_ev[0][0])
+        for (int r = 0; r < ORB_PROF_RING; ++r)
+            for (int s = 0; s < 3; ++s) cudaEventDestroy(db->prof_ev[r][s]);
     if (db->own_stream && db->stream) cudaStreamDestroy(db->stream);
     delete db;
 }
@@ -263,6 +298,30 @@ int orb_db_add_device(orb_db* db, const uint8_t* d_desc, int64_t nrows) {
     ORB_CUDA(cudaSetDevice(db->device));
     ORB_CUDA(cudaMemcpyAsync(db->d_rows + db->n * 32, d_desc, (size_t)nrows * 32, cudaMemcpyDeviceToDevice, db->stream));
     db->n += nrows;
+    return ORB_OK;
+}
+
+int orb_db_profile_enable(orb_db* db, int enable) {
+    if (!db) return ORB_ERR_INVALID;
+    ORB_CUDA(cudaSetDevice(db->device));
+    if (enable && !db->prof_ev[0][0])
+        for (int r = 0; r < ORB_PROF_RING; ++r)
+            for (int s = 0; s < 3; ++s) ORB_CUDA(cudaEventCreate(&db->prof_ev[r][s]));
+    db->profile = enable != 0;
+    return ORB_OK;
+}
+
+int orb_db_profile_read(orb_db* db, double* search_ms, double* merge_ms, int64_t* calls, int reset) {
+    if (!db) return ORB_ERR_INVALID;
+    if (db->prof_ev[0][0]) {
+        ORB_CUDA(cudaSetDevice(db->device));
+        for (int r = 0; r < ORB_PROF_RING; ++r)
+            if (db->prof_pending[r]) { int rc = db_harvest(db, r); if (rc != ORB_OK) return rc; }
+    }
+    if (search_ms) *search_ms = db->prof_ms[0];
+    if (merge_ms) *merge_ms = db->prof_ms[1];
+    if (calls) *calls = db->prof_calls;
+    if (reset) { db->prof_ms[0] = db->prof_ms[1] = 0; db->prof_calls = 0; }
     return ORB_OK;
 }
 

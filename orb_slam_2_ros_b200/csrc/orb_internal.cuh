@@ -13,6 +13,8 @@
 #define ORB_MINB 16        // EDGE_THRESHOLD-3 (reference ORBextractor.cc:801)
 #define ORB_HALF_PATCH 15  // reference ORBextractor.cc:71
 #define ORB_PATCH 31       // reference ORBextractor.cc:70
+#define ORB_NSTAGES 5      // pyramid, FAST cells, quadtree, blur, orientation+descriptors
+#define ORB_PROF_RING 64
 
 // thread-local error string ---------------------------------------------------------------------------
 void orb_set_error(const char* fmt, ...);
@@ -100,7 +102,17 @@ struct orb_ctx {
     orb_kp* d_kps_out = nullptr; uint8_t* d_desc_out = nullptr; int* d_n_out = nullptr; int out_cap = 0;
     orb_kp* h_kps = nullptr; uint8_t* h_desc = nullptr; int* h_n = nullptr; uint8_t* h_in = nullptr;  // pinned
     size_t h_in_bytes = 0;
+    // per-stage CUDA-event timers (orb_profile_enable / orb_profile_read): a ring of event sets so that reading
+    // never stalls the stream; stage s of a call = elapsed(ev[s], ev[s+1])
+    bool profile = false;
+    cudaEvent_t prof_ev[ORB_PROF_RING][ORB_NSTAGES + 1] = {};
+    bool prof_pending[ORB_PROF_RING] = {};
+    int prof_frames[ORB_PROF_RING] = {};
+    int prof_head = 0;
+    double prof_ms[ORB_NSTAGES] = {};
+    long long prof_calls = 0, prof_total_frames = 0;
 };
+int orb_profile_harvest(orb_ctx* c, int slot);
 
 // kernels' launchers (orb_extract_kernels.cu)
 int orb_blur_tile_bases(const Geometry& g, int* bases);

@@ -123,3 +123,16 @@ class ORBextractor:
 
     def launch_count(self):
         return lib().orb_launch_count(self._h)
+
+    # ---- per-stage device timers (CUDA events recorded by the library around every stage) ----
+    STAGES = ("pyramid", "fast_cells", "quadtree", "blur", "orient_describe")
+
+    def profile_enable(self, on=True):
+        check(lib().orb_profile_enable(self._h, int(on)))
+
+    def profile_read(self, reset=True):
+        """-> ({stage: accumulated ms}, calls, frames)"""
+        ms = (C.c_double * len(self.STAGES))()
+        calls, frames = C.c_int64(0), C.c_int64(0)
+        check(lib().orb_profile_read(self._h, ms, C.byref(calls), C.byref(frames), int(reset)))
+        return dict(zip(self.STAGES, list(ms))), calls.value, frames.value

@@ -114,3 +114,12 @@ class DescriptorDB:
 
     def launch_count(self):
         return lib().orb_db_launch_count(self._h)
+
+    def profile_enable(self, on=True):
+        check(lib().orb_db_profile_enable(self._h, int(on)))
+
+    def profile_read(self, reset=True):
+        """-> (search kernel ms, merge kernel ms, calls), accumulated since the last reset"""
+        a, b, n = C.c_double(0), C.c_double(0), C.c_int64(0)
+        check(lib().orb_db_profile_read(self._h, C.byref(a), C.byref(b), C.byref(n), int(reset)))
+        return a.value, b.value, n.value
