@@ -567,97 +567,140 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 }
 
 #define OD_WARPS 8
+#define OD_KPW 4                       // keypoints per warp
+#define OD_KPB (OD_WARPS * OD_KPW)     // keypoints per CTA (== 32: one lane of warp 0 per keypoint in phase 2)
 
+// Three phases per CTA of 32 keypoint slots:
+//   1. every warp accumulates the patch moments of its 4 keypoints (lane = patch column, 31 row loads in flight)
+//   2. warp 0, one LANE per keypoint: fastAtan2 + the double-precision sin/cos of pin (iii) (thread-parallel, so the
+//      long fp64 sequence is issued once per 32 keypoints instead of once per keypoint)
+//   3. every warp builds the 4 descriptors (lane = descriptor byte); the 512-point pattern sits in shared memory as
+//      float4 [8][32] so that a warp-wide read is conflict-free (a per-lane index into __constant__ serialises)
 __global__ void __launch_bounds__(OD_WARPS * 32)
 orient_describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur,
                        const unsigned long long* __restrict__ kept, const int* __restrict__ kept_count,
                        orb_kp* __restrict__ kps_out, uint8_t* __restrict__ desc_out, int cap,
                        int* __restrict__ n_out, const __grid_constant__ Geometry g) {
-    const int lane = threadIdx.x & 31;
-    const int slot = blockIdx.x * OD_WARPS + (threadIdx.x >> 5);
+    __shared__ float4 s_pat[8 * 32];
+    __shared__ int s_m[OD_KPB][2];
+    __shared__ float s_ang[OD_KPB], s_a[OD_KPB], s_b[OD_KPB];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int f = blockIdx.y;
     const int* kc = kept_count + f * g.nlevels;
-    if (slot == 0 && lane == 0) {
+    // pattern: byte `i` of the descriptor uses points 16 i .. 16 i + 15; s_pat[k * 32 + i] = (x0, y0, x1, y1) of bit k
+    {
+        const int k = threadIdx.x >> 5, i = threadIdx.x & 31;
+        const int* p = c_pattern + i * 32 + 4 * k;   // one-off divergent constant reads, 4 per thread
+        s_pat[k * 32 + i] = make_float4((float)p[0], (float)p[1], (float)p[2], (float)p[3]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
         int tot = 0;
         for (int l = 0; l < g.nlevels; ++l) tot += kc[l];
         n_out[f] = tot;
     }
-    if (slot >= g.total_kp_slots) return;
-    int l = 0;
-    while (l + 1 < g.nlevels && slot >= g.lv[l + 1].kp_base) ++l;
-    const LevelGeom& L = g.lv[l];
-    const int i = slot - L.kp_base;
-    if (i >= kc[l]) return;
-    int off = i;
-    for (int k = 0; k < l; ++k) off += kc[k];
-    if (off >= cap) return;
-    const unsigned long long rec = kept[(long long)f * g.total_kp_slots + slot];
-    const int x = corner_x(rec) + ORB_MINB, y = corner_y(rec) + ORB_MINB;  // ORBextractor.cc:881-882
-
-    // ---- IC_Angle (ORBextractor.cc:77-104): lane u-15 handles column u of the circular patch ----
-    const uint8_t* center = pyr + L.base + (long long)f * L.frame_stride + (long long)(ORB_EDGE + y) * L.pitch + ORB_EDGE + x;
-    int m10 = 0, m01 = 0;
-    if (lane < 31) {
-        const int u = lane - ORB_HALF_PATCH;
-        const int au = abs(u);
-#pragma unroll 4
-        for (int v = -ORB_HALF_PATCH; v <= ORB_HALF_PATCH; ++v) {
-            if (au <= c_umax[abs(v)]) {
-                const int val = center[(long long)v * L.pitch + u];
-                m10 += u * val;
-                m01 += v * val;
+    // ---- slot -> (level, index, output row) for this warp's 4 keypoints ----
+    int lv[OD_KPW], px[OD_KPW], py[OD_KPW], off[OD_KPW], sc[OD_KPW];
+#pragma unroll
+    for (int q = 0; q < OD_KPW; ++q) {
+        const int slot = blockIdx.x * OD_KPB + warp * OD_KPW + q;
+        lv[q] = -1; px[q] = py[q] = off[q] = sc[q] = 0;
+        if (slot < g.total_kp_slots) {
+            int l = 0;
+            while (l + 1 < g.nlevels && slot >= g.lv[l + 1].kp_base) ++l;
+            const int i = slot - g.lv[l].kp_base;
+            if (i < kc[l]) {
+                int o = i;
+                for (int k = 0; k < l; ++k) o += kc[k];
+                if (o < cap) {
+                    const unsigned long long rec = kept[(long long)f * g.total_kp_slots + slot];
+                    lv[q] = l; off[q] = o; sc[q] = corner_score(rec);
+                    px[q] = corner_x(rec) + ORB_MINB; py[q] = corner_y(rec) + ORB_MINB;   // ORBextractor.cc:881-882
+                }
             }
         }
     }
+    // ---- phase 1: IC_Angle moments (ORBextractor.cc:77-104) ----
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
-        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
-    }
-    const float angle = fast_atan2_deg((float)m01, (float)m10);
-
-    // ---- computeOrbDescriptor (ORBextractor.cc:106-147): lane i builds byte i ----
-    const float factorPI = (float)(3.1415926535897932384626433832795 / 180.0);  // (float)(CV_PI/180.f)
-    const float ang = __fmul_rn(angle, factorPI);
-    float a, b;
-    {   // pin (iii): a = (float)cos((double)ang), b = (float)sin((double)ang); lane 0 / lane 1 evaluate, then broadcast
-        float t = 0.f;
-        if (lane == 0) t = (float)cos((double)ang);
-        if (lane == 1) t = (float)sin((double)ang);
-        a = __shfl_sync(0xffffffffu, t, 0);
-        b = __shfl_sync(0xffffffffu, t, 1);
-    }
-    const uint8_t* bc = blur + L.bbase + (long long)f * L.bframe_stride + (long long)y * L.bpitch + x;
-    const int* pat = c_pattern + lane * 32;  // byte `lane` uses points 16*lane .. 16*lane+15 (2 ints each)
-    unsigned val = 0;
+    for (int q = 0; q < OD_KPW; ++q) {
+        int m10 = 0, m01 = 0;
+        if (lv[q] >= 0 && lane < 31) {
+            const LevelGeom& L = g.lv[lv[q]];
+            const int pitch = L.pitch;
+            const uint8_t* center = pyr + L.base + (long long)f * L.frame_stride + (ORB_EDGE + py[q]) * pitch + ORB_EDGE + px[q];
+            const int u = lane - ORB_HALF_PATCH;
+            const int au = abs(u);
+            int col = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const float x0 = (float)pat[4 * k], y0 = (float)pat[4 * k + 1];
-        const float x1 = (float)pat[4 * k + 2], y1 = (float)pat[4 * k + 3];
-        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
-        const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
-        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
-        const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-        const int t0 = bc[(long long)r0 * L.bpitch + c0], t1 = bc[(long long)r1 * L.bpitch + c1];
-        val |= (unsigned)(t0 < t1) << k;
+            for (int v = -ORB_HALF_PATCH; v <= ORB_HALF_PATCH; ++v) {
+                const int um = (v < 0 ? -v : v);
+                // umax = 15 15 15 15 14 14 14 13 13 12 11 10 9 8 6 3 (ORBextractor.cc:463-478), folded at compile time
+                const int lim = um <= 3 ? 15 : um <= 6 ? 14 : um <= 8 ? 13 : um == 9 ? 12 : um == 10 ? 11 : um == 11 ? 10 :
+                                um == 12 ? 9 : um == 13 ? 8 : um == 14 ? 6 : 3;
+                if (au <= lim) {
+                    const int val = center[v * pitch + u];
+                    col += val;
+                    m01 += v * val;
+                }
+            }
+            m10 = u * col;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+            m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+        }
+        if (lane == 0) { s_m[warp * OD_KPW + q][0] = m01; s_m[warp * OD_KPW + q][1] = m10; }
     }
-    // 32-byte descriptor row: gather 4 lanes' bytes into one word, 8 lanes store 8 words (one 32-B sector)
-    unsigned w = val;
-    w |= __shfl_down_sync(0xffffffffu, val, 1) << 8;
-    w |= __shfl_down_sync(0xffffffffu, val, 2) << 16;
-    w |= __shfl_down_sync(0xffffffffu, val, 3) << 24;
-    const long long o = (long long)f * cap + off;
-    if ((lane & 3) == 0) reinterpret_cast<unsigned*>(desc_out + o * 32)[lane >> 2] = w;
-    if (lane == 0) {
-        orb_kp kp;
-        kp.x = (l != 0) ? __fmul_rn((float)x, L.scale) : (float)x;   // ORBextractor.cc:1139-1145
-        kp.y = (l != 0) ? __fmul_rn((float)y, L.scale) : (float)y;
-        kp.size = L.size;
-        kp.angle = angle;
-        kp.response = (float)corner_score(rec);
-        kp.octave = l;
-        kp.class_id = -1;
-        kps_out[o] = kp;
+    __syncthreads();
+    // ---- phase 2: angle and steering coefficients, one lane per keypoint ----
+    if (warp == 0) {
+        const float angle = fast_atan2_deg((float)s_m[lane][0], (float)s_m[lane][1]);
+        const float factorPI = (float)(3.1415926535897932384626433832795 / 180.0);  // (float)(CV_PI/180.f)
+        const float ang = __fmul_rn(angle, factorPI);
+        double sn, cs;
+        sincos((double)ang, &sn, &cs);   // pin (iii): a = (float)cos((double)ang), b = (float)sin((double)ang)
+        s_ang[lane] = angle; s_a[lane] = (float)cs; s_b[lane] = (float)sn;
+    }
+    __syncthreads();
+    // ---- phase 3: computeOrbDescriptor (ORBextractor.cc:106-147): lane i builds byte i ----
+#pragma unroll
+    for (int q = 0; q < OD_KPW; ++q) {
+        if (lv[q] < 0) continue;   // warp-uniform
+        const int l = lv[q];
+        const LevelGeom& L = g.lv[l];
+        const int kq = warp * OD_KPW + q;
+        const float a = s_a[kq], b = s_b[kq];
+        const int bp = L.bpitch;
+        const uint8_t* bc = blur + L.bbase + (long long)f * L.bframe_stride + py[q] * bp + px[q];
+        unsigned val = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float4 pt = s_pat[k * 32 + lane];
+            const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(pt.x, b), __fmul_rn(pt.y, a)));
+            const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(pt.x, a), __fmul_rn(pt.y, b)));
+            const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(pt.z, b), __fmul_rn(pt.w, a)));
+            const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(pt.z, a), __fmul_rn(pt.w, b)));
+            const int t0 = bc[r0 * bp + c0], t1 = bc[r1 * bp + c1];
+            val |= (unsigned)(t0 < t1) << k;
+        }
+        // 32-byte descriptor row: gather 4 lanes' bytes into one word, 8 lanes store 8 words (one 32-B sector)
+        unsigned w = val;
+        w |= __shfl_down_sync(0xffffffffu, val, 1) << 8;
+        w |= __shfl_down_sync(0xffffffffu, val, 2) << 16;
+        w |= __shfl_down_sync(0xffffffffu, val, 3) << 24;
+        const long long o = (long long)f * cap + off[q];
+        if ((lane & 3) == 0) reinterpret_cast<unsigned*>(desc_out + o * 32)[lane >> 2] = w;
+        if (lane == 0) {
+            orb_kp kp;
+            kp.x = (l != 0) ? __fmul_rn((float)px[q], L.scale) : (float)px[q];   // ORBextractor.cc:1139-1145
+            kp.y = (l != 0) ? __fmul_rn((float)py[q], L.scale) : (float)py[q];
+            kp.size = L.size;
+            kp.angle = s_ang[kq];
+            kp.response = (float)sc[q];
+            kp.octave = l;
+            kp.class_id = -1;
+            kps_out[o] = kp;
+        }
     }
 }
 
@@ -667,8 +710,10 @@ __global__ void sincos_range_kernel(unsigned first_bits, long long n, float* __r
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float x = __uint_as_float(first_bits + (unsigned)i);
-    a[i] = (float)cos((double)x);
-    b[i] = (float)sin((double)x);
+    double sn, cs;
+    sincos((double)x, &sn, &cs);   // the same call as orient_describe_kernel phase 2
+    a[i] = (float)cs;
+    b[i] = (float)sn;
 }
 
 }  // namespace
@@ -739,7 +784,7 @@ int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int F, size_t row_stri
     }
     ORB_STAGE_MARK(4);
     {   // K4 + K6
-        orient_describe_kernel<<<dim3((g.total_kp_slots + OD_WARPS - 1) / OD_WARPS, F), OD_WARPS * 32, 0, st>>>(
+        orient_describe_kernel<<<dim3((g.total_kp_slots + OD_KPB - 1) / OD_KPB, F), OD_WARPS * 32, 0, st>>>(
             c->d_pyr, c->d_blur, c->d_kept, c->d_kept_count, d_kps, d_desc, cap, d_n_out, g);
         c->launches++;
     }
