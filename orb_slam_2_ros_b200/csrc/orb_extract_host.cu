@@ -35,11 +35,11 @@ inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 void free_geometry_buffers(orb_ctx* c) {
     cudaFree(c->d_in); cudaFree(c->d_pyr); cudaFree(c->d_blur); cudaFree(c->d_corners); cudaFree(c->d_node_of_key);
     cudaFree(c->d_corner_count); cudaFree(c->d_kept); cudaFree(c->d_kept_count); cudaFree(c->d_taps);
-    cudaFree(c->d_blur_tile_base); cudaFree(c->d_kps_out); cudaFree(c->d_desc_out); cudaFree(c->d_n_out);
+    cudaFree(c->d_wtaps); cudaFree(c->d_kps_out); cudaFree(c->d_desc_out); cudaFree(c->d_n_out);
     cudaFreeHost(c->h_kps); cudaFreeHost(c->h_desc); cudaFreeHost(c->h_n); cudaFreeHost(c->h_in);
     c->d_in = c->d_pyr = c->d_blur = nullptr; c->d_corners = nullptr; c->d_node_of_key = nullptr;
     c->d_corner_count = c->d_kept_count = nullptr; c->d_kept = nullptr; c->d_taps = nullptr;
-    c->d_blur_tile_base = nullptr; c->d_kps_out = nullptr; c->d_desc_out = nullptr; c->d_n_out = nullptr;
+    c->d_wtaps = nullptr; c->d_kps_out = nullptr; c->d_desc_out = nullptr; c->d_n_out = nullptr;
     c->h_kps = nullptr; c->h_desc = nullptr; c->h_n = nullptr; c->h_in = nullptr;
     c->in_bytes = c->h_in_bytes = 0; c->out_cap = 0;
     c->have_geom = false;
@@ -77,14 +77,16 @@ int build_geometry(orb_ctx* c, int w, int h) {
     g.nlevels = c->nlevels; g.w = w; g.h = h; g.ini_th = c->ini_th; g.min_th = c->min_th;
     const int F = c->max_batch;
     long long pyr_off = 0, blur_off = 0, corner_off = 0;
-    int cells = 0, kp_slots = 0, taps = 0, max_node_cap = 0;
+    int cells = 0, kp_slots = 0, taps = 0, wtaps = 0, max_node_cap = 0, fast_ctas = 0, border_items = 0, blur_items = 0;
     for (int l = 0; l < g.nlevels; ++l) {
         LevelGeom& L = g.lv[l];
         L.w = cv_round_f((float)w * c->inv_scale[l]);  // ORBextractor.cc:1159
         L.h = cv_round_f((float)h * c->inv_scale[l]);
         if (L.w > 4096 + 32 || L.h > 4096 + 32) { orb_set_error("image larger than 4128 px is not supported"); return ORB_ERR_INVALID; }
-        L.pitch = (int)round_up(L.w + 2 * ORB_EDGE, 64);
+        // row layout: [0,13) dead | [13,32) left border | [32, 32+w) interior (16-B aligned) | 19 right border | pad
+        L.pitch = (int)round_up(ORB_XOFF + L.w + ORB_EDGE, 64);
         L.rows = L.h + 2 * ORB_EDGE;
+        L.ioff = ORB_EDGE * L.pitch + ORB_XOFF;
         L.frame_stride = (long long)L.pitch * L.rows;
         L.base = pyr_off; pyr_off += L.frame_stride * F;
         L.bpitch = (int)round_up(L.w, 64);
@@ -101,6 +103,7 @@ int build_geometry(orb_ctx* c, int w, int h) {
         L.wCell = (int)ceilf(width / L.nCols); L.hCell = (int)ceilf(height / L.nRows);
         L.cell_base = cells; cells += L.nCols * L.nRows;
         if (L.nCols * L.nRows > 4096) { orb_set_error("more than 4096 cells per level is not supported"); return ORB_ERR_INVALID; }
+        if (L.wCell > 60 || L.hCell > 60) { orb_set_error("internal: cell larger than 60 px"); return ORB_ERR_INVALID; }
         L.quota = c->quota[l];
         // quadtree roots, ORBextractor.cc:566-568
         L.nIni = (int)roundf((float)(L.maxBX - ORB_MINB) / (L.maxBY - ORB_MINB));
@@ -127,21 +130,52 @@ int build_geometry(orb_ctx* c, int w, int h) {
         L.kp_base = kp_slots; kp_slots += L.node_cap;
         L.xtab = taps; taps += L.w;
         L.ytab = taps; taps += L.h;
+        L.xwtab = wtaps; wtaps += (L.w + 3) / 4;
         L.scale = c->scale[l];
         L.size = (float)(int)(ORB_PATCH * c->scale[l]);  // ORBextractor.cc:874
+        // FAST strips: one CTA = fast_G consecutive cells of one cell row (tile width fast_G * wCell + 6 <= 256)
+        const int gmax = std::max(1, 250 / L.wCell);
+        L.fast_groups = (L.nCols + gmax - 1) / gmax;
+        L.fast_G = (L.nCols + L.fast_groups - 1) / L.fast_groups;
+        L.fast_cta_base = fast_ctas; fast_ctas += L.nRows * L.fast_groups;
+        // border fill: all words of the 38 top/bottom rows + the left/right border words of the h interior rows
+        const int first_w = (ORB_XOFF - ORB_EDGE) / 4;                          // word holding byte 13
+        const int end_w = (ORB_XOFF + L.w + ORB_EDGE + 3) / 4;                   // one past the last border word
+        L.border_words = end_w - first_w;
+        const int right_first = (ORB_XOFF + L.w) / 4;
+        L.border_base = border_items;
+        border_items += 2 * ORB_EDGE * L.border_words + L.h * ((ORB_XOFF / 4 - first_w) + (end_w - right_first));
+        // blur: one thread = one output word x ORB_BLUR_ROWS rows
+        L.blur_wpr = (L.w + 3) / 4;
+        L.blur_base = blur_items; blur_items += L.blur_wpr * ((L.h + ORB_BLUR_ROWS - 1) / ORB_BLUR_ROWS);
     }
     if (max_node_cap > 65535) { orb_set_error("nfeatures too large"); return ORB_ERR_INVALID; }
     if ((size_t)max_node_cap * 80 > 200 * 1024) { orb_set_error("nfeatures too large for the quadtree kernel"); return ORB_ERR_INVALID; }
     g.total_cells = cells; g.total_kp_slots = kp_slots; g.max_node_cap = max_node_cap;
+    g.fast_ctas = fast_ctas; g.border_items = border_items; g.blur_items = blur_items;
     g.pyr_frame_total = pyr_off / F;
-    // resize taps
-    std::vector<ResizeTap> h_taps(taps);
+    // resize taps: per-column / per-row tables + the packed per-output-word table of the fast path
+    std::vector<ResizeTap> h_taps(std::max(taps, 1));
+    std::vector<ResizeWord> h_wtaps(std::max(wtaps, 1));
     for (int l = 1; l < g.nlevels; ++l) {
-        make_taps(g.lv[l - 1].w, g.lv[l].w, false, h_taps.data() + g.lv[l].xtab);
-        make_taps(g.lv[l - 1].h, g.lv[l].h, true, h_taps.data() + g.lv[l].ytab);
+        LevelGeom& L = g.lv[l];
+        ResizeTap* xt = h_taps.data() + L.xtab;
+        make_taps(g.lv[l - 1].w, L.w, false, xt);
+        make_taps(g.lv[l - 1].h, L.h, true, h_taps.data() + L.ytab);
+        L.fast_resize = 1;
+        for (int wc = 0; wc < (L.w + 3) / 4; ++wc) {
+            ResizeWord& rw = h_wtaps[L.xwtab + wc];
+            memset(&rw, 0, sizeof(rw));
+            rw.wb = xt[4 * wc].s0 >> 2;
+            for (int p = 0; p < 4; ++p) {
+                const ResizeTap& t = xt[std::min(4 * wc + p, L.w - 1)];
+                const int off = (int)t.s0 - 4 * rw.wb;
+                if (off < 0 || off > 7) L.fast_resize = 0;
+                rw.off |= (unsigned)(off & 0xFF) << (8 * p);
+                rw.cc[p] = (unsigned)(unsigned short)t.c0 | ((unsigned)(unsigned short)t.c1 << 16);
+            }
+        }
     }
-    int tile_base[ORB_MAX_LEVELS];
-    c->blur_tiles = orb_blur_tile_bases(g, tile_base);
 
     c->pyr_bytes = (size_t)pyr_off; c->blur_bytes = (size_t)blur_off; c->corner_elems = (size_t)corner_off;
     ORB_CUDA(cudaMalloc(&c->d_pyr, c->pyr_bytes + 256));
@@ -151,10 +185,10 @@ int build_geometry(orb_ctx* c, int w, int h) {
     ORB_CUDA(cudaMalloc(&c->d_corner_count, sizeof(int) * 2 * (size_t)F * g.nlevels));
     ORB_CUDA(cudaMalloc(&c->d_kept, sizeof(unsigned long long) * (size_t)F * kp_slots));
     ORB_CUDA(cudaMalloc(&c->d_kept_count, sizeof(int) * (size_t)F * g.nlevels));
-    ORB_CUDA(cudaMalloc(&c->d_taps, sizeof(ResizeTap) * (size_t)std::max(taps, 1)));
-    ORB_CUDA(cudaMalloc(&c->d_blur_tile_base, sizeof(int) * ORB_MAX_LEVELS));
-    ORB_CUDA(cudaMemcpyAsync(c->d_taps, h_taps.data(), sizeof(ResizeTap) * taps, cudaMemcpyHostToDevice, c->stream));
-    ORB_CUDA(cudaMemcpyAsync(c->d_blur_tile_base, tile_base, sizeof(int) * g.nlevels, cudaMemcpyHostToDevice, c->stream));
+    ORB_CUDA(cudaMalloc(&c->d_taps, sizeof(ResizeTap) * h_taps.size()));
+    ORB_CUDA(cudaMalloc(&c->d_wtaps, sizeof(ResizeWord) * h_wtaps.size()));
+    ORB_CUDA(cudaMemcpyAsync(c->d_taps, h_taps.data(), sizeof(ResizeTap) * h_taps.size(), cudaMemcpyHostToDevice, c->stream));
+    ORB_CUDA(cudaMemcpyAsync(c->d_wtaps, h_wtaps.data(), sizeof(ResizeWord) * h_wtaps.size(), cudaMemcpyHostToDevice, c->stream));
     ORB_CUDA(cudaMemsetAsync(c->d_pyr, 0, c->pyr_bytes + 256, c->stream));
     ORB_CUDA(cudaMemsetAsync(c->d_blur, 0, c->blur_bytes + 256, c->stream));
     ORB_CUDA(cudaMemsetAsync(c->d_kept_count, 0, sizeof(int) * (size_t)F * g.nlevels, c->stream));
@@ -441,7 +475,7 @@ int orb_pyramid_level(orb_ctx* c, int frame, int level, uint8_t* dst, size_t dst
     const int bw = L.w + 2 * ORB_EDGE;
     if (dst_stride < (size_t)bw) return ORB_ERR_INVALID;
     ORB_CUDA(cudaSetDevice(c->device));
-    ORB_CUDA(cudaMemcpy2DAsync(dst, dst_stride, c->d_pyr + L.base + (long long)frame * L.frame_stride, L.pitch, bw, L.rows,
+    ORB_CUDA(cudaMemcpy2DAsync(dst, dst_stride, c->d_pyr + L.base + (long long)frame * L.frame_stride + (ORB_XOFF - ORB_EDGE), L.pitch, bw, L.rows,
                                cudaMemcpyDeviceToHost, c->stream));
     ORB_CUDA(cudaStreamSynchronize(c->stream));
     return ORB_OK;

@@ -1,15 +1,15 @@
-// orb_extract_kernels.cu — sm_100a kernels of the ORB extractor (the replacement of
-// ORBextractor::operator(), reference orb_slam2/src/ORBextractor.cc:1083-1149).
+// orb_extract_kernels.cu — sm_100a kernels of the ORB extractor, part 2, and the launch sequence of
+// ORBextractor::operator() (reference orb_slam2/src/ORBextractor.cc:1083-1149).
 //
-// Stages (one launch each, batched over frames; blockIdx.z / blockIdx.y = frame):
-//   K1  pyr_level0_kernel / pyr_resize_kernel   ComputePyramid              ORBextractor.cc:1152-1185
-//   K2  fast_cells_kernel                       per-cell FAST + retry       ORBextractor.cc:820-863
-//   K3  quadtree_kernel                         DistributeOctTree           ORBextractor.cc:561-787
-//   K5  blur_kernel                             GaussianBlur 7x7 sigma 2    ORBextractor.cc:1129-1130
-//   K4+K6 orient_describe_kernel                IC_Angle + rBRIEF + output  ORBextractor.cc:77-147,1134-1147
+// Stages (batched over frames; blockIdx.y = frame):
+//   K1  orb_pyramid.cu   ComputePyramid                        ORBextractor.cc:1152-1185
+//   K2  orb_fast.cu      per-cell FAST + retry                 ORBextractor.cc:820-863
+//   K3  quadtree_kernel  DistributeOctTree                     ORBextractor.cc:561-787       (this file)
+//   K5  orb_blur.cu      GaussianBlur 7x7 sigma 2              ORBextractor.cc:1129-1130
+//   K4+K6 orient_describe_kernel  IC_Angle + rBRIEF + output   ORBextractor.cc:77-147,1134-1147 (this file)
 //
-// All arithmetic is integer or separately-rounded IEEE fp32 (file is compiled with -fmad=false) so the
-// results are bit-identical to the CPU reference semantics (OpenCV 4.13.0 primitives).
+// All arithmetic is integer or separately-rounded IEEE fp32 (compiled with -fmad=false) so the results are
+// bit-identical to the CPU reference semantics (OpenCV 4.13.0 primitives).
 #include "orb_internal.cuh"
 
 namespace {
@@ -18,218 +18,6 @@ __constant__ int c_pattern[1024] = {
 #include "orb_pattern_31.inc"
 };
 __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
-
-__device__ __forceinline__ int reflect101(int i, int n) {
-    // |i| < n guaranteed for a 19-px border on levels >= 20 px; loop keeps tiny levels correct
-    while (i < 0 || i >= n) i = (i < 0) ? -i : 2 * n - 2 - i;
-    return i;
-}
-
-// ======================================================================================================
-// K1a: level 0 = copyMakeBorder(image, 19, BORDER_REFLECT_101)
-// ======================================================================================================
-__global__ void __launch_bounds__(256)
-pyr_level0_kernel(const uint8_t* __restrict__ in, size_t row_stride, size_t frame_stride, uint8_t* __restrict__ pyr,
-                  const __grid_constant__ Geometry g) {
-    const LevelGeom& L = g.lv[0];
-    const int bx4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int by = blockIdx.y * blockDim.y + threadIdx.y;
-    const int f = blockIdx.z;
-    if (bx4 >= L.pitch || by >= L.rows) return;
-    const uint8_t* src = in + (size_t)f * frame_stride + (size_t)reflect101(by - ORB_EDGE, L.h) * row_stride;
-    unsigned v = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int bx = bx4 + i;
-        unsigned b = 0;
-        if (bx < L.w + 2 * ORB_EDGE) b = src[reflect101(bx - ORB_EDGE, L.w)];
-        v |= b << (8 * i);
-    }
-    *reinterpret_cast<unsigned*>(pyr + L.base + (long long)f * L.frame_stride + (long long)by * L.pitch + bx4) = v;
-}
-
-// ======================================================================================================
-// K1b: level l = resize(level l-1, INTER_LINEAR) + copyMakeBorder(REFLECT_101), fused:
-// each thread produces 4 bordered output bytes; a border pixel recomputes the interior pixel it mirrors.
-// Fixed-point recipe (OpenCV resize.cpp 8u path): Q11 taps horizontally, then
-//   out = (((b0*(H0>>4))>>16) + ((b1*(H1>>4))>>16) + 2) >> 2
-// ======================================================================================================
-__global__ void __launch_bounds__(256)
-pyr_resize_kernel(uint8_t* __restrict__ pyr, const ResizeTap* __restrict__ taps, int level,
-                  const __grid_constant__ Geometry g) {
-    const LevelGeom& L = g.lv[level];
-    const LevelGeom& P = g.lv[level - 1];
-    const int bx4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int by = blockIdx.y * blockDim.y + threadIdx.y;
-    const int f = blockIdx.z;
-    if (bx4 >= L.pitch || by >= L.rows) return;
-    const ResizeTap ty = taps[L.ytab + reflect101(by - ORB_EDGE, L.h)];
-    const uint8_t* S = pyr + P.base + (long long)f * P.frame_stride + (long long)ORB_EDGE * P.pitch + ORB_EDGE;
-    const uint8_t* r0 = S + (long long)ty.s0 * P.pitch;
-    const uint8_t* r1 = S + (long long)ty.s1 * P.pitch;
-    const int b0 = ty.c0, b1 = ty.c1;
-    unsigned v = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int bx = bx4 + i;
-        unsigned o = 0;
-        if (bx < L.w + 2 * ORB_EDGE) {
-            const ResizeTap tx = taps[L.xtab + reflect101(bx - ORB_EDGE, L.w)];
-            const int h0 = (int)__ldcg(r0 + tx.s0) * tx.c0 + (int)__ldcg(r0 + tx.s1) * tx.c1;
-            const int h1 = (int)__ldcg(r1 + tx.s0) * tx.c0 + (int)__ldcg(r1 + tx.s1) * tx.c1;
-            o = (unsigned)((((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2) & 0xFFu;
-        }
-        v |= o << (8 * i);
-    }
-    *reinterpret_cast<unsigned*>(pyr + L.base + (long long)f * L.frame_stride + (long long)by * L.pitch + bx4) = v;
-}
-
-// ======================================================================================================
-// tile loader: copies `rows` rows of `width` bytes starting at g (arbitrary alignment, row pitch gp a
-// multiple of 4 and base 4-aligned) into smem as aligned 32-bit words.  Returns the byte shift: global byte
-// (row r, col x) lands at s[r*sp + shift + x].
-// ======================================================================================================
-__device__ __forceinline__ int load_tile_u8(uint8_t* s, int sp, const uint8_t* gsrc, long long gp, int width, int rows) {
-    const int shift = (int)((uintptr_t)gsrc & 3);
-    const uint8_t* g0 = gsrc - shift;
-    const int words = (width + shift + 3) >> 2;
-    for (int i = threadIdx.x; i < rows * words; i += blockDim.x) {
-        const int r = i / words, wd = i - r * words;
-        const unsigned v = __ldg(reinterpret_cast<const unsigned*>(g0 + (long long)r * gp) + wd);
-        reinterpret_cast<unsigned*>(s + r * sp)[wd] = v;
-    }
-    return shift;
-}
-
-// ======================================================================================================
-// K2: per-cell FAST-9/16 + 3x3 NMS + iniThFAST/minThFAST retry.  One CTA per (cell, frame).
-//   score(p) = max( max_arc min_k (c - r_k), max_arc min_k (r_k - c) ) - 1  (16 arcs of 9 ring pixels);
-//   corner at threshold t <=> score >= t; NMS is confined to the cell's evaluated area, exactly like a
-//   cv::FAST call on the cell sub-image; the cell emits its NMS maxima with score >= iniThFAST if there is
-//   at least one, else those with score >= minThFAST (the reference's second FAST call).
-// ======================================================================================================
-#define FAST_TP 72        // smem pitch of the pixel tile  (cell sub-image width <= 66, + alignment shift)
-#define FAST_SP 64        // smem pitch of the score tile  (evaluated width <= 60, + 2 apron)
-#define FAST_THREADS 128
-
-__device__ __forceinline__ int fast_score16(int c, const int (&r)[16]) {
-    int mx3[16], mn3[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        mx3[k] = __vimax3_s32(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
-        mn3[k] = __vimin3_s32(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
-    }
-    int amin = 255, bmax = 0;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        amin = min(amin, __vimax3_s32(mx3[k], mx3[(k + 3) & 15], mx3[(k + 6) & 15]));
-        bmax = max(bmax, __vimin3_s32(mn3[k], mn3[(k + 3) & 15], mn3[(k + 6) & 15]));
-    }
-    return max(c - amin, bmax - c) - 1;
-}
-
-__global__ void __launch_bounds__(FAST_THREADS)
-fast_cells_kernel(const uint8_t* __restrict__ pyr, unsigned long long* __restrict__ corners,
-                  int* __restrict__ corner_count, const __grid_constant__ Geometry g) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    const int cell = blockIdx.x, f = blockIdx.y;
-    int l = 0;
-    while (l + 1 < g.nlevels && cell >= g.lv[l + 1].cell_base) ++l;
-    const LevelGeom& L = g.lv[l];
-    const int ci = cell - L.cell_base;
-    const int i = ci / L.nCols, j = ci - i * L.nCols;
-    // reference ORBextractor.cc:822-837 (all values are integers held in floats there)
-    const int iniY = ORB_MINB + i * L.hCell, iniX = ORB_MINB + j * L.wCell;
-    if (iniY >= L.maxBY - 3 || iniX >= L.maxBX - 6) return;
-    const int maxY = min(iniY + L.hCell + 6, L.maxBY), maxX = min(iniX + L.wCell + 6, L.maxBX);
-    const int cw = maxX - iniX, ch = maxY - iniY;
-    if (cw < 7 || ch < 7) return;  // cv::FAST returns nothing on such a sub-image
-    const int ew = cw - 6, eh = ch - 6, npx = ew * eh;
-
-    // smem carve-up
-    uint8_t* tile = smem;                                    // 66 x FAST_TP
-    uint8_t* score = tile + 66 * FAST_TP;                    // 62 x FAST_SP (1-px zero apron)
-    unsigned short* surv = reinterpret_cast<unsigned short*>(score + 62 * FAST_SP);  // <= 3600
-    unsigned long long* outl = reinterpret_cast<unsigned long long*>(surv + 3600);   // <= 900
-    __shared__ int s_nsurv, s_nout, s_base, s_any_ini;
-    if (threadIdx.x == 0) { s_nsurv = 0; s_nout = 0; s_any_ini = 0; }
-
-    const uint8_t* src = pyr + L.base + (long long)f * L.frame_stride + (long long)(ORB_EDGE + iniY) * L.pitch +
-                         ORB_EDGE + iniX;
-    const int shift = load_tile_u8(tile, FAST_TP, src, L.pitch, cw, ch);
-    for (int k = threadIdx.x; k < (eh + 2) * (FAST_SP / 4); k += blockDim.x) reinterpret_cast<unsigned*>(score)[k] = 0;
-    __syncthreads();
-
-    const int tmin = g.min_th, tini = g.ini_th;
-    // pass 1: quick reject at minThFAST — every opposite ring pair must hold a darker (brighter) pixel
-    for (int p = threadIdx.x; p < npx; p += blockDim.x) {
-        const int y = p / ew, x = p - y * ew;
-        const uint8_t* t = tile + (y + 3) * FAST_TP + shift + x + 3;
-        const int c = t[0], lo = c - tmin, hi = c + tmin;
-        int a = t[3 * FAST_TP], b = t[-3 * FAST_TP];               // ring 0, 8
-        bool dk = (a < lo) | (b < lo), br = (a > hi) | (b > hi);
-        if (dk | br) {
-            a = t[3]; b = t[-3];                                   // ring 4, 12
-            dk &= (a < lo) | (b < lo); br &= (a > hi) | (b > hi);
-            if (dk | br) {
-                a = t[2 * FAST_TP + 2]; b = t[-2 * FAST_TP - 2];   // ring 2, 10
-                dk &= (a < lo) | (b < lo); br &= (a > hi) | (b > hi);
-                a = t[-2 * FAST_TP + 2]; b = t[2 * FAST_TP - 2];   // ring 6, 14
-                dk &= (a < lo) | (b < lo); br &= (a > hi) | (b > hi);
-                if (dk | br) surv[atomicAdd(&s_nsurv, 1)] = (unsigned short)p;
-            }
-        }
-    }
-    __syncthreads();
-    const int nsurv = s_nsurv;
-    // pass 2: exact score of the survivors
-    for (int s = threadIdx.x; s < nsurv; s += blockDim.x) {
-        const int p = surv[s];
-        const int y = p / ew, x = p - y * ew;
-        const uint8_t* t = tile + (y + 3) * FAST_TP + shift + x + 3;
-        int r[16];
-        r[0] = t[3 * FAST_TP];       r[1] = t[3 * FAST_TP + 1];   r[2] = t[2 * FAST_TP + 2];   r[3] = t[FAST_TP + 3];
-        r[4] = t[3];                 r[5] = t[-FAST_TP + 3];      r[6] = t[-2 * FAST_TP + 2];  r[7] = t[-3 * FAST_TP + 1];
-        r[8] = t[-3 * FAST_TP];      r[9] = t[-3 * FAST_TP - 1];  r[10] = t[-2 * FAST_TP - 2]; r[11] = t[-FAST_TP - 3];
-        r[12] = t[-3];               r[13] = t[FAST_TP - 3];      r[14] = t[2 * FAST_TP - 2];  r[15] = t[3 * FAST_TP - 1];
-        const int sc = fast_score16(t[0], r);
-        if (sc >= tmin) score[(y + 1) * FAST_SP + x + 1] = (uint8_t)sc;
-    }
-    __syncthreads();
-    // pass 3: 3x3 NMS (strict >, neighbours outside the evaluated area count as 0)
-    unsigned maxmask = 0;  // bit k: survivor threadIdx.x + k*blockDim.x is an NMS maximum
-    bool any_ini = false;
-    for (int s = threadIdx.x, k = 0; s < nsurv; s += blockDim.x, ++k) {
-        const int p = surv[s];
-        const int y = p / ew, x = p - y * ew;
-        const uint8_t* q = score + (y + 1) * FAST_SP + x + 1;
-        const int sc = q[0];
-        if (sc != 0 && sc > q[-1] && sc > q[1] && sc > q[-FAST_SP - 1] && sc > q[-FAST_SP] && sc > q[-FAST_SP + 1] &&
-            sc > q[FAST_SP - 1] && sc > q[FAST_SP] && sc > q[FAST_SP + 1]) {
-            maxmask |= 1u << k;
-            any_ini |= (sc >= tini);
-        }
-    }
-    if (any_ini) s_any_ini = 1;
-    __syncthreads();
-    const int th = s_any_ini ? tini : tmin;
-    for (int s = threadIdx.x, k = 0; s < nsurv; s += blockDim.x, ++k) {
-        if (!((maxmask >> k) & 1u)) continue;
-        const int p = surv[s];
-        const int y = p / ew, x = p - y * ew;
-        const int sc = score[(y + 1) * FAST_SP + x + 1];
-        if (sc < th) continue;
-        // keypoint position in vToDistributeKeys coordinates (ORBextractor.cc:856-857)
-        outl[atomicAdd(&s_nout, 1)] = corner_pack(x + 3 + j * L.wCell, y + 3 + i * L.hCell, sc, (ci << 12) | (y << 6) | x);
-    }
-    __syncthreads();
-    const int nout = s_nout;
-    if (nout == 0) return;
-    if (threadIdx.x == 0) s_base = atomicAdd(&corner_count[f * g.nlevels + l], nout);
-    __syncthreads();
-    unsigned long long* dst = corners + L.corner_base + (long long)f * L.corner_cap + s_base;
-    for (int k = threadIdx.x; k < nout; k += blockDim.x) dst[k] = outl[k];
-}
 
 // ======================================================================================================
 // K3: DistributeOctTree as block-wide scans.  One CTA per (level, frame).
@@ -491,56 +279,6 @@ quadtree_kernel(const unsigned long long* __restrict__ corners, const int* __res
 }
 
 // ======================================================================================================
-// K5: GaussianBlur(7x7, sigma 2) — OpenCV >= 4 fixed-point path: Q8 kernel [18 34 48 56 48 34 18],
-// horizontal pass exact in 16 bits, vertical pass rounded (V + 32768) >> 16.  Reads the bordered pyramid
-// (whose 19-px reflect-101 border IS the blur's BORDER_REFLECT_101), writes the w x h blurred level.
-// ======================================================================================================
-#define BL_TW 64
-#define BL_TH 32
-#define BL_TP 76   // (BL_TW + 6 + 3 alignment) rounded up to a multiple of 4
-#define BL_THREADS 256
-
-__global__ void __launch_bounds__(BL_THREADS)
-blur_kernel(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur, const int* __restrict__ tile_level_base,
-            const __grid_constant__ Geometry g) {
-    __shared__ __align__(16) uint8_t tile[(BL_TH + 6) * BL_TP];
-    __shared__ __align__(16) unsigned short hbuf[(BL_TH + 6) * BL_TW];
-    const int t = blockIdx.x, f = blockIdx.y;
-    int l = 0;
-    while (l + 1 < g.nlevels && t >= tile_level_base[l + 1]) ++l;
-    const LevelGeom& L = g.lv[l];
-    const int tl = t - tile_level_base[l];
-    const int tiles_x = (L.w + BL_TW - 1) / BL_TW;
-    const int ty = tl / tiles_x, tx = tl - ty * tiles_x;
-    const int x0 = tx * BL_TW, y0 = ty * BL_TH;
-    const int tw = min(BL_TW, L.w - x0), th = min(BL_TH, L.h - y0);
-    const uint8_t* src = pyr + L.base + (long long)f * L.frame_stride + (long long)(ORB_EDGE + y0 - 3) * L.pitch +
-                         ORB_EDGE + x0 - 3;
-    const int shift = load_tile_u8(tile, BL_TP, src, L.pitch, tw + 6, th + 6);
-    __syncthreads();
-    for (int i = threadIdx.x; i < (th + 6) * tw; i += blockDim.x) {
-        const int r = i / tw, x = i - r * tw;
-        const uint8_t* p = tile + r * BL_TP + shift + x;
-        hbuf[r * BL_TW + x] = (unsigned short)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
-    }
-    __syncthreads();
-    uint8_t* dst = blur + L.bbase + (long long)f * L.bframe_stride + (long long)y0 * L.bpitch + x0;
-    const int tw4 = (tw + 3) >> 2;
-    for (int i = threadIdx.x; i < th * tw4; i += blockDim.x) {
-        const int r = i / tw4, x4 = (i - r * tw4) * 4;
-        unsigned v = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const unsigned short* h = hbuf + r * BL_TW + x4 + k;   // columns >= tw hold stale data, masked by pitch
-            const unsigned acc = 18u * (h[0] + h[6 * BL_TW]) + 34u * (h[BL_TW] + h[5 * BL_TW]) +
-                                 48u * (h[2 * BL_TW] + h[4 * BL_TW]) + 56u * h[3 * BL_TW];
-            v |= ((acc + 32768u) >> 16) << (8 * k);
-        }
-        *reinterpret_cast<unsigned*>(dst + (long long)r * L.bpitch + x4) = v;  // bpitch, x0 multiples of 4
-    }
-}
-
-// ======================================================================================================
 // K4 + K6: one warp per kept keypoint: IC_Angle (integer moments + fastAtan2 polynomial), rBRIEF-256 on
 // the blurred level, coordinate scaling and the final KeyPoint / descriptor rows in level-major order.
 // ======================================================================================================
@@ -626,7 +364,7 @@ orient_describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restric
         if (lv[q] >= 0 && lane < 31) {
             const LevelGeom& L = g.lv[lv[q]];
             const int pitch = L.pitch;
-            const uint8_t* center = pyr + L.base + (long long)f * L.frame_stride + (ORB_EDGE + py[q]) * pitch + ORB_EDGE + px[q];
+            const uint8_t* center = pyr + L.base + (long long)f * L.frame_stride + L.ioff + py[q] * pitch + px[q];
             const int u = lane - ORB_HALF_PATCH;
             const int au = abs(u);
             int col = 0;
@@ -752,24 +490,9 @@ int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int F, size_t row_stri
     ORB_CUDA(cudaMemsetAsync(c->d_corner_count, 0, sizeof(int) * 2 * (size_t)c->max_batch * g.nlevels, st));
     int* d_tie = c->d_corner_count + (size_t)c->max_batch * g.nlevels;  // second half: tie-at-cut counters
     ORB_STAGE_MARK(0);
-    {   // K1
-        const LevelGeom& L = g.lv[0];
-        dim3 blk(64, 4), grd((L.pitch / 4 + 63) / 64, (L.rows + 3) / 4, F);
-        pyr_level0_kernel<<<grd, blk, 0, st>>>(d_imgs, row_stride, frame_stride, c->d_pyr, g);
-        c->launches++;
-        for (int l = 1; l < g.nlevels; ++l) {
-            const LevelGeom& Ll = g.lv[l];
-            dim3 grd2((Ll.pitch / 4 + 63) / 64, (Ll.rows + 3) / 4, F);
-            pyr_resize_kernel<<<grd2, blk, 0, st>>>(c->d_pyr, c->d_taps, l, g);
-            c->launches++;
-        }
-    }
+    { int rc = orb_launch_pyramid(c, d_imgs, F, row_stride, frame_stride); if (rc != ORB_OK) return rc; }   // K1
     ORB_STAGE_MARK(1);
-    {   // K2
-        const size_t smem = 66 * FAST_TP + 62 * FAST_SP + 3600 * 2 + 900 * 8;
-        fast_cells_kernel<<<dim3(g.total_cells, F), FAST_THREADS, smem, st>>>(c->d_pyr, c->d_corners, c->d_corner_count, g);
-        c->launches++;
-    }
+    { int rc = orb_launch_fast(c, F); if (rc != ORB_OK) return rc; }                                         // K2
     ORB_STAGE_MARK(2);
     {   // K3
         const size_t smem = (size_t)g.max_node_cap * 80;
@@ -778,10 +501,7 @@ int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int F, size_t row_stri
         c->launches++;
     }
     ORB_STAGE_MARK(3);
-    {   // K5
-        blur_kernel<<<dim3(c->blur_tiles, F), BL_THREADS, 0, st>>>(c->d_pyr, c->d_blur, c->d_blur_tile_base, g);
-        c->launches++;
-    }
+    { int rc = orb_launch_blur(c, F); if (rc != ORB_OK) return rc; }                                         // K5
     ORB_STAGE_MARK(4);
     {   // K4 + K6
         orient_describe_kernel<<<dim3((g.total_kp_slots + OD_KPB - 1) / OD_KPB, F), OD_WARPS * 32, 0, st>>>(
@@ -794,13 +514,3 @@ int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int F, size_t row_stri
     return ORB_OK;
 }
 
-int orb_blur_tile_bases(const Geometry& g, int* bases) {
-    int tot = 0;
-    for (int l = 0; l < g.nlevels; ++l) {
-        bases[l] = tot;
-        tot += ((g.lv[l].w + BL_TW - 1) / BL_TW) * ((g.lv[l].h + BL_TH - 1) / BL_TH);
-    }
-    return tot;
-}
-
-int orb_fast_smem_bytes() { return 66 * FAST_TP + 62 * FAST_SP + 3600 * 2 + 900 * 8; }

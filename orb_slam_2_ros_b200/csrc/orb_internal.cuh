@@ -13,6 +13,7 @@
 #define ORB_MINB 16        // EDGE_THRESHOLD-3 (reference ORBextractor.cc:801)
 #define ORB_HALF_PATCH 15  // reference ORBextractor.cc:71
 #define ORB_PATCH 31       // reference ORBextractor.cc:70
+#define ORB_XOFF 32        // byte offset of interior pixel x = 0 inside a pyramid row (border occupies [13, 32))
 #define ORB_NSTAGES 5      // pyramid, FAST cells, quadtree, blur, orientation+descriptors
 #define ORB_PROF_RING 64
 
@@ -31,8 +32,9 @@ void orb_set_error(const char* fmt, ...);
 // per-level geometry, passed BY VALUE to kernels (lives in the constant bank) ---------------------------
 struct LevelGeom {
     int w, h;                  // interior size of mvImagePyramid[l]
-    int pitch, rows;           // bordered buffer: pitch bytes per row, rows = h + 38
-    long long base;            // byte offset of frame 0 of this level in the pyramid arena
+    int pitch, rows;           // bordered buffer: pitch bytes per row (multiple of 64), rows = h + 38
+    int ioff;                  // byte offset of interior pixel (0,0) from the frame's level base: 19 * pitch + ORB_XOFF
+    long long base;            // byte offset of frame 0 of this level in the pyramid arena (256-B aligned)
     long long frame_stride;    // pitch * rows
     int bpitch;                // blurred buffer pitch (w x h, no border)
     long long bbase, bframe_stride;
@@ -46,6 +48,13 @@ struct LevelGeom {
     int node_cap;              // max quadtree list length (+ slack)
     int kp_base;               // offset of this level's slots in a frame's kept-keypoint array
     int xtab, ytab;            // offsets into the resize tables (entries of ResizeTap)
+    int xwtab;                 // offset (entries of ResizeWord) of the packed per-output-word column table
+    int fast_resize;           // 1: every output word's source taps fit 3 aligned source words (scale <= 4/3)
+    int fast_G, fast_groups;   // FAST strips: cells per CTA, CTAs per cell row
+    int fast_cta_base;         // number of FAST CTAs of levels < l (per frame)
+    int border_base;           // number of border-fill items (words) of levels < l (per frame)
+    int border_words;          // words per bordered row that the border kernel may touch
+    int blur_base, blur_wpr;   // blur: number of thread items of levels < l; words per row
     float scale;               // mvScaleFactor[l]
     float size;                // (float)(int)(PATCH_SIZE * scale)
 };
@@ -54,6 +63,7 @@ struct Geometry {
     int nlevels, w, h;
     int ini_th, min_th;
     int total_cells, total_kp_slots, max_node_cap, max_tile_bytes;
+    int fast_ctas, border_items, blur_items;   // per-frame grid sizes of the strip / border / blur kernels
     long long pyr_frame_total;   // not used for addressing (level-major layout), informational
     LevelGeom lv[ORB_MAX_LEVELS];
 };
@@ -62,6 +72,14 @@ struct ResizeTap {  // one destination coordinate of resize(INTER_LINEAR): two s
     unsigned short s0, s1;
     short c0, c1;
 };
+struct __align__(16) ResizeWord {  // 4 adjacent destination columns (one output word) of the fast resize path
+    int wb;              // index of the first aligned source word
+    unsigned off;        // byte offset (0..7) of each column's left tap inside (word wb, wb+1, wb+2), 8 bits each
+    unsigned cc[4];      // c0 | c1 << 16 per column (Q11)
+    int pad[2];
+};
+#define ORB_BLUR_ROWS 16   // output rows per blur thread
+#define ORB_RESIZE_ROWS 8  // output rows per resize thread
 
 // 64-bit corner record: max() over records picks the reference's winner inside a quadtree node:
 //   hi 32 bits = score << 24 | (0xFFFFFF - order)   order = (cell index << 12 | y_in_cell << 6 | x_in_cell)
@@ -98,7 +116,8 @@ struct orb_ctx {
     unsigned long long* d_kept = nullptr;               // [max_batch][total_kp_slots]
     int* d_kept_count = nullptr;                        // [max_batch][nlevels]
     ResizeTap* d_taps = nullptr;
-    int* d_blur_tile_base = nullptr; int blur_tiles = 0;
+    ResizeWord* d_wtaps = nullptr;
+    bool fast_attr_set = false;
     orb_kp* d_kps_out = nullptr; uint8_t* d_desc_out = nullptr; int* d_n_out = nullptr; int out_cap = 0;
     orb_kp* h_kps = nullptr; uint8_t* h_desc = nullptr; int* h_n = nullptr; uint8_t* h_in = nullptr;  // pinned
     size_t h_in_bytes = 0;
@@ -115,7 +134,8 @@ struct orb_ctx {
 int orb_profile_harvest(orb_ctx* c, int slot);
 
 // kernels' launchers (orb_extract_kernels.cu)
-int orb_blur_tile_bases(const Geometry& g, int* bases);
-int orb_fast_smem_bytes();
+int orb_launch_pyramid(orb_ctx* c, const uint8_t* d_imgs, int nframes, size_t row_stride, size_t frame_stride);
+int orb_launch_fast(orb_ctx* c, int nframes);
+int orb_launch_blur(orb_ctx* c, int nframes);
 int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int nframes, size_t row_stride, size_t frame_stride,
                        orb_kp* d_kps, uint8_t* d_desc, int cap, int* d_n_out);

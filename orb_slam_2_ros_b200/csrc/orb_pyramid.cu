@@ -1,0 +1,205 @@
+// orb_pyramid.cu — K1: ORBextractor::ComputePyramid (reference orb_slam2/src/ORBextractor.cc:1152-1185) for sm_100a.
+//
+//   level 0      = copyMakeBorder(image, 19, BORDER_REFLECT_101)                        ORBextractor.cc:1180
+//   level l >= 1 = resize(level l-1, INTER_LINEAR) + copyMakeBorder(19, REFLECT_101)    ORBextractor.cc:1171-1175
+//
+// Data layout: every level of every frame is a bordered u8 image of (h + 38) rows with a
+// 64-byte-multiple pitch; interior pixel (0,0) sits at byte ORB_XOFF = 32 of row 19, so interior rows are
+// 16-byte aligned and all kernels work on aligned 32-bit words of 4 pixels.
+//
+// Launch chain per batch: pyr_copy0 (interior of level 0) -> 7 x pyr_resize (interior of level l from the stored
+// u8 interior of level l-1: a true dependency, OpenCV's fixed-point result is defined on the rounded level) ->
+// pyr_border (the 19-px reflect-101 frame of ALL levels in one launch; nothing in the chain reads a border).
+//
+// Resize arithmetic = OpenCV resize.cpp 8u INTER_LINEAR: Q11 column taps (c0,c1), Q11 row taps (b0,b1),
+//   H = S[s]*c0 + S[s+1]*c1 ;  out = (((b0*(H0>>4))>>16) + ((b1*(H1>>4))>>16) + 2) >> 2
+// The fast path computes one output word (4 px) x ORB_RESIZE_ROWS rows per thread: 3 aligned source words per
+// source row, the two taps of a column picked with a funnel shift and multiplied with IDP.2A (__dp2a_lo), and the
+// horizontal result of the lower source row is reused as the upper row of the next output row when they coincide.
+#include "orb_internal.cuh"
+
+namespace {
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+    // |i| < n guaranteed for a 19-px border on levels >= 20 px; the loop keeps tiny levels correct
+    while (i < 0 || i >= n) i = (i < 0) ? -i : 2 * n - 2 - i;
+    return i;
+}
+
+// ---- level 0 interior: 16 bytes per thread -------------------------------------------------------------
+template <bool ALIGNED>
+__global__ void __launch_bounds__(256)
+pyr_copy0_kernel(const uint8_t* __restrict__ in, size_t row_stride, size_t frame_stride, uint8_t* __restrict__ pyr,
+                 const __grid_constant__ Geometry g) {
+    const LevelGeom& L = g.lv[0];
+    const int vpr = (L.w + 15) >> 4;                       // 16-byte vectors per row
+    const int item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= vpr * L.h) return;
+    const int y = item / vpr, x = (item - y * vpr) << 4;
+    const int f = blockIdx.y;
+    const uint8_t* src = in + (size_t)f * frame_stride + (size_t)y * row_stride + x;
+    uint4 v;
+    if (ALIGNED && x + 16 <= L.w) {
+        v = __ldg(reinterpret_cast<const uint4*>(src));
+    } else {
+        unsigned wv[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            if (x + k < L.w) wv[k >> 2] |= (unsigned)__ldg(src + k) << (8 * (k & 3));
+        v = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+    }
+    // bytes past w land in the right border and are rewritten by pyr_border_kernel
+    *reinterpret_cast<uint4*>(pyr + L.base + (long long)f * L.frame_stride + L.ioff + y * L.pitch + x) = v;
+}
+
+// ---- fast resize: one output word x ORB_RESIZE_ROWS rows per thread ------------------------------------
+__device__ __forceinline__ void hrow4(const unsigned* __restrict__ srow, const ResizeWord& t, unsigned (&h)[4]) {
+    const unsigned w0 = __ldg(srow + t.wb), w1 = __ldg(srow + t.wb + 1), w2 = __ldg(srow + t.wb + 2);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const unsigned off = (t.off >> (8 * p)) & 0xFFu;          // 0..7
+        const unsigned lo = off < 4 ? w0 : w1, hi = off < 4 ? w1 : w2;
+        const unsigned pair = __funnelshift_r(lo, hi, (off & 3u) * 8u);   // byte0 = S[s], byte1 = S[s+1]
+        h[p] = __dp2a_lo(t.cc[p], pair, 0u);                       // c0*S[s] + c1*S[s+1]
+    }
+}
+
+__global__ void __launch_bounds__(256)
+pyr_resize_fast_kernel(uint8_t* __restrict__ pyr, const ResizeTap* __restrict__ taps, const ResizeWord* __restrict__ wtaps,
+                       int level, const __grid_constant__ Geometry g) {
+    const LevelGeom& L = g.lv[level];
+    const LevelGeom& P = g.lv[level - 1];
+    const int wpr = (L.w + 3) >> 2;
+    const int item = blockIdx.x * blockDim.x + threadIdx.x;
+    const int strips = (L.h + ORB_RESIZE_ROWS - 1) / ORB_RESIZE_ROWS;
+    if (item >= wpr * strips) return;
+    const int strip = item / wpr, wc = item - strip * wpr;
+    const int f = blockIdx.y;
+    const ResizeWord t = wtaps[L.xwtab + wc];
+    const uint8_t* S = pyr + P.base + (long long)f * P.frame_stride + P.ioff;    // 16-byte aligned
+    uint8_t* D = pyr + L.base + (long long)f * L.frame_stride + L.ioff + 4 * wc;
+    const int y0 = strip * ORB_RESIZE_ROWS, y1 = min(y0 + ORB_RESIZE_ROWS, L.h);
+    unsigned h0[4], h1[4];
+    int have1 = -1;                                       // source row whose horizontal pass sits in h1
+    for (int y = y0; y < y1; ++y) {
+        const ResizeTap ty = taps[L.ytab + y];
+        if ((int)ty.s0 == have1) {
+#pragma unroll
+            for (int p = 0; p < 4; ++p) h0[p] = h1[p];
+        } else {
+            hrow4(reinterpret_cast<const unsigned*>(S + (int)ty.s0 * P.pitch), t, h0);
+        }
+        if (ty.s1 == ty.s0) {
+#pragma unroll
+            for (int p = 0; p < 4; ++p) h1[p] = h0[p];
+        } else {
+            hrow4(reinterpret_cast<const unsigned*>(S + (int)ty.s1 * P.pitch), t, h1);
+        }
+        have1 = ty.s1;
+        const int b0 = ty.c0, b1 = ty.c1;
+        unsigned v = 0;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int o = (((b0 * (int)(h0[p] >> 4)) >> 16) + ((b1 * (int)(h1[p] >> 4)) >> 16) + 2) >> 2;
+            v |= (unsigned)o << (8 * p);                  // 0 <= o <= 255
+        }
+        *reinterpret_cast<unsigned*>(D + y * L.pitch) = v;
+    }
+}
+
+// ---- generic resize (any scale factor): one output word per thread, per-pixel taps -----------------------
+__global__ void __launch_bounds__(256)
+pyr_resize_generic_kernel(uint8_t* __restrict__ pyr, const ResizeTap* __restrict__ taps, int level,
+                          const __grid_constant__ Geometry g) {
+    const LevelGeom& L = g.lv[level];
+    const LevelGeom& P = g.lv[level - 1];
+    const int wpr = (L.w + 3) >> 2;
+    const int item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= wpr * L.h) return;
+    const int y = item / wpr, x4 = (item - y * wpr) << 2;
+    const int f = blockIdx.y;
+    const ResizeTap ty = taps[L.ytab + y];
+    const uint8_t* S = pyr + P.base + (long long)f * P.frame_stride + P.ioff;
+    const uint8_t* r0 = S + (int)ty.s0 * P.pitch;
+    const uint8_t* r1 = S + (int)ty.s1 * P.pitch;
+    const int b0 = ty.c0, b1 = ty.c1;
+    unsigned v = 0;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const ResizeTap tx = taps[L.xtab + min(x4 + p, L.w - 1)];
+        const int h0 = (int)r0[tx.s0] * tx.c0 + (int)r0[tx.s1] * tx.c1;
+        const int h1 = (int)r1[tx.s0] * tx.c0 + (int)r1[tx.s1] * tx.c1;
+        v |= (unsigned)((((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2) << (8 * p);
+    }
+    *reinterpret_cast<unsigned*>(pyr + L.base + (long long)f * L.frame_stride + L.ioff + y * L.pitch + x4) = v;
+}
+
+// ---- the 19-px BORDER_REFLECT_101 frame of every level, one launch ---------------------------------------
+__global__ void __launch_bounds__(256)
+pyr_border_kernel(uint8_t* __restrict__ pyr, const __grid_constant__ Geometry g) {
+    const int item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= g.border_items) return;
+    int l = 0;
+    while (l + 1 < g.nlevels && item >= g.lv[l + 1].border_base) ++l;
+    const LevelGeom& L = g.lv[l];
+    const int f = blockIdx.y;
+    int it = item - L.border_base;
+    const int first_w = (ORB_XOFF - ORB_EDGE) / 4;
+    const int nbw = L.border_words;
+    int row, word;
+    if (it < 2 * ORB_EDGE * nbw) {                       // top / bottom rows: every word of the bordered row
+        const int r = it / nbw;
+        word = first_w + (it - r * nbw);
+        row = r < ORB_EDGE ? r : L.h + r;                // r in [19, 38) -> rows h+19 .. h+37
+    } else {                                              // interior rows: left and right border words only
+        it -= 2 * ORB_EDGE * nbw;
+        const int nleft = ORB_XOFF / 4 - first_w;
+        const int right_first = (ORB_XOFF + L.w) / 4;
+        const int per_row = nleft + (first_w + nbw - right_first);
+        const int r = it / per_row, k = it - r * per_row;
+        row = ORB_EDGE + r;
+        word = k < nleft ? first_w + k : right_first + (k - nleft);
+    }
+    uint8_t* img = pyr + L.base + (long long)f * L.frame_stride;
+    const uint8_t* srow = img + L.ioff + reflect101(row - ORB_EDGE, L.h) * L.pitch;
+    unsigned v = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int q = 4 * word + k;                       // byte position in the row
+        if (q >= ORB_XOFF - ORB_EDGE && q < ORB_XOFF + L.w + ORB_EDGE)
+            v |= (unsigned)srow[reflect101(q - ORB_XOFF, L.w)] << (8 * k);   // identity on interior bytes
+    }
+    *reinterpret_cast<unsigned*>(img + row * L.pitch + 4 * word) = v;
+}
+
+}  // namespace
+
+int orb_launch_pyramid(orb_ctx* c, const uint8_t* d_imgs, int F, size_t row_stride, size_t frame_stride) {
+    const Geometry& g = c->g;
+    cudaStream_t st = c->stream;
+    {
+        const LevelGeom& L = g.lv[0];
+        const int items = ((L.w + 15) >> 4) * L.h;
+        const bool aligned = ((((uintptr_t)d_imgs) | row_stride | frame_stride) & 15) == 0;
+        dim3 grd((items + 255) / 256, F);
+        if (aligned) pyr_copy0_kernel<true><<<grd, 256, 0, st>>>(d_imgs, row_stride, frame_stride, c->d_pyr, g);
+        else pyr_copy0_kernel<false><<<grd, 256, 0, st>>>(d_imgs, row_stride, frame_stride, c->d_pyr, g);
+        c->launches++;
+    }
+    for (int l = 1; l < g.nlevels; ++l) {
+        const LevelGeom& L = g.lv[l];
+        const int wpr = (L.w + 3) >> 2;
+        if (L.fast_resize) {
+            const int items = wpr * ((L.h + ORB_RESIZE_ROWS - 1) / ORB_RESIZE_ROWS);
+            pyr_resize_fast_kernel<<<dim3((items + 255) / 256, F), 256, 0, st>>>(c->d_pyr, c->d_taps, c->d_wtaps, l, g);
+        } else {
+            const int items = wpr * L.h;
+            pyr_resize_generic_kernel<<<dim3((items + 255) / 256, F), 256, 0, st>>>(c->d_pyr, c->d_taps, l, g);
+        }
+        c->launches++;
+    }
+    pyr_border_kernel<<<dim3((g.border_items + 255) / 256, F), 256, 0, st>>>(c->d_pyr, g);
+    c->launches++;
+    ORB_CUDA(cudaGetLastError());
+    return ORB_OK;
+}

@@ -74,8 +74,8 @@ stereo_match_kernel(const uint8_t* __restrict__ pyrL, const uint8_t* __restrict_
     const float endu = __fadd_rn(__fadd_rn(__fadd_rn(scaleduR0, (float)Lh), (float)w), 1.0f);
     if (iniu < 0 || endu >= (float)G.w) return;
     const int y0 = (int)(scaledvL - w), xl0 = (int)(scaleduL - w), xr0 = (int)(scaleduR0 - w);
-    const uint8_t* PL = pyrL + G.base + (long long)ORB_EDGE * G.pitch + ORB_EDGE;  // frame 0 interior
-    const uint8_t* PR = pyrR + G.base + (long long)ORB_EDGE * G.pitch + ORB_EDGE;
+    const uint8_t* PL = pyrL + G.base + G.ioff;  // frame 0 interior
+    const uint8_t* PR = pyrR + G.base + G.ioff;
     const int cL = PL[(long long)(y0 + w) * G.pitch + xl0 + w];
     // each lane owns up to 4 of the 121 patch pixels
     int il[4], py[4], px[4];
