@@ -14,40 +14,54 @@
 // memory).  Threads work on aligned 32-bit words of 4 pixels:
 //   pass 1a direction-aware quick reject, 2 pixels per instruction on s16x2 lanes (VIMNMX.S16x2): a bright (dark)
 //           9-arc holds one pixel of each antipodal ring pair, so  min over the 4 axis/diagonal pairs of
-//           max(r_k, r_k+8) > c + t  (resp. max of min < c - t) is necessary; survivors are compacted into a
-//           shared-memory candidate list
-//   pass 1b exact 16-pixel score (VIMNMX3 trees) of the candidates, all lanes busy -> u8 score tile
-//   pass 2  cells decide their threshold: any NMS maximum with score >= iniThFAST?
+//           max(r_k, r_k+8) > c + t  (resp. max of min < c - t) is necessary.  Every lane keeps a 64-bit mask of
+//           its candidates; each WARP compacts its masks once into a private shared-memory segment
+//   pass 1b exact 16-pixel score of the warp's candidates, all lanes busy; both polarities in one s16x2 tree on
+//           (r, 255 - r) pairs -> u8 score tile + CTA-wide list of scored corners (score >= minThFAST)
+//   pass 2  NMS over the scored list (dense); cells decide their threshold: any NMS maximum >= iniThFAST?
 //   pass 3  NMS maxima with score >= the cell's threshold -> shared-memory record list -> one global atomicAdd per
 //           CTA -> coalesced copy into the level's corner list (record = corner_pack(x, y, score, order key)).
+// Capacity overflows (pathological images only) fall back to slower but identical-result paths.
 #include "orb_internal.cuh"
 
 namespace {
 
 #define FS_THREADS 256
+#define FS_WARPS (FS_THREADS / 32)
 #define FS_PITCH 272       // bytes per shared-memory row: 7 (alignment shift) + 256 (tile) + word slack, multiple of 16
 #define FS_ROWS 66         // cell sub-image height <= hCell + 6 <= 66
 #define FS_SROWS 62        // evaluated rows <= 60, plus a zero row above and below
 #define FS_MAXG 8          // 250 / 30
-#define FS_CAND 9216       // candidate list entries (u16): 36 rows x 256 px per chunk
+#define FS_WCAP 896        // candidate entries (u16) per warp segment
+#define FS_SCAP 3072       // scored-corner list entries (u16)
 #define FS_TILE_BYTES (FS_ROWS * FS_PITCH)
+#define FS_CAND_BYTES (FS_WARPS * FS_WCAP * 2)
+#define FS_SCORED_BYTES (FS_SCAP * 2)
 #define FS_SCORE_BYTES (FS_SROWS * FS_PITCH)
-#define FS_SMEM (FS_TILE_BYTES + FS_CAND * 2 + FS_SCORE_BYTES)
-#define FS_OUT_CAP ((FS_TILE_BYTES + FS_CAND * 2) / 8)   // records that fit the (dead) tile + candidate list: 4548 >= 3750
+#define FS_SMEM (FS_TILE_BYTES + FS_CAND_BYTES + FS_SCORED_BYTES + FS_SCORE_BYTES)
+#define FS_OUT_CAP ((FS_TILE_BYTES + FS_CAND_BYTES) / 8)   // records that fit the (dead) tile + candidate segments: 4036 >= 3750
 
-__device__ __forceinline__ int fast_score16(int c, const int (&r)[16]) {
-    int mx3[16], mn3[16];
+// exact FAST score of the pixel at t (shared-memory tile): both polarities in one s16x2 min/max tree on the packed
+// pairs (r_k, 255 - r_k):  lo -> max_arc min r = bmax,  hi -> max_arc min (255 - r) = 255 - min_arc max r = 255 - amin
+__device__ __forceinline__ int fast_score_at(const uint8_t* t) {
+    unsigned p[16];
+    const int o[16] = {3 * FS_PITCH,      3 * FS_PITCH + 1,  2 * FS_PITCH + 2,  FS_PITCH + 3,  3,  -FS_PITCH + 3, -2 * FS_PITCH + 2,
+                       -3 * FS_PITCH + 1, -3 * FS_PITCH,     -3 * FS_PITCH - 1, -2 * FS_PITCH - 2, -FS_PITCH - 3, -3, FS_PITCH - 3,
+                       2 * FS_PITCH - 2,  3 * FS_PITCH - 1};
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        mx3[k] = __vimax3_s32(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
-        mn3[k] = __vimin3_s32(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
-    }
-    int amin = 255, bmax = 0;
+    for (int k = 0; k < 16; ++k) p[k] = (unsigned)t[o[k]] * 0xFFFF0001u + 0x00FF0000u;   // lo = r, hi = 255 - r
+    unsigned m3[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        amin = min(amin, __vimax3_s32(mx3[k], mx3[(k + 3) & 15], mx3[(k + 6) & 15]));
-        bmax = max(bmax, __vimin3_s32(mn3[k], mn3[(k + 3) & 15], mn3[(k + 6) & 15]));
+    for (int k = 0; k < 16; ++k) m3[k] = __vimin3_s16x2(p[k], p[(k + 1) & 15], p[(k + 2) & 15]);
+    unsigned best = 0u;
+#pragma unroll
+    for (int k = 0; k < 16; k += 2) {
+        const unsigned a = __vimin3_s16x2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
+        const unsigned b = __vimin3_s16x2(m3[k + 1], m3[(k + 4) & 15], m3[(k + 7) & 15]);
+        best = __vimax3_s16x2(best, a, b);
     }
+    const int c = t[0];
+    const int bmax = (int)(best & 0xFFFFu), amin = 255 - (int)(best >> 16);
     return max(c - amin, bmax - c) - 1;
 }
 
@@ -74,12 +88,13 @@ __global__ void __launch_bounds__(FS_THREADS)
 fast_strip_kernel(const uint8_t* __restrict__ pyr, unsigned long long* __restrict__ corners,
                   int* __restrict__ corner_count, const __grid_constant__ Geometry g) {
     extern __shared__ __align__(16) uint8_t fs_smem[];
-    uint8_t* tile = fs_smem;                                                        // FS_ROWS x FS_PITCH pixels
-    unsigned short* cand = reinterpret_cast<unsigned short*>(fs_smem + FS_TILE_BYTES);   // FS_CAND entries
-    uint8_t* score = fs_smem + FS_TILE_BYTES + FS_CAND * 2;                          // FS_SROWS x FS_PITCH scores
-    unsigned long long* outl = reinterpret_cast<unsigned long long*>(fs_smem);      // pass 3: aliases tile + cand
+    uint8_t* tile = fs_smem;                                                                     // FS_ROWS x FS_PITCH pixels
+    unsigned short* cand = reinterpret_cast<unsigned short*>(fs_smem + FS_TILE_BYTES);            // per-warp segments
+    unsigned short* scored = reinterpret_cast<unsigned short*>(fs_smem + FS_TILE_BYTES + FS_CAND_BYTES);
+    uint8_t* score = fs_smem + FS_TILE_BYTES + FS_CAND_BYTES + FS_SCORED_BYTES;                   // FS_SROWS x FS_PITCH scores
+    unsigned long long* outl = reinterpret_cast<unsigned long long*>(fs_smem);                   // pass 3: aliases tile + cand
     __shared__ int s_any[FS_MAXG];
-    __shared__ int s_ncand, s_nout, s_base;
+    __shared__ int s_nscored, s_nout, s_base;
 
     const int cta = blockIdx.x, f = blockIdx.y;
     int l = 0;
@@ -119,7 +134,7 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, unsigned long long* __restric
         reinterpret_cast<unsigned*>(tile + r * FS_PITCH)[wd] = __ldg(src_w + r * gpw + wd);
     }
     if (threadIdx.x < FS_MAXG) s_any[threadIdx.x] = 0;
-    if (threadIdx.x == 0) { s_ncand = 0; s_nout = 0; }
+    if (threadIdx.x == 0) { s_nscored = 0; s_nout = 0; }
     for (int k = threadIdx.x; k < (eh + 2) * (FS_PITCH / 16); k += FS_THREADS)
         reinterpret_cast<uint4*>(score)[k] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
@@ -132,74 +147,80 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, unsigned long long* __restric
     const int nw = whi - wlo + 1;                          // words holding evaluated pixels (<= 64)
     const unsigned inv_nw = 0xFFFFFFFFu / (unsigned)nw + 1u;
     const unsigned vfirst = 0xFu << (sb_lo & 3), vlast = 0xFu >> (3 - ((sb_hi - 1) & 3));
-    const int chunk_rows = min(eh, FS_CAND / (4 * nw));
-    const int lane = threadIdx.x & 31;
-    for (int rc0 = 0; rc0 < eh; rc0 += chunk_rows) {
-        const int rows = min(chunk_rows, eh - rc0);
-        const int total = rows * nw;
-        // 1a: quick test + compaction (uniform trip count: the ballots need the whole warp)
-        for (int k0 = 0; k0 < total; k0 += FS_THREADS) {
-            const int k = k0 + threadIdx.x;
-            unsigned m = 0;
-            int r = 0, wd = 0;
-            if (k < total) {
-                r = (int)__umulhi((unsigned)k, inv_nw);
-                wd = wlo + (k - r * nw);
-                r += rc0;
-                const unsigned* row = reinterpret_cast<const unsigned*>(tile + (r + 3) * FS_PITCH) + wd;   // centre row
-                constexpr int P = FS_PITCH / 4;
-                const unsigned c = row[0], wl = row[-1], wr = row[1];
-                const unsigned r0 = row[3 * P], r8 = row[-3 * P];                                    // (0,+3) (0,-3)
-                const unsigned r4 = __funnelshift_r(c, wr, 24), r12 = __funnelshift_r(wl, c, 8);     // (+3,0) (-3,0)
-                const unsigned* rp = row + 2 * P;
-                const unsigned* rm = row - 2 * P;
-                const unsigned r2 = __funnelshift_r(rp[0], rp[1], 16), r14 = __funnelshift_r(rp[-1], rp[0], 16);  // (+2,+2) (-2,+2)
-                const unsigned r6 = __funnelshift_r(rm[0], rm[1], 16), r10 = __funnelshift_r(rm[-1], rm[0], 16);  // (+2,-2) (-2,-2)
-                m = quick2<0>(c, r0, r8, r4, r12, r2, r10, r6, r14, tp1, ntp1) |
-                    (quick2<1>(c, r0, r8, r4, r12, r2, r10, r6, r14, tp1, ntp1) << 2);
-                if (wd == wlo) m &= vfirst;
-                if (wd == whi) m &= vlast;
-            }
-            const unsigned b0 = __ballot_sync(0xffffffffu, m & 1u), b1 = __ballot_sync(0xffffffffu, m & 2u);
-            const unsigned b2 = __ballot_sync(0xffffffffu, m & 4u), b3 = __ballot_sync(0xffffffffu, m & 8u);
-            const int tot = __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
-            if (tot) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&s_ncand, tot);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (m) {
-                    const unsigned below = (1u << lane) - 1u;
-                    int o = base + __popc(b0 & below) + __popc(b1 & below) + __popc(b2 & below) + __popc(b3 & below);
-                    const int code = r * FS_PITCH + (wd << 2);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int total = eh * nw;                             // <= 60 * 64 words: at most 15 iterations of 256 threads
+    auto score_one = [&](int r, int sb) {
+        const int sc = fast_score_at(tile + (r + 3) * FS_PITCH + sb);
+        if (sc >= tmin) {
+            score[(r + 1) * FS_PITCH + sb] = (uint8_t)sc;
+            const int o = atomicAdd(&s_nscored, 1);
+            if (o < FS_SCAP) scored[o] = (unsigned short)(r * FS_PITCH + sb);
+        }
+    };
+    {
+        // 1a: quick test, 4 candidate bits per iteration per lane
+        unsigned long long cmask = 0ull;
+        int it = 0;
+        for (int k = threadIdx.x; k < total; k += FS_THREADS, ++it) {
+            const int r = (int)__umulhi((unsigned)k, inv_nw);
+            const int wd = wlo + (k - r * nw);
+            const unsigned* row = reinterpret_cast<const unsigned*>(tile + (r + 3) * FS_PITCH) + wd;   // centre row
+            constexpr int P = FS_PITCH / 4;
+            const unsigned c = row[0], wl = row[-1], wr = row[1];
+            const unsigned r0 = row[3 * P], r8 = row[-3 * P];                                    // (0,+3) (0,-3)
+            const unsigned r4 = __funnelshift_r(c, wr, 24), r12 = __funnelshift_r(wl, c, 8);     // (+3,0) (-3,0)
+            const unsigned* rp = row + 2 * P;
+            const unsigned* rm = row - 2 * P;
+            const unsigned r2 = __funnelshift_r(rp[0], rp[1], 16), r14 = __funnelshift_r(rp[-1], rp[0], 16);  // (+2,+2) (-2,+2)
+            const unsigned r6 = __funnelshift_r(rm[0], rm[1], 16), r10 = __funnelshift_r(rm[-1], rm[0], 16);  // (+2,-2) (-2,-2)
+            unsigned m = quick2<0>(c, r0, r8, r4, r12, r2, r10, r6, r14, tp1, ntp1) |
+                         (quick2<1>(c, r0, r8, r4, r12, r2, r10, r6, r14, tp1, ntp1) << 2);
+            if (wd == wlo) m &= vfirst;
+            if (wd == whi) m &= vlast;
+            cmask |= (unsigned long long)m << (4 * it);
+        }
+        // warp-level compaction: exclusive prefix of the per-lane counts
+        const int cnt = __popcll(cmask);
+        int incl = cnt;
 #pragma unroll
-                    for (int b = 0; b < 4; ++b)
-                        if (m & (1u << b)) cand[o++] = (unsigned short)(code + b);
-                }
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        const int wtotal = __shfl_sync(0xffffffffu, incl, 31);
+        unsigned short* seg = cand + warp * FS_WCAP;
+        if (wtotal <= FS_WCAP) {
+            int o = incl - cnt;
+            while (cmask) {
+                const int bit = __ffsll((long long)cmask) - 1;
+                cmask &= cmask - 1ull;
+                const int k = threadIdx.x + (bit >> 2) * FS_THREADS;
+                const int r = (int)__umulhi((unsigned)k, inv_nw);
+                const int wd = wlo + (k - r * nw);
+                seg[o++] = (unsigned short)(r * FS_PITCH + (wd << 2) + (bit & 3));
+            }
+            __syncwarp();
+            // 1b: exact score of the warp's candidates
+            for (int k = lane; k < wtotal; k += 32) {
+                const int code = seg[k];
+                const int r = (int)__umulhi((unsigned)code, 0xFFFFFFFFu / FS_PITCH + 1u);
+                score_one(r, code - r * FS_PITCH);
+            }
+        } else {
+            // segment overflow (a warp with > 896 candidates): score in place, lane by lane
+            while (cmask) {
+                const int bit = __ffsll((long long)cmask) - 1;
+                cmask &= cmask - 1ull;
+                const int k = threadIdx.x + (bit >> 2) * FS_THREADS;
+                const int r = (int)__umulhi((unsigned)k, inv_nw);
+                const int wd = wlo + (k - r * nw);
+                score_one(r, (wd << 2) + (bit & 3));
             }
         }
-        __syncthreads();
-        // 1b: exact score of the candidates
-        const int ncand = s_ncand;
-        for (int k = threadIdx.x; k < ncand; k += FS_THREADS) {
-            const int code = cand[k];
-            const int r = (int)__umulhi((unsigned)code, 0xFFFFFFFFu / FS_PITCH + 1u);
-            const int sb = code - r * FS_PITCH;
-            const uint8_t* t = tile + (r + 3) * FS_PITCH + sb;
-            int rr[16];
-            rr[0] = t[3 * FS_PITCH];       rr[1] = t[3 * FS_PITCH + 1];   rr[2] = t[2 * FS_PITCH + 2];   rr[3] = t[FS_PITCH + 3];
-            rr[4] = t[3];                  rr[5] = t[-FS_PITCH + 3];      rr[6] = t[-2 * FS_PITCH + 2];  rr[7] = t[-3 * FS_PITCH + 1];
-            rr[8] = t[-3 * FS_PITCH];      rr[9] = t[-3 * FS_PITCH - 1];  rr[10] = t[-2 * FS_PITCH - 2]; rr[11] = t[-FS_PITCH - 3];
-            rr[12] = t[-3];                rr[13] = t[FS_PITCH - 3];      rr[14] = t[2 * FS_PITCH - 2];  rr[15] = t[3 * FS_PITCH - 1];
-            const int sc = fast_score16(t[0], rr);
-            if (sc >= tmin) score[(r + 1) * FS_PITCH + sb] = (uint8_t)sc;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) s_ncand = 0;
-        // (the next chunk's first atomicAdd on s_ncand comes after its own quick-test work; the barrier below orders it)
-        __syncthreads();
     }
+    __syncthreads();
 
-    // ---- pass 2 / 3 scan the score tile in 16-byte chunks and share the NMS test ----
+    // ---- pass 2 / 3: NMS (strict >, neighbours outside the cell's evaluated area count as 0) ----
     const int wCell = L.wCell;
     const unsigned inv_wc = 0xFFFFFFFFu / (unsigned)wCell + 1u;
     auto nms_max = [&](int r, int sb, int sc, int& jj, int& xr) -> bool {
@@ -213,51 +234,62 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, unsigned long long* __restric
         if (!right) ok = ok && sc > q[1] && sc > q[-FS_PITCH + 1] && sc > q[FS_PITCH + 1];
         return ok;
     };
-    const int qlo = sb_lo >> 4, nq = ((sb_hi - 1) >> 4) - qlo + 1;      // 16-byte chunks per row (<= 17)
-    const unsigned inv_nq = 0xFFFFFFFFu / (unsigned)nq + 1u;
-    for (int k = threadIdx.x; k < eh * nq; k += FS_THREADS) {
-        const int r = (int)__umulhi((unsigned)k, inv_nq);
-        const int qd = qlo + (k - r * nq);
-        const uint4 v = reinterpret_cast<const uint4*>(score + (r + 1) * FS_PITCH)[qd];
-        if ((v.x | v.y | v.z | v.w) == 0u) continue;
-        const unsigned wv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int w4 = 0; w4 < 4; ++w4) {
-            if (wv[w4] == 0u) continue;
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const int sc = (wv[w4] >> (8 * b)) & 0xFF;
-                if (sc >= tini) {
-                    int jj, xr;
-                    if (nms_max(r, (qd << 4) + (w4 << 2) + b, sc, jj, xr)) s_any[jj] = 1;
-                }
+    auto emit = [&](int r, int sb, int sc, int jj, int xr) {
+        // vToDistributeKeys coordinates (ORBextractor.cc:856-857) and the reference's visiting order key
+        const int cell = i * L.nCols + j0 + jj;
+        const int o = atomicAdd(&s_nout, 1);
+        if (o < FS_OUT_CAP)
+            outl[o] = corner_pack(j0 * wCell + 3 + (sb - sb_lo), i * L.hCell + 3 + r, sc, (cell << 12) | (r << 6) | xr);
+    };
+    const int nscored = s_nscored;
+    if (nscored <= FS_SCAP) {
+        // dense: one scored corner per thread; bit 15 of the entry remembers "is an NMS maximum"
+        for (int k = threadIdx.x; k < nscored; k += FS_THREADS) {
+            const int code = scored[k];
+            const int r = (int)__umulhi((unsigned)code, 0xFFFFFFFFu / FS_PITCH + 1u);
+            const int sb = code - r * FS_PITCH;
+            const int sc = score[(r + 1) * FS_PITCH + sb];
+            int jj, xr;
+            if (nms_max(r, sb, sc, jj, xr)) {
+                scored[k] = (unsigned short)(code | 0x8000);
+                if (sc >= tini) s_any[jj] = 1;
             }
         }
-    }
-    __syncthreads();   // also: every read of tile / cand is done, outl may overwrite them
-    for (int k = threadIdx.x; k < eh * nq; k += FS_THREADS) {
-        const int r = (int)__umulhi((unsigned)k, inv_nq);
-        const int qd = qlo + (k - r * nq);
-        const uint4 v = reinterpret_cast<const uint4*>(score + (r + 1) * FS_PITCH)[qd];
-        if ((v.x | v.y | v.z | v.w) == 0u) continue;
-        const unsigned wv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int w4 = 0; w4 < 4; ++w4) {
-            if (wv[w4] == 0u) continue;
-#pragma unroll
+        __syncthreads();   // also: every read of tile / cand is done, outl may overwrite them
+        for (int k = threadIdx.x; k < nscored; k += FS_THREADS) {
+            const int code = scored[k];
+            if (!(code & 0x8000)) continue;
+            const int r = (int)__umulhi((unsigned)(code & 0x7FFF), 0xFFFFFFFFu / FS_PITCH + 1u);
+            const int sb = (code & 0x7FFF) - r * FS_PITCH;
+            const int sc = score[(r + 1) * FS_PITCH + sb];
+            const int xe = sb - sb_lo;
+            const int jj = (int)__umulhi((unsigned)xe, inv_wc);
+            if (sc < (s_any[jj] ? tini : tmin)) continue;
+            emit(r, sb, sc, jj, xe - jj * wCell);
+        }
+    } else {
+        // scored-list overflow: scan the score tile instead (same result, slower)
+        for (int k = threadIdx.x; k < eh * nw; k += FS_THREADS) {
+            const int r = (int)__umulhi((unsigned)k, inv_nw);
+            const int wd = wlo + (k - r * nw);
+            const unsigned sw = reinterpret_cast<const unsigned*>(score + (r + 1) * FS_PITCH)[wd];
             for (int b = 0; b < 4; ++b) {
-                const int sc = (wv[w4] >> (8 * b)) & 0xFF;
-                if (sc == 0) continue;
+                const int sc = (sw >> (8 * b)) & 0xFF;
                 int jj, xr;
-                const int sb = (qd << 4) + (w4 << 2) + b;
-                if (!nms_max(r, sb, sc, jj, xr)) continue;
+                if (sc >= tini && nms_max(r, (wd << 2) + b, sc, jj, xr)) s_any[jj] = 1;
+            }
+        }
+        __syncthreads();
+        for (int k = threadIdx.x; k < eh * nw; k += FS_THREADS) {
+            const int r = (int)__umulhi((unsigned)k, inv_nw);
+            const int wd = wlo + (k - r * nw);
+            const unsigned sw = reinterpret_cast<const unsigned*>(score + (r + 1) * FS_PITCH)[wd];
+            for (int b = 0; b < 4; ++b) {
+                const int sc = (sw >> (8 * b)) & 0xFF;
+                int jj, xr;
+                if (sc == 0 || !nms_max(r, (wd << 2) + b, sc, jj, xr)) continue;
                 if (sc < (s_any[jj] ? tini : tmin)) continue;
-                const int xe = sb - sb_lo;
-                // vToDistributeKeys coordinates (ORBextractor.cc:856-857) and the reference's visiting order key
-                const int cell = i * L.nCols + j0 + jj;
-                const int o = atomicAdd(&s_nout, 1);
-                if (o < FS_OUT_CAP)
-                    outl[o] = corner_pack(j0 * wCell + 3 + xe, i * L.hCell + 3 + r, sc, (cell << 12) | (r << 6) | xr);
+                emit(r, (wd << 2) + b, sc, jj, xr);
             }
         }
     }
