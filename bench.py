@@ -277,8 +277,9 @@ def main():
     value = world * B * args.steps / (ms_dev * 1e-3)
 
     # ---- e2e: host frames -> host keypoints + descriptors through the public call ----
-    kps_h = np.zeros((B, cap), KP_DTYPE)
-    desc_h = np.zeros((B, cap, 32), np.uint8)
+    t_kps_h = torch.zeros((B, cap, KP_DTYPE.itemsize), dtype=torch.uint8).pin_memory()   # pinned host outputs
+    t_desc_h = torch.zeros((B, cap, 32), dtype=torch.uint8).pin_memory()
+    kps_h, desc_h = t_kps_h.numpy(), t_desc_h.numpy()
     n_h = np.zeros(B, np.int32)
     from orb_slam_2_ros_b200._lib import check, lib, ptr
 

@@ -64,9 +64,8 @@ blur_kernel(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur, const _
 
 }  // namespace
 
-int orb_launch_blur(orb_ctx* c, int F) {
-    const Geometry& g = c->g;
-    blur_kernel<<<dim3((g.blur_items + 255) / 256, F), 256, 0, c->stream>>>(c->d_pyr, c->d_blur, g);
+int orb_launch_blur(orb_ctx* c, const Geometry& g, int F, cudaStream_t st) {
+    blur_kernel<<<dim3((g.blur_items + 255) / 256, F), 256, 0, st>>>(c->d_pyr, c->d_blur, g);
     c->launches++;
     ORB_CUDA(cudaGetLastError());
     return ORB_OK;

@@ -37,6 +37,7 @@ void free_geometry_buffers(orb_ctx* c) {
     cudaFree(c->d_corner_count); cudaFree(c->d_kept); cudaFree(c->d_kept_count); cudaFree(c->d_taps);
     cudaFree(c->d_wtaps); cudaFree(c->d_kps_out); cudaFree(c->d_desc_out); cudaFree(c->d_n_out);
     cudaFreeHost(c->h_kps); cudaFreeHost(c->h_desc); cudaFreeHost(c->h_n); cudaFreeHost(c->h_in);
+    c->h_out_cap = 0;
     c->d_in = c->d_pyr = c->d_blur = nullptr; c->d_corners = nullptr; c->d_node_of_key = nullptr;
     c->d_corner_count = c->d_kept_count = nullptr; c->d_kept = nullptr; c->d_taps = nullptr;
     c->d_wtaps = nullptr; c->d_kps_out = nullptr; c->d_desc_out = nullptr; c->d_n_out = nullptr;
@@ -198,30 +199,51 @@ int build_geometry(orb_ctx* c, int w, int h) {
     return ORB_OK;
 }
 
-int ensure_staging(orb_ctx* c, int cap) {
+// device output rows [max_batch][dcap] (+ pinned mirrors, used when the caller's buffers are pageable)
+int ensure_outputs(orb_ctx* c, int dcap, bool need_host_mirror) {
     const int F = c->max_batch;
-    const size_t in_bytes = (size_t)F * c->g.w * c->g.h;
-    if (c->in_bytes < in_bytes) {
-        cudaFree(c->d_in); cudaFreeHost(c->h_in);
-        c->d_in = nullptr; c->h_in = nullptr;
-        ORB_CUDA(cudaMalloc(&c->d_in, in_bytes));
-        ORB_CUDA(cudaMallocHost(&c->h_in, in_bytes));
-        c->in_bytes = c->h_in_bytes = in_bytes;
-    }
-    if (c->out_cap < cap) {
+    if (c->out_cap < dcap) {
+        ORB_CUDA(cudaStreamSynchronize(c->stream));
         cudaFree(c->d_kps_out); cudaFree(c->d_desc_out); cudaFree(c->d_n_out);
         cudaFreeHost(c->h_kps); cudaFreeHost(c->h_desc); cudaFreeHost(c->h_n);
         c->d_kps_out = nullptr; c->d_desc_out = nullptr; c->d_n_out = nullptr;
-        c->h_kps = nullptr; c->h_desc = nullptr; c->h_n = nullptr;
-        ORB_CUDA(cudaMalloc(&c->d_kps_out, sizeof(orb_kp) * (size_t)F * cap));
-        ORB_CUDA(cudaMalloc(&c->d_desc_out, (size_t)32 * F * cap));
+        c->h_kps = nullptr; c->h_desc = nullptr; c->h_n = nullptr; c->h_out_cap = 0;
+        ORB_CUDA(cudaMalloc(&c->d_kps_out, sizeof(orb_kp) * (size_t)F * dcap));
+        ORB_CUDA(cudaMalloc(&c->d_desc_out, (size_t)32 * F * dcap));
         ORB_CUDA(cudaMalloc(&c->d_n_out, sizeof(int) * F));
-        ORB_CUDA(cudaMallocHost(&c->h_kps, sizeof(orb_kp) * (size_t)F * cap));
-        ORB_CUDA(cudaMallocHost(&c->h_desc, (size_t)32 * F * cap));
         ORB_CUDA(cudaMallocHost(&c->h_n, sizeof(int) * F));
-        c->out_cap = cap;
+        c->out_cap = dcap;
+    }
+    if (need_host_mirror && c->h_out_cap < c->out_cap) {
+        cudaFreeHost(c->h_kps); cudaFreeHost(c->h_desc);
+        c->h_kps = nullptr; c->h_desc = nullptr;
+        ORB_CUDA(cudaMallocHost(&c->h_kps, sizeof(orb_kp) * (size_t)F * c->out_cap));
+        ORB_CUDA(cudaMallocHost(&c->h_desc, (size_t)32 * F * c->out_cap));
+        c->h_out_cap = c->out_cap;
     }
     return ORB_OK;
+}
+
+int ensure_input_staging(orb_ctx* c, bool need_host_mirror) {
+    const size_t in_bytes = (size_t)c->max_batch * c->g.w * c->g.h;
+    if (c->in_bytes < in_bytes) {
+        ORB_CUDA(cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_in); c->d_in = nullptr;
+        ORB_CUDA(cudaMalloc(&c->d_in, in_bytes));
+        c->in_bytes = in_bytes;
+    }
+    if (need_host_mirror && c->h_in_bytes < in_bytes) {
+        cudaFreeHost(c->h_in); c->h_in = nullptr;
+        ORB_CUDA(cudaMallocHost(&c->h_in, in_bytes));
+        c->h_in_bytes = in_bytes;
+    }
+    return ORB_OK;
+}
+
+bool is_pinned(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
 }
 
 int check_device() {
@@ -292,6 +314,15 @@ static int ensure_device(orb_ctx* c) {
         ORB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         c->own_stream = true;
     }
+    if (!c->st_h2d) {
+        ORB_CUDA(cudaStreamCreateWithFlags(&c->st_h2d, cudaStreamNonBlocking));
+        ORB_CUDA(cudaStreamCreateWithFlags(&c->st_d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < ORB_PIPE_SLOTS; ++i) {
+            ORB_CUDA(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
+            ORB_CUDA(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+            ORB_CUDA(cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming));
+        }
+    }
     return ORB_OK;
 }
 
@@ -305,6 +336,10 @@ void orb_destroy(orb_ctx* c) {
             for (int r = 0; r < ORB_PROF_RING; ++r)
                 for (int s = 0; s <= ORB_NSTAGES; ++s) cudaEventDestroy(c->prof_ev[r][s]);
         if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+        if (c->st_h2d) {
+            cudaStreamDestroy(c->st_h2d); cudaStreamDestroy(c->st_d2h);
+            for (int i = 0; i < ORB_PIPE_SLOTS; ++i) { cudaEventDestroy(c->ev_in[i]); cudaEventDestroy(c->ev_done[i]); cudaEventDestroy(c->ev_out[i]); }
+        }
     }
     delete c;
 }
@@ -390,9 +425,12 @@ int orb_extract_batch_device(orb_ctx* c, const uint8_t* d_imgs, int nframes, int
     rc = build_geometry(c, w, h);
     if (rc != ORB_OK) return rc;
     c->last_frames = nframes;
-    return orb_launch_extract(c, d_imgs, nframes, row_stride, frame_stride, d_kps, d_desc, cap, d_n_out);
+    return orb_launch_extract(c, d_imgs, nframes, 0, row_stride, frame_stride, d_kps, d_desc, cap, d_n_out, c->stream);
 }
 
+// Host buffers in, host buffers out.  The batch is cut into chunks of ORB_PIPE_CHUNK frames that flow through three
+// streams (H2D copy -> kernels -> D2H copy), so the PCIe transfers of neighbouring chunks overlap the kernels.
+// Pinned caller buffers are used directly; pageable ones go through the context's pinned mirrors.
 int orb_extract_batch(orb_ctx* c, const uint8_t* imgs, int nframes, int w, int h, size_t row_stride, size_t frame_stride,
                       orb_kp* kps, uint8_t* desc, int cap, int32_t* n_out) {
     if (!c || !n_out || nframes < 0 || cap < 0) return ORB_ERR_INVALID;
@@ -403,50 +441,82 @@ int orb_extract_batch(orb_ctx* c, const uint8_t* imgs, int nframes, int w, int h
     if (rc != ORB_OK) return rc;
     rc = build_geometry(c, w, h);
     if (rc != ORB_OK) return rc;
+    const bool tight = row_stride == (size_t)w && frame_stride == (size_t)w * h;
+    const bool in_direct = tight && is_pinned(imgs);
+    const bool out_direct = is_pinned(kps) && is_pinned(desc);
     const int dcap = std::min(cap, c->g.total_kp_slots);
-    rc = ensure_staging(c, std::max(dcap, c->out_cap));
+    rc = ensure_outputs(c, std::max(dcap, c->out_cap), !out_direct);
     if (rc != ORB_OK) return rc;
-    const int ocap = c->out_cap;
+    rc = ensure_input_staging(c, !in_direct);
+    if (rc != ORB_OK) return rc;
+    const int ocap = c->out_cap;                        // device row length (>= dcap)
+    const size_t fbytes = (size_t)w * h;
     int status = ORB_OK;
-    for (int f0 = 0; f0 < nframes; f0 += c->max_batch) {
-        const int F = std::min(c->max_batch, nframes - f0);
-        // host -> pinned staging (tight rows) -> device
-        for (int f = 0; f < F; ++f) {
-            const uint8_t* src = imgs + (size_t)(f0 + f) * frame_stride;
-            uint8_t* dst = c->h_in + (size_t)f * w * h;
-            if (row_stride == (size_t)w) memcpy(dst, src, (size_t)w * h);
-            else for (int y = 0; y < h; ++y) memcpy(dst + (size_t)y * w, src + (size_t)y * row_stride, w);
-        }
-        ORB_CUDA(cudaMemcpyAsync(c->d_in, c->h_in, (size_t)F * w * h, cudaMemcpyHostToDevice, c->stream));
-        c->last_frames = F;
-        rc = orb_launch_extract(c, c->d_in, F, (size_t)w, (size_t)w * h, c->d_kps_out, c->d_desc_out, ocap, c->d_n_out);
-        if (rc != ORB_OK) return rc;
-        ORB_CUDA(cudaMemcpyAsync(c->h_n, c->d_n_out, sizeof(int) * F, cudaMemcpyDeviceToHost, c->stream));
-        ORB_CUDA(cudaStreamSynchronize(c->stream));
-        // copy back only what was produced
-        for (int f = 0; f < F; ++f) {
-            const int n = c->h_n[f];
-            n_out[f0 + f] = n;
-            if (n > cap || n > ocap) {
-                orb_set_error("frame %d produced %d keypoints, capacity %d", f0 + f, n, cap);
-                status = ORB_ERR_CAPACITY;
+    // the caller's stream (c->stream) may have pending work that produced or still reads our buffers
+    ORB_CUDA(cudaStreamSynchronize(c->stream));
+    for (int b0 = 0; b0 < nframes; b0 += c->max_batch) {
+        const int B = std::min(c->max_batch, nframes - b0);
+        const int nchunks = (B + ORB_PIPE_CHUNK - 1) / ORB_PIPE_CHUNK;
+        c->last_frames = B;
+        auto finish_chunk = [&](int k) -> int {       // host side of chunk k once its D2H has landed
+            const int f0 = k * ORB_PIPE_CHUNK, F = std::min(ORB_PIPE_CHUNK, B - f0);
+            ORB_CUDA(cudaEventSynchronize(c->ev_out[k % ORB_PIPE_SLOTS]));
+            for (int f = 0; f < F; ++f) {
+                const int n = c->h_n[f0 + f];
+                n_out[b0 + f0 + f] = n;
+                if (n > cap) { orb_set_error("frame %d produced %d keypoints, capacity %d", b0 + f0 + f, n, cap); status = ORB_ERR_CAPACITY; }
+                if (!out_direct) {
+                    const int m = std::min(n, std::min(cap, ocap));
+                    memcpy(kps + (size_t)(b0 + f0 + f) * cap, c->h_kps + (size_t)(f0 + f) * ocap, sizeof(orb_kp) * m);
+                    memcpy(desc + (size_t)(b0 + f0 + f) * cap * 32, c->h_desc + (size_t)(f0 + f) * ocap * 32, (size_t)32 * m);
+                }
             }
+            return ORB_OK;
+        };
+        for (int k = 0; k < nchunks; ++k) {
+            const int f0 = k * ORB_PIPE_CHUNK, F = std::min(ORB_PIPE_CHUNK, B - f0);
+            const int slot = k % ORB_PIPE_SLOTS;
+            if (k >= ORB_PIPE_SLOTS) { rc = finish_chunk(k - ORB_PIPE_SLOTS); if (rc != ORB_OK) return rc; }   // frees the slot's events
+            // ---- H2D ----
+            const uint8_t* src = imgs + (size_t)(b0 + f0) * frame_stride;
+            if (!in_direct) {
+                uint8_t* stage = c->h_in + (size_t)f0 * fbytes;
+                for (int f = 0; f < F; ++f) {
+                    const uint8_t* s1 = src + (size_t)f * frame_stride;
+                    uint8_t* d1 = stage + (size_t)f * fbytes;
+                    if (row_stride == (size_t)w) memcpy(d1, s1, fbytes);
+                    else for (int y = 0; y < h; ++y) memcpy(d1 + (size_t)y * w, s1 + (size_t)y * row_stride, w);
+                }
+                src = stage;
+            }
+            uint8_t* d_src = c->d_in + (size_t)f0 * fbytes;
+            ORB_CUDA(cudaMemcpyAsync(d_src, src, (size_t)F * fbytes, cudaMemcpyHostToDevice, c->st_h2d));
+            ORB_CUDA(cudaEventRecord(c->ev_in[slot], c->st_h2d));
+            // ---- kernels ----
+            ORB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_in[slot], 0));
+            rc = orb_launch_extract(c, d_src, F, f0, (size_t)w, fbytes, c->d_kps_out + (size_t)f0 * ocap,
+                                    c->d_desc_out + (size_t)f0 * ocap * 32, ocap, c->d_n_out + f0, c->stream);
+            if (rc != ORB_OK) return rc;
+            ORB_CUDA(cudaEventRecord(c->ev_done[slot], c->stream));
+            // ---- D2H ----
+            ORB_CUDA(cudaStreamWaitEvent(c->st_d2h, c->ev_done[slot], 0));
+            ORB_CUDA(cudaMemcpyAsync(c->h_n + f0, c->d_n_out + f0, sizeof(int) * F, cudaMemcpyDeviceToHost, c->st_d2h));
+            const int rows = std::min(ocap, cap);       // keypoint slots copied per frame
+            if (out_direct) {
+                ORB_CUDA(cudaMemcpy2DAsync(kps + (size_t)(b0 + f0) * cap, sizeof(orb_kp) * (size_t)cap, c->d_kps_out + (size_t)f0 * ocap,
+                                           sizeof(orb_kp) * (size_t)ocap, sizeof(orb_kp) * (size_t)rows, F, cudaMemcpyDeviceToHost, c->st_d2h));
+                ORB_CUDA(cudaMemcpy2DAsync(desc + (size_t)(b0 + f0) * cap * 32, (size_t)32 * cap, c->d_desc_out + (size_t)f0 * ocap * 32,
+                                           (size_t)32 * ocap, (size_t)32 * rows, F, cudaMemcpyDeviceToHost, c->st_d2h));
+            } else {
+                ORB_CUDA(cudaMemcpyAsync(c->h_kps + (size_t)f0 * ocap, c->d_kps_out + (size_t)f0 * ocap, sizeof(orb_kp) * (size_t)F * ocap,
+                                         cudaMemcpyDeviceToHost, c->st_d2h));
+                ORB_CUDA(cudaMemcpyAsync(c->h_desc + (size_t)f0 * ocap * 32, c->d_desc_out + (size_t)f0 * ocap * 32, (size_t)32 * F * ocap,
+                                         cudaMemcpyDeviceToHost, c->st_d2h));
+            }
+            ORB_CUDA(cudaEventRecord(c->ev_out[slot], c->st_d2h));
         }
-        for (int f = 0; f < F; ++f) {
-            const int n = std::min(std::min(c->h_n[f], cap), ocap);
-            if (n <= 0) continue;
-            ORB_CUDA(cudaMemcpyAsync(c->h_kps + (size_t)f * ocap, c->d_kps_out + (size_t)f * ocap, sizeof(orb_kp) * n,
-                                     cudaMemcpyDeviceToHost, c->stream));
-            ORB_CUDA(cudaMemcpyAsync(c->h_desc + (size_t)f * ocap * 32, c->d_desc_out + (size_t)f * ocap * 32, (size_t)32 * n,
-                                     cudaMemcpyDeviceToHost, c->stream));
-        }
+        for (int k = std::max(0, nchunks - ORB_PIPE_SLOTS); k < nchunks; ++k) { rc = finish_chunk(k); if (rc != ORB_OK) return rc; }
         ORB_CUDA(cudaStreamSynchronize(c->stream));
-        for (int f = 0; f < F; ++f) {
-            const int n = std::min(std::min(c->h_n[f], cap), ocap);
-            if (n <= 0) continue;
-            memcpy(kps + (size_t)(f0 + f) * cap, c->h_kps + (size_t)f * ocap, sizeof(orb_kp) * n);
-            memcpy(desc + (size_t)(f0 + f) * cap * 32, c->h_desc + (size_t)f * ocap * 32, (size_t)32 * n);
-        }
     }
     return status;
 }

@@ -473,10 +473,21 @@ extern "C" int orb_debug_sincos_range(int device, unsigned first_bits, long long
 // ======================================================================================================
 // host-side launch sequence of one batch (asynchronous on c->stream)
 // ======================================================================================================
-int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int F, size_t row_stride, size_t frame_stride,
-                       orb_kp* d_kps, uint8_t* d_desc, int cap, int* d_n_out) {
-    const Geometry& g = c->g;
-    cudaStream_t st = c->stream;
+int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int F, int f0, size_t row_stride, size_t frame_stride,
+                       orb_kp* d_kps, uint8_t* d_desc, int cap, int* d_n_out, cudaStream_t st) {
+    // frames [f0, f0 + F) of the arena: a per-launch copy of the geometry with shifted bases, so the kernels index
+    // frames by blockIdx.y alone; d_imgs / d_kps / d_desc / d_n_out already point at the chunk's first frame
+    Geometry& g = c->gl;
+    g = c->g;
+    for (int l = 0; l < g.nlevels; ++l) {
+        g.lv[l].base += (long long)f0 * g.lv[l].frame_stride;
+        g.lv[l].bbase += (long long)f0 * g.lv[l].bframe_stride;
+        g.lv[l].corner_base += (long long)f0 * g.lv[l].corner_cap;
+    }
+    int* d_cc = c->d_corner_count + (size_t)f0 * g.nlevels;
+    int* d_tie = c->d_corner_count + ((size_t)c->max_batch + f0) * g.nlevels;  // second half: tie-at-cut counters
+    unsigned long long* d_kept = c->d_kept + (size_t)f0 * g.total_kp_slots;
+    int* d_kept_count = c->d_kept_count + (size_t)f0 * g.nlevels;
     cudaEvent_t* ev = nullptr;
     if (c->profile) {
         const int slot = c->prof_head;
@@ -487,25 +498,25 @@ int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int F, size_t row_stri
         c->prof_head = (slot + 1) % ORB_PROF_RING;
     }
 #define ORB_STAGE_MARK(i) do { if (ev) ORB_CUDA(cudaEventRecord(ev[i], st)); } while (0)
-    ORB_CUDA(cudaMemsetAsync(c->d_corner_count, 0, sizeof(int) * 2 * (size_t)c->max_batch * g.nlevels, st));
-    int* d_tie = c->d_corner_count + (size_t)c->max_batch * g.nlevels;  // second half: tie-at-cut counters
+    ORB_CUDA(cudaMemsetAsync(d_cc, 0, sizeof(int) * (size_t)F * g.nlevels, st));
+    ORB_CUDA(cudaMemsetAsync(d_tie, 0, sizeof(int) * (size_t)F * g.nlevels, st));
     ORB_STAGE_MARK(0);
-    { int rc = orb_launch_pyramid(c, d_imgs, F, row_stride, frame_stride); if (rc != ORB_OK) return rc; }   // K1
+    { int rc = orb_launch_pyramid(c, g, d_imgs, F, row_stride, frame_stride, st); if (rc != ORB_OK) return rc; }   // K1
     ORB_STAGE_MARK(1);
-    { int rc = orb_launch_fast(c, F); if (rc != ORB_OK) return rc; }                                         // K2
+    { int rc = orb_launch_fast(c, g, d_cc, F, st); if (rc != ORB_OK) return rc; }                                   // K2
     ORB_STAGE_MARK(2);
     {   // K3
         const size_t smem = (size_t)g.max_node_cap * 80;
-        quadtree_kernel<<<dim3(g.nlevels, F), QT_THREADS, smem, st>>>(c->d_corners, c->d_corner_count, c->d_node_of_key,
-                                                                       c->d_kept, c->d_kept_count, d_tie, g);
+        quadtree_kernel<<<dim3(g.nlevels, F), QT_THREADS, smem, st>>>(c->d_corners, d_cc, c->d_node_of_key, d_kept, d_kept_count,
+                                                                       d_tie, g);
         c->launches++;
     }
     ORB_STAGE_MARK(3);
-    { int rc = orb_launch_blur(c, F); if (rc != ORB_OK) return rc; }                                         // K5
+    { int rc = orb_launch_blur(c, g, F, st); if (rc != ORB_OK) return rc; }                                         // K5
     ORB_STAGE_MARK(4);
     {   // K4 + K6
         orient_describe_kernel<<<dim3((g.total_kp_slots + OD_KPB - 1) / OD_KPB, F), OD_WARPS * 32, 0, st>>>(
-            c->d_pyr, c->d_blur, c->d_kept, c->d_kept_count, d_kps, d_desc, cap, d_n_out, g);
+            c->d_pyr, c->d_blur, d_kept, d_kept_count, d_kps, d_desc, cap, d_n_out, g);
         c->launches++;
     }
     ORB_STAGE_MARK(5);
@@ -513,4 +524,3 @@ int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int F, size_t row_stri
     ORB_CUDA(cudaGetLastError());
     return ORB_OK;
 }
-

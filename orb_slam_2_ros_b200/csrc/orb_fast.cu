@@ -306,13 +306,12 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, unsigned long long* __restric
 
 }  // namespace
 
-int orb_launch_fast(orb_ctx* c, int F) {
-    const Geometry& g = c->g;
+int orb_launch_fast(orb_ctx* c, const Geometry& g, int* d_corner_count, int F, cudaStream_t st) {
     if (!c->fast_attr_set) {   // > 48 KB of dynamic shared memory needs the opt-in, once per context (= per device)
         ORB_CUDA(cudaFuncSetAttribute(fast_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM));
         c->fast_attr_set = true;
     }
-    fast_strip_kernel<<<dim3(g.fast_ctas, F), FS_THREADS, FS_SMEM, c->stream>>>(c->d_pyr, c->d_corners, c->d_corner_count, g);
+    fast_strip_kernel<<<dim3(g.fast_ctas, F), FS_THREADS, FS_SMEM, st>>>(c->d_pyr, c->d_corners, d_corner_count, g);
     c->launches++;
     ORB_CUDA(cudaGetLastError());
     return ORB_OK;

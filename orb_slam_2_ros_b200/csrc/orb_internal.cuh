@@ -16,6 +16,8 @@
 #define ORB_XOFF 32        // byte offset of interior pixel x = 0 inside a pyramid row (border occupies [13, 32))
 #define ORB_NSTAGES 5      // pyramid, FAST cells, quadtree, blur, orientation+descriptors
 #define ORB_PROF_RING 64
+#define ORB_PIPE_SLOTS 4   // chunks in flight in the host-buffer pipeline
+#define ORB_PIPE_CHUNK 64  // frames per chunk of the host-buffer pipeline
 
 // thread-local error string ---------------------------------------------------------------------------
 void orb_set_error(const char* fmt, ...);
@@ -106,6 +108,10 @@ struct orb_ctx {
     // geometry-dependent state (rebuilt when the image size changes)
     bool have_geom = false;
     Geometry g;
+    Geometry gl;               // per-launch copy of g with the bases shifted to the chunk's first frame
+    // host-API pipeline (orb_extract_batch): copy streams + per-chunk events
+    cudaStream_t st_h2d = nullptr, st_d2h = nullptr;
+    cudaEvent_t ev_in[ORB_PIPE_SLOTS] = {}, ev_done[ORB_PIPE_SLOTS] = {}, ev_out[ORB_PIPE_SLOTS] = {};
     int last_frames = 0;
     uint8_t* d_in = nullptr;  size_t in_bytes = 0;      // staging of host input frames
     uint8_t* d_pyr = nullptr; size_t pyr_bytes = 0;     // bordered pyramids, level-major
@@ -121,6 +127,7 @@ struct orb_ctx {
     orb_kp* d_kps_out = nullptr; uint8_t* d_desc_out = nullptr; int* d_n_out = nullptr; int out_cap = 0;
     orb_kp* h_kps = nullptr; uint8_t* h_desc = nullptr; int* h_n = nullptr; uint8_t* h_in = nullptr;  // pinned
     size_t h_in_bytes = 0;
+    int h_out_cap = 0;
     // per-stage CUDA-event timers (orb_profile_enable / orb_profile_read): a ring of event sets so that reading
     // never stalls the stream; stage s of a call = elapsed(ev[s], ev[s+1])
     bool profile = false;
@@ -134,8 +141,10 @@ struct orb_ctx {
 int orb_profile_harvest(orb_ctx* c, int slot);
 
 // kernels' launchers (orb_extract_kernels.cu)
-int orb_launch_pyramid(orb_ctx* c, const uint8_t* d_imgs, int nframes, size_t row_stride, size_t frame_stride);
-int orb_launch_fast(orb_ctx* c, int nframes);
-int orb_launch_blur(orb_ctx* c, int nframes);
-int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int nframes, size_t row_stride, size_t frame_stride,
-                       orb_kp* d_kps, uint8_t* d_desc, int cap, int* d_n_out);
+int orb_launch_pyramid(orb_ctx* c, const Geometry& g, const uint8_t* d_imgs, int nframes, size_t row_stride,
+                       size_t frame_stride, cudaStream_t st);
+int orb_launch_fast(orb_ctx* c, const Geometry& g, int* d_corner_count, int nframes, cudaStream_t st);
+int orb_launch_blur(orb_ctx* c, const Geometry& g, int nframes, cudaStream_t st);
+// frames [f0, f0 + nframes) of the arena; all pointers address the chunk's first frame; asynchronous on st
+int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int nframes, int f0, size_t row_stride, size_t frame_stride,
+                       orb_kp* d_kps, uint8_t* d_desc, int cap, int* d_n_out, cudaStream_t st);

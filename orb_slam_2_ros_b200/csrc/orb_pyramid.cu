@@ -174,9 +174,8 @@ pyr_border_kernel(uint8_t* __restrict__ pyr, const __grid_constant__ Geometry g)
 
 }  // namespace
 
-int orb_launch_pyramid(orb_ctx* c, const uint8_t* d_imgs, int F, size_t row_stride, size_t frame_stride) {
-    const Geometry& g = c->g;
-    cudaStream_t st = c->stream;
+int orb_launch_pyramid(orb_ctx* c, const Geometry& g, const uint8_t* d_imgs, int F, size_t row_stride, size_t frame_stride,
+                       cudaStream_t st) {
     {
         const LevelGeom& L = g.lv[0];
         const int items = ((L.w + 15) >> 4) * L.h;

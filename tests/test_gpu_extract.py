@@ -102,6 +102,43 @@ def test_batch_equals_single_and_strided_input(oracle, ORB):
     assert np.array_equal(d, od)
 
 
+def test_pipelined_batch_chunks_pinned_and_pageable(oracle, ORB):
+    """orb_extract_batch cuts a batch into 64-frame chunks flowing through H2D / kernel / D2H streams: 150 frames
+    through a 100-frame arena = chunks of 64 + 36, then 50; once with pageable numpy buffers (staged through the
+    context's pinned mirrors) and once with pinned buffers (direct DMA, strided 2-D copies into the caller's rows)."""
+    import ctypes as C
+    import torch
+    from orb_slam_2_ros_b200 import _lib
+    w, h, n = 320, 240, 150
+    imgs = synth.synth_batch(300, n, w, h, unique=5)
+    ex = ORB(500, 1.2, 6, 20, 7, max_batch=100)
+    oex = oracle.Extractor(500, 1.2, 6, 20, 7)
+    want = [oex.extract(imgs[f]) for f in range(5)]        # frames >= 5 are circular shifts: check those through frame 0..4 too
+    res = ex.extract_batch(imgs)
+    assert len(res) == n
+    for f in range(5):
+        assert_kps_equal(res[f][0], want[f][0], "pageable frame %d" % f)
+        assert np.array_equal(res[f][1], want[f][1])
+    # every frame against single-frame extraction on the same context (same kernels, different arena slots)
+    for f in (5, 63, 64, 99, 100, 149):
+        k1, d1 = ex(imgs[f])
+        assert_kps_equal(res[f][0], k1, "frame %d" % f)
+        assert np.array_equal(res[f][1], d1)
+    # pinned in / out with a caller capacity larger than the device row length
+    cap = ex.max_keypoints + 37
+    t_in = torch.from_numpy(imgs).pin_memory()
+    t_k = torch.zeros((n, cap, _lib.KP_DTYPE.itemsize), dtype=torch.uint8).pin_memory()
+    t_d = torch.zeros((n, cap, 32), dtype=torch.uint8).pin_memory()
+    n_out = np.zeros(n, np.int32)
+    _lib.check(_lib.lib().orb_extract_batch(ex._h, C.c_void_p(t_in.data_ptr()), n, w, h, w, w * h, C.c_void_p(t_k.data_ptr()),
+                                            C.c_void_p(t_d.data_ptr()), cap, _lib.ptr(n_out)))
+    kp = t_k.numpy().view(_lib.KP_DTYPE).reshape(n, cap)
+    for f in range(n):
+        assert n_out[f] == len(res[f][0])
+        assert np.array_equal(kp[f, :n_out[f]].view(np.uint8), np.ascontiguousarray(res[f][0]).view(np.uint8)), "pinned frame %d" % f
+        assert np.array_equal(t_d.numpy()[f, :n_out[f]], res[f][1])
+
+
 def test_edge_cases(oracle, ORB):
     ex = ORB(500)
     k, d = ex(np.zeros((0, 0), np.uint8))                 # empty image => silent return (ORBextractor.cc:1086)
