@@ -1,0 +1,59 @@
+// ORBmatcher.h — array-level replacement of the loops in orb_slam2/src/ORBmatcher.cc (reference ORBmatcher.h:37-103).
+// The reference methods take Frame / KeyFrame / MapPoint objects; their bodies reduce to the array routines below
+// (what each loop reads and writes).  INTEGRATION.md shows the few lines of glue that keep the original
+// SearchByProjection(Frame&, ...) signatures on top of them.
+#ifndef ORBMATCHER_H
+#define ORBMATCHER_H
+
+#include <cstdint>
+#include <vector>
+
+#include "cv_compat.h"
+
+namespace ORB_SLAM2 {
+
+class ORBmatcher {
+public:
+    ORBmatcher(float nnratio = 0.6, bool checkOri = true, int device = 0) : mfNNratio(nnratio), mbCheckOrientation(checkOri), device_(device) {}
+
+    // Computes the Hamming distance between two ORB descriptors (ORBmatcher.cc:1649-1665).
+    static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b);
+
+    struct TargetFrame {                       // the fields of the Frame being searched
+        const cv::KeyPoint* keysUn; const uint8_t* descriptors; const float* uRight /* NULL: monocular */; int N;
+        float minX, minY, maxX, maxY;          // Frame::mnMinX ...
+    };
+    struct Queries {                           // one entry per projected map point, in the reference's loop order
+        int n; const float *u, *v, *radius; const int32_t *minLevel, *maxLevel; const uint8_t* descriptors;
+        const float *uR, *erMax, *angle; const uint8_t *valid, *hasObservations;
+    };
+    // SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono)     ORBmatcher.cc:1330-1472
+    int SearchByProjectionLastFrame(const TargetFrame& F, std::vector<uint8_t>& taken, const Queries& q, int thDist,
+                                    std::vector<int32_t>& matchOfQuery, std::vector<int32_t>& ownerOfTarget) const;
+    // SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, th)           ORBmatcher.cc:45-129
+    int SearchByProjectionLocalPoints(const TargetFrame& F, std::vector<uint8_t>& taken, const Queries& q,
+                                      std::vector<int32_t>& matchOfQuery, std::vector<int32_t>& ownerOfTarget) const;
+    // inner loop of SearchByBoW over one vocabulary node (ORBmatcher.cc:196-252)
+    int MatchNode(const uint8_t* desc1, const float* angle1, int n1, const uint8_t* desc2, const float* angle2, int n2, int thDist,
+                  std::vector<int32_t>& match12) const;
+
+    static const int TH_LOW = 50;
+    static const int TH_HIGH = 100;
+    static const int HISTO_LENGTH = 30;
+
+protected:
+    int Search(int mode, const TargetFrame& F, std::vector<uint8_t>& taken, const Queries& q, int thDist,
+               std::vector<int32_t>& matchOfQuery, std::vector<int32_t>& ownerOfTarget) const;
+    float mfNNratio;
+    bool mbCheckOrientation;
+    int device_;
+};
+
+// Frame::ComputeStereoMatches (Frame.cc:502-676): both extractors must have just processed the left / right image.
+class ORBextractor;
+int ComputeStereoMatches(ORBextractor& left, ORBextractor& right, const std::vector<cv::KeyPoint>& keysL, const cv::Mat& descL,
+                         const std::vector<cv::KeyPoint>& keysR, const cv::Mat& descR, float bf, float b,
+                         std::vector<float>& mvuRight, std::vector<float>& mvDepth);
+
+}  // namespace ORB_SLAM2
+#endif
