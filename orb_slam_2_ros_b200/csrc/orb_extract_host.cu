@@ -35,12 +35,12 @@ inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 void free_geometry_buffers(orb_ctx* c) {
     cudaFree(c->d_in); cudaFree(c->d_pyr); cudaFree(c->d_blur); cudaFree(c->d_corners); cudaFree(c->d_node_of_key);
     cudaFree(c->d_corner_count); cudaFree(c->d_kept); cudaFree(c->d_kept_count); cudaFree(c->d_taps);
-    cudaFree(c->d_wtaps); cudaFree(c->d_kps_out); cudaFree(c->d_desc_out); cudaFree(c->d_n_out);
+    cudaFree(c->d_wtaps); cudaFree(c->d_strips); cudaFree(c->d_kps_out); cudaFree(c->d_desc_out); cudaFree(c->d_n_out);
     cudaFreeHost(c->h_kps); cudaFreeHost(c->h_desc); cudaFreeHost(c->h_n); cudaFreeHost(c->h_in);
     c->h_out_cap = 0;
     c->d_in = c->d_pyr = c->d_blur = nullptr; c->d_corners = nullptr; c->d_node_of_key = nullptr;
     c->d_corner_count = c->d_kept_count = nullptr; c->d_kept = nullptr; c->d_taps = nullptr;
-    c->d_wtaps = nullptr; c->d_kps_out = nullptr; c->d_desc_out = nullptr; c->d_n_out = nullptr;
+    c->d_wtaps = nullptr; c->d_strips = nullptr; c->d_kps_out = nullptr; c->d_desc_out = nullptr; c->d_n_out = nullptr;
     c->h_kps = nullptr; c->h_desc = nullptr; c->h_n = nullptr; c->h_in = nullptr;
     c->in_bytes = c->h_in_bytes = 0; c->out_cap = 0;
     c->have_geom = false;
@@ -139,13 +139,12 @@ int build_geometry(orb_ctx* c, int w, int h) {
         L.fast_groups = (L.nCols + gmax - 1) / gmax;
         L.fast_G = (L.nCols + L.fast_groups - 1) / L.fast_groups;
         L.fast_cta_base = fast_ctas; fast_ctas += L.nRows * L.fast_groups;
-        // border fill: all words of the 38 top/bottom rows + the left/right border words of the h interior rows
+        // border fill: one warp per bordered row (border_items counts rows)
         const int first_w = (ORB_XOFF - ORB_EDGE) / 4;                          // word holding byte 13
         const int end_w = (ORB_XOFF + L.w + ORB_EDGE + 3) / 4;                   // one past the last border word
         L.border_words = end_w - first_w;
-        const int right_first = (ORB_XOFF + L.w) / 4;
         L.border_base = border_items;
-        border_items += 2 * ORB_EDGE * L.border_words + L.h * ((ORB_XOFF / 4 - first_w) + (end_w - right_first));
+        border_items += L.h + 2 * ORB_EDGE;
         // blur: one thread = one output word x ORB_BLUR_ROWS rows
         L.blur_wpr = (L.w + 3) / 4;
         L.blur_base = blur_items; blur_items += L.blur_wpr * ((L.h + ORB_BLUR_ROWS - 1) / ORB_BLUR_ROWS);
@@ -153,7 +152,7 @@ int build_geometry(orb_ctx* c, int w, int h) {
     if (max_node_cap > 65535) { orb_set_error("nfeatures too large"); return ORB_ERR_INVALID; }
     if ((size_t)max_node_cap * 80 > 200 * 1024) { orb_set_error("nfeatures too large for the quadtree kernel"); return ORB_ERR_INVALID; }
     g.total_cells = cells; g.total_kp_slots = kp_slots; g.max_node_cap = max_node_cap;
-    g.fast_ctas = fast_ctas; g.border_items = border_items; g.blur_items = blur_items;
+    g.border_items = border_items; g.blur_items = blur_items;
     g.pyr_frame_total = pyr_off / F;
     // resize taps: per-column / per-row tables + the packed per-output-word table of the fast path
     std::vector<ResizeTap> h_taps(std::max(taps, 1));
@@ -177,6 +176,47 @@ int build_geometry(orb_ctx* c, int w, int h) {
             }
         }
     }
+
+    // FAST strips: valid cells only (ORBextractor.cc:822-837 skip rules), everything a CTA needs precomputed
+    std::vector<FastStrip> strips;
+    for (int l = 0; l < g.nlevels; ++l) {
+        LevelGeom& L = g.lv[l];
+        L.fast_cta_base = (int)strips.size();
+        for (int i = 0; i < L.nRows; ++i) {
+            const int iniY = ORB_MINB + i * L.hCell;
+            if (iniY >= L.maxBY - 3) continue;
+            const int ch = std::min(iniY + L.hCell + 6, L.maxBY) - iniY;
+            if (ch < 7) continue;                                   // cv::FAST returns nothing on such a sub-image
+            for (int j0 = 0; j0 < L.nCols; j0 += L.fast_G) {
+                int ncell = 0, X1 = 0;
+                for (int j = j0; j < std::min(j0 + L.fast_G, L.nCols); ++j) {
+                    const int iniX = ORB_MINB + j * L.wCell;
+                    if (iniX >= L.maxBX - 6) break;
+                    const int maxX = std::min(iniX + L.wCell + 6, L.maxBX);
+                    if (maxX - iniX < 7) break;
+                    ncell = j - j0 + 1; X1 = maxX;
+                }
+                if (ncell == 0) continue;
+                FastStrip s;
+                memset(&s, 0, sizeof(s));
+                s.level = l; s.i = i; s.j0 = j0; s.ncell = ncell; s.iniY = iniY; s.ch = ch;
+                s.X0 = ORB_MINB + j0 * L.wCell; s.tw = X1 - s.X0;
+                // interior rows start 16-byte aligned, so the tile's byte alignment is X0 & 3; one spare word on the left
+                s.a = (s.X0 & 3) + 4;
+                s.lw = (s.a + s.tw + 3) >> 2;
+                const int sb_lo = s.a + 3, sb_hi = s.a + 3 + (s.tw - 6);
+                s.wlo = sb_lo >> 2; s.nw = ((sb_hi - 1) >> 2) - s.wlo + 1;
+                s.inv_lw = 0xFFFFFFFFu / (unsigned)s.lw + 1u;
+                s.inv_nw = 0xFFFFFFFFu / (unsigned)s.nw + 1u;
+                s.inv_wc = 0xFFFFFFFFu / (unsigned)L.wCell + 1u;
+                strips.push_back(s);
+            }
+        }
+    }
+    g.fast_ctas = (int)strips.size();
+    if (strips.empty()) strips.push_back(FastStrip());
+    ORB_CUDA(cudaMalloc(&c->d_strips, sizeof(FastStrip) * strips.size()));
+    ORB_CUDA(cudaMemcpyAsync(c->d_strips, strips.data(), sizeof(FastStrip) * strips.size(), cudaMemcpyHostToDevice, c->stream));
 
     c->pyr_bytes = (size_t)pyr_off; c->blur_bytes = (size_t)blur_off; c->corner_elems = (size_t)corner_off;
     ORB_CUDA(cudaMalloc(&c->d_pyr, c->pyr_bytes + 256));
@@ -314,6 +354,24 @@ static int ensure_device(orb_ctx* c) {
         ORB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         c->own_stream = true;
     }
+    if (!c->d_mom_tab) {
+        // IC_Angle (ORBextractor.cc:77-104) as word dot products: for patch alignment a, item = row*9 + word holds the
+        // signed u-weights of the word's 4 bytes (0 outside the circular patch, umax from :463-478) and the 0/1 mask
+        static const int umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+        std::vector<uint2> tab(4 * 288);
+        for (int a = 0; a < 4; ++a)
+            for (int item = 0; item < 288; ++item) {
+                const int r = item / 9, wi = item % 9, v = r - ORB_HALF_PATCH;
+                unsigned wu = 0, wm = 0;
+                for (int b = 0; b < 4; ++b) {
+                    const int u = 4 * wi + b - a - ORB_HALF_PATCH;
+                    if (r <= 30 && abs(u) <= umax[abs(v)]) { wu |= (unsigned)(uint8_t)(int8_t)u << (8 * b); wm |= 1u << (8 * b); }
+                }
+                tab[a * 288 + item] = make_uint2(wu, wm);
+            }
+        ORB_CUDA(cudaMalloc(&c->d_mom_tab, sizeof(uint2) * tab.size()));
+        ORB_CUDA(cudaMemcpy(c->d_mom_tab, tab.data(), sizeof(uint2) * tab.size(), cudaMemcpyHostToDevice));
+    }
     if (!c->st_h2d) {
         ORB_CUDA(cudaStreamCreateWithFlags(&c->st_h2d, cudaStreamNonBlocking));
         ORB_CUDA(cudaStreamCreateWithFlags(&c->st_d2h, cudaStreamNonBlocking));
@@ -332,6 +390,7 @@ void orb_destroy(orb_ctx* c) {
         cudaSetDevice(c->device);
         if (c->stream) cudaStreamSynchronize(c->stream);
         free_geometry_buffers(c);
+        cudaFree(c->d_mom_tab);
         if (c->prof_ev[0][0])
             for (int r = 0; r < ORB_PROF_RING; ++r)
                 for (int s = 0; s <= ORB_NSTAGES; ++s) cudaEventDestroy(c->prof_ev[r][s]);

@@ -307,80 +307,88 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 #define OD_WARPS 8
 #define OD_KPW 4                       // keypoints per warp
 #define OD_KPB (OD_WARPS * OD_KPW)     // keypoints per CTA (== 32: one lane of warp 0 per keypoint in phase 2)
+#define OD_ITEMS 288                   // 31 patch rows x 9 aligned words, padded to 9 x 32 lanes
+#define OD_TAPR 19                     // |tap offset| <= 19 after rotation
 
-// Three phases per CTA of 32 keypoint slots:
-//   1. every warp accumulates the patch moments of its 4 keypoints (lane = patch column, 31 row loads in flight)
-//   2. warp 0, one LANE per keypoint: fastAtan2 + the double-precision sin/cos of pin (iii) (thread-parallel, so the
-//      long fp64 sequence is issued once per 32 keypoints instead of once per keypoint)
-//   3. every warp builds the 4 descriptors (lane = descriptor byte); the 512-point pattern sits in shared memory as
+__device__ __forceinline__ int dp4a_su(unsigned a_signed, unsigned b_unsigned, int c) {
+    int d;
+    asm("dp4a.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_signed), "r"(b_unsigned), "r"(c));
+    return d;
+}
+
+// One CTA = 32 consecutive OUTPUT keypoints of one frame (level-major order, ORBextractor.cc:1122-1147):
+//   1. every warp: prefix of the per-level kept counts -> (level, index) of its 4 keypoints; patch moments with
+//      aligned word loads: lane k takes (row, word) items k, k+32, ... of the 31 x 9-word patch window and two
+//      IDP.4A per word against a precomputed table of signed u-weights / circular-mask bytes (indexed by the
+//      alignment of the patch), then  m10 += sum u*I,  m01 += v * sum I
+//   2. warp 0, one LANE per keypoint: fastAtan2 + the double-precision sincos of pin (iii)
+//   3. every warp builds its 4 descriptors (lane = descriptor byte); the 512-point pattern sits in shared memory as
 //      float4 [8][32] so that a warp-wide read is conflict-free (a per-lane index into __constant__ serialises)
 __global__ void __launch_bounds__(OD_WARPS * 32)
 orient_describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur,
                        const unsigned long long* __restrict__ kept, const int* __restrict__ kept_count,
-                       orb_kp* __restrict__ kps_out, uint8_t* __restrict__ desc_out, int cap,
-                       int* __restrict__ n_out, const __grid_constant__ Geometry g) {
+                       const uint2* __restrict__ mom_tab, orb_kp* __restrict__ kps_out, uint8_t* __restrict__ desc_out,
+                       int cap, int* __restrict__ n_out, const __grid_constant__ Geometry g) {
     __shared__ float4 s_pat[8 * 32];
     __shared__ int s_m[OD_KPB][2];
     __shared__ float s_ang[OD_KPB], s_a[OD_KPB], s_b[OD_KPB];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int f = blockIdx.y;
-    const int* kc = kept_count + f * g.nlevels;
+    // ---- per-level kept counts: lane l holds level l, inclusive prefix by shuffles ----
+    const int kc = lane < g.nlevels ? kept_count[f * g.nlevels + lane] : 0;
+    int cum = kc;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, cum, o);
+        if (lane >= o) cum += y;
+    }
+    const int total = min(__shfl_sync(0xffffffffu, cum, ORB_MAX_LEVELS - 1), cap);
+    if (blockIdx.x == 0 && warp == 0) {
+        const int tot_all = __shfl_sync(0xffffffffu, cum, ORB_MAX_LEVELS - 1);
+        if (lane == 0) n_out[f] = tot_all;
+    }
+    if (blockIdx.x * OD_KPB >= total) return;   // uniform per CTA
     // pattern: byte `i` of the descriptor uses points 16 i .. 16 i + 15; s_pat[k * 32 + i] = (x0, y0, x1, y1) of bit k
     {
         const int k = threadIdx.x >> 5, i = threadIdx.x & 31;
         const int* p = c_pattern + i * 32 + 4 * k;   // one-off divergent constant reads, 4 per thread
         s_pat[k * 32 + i] = make_float4((float)p[0], (float)p[1], (float)p[2], (float)p[3]);
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        int tot = 0;
-        for (int l = 0; l < g.nlevels; ++l) tot += kc[l];
-        n_out[f] = tot;
-    }
-    // ---- slot -> (level, index, output row) for this warp's 4 keypoints ----
+    // ---- output index -> (level, index in level) for this warp's 4 keypoints ----
     int lv[OD_KPW], px[OD_KPW], py[OD_KPW], off[OD_KPW], sc[OD_KPW];
 #pragma unroll
     for (int q = 0; q < OD_KPW; ++q) {
-        const int slot = blockIdx.x * OD_KPB + warp * OD_KPW + q;
-        lv[q] = -1; px[q] = py[q] = off[q] = sc[q] = 0;
-        if (slot < g.total_kp_slots) {
-            int l = 0;
-            while (l + 1 < g.nlevels && slot >= g.lv[l + 1].kp_base) ++l;
-            const int i = slot - g.lv[l].kp_base;
-            if (i < kc[l]) {
-                int o = i;
-                for (int k = 0; k < l; ++k) o += kc[k];
-                if (o < cap) {
-                    const unsigned long long rec = kept[(long long)f * g.total_kp_slots + slot];
-                    lv[q] = l; off[q] = o; sc[q] = corner_score(rec);
-                    px[q] = corner_x(rec) + ORB_MINB; py[q] = corner_y(rec) + ORB_MINB;   // ORBextractor.cc:881-882
-                }
-            }
+        const int o = blockIdx.x * OD_KPB + warp * OD_KPW + q;
+        const unsigned below = __ballot_sync(0xffffffffu, lane < g.nlevels && o < cum);   // levels whose prefix exceeds o
+        lv[q] = -1; px[q] = py[q] = sc[q] = 0; off[q] = o;
+        if (o < total && below) {
+            const int l = __ffs(below) - 1;
+            const int first = __shfl_sync(0xffffffffu, cum - kc, l);
+            const unsigned long long rec = kept[(long long)f * g.total_kp_slots + g.lv[l].kp_base + (o - first)];
+            lv[q] = l; sc[q] = corner_score(rec);
+            px[q] = corner_x(rec) + ORB_MINB; py[q] = corner_y(rec) + ORB_MINB;   // ORBextractor.cc:881-882
         }
     }
     // ---- phase 1: IC_Angle moments (ORBextractor.cc:77-104) ----
 #pragma unroll
     for (int q = 0; q < OD_KPW; ++q) {
         int m10 = 0, m01 = 0;
-        if (lv[q] >= 0 && lane < 31) {
+        if (lv[q] >= 0) {
             const LevelGeom& L = g.lv[lv[q]];
-            const int pitch = L.pitch;
-            const uint8_t* center = pyr + L.base + (long long)f * L.frame_stride + L.ioff + py[q] * pitch + px[q];
-            const int u = lane - ORB_HALF_PATCH;
-            const int au = abs(u);
-            int col = 0;
+            const int a = (px[q] - ORB_HALF_PATCH) & 3;                       // alignment of the patch's first column
+            const uint8_t* p0 = pyr + L.base + (long long)f * L.frame_stride + L.ioff + (py[q] - ORB_HALF_PATCH) * L.pitch +
+                                (px[q] - ORB_HALF_PATCH - a);                 // 4-byte aligned
+            const uint2* tab = mom_tab + a * OD_ITEMS + lane;
+            const unsigned pw = (unsigned)L.pitch >> 2;
 #pragma unroll
-            for (int v = -ORB_HALF_PATCH; v <= ORB_HALF_PATCH; ++v) {
-                const int um = (v < 0 ? -v : v);
-                // umax = 15 15 15 15 14 14 14 13 13 12 11 10 9 8 6 3 (ORBextractor.cc:463-478), folded at compile time
-                const int lim = um <= 3 ? 15 : um <= 6 ? 14 : um <= 8 ? 13 : um == 9 ? 12 : um == 10 ? 11 : um == 11 ? 10 :
-                                um == 12 ? 9 : um == 13 ? 8 : um == 14 ? 6 : 3;
-                if (au <= lim) {
-                    const int val = center[v * pitch + u];
-                    col += val;
-                    m01 += v * val;
-                }
+            for (int j = 0; j < OD_ITEMS / 32; ++j) {
+                const int item = lane + 32 * j;
+                const int r = item / 9, wi = item - 9 * r;                    // rows 0..31 (row 31 has zero weights)
+                const unsigned pix = __ldg(reinterpret_cast<const unsigned*>(p0) + r * pw + wi);
+                const uint2 w = __ldg(tab + 32 * j);
+                m10 = dp4a_su(w.x, pix, m10);                                 // sum u * I
+                m01 += (r - ORB_HALF_PATCH) * (int)__dp4a(w.y, pix, 0u);      // v * sum I over the row's circular extent
             }
-            m10 = u * col;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -408,8 +416,10 @@ orient_describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restric
         const LevelGeom& L = g.lv[l];
         const int kq = warp * OD_KPW + q;
         const float a = s_a[kq], b = s_b[kq];
-        const int bp = L.bpitch;
-        const uint8_t* bc = blur + L.bbase + (long long)f * L.bframe_stride + py[q] * bp + px[q];
+        const unsigned bp = (unsigned)L.bpitch;
+        // taps are addressed with non-negative 32-bit offsets from the patch window's top-left corner
+        const uint8_t* b2 = blur + L.bbase + (long long)f * L.bframe_stride + (py[q] - OD_TAPR) * (int)bp + (px[q] - OD_TAPR);
+        const unsigned centre = OD_TAPR * bp + OD_TAPR;
         unsigned val = 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -418,7 +428,7 @@ orient_describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restric
             const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(pt.x, a), __fmul_rn(pt.y, b)));
             const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(pt.z, b), __fmul_rn(pt.w, a)));
             const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(pt.z, a), __fmul_rn(pt.w, b)));
-            const int t0 = bc[r0 * bp + c0], t1 = bc[r1 * bp + c1];
+            const unsigned t0 = b2[centre + (unsigned)(r0 * (int)bp + c0)], t1 = b2[centre + (unsigned)(r1 * (int)bp + c1)];
             val |= (unsigned)(t0 < t1) << k;
         }
         // 32-byte descriptor row: gather 4 lanes' bytes into one word, 8 lanes store 8 words (one 32-B sector)
@@ -516,7 +526,7 @@ int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int F, int f0, size_t 
     ORB_STAGE_MARK(4);
     {   // K4 + K6
         orient_describe_kernel<<<dim3((g.total_kp_slots + OD_KPB - 1) / OD_KPB, F), OD_WARPS * 32, 0, st>>>(
-            c->d_pyr, c->d_blur, d_kept, d_kept_count, d_kps, d_desc, cap, d_n_out, g);
+            c->d_pyr, c->d_blur, d_kept, d_kept_count, c->d_mom_tab, d_kps, d_desc, cap, d_n_out, g);
         c->launches++;
     }
     ORB_STAGE_MARK(5);

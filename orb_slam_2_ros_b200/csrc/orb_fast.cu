@@ -85,7 +85,7 @@ __device__ __forceinline__ unsigned quick2(unsigned c, unsigned r0, unsigned r8,
 }
 
 __global__ void __launch_bounds__(FS_THREADS)
-fast_strip_kernel(const uint8_t* __restrict__ pyr, unsigned long long* __restrict__ corners,
+fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__ strips, unsigned long long* __restrict__ corners,
                   int* __restrict__ corner_count, const __grid_constant__ Geometry g) {
     extern __shared__ __align__(16) uint8_t fs_smem[];
     uint8_t* tile = fs_smem;                                                                     // FS_ROWS x FS_PITCH pixels
@@ -96,38 +96,21 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, unsigned long long* __restric
     __shared__ int s_any[FS_MAXG];
     __shared__ int s_nscored, s_nout, s_base;
 
-    const int cta = blockIdx.x, f = blockIdx.y;
-    int l = 0;
-    while (l + 1 < g.nlevels && cta >= g.lv[l + 1].fast_cta_base) ++l;
+    const int f = blockIdx.y;
+    const FastStrip S = strips[blockIdx.x];               // host-precomputed (uniform loads)
+    const int l = S.level;
     const LevelGeom& L = g.lv[l];
-    const int ci = cta - L.fast_cta_base;
-    const int i = ci / L.fast_groups, gi = ci - i * L.fast_groups;
-    // reference ORBextractor.cc:822-837 (all values are integers held in floats there)
-    const int iniY = ORB_MINB + i * L.hCell;
-    if (iniY >= L.maxBY - 3) return;
-    const int ch = min(iniY + L.hCell + 6, L.maxBY) - iniY;
-    if (ch < 7) return;                                    // cv::FAST returns nothing on such a sub-image
-    const int j0 = gi * L.fast_G;
-    int ncell = 0, X1 = 0;                                 // valid cells of this strip, right end of the last one
-    for (int j = j0; j < min(j0 + L.fast_G, L.nCols); ++j) {
-        const int iniX = ORB_MINB + j * L.wCell;
-        if (iniX >= L.maxBX - 6) break;
-        const int maxX = min(iniX + L.wCell + 6, L.maxBX);
-        if (maxX - iniX < 7) break;
-        ncell = j - j0 + 1; X1 = maxX;
-    }
-    if (ncell == 0) return;
-    const int X0 = ORB_MINB + j0 * L.wCell;
-    const int tw = X1 - X0;                                // tile width in pixels (<= 256)
+    const int i = S.i, j0 = S.j0;
+    const int ch = S.ch, tw = S.tw;
     const int ew = tw - 6, eh = ch - 6;                    // evaluated area
 
     // ---- load the tile as aligned words: tile pixel (x, y) lands at tile[y * FS_PITCH + a + x] ----
-    const uint8_t* src = pyr + L.base + (long long)f * L.frame_stride + L.ioff + iniY * L.pitch + X0;
-    // (one extra word on the left, so that word index wd - 1 of the first evaluated word stays inside the row)
-    const int a = (int)((uintptr_t)src & 3) + 4;
-    const unsigned* src_w = reinterpret_cast<const unsigned*>(src - a);
-    const int lw = (a + tw + 3) >> 2;                      // words per row to load (<= 66)
-    const unsigned inv_lw = 0xFFFFFFFFu / (unsigned)lw + 1u;
+    // (a = (X0 & 3) + 4: one spare word on the left, so that word index wd - 1 of the first evaluated word exists)
+    const int a = S.a;
+    const unsigned* src_w = reinterpret_cast<const unsigned*>(pyr + L.base + (long long)f * L.frame_stride + L.ioff +
+                                                              S.iniY * L.pitch + S.X0 - a);
+    const int lw = S.lw;                                   // words per row to load (<= 66)
+    const unsigned inv_lw = S.inv_lw;
     const int gpw = L.pitch >> 2;
     for (int k = threadIdx.x; k < ch * lw; k += FS_THREADS) {
         const int r = (int)__umulhi((unsigned)k, inv_lw), wd = k - r * lw;
@@ -143,9 +126,8 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, unsigned long long* __restric
     const int tmin = g.min_th, tini = g.ini_th;
     const unsigned tp1 = (unsigned)(tmin + 1) * 0x10001u, ntp1 = ((unsigned)(-(tmin + 1)) & 0xFFFFu) * 0x10001u;
     const int sb_lo = a + 3, sb_hi = a + 3 + ew;
-    const int wlo = sb_lo >> 2, whi = (sb_hi - 1) >> 2;
-    const int nw = whi - wlo + 1;                          // words holding evaluated pixels (<= 64)
-    const unsigned inv_nw = 0xFFFFFFFFu / (unsigned)nw + 1u;
+    const int wlo = S.wlo, nw = S.nw, whi = wlo + nw - 1;  // words holding evaluated pixels (<= 64)
+    const unsigned inv_nw = S.inv_nw;
     const unsigned vfirst = 0xFu << (sb_lo & 3), vlast = 0xFu >> (3 - ((sb_hi - 1) & 3));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int total = eh * nw;                             // <= 60 * 64 words: at most 15 iterations of 256 threads
@@ -222,17 +204,18 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, unsigned long long* __restric
 
     // ---- pass 2 / 3: NMS (strict >, neighbours outside the cell's evaluated area count as 0) ----
     const int wCell = L.wCell;
-    const unsigned inv_wc = 0xFFFFFFFFu / (unsigned)wCell + 1u;
+    const unsigned inv_wc = S.inv_wc;
     auto nms_max = [&](int r, int sb, int sc, int& jj, int& xr) -> bool {
         const int xe = sb - sb_lo;                         // column inside the strip's evaluated area
         jj = (int)__umulhi((unsigned)xe, inv_wc);
         xr = xe - jj * wCell;
         const bool left = (xr == 0), right = (xr == wCell - 1) || (xe == ew - 1);   // cell edges: neighbours beyond are 0
         const uint8_t* q = score + (r + 1) * FS_PITCH + sb;
-        bool ok = sc > q[-FS_PITCH] && sc > q[FS_PITCH];
-        if (!left) ok = ok && sc > q[-1] && sc > q[-FS_PITCH - 1] && sc > q[FS_PITCH - 1];
-        if (!right) ok = ok && sc > q[1] && sc > q[-FS_PITCH + 1] && sc > q[FS_PITCH + 1];
-        return ok;
+        // branch-free: all 8 neighbours are loaded, the columns beyond a cell edge are masked to 0
+        const int l3 = __vimax3_s32(q[-1], q[-FS_PITCH - 1], q[FS_PITCH - 1]);
+        const int r3 = __vimax3_s32(q[1], q[-FS_PITCH + 1], q[FS_PITCH + 1]);
+        const int m = __vimax3_s32(max((int)q[-FS_PITCH], (int)q[FS_PITCH]), left ? 0 : l3, right ? 0 : r3);
+        return sc > m;
     };
     auto emit = [&](int r, int sb, int sc, int jj, int xr) {
         // vToDistributeKeys coordinates (ORBextractor.cc:856-857) and the reference's visiting order key
@@ -311,7 +294,7 @@ int orb_launch_fast(orb_ctx* c, const Geometry& g, int* d_corner_count, int F, c
         ORB_CUDA(cudaFuncSetAttribute(fast_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM));
         c->fast_attr_set = true;
     }
-    fast_strip_kernel<<<dim3(g.fast_ctas, F), FS_THREADS, FS_SMEM, st>>>(c->d_pyr, c->d_corners, d_corner_count, g);
+    fast_strip_kernel<<<dim3(g.fast_ctas, F), FS_THREADS, FS_SMEM, st>>>(c->d_pyr, c->d_strips, c->d_corners, d_corner_count, g);
     c->launches++;
     ORB_CUDA(cudaGetLastError());
     return ORB_OK;

@@ -54,7 +54,7 @@ struct LevelGeom {
     int fast_resize;           // 1: every output word's source taps fit 3 aligned source words (scale <= 4/3)
     int fast_G, fast_groups;   // FAST strips: cells per CTA, CTAs per cell row
     int fast_cta_base;         // number of FAST CTAs of levels < l (per frame)
-    int border_base;           // number of border-fill items (words) of levels < l (per frame)
+    int border_base;           // number of bordered rows (= border-fill warps) of levels < l (per frame)
     int border_words;          // words per bordered row that the border kernel may touch
     int blur_base, blur_wpr;   // blur: number of thread items of levels < l; words per row
     float scale;               // mvScaleFactor[l]
@@ -79,6 +79,12 @@ struct __align__(16) ResizeWord {  // 4 adjacent destination columns (one output
     unsigned off;        // byte offset (0..7) of each column's left tap inside (word wb, wb+1, wb+2), 8 bits each
     unsigned cc[4];      // c0 | c1 << 16 per column (Q11)
     int pad[2];
+};
+struct __align__(16) FastStrip {   // one CTA of fast_strip_kernel: up to fast_G consecutive valid cells of one cell row
+    int level, i, j0, ncell;       // cell row, first cell column, number of valid cells
+    int iniY, ch, X0, tw;          // cell sub-image rows [iniY, iniY+ch), tile columns [X0, X0+tw) (interior coords)
+    int a, lw, nw, wlo;            // smem byte shift, words loaded per row, words with evaluated pixels, first such word
+    unsigned inv_lw, inv_nw, inv_wc, pad;   // ceil(2^32 / x) magic numbers for the index divisions
 };
 #define ORB_BLUR_ROWS 16   // output rows per blur thread
 #define ORB_RESIZE_ROWS 8  // output rows per resize thread
@@ -123,6 +129,8 @@ struct orb_ctx {
     int* d_kept_count = nullptr;                        // [max_batch][nlevels]
     ResizeTap* d_taps = nullptr;
     ResizeWord* d_wtaps = nullptr;
+    FastStrip* d_strips = nullptr;
+    uint2* d_mom_tab = nullptr;   // IC_Angle weight table [4 alignments][288 items] (orient_describe_kernel)
     bool fast_attr_set = false;
     orb_kp* d_kps_out = nullptr; uint8_t* d_desc_out = nullptr; int* d_n_out = nullptr; int out_cap = 0;
     orb_kp* h_kps = nullptr; uint8_t* h_desc = nullptr; int* h_n = nullptr; uint8_t* h_in = nullptr;  // pinned

@@ -135,41 +135,48 @@ pyr_resize_generic_kernel(uint8_t* __restrict__ pyr, const ResizeTap* __restrict
 }
 
 // ---- the 19-px BORDER_REFLECT_101 frame of every level, one launch ---------------------------------------
+// One warp per bordered row of one level: the 38 top/bottom rows are written in full, interior rows get their
+// left and right border words.  A single reflection suffices (19 < w, h: smaller levels are rejected at geometry
+// build time because the reference's 30-px cell grid does not exist there either).
+__device__ __forceinline__ int reflect1(int i, int n) {
+    i = i < 0 ? -i : i;
+    return i >= n ? 2 * n - 2 - i : i;
+}
+
 __global__ void __launch_bounds__(256)
 pyr_border_kernel(uint8_t* __restrict__ pyr, const __grid_constant__ Geometry g) {
-    const int item = blockIdx.x * blockDim.x + threadIdx.x;
-    if (item >= g.border_items) return;
+    const int lane = threadIdx.x & 31;
+    const int job = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // bordered row index over all levels
+    if (job >= g.border_items) return;
     int l = 0;
-    while (l + 1 < g.nlevels && item >= g.lv[l + 1].border_base) ++l;
+    while (l + 1 < g.nlevels && job >= g.lv[l + 1].border_base) ++l;
     const LevelGeom& L = g.lv[l];
     const int f = blockIdx.y;
-    int it = item - L.border_base;
-    const int first_w = (ORB_XOFF - ORB_EDGE) / 4;
-    const int nbw = L.border_words;
-    int row, word;
-    if (it < 2 * ORB_EDGE * nbw) {                       // top / bottom rows: every word of the bordered row
-        const int r = it / nbw;
-        word = first_w + (it - r * nbw);
-        row = r < ORB_EDGE ? r : L.h + r;                // r in [19, 38) -> rows h+19 .. h+37
-    } else {                                              // interior rows: left and right border words only
-        it -= 2 * ORB_EDGE * nbw;
-        const int nleft = ORB_XOFF / 4 - first_w;
-        const int right_first = (ORB_XOFF + L.w) / 4;
-        const int per_row = nleft + (first_w + nbw - right_first);
-        const int r = it / per_row, k = it - r * per_row;
-        row = ORB_EDGE + r;
-        word = k < nleft ? first_w + k : right_first + (k - nleft);
-    }
+    const int row = job - L.border_base;                                       // 0 .. h + 37
     uint8_t* img = pyr + L.base + (long long)f * L.frame_stride;
-    const uint8_t* srow = img + L.ioff + reflect101(row - ORB_EDGE, L.h) * L.pitch;
-    unsigned v = 0;
+    const uint8_t* srow = img + L.ioff + reflect1(row - ORB_EDGE, L.h) * L.pitch;
+    unsigned* drow = reinterpret_cast<unsigned*>(img + row * L.pitch);
+    const int first_w = (ORB_XOFF - ORB_EDGE) / 4;                             // word holding byte 13
+    const int end_w = first_w + L.border_words;                                // one past the last border word
+    const int lo = ORB_XOFF - ORB_EDGE, hi = ORB_XOFF + L.w + ORB_EDGE;        // bordered bytes of a row
+    auto put = [&](int word) {
+        unsigned v = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int q = 4 * word + k;                       // byte position in the row
-        if (q >= ORB_XOFF - ORB_EDGE && q < ORB_XOFF + L.w + ORB_EDGE)
-            v |= (unsigned)srow[reflect101(q - ORB_XOFF, L.w)] << (8 * k);   // identity on interior bytes
+        for (int k = 0; k < 4; ++k) {
+            const int q = 4 * word + k;
+            const unsigned b = srow[reflect1(min(max(q, lo), hi - 1) - ORB_XOFF, L.w)];   // identity on interior bytes
+            v |= (q >= lo && q < hi ? b : 0u) << (8 * k);
+        }
+        drow[word] = v;
+    };
+    if (row < ORB_EDGE || row >= L.h + ORB_EDGE) {
+        for (int word = first_w + lane; word < end_w; word += 32) put(word);
+    } else {
+        const int nleft = ORB_XOFF / 4 - first_w;                              // 5 words: bytes 12..31
+        const int right_first = (ORB_XOFF + L.w) / 4;                          // may straddle interior | border
+        const int word = lane < nleft ? first_w + lane : right_first + (lane - nleft);
+        if (word < end_w) put(word);
     }
-    *reinterpret_cast<unsigned*>(img + row * L.pitch + 4 * word) = v;
 }
 
 }  // namespace
@@ -197,7 +204,7 @@ int orb_launch_pyramid(orb_ctx* c, const Geometry& g, const uint8_t* d_imgs, int
         }
         c->launches++;
     }
-    pyr_border_kernel<<<dim3((g.border_items + 255) / 256, F), 256, 0, st>>>(c->d_pyr, g);
+    pyr_border_kernel<<<dim3((g.border_items + 7) / 8, F), 256, 0, st>>>(c->d_pyr, g);
     c->launches++;
     ORB_CUDA(cudaGetLastError());
     return ORB_OK;
