@@ -78,7 +78,7 @@ int build_geometry(orb_ctx* c, int w, int h) {
     g.nlevels = c->nlevels; g.w = w; g.h = h; g.ini_th = c->ini_th; g.min_th = c->min_th;
     const int F = c->max_batch;
     long long pyr_off = 0, blur_off = 0, corner_off = 0;
-    int cells = 0, kp_slots = 0, taps = 0, wtaps = 0, max_node_cap = 0, fast_ctas = 0, border_items = 0, blur_items = 0;
+    int cells = 0, kp_slots = 0, taps = 0, wtaps = 0, max_node_cap = 0, fast_ctas = 0, border_items = 0, copy_items = 0, blur_items = 0;
     for (int l = 0; l < g.nlevels; ++l) {
         LevelGeom& L = g.lv[l];
         L.w = cv_round_f((float)w * c->inv_scale[l]);  // ORBextractor.cc:1159
@@ -145,6 +145,9 @@ int build_geometry(orb_ctx* c, int w, int h) {
         L.border_words = end_w - first_w;
         L.border_base = border_items;
         border_items += L.h + 2 * ORB_EDGE;
+        L.copy_base = copy_items;
+        L.inv_wpr = 0xFFFFFFFFu / (unsigned)std::max(L.w >> 2, 1) + 1u;
+        copy_items += 2 * ORB_EDGE * (L.w >> 2);
         // blur: one thread = one output word x ORB_BLUR_ROWS rows
         L.blur_wpr = (L.w + 3) / 4;
         L.blur_base = blur_items; blur_items += L.blur_wpr * ((L.h + ORB_BLUR_ROWS - 1) / ORB_BLUR_ROWS);
@@ -152,7 +155,7 @@ int build_geometry(orb_ctx* c, int w, int h) {
     if (max_node_cap > 65535) { orb_set_error("nfeatures too large"); return ORB_ERR_INVALID; }
     if ((size_t)max_node_cap * 80 > 200 * 1024) { orb_set_error("nfeatures too large for the quadtree kernel"); return ORB_ERR_INVALID; }
     g.total_cells = cells; g.total_kp_slots = kp_slots; g.max_node_cap = max_node_cap;
-    g.border_items = border_items; g.blur_items = blur_items;
+    g.border_items = border_items; g.border_copy_items = copy_items; g.blur_items = blur_items;
     g.pyr_frame_total = pyr_off / F;
     // resize taps: per-column / per-row tables + the packed per-output-word table of the fast path
     std::vector<ResizeTap> h_taps(std::max(taps, 1));

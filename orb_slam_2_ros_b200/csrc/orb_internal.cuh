@@ -56,6 +56,8 @@ struct LevelGeom {
     int fast_cta_base;         // number of FAST CTAs of levels < l (per frame)
     int border_base;           // number of bordered rows (= border-fill warps) of levels < l (per frame)
     int border_words;          // words per bordered row that the border kernel may touch
+    int copy_base;             // number of top/bottom row-copy items (words) of levels < l (per frame)
+    unsigned inv_wpr;          // ceil(2^32 / (w >> 2))
     int blur_base, blur_wpr;   // blur: number of thread items of levels < l; words per row
     float scale;               // mvScaleFactor[l]
     float size;                // (float)(int)(PATCH_SIZE * scale)
@@ -65,7 +67,7 @@ struct Geometry {
     int nlevels, w, h;
     int ini_th, min_th;
     int total_cells, total_kp_slots, max_node_cap, max_tile_bytes;
-    int fast_ctas, border_items, blur_items;   // per-frame grid sizes of the strip / border / blur kernels
+    int fast_ctas, border_items, border_copy_items, blur_items;   // per-frame grid sizes of the strip / border / blur kernels
     long long pyr_frame_total;   // not used for addressing (level-major layout), informational
     LevelGeom lv[ORB_MAX_LEVELS];
 };

@@ -53,14 +53,16 @@ pyr_copy0_kernel(const uint8_t* __restrict__ in, size_t row_stride, size_t frame
 }
 
 // ---- fast resize: one output word x ORB_RESIZE_ROWS rows per thread ------------------------------------
-__device__ __forceinline__ void hrow4(const unsigned* __restrict__ srow, const ResizeWord& t, unsigned (&h)[4]) {
-    const unsigned w0 = __ldg(srow + t.wb), w1 = __ldg(srow + t.wb + 1), w2 = __ldg(srow + t.wb + 2);
+struct ColSel { unsigned sh[4]; bool hi[4]; };   // per column: funnel-shift amount and which word pair holds its taps
+
+__device__ __forceinline__ void hrow4(const unsigned* __restrict__ srow, int wb, const ColSel& cs, const unsigned (&cc)[4],
+                                      unsigned (&h)[4]) {
+    const unsigned w0 = __ldg(srow + wb), w1 = __ldg(srow + wb + 1), w2 = __ldg(srow + wb + 2);
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
-        const unsigned off = (t.off >> (8 * p)) & 0xFFu;          // 0..7
-        const unsigned lo = off < 4 ? w0 : w1, hi = off < 4 ? w1 : w2;
-        const unsigned pair = __funnelshift_r(lo, hi, (off & 3u) * 8u);   // byte0 = S[s], byte1 = S[s+1]
-        h[p] = __dp2a_lo(t.cc[p], pair, 0u);                       // c0*S[s] + c1*S[s+1]
+        const unsigned lo = cs.hi[p] ? w1 : w0, hi = cs.hi[p] ? w2 : w1;
+        const unsigned pair = __funnelshift_r(lo, hi, cs.sh[p]);      // byte0 = S[s], byte1 = S[s+1]
+        h[p] = __dp2a_lo(cc[p], pair, 0u);                            // c0*S[s] + c1*S[s+1]
     }
 }
 
@@ -76,32 +78,43 @@ pyr_resize_fast_kernel(uint8_t* __restrict__ pyr, const ResizeTap* __restrict__ 
     const int strip = item / wpr, wc = item - strip * wpr;
     const int f = blockIdx.y;
     const ResizeWord t = wtaps[L.xwtab + wc];
+    ColSel cs;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const unsigned off = (t.off >> (8 * p)) & 0xFFu;              // 0..7
+        cs.sh[p] = (off & 3u) * 8u; cs.hi[p] = off >= 4u;
+    }
+    const unsigned cc[4] = {t.cc[0], t.cc[1], t.cc[2], t.cc[3]};
     const uint8_t* S = pyr + P.base + (long long)f * P.frame_stride + P.ioff;    // 16-byte aligned
     uint8_t* D = pyr + L.base + (long long)f * L.frame_stride + L.ioff + 4 * wc;
     const int y0 = strip * ORB_RESIZE_ROWS, y1 = min(y0 + ORB_RESIZE_ROWS, L.h);
+    const uint2* ytab = reinterpret_cast<const uint2*>(taps + L.ytab);   // ResizeTap = {u16 s0, u16 s1, s16 c0, s16 c1}
+    const int ppw = P.pitch >> 2;
     unsigned h0[4], h1[4];
     int have1 = -1;                                       // source row whose horizontal pass sits in h1
     for (int y = y0; y < y1; ++y) {
-        const ResizeTap ty = taps[L.ytab + y];
-        if ((int)ty.s0 == have1) {
+        const uint2 ty = __ldg(ytab + y);
+        const int s0 = (int)(ty.x & 0xFFFFu), s1 = (int)(ty.x >> 16);
+        if (s0 == have1) {
 #pragma unroll
             for (int p = 0; p < 4; ++p) h0[p] = h1[p];
         } else {
-            hrow4(reinterpret_cast<const unsigned*>(S + (int)ty.s0 * P.pitch), t, h0);
+            hrow4(reinterpret_cast<const unsigned*>(S) + s0 * ppw, t.wb, cs, cc, h0);
         }
-        if (ty.s1 == ty.s0) {
+        if (s1 == s0) {
 #pragma unroll
             for (int p = 0; p < 4; ++p) h1[p] = h0[p];
         } else {
-            hrow4(reinterpret_cast<const unsigned*>(S + (int)ty.s1 * P.pitch), t, h1);
+            hrow4(reinterpret_cast<const unsigned*>(S) + s1 * ppw, t.wb, cs, cc, h1);
         }
-        have1 = ty.s1;
-        const int b0 = ty.c0, b1 = ty.c1;
+        have1 = s1;
+        // ((b*(h>>4))>>16) == umulhi(b<<16, h>>4): 0 <= b <= 2048, h>>4 < 2^15
+        const unsigned b0 = (ty.y & 0xFFFFu) << 16, b1 = ty.y & 0xFFFF0000u;
         unsigned v = 0;
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-            const int o = (((b0 * (int)(h0[p] >> 4)) >> 16) + ((b1 * (int)(h1[p] >> 4)) >> 16) + 2) >> 2;
-            v |= (unsigned)o << (8 * p);                  // 0 <= o <= 255
+            const unsigned o = (__umulhi(b0, h0[p] >> 4) + __umulhi(b1, h1[p] >> 4) + 2u) >> 2;
+            v |= o << (8 * p);                            // 0 <= o <= 255
         }
         *reinterpret_cast<unsigned*>(D + y * L.pitch) = v;
     }
@@ -135,9 +148,12 @@ pyr_resize_generic_kernel(uint8_t* __restrict__ pyr, const ResizeTap* __restrict
 }
 
 // ---- the 19-px BORDER_REFLECT_101 frame of every level, one launch ---------------------------------------
-// One warp per bordered row of one level: the 38 top/bottom rows are written in full, interior rows get their
-// left and right border words.  A single reflection suffices (19 < w, h: smaller levels are rejected at geometry
-// build time because the reference's 30-px cell grid does not exist there either).
+// Two kinds of work items, one thread each:
+//   side  : (bordered row, slot) — slots 0..4 are the 5 left border words (bytes 12..31), slots 5..15 the right
+//           border words (the first may straddle interior | border); bytes come from the reflected interior row
+//   copy  : (top/bottom bordered row, interior word) — a plain aligned word copy of the reflected interior row
+// A single reflection suffices (19 < w, h: smaller levels are rejected at geometry build time because the
+// reference's 30-px cell grid does not exist there either).
 __device__ __forceinline__ int reflect1(int i, int n) {
     i = i < 0 ? -i : i;
     return i >= n ? 2 * n - 2 - i : i;
@@ -145,21 +161,21 @@ __device__ __forceinline__ int reflect1(int i, int n) {
 
 __global__ void __launch_bounds__(256)
 pyr_border_kernel(uint8_t* __restrict__ pyr, const __grid_constant__ Geometry g) {
-    const int lane = threadIdx.x & 31;
-    const int job = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // bordered row index over all levels
-    if (job >= g.border_items) return;
-    int l = 0;
-    while (l + 1 < g.nlevels && job >= g.lv[l + 1].border_base) ++l;
-    const LevelGeom& L = g.lv[l];
+    const int item = blockIdx.x * blockDim.x + threadIdx.x;
     const int f = blockIdx.y;
-    const int row = job - L.border_base;                                       // 0 .. h + 37
-    uint8_t* img = pyr + L.base + (long long)f * L.frame_stride;
-    const uint8_t* srow = img + L.ioff + reflect1(row - ORB_EDGE, L.h) * L.pitch;
-    unsigned* drow = reinterpret_cast<unsigned*>(img + row * L.pitch);
-    const int first_w = (ORB_XOFF - ORB_EDGE) / 4;                             // word holding byte 13
-    const int end_w = first_w + L.border_words;                                // one past the last border word
-    const int lo = ORB_XOFF - ORB_EDGE, hi = ORB_XOFF + L.w + ORB_EDGE;        // bordered bytes of a row
-    auto put = [&](int word) {
+    const int side_items = g.border_items * 16;
+    if (item < side_items) {
+        const int job = item >> 4, slot = item & 15;
+        int l = 0;
+        while (l + 1 < g.nlevels && job >= g.lv[l + 1].border_base) ++l;
+        const LevelGeom& L = g.lv[l];
+        const int row = job - L.border_base;                                   // 0 .. h + 37
+        const int first_w = (ORB_XOFF - ORB_EDGE) / 4, nleft = ORB_XOFF / 4 - first_w;
+        const int word = slot < nleft ? first_w + slot : (ORB_XOFF + L.w) / 4 + (slot - nleft);
+        if (word >= first_w + L.border_words) return;
+        uint8_t* img = pyr + L.base + (long long)f * L.frame_stride;
+        const uint8_t* srow = img + L.ioff + reflect1(row - ORB_EDGE, L.h) * L.pitch;
+        const int lo = ORB_XOFF - ORB_EDGE, hi = ORB_XOFF + L.w + ORB_EDGE;    // bordered bytes of a row
         unsigned v = 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -167,15 +183,20 @@ pyr_border_kernel(uint8_t* __restrict__ pyr, const __grid_constant__ Geometry g)
             const unsigned b = srow[reflect1(min(max(q, lo), hi - 1) - ORB_XOFF, L.w)];   // identity on interior bytes
             v |= (q >= lo && q < hi ? b : 0u) << (8 * k);
         }
-        drow[word] = v;
-    };
-    if (row < ORB_EDGE || row >= L.h + ORB_EDGE) {
-        for (int word = first_w + lane; word < end_w; word += 32) put(word);
+        reinterpret_cast<unsigned*>(img + row * L.pitch)[word] = v;
     } else {
-        const int nleft = ORB_XOFF / 4 - first_w;                              // 5 words: bytes 12..31
-        const int right_first = (ORB_XOFF + L.w) / 4;                          // may straddle interior | border
-        const int word = lane < nleft ? first_w + lane : right_first + (lane - nleft);
-        if (word < end_w) put(word);
+        int it = item - side_items;
+        if (it >= g.border_copy_items) return;
+        int l = 0;
+        while (l + 1 < g.nlevels && it >= g.lv[l + 1].copy_base) ++l;
+        const LevelGeom& L = g.lv[l];
+        it -= L.copy_base;
+        const int wpr = L.w >> 2;                                              // whole interior words (a partial last word is a side item)
+        const int r = (int)__umulhi((unsigned)it, L.inv_wpr), wd = it - r * wpr;
+        const int row = r < ORB_EDGE ? r : L.h + r;                            // r in [19, 38) -> rows h+19 .. h+37
+        uint8_t* img = pyr + L.base + (long long)f * L.frame_stride;
+        const unsigned* srow = reinterpret_cast<const unsigned*>(img + L.ioff + reflect1(row - ORB_EDGE, L.h) * L.pitch);
+        reinterpret_cast<unsigned*>(img + row * L.pitch + ORB_XOFF)[wd] = srow[wd];
     }
 }
 
@@ -204,7 +225,7 @@ int orb_launch_pyramid(orb_ctx* c, const Geometry& g, const uint8_t* d_imgs, int
         }
         c->launches++;
     }
-    pyr_border_kernel<<<dim3((g.border_items + 7) / 8, F), 256, 0, st>>>(c->d_pyr, g);
+    pyr_border_kernel<<<dim3((g.border_items * 16 + g.border_copy_items + 255) / 256, F), 256, 0, st>>>(c->d_pyr, g);
     c->launches++;
     ORB_CUDA(cudaGetLastError());
     return ORB_OK;
