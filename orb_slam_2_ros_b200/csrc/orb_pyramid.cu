@@ -175,13 +175,19 @@ pyr_border_kernel(uint8_t* __restrict__ pyr, const __grid_constant__ Geometry g)
         if (word >= first_w + L.border_words) return;
         uint8_t* img = pyr + L.base + (long long)f * L.frame_stride;
         const uint8_t* srow = img + L.ioff + reflect1(row - ORB_EDGE, L.h) * L.pitch;
-        const int lo = ORB_XOFF - ORB_EDGE, hi = ORB_XOFF + L.w + ORB_EDGE;    // bordered bytes of a row
-        unsigned v = 0;
+        const unsigned* sw = reinterpret_cast<const unsigned*>(srow);
+        const int x0 = 4 * word - ORB_XOFF;                                    // interior x of the word's first byte
+        unsigned v;
+        if (x0 + 3 < 0 || x0 >= L.w) {
+            // 4 mirrored bytes = a byte-reversed unaligned window of the interior row (gfedcb|abcdefgh|gfedcba)
+            const int s0 = x0 < 0 ? -x0 - 3 : 2 * L.w - 5 - x0;               // window [s0, s0+3], s0 >= 1
+            const unsigned win = __funnelshift_r(sw[s0 >> 2], sw[(s0 >> 2) + 1], (s0 & 3) * 8);
+            v = __byte_perm(win, 0u, 0x0123);                                  // (dead bytes beyond the 19-px frame: don't care)
+        } else {
+            // the one word that straddles interior | right border
+            v = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int q = 4 * word + k;
-            const unsigned b = srow[reflect1(min(max(q, lo), hi - 1) - ORB_XOFF, L.w)];   // identity on interior bytes
-            v |= (q >= lo && q < hi ? b : 0u) << (8 * k);
+            for (int k = 0; k < 4; ++k) v |= (unsigned)srow[reflect1(x0 + k, L.w)] << (8 * k);
         }
         reinterpret_cast<unsigned*>(img + row * L.pitch)[word] = v;
     } else {
