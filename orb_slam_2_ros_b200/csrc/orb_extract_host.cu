@@ -3,6 +3,7 @@
 // (orb_slam2/src/ORBextractor.cc:416-479) and ComputePyramid's size rules (:1152-1165).
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -378,6 +379,7 @@ static int ensure_device(orb_ctx* c) {
     if (!c->st_h2d) {
         ORB_CUDA(cudaStreamCreateWithFlags(&c->st_h2d, cudaStreamNonBlocking));
         ORB_CUDA(cudaStreamCreateWithFlags(&c->st_d2h, cudaStreamNonBlocking));
+        ORB_CUDA(cudaStreamCreateWithFlags(&c->st_c2, cudaStreamNonBlocking));
         for (int i = 0; i < ORB_PIPE_SLOTS; ++i) {
             ORB_CUDA(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
             ORB_CUDA(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
@@ -399,7 +401,7 @@ void orb_destroy(orb_ctx* c) {
                 for (int s = 0; s <= ORB_NSTAGES; ++s) cudaEventDestroy(c->prof_ev[r][s]);
         if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
         if (c->st_h2d) {
-            cudaStreamDestroy(c->st_h2d); cudaStreamDestroy(c->st_d2h);
+            cudaStreamDestroy(c->st_h2d); cudaStreamDestroy(c->st_d2h); cudaStreamDestroy(c->st_c2);
             for (int i = 0; i < ORB_PIPE_SLOTS; ++i) { cudaEventDestroy(c->ev_in[i]); cudaEventDestroy(c->ev_done[i]); cudaEventDestroy(c->ev_out[i]); }
         }
     }
@@ -487,6 +489,8 @@ int orb_extract_batch_device(orb_ctx* c, const uint8_t* d_imgs, int nframes, int
     rc = build_geometry(c, w, h);
     if (rc != ORB_OK) return rc;
     c->last_frames = nframes;
+    // (measured: cutting a resident batch into sub-batches on two streams is SLOWER, 147k -> 130k frames/s at 512
+    // frames; the big launches already fill the chip.  Only the host pipeline below alternates streams.)
     return orb_launch_extract(c, d_imgs, nframes, 0, row_stride, frame_stride, d_kps, d_desc, cap, d_n_out, c->stream);
 }
 
@@ -512,16 +516,21 @@ int orb_extract_batch(orb_ctx* c, const uint8_t* imgs, int nframes, int w, int h
     rc = ensure_input_staging(c, !in_direct);
     if (rc != ORB_OK) return rc;
     const int ocap = c->out_cap;                        // device row length (>= dcap)
+    static const int chunk_frames = [] {               // frames per pipeline chunk (tunable for experiments)
+        const char* e = getenv("ORB_B200_PIPE_CHUNK");
+        const int v = e ? atoi(e) : 0;
+        return v > 0 ? v : ORB_PIPE_CHUNK;
+    }();
     const size_t fbytes = (size_t)w * h;
     int status = ORB_OK;
     // the caller's stream (c->stream) may have pending work that produced or still reads our buffers
     ORB_CUDA(cudaStreamSynchronize(c->stream));
     for (int b0 = 0; b0 < nframes; b0 += c->max_batch) {
         const int B = std::min(c->max_batch, nframes - b0);
-        const int nchunks = (B + ORB_PIPE_CHUNK - 1) / ORB_PIPE_CHUNK;
+        const int nchunks = (B + chunk_frames - 1) / chunk_frames;
         c->last_frames = B;
         auto finish_chunk = [&](int k) -> int {       // host side of chunk k once its D2H has landed
-            const int f0 = k * ORB_PIPE_CHUNK, F = std::min(ORB_PIPE_CHUNK, B - f0);
+            const int f0 = k * chunk_frames, F = std::min(chunk_frames, B - f0);
             ORB_CUDA(cudaEventSynchronize(c->ev_out[k % ORB_PIPE_SLOTS]));
             for (int f = 0; f < F; ++f) {
                 const int n = c->h_n[f0 + f];
@@ -536,7 +545,7 @@ int orb_extract_batch(orb_ctx* c, const uint8_t* imgs, int nframes, int w, int h
             return ORB_OK;
         };
         for (int k = 0; k < nchunks; ++k) {
-            const int f0 = k * ORB_PIPE_CHUNK, F = std::min(ORB_PIPE_CHUNK, B - f0);
+            const int f0 = k * chunk_frames, F = std::min(chunk_frames, B - f0);
             const int slot = k % ORB_PIPE_SLOTS;
             if (k >= ORB_PIPE_SLOTS) { rc = finish_chunk(k - ORB_PIPE_SLOTS); if (rc != ORB_OK) return rc; }   // frees the slot's events
             // ---- H2D ----
@@ -554,12 +563,14 @@ int orb_extract_batch(orb_ctx* c, const uint8_t* imgs, int nframes, int w, int h
             uint8_t* d_src = c->d_in + (size_t)f0 * fbytes;
             ORB_CUDA(cudaMemcpyAsync(d_src, src, (size_t)F * fbytes, cudaMemcpyHostToDevice, c->st_h2d));
             ORB_CUDA(cudaEventRecord(c->ev_in[slot], c->st_h2d));
-            // ---- kernels ----
-            ORB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_in[slot], 0));
+            // ---- kernels: chunks alternate between two compute streams, so the latency-bound small launches of one
+            // chunk (upper pyramid levels, quadtree) overlap the issue-bound ones of its neighbour ----
+            cudaStream_t cs = (k & 1) ? c->st_c2 : c->stream;
+            ORB_CUDA(cudaStreamWaitEvent(cs, c->ev_in[slot], 0));
             rc = orb_launch_extract(c, d_src, F, f0, (size_t)w, fbytes, c->d_kps_out + (size_t)f0 * ocap,
-                                    c->d_desc_out + (size_t)f0 * ocap * 32, ocap, c->d_n_out + f0, c->stream);
+                                    c->d_desc_out + (size_t)f0 * ocap * 32, ocap, c->d_n_out + f0, cs);
             if (rc != ORB_OK) return rc;
-            ORB_CUDA(cudaEventRecord(c->ev_done[slot], c->stream));
+            ORB_CUDA(cudaEventRecord(c->ev_done[slot], cs));
             // ---- D2H ----
             ORB_CUDA(cudaStreamWaitEvent(c->st_d2h, c->ev_done[slot], 0));
             ORB_CUDA(cudaMemcpyAsync(c->h_n + f0, c->d_n_out + f0, sizeof(int) * F, cudaMemcpyDeviceToHost, c->st_d2h));
@@ -579,6 +590,7 @@ int orb_extract_batch(orb_ctx* c, const uint8_t* imgs, int nframes, int w, int h
         }
         for (int k = std::max(0, nchunks - ORB_PIPE_SLOTS); k < nchunks; ++k) { rc = finish_chunk(k); if (rc != ORB_OK) return rc; }
         ORB_CUDA(cudaStreamSynchronize(c->stream));
+        ORB_CUDA(cudaStreamSynchronize(c->st_c2));
     }
     return status;
 }

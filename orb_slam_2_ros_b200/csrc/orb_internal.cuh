@@ -118,7 +118,7 @@ struct orb_ctx {
     Geometry g;
     Geometry gl;               // per-launch copy of g with the bases shifted to the chunk's first frame
     // host-API pipeline (orb_extract_batch): copy streams + per-chunk events
-    cudaStream_t st_h2d = nullptr, st_d2h = nullptr;
+    cudaStream_t st_h2d = nullptr, st_d2h = nullptr, st_c2 = nullptr;
     cudaEvent_t ev_in[ORB_PIPE_SLOTS] = {}, ev_done[ORB_PIPE_SLOTS] = {}, ev_out[ORB_PIPE_SLOTS] = {};
     int last_frames = 0;
     uint8_t* d_in = nullptr;  size_t in_bytes = 0;      // staging of host input frames
