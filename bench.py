@@ -182,6 +182,7 @@ def main():
     ap.add_argument("--db-rows", type=int, default=10_000_000, help="total database rows of the Hamming leg")
     ap.add_argument("--ref-frames", type=int, default=64)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--noise", type=int, default=8, help="+-grey-level noise of the synthetic frames (SURVEY.md §8d: 8)")
     ap.add_argument("--no-hamming", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -237,7 +238,7 @@ def main():
 
     B = args.batch
     # ---- synthetic frames: every rank its own contiguous block of seeds (config 4's sharding) ----
-    frames_np = synth.synth_batch(1000 * rank, B, W, H, unique=16)
+    frames_np = synth.synth_batch(1000 * rank, B, W, H, unique=16, noise=args.noise)
     h_frames = torch.from_numpy(frames_np).pin_memory()
     d_frames = h_frames.to(dev, non_blocking=False)
     ex = ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=local_rank, max_batch=B)
@@ -303,8 +304,8 @@ def main():
     ham = None
     if not args.no_hamming:
         rows_total = args.db_rows
-        per = (rows_total + world - 1) // world
-        r0, r1 = min(rank * per, rows_total), min((rank + 1) * per, rows_total)
+        from orb_slam_2_ros_b200.sharding import shard_range
+        r0, r1 = shard_range(rows_total, rank, world)
         db = DescriptorDB(max(r1 - r0, 1), index_base=r0, device=local_rank)
         chunk = 1 << 20
         for s in range(r0, r1, chunk):
@@ -380,25 +381,34 @@ def main():
             pass
         hbm_peak, peak_src = (peaks["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs") if "hbm_gbs" in peaks else (6650.0, "fallback")
         ab = algorithmic_bytes(W, H)
+        traffic = {}
+        try:   # DRAM bytes per frame and stage from the committed `ncu --set full` capture of one bench step
+            import glob
+            tf = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))[-1]
+            traffic = {k: v["dram_bytes_per_frame"] * B for k, v in json.load(open(tf))["stages"].items()}
+            traffic["_source"] = os.path.relpath(tf, ROOT)
+        except (IndexError, OSError, KeyError, ValueError):
+            pass
         per_call = {k: v / max(prof_calls, 1) for k, v in stage_ms.items()}
         stages = {}
         for k in ("pyramid", "fast_cells", "blur"):
             gbs = ab[k] * B / (per_call[k] * 1e-3) / 1e9 if per_call[k] > 0 else 0.0
-            stages[k] = {"ms": per_call[k], "alg_bytes": ab[k] * B, "gbs": gbs, "frac": gbs / hbm_peak}
+            stages[k] = {"ms": per_call[k], "alg_bytes": ab[k] * B, "gbs": gbs, "frac": gbs / hbm_peak, "traffic": traffic.get(k)}
         for k in ("quadtree", "orient_describe"):
-            stages[k] = {"ms": per_call[k]}
+            stages[k] = {"ms": per_call[k], "traffic": traffic.get(k)}
         dom = max(("pyramid", "fast_cells", "blur", "quadtree", "orient_describe"), key=lambda k: per_call[k])
         total_alg = sum(ab.values()) * B
         sum_ms = sum(per_call.values())
         if dom in ab:
             roof = {"bound": "hbm", "achieved": stages[dom]["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": stages[dom]["frac"],
-                    "traffic": None, "kernel": dom, "peak_source": peak_src, "avg_launch_ms": per_call[dom]}
+                    "traffic": traffic.get(dom), "kernel": dom, "peak_source": peak_src, "avg_launch_ms": per_call[dom]}
         else:
             # the dominant stage moves no image-sized data: report the whole step against the unfused-stage byte model
             gbs = total_alg / (sum_ms * 1e-3) / 1e9
             roof = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None,
                     "kernel": dom + " (latency-bound stage; achieved = all stages' algorithmic bytes / step time)",
                     "peak_source": peak_src, "avg_launch_ms": per_call[dom]}
+        roof["traffic_source"] = traffic.get("_source")
         roof["stages"] = stages
         roof["step_alg_bytes"] = total_alg
         roof["step_gbs"] = total_alg / (ms_dev / args.steps * 1e-3) / 1e9
@@ -417,7 +427,7 @@ def main():
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": "ORBextractor 640x480 nFeatures=1000 8 levels 1.2 20/7 (BASELINE config 1), batch of %d frames "
-                                   "per GPU per step" % B, "frames_per_step_per_gpu": B, "keypoints_per_step_per_gpu": n_kp,
+                                   "per GPU per step, synthetic frames with +-%d grey-level noise" % (B, args.noise), "frames_per_step_per_gpu": B, "keypoints_per_step_per_gpu": n_kp,
                        "l2": "inputs larger than L2 (%d MB of frames + %d MB pyramid arena per step)" % (B * W * H >> 20, (B * 1158012) >> 20),
                        "parallelism": "frames sharded over %d GPU(s), no collective" % world},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
