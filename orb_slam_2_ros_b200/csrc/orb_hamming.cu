@@ -30,7 +30,29 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+__device__ __forceinline__ unsigned lop3_xor3(unsigned a, unsigned b, unsigned c) {
+    unsigned d; asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d;
+}
+__device__ __forceinline__ unsigned lop3_maj(unsigned a, unsigned b, unsigned c) {
+    unsigned d; asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d;
+}
+
+// popcount of the 256-bit XOR.  POPC issues at a quarter of the LOP3 rate on sm_100 (measured: orb_bench_issue_rate),
+// so the 8 words first go through a carry-save adder tree (Harley-Seal: 4 CSAs = 8 LOP3) that leaves 4 words of
+// weight 1, 1, 2, 4: 4 POPC instead of 8, the rest on the ALU / FMA pipes.  Exact, like the reference's bit-hack
+// (ORBmatcher.cc:1649-1665).
 __device__ __forceinline__ int hamming256(const uint4& a, const uint4& b, const unsigned (&q)[8]) {
+    const unsigned x0 = a.x ^ q[0], x1 = a.y ^ q[1], x2 = a.z ^ q[2], x3 = a.w ^ q[3];
+    const unsigned x4 = b.x ^ q[4], x5 = b.y ^ q[5], x6 = b.z ^ q[6], x7 = b.w ^ q[7];
+    const unsigned s1 = lop3_xor3(x0, x1, x2), c1 = lop3_maj(x0, x1, x2);
+    const unsigned s2 = lop3_xor3(x3, x4, x5), c2 = lop3_maj(x3, x4, x5);
+    const unsigned s3 = lop3_xor3(s1, s2, x6), c3 = lop3_maj(s1, s2, x6);
+    const unsigned t1 = lop3_xor3(c1, c2, c3), f1 = lop3_maj(c1, c2, c3);
+    return __popc(s3) + __popc(x7) + 2 * __popc(t1) + 4 * __popc(f1);
+}
+
+// the plain form (8 POPC), kept for the issue-rate microbenchmark that defines the popc roofline
+__device__ __forceinline__ int hamming256_popc8(const uint4& a, const uint4& b, const unsigned (&q)[8]) {
     const int s0 = __popc(a.x ^ q[0]) + __popc(a.y ^ q[1]) + __popc(a.z ^ q[2]);
     const int s1 = __popc(a.w ^ q[3]) + __popc(b.x ^ q[4]) + __popc(b.y ^ q[5]);
     return s0 + s1 + __popc(b.z ^ q[6]) + __popc(b.w ^ q[7]);
@@ -138,6 +160,7 @@ __global__ void popc_peak_kernel(unsigned* out, int iters, unsigned seed) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
 }
 // the compare itself (8 xor + 8 popc + adds + packed top-2 update) with all operands in registers
+template <bool CSA>
 __global__ void compare_peak_kernel(unsigned* out, int iters, unsigned seed) {
     unsigned q[8];
 #pragma unroll
@@ -149,7 +172,8 @@ __global__ void compare_peak_kernel(unsigned* out, int iters, unsigned seed) {
         for (int u = 0; u < 8; ++u) {
             // every word of the row changes every iteration (8 extra IADD on the ALU pipe), so no popc is hoisted
             a.x += 0x9E3779B9u; a.y += a.x; a.z += a.y; a.w += a.z; b.x += a.w; b.y += b.x; b.z += b.y; b.w += b.z;
-            const unsigned key = ((unsigned)hamming256(a, b, q) << HT_IDX_BITS) | (unsigned)(i * 8 + u);
+            const unsigned dist = CSA ? (unsigned)hamming256(a, b, q) : (unsigned)hamming256_popc8(a, b, q);
+            const unsigned key = (dist << HT_IDX_BITS) | (unsigned)(i * 8 + u);
             k2 = min(k2, max(key, k1));
             k1 = min(k1, key);
         }
@@ -399,7 +423,8 @@ int orb_top2_merge(const orb_top2* parts, int nparts, int nq, orb_top2* out) {
 }
 
 /* issue-rate microbenchmarks (not in the public header; bench.py binds them through ctypes):
- * kind 0: POPC only -> *gops = 1e9 popc/s ; kind 1: full 256-bit compare + top-2 update -> 1e9 compares/s */
+ * kind 0: POPC only -> *gops = 1e9 popc/s ; kind 1: register-only 256-bit compare with 8 POPC + top-2 update ->
+ * 1e9 compares/s ; kind 2: the same with the carry-save (4 POPC) popcount the search kernel uses */
 int orb_bench_issue_rate(int device, int kind, int iters, double* gops) {
     if (!gops || iters <= 0) return ORB_ERR_INVALID;
     if (orb_device_count() <= 0) { orb_set_error("no CUDA device visible"); return ORB_ERR_NO_DEVICE; }
@@ -415,7 +440,8 @@ int orb_bench_issue_rate(int device, int kind, int iters, double* gops) {
     for (int rep = 0; rep < 4; ++rep) {
         ORB_CUDA(cudaEventRecord(e0));
         if (kind == 0) popc_peak_kernel<<<blocks, threads>>>(d_out, iters, 12345u + rep);
-        else compare_peak_kernel<<<blocks, threads>>>(d_out, iters, 12345u + rep);
+        else if (kind == 1) compare_peak_kernel<false><<<blocks, threads>>>(d_out, iters, 12345u + rep);
+        else compare_peak_kernel<true><<<blocks, threads>>>(d_out, iters, 12345u + rep);
         ORB_CUDA(cudaEventRecord(e1));
         ORB_CUDA(cudaEventSynchronize(e1));
         float ms = 0;
