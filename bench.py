@@ -133,6 +133,87 @@ def cpu_hamming_throughput(q, db, threads):
     return len(q) * len(db) / dt, dt
 
 
+def _median_ms(fn, reps, warm=3):
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        fn()
+        ts.append((time.perf_counter() - t0) * 1e3)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def other_configs(device):
+    """BASELINE configs 1-3 as the SLAM caller sees them: host buffers in, host results out, one call at a time
+    (latency, not batch throughput), each next to the CPU oracle on ONE thread (the reference runs one thread per
+    extractor, Frame.cc:79-82).  Results were already checked against the oracle by tests/ and smoke()."""
+    from oracle import orb_oracle
+    from orb_slam_2_ros_b200 import ORBextractor, ORBmatcher, compute_stereo_matches, synth
+    from orb_slam_2_ros_b200.matcher import MODE_TRACK_LAST
+    out = {}
+    # config 1: one 640x480 frame, 1000 features
+    img = synth.synth_frame(0, W, H)
+    ex = ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=device, max_batch=1)
+    oex = orb_oracle.Extractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH)
+    ms = _median_ms(lambda: ex(img), 50)
+    cms = _median_ms(lambda: oex.extract(img), 5, warm=1)
+    out["config1_single_frame"] = {"workload": "one 640x480 frame, nFeatures=1000, host image -> host keypoints + descriptors",
+                                   "ms": ms, "frames_per_s": 1e3 / ms, "cpu_oracle_ms_1thread": cms}
+    # config 2: 1000 x 1000 brute-force matching + SearchByProjection between two extracted frames
+    img_b = synth.shifted_frame(img, 3, -2, 0)
+    ka, da = ex(img)
+    kb, db = ex(img_b)
+    m = ORBmatcher(0.6, True, device=device)
+    ms_bf = _median_ms(lambda: m.MatchBruteForce(da, ka["angle"], db, kb["angle"], 50), 30)
+    cms_bf = _median_ms(lambda: orb_oracle.match_bruteforce(da, ka["angle"], db, kb["angle"], 50, 0.6, True), 5, warm=1)
+    sf = ex.mvScaleFactor
+    q_u = (ka["x"] + np.float32(3)).astype(np.float32); q_v = (ka["y"] - np.float32(2)).astype(np.float32)
+    q_r = (np.float32(15.0) * sf[ka["octave"]]).astype(np.float32)
+    qmin, qmax = ka["octave"] - 1, ka["octave"] + 1
+    bounds = (0.0, 0.0, float(W), float(H))
+    m9 = ORBmatcher(0.9, True, device=device)
+
+    def sbp():
+        return m9.SearchByProjection(MODE_TRACK_LAST, kb, db, bounds, np.zeros(len(kb), np.uint8), q_u, q_v, q_r, qmin, qmax, da,
+                                     q_angle=ka["angle"], th_dist=100)
+    grid = orb_oracle.Grid(kb, *bounds)
+
+    def sbp_cpu():
+        return orb_oracle.search_by_projection(orb_oracle.MODE_TRACK_LAST, grid, db, None, np.zeros(len(kb), np.uint8), q_u, q_v, q_r,
+                                               qmin, qmax, da, q_angle=ka["angle"], th_dist=100, nn_ratio=0.9, check_orientation=True)
+    ms_sbp = _median_ms(sbp, 30)
+    cms_sbp = _median_ms(sbp_cpu, 5, warm=1)
+    out["config2_matching"] = {"workload": "%d x %d descriptors of two extracted frames" % (len(da), len(db)),
+                               "bruteforce_ratio_rothist_ms": ms_bf, "bruteforce_compares_per_s": len(da) * len(db) / (ms_bf * 1e-3),
+                               "bruteforce_cpu_oracle_ms_1thread": cms_bf, "bruteforce_matches": int(m.MatchBruteForce(da, ka["angle"], db, kb["angle"], 50)[0]),
+                               "search_by_projection_ms": ms_sbp, "search_by_projection_cpu_oracle_ms_1thread": cms_sbp,
+                               "search_by_projection_matches": int(sbp()[0])}
+    # config 3: KITTI-shape stereo pair, 2000 features: both extractions + ComputeStereoMatches
+    left, right, _ = synth.synth_stereo_pair(2, 1241, 376)
+    exl = ORBextractor(2000, SCALE, NLEVELS, INI_TH, MIN_TH, device=device, max_batch=1)
+    exr = ORBextractor(2000, SCALE, NLEVELS, INI_TH, MIN_TH, device=device, max_batch=1)
+    bf, b = 386.1448, 0.53716
+    res = {}
+
+    def stereo():
+        kl, dl = exl(left)
+        kr, dr = exr(right)
+        res["n"] = compute_stereo_matches(exl, exr, kl, dl, kr, dr, bf, b)[0]
+    oL, oR = orb_oracle.Extractor(2000, SCALE, NLEVELS, INI_TH, MIN_TH), orb_oracle.Extractor(2000, SCALE, NLEVELS, INI_TH, MIN_TH)
+
+    def stereo_cpu():
+        kl, dl = oL.extract(left)
+        kr, dr = oR.extract(right)
+        orb_oracle.stereo_match(oL, oR, kl, dl, kr, dr, bf, b)
+    ms_st = _median_ms(stereo, 30)
+    cms_st = _median_ms(stereo_cpu, 3, warm=1)
+    out["config3_stereo"] = {"workload": "1241x376 pair, nFeatures=2000: 2 extractions + ComputeStereoMatches, sequential calls",
+                             "ms": ms_st, "pairs_per_s": 1e3 / ms_st, "stereo_matches": int(res["n"]), "cpu_oracle_ms_1thread": cms_st}
+    return out
+
+
 def run_reference(args, rank):
     """--impl reference: the reference's CPU path.  Its own translation units need OpenCV C++ headers that this
     image lacks, so the arm times oracle/'s restatement (kind "port") on all host cores."""
@@ -441,6 +522,7 @@ def main():
             "roofline": roof,
             "cpu_baseline": cpu,
             "hamming": ham,
+            "other_configs": other_configs(local_rank) if (world == 1 and not args.no_cpu) else None,
             "clocks": summarize_clocks(clk.get("rows")),
         }
         print(json.dumps(line), flush=True)

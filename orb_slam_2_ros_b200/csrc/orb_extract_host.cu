@@ -395,7 +395,7 @@ void orb_destroy(orb_ctx* c) {
         cudaSetDevice(c->device);
         if (c->stream) cudaStreamSynchronize(c->stream);
         free_geometry_buffers(c);
-        cudaFree(c->d_mom_tab);
+        cudaFree(c->d_mom_tab); cudaFree(c->d_scratch); cudaFreeHost(c->h_scratch);
         if (c->prof_ev[0][0])
             for (int r = 0; r < ORB_PROF_RING; ++r)
                 for (int s = 0; s <= ORB_NSTAGES; ++s) cudaEventDestroy(c->prof_ev[r][s]);

@@ -138,6 +138,8 @@ struct orb_ctx {
     orb_kp* h_kps = nullptr; uint8_t* h_desc = nullptr; int* h_n = nullptr; uint8_t* h_in = nullptr;  // pinned
     size_t h_in_bytes = 0;
     int h_out_cap = 0;
+    uint8_t *d_scratch = nullptr, *h_scratch = nullptr;   // grow-only slabs of orb_stereo_match
+    size_t d_scratch_cap = 0, h_scratch_cap = 0;
     // per-stage CUDA-event timers (orb_profile_enable / orb_profile_read): a ring of event sets so that reading
     // never stalls the stream; stage s of a call = elapsed(ev[s], ev[s+1])
     bool profile = false;

@@ -10,6 +10,8 @@
 // (grid build, window enumeration in the reference's (ix, iy, insertion) order, Hamming distances, per-row
 // top-K); the greedy assignment, whose result depends on the order of the queries, is resolved by ONE warp
 // that walks the queries in order over those precomputed lists, then applies the rotation-histogram filter.
+#include <string.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -71,6 +73,10 @@ grid_build_kernel(const orb_kp* __restrict__ kps, int n, int npad, float min_x, 
     }
 }
 
+#define SR_K 8   // unmasked top-K per query kept for the optimistic resolve
+#define SR_CH 1024  // queries staged in shared memory per chunk of the sequential walk
+#define SR_THREADS 256
+
 struct SearchArgs {
     const orb_kp* kps; const uint8_t* desc; const float* u_right; int n;
     int nq; const float *q_u, *q_v, *q_radius; const int *q_min_level, *q_max_level; const uint8_t* q_desc;
@@ -79,6 +85,7 @@ struct SearchArgs {
     const unsigned* items; const int* cell_start;
     int* cand_count; int* cand_base; int* cand_total; int cand_cap;
     int* cand_idx; unsigned short* cand_dist;
+    unsigned* topk;   // [nq][SR_K] sorted keys (dist << 16 | position in the candidate list), 0xFFFFFFFF = none
 };
 
 // ---- one warp per query: GetFeaturesInArea in reference order + distances -----------------------------------
@@ -89,6 +96,7 @@ window_candidates_kernel(const SearchArgs a) {
     const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (qi >= a.nq) return;
     if (lane == 0) { a.cand_count[qi] = 0; a.cand_base[qi] = 0; }
+    if (lane < SR_K) a.topk[(size_t)qi * SR_K + lane] = 0xFFFFFFFFu;
     if (a.q_valid && !a.q_valid[qi]) return;
     const float x = a.q_u[qi], y = a.q_v[qi], r = a.q_radius[qi];
     const int minLevel = a.q_min_level[qi], maxLevel = a.q_max_level[qi];
@@ -104,6 +112,17 @@ window_candidates_kernel(const SearchArgs a) {
     const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
     const uint4* dq = reinterpret_cast<const uint4*>(a.q_desc + (size_t)qi * 32);
     int base = 0, total = 0;
+    unsigned best[SR_K];
+#pragma unroll
+    for (int k = 0; k < SR_K; ++k) best[k] = 0xFFFFFFFFu;
+    auto insert = [&](unsigned key) {
+#pragma unroll
+        for (int k = 0; k < SR_K; ++k) {
+            const unsigned lo = min(best[k], key);
+            key = max(best[k], key);
+            best[k] = lo;
+        }
+    };
     for (int pass = 0; pass < 2; ++pass) {
         int written = 0;
         for (int ix = nMinCellX; ix <= nMaxCellX; ++ix) {
@@ -136,6 +155,7 @@ window_candidates_kernel(const SearchArgs a) {
                     }
                     a.cand_idx[pos] = id;
                     a.cand_dist[pos] = (unsigned short)d;
+                    if (d < 256) insert(((unsigned)d << 16) | (unsigned)(pos - base));
                 }
                 written += __popc(m);
             }
@@ -151,6 +171,19 @@ window_candidates_kernel(const SearchArgs a) {
             }
             if (lane == 0) { a.cand_count[qi] = total; a.cand_base[qi] = base; }
         }
+    }
+    // warp merge of the per-lane sorted top-K lists
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned other[SR_K];
+#pragma unroll
+        for (int k = 0; k < SR_K; ++k) other[k] = __shfl_xor_sync(0xffffffffu, best[k], o);
+#pragma unroll
+        for (int k = 0; k < SR_K; ++k) insert(other[k]);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < SR_K; ++k) a.topk[(size_t)qi * SR_K + k] = best[k];
     }
 }
 
@@ -181,89 +214,155 @@ __device__ __forceinline__ int rot_bin(float aq, float at) {  // ORBmatcher.cc:1
     return bin;
 }
 
-// ---- the order-dependent part: one warp walks the queries in reference order -------------------------------
-__global__ void __launch_bounds__(32)
-window_resolve_kernel(const SearchArgs a, int mode, int th_dist, float nn_ratio, int check_ori, uint8_t* taken,
-                      int* match_of_query, int* target_query, signed char* match_bin, int* nmatches_out) {
-    const int lane = threadIdx.x;
+// ---- the order-dependent part: the queries are walked in reference order -----------------------------------------
+// One CTA.  Per chunk of SR_CH queries all threads stage the sorted top-K lists (target index, distance, octave)
+// in shared memory; then warp 0 walks the chunk sequentially — every lane executes the same broadcast shared-memory
+// reads, lane 0 commits — so one query costs a few dependent shared-memory accesses instead of global round trips.
+// `taken` lives in shared memory.  The top-K list answers a query whenever enough of its entries are still free;
+// otherwise (list truncated and too many entries taken) warp 0 scans the query's full candidate list.
+struct SrStage {
+    unsigned short id[SR_CH][SR_K];   // target index, 0xFFFF = none
+    uint8_t dist[SR_CH][SR_K];
+    uint8_t oct[SR_CH][SR_K];
+    uint8_t flags[SR_CH];             // bit 0: list truncated (all K entries valid), bit 1: query blocks its target
+};
+
+__global__ void __launch_bounds__(SR_THREADS)
+window_resolve_kernel(const SearchArgs a, int mode, int th_dist, float nn_ratio, int check_ori, uint8_t* taken_g,
+                      int* match_of_query, int* target_query, signed char* match_bin, int* nmatches_out, int* overflow) {
+    extern __shared__ __align__(16) uint8_t sr_smem[];
+    SrStage& S = *reinterpret_cast<SrStage*>(sr_smem);
+    uint8_t* taken = sr_smem + sizeof(SrStage);   // [n]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     __shared__ int hist[HISTO_LENGTH];
-    if (lane < HISTO_LENGTH) hist[lane] = 0;
-    for (int i = lane; i < a.n; i += 32) target_query[i] = -1;
-    __syncwarp();
-    int nmatches = 0;
-    for (int qi = 0; qi < a.nq; ++qi) {
-        if (lane == 0) { match_of_query[qi] = -1; match_bin[qi] = -1; }
-        const int cnt = a.cand_count[qi];
-        if (cnt == 0) continue;
-        const int base = a.cand_base[qi];
-        // best = min over (dist, position) of the candidates that are not taken and passed the stereo test
-        unsigned k1 = 0xFFFFFFFFu;
-        for (int p = lane; p < cnt; p += 32) {
-            const unsigned d = a.cand_dist[base + p];
-            if (d < 256u && !taken[a.cand_idx[base + p]]) k1 = min(k1, (d << 16) | (unsigned)p);
-        }
-        k1 = warp_min_u32(k1);
-        if (k1 == 0xFFFFFFFFu) continue;
-        const int bestDist = (int)(k1 >> 16), bestPos = (int)(k1 & 0xFFFFu);
-        const int bestIdx = a.cand_idx[base + bestPos];
-        if (bestDist > th_dist) continue;
-        if (mode == ORB_MODE_LOCAL_POINTS) {
-            unsigned k2 = 0xFFFFFFFFu;
-            for (int p = lane; p < cnt; p += 32) {
-                const unsigned d = a.cand_dist[base + p];
-                if (p != bestPos && d < 256u && !taken[a.cand_idx[base + p]]) k2 = min(k2, (d << 16) | (unsigned)p);
-            }
-            k2 = warp_min_u32(k2);
-            int bestDist2 = 256, bestLevel2 = -1;
-            if (k2 != 0xFFFFFFFFu) { bestDist2 = (int)(k2 >> 16); bestLevel2 = a.kps[a.cand_idx[base + (k2 & 0xFFFFu)]].octave; }
-            const int bestLevel = a.kps[bestIdx].octave;
-            if (bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(nn_ratio, (float)bestDist2)) continue;  // ORBmatcher.cc:120
-        }
-        if (lane == 0) {
-            match_of_query[qi] = bestIdx;
-            target_query[bestIdx] = qi;
-            if (!a.q_obs || a.q_obs[qi]) taken[bestIdx] = 1;
-            if (mode == ORB_MODE_TRACK_LAST && check_ori) {
-                const int bin = rot_bin(a.q_angle[qi], a.kps[bestIdx].angle);
-                match_bin[qi] = (signed char)bin;
-                hist[bin]++;
-            }
-        }
-        nmatches++;
-        __syncwarp();
+    __shared__ int s_nmatches;
+    if (*a.cand_total > a.cand_cap) {    // candidate arena too small: the host retries with a larger one
+        if (threadIdx.x == 0) *overflow = *a.cand_total;
+        return;
     }
-    __syncwarp();
+    if (threadIdx.x == 0) { *overflow = 0; s_nmatches = 0; }
+    if (threadIdx.x < HISTO_LENGTH) hist[threadIdx.x] = 0;
+    for (int i = threadIdx.x; i < a.n; i += SR_THREADS) { target_query[i] = -1; taken[i] = taken_g[i]; }
+    const int need = (mode == ORB_MODE_LOCAL_POINTS) ? 2 : 1;
+    int nmatches = 0;
+    for (int q0 = 0; q0 < a.nq; q0 += SR_CH) {
+        const int nb = min(SR_CH, a.nq - q0);
+        __syncthreads();
+        // ---- stage the chunk ----
+        for (int e = threadIdx.x; e < nb * SR_K; e += SR_THREADS) {
+            const int j = e / SR_K, k = e - j * SR_K, qi = q0 + j;
+            const unsigned key = a.topk[(size_t)qi * SR_K + k];
+            int id = 0xFFFF, oc = 0;
+            if (key != 0xFFFFFFFFu) {
+                id = a.cand_idx[a.cand_base[qi] + (key & 0xFFFFu)];
+                if (mode == ORB_MODE_LOCAL_POINTS) oc = a.kps[id].octave;
+            }
+            S.id[j][k] = (unsigned short)id; S.dist[j][k] = (uint8_t)(key >> 16); S.oct[j][k] = (uint8_t)oc;
+            if (k == SR_K - 1) S.flags[j] = (uint8_t)((key != 0xFFFFFFFFu ? 1 : 0) | ((!a.q_obs || a.q_obs[qi]) ? 2 : 0));
+        }
+        for (int j = threadIdx.x; j < nb; j += SR_THREADS) { match_of_query[q0 + j] = -1; match_bin[q0 + j] = -1; }
+        __syncthreads();
+        // ---- sequential walk by warp 0 ----
+        if (warp == 0) {
+            for (int j = 0; j < nb; ++j) {
+                const int qi = q0 + j;
+                int d1 = 256, d2 = 256, i1 = -1, o1 = -1, o2 = -1, nfree = 0;
+#pragma unroll
+                for (int k = 0; k < SR_K; ++k) {
+                    const int id = S.id[j][k];
+                    if (id == 0xFFFF || nfree >= need) break;
+                    if (taken[id]) continue;
+                    if (nfree == 0) { d1 = S.dist[j][k]; i1 = id; o1 = S.oct[j][k]; } else { d2 = S.dist[j][k]; o2 = S.oct[j][k]; }
+                    ++nfree;
+                }
+                const int flags = S.flags[j];
+                if (nfree < need && (flags & 1)) {
+                    // the list was truncated and too many of its entries are taken: scan all candidates of the query
+                    const int cnt = a.cand_count[qi], base = a.cand_base[qi];
+                    unsigned a1 = 0xFFFFFFFFu, a2 = 0xFFFFFFFFu;
+                    for (int p = lane; p < cnt; p += 32) {
+                        const unsigned d = a.cand_dist[base + p];
+                        if (d < 256u && !taken[a.cand_idx[base + p]]) {
+                            const unsigned k = (d << 16) | (unsigned)p;
+                            a2 = min(a2, max(k, a1));
+                            a1 = min(a1, k);
+                        }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const unsigned b1 = __shfl_xor_sync(0xffffffffu, a1, o), b2 = __shfl_xor_sync(0xffffffffu, a2, o);
+                        const unsigned lo = min(a1, b1), hi = max(a1, b1);
+                        a2 = min(hi, min(a2, b2));
+                        a1 = lo;
+                    }
+                    d1 = d2 = 256; i1 = -1;
+                    if (a1 != 0xFFFFFFFFu) { d1 = (int)(a1 >> 16); i1 = a.cand_idx[base + (a1 & 0xFFFFu)]; }
+                    int i2 = -1;
+                    if (a2 != 0xFFFFFFFFu) { d2 = (int)(a2 >> 16); i2 = a.cand_idx[base + (a2 & 0xFFFFu)]; }
+                    if (mode == ORB_MODE_LOCAL_POINTS) { o1 = i1 >= 0 ? a.kps[i1].octave : -1; o2 = i2 >= 0 ? a.kps[i2].octave : -1; }
+                }
+                if (i1 < 0 || d1 > th_dist) continue;
+                if (mode == ORB_MODE_LOCAL_POINTS) {
+                    const int bestLevel2 = (d2 < 256) ? o2 : -1;
+                    if (o1 == bestLevel2 && (float)d1 > __fmul_rn(nn_ratio, (float)d2)) continue;   // ORBmatcher.cc:120
+                }
+                if (lane == 0) {
+                    match_of_query[qi] = i1;
+                    target_query[i1] = qi;
+                    if (flags & 2) taken[i1] = 1;
+                }
+                nmatches++;
+                __syncwarp();
+            }
+        }
+    }
+    if (threadIdx.x == 0) s_nmatches = nmatches;
+    __syncthreads();
+    nmatches = s_nmatches;
+    for (int i = threadIdx.x; i < a.n; i += SR_THREADS) taken_g[i] = taken[i];
     if (mode == ORB_MODE_TRACK_LAST && check_ori) {
+        // rotation histogram of every match made (ORBmatcher.cc:1433-1441), after the walk: its global loads are parallel
+        for (int qi = threadIdx.x; qi < a.nq; qi += SR_THREADS) {
+            const int m = match_of_query[qi];
+            if (m >= 0) {
+                const int bin = rot_bin(a.q_angle[qi], a.kps[m].angle);
+                match_bin[qi] = (signed char)bin;
+                atomicAdd(&hist[bin], 1);
+            }
+        }
+        __syncthreads();
         int ind1, ind2, ind3;
         three_maxima(hist, ind1, ind2, ind3);
+        __syncthreads();
+        if (threadIdx.x == 0) s_nmatches = 0;
+        __syncthreads();
         int removed = 0;
-        for (int qi = lane; qi < a.nq; qi += 32) {
+        for (int qi = threadIdx.x; qi < a.nq; qi += SR_THREADS) {
             const int bin = match_bin[qi];
             if (bin >= 0 && bin != ind1 && bin != ind2 && bin != ind3) {
                 target_query[match_of_query[qi]] = -1;   // ORBmatcher.cc:1462-1466
                 removed++;
             }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);
-        nmatches -= removed;
-        __syncwarp();
+        atomicAdd(&s_nmatches, removed);
+        __syncthreads();
+        nmatches -= s_nmatches;
         // per-query view: a query whose target was nulled loses its match
-        for (int qi = lane; qi < a.nq; qi += 32) {
+        for (int qi = threadIdx.x; qi < a.nq; qi += SR_THREADS) {
             const int m = match_of_query[qi];
             if (m >= 0 && target_query[m] == -1) match_of_query[qi] = -1;
         }
     }
-    if (lane == 0) *nmatches_out = nmatches;
+    if (threadIdx.x == 0) *nmatches_out = nmatches;
 }
 
 // =============================== brute force with mask (SearchByBoW inner loop) ===============================
-#define BF_K 4   // unmasked top-K per query kept for the optimistic resolve
+#define BF_K SR_K
 
 // one warp per query row: distances to every target (stored, u16) + sorted top-K packed keys (dist<<16 | j)
 __global__ void __launch_bounds__(256)
 bf_rows_kernel(const uint8_t* __restrict__ d1, int n1, const uint8_t* __restrict__ d2, int n2,
-               unsigned short* __restrict__ D, unsigned* __restrict__ topk) {
+               unsigned short* __restrict__ D, int dpitch, unsigned* __restrict__ topk) {
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= n1) return;
@@ -281,7 +380,7 @@ bf_rows_kernel(const uint8_t* __restrict__ d1, int n1, const uint8_t* __restrict
     };
     for (int j = lane; j < n2; j += 32) {
         const int d = dist256(dq, reinterpret_cast<const uint4*>(d2 + (size_t)j * 32));
-        D[(size_t)i * n2 + j] = (unsigned short)d;
+        D[(size_t)i * dpitch + j] = (unsigned short)d;
         insert(((unsigned)d << 16) | (unsigned)j);
     }
 #pragma unroll
@@ -298,103 +397,156 @@ bf_rows_kernel(const uint8_t* __restrict__ d1, int n1, const uint8_t* __restrict
     }
 }
 
-__global__ void __launch_bounds__(32)
-bf_resolve_kernel(const unsigned short* __restrict__ D, const unsigned* __restrict__ topk, int n1, int n2,
+__global__ void __launch_bounds__(SR_THREADS)
+bf_resolve_kernel(const unsigned short* __restrict__ D, int dpitch, const unsigned* __restrict__ topk, int n1, int n2,
                   const float* __restrict__ angle1, const float* __restrict__ angle2, int th_dist, float nn_ratio,
                   int check_ori, int* owner /*[n2]*/, int* match12, signed char* match_bin, int* nmatches_out) {
-    const int lane = threadIdx.x;
+    extern __shared__ __align__(16) uint8_t sr_smem[];
+    SrStage& S = *reinterpret_cast<SrStage*>(sr_smem);
+    unsigned* taken_bits = reinterpret_cast<unsigned*>(sr_smem + sizeof(SrStage));   // [(n2 + 31) / 32] (ORBmatcher.cc:210)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     __shared__ int hist[HISTO_LENGTH];
-    if (lane < HISTO_LENGTH) hist[lane] = 0;
-    for (int j = lane; j < n2; j += 32) owner[j] = -1;
-    __syncwarp();
+    __shared__ int s_nmatches;
+    if (threadIdx.x < HISTO_LENGTH) hist[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_nmatches = 0;
+    for (int j = threadIdx.x; j < n2; j += SR_THREADS) owner[j] = -1;
+    for (int j = threadIdx.x; j < (n2 + 31) / 32; j += SR_THREADS) taken_bits[j] = 0u;
     int nmatches = 0;
-    for (int i = 0; i < n1; ++i) {
-        if (lane == 0) { match12[i] = -1; match_bin[i] = -1; }
-        // optimistic: the first two untaken entries of the sorted unmasked top-K are the masked best / second
-        unsigned key = 0xFFFFFFFFu;
-        bool free_ = false;
-        if (lane < BF_K) {
-            key = topk[(size_t)i * BF_K + lane];
-            free_ = (key != 0xFFFFFFFFu) && (owner[key & 0xFFFFu] < 0);
+    for (int i0 = 0; i0 < n1; i0 += SR_CH) {
+        const int nb = min(SR_CH, n1 - i0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < nb * SR_K; e += SR_THREADS) {
+            const int j = e / SR_K, k = e - j * SR_K;
+            const unsigned key = topk[(size_t)(i0 + j) * SR_K + k];
+            S.id[j][k] = (unsigned short)(key == 0xFFFFFFFFu ? 0xFFFFu : (key & 0xFFFFu));
+            S.dist[j][k] = (uint8_t)min(key >> 16, 255u);
+            if (k == SR_K - 1) S.flags[j] = (uint8_t)(key != 0xFFFFFFFFu ? 1 : 0);
         }
-        const unsigned fm = __ballot_sync(0xffffffffu, free_);
-        const unsigned present = __ballot_sync(0xffffffffu, key != 0xFFFFFFFFu);
-        unsigned k1, k2;
-        if (__popc(fm) >= 2 || __popc(present) < BF_K) {
-            // enough free entries, or the list holds ALL targets (n2 < K): exact
-            const int p1 = fm ? __ffs(fm) - 1 : -1;
-            const unsigned fm2 = fm & (fm - 1);
-            const int p2 = fm2 ? __ffs(fm2) - 1 : -1;
-            k1 = p1 >= 0 ? __shfl_sync(0xffffffffu, key, p1) : 0xFFFFFFFFu;
-            k2 = p2 >= 0 ? __shfl_sync(0xffffffffu, key, p2) : 0xFFFFFFFFu;
-        } else {
-            // fallback: masked scan of the whole row
-            unsigned a1 = 0xFFFFFFFFu, a2 = 0xFFFFFFFFu;
-            for (int j = lane; j < n2; j += 32) {
-                if (owner[j] >= 0) continue;
-                const unsigned k = ((unsigned)D[(size_t)i * n2 + j] << 16) | (unsigned)j;
-                a2 = min(a2, max(k, a1));
-                a1 = min(a1, k);
-            }
+        for (int j = threadIdx.x; j < nb; j += SR_THREADS) { match12[i0 + j] = -1; match_bin[i0 + j] = -1; }
+        __syncthreads();
+        if (warp == 0) {
+            for (int j = 0; j < nb; ++j) {
+                const int i = i0 + j;
+                // optimistic: the first two untaken entries of the sorted unmasked top-K are the masked best / second
+                int best1 = 256, best2 = 256, bestIdx = -1, nfree = 0;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const unsigned b1 = __shfl_xor_sync(0xffffffffu, a1, o), b2 = __shfl_xor_sync(0xffffffffu, a2, o);
-                const unsigned lo = min(a1, b1), hi = max(a1, b1);
-                a2 = min(hi, min(a2, b2));
-                a1 = lo;
-            }
-            k1 = a1; k2 = a2;
-        }
-        if (k1 == 0xFFFFFFFFu) continue;
-        const int best1 = (int)(k1 >> 16), bestIdx = (int)(k1 & 0xFFFFu);
-        const int best2 = (k2 == 0xFFFFFFFFu) ? 256 : (int)(k2 >> 16);
-        if (best1 >= 256) continue;
-        if (best1 <= th_dist && (float)best1 < __fmul_rn(nn_ratio, (float)best2)) {   // ORBmatcher.cc:229-231
-            if (lane == 0) {
-                owner[bestIdx] = i;
-                match12[i] = bestIdx;
-                if (check_ori) {
-                    const int bin = rot_bin(angle1[i], angle2[bestIdx]);
-                    match_bin[i] = (signed char)bin;
-                    hist[bin]++;
+                for (int k = 0; k < SR_K; ++k) {
+                    const unsigned id = S.id[j][k];
+                    if (id == 0xFFFFu || nfree >= 2) break;
+                    if ((taken_bits[id >> 5] >> (id & 31)) & 1u) continue;
+                    if (nfree == 0) { best1 = S.dist[j][k]; bestIdx = (int)id; } else best2 = S.dist[j][k];
+                    ++nfree;
                 }
+                if (nfree < 2 && (S.flags[j] & 1)) {
+                    // fallback: masked scan of the whole row of the distance matrix (8 entries per load)
+                    unsigned a1 = 0xFFFFFFFFu, a2 = 0xFFFFFFFFu;
+                    const uint4* row = reinterpret_cast<const uint4*>(D + (size_t)i * dpitch);
+                    for (int v = lane; v < dpitch / 8; v += 32) {
+                        const uint4 t = row[v];
+                        const unsigned w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                        for (int h = 0; h < 8; ++h) {
+                            const int jj = v * 8 + h;
+                            if (jj >= n2 || ((taken_bits[jj >> 5] >> (jj & 31)) & 1u)) continue;
+                            const unsigned k = (((w[h >> 1] >> (16 * (h & 1))) & 0xFFFFu) << 16) | (unsigned)jj;
+                            a2 = min(a2, max(k, a1));
+                            a1 = min(a1, k);
+                        }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const unsigned b1 = __shfl_xor_sync(0xffffffffu, a1, o), b2 = __shfl_xor_sync(0xffffffffu, a2, o);
+                        const unsigned lo = min(a1, b1), hi = max(a1, b1);
+                        a2 = min(hi, min(a2, b2));
+                        a1 = lo;
+                    }
+                    best1 = best2 = 256; bestIdx = -1;
+                    if (a1 != 0xFFFFFFFFu) { best1 = (int)(a1 >> 16); bestIdx = (int)(a1 & 0xFFFFu); }
+                    if (a2 != 0xFFFFFFFFu) best2 = (int)(a2 >> 16);
+                }
+                if (bestIdx < 0 || best1 >= 256) continue;
+                if (best1 <= th_dist && (float)best1 < __fmul_rn(nn_ratio, (float)best2)) {   // ORBmatcher.cc:229-231
+                    if (lane == 0) {
+                        owner[bestIdx] = i;
+                        taken_bits[bestIdx >> 5] |= 1u << (bestIdx & 31);
+                        match12[i] = bestIdx;
+                    }
+                    nmatches++;
+                }
+                __syncwarp();
             }
-            nmatches++;
         }
-        __syncwarp();
     }
-    __syncwarp();
+    if (threadIdx.x == 0) s_nmatches = nmatches;
+    __syncthreads();
+    nmatches = s_nmatches;
     if (check_ori) {
+        for (int i = threadIdx.x; i < n1; i += SR_THREADS) {      // rotation histogram (ORBmatcher.cc:236-247), parallel
+            const int m = match12[i];
+            if (m >= 0) {
+                const int bin = rot_bin(angle1[i], angle2[m]);
+                match_bin[i] = (signed char)bin;
+                atomicAdd(&hist[bin], 1);
+            }
+        }
+        __syncthreads();
         int ind1, ind2, ind3;
         three_maxima(hist, ind1, ind2, ind3);
+        __syncthreads();
+        if (threadIdx.x == 0) s_nmatches = 0;
+        __syncthreads();
         int removed = 0;
-        for (int i = lane; i < n1; i += 32) {
+        for (int i = threadIdx.x; i < n1; i += SR_THREADS) {
             const int bin = match_bin[i];
             if (bin >= 0 && bin != ind1 && bin != ind2 && bin != ind3) { owner[match12[i]] = -1; match12[i] = -1; removed++; }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);
-        nmatches -= removed;
+        atomicAdd(&s_nmatches, removed);
+        __syncthreads();
+        nmatches -= s_nmatches;
     }
-    if (lane == 0) *nmatches_out = nmatches;
+    if (threadIdx.x == 0) *nmatches_out = nmatches;
 }
 
-// small RAII arena for the one-shot host-pointer entry points
-struct DevBuf {
-    std::vector<void*> ptrs;
-    ~DevBuf() { for (void* p : ptrs) cudaFree(p); }
-    template <typename T> T* alloc(size_t n) {
-        void* p = nullptr;
-        if (cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)) != cudaSuccess) return nullptr;
-        ptrs.push_back(p);
-        return (T*)p;
+// Per-thread, per-device workspace of the host-pointer entry points: one grow-only device slab, one grow-only pinned
+// slab and a private stream.  A call packs all its inputs into the pinned slab, issues ONE H2D copy, the kernels and
+// ONE D2H copy, and synchronises once — no cudaMalloc / cudaFree on the call path.
+struct Workspace {
+    int device = -1;
+    cudaStream_t st = nullptr;
+    uint8_t *d = nullptr, *h = nullptr;
+    size_t d_cap = 0, h_cap = 0;
+    ~Workspace() {
+        // (the CUDA context may already be gone at thread exit: ignore errors)
+        if (device >= 0 && cudaSetDevice(device) == cudaSuccess) { cudaFree(d); cudaFreeHost(h); if (st) cudaStreamDestroy(st); }
     }
-    template <typename T> T* upload(const T* h, size_t n, cudaStream_t st) {
-        if (!h) return nullptr;
-        T* d = alloc<T>(n);
-        if (d && n) cudaMemcpyAsync(d, h, n * sizeof(T), cudaMemcpyHostToDevice, st);
-        return d;
+    int prepare(int dev, size_t dbytes, size_t hbytes) {
+        ORB_CUDA(cudaSetDevice(dev));
+        if (device != dev) {
+            if (device >= 0) { cudaSetDevice(device); cudaFree(d); cudaFreeHost(h); if (st) cudaStreamDestroy(st); cudaSetDevice(dev); }
+            d = h = nullptr; d_cap = h_cap = 0; st = nullptr; device = dev;
+            ORB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        }
+        if (d_cap < dbytes) {
+            ORB_CUDA(cudaStreamSynchronize(st));
+            cudaFree(d); d = nullptr; d_cap = 0;
+            ORB_CUDA(cudaMalloc(&d, dbytes + dbytes / 2));
+            d_cap = dbytes + dbytes / 2;
+        }
+        if (h_cap < hbytes) {
+            ORB_CUDA(cudaStreamSynchronize(st));
+            cudaFreeHost(h); h = nullptr; h_cap = 0;
+            ORB_CUDA(cudaMallocHost(&h, hbytes + hbytes / 2));
+            h_cap = hbytes + hbytes / 2;
+        }
+        return ORB_OK;
     }
+};
+thread_local Workspace g_ws;
+
+// carve-up helper: the same offsets are valid in the pinned slab (inputs / outputs) and the device slab
+struct Carver {
+    size_t off = 0;
+    size_t take(size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; }
 };
 
 }  // namespace
@@ -418,57 +570,76 @@ int orb_search_by_projection(int device, const orb_search_params* prm, const orb
     if (n == 0 || nq == 0) return ORB_OK;
     if (n > GB_MAX_N) { orb_set_error("orb_search_by_projection: more than %d target keypoints", GB_MAX_N); return ORB_ERR_CAPACITY; }
     if (orb_device_count() <= 0) { orb_set_error("no CUDA device visible: liborb_b200 has no CPU fallback"); return ORB_ERR_NO_DEVICE; }
-    ORB_CUDA(cudaSetDevice(device));
-    cudaStream_t st = nullptr;  // legacy default stream: this one-shot entry point is synchronous anyway
-    DevBuf B;
-    SearchArgs a;
-    memset(&a, 0, sizeof(a));
-    a.n = n; a.nq = nq;
-    a.kps = B.upload(kps_un, n, st); a.desc = B.upload(desc, (size_t)n * 32, st); a.u_right = B.upload(u_right, n, st);
-    a.q_u = B.upload(q_u, nq, st); a.q_v = B.upload(q_v, nq, st); a.q_radius = B.upload(q_radius, nq, st);
-    a.q_min_level = B.upload(q_min_level, nq, st); a.q_max_level = B.upload(q_max_level, nq, st);
-    a.q_desc = B.upload(q_desc, (size_t)nq * 32, st);
-    a.q_ur = B.upload(q_ur, nq, st); a.q_er_max = B.upload(q_er_max, nq, st); a.q_angle = B.upload(q_angle, nq, st);
-    a.q_valid = B.upload(q_valid, nq, st); a.q_obs = B.upload(q_obs, nq, st);
-    uint8_t* d_taken = B.upload(taken, n, st);
-    a.min_x = prm->min_x; a.min_y = prm->min_y;
-    a.inv_w = (float)GRID_COLS / (prm->max_x - prm->min_x);   // Frame.cc:162-163
-    a.inv_h = (float)GRID_ROWS / (prm->max_y - prm->min_y);
     int npad = 32;
     while (npad < n) npad <<= 1;
-    unsigned* d_items = B.alloc<unsigned>(npad);
-    int* d_cell_start = B.alloc<int>(GRID_COLS * GRID_ROWS + 1);
-    int* d_count = B.alloc<int>(nq); int* d_base = B.alloc<int>(nq); int* d_total = B.alloc<int>(2);
-    int* d_moq = B.alloc<int>(nq); int* d_tq = B.alloc<int>(n); signed char* d_bin = B.alloc<signed char>(nq);
-    if (!a.kps || !a.desc || !d_taken || !d_items || !d_cell_start || !d_count || !d_base || !d_total || !d_moq || !d_tq || !d_bin) {
-        orb_set_error("orb_search_by_projection: device allocation failed"); cudaGetLastError(); return ORB_ERR_CUDA;
-    }
-    a.items = d_items; a.cell_start = d_cell_start; a.cand_count = d_count; a.cand_base = d_base; a.cand_total = d_total;
-    grid_build_kernel<<<1, 1024, npad * sizeof(unsigned), st>>>(a.kps, n, npad, a.min_x, a.min_y, a.inv_w, a.inv_h, d_items, d_cell_start);
     int cand_cap = std::max(nq * 128, 4096);
     for (int attempt = 0; attempt < 2; ++attempt) {
-        a.cand_cap = cand_cap;
-        a.cand_idx = B.alloc<int>(cand_cap);
-        a.cand_dist = B.alloc<unsigned short>(cand_cap);
-        if (!a.cand_idx || !a.cand_dist) { orb_set_error("orb_search_by_projection: candidate arena allocation failed"); cudaGetLastError(); return ORB_ERR_CUDA; }
-        ORB_CUDA(cudaMemsetAsync(d_total, 0, sizeof(int) * 2, st));
+        // ---- layout: [inputs | outputs] mirrored in the pinned and device slabs, then device-only scratch ----
+        Carver c;
+        const size_t o_kps = c.take(sizeof(orb_kp) * n), o_desc = c.take((size_t)32 * n), o_ur = c.take(sizeof(float) * n);
+        const size_t o_qu = c.take(4 * (size_t)nq), o_qv = c.take(4 * (size_t)nq), o_qr = c.take(4 * (size_t)nq);
+        const size_t o_qmin = c.take(4 * (size_t)nq), o_qmax = c.take(4 * (size_t)nq), o_qdesc = c.take((size_t)32 * nq);
+        const size_t o_qur = c.take(4 * (size_t)nq), o_qer = c.take(4 * (size_t)nq), o_qang = c.take(4 * (size_t)nq);
+        const size_t o_qvalid = c.take(nq), o_qobs = c.take(nq), o_taken = c.take(n);
+        const size_t in_bytes = c.off;
+        const size_t o_moq = c.take(4 * (size_t)nq), o_tq = c.take(4 * (size_t)n), o_scal = c.take(16);
+        const size_t io_bytes = c.off;   // outputs: [o_taken .. io_bytes) is copied back (taken + results)
+        const size_t o_items = c.take(4 * (size_t)npad), o_cells = c.take(4 * (GRID_COLS * GRID_ROWS + 1));
+        const size_t o_cnt = c.take(4 * (size_t)nq), o_base = c.take(4 * (size_t)nq), o_bin = c.take(nq);
+        const size_t o_topk = c.take(4 * (size_t)nq * SR_K);
+        const size_t o_cidx = c.take(4 * (size_t)cand_cap), o_cdist = c.take(2 * (size_t)cand_cap);
+        Workspace& W = g_ws;
+        int rc = W.prepare(device, c.off, io_bytes);
+        if (rc != ORB_OK) return rc;
+        cudaStream_t st = W.st;
+        uint8_t *H = W.h, *Dv = W.d;
+        auto put = [&](size_t off, const void* src, size_t bytes) { if (src) memcpy(H + off, src, bytes); };
+        put(o_kps, kps_un, sizeof(orb_kp) * n); put(o_desc, desc, (size_t)32 * n); put(o_ur, u_right, sizeof(float) * n);
+        put(o_qu, q_u, 4 * (size_t)nq); put(o_qv, q_v, 4 * (size_t)nq); put(o_qr, q_radius, 4 * (size_t)nq);
+        put(o_qmin, q_min_level, 4 * (size_t)nq); put(o_qmax, q_max_level, 4 * (size_t)nq); put(o_qdesc, q_desc, (size_t)32 * nq);
+        put(o_qur, q_ur, 4 * (size_t)nq); put(o_qer, q_er_max, 4 * (size_t)nq); put(o_qang, q_angle, 4 * (size_t)nq);
+        put(o_qvalid, q_valid, nq); put(o_qobs, q_obs, nq); put(o_taken, taken, n);
+        ORB_CUDA(cudaMemcpyAsync(Dv, H, in_bytes, cudaMemcpyHostToDevice, st));
+        SearchArgs a;
+        memset(&a, 0, sizeof(a));
+        a.n = n; a.nq = nq;
+        a.kps = (const orb_kp*)(Dv + o_kps); a.desc = Dv + o_desc; a.u_right = u_right ? (const float*)(Dv + o_ur) : nullptr;
+        a.q_u = (const float*)(Dv + o_qu); a.q_v = (const float*)(Dv + o_qv); a.q_radius = (const float*)(Dv + o_qr);
+        a.q_min_level = (const int*)(Dv + o_qmin); a.q_max_level = (const int*)(Dv + o_qmax); a.q_desc = Dv + o_qdesc;
+        a.q_ur = q_ur ? (const float*)(Dv + o_qur) : nullptr; a.q_er_max = q_er_max ? (const float*)(Dv + o_qer) : nullptr;
+        a.q_angle = q_angle ? (const float*)(Dv + o_qang) : nullptr;
+        a.q_valid = q_valid ? Dv + o_qvalid : nullptr; a.q_obs = q_obs ? Dv + o_qobs : nullptr;
+        a.min_x = prm->min_x; a.min_y = prm->min_y;
+        a.inv_w = (float)GRID_COLS / (prm->max_x - prm->min_x);   // Frame.cc:162-163
+        a.inv_h = (float)GRID_ROWS / (prm->max_y - prm->min_y);
+        int* d_scal = (int*)(Dv + o_scal);                        // [0] candidate total, [1] nmatches, [2] overflow
+        a.items = (const unsigned*)(Dv + o_items); a.cell_start = (const int*)(Dv + o_cells);
+        a.cand_count = (int*)(Dv + o_cnt); a.cand_base = (int*)(Dv + o_base); a.cand_total = d_scal;
+        a.cand_cap = cand_cap; a.cand_idx = (int*)(Dv + o_cidx); a.cand_dist = (unsigned short*)(Dv + o_cdist);
+        a.topk = (unsigned*)(Dv + o_topk);
+        ORB_CUDA(cudaMemsetAsync(d_scal, 0, 16, st));
+        grid_build_kernel<<<1, 1024, npad * sizeof(unsigned), st>>>(a.kps, n, npad, a.min_x, a.min_y, a.inv_w, a.inv_h,
+                                                                    (unsigned*)(Dv + o_items), (int*)(Dv + o_cells));
         window_candidates_kernel<<<(nq + 7) / 8, 256, 0, st>>>(a);
-        int total = 0;
-        ORB_CUDA(cudaMemcpyAsync(&total, d_total, sizeof(int), cudaMemcpyDeviceToHost, st));
+        window_resolve_kernel<<<1, SR_THREADS, sizeof(SrStage) + (size_t)n, st>>>(a, prm->mode, prm->th_dist, prm->nn_ratio, prm->check_orientation,
+                                                        Dv + o_taken, (int*)(Dv + o_moq), (int*)(Dv + o_tq),
+                                                        (signed char*)(Dv + o_bin), d_scal + 1, d_scal + 2);
+        ORB_CUDA(cudaGetLastError());
+        ORB_CUDA(cudaMemcpyAsync(H + o_taken, Dv + o_taken, io_bytes - o_taken, cudaMemcpyDeviceToHost, st));
         ORB_CUDA(cudaStreamSynchronize(st));
-        if (total <= cand_cap) break;
-        if (attempt == 1) { orb_set_error("orb_search_by_projection: candidate arena overflow"); return ORB_ERR_CAPACITY; }
-        cand_cap = total;
+        const int* scal = (const int*)(H + o_scal);
+        if (scal[2] > 0) {                                        // candidate arena overflow: once more with the exact size
+            if (attempt == 1) { orb_set_error("orb_search_by_projection: candidate arena overflow"); return ORB_ERR_CAPACITY; }
+            cand_cap = scal[2];
+            continue;
+        }
+        memcpy(taken, H + o_taken, n);
+        memcpy(match_of_query, H + o_moq, 4 * (size_t)nq);
+        if (target_query) memcpy(target_query, H + o_tq, 4 * (size_t)n);
+        *nmatches = scal[1];
+        return ORB_OK;
     }
-    window_resolve_kernel<<<1, 32, 0, st>>>(a, prm->mode, prm->th_dist, prm->nn_ratio, prm->check_orientation, d_taken, d_moq, d_tq,
-                                           d_bin, d_total + 1);
-    ORB_CUDA(cudaGetLastError());
-    ORB_CUDA(cudaMemcpyAsync(match_of_query, d_moq, sizeof(int) * nq, cudaMemcpyDeviceToHost, st));
-    if (target_query) ORB_CUDA(cudaMemcpyAsync(target_query, d_tq, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
-    ORB_CUDA(cudaMemcpyAsync(taken, d_taken, n, cudaMemcpyDeviceToHost, st));
-    ORB_CUDA(cudaMemcpyAsync(nmatches, d_total + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
-    ORB_CUDA(cudaStreamSynchronize(st));
-    return ORB_OK;
+    return ORB_ERR_CAPACITY;
 }
 
 int orb_match_bruteforce(int device, const uint8_t* desc1, const float* angle1, int n1, const uint8_t* desc2,
@@ -481,23 +652,32 @@ int orb_match_bruteforce(int device, const uint8_t* desc1, const float* angle1, 
     if (n1 == 0 || n2 == 0) return ORB_OK;
     if (n2 > 65535) { orb_set_error("orb_match_bruteforce: more than 65535 targets"); return ORB_ERR_CAPACITY; }
     if (orb_device_count() <= 0) { orb_set_error("no CUDA device visible: liborb_b200 has no CPU fallback"); return ORB_ERR_NO_DEVICE; }
-    ORB_CUDA(cudaSetDevice(device));
-    cudaStream_t st = nullptr;
-    DevBuf B;
-    const uint8_t* d1 = B.upload(desc1, (size_t)n1 * 32, st);
-    const uint8_t* d2 = B.upload(desc2, (size_t)n2 * 32, st);
-    const float* a1 = B.upload(angle1, n1, st);
-    const float* a2 = B.upload(angle2, n2, st);
-    unsigned short* D = B.alloc<unsigned short>((size_t)n1 * n2);
-    unsigned* topk = B.alloc<unsigned>((size_t)n1 * BF_K);
-    int* owner = B.alloc<int>(n2); int* m12 = B.alloc<int>(n1); signed char* bin = B.alloc<signed char>(n1); int* d_nm = B.alloc<int>(1);
-    if (!d1 || !d2 || !D || !topk || !owner || !m12 || !bin || !d_nm) { orb_set_error("orb_match_bruteforce: device allocation failed"); cudaGetLastError(); return ORB_ERR_CUDA; }
-    bf_rows_kernel<<<(n1 + 7) / 8, 256, 0, st>>>(d1, n1, d2, n2, D, topk);
-    bf_resolve_kernel<<<1, 32, 0, st>>>(D, topk, n1, n2, a1, a2, th_dist, nn_ratio, check_orientation, owner, m12, bin, d_nm);
+    Carver c;
+    const size_t o_d1 = c.take((size_t)32 * n1), o_d2 = c.take((size_t)32 * n2), o_a1 = c.take(4 * (size_t)n1), o_a2 = c.take(4 * (size_t)n2);
+    const size_t in_bytes = c.off;
+    const size_t o_m12 = c.take(4 * (size_t)n1), o_nm = c.take(16);
+    const size_t io_bytes = c.off;
+    const int dpitch = (n2 + 7) & ~7;   // 16-byte aligned rows of the u16 distance matrix
+    const size_t o_D = c.take(2 * (size_t)n1 * dpitch), o_topk = c.take(4 * (size_t)n1 * BF_K), o_owner = c.take(4 * (size_t)n2), o_bin = c.take(n1);
+    Workspace& W = g_ws;
+    int rc = W.prepare(device, c.off, io_bytes);
+    if (rc != ORB_OK) return rc;
+    cudaStream_t st = W.st;
+    uint8_t *H = W.h, *Dv = W.d;
+    memcpy(H + o_d1, desc1, (size_t)32 * n1); memcpy(H + o_d2, desc2, (size_t)32 * n2);
+    if (angle1) memcpy(H + o_a1, angle1, 4 * (size_t)n1);
+    if (angle2) memcpy(H + o_a2, angle2, 4 * (size_t)n2);
+    ORB_CUDA(cudaMemcpyAsync(Dv, H, in_bytes, cudaMemcpyHostToDevice, st));
+    bf_rows_kernel<<<(n1 + 7) / 8, 256, 0, st>>>(Dv + o_d1, n1, Dv + o_d2, n2, (unsigned short*)(Dv + o_D), dpitch, (unsigned*)(Dv + o_topk));
+    bf_resolve_kernel<<<1, SR_THREADS, sizeof(SrStage) + 4 * (size_t)((n2 + 31) / 32), st>>>((const unsigned short*)(Dv + o_D), dpitch, (const unsigned*)(Dv + o_topk), n1, n2,
+                                                                  (const float*)(Dv + o_a1), (const float*)(Dv + o_a2), th_dist, nn_ratio,
+                                                                  check_orientation, (int*)(Dv + o_owner), (int*)(Dv + o_m12),
+                                                                  (signed char*)(Dv + o_bin), (int*)(Dv + o_nm));
     ORB_CUDA(cudaGetLastError());
-    ORB_CUDA(cudaMemcpyAsync(match12, m12, sizeof(int) * n1, cudaMemcpyDeviceToHost, st));
-    ORB_CUDA(cudaMemcpyAsync(nmatches, d_nm, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaMemcpyAsync(H + o_m12, Dv + o_m12, io_bytes - o_m12, cudaMemcpyDeviceToHost, st));
     ORB_CUDA(cudaStreamSynchronize(st));
+    memcpy(match12, H + o_m12, 4 * (size_t)n1);
+    *nmatches = *(const int*)(H + o_nm);
     return ORB_OK;
 }
 

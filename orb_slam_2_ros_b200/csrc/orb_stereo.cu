@@ -6,6 +6,8 @@
 // filled in ascending iR order); (2) if < (TH_HIGH+TH_LOW)/2: 11x11 centre-subtracted L1 patch distance
 // over 11 horizontal shifts in pyramid level kpL.octave (exact in integers), parabola sub-pixel fit and
 // depth in separately-rounded fp32.  A second kernel applies the median cut (Frame.cc:662-675).
+#include <string.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -135,13 +137,17 @@ stereo_median_kernel(int N, float* uRight, float* depth, const int* __restrict__
     const int count = s_count;
     if (count == 0) { if (threadIdx.x == 0) *nkept_out = 0; return; }
     const int target = count / 2;
-    // element of rank `target` in (sad, index) order
+    // element of rank `target` in (sad, index) order; the SADs are staged in shared memory (N <= ST_MAX_N), so the
+    // O(N^2) rank count runs at shared-memory bandwidth
+    extern __shared__ int s_sad[];
+    for (int i = threadIdx.x; i < N; i += blockDim.x) s_sad[i] = sad[i];
+    __syncthreads();
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
-        const int si = sad[i];
+        const int si = s_sad[i];
         if (si < 0) continue;
         int rank = 0;
         for (int j = 0; j < N; ++j) {
-            const int sj = sad[j];
+            const int sj = s_sad[j];
             rank += (sj >= 0) && (sj < si || (sj == si && j < i));
         }
         if (rank == target) s_median = si;
@@ -179,38 +185,50 @@ extern "C" int orb_stereo_match(orb_ctx* cl, orb_ctx* cr, const orb_kp* kps_l, c
     }
     if (nl == 0 || nr == 0) return ORB_OK;
     if (nr > 65535) { orb_set_error("orb_stereo_match: more than 65535 right keypoints"); return ORB_ERR_CAPACITY; }
+    if (nl > 10000) { orb_set_error("orb_stereo_match: more than 10000 left keypoints"); return ORB_ERR_CAPACITY; }
     for (int i = 0; i < nl; ++i) if (kps_l[i].octave < 0 || kps_l[i].octave >= cl->nlevels) return ORB_ERR_INVALID;
     for (int i = 0; i < nr; ++i) if (kps_r[i].octave < 0 || kps_r[i].octave >= cl->nlevels) return ORB_ERR_INVALID;
     ORB_CUDA(cudaSetDevice(cl->device));
     ORB_CUDA(cudaStreamSynchronize(cr->stream));  // the right pyramid must be complete; work runs on the left stream
     cudaStream_t st = cl->stream;
-    orb_kp *d_kl = nullptr, *d_kr = nullptr; uint8_t *d_dl = nullptr, *d_dr = nullptr;
-    float *d_ur = nullptr, *d_dep = nullptr; int *d_sad = nullptr, *d_nk = nullptr;
-    int rc = ORB_OK;
-#define ST_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { orb_set_error("%s -> %s", #x, cudaGetErrorString(e_)); rc = ORB_ERR_CUDA; goto done; } } while (0)
-    ST_CUDA(cudaMalloc(&d_kl, sizeof(orb_kp) * nl)); ST_CUDA(cudaMalloc(&d_kr, sizeof(orb_kp) * nr));
-    ST_CUDA(cudaMalloc(&d_dl, (size_t)32 * nl)); ST_CUDA(cudaMalloc(&d_dr, (size_t)32 * nr));
-    ST_CUDA(cudaMalloc(&d_ur, sizeof(float) * nl)); ST_CUDA(cudaMalloc(&d_dep, sizeof(float) * nl));
-    ST_CUDA(cudaMalloc(&d_sad, sizeof(int) * nl)); ST_CUDA(cudaMalloc(&d_nk, sizeof(int)));
-    ST_CUDA(cudaMemcpyAsync(d_kl, kps_l, sizeof(orb_kp) * nl, cudaMemcpyHostToDevice, st));
-    ST_CUDA(cudaMemcpyAsync(d_kr, kps_r, sizeof(orb_kp) * nr, cudaMemcpyHostToDevice, st));
-    ST_CUDA(cudaMemcpyAsync(d_dl, desc_l, (size_t)32 * nl, cudaMemcpyHostToDevice, st));
-    ST_CUDA(cudaMemcpyAsync(d_dr, desc_r, (size_t)32 * nr, cudaMemcpyHostToDevice, st));
+    // one pinned + one device slab owned by the left context (grow-only): a single H2D, the two kernels, a single D2H
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_kl = take(sizeof(orb_kp) * nl), o_kr = take(sizeof(orb_kp) * nr), o_dl = take((size_t)32 * nl), o_dr = take((size_t)32 * nr);
+    const size_t in_bytes = off;
+    const size_t o_ur = take(sizeof(float) * nl), o_dep = take(sizeof(float) * nl), o_nk = take(16);
+    const size_t io_bytes = off;
+    const size_t o_sad = take(sizeof(int) * nl);
+    if (cl->d_scratch_cap < off) {
+        ORB_CUDA(cudaStreamSynchronize(st));
+        cudaFree(cl->d_scratch); cl->d_scratch = nullptr; cl->d_scratch_cap = 0;
+        ORB_CUDA(cudaMalloc(&cl->d_scratch, off * 2));
+        cl->d_scratch_cap = off * 2;
+    }
+    if (cl->h_scratch_cap < io_bytes) {
+        ORB_CUDA(cudaStreamSynchronize(st));
+        cudaFreeHost(cl->h_scratch); cl->h_scratch = nullptr; cl->h_scratch_cap = 0;
+        ORB_CUDA(cudaMallocHost(&cl->h_scratch, io_bytes * 2));
+        cl->h_scratch_cap = io_bytes * 2;
+    }
+    uint8_t *H = cl->h_scratch, *D = cl->d_scratch;
+    memcpy(H + o_kl, kps_l, sizeof(orb_kp) * nl); memcpy(H + o_kr, kps_r, sizeof(orb_kp) * nr);
+    memcpy(H + o_dl, desc_l, (size_t)32 * nl); memcpy(H + o_dr, desc_r, (size_t)32 * nr);
+    ORB_CUDA(cudaMemcpyAsync(D, H, in_bytes, cudaMemcpyHostToDevice, st));
     {
         StereoScales sc;
         for (int l = 0; l < ORB_MAX_LEVELS; ++l) { sc.scale[l] = l < cl->nlevels ? cl->scale[l] : 1.f; sc.inv_scale[l] = l < cl->nlevels ? cl->inv_scale[l] : 1.f; }
-        stereo_match_kernel<<<(nl + 7) / 8, 256, 0, st>>>(cl->d_pyr, cr->d_pyr, d_kl, d_dl, nl, d_kr, d_dr, nr, bf, b, sc, d_ur, d_dep,
-                                                         d_sad, cl->g);
-        stereo_median_kernel<<<1, 1024, 0, st>>>(nl, d_ur, d_dep, d_sad, d_nk);
+        stereo_match_kernel<<<(nl + 7) / 8, 256, 0, st>>>(cl->d_pyr, cr->d_pyr, (const orb_kp*)(D + o_kl), D + o_dl, nl, (const orb_kp*)(D + o_kr),
+                                                         D + o_dr, nr, bf, b, sc, (float*)(D + o_ur), (float*)(D + o_dep), (int*)(D + o_sad), cl->g);
+        stereo_median_kernel<<<1, 1024, sizeof(int) * (size_t)nl, st>>>(nl, (float*)(D + o_ur), (float*)(D + o_dep), (const int*)(D + o_sad), (int*)(D + o_nk));
         cl->launches += 2;
     }
-    ST_CUDA(cudaGetLastError());
-    ST_CUDA(cudaMemcpyAsync(u_right, d_ur, sizeof(float) * nl, cudaMemcpyDeviceToHost, st));
-    ST_CUDA(cudaMemcpyAsync(depth, d_dep, sizeof(float) * nl, cudaMemcpyDeviceToHost, st));
-    ST_CUDA(cudaMemcpyAsync(nmatches, d_nk, sizeof(int), cudaMemcpyDeviceToHost, st));
-    ST_CUDA(cudaStreamSynchronize(st));
-done:
-    cudaFree(d_kl); cudaFree(d_kr); cudaFree(d_dl); cudaFree(d_dr); cudaFree(d_ur); cudaFree(d_dep); cudaFree(d_sad); cudaFree(d_nk);
-    return rc;
-#undef ST_CUDA
+    ORB_CUDA(cudaGetLastError());
+    ORB_CUDA(cudaMemcpyAsync(H + o_ur, D + o_ur, io_bytes - o_ur, cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaStreamSynchronize(st));
+    memcpy(u_right, H + o_ur, sizeof(float) * nl);
+    memcpy(depth, H + o_dep, sizeof(float) * nl);
+    *nmatches = *(const int*)(H + o_nk);
+    return ORB_OK;
 }
+
