@@ -27,16 +27,18 @@ __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9
 // the size>=N cut, ORBextractor.cc:700-761).  New list = reverse(children in creation order) ++ (old list
 // minus expanded parents), exactly what push_front / erase produce.
 // ======================================================================================================
-#define QT_THREADS 256
+#define QT_THREADS 256        // throughput shape (many frames in flight)
+#define QT_THREADS_LAT 1024   // latency shape (a few frames): 4x the threads for the key passes of the big levels
 
 struct QtNode { short x0, y0, x1, y1; };
 
-__device__ __forceinline__ int block_exclusive_scan(int* data, int n, int* s_warp /*[8]*/, int* s_carry) {
+template <int NT>
+__device__ __forceinline__ int block_exclusive_scan(int* data, int n, int* s_warp /*[NT / 32]*/, int* s_carry) {
     // in-place exclusive scan of data[0..n), returns the total; all threads must call
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (threadIdx.x == 0) *s_carry = 0;
     __syncthreads();
-    for (int base = 0; base < n; base += QT_THREADS) {
+    for (int base = 0; base < n; base += NT) {
         const int i = base + threadIdx.x;
         const int v = (i < n) ? data[i] : 0;
         int x = v;
@@ -52,13 +54,14 @@ __device__ __forceinline__ int block_exclusive_scan(int* data, int n, int* s_war
         const int carry = *s_carry;
         if (i < n) data[i] = carry + woff + x - v;
         __syncthreads();
-        if (threadIdx.x == QT_THREADS - 1) *s_carry = carry + woff + x;
+        if (threadIdx.x == NT - 1) *s_carry = carry + woff + x;
         __syncthreads();
     }
     return *s_carry;
 }
 
-__global__ void __launch_bounds__(QT_THREADS)
+template <int NT>
+__global__ void __launch_bounds__(NT)
 quadtree_kernel(const unsigned long long* __restrict__ corners, const int* __restrict__ corner_count,
                 unsigned short* __restrict__ node_of_key, unsigned long long* __restrict__ kept,
                 int* __restrict__ kept_count, int* __restrict__ tie_count, const __grid_constant__ Geometry g) {
@@ -92,7 +95,7 @@ quadtree_kernel(const unsigned long long* __restrict__ corners, const int* __res
     unsigned short* cand_id2 = cand_id + cap;                                         // 2*cap
     short2* split = reinterpret_cast<short2*>(cand_id2 + cap);                        // 4*cap
     uint8_t* expanding = reinterpret_cast<uint8_t*>(split + cap);                     // cap
-    __shared__ int s_warp[8], s_carry, s_L, s_nS, s_nExp, s_ncand, s_ncand2, s_nexp_children, s_nextid;
+    __shared__ int s_warp[NT / 32], s_carry, s_L, s_nS, s_nExp, s_ncand, s_ncand2, s_nexp_children, s_nextid;
 
     const int W = L.maxBX - ORB_MINB, H = L.maxBY - ORB_MINB;
     const float hX = L.hX;
@@ -133,7 +136,7 @@ quadtree_kernel(const unsigned long long* __restrict__ corners, const int* __res
         if (phase == 1) {
             for (int p = threadIdx.x; p < Lcur; p += blockDim.x) scan_a[p] = cnt[list[p]] > 1;
             __syncthreads();
-            const int nS = block_exclusive_scan(scan_a, Lcur, s_warp, &s_carry);
+            const int nS = block_exclusive_scan<NT>(scan_a, Lcur, s_warp, &s_carry);
             for (int p = threadIdx.x; p < Lcur; p += blockDim.x)
                 if (cnt[list[p]] > 1) S[scan_a[p]] = list[p];
             if (threadIdx.x == 0) s_nS = nS;
@@ -183,7 +186,7 @@ quadtree_kernel(const unsigned long long* __restrict__ corners, const int* __res
             scan_b[r] = nc - 1;   // -> id offset / size gain
         }
         __syncthreads();
-        block_exclusive_scan(scan_b, nS, s_warp, &s_carry);
+        block_exclusive_scan<NT>(scan_b, nS, s_warp, &s_carry);
         if (threadIdx.x == 0) s_nExp = nS;
         __syncthreads();
         if (phase == 2) {
@@ -198,7 +201,7 @@ quadtree_kernel(const unsigned long long* __restrict__ corners, const int* __res
         const int nExp = s_nExp;
         if (phase == 2 && nExp < nS && threadIdx.x == 0 && cnt[S[nExp]] == cnt[S[nExp - 1]])
             atomicAdd(&tie_count[f * g.nlevels + l], 1);  // the cut fell inside an equal-size group (pin (ii))
-        const int T = block_exclusive_scan(scan_a, nExp, s_warp, &s_carry);  // total children created
+        const int T = block_exclusive_scan<NT>(scan_a, nExp, s_warp, &s_carry);  // total children created
         if (threadIdx.x == 0) { s_ncand2 = 0; s_nexp_children = 0; }
         __syncthreads();
         // ---- 5. create children ----
@@ -237,7 +240,7 @@ quadtree_kernel(const unsigned long long* __restrict__ corners, const int* __res
         // ---- 6. old list minus expanded parents keeps its order behind the new children ----
         for (int p = threadIdx.x; p < Lcur; p += blockDim.x) scan_a[p] = expanding[list[p]] ? 0 : 1;
         __syncthreads();
-        const int nkeep = block_exclusive_scan(scan_a, Lcur, s_warp, &s_carry);
+        const int nkeep = block_exclusive_scan<NT>(scan_a, Lcur, s_warp, &s_carry);
         for (int p = threadIdx.x; p < Lcur; p += blockDim.x) {
             const int id = list[p];
             if (!expanding[id] && T + scan_a[p] < cap) nlist[T + scan_a[p]] = (unsigned short)id;
@@ -517,8 +520,12 @@ int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int F, int f0, size_t 
     ORB_STAGE_MARK(2);
     {   // K3
         const size_t smem = (size_t)g.max_node_cap * 80;
-        quadtree_kernel<<<dim3(g.nlevels, F), QT_THREADS, smem, st>>>(c->d_corners, d_cc, c->d_node_of_key, d_kept, d_kept_count,
-                                                                       d_tie, g);
+        if (F >= 8)
+            quadtree_kernel<QT_THREADS><<<dim3(g.nlevels, F), QT_THREADS, smem, st>>>(c->d_corners, d_cc, c->d_node_of_key, d_kept,
+                                                                                       d_kept_count, d_tie, g);
+        else
+            quadtree_kernel<QT_THREADS_LAT><<<dim3(g.nlevels, F), QT_THREADS_LAT, smem, st>>>(c->d_corners, d_cc, c->d_node_of_key, d_kept,
+                                                                                               d_kept_count, d_tie, g);
         c->launches++;
     }
     ORB_STAGE_MARK(3);

@@ -66,6 +66,7 @@ __device__ __forceinline__ void hrow4(const unsigned* __restrict__ srow, int wb,
     }
 }
 
+template <int ROWS>
 __global__ void __launch_bounds__(256)
 pyr_resize_fast_kernel(uint8_t* __restrict__ pyr, const ResizeTap* __restrict__ taps, const ResizeWord* __restrict__ wtaps,
                        int level, const __grid_constant__ Geometry g) {
@@ -73,7 +74,7 @@ pyr_resize_fast_kernel(uint8_t* __restrict__ pyr, const ResizeTap* __restrict__ 
     const LevelGeom& P = g.lv[level - 1];
     const int wpr = (L.w + 3) >> 2;
     const int item = blockIdx.x * blockDim.x + threadIdx.x;
-    const int strips = (L.h + ORB_RESIZE_ROWS - 1) / ORB_RESIZE_ROWS;
+    const int strips = (L.h + ROWS - 1) / ROWS;
     if (item >= wpr * strips) return;
     const int strip = item / wpr, wc = item - strip * wpr;
     const int f = blockIdx.y;
@@ -87,7 +88,7 @@ pyr_resize_fast_kernel(uint8_t* __restrict__ pyr, const ResizeTap* __restrict__ 
     const unsigned cc[4] = {t.cc[0], t.cc[1], t.cc[2], t.cc[3]};
     const uint8_t* S = pyr + P.base + (long long)f * P.frame_stride + P.ioff;    // 16-byte aligned
     uint8_t* D = pyr + L.base + (long long)f * L.frame_stride + L.ioff + 4 * wc;
-    const int y0 = strip * ORB_RESIZE_ROWS, y1 = min(y0 + ORB_RESIZE_ROWS, L.h);
+    const int y0 = strip * ROWS, y1 = min(y0 + ROWS, L.h);
     const uint2* ytab = reinterpret_cast<const uint2*>(taps + L.ytab);   // ResizeTap = {u16 s0, u16 s1, s16 c0, s16 c1}
     const int ppw = P.pitch >> 2;
     unsigned h0[4], h1[4];
@@ -222,9 +223,14 @@ int orb_launch_pyramid(orb_ctx* c, const Geometry& g, const uint8_t* d_imgs, int
     for (int l = 1; l < g.nlevels; ++l) {
         const LevelGeom& L = g.lv[l];
         const int wpr = (L.w + 3) >> 2;
-        if (L.fast_resize) {
+        if (L.fast_resize && F >= 8) {
+            // throughput shape: 8 output rows per thread (the lower source row is reused 4 times out of 5)
             const int items = wpr * ((L.h + ORB_RESIZE_ROWS - 1) / ORB_RESIZE_ROWS);
-            pyr_resize_fast_kernel<<<dim3((items + 255) / 256, F), 256, 0, st>>>(c->d_pyr, c->d_taps, c->d_wtaps, l, g);
+            pyr_resize_fast_kernel<ORB_RESIZE_ROWS><<<dim3((items + 255) / 256, F), 256, 0, st>>>(c->d_pyr, c->d_taps, c->d_wtaps, l, g);
+        } else if (L.fast_resize) {
+            // latency shape (a few frames): 2 rows per thread = 4x the threads and a 4x shorter dependent-load chain
+            const int items = wpr * ((L.h + 1) / 2);
+            pyr_resize_fast_kernel<2><<<dim3((items + 255) / 256, F), 256, 0, st>>>(c->d_pyr, c->d_taps, c->d_wtaps, l, g);
         } else {
             const int items = wpr * L.h;
             pyr_resize_generic_kernel<<<dim3((items + 255) / 256, F), 256, 0, st>>>(c->d_pyr, c->d_taps, l, g);
