@@ -39,7 +39,7 @@ namespace {
 #define FS_SCORED_BYTES (FS_SCAP * 2)
 #define FS_SCORE_BYTES (FS_SROWS * FS_PITCH)
 #define FS_SMEM (FS_TILE_BYTES + FS_CAND_BYTES + FS_SCORED_BYTES + FS_SCORE_BYTES)
-#define FS_OUT_CAP ((FS_TILE_BYTES + FS_CAND_BYTES) / 8)   // records that fit the (dead) tile + candidate segments: 4036 >= 3750
+#define FS_OUT_CAP ((FS_TILE_BYTES + FS_CAND_BYTES) / 8)   // records that fit the (dead) tile + candidate segments (4036 >= the 3750 worst case; anything beyond goes straight to global)
 
 // exact FAST score of the pixel at t (shared-memory tile): both polarities in one s16x2 min/max tree on the packed
 // pairs (r_k, 255 - r_k):  lo -> max_arc min r = bmax,  hi -> max_arc min (255 - r) = 255 - min_arc max r = 255 - amin
@@ -220,9 +220,14 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
     auto emit = [&](int r, int sb, int sc, int jj, int xr) {
         // vToDistributeKeys coordinates (ORBextractor.cc:856-857) and the reference's visiting order key
         const int cell = i * L.nCols + j0 + jj;
+        const unsigned long long rec = corner_pack(j0 * wCell + 3 + (sb - sb_lo), i * L.hCell + 3 + r, sc, (cell << 12) | (r << 6) | xr);
         const int o = atomicAdd(&s_nout, 1);
-        if (o < FS_OUT_CAP)
-            outl[o] = corner_pack(j0 * wCell + 3 + (sb - sb_lo), i * L.hCell + 3 + r, sc, (cell << 12) | (r << 6) | xr);
+        if (o < FS_OUT_CAP) {
+            outl[o] = rec;
+        } else {   // staging list full (> 3000 NMS maxima in one strip): append to the level's list directly
+            const int gi = atomicAdd(corner_count + f * g.nlevels + l, 1);
+            if (gi < L.corner_cap) corners[L.corner_base + (long long)f * L.corner_cap + gi] = rec;
+        }
     };
     const int nscored = s_nscored;
     if (nscored <= FS_SCAP) {
