@@ -36,12 +36,12 @@ inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 void free_geometry_buffers(orb_ctx* c) {
     cudaFree(c->d_in); cudaFree(c->d_pyr); cudaFree(c->d_blur); cudaFree(c->d_corners); cudaFree(c->d_node_of_key);
     cudaFree(c->d_corner_count); cudaFree(c->d_kept); cudaFree(c->d_kept_count); cudaFree(c->d_taps);
-    cudaFree(c->d_wtaps); cudaFree(c->d_strips); cudaFree(c->d_kps_out); cudaFree(c->d_desc_out); cudaFree(c->d_n_out);
+    cudaFree(c->d_wtaps); cudaFree(c->d_strips); cudaFree(c->d_tmaps); cudaFree(c->d_kps_out); cudaFree(c->d_desc_out); cudaFree(c->d_n_out);
     cudaFreeHost(c->h_kps); cudaFreeHost(c->h_desc); cudaFreeHost(c->h_n); cudaFreeHost(c->h_in);
     c->h_out_cap = 0;
     c->d_in = c->d_pyr = c->d_blur = nullptr; c->d_corners = nullptr; c->d_node_of_key = nullptr;
     c->d_corner_count = c->d_kept_count = nullptr; c->d_kept = nullptr; c->d_taps = nullptr;
-    c->d_wtaps = nullptr; c->d_strips = nullptr; c->d_kps_out = nullptr; c->d_desc_out = nullptr; c->d_n_out = nullptr;
+    c->d_wtaps = nullptr; c->d_strips = nullptr; c->d_tmaps = nullptr; c->d_kps_out = nullptr; c->d_desc_out = nullptr; c->d_n_out = nullptr;
     c->h_kps = nullptr; c->h_desc = nullptr; c->h_n = nullptr; c->h_in = nullptr;
     c->in_bytes = c->h_in_bytes = 0; c->out_cap = 0;
     c->have_geom = false;
@@ -136,7 +136,7 @@ int build_geometry(orb_ctx* c, int w, int h) {
         L.scale = c->scale[l];
         L.size = (float)(int)(ORB_PATCH * c->scale[l]);  // ORBextractor.cc:874
         // FAST strips: one CTA = fast_G consecutive cells of one cell row (tile width fast_G * wCell + 6 <= 256)
-        const int gmax = std::max(1, 250 / L.wCell);
+        const int gmax = std::max(1, 231 / L.wCell);   // 19 (alignment shift) + tile <= 256 bytes = one TMA box row
         L.fast_groups = (L.nCols + gmax - 1) / gmax;
         L.fast_G = (L.nCols + L.fast_groups - 1) / L.fast_groups;
         L.fast_cta_base = fast_ctas; fast_ctas += L.nRows * L.fast_groups;
@@ -205,8 +205,9 @@ int build_geometry(orb_ctx* c, int w, int h) {
                 memset(&s, 0, sizeof(s));
                 s.level = l; s.i = i; s.j0 = j0; s.ncell = ncell; s.iniY = iniY; s.ch = ch;
                 s.X0 = ORB_MINB + j0 * L.wCell; s.tw = X1 - s.X0;
-                // interior rows start 16-byte aligned, so the tile's byte alignment is X0 & 3; one spare word on the left
-                s.a = (s.X0 & 3) + 4;
+                // the tile starts at a 16-byte aligned global address (a TMA requirement; interior rows are 16-byte aligned,
+                // so that is X0 rounded down to 16) with at least one spare word on the left: shift a in [4, 19]
+                s.a = (s.X0 & 15) < 4 ? (s.X0 & 15) + 16 : (s.X0 & 15);
                 s.lw = (s.a + s.tw + 3) >> 2;
                 const int sb_lo = s.a + 3, sb_hi = s.a + 3 + (s.tw - 6);
                 s.wlo = sb_lo >> 2; s.nw = ((sb_hi - 1) >> 2) - s.wlo + 1;
@@ -234,6 +235,39 @@ int build_geometry(orb_ctx* c, int w, int h) {
     ORB_CUDA(cudaMalloc(&c->d_wtaps, sizeof(ResizeWord) * h_wtaps.size()));
     ORB_CUDA(cudaMemcpyAsync(c->d_taps, h_taps.data(), sizeof(ResizeTap) * h_taps.size(), cudaMemcpyHostToDevice, c->stream));
     ORB_CUDA(cudaMemcpyAsync(c->d_wtaps, h_wtaps.data(), sizeof(ResizeWord) * h_wtaps.size(), cudaMemcpyHostToDevice, c->stream));
+    // TMA descriptors for the FAST strip loader (cuTensorMapEncodeTiled through the runtime's driver entry point: no
+    // link dependency on libcuda).  Without them the kernel falls back to its LDG -> STS loader.
+    c->use_tma = false;
+    {
+        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (!getenv("ORB_B200_NO_TMA") &&
+            cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn &&
+            qres == cudaDriverEntryPointSuccess) {
+            bool ok = true;
+            for (int l = 0; l < g.nlevels && ok; ++l) {
+                const LevelGeom& L = g.lv[l];
+                const cuuint64_t dims[3] = {(cuuint64_t)L.pitch, (cuuint64_t)L.rows, (cuuint64_t)F};
+                const cuuint64_t strides[2] = {(cuuint64_t)L.pitch, (cuuint64_t)L.frame_stride};   // bytes, dims 1 and 2
+                const cuuint32_t box[3] = {ORB_TMA_BOX_W, ORB_TMA_BOX_H, 1};
+                const cuuint32_t estr[3] = {1, 1, 1};
+                const CUresult r = ((EncodeFn)fn)(&c->tmaps.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, c->d_pyr + L.base, dims, strides, box,
+                                                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                ok = (r == CUDA_SUCCESS);
+            }
+            if (ok) {
+                ORB_CUDA(cudaMalloc(&c->d_tmaps, sizeof(FastTmaps)));
+                ORB_CUDA(cudaMemcpyAsync(c->d_tmaps, &c->tmaps, sizeof(FastTmaps), cudaMemcpyHostToDevice, c->stream));
+            }
+            c->use_tma = ok;
+        } else {
+            cudaGetLastError();
+        }
+    }
     ORB_CUDA(cudaMemsetAsync(c->d_pyr, 0, c->pyr_bytes + 256, c->stream));
     ORB_CUDA(cudaMemsetAsync(c->d_blur, 0, c->blur_bytes + 256, c->stream));
     ORB_CUDA(cudaMemsetAsync(c->d_kept_count, 0, sizeof(int) * (size_t)F * g.nlevels, c->stream));

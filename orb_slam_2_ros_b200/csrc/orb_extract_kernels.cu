@@ -516,7 +516,7 @@ int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int F, int f0, size_t 
     ORB_STAGE_MARK(0);
     { int rc = orb_launch_pyramid(c, g, d_imgs, F, row_stride, frame_stride, st); if (rc != ORB_OK) return rc; }   // K1
     ORB_STAGE_MARK(1);
-    { int rc = orb_launch_fast(c, g, d_cc, F, st); if (rc != ORB_OK) return rc; }                                   // K2
+    { int rc = orb_launch_fast(c, g, d_cc, F, f0, st); if (rc != ORB_OK) return rc; }                                   // K2
     ORB_STAGE_MARK(2);
     {   // K3
         const size_t smem = (size_t)g.max_node_cap * 80;

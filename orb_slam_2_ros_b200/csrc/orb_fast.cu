@@ -28,7 +28,7 @@ namespace {
 
 #define FS_THREADS 256
 #define FS_WARPS (FS_THREADS / 32)
-#define FS_PITCH 272       // bytes per shared-memory row: 7 (alignment shift) + 256 (tile) + word slack, multiple of 16
+#define FS_PITCH 256       // bytes per shared-memory row = one TMA box row: alignment shift (<= 19) + tile (<= 237)
 #define FS_ROWS 66         // cell sub-image height <= hCell + 6 <= 66
 #define FS_SROWS 62        // evaluated rows <= 60, plus a zero row above and below
 #define FS_MAXG 8          // 250 / 30
@@ -38,7 +38,7 @@ namespace {
 #define FS_CAND_BYTES (FS_WARPS * FS_WCAP * 2)
 #define FS_SCORED_BYTES (FS_SCAP * 2)
 #define FS_SCORE_BYTES (FS_SROWS * FS_PITCH)
-#define FS_SMEM (FS_TILE_BYTES + FS_CAND_BYTES + FS_SCORED_BYTES + FS_SCORE_BYTES)
+#define FS_SMEM (FS_TILE_BYTES + FS_CAND_BYTES + FS_SCORED_BYTES + FS_SCORE_BYTES + 128)
 #define FS_OUT_CAP ((FS_TILE_BYTES + FS_CAND_BYTES) / 8)   // records that fit the (dead) tile + candidate segments (4036 >= the 3750 worst case; anything beyond goes straight to global)
 
 // exact FAST score of the pixel at t (shared-memory tile): both polarities in one s16x2 min/max tree on the packed
@@ -67,6 +67,31 @@ __device__ __forceinline__ int fast_score_at(const uint8_t* t) {
 
 // bits 0/1: pixel 2h / 2h+1 of the word passes the directional quick test.  All operands hold two u8 pixels
 // widened to s16x2.
+// ---- TMA (cp.async.bulk.tensor) + mbarrier plumbing ----------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int x, int y, int z, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+}
+
 template <int H>
 __device__ __forceinline__ unsigned quick2(unsigned c, unsigned r0, unsigned r8, unsigned r4, unsigned r12, unsigned r2,
                                            unsigned r10, unsigned r6, unsigned r14, unsigned tp1, unsigned ntp1) {
@@ -84,10 +109,13 @@ __device__ __forceinline__ unsigned quick2(unsigned c, unsigned r0, unsigned r8,
     return ((bl | dl) ? 1u : 0u) | ((bh | dh) ? 2u : 0u);
 }
 
+template <bool TMA>
 __global__ void __launch_bounds__(FS_THREADS)
 fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__ strips, unsigned long long* __restrict__ corners,
-                  int* __restrict__ corner_count, const __grid_constant__ Geometry g) {
-    extern __shared__ __align__(16) uint8_t fs_smem[];
+                  int* __restrict__ corner_count, const __grid_constant__ Geometry g, const FastTmaps* __restrict__ tm, int f0) {
+    extern __shared__ __align__(1024) uint8_t fs_smem_raw[];
+    // the TMA destination must be 128-byte aligned: align by hand (static shared variables precede the dynamic window)
+    uint8_t* fs_smem = fs_smem_raw + ((128u - (smem_u32(fs_smem_raw) & 127u)) & 127u);
     uint8_t* tile = fs_smem;                                                                     // FS_ROWS x FS_PITCH pixels
     unsigned short* cand = reinterpret_cast<unsigned short*>(fs_smem + FS_TILE_BYTES);            // per-warp segments
     unsigned short* scored = reinterpret_cast<unsigned short*>(fs_smem + FS_TILE_BYTES + FS_CAND_BYTES);
@@ -95,6 +123,7 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
     unsigned long long* outl = reinterpret_cast<unsigned long long*>(fs_smem);                   // pass 3: aliases tile + cand
     __shared__ int s_any[FS_MAXG];
     __shared__ int s_nscored, s_nout, s_base;
+    __shared__ __align__(8) unsigned long long s_mbar;
 
     const int f = blockIdx.y;
     const FastStrip S = strips[blockIdx.x];               // host-precomputed (uniform loads)
@@ -104,23 +133,39 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
     const int ch = S.ch, tw = S.tw;
     const int ew = tw - 6, eh = ch - 6;                    // evaluated area
 
-    // ---- load the tile as aligned words: tile pixel (x, y) lands at tile[y * FS_PITCH + a + x] ----
-    // (a = (X0 & 3) + 4: one spare word on the left, so that word index wd - 1 of the first evaluated word exists)
+    // ---- load the tile: tile pixel (x, y) lands at tile[y * FS_PITCH + a + x] ----
+    // (a in [4, 19]: the tile starts at a 16-byte aligned global address — the TMA unit faults otherwise — with at
+    // least one spare word on the left, so that word index wd - 1 of the first evaluated word exists)
     const int a = S.a;
-    const unsigned* src_w = reinterpret_cast<const unsigned*>(pyr + L.base + (long long)f * L.frame_stride + L.ioff +
-                                                              S.iniY * L.pitch + S.X0 - a);
-    const int lw = S.lw;                                   // words per row to load (<= 66)
-    const unsigned inv_lw = S.inv_lw;
-    const int gpw = L.pitch >> 2;
-    for (int k = threadIdx.x; k < ch * lw; k += FS_THREADS) {
-        const int r = (int)__umulhi((unsigned)k, inv_lw), wd = k - r * lw;
-        reinterpret_cast<unsigned*>(tile + r * FS_PITCH)[wd] = __ldg(src_w + r * gpw + wd);
+    if (TMA) {
+        // one elected thread arms the mbarrier and issues 1-2 bulk tensor copies (box 256 B x 33 rows) of the strip with
+        // its halo; rows / bytes beyond the level are zero-filled by the TMA unit and never evaluated
+        if (threadIdx.x == 0) mbar_init(&s_mbar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int parts = (ch + ORB_TMA_BOX_H - 1) / ORB_TMA_BOX_H;
+            mbar_expect_tx(&s_mbar, (unsigned)parts * ORB_TMA_BOX_W * ORB_TMA_BOX_H);
+            for (int p = 0; p < parts; ++p)
+                tma_load_3d(tile + p * ORB_TMA_BOX_H * FS_PITCH, &tm->m[l], ORB_XOFF + S.X0 - a, ORB_EDGE + S.iniY + p * ORB_TMA_BOX_H,
+                            f0 + f, &s_mbar);
+        }
+    } else {
+        const unsigned* src_w = reinterpret_cast<const unsigned*>(pyr + L.base + (long long)f * L.frame_stride + L.ioff +
+                                                                  S.iniY * L.pitch + S.X0 - a);
+        const int lw = S.lw;                               // words per row to load (<= 64)
+        const unsigned inv_lw = S.inv_lw;
+        const int gpw = L.pitch >> 2;
+        for (int k = threadIdx.x; k < ch * lw; k += FS_THREADS) {
+            const int r = (int)__umulhi((unsigned)k, inv_lw), wd = k - r * lw;
+            reinterpret_cast<unsigned*>(tile + r * FS_PITCH)[wd] = __ldg(src_w + r * gpw + wd);
+        }
     }
     if (threadIdx.x < FS_MAXG) s_any[threadIdx.x] = 0;
     if (threadIdx.x == 0) { s_nscored = 0; s_nout = 0; }
     for (int k = threadIdx.x; k < (eh + 2) * (FS_PITCH / 16); k += FS_THREADS)
         reinterpret_cast<uint4*>(score)[k] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
+    if (TMA) mbar_wait(&s_mbar, 0);   // the tile has landed (async-proxy writes are visible after the wait)
 
     // ---- pass 1: scores.  Evaluated pixels are the shared-memory bytes [sb_lo, sb_hi) of tile rows [3, 3+eh) ----
     const int tmin = g.min_th, tini = g.ini_th;
@@ -294,12 +339,18 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
 
 }  // namespace
 
-int orb_launch_fast(orb_ctx* c, const Geometry& g, int* d_corner_count, int F, cudaStream_t st) {
+int orb_launch_fast(orb_ctx* c, const Geometry& g, int* d_corner_count, int F, int f0, cudaStream_t st) {
     if (!c->fast_attr_set) {   // > 48 KB of dynamic shared memory needs the opt-in, once per context (= per device)
-        ORB_CUDA(cudaFuncSetAttribute(fast_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM));
+        ORB_CUDA(cudaFuncSetAttribute(fast_strip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM));
+        ORB_CUDA(cudaFuncSetAttribute(fast_strip_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM));
         c->fast_attr_set = true;
     }
-    fast_strip_kernel<<<dim3(g.fast_ctas, F), FS_THREADS, FS_SMEM, st>>>(c->d_pyr, c->d_strips, c->d_corners, d_corner_count, g);
+    if (c->use_tma)
+        fast_strip_kernel<true><<<dim3(g.fast_ctas, F), FS_THREADS, FS_SMEM, st>>>(c->d_pyr, c->d_strips, c->d_corners, d_corner_count, g,
+                                                                                   c->d_tmaps, f0);
+    else
+        fast_strip_kernel<false><<<dim3(g.fast_ctas, F), FS_THREADS, FS_SMEM, st>>>(c->d_pyr, c->d_strips, c->d_corners, d_corner_count, g,
+                                                                                    c->d_tmaps, f0);
     c->launches++;
     ORB_CUDA(cudaGetLastError());
     return ORB_OK;

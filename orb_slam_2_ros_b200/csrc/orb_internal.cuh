@@ -1,5 +1,6 @@
 // orb_internal.cuh — shared declarations of liborb_b200 (sm_100a).  Not a public header.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -82,6 +83,11 @@ struct __align__(16) ResizeWord {  // 4 adjacent destination columns (one output
     unsigned cc[4];      // c0 | c1 << 16 per column (Q11)
     int pad[2];
 };
+// TMA descriptors of the pyramid levels (dims: row bytes, rows, frames of the arena) for the FAST strip loader
+struct FastTmaps { CUtensorMap m[ORB_MAX_LEVELS]; };
+#define ORB_TMA_BOX_W 256
+#define ORB_TMA_BOX_H 33
+
 struct __align__(16) FastStrip {   // one CTA of fast_strip_kernel: up to fast_G consecutive valid cells of one cell row
     int level, i, j0, ncell;       // cell row, first cell column, number of valid cells
     int iniY, ch, X0, tw;          // cell sub-image rows [iniY, iniY+ch), tile columns [X0, X0+tw) (interior coords)
@@ -132,6 +138,9 @@ struct orb_ctx {
     ResizeTap* d_taps = nullptr;
     ResizeWord* d_wtaps = nullptr;
     FastStrip* d_strips = nullptr;
+    FastTmaps tmaps;              // valid when use_tma
+    FastTmaps* d_tmaps = nullptr; // device copy (the TMA unit reads the descriptor from global memory)
+    bool use_tma = false;
     uint2* d_mom_tab = nullptr;   // IC_Angle weight table [4 alignments][288 items] (orient_describe_kernel)
     bool fast_attr_set = false;
     orb_kp* d_kps_out = nullptr; uint8_t* d_desc_out = nullptr; int* d_n_out = nullptr; int out_cap = 0;
@@ -155,7 +164,7 @@ int orb_profile_harvest(orb_ctx* c, int slot);
 // kernels' launchers (orb_extract_kernels.cu)
 int orb_launch_pyramid(orb_ctx* c, const Geometry& g, const uint8_t* d_imgs, int nframes, size_t row_stride,
                        size_t frame_stride, cudaStream_t st);
-int orb_launch_fast(orb_ctx* c, const Geometry& g, int* d_corner_count, int nframes, cudaStream_t st);
+int orb_launch_fast(orb_ctx* c, const Geometry& g, int* d_corner_count, int nframes, int f0, cudaStream_t st);
 int orb_launch_blur(orb_ctx* c, const Geometry& g, int nframes, cudaStream_t st);
 // frames [f0, f0 + nframes) of the arena; all pointers address the chunk's first frame; asynchronous on st
 int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int nframes, int f0, size_t row_stride, size_t frame_stride,
