@@ -510,14 +510,30 @@ int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int F, int f0, size_t 
         c->prof_pending[slot] = true;
         c->prof_head = (slot + 1) % ORB_PROF_RING;
     }
-#define ORB_STAGE_MARK(i) do { if (ev) ORB_CUDA(cudaEventRecord(ev[i], st)); } while (0)
+    // Two independent chains follow the pyramid interior:  border -> blur  (memory-bound, no shared memory)  and
+    // FAST -> quadtree  (ALU-pipe-bound, shared-memory heavy).  With ORB_B200_OVERLAP=1 they run on two streams and
+    // meet before the orientation / descriptor kernel; measured gain on B200: none, so the default is aux == st.
+    const int which = (st == c->st_c2) ? 1 : 0;
+    cudaStream_t aux = (c->overlap && c->st_aux[which]) ? c->st_aux[which] : st;
+#define ORB_STAGE_MARK(i, s_) do { if (ev) ORB_CUDA(cudaEventRecord(ev[i], s_)); } while (0)
     ORB_CUDA(cudaMemsetAsync(d_cc, 0, sizeof(int) * (size_t)F * g.nlevels, st));
     ORB_CUDA(cudaMemsetAsync(d_tie, 0, sizeof(int) * (size_t)F * g.nlevels, st));
-    ORB_STAGE_MARK(0);
-    { int rc = orb_launch_pyramid(c, g, d_imgs, F, row_stride, frame_stride, st); if (rc != ORB_OK) return rc; }   // K1
-    ORB_STAGE_MARK(1);
-    { int rc = orb_launch_fast(c, g, d_cc, F, f0, st); if (rc != ORB_OK) return rc; }                                   // K2
-    ORB_STAGE_MARK(2);
+    ORB_STAGE_MARK(0, st);
+    { int rc = orb_launch_pyramid(c, g, d_imgs, F, row_stride, frame_stride, st); if (rc != ORB_OK) return rc; }   // K1 interior
+    ORB_STAGE_MARK(1, st);
+    if (aux != st) {
+        ORB_CUDA(cudaEventRecord(c->ev_pyr[which], st));
+        ORB_CUDA(cudaStreamWaitEvent(aux, c->ev_pyr[which], 0));
+    }
+    ORB_STAGE_MARK(6, aux);
+    { int rc = orb_launch_border(c, g, F, aux); if (rc != ORB_OK) return rc; }                                      // K1 borders
+    ORB_STAGE_MARK(7, aux);
+    { int rc = orb_launch_blur(c, g, F, aux); if (rc != ORB_OK) return rc; }                                        // K5
+    ORB_STAGE_MARK(8, aux);
+    if (aux != st) ORB_CUDA(cudaEventRecord(c->ev_blur[which], aux));
+    ORB_STAGE_MARK(9, st);
+    { int rc = orb_launch_fast(c, g, d_cc, F, f0, st); if (rc != ORB_OK) return rc; }                               // K2
+    ORB_STAGE_MARK(2, st);
     {   // K3
         const size_t smem = (size_t)g.max_node_cap * 80;
         if (F >= 8)
@@ -528,15 +544,15 @@ int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int F, int f0, size_t 
                                                                                                d_kept_count, d_tie, g);
         c->launches++;
     }
-    ORB_STAGE_MARK(3);
-    { int rc = orb_launch_blur(c, g, F, st); if (rc != ORB_OK) return rc; }                                         // K5
-    ORB_STAGE_MARK(4);
+    ORB_STAGE_MARK(3, st);
+    if (aux != st) ORB_CUDA(cudaStreamWaitEvent(st, c->ev_blur[which], 0));
+    ORB_STAGE_MARK(4, st);
     {   // K4 + K6
         orient_describe_kernel<<<dim3((g.total_kp_slots + OD_KPB - 1) / OD_KPB, F), OD_WARPS * 32, 0, st>>>(
             c->d_pyr, c->d_blur, d_kept, d_kept_count, c->d_mom_tab, d_kps, d_desc, cap, d_n_out, g);
         c->launches++;
     }
-    ORB_STAGE_MARK(5);
+    ORB_STAGE_MARK(5, st);
 #undef ORB_STAGE_MARK
     ORB_CUDA(cudaGetLastError());
     return ORB_OK;

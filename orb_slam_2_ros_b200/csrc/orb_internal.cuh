@@ -17,6 +17,7 @@
 #define ORB_XOFF 32        // byte offset of interior pixel x = 0 inside a pyramid row (border occupies [13, 32))
 #define ORB_NSTAGES 5      // pyramid, FAST cells, quadtree, blur, orientation+descriptors
 #define ORB_PROF_RING 64
+#define ORB_PROF_EVENTS 10
 #define ORB_PIPE_SLOTS 4   // chunks in flight in the host-buffer pipeline
 #define ORB_PIPE_CHUNK 64  // frames per chunk of the host-buffer pipeline
 
@@ -125,6 +126,9 @@ struct orb_ctx {
     Geometry gl;               // per-launch copy of g with the bases shifted to the chunk's first frame
     // host-API pipeline (orb_extract_batch): copy streams + per-chunk events
     cudaStream_t st_h2d = nullptr, st_d2h = nullptr, st_c2 = nullptr;
+    cudaStream_t st_aux[2] = {nullptr, nullptr};   // border -> blur chain next to FAST -> quadtree (one per compute stream)
+    cudaEvent_t ev_pyr[2] = {}, ev_blur[2] = {};
+    bool overlap = false;
     cudaEvent_t ev_in[ORB_PIPE_SLOTS] = {}, ev_done[ORB_PIPE_SLOTS] = {}, ev_out[ORB_PIPE_SLOTS] = {};
     int last_frames = 0;
     uint8_t* d_in = nullptr;  size_t in_bytes = 0;      // staging of host input frames
@@ -152,7 +156,7 @@ struct orb_ctx {
     // per-stage CUDA-event timers (orb_profile_enable / orb_profile_read): a ring of event sets so that reading
     // never stalls the stream; stage s of a call = elapsed(ev[s], ev[s+1])
     bool profile = false;
-    cudaEvent_t prof_ev[ORB_PROF_RING][ORB_NSTAGES + 1] = {};
+    cudaEvent_t prof_ev[ORB_PROF_RING][ORB_PROF_EVENTS] = {};   // main stream 0..5, [6..8] border/blur chain, [9] FAST start
     bool prof_pending[ORB_PROF_RING] = {};
     int prof_frames[ORB_PROF_RING] = {};
     int prof_head = 0;
@@ -164,6 +168,7 @@ int orb_profile_harvest(orb_ctx* c, int slot);
 // kernels' launchers (orb_extract_kernels.cu)
 int orb_launch_pyramid(orb_ctx* c, const Geometry& g, const uint8_t* d_imgs, int nframes, size_t row_stride,
                        size_t frame_stride, cudaStream_t st);
+int orb_launch_border(orb_ctx* c, const Geometry& g, int nframes, cudaStream_t st);
 int orb_launch_fast(orb_ctx* c, const Geometry& g, int* d_corner_count, int nframes, int f0, cudaStream_t st);
 int orb_launch_blur(orb_ctx* c, const Geometry& g, int nframes, cudaStream_t st);
 // frames [f0, f0 + nframes) of the arena; all pointers address the chunk's first frame; asynchronous on st

@@ -237,6 +237,11 @@ int orb_launch_pyramid(orb_ctx* c, const Geometry& g, const uint8_t* d_imgs, int
         }
         c->launches++;
     }
+    ORB_CUDA(cudaGetLastError());
+    return ORB_OK;
+}
+
+int orb_launch_border(orb_ctx* c, const Geometry& g, int F, cudaStream_t st) {
     pyr_border_kernel<<<dim3((g.border_items * 16 + g.border_copy_items + 255) / 256, F), 256, 0, st>>>(c->d_pyr, g);
     c->launches++;
     ORB_CUDA(cudaGetLastError());
