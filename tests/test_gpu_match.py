@@ -198,3 +198,62 @@ def test_stereo_matches(oracle):
     assert kept_g == kept_o
     assert np.array_equal(ur_g.view(np.uint32), ur_o.view(np.uint32))
     assert np.array_equal(dep_g.view(np.uint32), dep_o.view(np.uint32))
+
+
+def test_search_contention_chunks_and_empty(oracle, frame_pair):
+    """The sequential "already matched" walk under stress: 2600 queries (three shared-memory chunks of 1024) that all
+    project onto a few dozen targets, so most top-8 lists run dry and the full candidate lists are scanned; both
+    modes; plus empty query / target sets."""
+    from orb_slam_2_ros_b200 import ORBmatcher
+    from orb_slam_2_ros_b200.matcher import MODE_LOCAL_POINTS, MODE_TRACK_LAST
+    ka, da, kb, db, sf = frame_pair
+    rng = np.random.default_rng(17)
+    n = len(kb)
+    hot = rng.choice(n, 40, replace=False)                      # contested targets
+    nq = 2600
+    tgt = hot[rng.integers(0, len(hot), nq)]
+    q_u = (kb["x"][tgt] + rng.uniform(-2, 2, nq)).astype(np.float32)
+    q_v = (kb["y"][tgt] + rng.uniform(-2, 2, nq)).astype(np.float32)
+    q_radius = np.full(nq, 25.0, np.float32)
+    q_min, q_max = np.full(nq, -1, np.int32), np.full(nq, -1, np.int32)   # no level filter
+    q_desc = db[tgt] ^ (rng.random((nq, 32)) < 0.03).astype(np.uint8)
+    q_angle = kb["angle"][tgt].copy()
+    q_obs = (rng.random(nq) > 0.2).astype(np.uint8)
+    bounds = (0.0, 0.0, 640.0, 480.0)
+    grid = oracle.Grid(kb, *bounds)
+    for mode, omode, ratio in ((MODE_TRACK_LAST, oracle.MODE_TRACK_LAST, 0.9), (MODE_LOCAL_POINTS, oracle.MODE_LOCAL_POINTS, 0.8)):
+        t_o, t_g = np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+        nm_o, moq_o, tq_o = oracle.search_by_projection(omode, grid, db, None, t_o, q_u, q_v, q_radius, q_min, q_max, q_desc,
+                                                        q_angle=q_angle, q_obs=q_obs, th_dist=100, nn_ratio=ratio,
+                                                        check_orientation=True)
+        nm_g, moq_g, tq_g = ORBmatcher(ratio, True).SearchByProjection(mode, kb, db, bounds, t_g, q_u, q_v, q_radius, q_min, q_max,
+                                                                     q_desc, q_angle=q_angle, q_obs=q_obs, th_dist=100)
+        assert nm_o > 20
+        assert nm_g == nm_o and np.array_equal(moq_g, moq_o) and np.array_equal(tq_g, tq_o) and np.array_equal(t_g, t_o)
+    # empty sets: no queries, no targets
+    m = ORBmatcher(0.9, True)
+    nm, moq, tq = m.SearchByProjection(MODE_TRACK_LAST, kb, db, bounds, np.zeros(n, np.uint8), q_u[:0], q_v[:0], q_radius[:0],
+                                       q_min[:0], q_max[:0], q_desc[:0], q_angle=q_angle[:0])
+    assert nm == 0 and len(moq) == 0 and np.all(tq == -1)
+    nm, moq, tq = m.SearchByProjection(MODE_TRACK_LAST, kb[:0], db[:0], bounds, np.zeros(0, np.uint8), q_u[:5], q_v[:5], q_radius[:5],
+                                       q_min[:5], q_max[:5], q_desc[:5], q_angle=q_angle[:5])
+    assert nm == 0 and np.all(moq == -1)
+
+
+def test_match_bruteforce_large_and_empty(oracle):
+    """More queries than one shared-memory chunk of the resolve kernel (1024), a non-multiple-of-8 target count (row
+    pitch padding of the distance matrix), and empty sides."""
+    from orb_slam_2_ros_b200 import ORBmatcher
+    rng = np.random.default_rng(23)
+    d2 = rng.integers(0, 256, (1501, 32), dtype=np.uint8)
+    pick = rng.integers(0, len(d2), 2300)
+    d1 = d2[pick] ^ (rng.random((2300, 32)) < 0.04).astype(np.uint8)
+    a1 = rng.uniform(0, 360, len(d1)).astype(np.float32); a2 = rng.uniform(0, 360, len(d2)).astype(np.float32)
+    for ratio, ori in ((0.9, True), (0.6, False)):
+        nm_o, m_o = oracle.match_bruteforce(d1, a1, d2, a2, 80, ratio, ori)
+        nm_g, m_g = ORBmatcher(ratio, ori).MatchBruteForce(d1, a1, d2, a2, 80)
+        assert nm_o > 100 and nm_g == nm_o and np.array_equal(m_g, m_o)
+    nm, m = ORBmatcher(0.9, True).MatchBruteForce(d1[:0], a1[:0], d2, a2, 80)
+    assert nm == 0 and len(m) == 0
+    nm, m = ORBmatcher(0.9, True).MatchBruteForce(d1[:7], a1[:7], d2[:0], a2[:0], 80)
+    assert nm == 0 and np.all(m == -1)
