@@ -122,6 +122,13 @@ int orb_debug_tie_counts(orb_ctx* ctx, int frame, int32_t* ties /* [nlevels] */)
 /* brute force, host buffers: every query against db[0..ndb) */
 int orb_hamming_top2(int device, const uint8_t* q, int nq, const uint8_t* db, int64_t ndb, orb_top2* out);
 
+/* the same over explicit candidate lists: candidates of query i = cand_idx[cand_off[i] .. cand_off[i+1]) (indices into
+ * db), ties keep the first candidate in list order.  The building block for the matcher loops whose gates (epipolar
+ * line, Sim3 / reprojection window, BoW node) are evaluated by the caller: SearchForTriangulation, SearchBySim3,
+ * SearchByProjection(KeyFrame, Scw, ...) (ORBmatcher.cc:659-825, 1104-1328, 291-404). */
+int orb_hamming_top2_csr(int device, const uint8_t* q, int nq, const uint8_t* db, int64_t ndb, const int32_t* cand_off,
+                         const int32_t* cand_idx, orb_top2* out);
+
 /* device-resident database shard (config 5: map-wide relocalisation-scale search).
  * index_base = global index of the shard's first row; results carry global indices. */
 int orb_db_create(orb_db** db, int device, int64_t capacity_rows, int64_t index_base);
@@ -143,7 +150,12 @@ int orb_top2_merge(const orb_top2* parts, int nparts, int nq, orb_top2* out);
 /* ---- windowed search with the sequential "already matched" rule ------------------------------------ */
 enum {
     ORB_MODE_TRACK_LAST = 0,  /* ORBmatcher.cc:1330-1472: best only, <= th_dist, rotation histogram      */
-    ORB_MODE_LOCAL_POINTS = 1 /* ORBmatcher.cc:45-129: best/second, same-octave ratio test, no histogram */
+    ORB_MODE_LOCAL_POINTS = 1, /* ORBmatcher.cc:45-129: best/second, same-octave ratio test, no histogram */
+    ORB_MODE_INITIALIZATION = 2 /* ORBmatcher.cc:406-521 SearchForInitialization: queries = F1 keypoints (q_valid = octave 0,
+                                  q_u/q_v = vbPrevMatched, q_radius = windowSize, levels 0/0), targets = F2; a target is
+                                  re-assigned to a strictly better match and the previous owner loses it; accept
+                                  best <= th_dist && best < second * nn_ratio; rotation histogram.  match_of_query =
+                                  vnMatches12, target_query = vnMatches21; `taken` is ignored */
 };
 typedef struct {
     int32_t mode;

@@ -97,7 +97,8 @@ int orc_grid_query(void* g, float x, float y, float r, int min_level, int max_le
 /* matcher modes for orc_search_by_projection */
 enum {
     ORC_MODE_TRACK_LAST = 0,  /* ORBmatcher.cc:1330-1472  (Cur, Last, th, bMono)  best only, <= th_dist, rot-hist */
-    ORC_MODE_LOCAL_POINTS = 1 /* ORBmatcher.cc:45-129     (F, vpMapPoints, th) best/second, level ratio test */
+    ORC_MODE_LOCAL_POINTS = 1, /* ORBmatcher.cc:45-129     (F, vpMapPoints, th) best/second, level ratio test */
+    ORC_MODE_INITIALIZATION = 2 /* ORBmatcher.cc:406-521   SearchForInitialization: steal-by-better-distance, ratio, rot-hist */
 };
 
 typedef struct {

@@ -20,6 +20,7 @@ TOP2_DTYPE = np.dtype([("best_dist", "<i4"), ("best_idx", "<i4"), ("second_dist"
 
 MODE_TRACK_LAST = 0
 MODE_LOCAL_POINTS = 1
+MODE_INITIALIZATION = 2
 
 
 class SearchParams(C.Structure):

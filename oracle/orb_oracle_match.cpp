@@ -176,6 +176,47 @@ int orc_search_by_projection_ex(const orc_search_params* prm, void* grid, const 
     std::vector<int> rotHist[HISTO_LENGTH];
     std::vector<int32_t> owner(n, -1);
     std::vector<int32_t> cand;
+    if (prm->mode == ORC_MODE_INITIALIZATION) {
+        // ORBmatcher::SearchForInitialization, OM:406-521.  Queries = F1 keypoints of octave 0 (q_valid), window centre =
+        // vbPrevMatched (q_u, q_v), radius = windowSize, levels (0, 0); a target may be stolen by a strictly better
+        // match (vMatchedDistance, OM:445) and the previous owner loses it (OM:464-468).
+        std::vector<int> vMatchedDistance(n, INT_MAX);
+        for (int i = 0; i < nq; ++i) match_of_query[i] = -1;          // vnMatches12
+        for (int i1 = 0; i1 < nq; ++i1) {
+            if (q_valid && !q_valid[i1]) continue;                     // level1 > 0 (OM:423-425)
+            grid_query(g, q_u[i1], q_v[i1], q_radius[i1], q_min_level[i1], q_max_level[i1], cand);
+            if (cand.empty()) continue;
+            const uint8_t* d1 = q_desc + (size_t)i1 * 32;
+            int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+            for (int32_t i2 : cand) {
+                const int dist = descriptor_distance(d1, desc + (size_t)i2 * 32);
+                if (vMatchedDistance[i2] <= dist) continue;
+                if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+                else if (dist < bestDist2) { bestDist2 = dist; }
+            }
+            if (bestDist <= prm->th_dist) {
+                if (bestDist < (float)bestDist2 * prm->nn_ratio) {
+                    if (owner[bestIdx2] >= 0) { match_of_query[owner[bestIdx2]] = -1; nmatches--; }
+                    match_of_query[i1] = bestIdx2;
+                    owner[bestIdx2] = i1;
+                    vMatchedDistance[bestIdx2] = bestDist;
+                    nmatches++;
+                    if (prm->check_orientation) rotHist[rot_bin(q_angle[i1], kps_un[bestIdx2].angle)].push_back(i1);
+                }
+            }
+        }
+        if (prm->check_orientation) {
+            int ind1 = -1, ind2 = -1, ind3 = -1;
+            three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+            for (int b = 0; b < HISTO_LENGTH; ++b) {
+                if (b == ind1 || b == ind2 || b == ind3) continue;
+                for (int idx1 : rotHist[b])
+                    if (match_of_query[idx1] >= 0) { match_of_query[idx1] = -1; nmatches--; }
+            }
+        }
+        if (target_query) memcpy(target_query, owner.data(), (size_t)n * 4);   // vnMatches21 (not touched by the filter)
+        return nmatches;
+    }
     for (int i = 0; i < nq; ++i) {
         match_of_query[i] = -1;
         if (q_valid && !q_valid[i]) continue;

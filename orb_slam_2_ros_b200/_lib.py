@@ -34,7 +34,7 @@ EXPORTS = [
     "orb_last_error", "orb_device_count", "orb_version", "orb_create", "orb_destroy", "orb_get_tables",
     "orb_max_keypoints", "orb_extract", "orb_extract_batch", "orb_extract_batch_device", "orb_set_stream", "orb_sync",
     "orb_launch_count", "orb_profile_enable", "orb_profile_read", "orb_level_dims", "orb_pyramid_level", "orb_debug_blurred", "orb_debug_raw_corners",
-    "orb_debug_tie_counts", "orb_hamming_top2", "orb_db_create", "orb_db_destroy", "orb_db_add", "orb_db_add_device",
+    "orb_debug_tie_counts", "orb_hamming_top2", "orb_hamming_top2_csr", "orb_db_create", "orb_db_destroy", "orb_db_add", "orb_db_add_device",
     "orb_db_size", "orb_db_set_stream", "orb_db_query_top2", "orb_db_query_top2_device", "orb_db_launch_count", "orb_db_profile_enable", "orb_db_profile_read",
     "orb_top2_merge", "orb_search_by_projection", "orb_match_bruteforce", "orb_stereo_match",
 ]
@@ -72,6 +72,7 @@ def lib():
     L.orb_debug_raw_corners.argtypes = [vp, i32, i32, vp, i32, C.POINTER(i32)]
     L.orb_debug_tie_counts.argtypes = [vp, i32, vp]
     L.orb_hamming_top2.argtypes = [i32, vp, i32, vp, i64, vp]
+    L.orb_hamming_top2_csr.argtypes = [i32, vp, i32, vp, i64, vp, vp, vp]
     L.orb_db_create.argtypes = [C.POINTER(vp), i32, i64, i64]
     L.orb_db_destroy.argtypes = [vp]
     L.orb_db_destroy.restype = None

@@ -229,10 +229,16 @@ struct SrStage {
 
 __global__ void __launch_bounds__(SR_THREADS)
 window_resolve_kernel(const SearchArgs a, int mode, int th_dist, float nn_ratio, int check_ori, uint8_t* taken_g,
-                      int* match_of_query, int* target_query, signed char* match_bin, int* nmatches_out, int* overflow) {
+                      int* match_of_query, int* target_query, signed char* match_bin, int* assigned, int* nmatches_out,
+                      int* overflow) {
     extern __shared__ __align__(16) uint8_t sr_smem[];
     SrStage& S = *reinterpret_cast<SrStage*>(sr_smem);
     uint8_t* taken = sr_smem + sizeof(SrStage);   // [n]
+    // SearchForInitialization state (ORBmatcher.cc:416-417): vMatchedDistance and vnMatches21, 16 bit each
+    const int npad = (a.n + 3) & ~3;
+    unsigned short* vmd = reinterpret_cast<unsigned short*>(taken + npad);      // 0xFFFF = INT_MAX
+    unsigned short* own = vmd + npad;                                           // 0xFFFF = -1
+    const bool init = (mode == ORB_MODE_INITIALIZATION);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     __shared__ int hist[HISTO_LENGTH];
     __shared__ int s_nmatches;
@@ -242,8 +248,11 @@ window_resolve_kernel(const SearchArgs a, int mode, int th_dist, float nn_ratio,
     }
     if (threadIdx.x == 0) { *overflow = 0; s_nmatches = 0; }
     if (threadIdx.x < HISTO_LENGTH) hist[threadIdx.x] = 0;
-    for (int i = threadIdx.x; i < a.n; i += SR_THREADS) { target_query[i] = -1; taken[i] = taken_g[i]; }
-    const int need = (mode == ORB_MODE_LOCAL_POINTS) ? 2 : 1;
+    for (int i = threadIdx.x; i < a.n; i += SR_THREADS) {
+        target_query[i] = -1; taken[i] = init ? 0 : taken_g[i];
+        if (init) { vmd[i] = 0xFFFFu; own[i] = 0xFFFFu; }
+    }
+    const int need = (mode == ORB_MODE_TRACK_LAST) ? 1 : 2;
     int nmatches = 0;
     for (int q0 = 0; q0 < a.nq; q0 += SR_CH) {
         const int nb = min(SR_CH, a.nq - q0);
@@ -260,7 +269,7 @@ window_resolve_kernel(const SearchArgs a, int mode, int th_dist, float nn_ratio,
             S.id[j][k] = (unsigned short)id; S.dist[j][k] = (uint8_t)(key >> 16); S.oct[j][k] = (uint8_t)oc;
             if (k == SR_K - 1) S.flags[j] = (uint8_t)((key != 0xFFFFFFFFu ? 1 : 0) | ((!a.q_obs || a.q_obs[qi]) ? 2 : 0));
         }
-        for (int j = threadIdx.x; j < nb; j += SR_THREADS) { match_of_query[q0 + j] = -1; match_bin[q0 + j] = -1; }
+        for (int j = threadIdx.x; j < nb; j += SR_THREADS) { match_of_query[q0 + j] = -1; match_bin[q0 + j] = -1; if (init) assigned[q0 + j] = -1; }
         __syncthreads();
         // ---- sequential walk by warp 0 ----
         if (warp == 0) {
@@ -271,7 +280,8 @@ window_resolve_kernel(const SearchArgs a, int mode, int th_dist, float nn_ratio,
                 for (int k = 0; k < SR_K; ++k) {
                     const int id = S.id[j][k];
                     if (id == 0xFFFF || nfree >= need) break;
-                    if (taken[id]) continue;
+                    // unavailable: already matched (ORBmatcher.cc:87-89, 1405-1407) / matched at least as well (:445)
+                    if (init ? (vmd[id] <= S.dist[j][k]) : (taken[id] != 0)) continue;
                     if (nfree == 0) { d1 = S.dist[j][k]; i1 = id; o1 = S.oct[j][k]; } else { d2 = S.dist[j][k]; o2 = S.oct[j][k]; }
                     ++nfree;
                 }
@@ -282,11 +292,12 @@ window_resolve_kernel(const SearchArgs a, int mode, int th_dist, float nn_ratio,
                     unsigned a1 = 0xFFFFFFFFu, a2 = 0xFFFFFFFFu;
                     for (int p = lane; p < cnt; p += 32) {
                         const unsigned d = a.cand_dist[base + p];
-                        if (d < 256u && !taken[a.cand_idx[base + p]]) {
-                            const unsigned k = (d << 16) | (unsigned)p;
-                            a2 = min(a2, max(k, a1));
-                            a1 = min(a1, k);
-                        }
+                        if (d >= 256u) continue;
+                        const int id = a.cand_idx[base + p];
+                        if (init ? (vmd[id] <= d) : (taken[id] != 0)) continue;
+                        const unsigned k = (d << 16) | (unsigned)p;
+                        a2 = min(a2, max(k, a1));
+                        a1 = min(a1, k);
                     }
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) {
@@ -306,6 +317,21 @@ window_resolve_kernel(const SearchArgs a, int mode, int th_dist, float nn_ratio,
                     const int bestLevel2 = (d2 < 256) ? o2 : -1;
                     if (o1 == bestLevel2 && (float)d1 > __fmul_rn(nn_ratio, (float)d2)) continue;   // ORBmatcher.cc:120
                 }
+                if (init) {
+                    // bestDist < (float)bestDist2 * mfNNratio with bestDist2 = INT_MAX when there is no second (ORBmatcher.cc:462)
+                    if (d2 < 256 && !((float)d1 < __fmul_rn((float)d2, nn_ratio))) continue;
+                    const int prev = own[i1];
+                    if (lane == 0) {
+                        if (prev != 0xFFFF) match_of_query[prev] = -1;                              // ORBmatcher.cc:464-468
+                        match_of_query[qi] = i1;
+                        own[i1] = (unsigned short)qi;
+                        vmd[i1] = (unsigned short)d1;
+                        assigned[qi] = i1;
+                    }
+                    nmatches += (prev != 0xFFFF) ? 0 : 1;
+                    __syncwarp();
+                    continue;
+                }
                 if (lane == 0) {
                     match_of_query[qi] = i1;
                     target_query[i1] = qi;
@@ -319,6 +345,36 @@ window_resolve_kernel(const SearchArgs a, int mode, int th_dist, float nn_ratio,
     if (threadIdx.x == 0) s_nmatches = nmatches;
     __syncthreads();
     nmatches = s_nmatches;
+    if (init) {
+        for (int i = threadIdx.x; i < a.n; i += SR_THREADS) target_query[i] = own[i] == 0xFFFFu ? -1 : (int)own[i];   // vnMatches21
+        if (check_ori) {
+            // rotation histogram of every assignment made, stale ones included (ORBmatcher.cc:473-482, 488-511)
+            for (int qi = threadIdx.x; qi < a.nq; qi += SR_THREADS) {
+                const int t = assigned[qi];
+                if (t >= 0) {
+                    const int bin = rot_bin(a.q_angle[qi], a.kps[t].angle);
+                    match_bin[qi] = (signed char)bin;
+                    atomicAdd(&hist[bin], 1);
+                }
+            }
+            __syncthreads();
+            int ind1, ind2, ind3;
+            three_maxima(hist, ind1, ind2, ind3);
+            __syncthreads();
+            if (threadIdx.x == 0) s_nmatches = 0;
+            __syncthreads();
+            int removed = 0;
+            for (int qi = threadIdx.x; qi < a.nq; qi += SR_THREADS) {
+                const int bin = match_bin[qi];
+                if (bin >= 0 && bin != ind1 && bin != ind2 && bin != ind3 && match_of_query[qi] >= 0) { match_of_query[qi] = -1; removed++; }
+            }
+            atomicAdd(&s_nmatches, removed);
+            __syncthreads();
+            nmatches -= s_nmatches;
+        }
+        if (threadIdx.x == 0) *nmatches_out = nmatches;
+        return;
+    }
     for (int i = threadIdx.x; i < a.n; i += SR_THREADS) taken_g[i] = taken[i];
     if (mode == ORB_MODE_TRACK_LAST && check_ori) {
         // rotation histogram of every match made (ORBmatcher.cc:1433-1441), after the walk: its global loads are parallel
@@ -507,6 +563,40 @@ bf_resolve_kernel(const unsigned short* __restrict__ D, int dpitch, const unsign
     if (threadIdx.x == 0) *nmatches_out = nmatches;
 }
 
+// ---- best / second-best over explicit candidate lists (CSR): one warp per query ------------------------------
+// Ties keep the FIRST candidate in list order (strict '<' of ORBmatcher.cc:217-226): key = dist << 23 | position.
+__global__ void __launch_bounds__(256)
+csr_top2_kernel(const uint8_t* __restrict__ q, int nq, const uint8_t* __restrict__ db, const int* __restrict__ off,
+                const int* __restrict__ idx, orb_top2* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= nq) return;
+    const uint4* dq = reinterpret_cast<const uint4*>(q + (size_t)i * 32);
+    const int c0 = off[i], cnt = off[i + 1] - c0;
+    unsigned k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
+    for (int p = lane; p < cnt; p += 32) {
+        const int d = dist256(dq, reinterpret_cast<const uint4*>(db + (size_t)idx[c0 + p] * 32));
+        const unsigned k = ((unsigned)d << 23) | (unsigned)p;
+        k2 = min(k2, max(k, k1));
+        k1 = min(k1, k);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned b1 = __shfl_xor_sync(0xffffffffu, k1, o), b2 = __shfl_xor_sync(0xffffffffu, k2, o);
+        const unsigned lo = min(k1, b1), hi = max(k1, b1);
+        k2 = min(hi, min(k2, b2));
+        k1 = lo;
+    }
+    if (lane == 0) {
+        orb_top2 r;
+        r.best_dist = k1 == 0xFFFFFFFFu ? 256 : (int)(k1 >> 23);
+        r.best_idx = k1 == 0xFFFFFFFFu ? -1 : idx[c0 + (k1 & 0x7FFFFFu)];
+        r.second_dist = k2 == 0xFFFFFFFFu ? 256 : (int)(k2 >> 23);
+        r.second_idx = k2 == 0xFFFFFFFFu ? -1 : idx[c0 + (k2 & 0x7FFFFFu)];
+        out[i] = r;
+    }
+}
+
 // Per-thread, per-device workspace of the host-pointer entry points: one grow-only device slab, one grow-only pinned
 // slab and a private stream.  A call packs all its inputs into the pinned slab, issues ONE H2D copy, the kernels and
 // ONE D2H copy, and synchronises once — no cudaMalloc / cudaFree on the call path.
@@ -564,7 +654,9 @@ int orb_search_by_projection(int device, const orb_search_params* prm, const orb
     if (nq && (!q_u || !q_v || !q_radius || !q_min_level || !q_max_level || !q_desc || !match_of_query)) return ORB_ERR_INVALID;
     if (n && (!kps_un || !desc || !taken)) return ORB_ERR_INVALID;
     if (u_right && (!q_ur || !q_er_max)) return ORB_ERR_INVALID;
-    if (prm->mode == ORB_MODE_TRACK_LAST && prm->check_orientation && nq && !q_angle) return ORB_ERR_INVALID;
+    if (prm->mode != ORB_MODE_TRACK_LAST && prm->mode != ORB_MODE_LOCAL_POINTS && prm->mode != ORB_MODE_INITIALIZATION) return ORB_ERR_INVALID;
+    if (prm->mode != ORB_MODE_LOCAL_POINTS && prm->check_orientation && nq && !q_angle) return ORB_ERR_INVALID;
+    if (prm->mode == ORB_MODE_INITIALIZATION && nq > 65535) { orb_set_error("SearchForInitialization: more than 65535 queries"); return ORB_ERR_CAPACITY; }
     for (int i = 0; i < nq; ++i) match_of_query[i] = -1;
     if (target_query) for (int i = 0; i < n; ++i) target_query[i] = -1;
     if (n == 0 || nq == 0) return ORB_OK;
@@ -586,7 +678,7 @@ int orb_search_by_projection(int device, const orb_search_params* prm, const orb
         const size_t io_bytes = c.off;   // outputs: [o_taken .. io_bytes) is copied back (taken + results)
         const size_t o_items = c.take(4 * (size_t)npad), o_cells = c.take(4 * (GRID_COLS * GRID_ROWS + 1));
         const size_t o_cnt = c.take(4 * (size_t)nq), o_base = c.take(4 * (size_t)nq), o_bin = c.take(nq);
-        const size_t o_topk = c.take(4 * (size_t)nq * SR_K);
+        const size_t o_topk = c.take(4 * (size_t)nq * SR_K), o_asg = c.take(4 * (size_t)nq);
         const size_t o_cidx = c.take(4 * (size_t)cand_cap), o_cdist = c.take(2 * (size_t)cand_cap);
         Workspace& W = g_ws;
         int rc = W.prepare(device, c.off, io_bytes);
@@ -621,9 +713,15 @@ int orb_search_by_projection(int device, const orb_search_params* prm, const orb
         grid_build_kernel<<<1, 1024, npad * sizeof(unsigned), st>>>(a.kps, n, npad, a.min_x, a.min_y, a.inv_w, a.inv_h,
                                                                     (unsigned*)(Dv + o_items), (int*)(Dv + o_cells));
         window_candidates_kernel<<<(nq + 7) / 8, 256, 0, st>>>(a);
-        window_resolve_kernel<<<1, SR_THREADS, sizeof(SrStage) + (size_t)n, st>>>(a, prm->mode, prm->th_dist, prm->nn_ratio, prm->check_orientation,
-                                                        Dv + o_taken, (int*)(Dv + o_moq), (int*)(Dv + o_tq),
-                                                        (signed char*)(Dv + o_bin), d_scal + 1, d_scal + 2);
+        const size_t rsmem = sizeof(SrStage) + (size_t)((n + 3) & ~3) * 5;   // stage + taken[n] + vMatchedDistance[n] + vnMatches21[n]
+        static thread_local int attr_dev = -1;
+        if (attr_dev != device) {
+            ORB_CUDA(cudaFuncSetAttribute(window_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(SrStage) + GB_MAX_N * 5)));
+            attr_dev = device;
+        }
+        window_resolve_kernel<<<1, SR_THREADS, rsmem, st>>>(a, prm->mode, prm->th_dist, prm->nn_ratio, prm->check_orientation,
+                                                            Dv + o_taken, (int*)(Dv + o_moq), (int*)(Dv + o_tq),
+                                                            (signed char*)(Dv + o_bin), (int*)(Dv + o_asg), d_scal + 1, d_scal + 2);
         ORB_CUDA(cudaGetLastError());
         ORB_CUDA(cudaMemcpyAsync(H + o_taken, Dv + o_taken, io_bytes - o_taken, cudaMemcpyDeviceToHost, st));
         ORB_CUDA(cudaStreamSynchronize(st));
@@ -640,6 +738,39 @@ int orb_search_by_projection(int device, const orb_search_params* prm, const orb
         return ORB_OK;
     }
     return ORB_ERR_CAPACITY;
+}
+
+int orb_hamming_top2_csr(int device, const uint8_t* q, int nq, const uint8_t* db, int64_t ndb, const int32_t* cand_off,
+                         const int32_t* cand_idx, orb_top2* out) {
+    if (nq < 0 || ndb < 0 || (nq && (!q || !cand_off || !out))) return ORB_ERR_INVALID;
+    if (nq == 0) return ORB_OK;
+    const int64_t total = cand_off[nq];
+    if (cand_off[0] != 0 || total < 0 || (total && (!cand_idx || !db))) return ORB_ERR_INVALID;
+    for (int i = 0; i < nq; ++i) {
+        if (cand_off[i + 1] < cand_off[i]) return ORB_ERR_INVALID;
+        if (cand_off[i + 1] - cand_off[i] >= (1 << 23)) { orb_set_error("orb_hamming_top2_csr: more than 8M candidates for one query"); return ORB_ERR_CAPACITY; }
+    }
+    for (int64_t c = 0; c < total; ++c) if (cand_idx[c] < 0 || cand_idx[c] >= ndb) { orb_set_error("orb_hamming_top2_csr: candidate index out of range"); return ORB_ERR_INVALID; }
+    if (orb_device_count() <= 0) { orb_set_error("no CUDA device visible: liborb_b200 has no CPU fallback"); return ORB_ERR_NO_DEVICE; }
+    Carver c;
+    const size_t o_q = c.take((size_t)32 * nq), o_db = c.take((size_t)32 * ndb), o_off = c.take(4 * (size_t)(nq + 1)), o_idx = c.take(4 * (size_t)total);
+    const size_t in_bytes = c.off;
+    const size_t o_out = c.take(sizeof(orb_top2) * (size_t)nq);
+    Workspace& W = g_ws;
+    int rc = W.prepare(device, c.off, c.off);
+    if (rc != ORB_OK) return rc;
+    uint8_t *H = W.h, *Dv = W.d;
+    memcpy(H + o_q, q, (size_t)32 * nq);
+    if (ndb) memcpy(H + o_db, db, (size_t)32 * ndb);
+    memcpy(H + o_off, cand_off, 4 * (size_t)(nq + 1));
+    if (total) memcpy(H + o_idx, cand_idx, 4 * (size_t)total);
+    ORB_CUDA(cudaMemcpyAsync(Dv, H, in_bytes, cudaMemcpyHostToDevice, W.st));
+    csr_top2_kernel<<<(nq + 7) / 8, 256, 0, W.st>>>(Dv + o_q, nq, Dv + o_db, (const int*)(Dv + o_off), (const int*)(Dv + o_idx), (orb_top2*)(Dv + o_out));
+    ORB_CUDA(cudaGetLastError());
+    ORB_CUDA(cudaMemcpyAsync(H + o_out, Dv + o_out, sizeof(orb_top2) * (size_t)nq, cudaMemcpyDeviceToHost, W.st));
+    ORB_CUDA(cudaStreamSynchronize(W.st));
+    memcpy(out, H + o_out, sizeof(orb_top2) * (size_t)nq);
+    return ORB_OK;
 }
 
 int orb_match_bruteforce(int device, const uint8_t* desc1, const float* angle1, int n1, const uint8_t* desc2,

@@ -10,7 +10,7 @@ from ._lib import KP_DTYPE, TOP2_DTYPE, SearchParams, check, lib, ptr
 TH_HIGH = 100      # ORBmatcher.cc:37
 TH_LOW = 50        # ORBmatcher.cc:38
 HISTO_LENGTH = 30  # ORBmatcher.cc:39
-MODE_TRACK_LAST, MODE_LOCAL_POINTS = 0, 1
+MODE_TRACK_LAST, MODE_LOCAL_POINTS, MODE_INITIALIZATION = 0, 1, 2
 
 
 def _f(a): return None if a is None else np.ascontiguousarray(a, np.float32)
@@ -49,6 +49,21 @@ class ORBmatcher:
                                              C.byref(nm)))
         return nm.value, moq, tq
 
+    def SearchForInitialization(self, kps1_un, desc1, kps2_un, desc2, bounds, vbPrevMatched, windowSize=100):
+        """ORBmatcher::SearchForInitialization (ORBmatcher.cc:406-521): F1 keypoints of octave 0 search F2 in a window
+        around vbPrevMatched.  Returns (nmatches, vnMatches12[n1]) and updates vbPrevMatched (float32 [n1, 2]) in place."""
+        kps1_un = np.ascontiguousarray(kps1_un, KP_DTYPE); kps2_un = np.ascontiguousarray(kps2_un, KP_DTYPE)
+        n1 = len(kps1_un)
+        pm = np.ascontiguousarray(vbPrevMatched, np.float32)
+        zeros = np.zeros(n1, np.int32)
+        nm, m12, _m21 = self.SearchByProjection(MODE_INITIALIZATION, kps2_un, desc2, bounds, np.zeros(len(kps2_un), np.uint8),
+                                                pm[:, 0].copy(), pm[:, 1].copy(), np.full(n1, windowSize, np.float32), zeros, zeros,
+                                                desc1, q_angle=kps1_un["angle"], q_valid=(kps1_un["octave"] <= 0).astype(np.uint8),
+                                                th_dist=TH_LOW)
+        ok = m12 >= 0                                            # ORBmatcher.cc:515-518
+        vbPrevMatched[ok, 0] = kps2_un["x"][m12[ok]]; vbPrevMatched[ok, 1] = kps2_un["y"][m12[ok]]
+        return nm, m12
+
     def MatchBruteForce(self, desc1, angle1, desc2, angle2, th_dist=TH_LOW):
         """SearchByBoW inner loop (ORBmatcher.cc:196-252) over one node holding both frames' keypoints."""
         desc1, desc2, angle1, angle2 = _b(desc1), _b(desc2), _f(angle1), _f(angle2)
@@ -63,6 +78,16 @@ def hamming_top2(q, db, device=0):
     q, db = _b(q), _b(db)
     out = np.zeros(len(q), TOP2_DTYPE)
     check(lib().orb_hamming_top2(device, ptr(q), len(q), ptr(db), len(db), ptr(out)))
+    return out
+
+
+def hamming_top2_csr(q, db, cand_off, cand_idx, device=0):
+    """Best / second-best of each query over its own candidate list (CSR): candidates of query i are
+    cand_idx[cand_off[i]:cand_off[i+1]] (rows of db); ties keep the first candidate in list order."""
+    q, db = _b(q), _b(db)
+    cand_off, cand_idx = _i(cand_off), _i(cand_idx)
+    out = np.zeros(len(q), TOP2_DTYPE)
+    check(lib().orb_hamming_top2_csr(device, ptr(q), len(q), ptr(db), len(db), ptr(cand_off), ptr(cand_idx), ptr(out)))
     return out
 
 

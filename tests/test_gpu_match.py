@@ -257,3 +257,82 @@ def test_match_bruteforce_large_and_empty(oracle):
     assert nm == 0 and len(m) == 0
     nm, m = ORBmatcher(0.9, True).MatchBruteForce(d1[:7], a1[:7], d2[:0], a2[:0], 80)
     assert nm == 0 and np.all(m == -1)
+
+
+@pytest.mark.parametrize("ratio,window", [(0.9, 100), (0.6, 30)])
+def test_search_for_initialization(oracle, frame_pair, ratio, window):
+    """ORBmatcher::SearchForInitialization (ORBmatcher.cc:406-521): level-0 keypoints only, large windows, targets are
+    stolen by strictly better matches and the previous owner loses its match, ratio test, rotation histogram that
+    also counts the stale assignments."""
+    from orb_slam_2_ros_b200 import ORBmatcher
+    ka, da, kb, db, _ = frame_pair
+    bounds = (0.0, 0.0, 640.0, 480.0)
+    n1 = len(ka)
+    prev = np.stack([ka["x"], ka["y"]], 1).astype(np.float32)          # Tracking.cc: mvbPrevMatched = initial keypoints
+    grid = oracle.Grid(kb, *bounds)
+    zeros = np.zeros(n1, np.int32)
+    valid = (ka["octave"] == 0).astype(np.uint8)
+    nm_o, m12_o, m21_o = oracle.search_by_projection(oracle.MODE_INITIALIZATION, grid, db, None, np.zeros(len(kb), np.uint8),
+                                                     prev[:, 0].copy(), prev[:, 1].copy(), np.full(n1, window, np.float32), zeros,
+                                                     zeros, da, q_angle=ka["angle"], q_valid=valid, th_dist=50, nn_ratio=ratio,
+                                                     check_orientation=True)
+    prev_g = prev.copy()
+    nm_g, m12_g = ORBmatcher(ratio, True).SearchForInitialization(ka, da, kb, db, bounds, prev_g, window)
+    assert nm_o > 30, "test input produced too few matches (%d)" % nm_o
+    assert nm_g == nm_o and np.array_equal(m12_g, m12_o)
+    assert (m12_g >= 0).sum() == nm_g and np.all(ka["octave"][m12_g >= 0] == 0)
+    ok = m12_o >= 0
+    assert np.array_equal(prev_g[ok, 0], kb["x"][m12_o[ok]]) and np.array_equal(prev_g[~ok], prev[~ok])
+
+
+def test_search_for_initialization_stealing(oracle):
+    """Few targets, many near-duplicate queries: nearly every accepted match steals a target from an earlier query."""
+    from orb_slam_2_ros_b200 import ORBmatcher
+    from orb_slam_2_ros_b200._lib import KP_DTYPE
+    rng = np.random.default_rng(29)
+    n2, n1 = 60, 900
+    kb = np.zeros(n2, KP_DTYPE)
+    kb["x"] = rng.uniform(100, 540, n2).astype(np.float32); kb["y"] = rng.uniform(100, 380, n2).astype(np.float32)
+    kb["angle"] = rng.uniform(0, 360, n2).astype(np.float32); kb["octave"] = 0
+    db = rng.integers(0, 256, (n2, 32), dtype=np.uint8)
+    t = rng.integers(0, n2, n1)
+    ka = np.zeros(n1, KP_DTYPE)
+    ka["x"] = kb["x"][t] + rng.uniform(-5, 5, n1).astype(np.float32); ka["y"] = kb["y"][t] + rng.uniform(-5, 5, n1).astype(np.float32)
+    ka["angle"] = (kb["angle"][t] + rng.uniform(-3, 3, n1)).astype(np.float32) % np.float32(360)
+    ka["octave"] = (rng.random(n1) < 0.1).astype(np.int32)             # 10 % of the queries are not on level 0
+    da = db[t] ^ (rng.random((n1, 32)) < rng.uniform(0.0, 0.05, (n1, 1))).astype(np.uint8)
+    bounds = (0.0, 0.0, 640.0, 480.0)
+    prev = np.stack([ka["x"], ka["y"]], 1).astype(np.float32)
+    grid = oracle.Grid(kb, *bounds)
+    zeros = np.zeros(n1, np.int32)
+    for ori in (True, False):
+        nm_o, m12_o, _ = oracle.search_by_projection(oracle.MODE_INITIALIZATION, grid, db, None, np.zeros(n2, np.uint8), prev[:, 0].copy(),
+                                                     prev[:, 1].copy(), np.full(n1, 100, np.float32), zeros, zeros, da, q_angle=ka["angle"],
+                                                     q_valid=(ka["octave"] == 0).astype(np.uint8), th_dist=50, nn_ratio=0.9,
+                                                     check_orientation=ori)
+        nm_g, m12_g = ORBmatcher(0.9, ori).SearchForInitialization(ka, da, kb, db, bounds, prev.copy(), 100)
+        assert nm_g == nm_o and np.array_equal(m12_g, m12_o)
+        assert nm_o <= n2
+
+
+def test_hamming_top2_csr(oracle):
+    """Candidate-list (CSR) best / second: ragged lists incl. empty ones, duplicates inside a list, ties resolved by
+    list order (not by index) — the inner loop of SearchForTriangulation / SearchBySim3 style routines."""
+    from orb_slam_2_ros_b200 import hamming_top2_csr
+    rng = np.random.default_rng(31)
+    ndb, nq = 3000, 500
+    db = rng.integers(0, 256, (ndb, 32), dtype=np.uint8)
+    db[100:110] = db[100]                                              # equal descriptors => distance ties
+    q = db[rng.integers(0, ndb, nq)] ^ (rng.random((nq, 32)) < 0.05).astype(np.uint8)
+    q[3] = db[100]
+    lens = rng.integers(0, 200, nq); lens[::17] = 0; lens[5] = 1; lens[6] = 1500
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    idx = rng.integers(0, ndb, off[-1]).astype(np.int32)
+    idx[off[3]:off[3] + 6] = [109, 103, 100, 2999, 103, 0]              # ties: first in list order (109) must win
+    g = hamming_top2_csr(q, db, off, idx)
+    o = oracle.hamming_top2_csr(q, db, off, idx)
+    assert np.array_equal(g["best_dist"], o["best_dist"]) and np.array_equal(g["second_dist"], o["second_dist"])
+    assert np.array_equal(g["best_idx"], o["best_idx"]) and np.array_equal(g["second_idx"], o["second_idx"])
+    if lens[3] >= 6:
+        assert g["best_idx"][3] == 109 and g["best_dist"][3] == 0
+    assert np.all(g["best_idx"][lens == 0] == -1) and np.all(g["best_dist"][lens == 0] == 256)
