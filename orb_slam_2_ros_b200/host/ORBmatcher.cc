@@ -47,6 +47,32 @@ int ORBmatcher::SearchByProjectionLocalPoints(const TargetFrame& F, std::vector<
     return Search(ORB_MODE_LOCAL_POINTS, F, taken, q, TH_HIGH, matchOfQuery, ownerOfTarget);
 }
 
+int ORBmatcher::SearchForInitialization(const cv::KeyPoint* keys1Un, const uint8_t* desc1, int n1, const TargetFrame& F2,
+                                        std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12, int windowSize) const {
+    std::vector<float> u(n1), v(n1), radius(n1, (float)windowSize), angle(n1);
+    std::vector<int32_t> lvl(n1, 0);
+    std::vector<uint8_t> valid(n1), taken;
+    for (int i = 0; i < n1; ++i) {
+        u[i] = vbPrevMatched[i].x; v[i] = vbPrevMatched[i].y; angle[i] = keys1Un[i].angle;
+        valid[i] = keys1Un[i].octave <= 0;                        // level1 > 0: continue (ORBmatcher.cc:423-425)
+    }
+    Queries q{n1, u.data(), v.data(), radius.data(), lvl.data(), lvl.data(), desc1, nullptr, nullptr, angle.data(), valid.data(), nullptr};
+    std::vector<int32_t> m12, m21;
+    const int nmatches = Search(ORB_MODE_INITIALIZATION, F2, taken, q, TH_LOW, m12, m21);
+    vnMatches12.assign(m12.begin(), m12.end());
+    for (int i = 0; i < n1; ++i)
+        if (vnMatches12[i] >= 0) vbPrevMatched[i] = F2.keysUn[vnMatches12[i]].pt;   // ORBmatcher.cc:515-518
+    return nmatches;
+}
+
+void ORBmatcher::BestTwoOverCandidates(const uint8_t* desc1, int n1, const uint8_t* desc2, int n2, const std::vector<int32_t>& candOff,
+                                       const std::vector<int32_t>& candIdx, std::vector<Best2>& out) const {
+    static_assert(sizeof(Best2) == sizeof(orb_top2), "Best2 mirrors orb_top2");
+    out.resize(n1);
+    check(orb_hamming_top2_csr(device_, desc1, n1, desc2, n2, candOff.data(), candIdx.data(), reinterpret_cast<orb_top2*>(out.data())),
+          "orb_hamming_top2_csr");
+}
+
 int ORBmatcher::MatchNode(const uint8_t* desc1, const float* angle1, int n1, const uint8_t* desc2, const float* angle2, int n2,
                           int thDist, std::vector<int32_t>& match12) const {
     match12.assign(n1, -1);

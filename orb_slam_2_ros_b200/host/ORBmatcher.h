@@ -33,6 +33,15 @@ public:
     // SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, th)           ORBmatcher.cc:45-129
     int SearchByProjectionLocalPoints(const TargetFrame& F, std::vector<uint8_t>& taken, const Queries& q,
                                       std::vector<int32_t>& matchOfQuery, std::vector<int32_t>& ownerOfTarget) const;
+    // SearchForInitialization(Frame &F1, Frame &F2, vbPrevMatched, vnMatches12, windowSize)    ORBmatcher.cc:406-521
+    // keys1Un / desc1 = F1, F = F2; vbPrevMatched is updated from the matches like the reference does (:515-518)
+    int SearchForInitialization(const cv::KeyPoint* keys1Un, const uint8_t* desc1, int n1, const TargetFrame& F2,
+                                std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12, int windowSize = 10) const;
+    // best / second-best over explicit candidate lists (the gated loops of SearchForTriangulation / SearchBySim3):
+    // candidates of query i = candIdx[candOff[i] .. candOff[i+1]) into desc2; returns (bestDist, bestIdx, secondDist) triples
+    struct Best2 { int bestDist, secondDist; long long bestIdx, secondIdx; };
+    void BestTwoOverCandidates(const uint8_t* desc1, int n1, const uint8_t* desc2, int n2, const std::vector<int32_t>& candOff,
+                               const std::vector<int32_t>& candIdx, std::vector<Best2>& out) const;
     // inner loop of SearchByBoW over one vocabulary node (ORBmatcher.cc:196-252)
     int MatchNode(const uint8_t* desc1, const float* angle1, int n1, const uint8_t* desc2, const float* angle2, int n2, int thDist,
                   std::vector<int32_t>& match12) const;
