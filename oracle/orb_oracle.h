@@ -13,7 +13,9 @@
  *   (ii)  DistributeOctTree equal-size tie-break = (size, creation sequence) instead of the
  *         reference's allocator-dependent (size, heap pointer)  (ORBextractor.cc:615,705-708).
  *   (iii) descriptor steering uses a=(float)cos((double)angle), b=(float)sin((double)angle).
- * The reference ships no tests / golden vectors for this path, so pin (i) is against the third-party
+ * PARITY UNPINNED BY THE REFERENCE'S OWN TESTS: the reference ships no tests / golden vectors / fixtures for this path
+ *  and its translation units cannot be compiled here (no OpenCV C++ headers), so there is no oracle/_ref.
+ * Pin (i) is against the third-party
  * module that owns the arithmetic (OpenCV), and (ii),(iii) are stated choices.
  */
 #ifndef ORB_ORACLE_H

@@ -147,8 +147,11 @@ int build_geometry(orb_ctx* c, int w, int h) {
         L.border_base = border_items;
         border_items += L.h + 2 * ORB_EDGE;
         L.copy_base = copy_items;
-        L.inv_wpr = 0xFFFFFFFFu / (unsigned)std::max(L.w >> 2, 1) + 1u;
-        copy_items += 2 * ORB_EDGE * (L.w >> 2);
+        {   // top/bottom row copies: 16-byte vectors + trailing whole words per row
+            const int per_row = (L.w >> 4) + ((L.w >> 2) - 4 * (L.w >> 4));
+            L.inv_wpr = 0xFFFFFFFFu / (unsigned)std::max(per_row, 1) + 1u;
+            copy_items += 2 * ORB_EDGE * per_row;
+        }
         // blur: one thread = one output word x ORB_BLUR_ROWS rows
         L.blur_wpr = (L.w + 3) / 4;
         L.blur_base = blur_items; blur_items += L.blur_wpr * ((L.h + ORB_BLUR_ROWS - 1) / ORB_BLUR_ROWS);

@@ -150,9 +150,9 @@ pyr_resize_generic_kernel(uint8_t* __restrict__ pyr, const ResizeTap* __restrict
 
 // ---- the 19-px BORDER_REFLECT_101 frame of every level, one launch ---------------------------------------
 // Two kinds of work items, one thread each:
-//   side  : (bordered row, slot) — slots 0..4 are the 5 left border words (bytes 12..31), slots 5..15 the right
-//           border words (the first may straddle interior | border); bytes come from the reflected interior row
-//   copy  : (top/bottom bordered row, interior word) — a plain aligned word copy of the reflected interior row
+//   side  : one bordered row — its 5 left border words (bytes 12..31) and its right border words (the first may
+//           straddle interior | border), each a byte-reversed unaligned window of the reflected interior row
+//   copy  : 16 bytes (or one trailing word) of a top/bottom bordered row — a plain aligned copy of the reflected row
 // A single reflection suffices (19 < w, h: smaller levels are rejected at geometry build time because the
 // reference's 30-px cell grid does not exist there either).
 __device__ __forceinline__ int reflect1(int i, int n) {
@@ -164,46 +164,54 @@ __global__ void __launch_bounds__(256)
 pyr_border_kernel(uint8_t* __restrict__ pyr, const __grid_constant__ Geometry g) {
     const int item = blockIdx.x * blockDim.x + threadIdx.x;
     const int f = blockIdx.y;
-    const int side_items = g.border_items * 16;
-    if (item < side_items) {
-        const int job = item >> 4, slot = item & 15;
+    if (item < g.border_items) {
         int l = 0;
-        while (l + 1 < g.nlevels && job >= g.lv[l + 1].border_base) ++l;
+        while (l + 1 < g.nlevels && item >= g.lv[l + 1].border_base) ++l;
         const LevelGeom& L = g.lv[l];
-        const int row = job - L.border_base;                                   // 0 .. h + 37
-        const int first_w = (ORB_XOFF - ORB_EDGE) / 4, nleft = ORB_XOFF / 4 - first_w;
-        const int word = slot < nleft ? first_w + slot : (ORB_XOFF + L.w) / 4 + (slot - nleft);
-        if (word >= first_w + L.border_words) return;
+        const int row = item - L.border_base;                                  // 0 .. h + 37
         uint8_t* img = pyr + L.base + (long long)f * L.frame_stride;
         const uint8_t* srow = img + L.ioff + reflect1(row - ORB_EDGE, L.h) * L.pitch;
         const unsigned* sw = reinterpret_cast<const unsigned*>(srow);
-        const int x0 = 4 * word - ORB_XOFF;                                    // interior x of the word's first byte
-        unsigned v;
-        if (x0 + 3 < 0 || x0 >= L.w) {
-            // 4 mirrored bytes = a byte-reversed unaligned window of the interior row (gfedcb|abcdefgh|gfedcba)
-            const int s0 = x0 < 0 ? -x0 - 3 : 2 * L.w - 5 - x0;               // window [s0, s0+3], s0 >= 1
-            const unsigned win = __funnelshift_r(sw[s0 >> 2], sw[(s0 >> 2) + 1], (s0 & 3) * 8);
-            v = __byte_perm(win, 0u, 0x0123);                                  // (dead bytes beyond the 19-px frame: don't care)
-        } else {
-            // the one word that straddles interior | right border
-            v = 0;
+        unsigned* drow = reinterpret_cast<unsigned*>(img + row * L.pitch);
+        // left: border word k (bytes x0 .. x0+3, x0 = -20 + 4k) = reversed interior window [-x0-3, -x0] = bytes 1..4 of
+        // the word pair (4-k, 5-k): gfedcb|abcdefgh.  (Byte 12 of the row is a dead byte.)
+        unsigned prev = sw[5];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) v |= (unsigned)srow[reflect1(x0 + k, L.w)] << (8 * k);
+        for (int k = 0; k < 5; ++k) {
+            const unsigned cur = sw[4 - k];
+            drow[(ORB_XOFF - ORB_EDGE) / 4 + k] = __byte_perm(__funnelshift_r(cur, prev, 8), 0u, 0x0123);
+            prev = cur;
         }
-        reinterpret_cast<unsigned*>(img + row * L.pitch)[word] = v;
+        // right: words from the one holding interior byte w (may straddle) to the end of the 19-px frame
+        const int first = (ORB_XOFF + L.w) >> 2, end = (ORB_XOFF - ORB_EDGE) / 4 + L.border_words;
+        for (int word = first; word < end; ++word) {
+            const int x0 = 4 * word - ORB_XOFF;
+            unsigned v;
+            if (x0 >= L.w) {
+                const int s0 = 2 * L.w - 5 - x0;                               // mirrored window [s0, s0+3]
+                v = __byte_perm(__funnelshift_r(sw[s0 >> 2], sw[(s0 >> 2) + 1], (s0 & 3) * 8), 0u, 0x0123);
+            } else {
+                v = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v |= (unsigned)srow[reflect1(x0 + k, L.w)] << (8 * k);
+            }
+            drow[word] = v;
+        }
     } else {
-        int it = item - side_items;
+        int it = item - g.border_items;
         if (it >= g.border_copy_items) return;
         int l = 0;
         while (l + 1 < g.nlevels && it >= g.lv[l + 1].copy_base) ++l;
         const LevelGeom& L = g.lv[l];
         it -= L.copy_base;
-        const int wpr = L.w >> 2;                                              // whole interior words (a partial last word is a side item)
-        const int r = (int)__umulhi((unsigned)it, L.inv_wpr), wd = it - r * wpr;
+        const int nvec = L.w >> 4, nrem = (L.w >> 2) - 4 * nvec, per_row = nvec + nrem;   // 16-byte vectors + trailing words
+        const int r = (int)__umulhi((unsigned)it, L.inv_wpr), u = it - r * per_row;
         const int row = r < ORB_EDGE ? r : L.h + r;                            // r in [19, 38) -> rows h+19 .. h+37
         uint8_t* img = pyr + L.base + (long long)f * L.frame_stride;
-        const unsigned* srow = reinterpret_cast<const unsigned*>(img + L.ioff + reflect1(row - ORB_EDGE, L.h) * L.pitch);
-        reinterpret_cast<unsigned*>(img + row * L.pitch + ORB_XOFF)[wd] = srow[wd];
+        const uint8_t* srow = img + L.ioff + reflect1(row - ORB_EDGE, L.h) * L.pitch;
+        uint8_t* drow = img + row * L.pitch + ORB_XOFF;
+        if (u < nvec) reinterpret_cast<uint4*>(drow)[u] = reinterpret_cast<const uint4*>(srow)[u];
+        else reinterpret_cast<unsigned*>(drow)[4 * nvec + (u - nvec)] = reinterpret_cast<const unsigned*>(srow)[4 * nvec + (u - nvec)];
     }
 }
 
@@ -242,7 +250,7 @@ int orb_launch_pyramid(orb_ctx* c, const Geometry& g, const uint8_t* d_imgs, int
 }
 
 int orb_launch_border(orb_ctx* c, const Geometry& g, int F, cudaStream_t st) {
-    pyr_border_kernel<<<dim3((g.border_items * 16 + g.border_copy_items + 255) / 256, F), 256, 0, st>>>(c->d_pyr, g);
+    pyr_border_kernel<<<dim3((g.border_items + g.border_copy_items + 255) / 256, F), 256, 0, st>>>(c->d_pyr, g);
     c->launches++;
     ORB_CUDA(cudaGetLastError());
     return ORB_OK;
