@@ -217,14 +217,22 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
         const int wtotal = __shfl_sync(0xffffffffu, incl, 31);
         unsigned short* seg = cand + warp * FS_WCAP;
         if (wtotal <= FS_WCAP) {
+            // every lane walks its iterations (uniform trip count, no divergence) and stores the 0-4 candidates of each
+            // word with predicated writes; o = running position in the warp's segment
             int o = incl - cnt;
-            while (cmask) {
-                const int bit = __ffsll((long long)cmask) - 1;
-                cmask &= cmask - 1ull;
-                const int k = threadIdx.x + (bit >> 2) * FS_THREADS;
+            int it2 = 0;
+            for (int k = threadIdx.x; k < total; k += FS_THREADS, ++it2) {
+                const unsigned m = (unsigned)(cmask >> (4 * it2)) & 15u;
                 const int r = (int)__umulhi((unsigned)k, inv_nw);
-                const int wd = wlo + (k - r * nw);
-                seg[o++] = (unsigned short)(r * FS_PITCH + (wd << 2) + (bit & 3));
+                const int code = r * FS_PITCH + ((wlo + (k - r * nw)) << 2);
+                if (m & 1u) seg[o] = (unsigned short)code;
+                o += m & 1u;
+                if (m & 2u) seg[o] = (unsigned short)(code + 1);
+                o += (m >> 1) & 1u;
+                if (m & 4u) seg[o] = (unsigned short)(code + 2);
+                o += (m >> 2) & 1u;
+                if (m & 8u) seg[o] = (unsigned short)(code + 3);
+                o += (m >> 3) & 1u;
             }
             __syncwarp();
             // 1b: exact score of the warp's candidates
