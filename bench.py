@@ -395,6 +395,8 @@ def main():
         d_q = torch.from_numpy(q_np).to(dev)
         d_top = torch.zeros((NQ, TOP2_DTYPE.itemsize), dtype=torch.uint8, device=dev)
         gathered = torch.zeros((world, NQ, TOP2_DTYPE.itemsize), dtype=torch.uint8, device=dev) if world > 1 else None
+        d_merged = torch.zeros((NQ, TOP2_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+        from orb_slam_2_ros_b200 import top2_merge_device
         db.set_stream(stream.cuda_stream)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
@@ -402,6 +404,7 @@ def main():
             db.query_top2_device(d_q.data_ptr(), NQ, d_top.data_ptr())
             if world > 1:
                 dist.all_gather_into_tensor(gathered, d_top)   # 2000 x 24 B per rank over NCCL / NVLink
+                top2_merge_device(gathered.data_ptr(), world, NQ, d_merged.data_ptr(), local_rank, stream.cuda_stream)
 
         for _ in range(args.warmup):
             step_hamming()
@@ -427,6 +430,9 @@ def main():
         parts = gathered.cpu().numpy().view(TOP2_DTYPE).reshape(world, NQ) if world > 1 else \
             d_top.cpu().numpy().view(TOP2_DTYPE).reshape(1, NQ)
         merged = top2_merge(parts)
+        if world > 1:   # the device-side merge of the timed step must equal the host merge
+            dm = d_merged.cpu().numpy().view(TOP2_DTYPE).reshape(NQ)
+            assert all(np.array_equal(dm[f], merged[f]) for f in ("best_dist", "second_dist", "best_idx", "second_idx")), "device merge != host merge"
         ok = int((merged["best_idx"][planted >= 0] == planted[planted >= 0]).sum())
         import ctypes
         issue = ctypes.c_double(0)
@@ -442,7 +448,7 @@ def main():
         ham = {
             "metric": "Hamming compares/s", "value": NQ * rows_total * hsteps / (tot * 1e-3), "unit": "compares/s",
             "scaling": "strong", "steps": hsteps, "ms_per_step": tot / hsteps,
-            "config": {"workload": "%d queries x %d-row descriptor DB sharded over %d GPU(s), top-2 + all-gather merge"
+            "config": {"workload": "%d queries x %d-row descriptor DB sharded over %d GPU(s), top-2 + NCCL all-gather + device merge"
                                    % (NQ, rows_total, world), "l2": "flushed between timed iterations"},
             "planted_top1_found": "%d/%d" % (ok, int((planted >= 0).sum())),
             "roofline": {"bound": "int-issue (LOP3 + POPC pipes)", "achieved": kern_cps / 1e9, "peak": peak_cmp / 1e9, "unit": "Gcompare/s",

@@ -146,6 +146,8 @@ int orb_db_profile_read(orb_db* db, double* search_ms, double* merge_ms, int64_t
 /* exact merge of per-shard results (after an all-gather): parts is [nparts][nq]; best = min distance,
  * lowest global index on ties; second = second smallest of the union. */
 int orb_top2_merge(const orb_top2* parts, int nparts, int nq, orb_top2* out);
+/* the same on the device, asynchronous on cuda_stream: the step after ncclAllGather of the per-shard results */
+int orb_top2_merge_device(int device, const orb_top2* d_parts, int nparts, int nq, orb_top2* d_out, void* cuda_stream);
 
 /* ---- windowed search with the sequential "already matched" rule ------------------------------------ */
 enum {

@@ -36,7 +36,7 @@ EXPORTS = [
     "orb_launch_count", "orb_profile_enable", "orb_profile_read", "orb_level_dims", "orb_pyramid_level", "orb_debug_blurred", "orb_debug_raw_corners",
     "orb_debug_tie_counts", "orb_hamming_top2", "orb_hamming_top2_csr", "orb_db_create", "orb_db_destroy", "orb_db_add", "orb_db_add_device",
     "orb_db_size", "orb_db_set_stream", "orb_db_query_top2", "orb_db_query_top2_device", "orb_db_launch_count", "orb_db_profile_enable", "orb_db_profile_read",
-    "orb_top2_merge", "orb_search_by_projection", "orb_match_bruteforce", "orb_stereo_match",
+    "orb_top2_merge", "orb_top2_merge_device", "orb_search_by_projection", "orb_match_bruteforce", "orb_stereo_match",
 ]
 
 _lib = None
@@ -88,6 +88,7 @@ def lib():
     L.orb_db_profile_enable.argtypes = [vp, i32]
     L.orb_db_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64), i32]
     L.orb_top2_merge.argtypes = [vp, i32, i32, vp]
+    L.orb_top2_merge_device.argtypes = [i32, vp, i32, i32, vp, vp]
     L.orb_search_by_projection.argtypes = [i32, C.POINTER(SearchParams), vp, vp, vp, i32, vp, i32] + [vp] * 13 + [C.POINTER(i32)]
     L.orb_match_bruteforce.argtypes = [i32, vp, vp, i32, vp, vp, i32, i32, f32, i32, vp, C.POINTER(i32)]
     L.orb_stereo_match.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, f32, f32, vp, vp, C.POINTER(i32)]

@@ -146,6 +146,31 @@ __global__ void hamming_merge_kernel(const uint2* __restrict__ partial, int nspl
     out[qi] = o;
 }
 
+// exact merge of per-shard results on the device (after the all-gather): parts[nparts][nq] hold global indices;
+// lexicographic (dist, index) top-2 of the union, shards in any order
+__global__ void top2_merge_kernel(const orb_top2* __restrict__ parts, int nparts, int nq, orb_top2* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    int d1 = 256, d2 = 256;
+    long long i1 = 0x7FFFFFFFFFFFFFFFll, i2 = 0x7FFFFFFFFFFFFFFFll;   // max = absent
+    for (int s = 0; s < nparts; ++s) {
+        const orb_top2 p = parts[(size_t)s * nq + i];
+        const int ds[2] = {p.best_dist, p.second_dist};
+        const long long is[2] = {p.best_idx, p.second_idx};
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (is[k] < 0) continue;
+            if (ds[k] < d1 || (ds[k] == d1 && is[k] < i1)) { d2 = d1; i2 = i1; d1 = ds[k]; i1 = is[k]; }
+            else if (ds[k] < d2 || (ds[k] == d2 && is[k] < i2)) { d2 = ds[k]; i2 = is[k]; }
+        }
+    }
+    orb_top2 o;
+    o.best_dist = d1; o.second_dist = d2;
+    o.best_idx = i1 == 0x7FFFFFFFFFFFFFFFll ? -1 : i1;
+    o.second_idx = i2 == 0x7FFFFFFFFFFFFFFFll ? -1 : i2;
+    out[i] = o;
+}
+
 // ---- register-only issue-rate microbenchmarks: the denominators of the popc roofline -------------------
 __global__ void popc_peak_kernel(unsigned* out, int iters, unsigned seed) {
     unsigned a0 = seed + threadIdx.x, a1 = a0 * 3u, a2 = a0 * 5u, a3 = a0 * 7u;
@@ -396,6 +421,16 @@ int orb_hamming_top2(int device, const uint8_t* q, int nq, const uint8_t* dbrows
     if (rc == ORB_OK) rc = orb_db_query_top2(db, q, nq, out);
     orb_db_destroy(db);
     return rc;
+}
+
+int orb_top2_merge_device(int device, const orb_top2* d_parts, int nparts, int nq, orb_top2* d_out, void* cuda_stream) {
+    if (!d_parts || !d_out || nparts <= 0 || nq < 0) return ORB_ERR_INVALID;
+    if (nq == 0) return ORB_OK;
+    if (orb_device_count() <= 0) { orb_set_error("no CUDA device visible"); return ORB_ERR_NO_DEVICE; }
+    ORB_CUDA(cudaSetDevice(device));
+    top2_merge_kernel<<<(nq + 127) / 128, 128, 0, (cudaStream_t)cuda_stream>>>(d_parts, nparts, nq, d_out);
+    ORB_CUDA(cudaGetLastError());
+    return ORB_OK;
 }
 
 int orb_top2_merge(const orb_top2* parts, int nparts, int nq, orb_top2* out) {

@@ -100,6 +100,11 @@ def top2_merge(parts):
     return out
 
 
+def top2_merge_device(d_parts, nparts, nq, d_out, device=0, stream=0):
+    """Device-side merge (raw device pointers, asynchronous on `stream`): d_parts = TOP2_DTYPE[nparts][nq]."""
+    check(lib().orb_top2_merge_device(device, C.c_void_p(d_parts), nparts, nq, C.c_void_p(d_out), C.c_void_p(stream)))
+
+
 class DescriptorDB:
     """One device-resident shard of a descriptor database (BASELINE config 5)."""
 

@@ -189,3 +189,24 @@ def test_sincos_pin_sampled(oracle):
         oa, ob = oracle.sincos_range(s, n)
         assert np.array_equal(a.view(np.uint32), oa.view(np.uint32)), "cos mismatch in range %x" % s
         assert np.array_equal(b.view(np.uint32), ob.view(np.uint32)), "sin mismatch in range %x" % s
+
+
+def test_config4_shape_large_batch_properties(oracle, ORB):
+    """BASELINE config 4 shape (752x480 EuRoC frames, nFeatures=1000) at a batch that spans several pipeline chunks:
+    sampled frames equal the oracle, duplicated frames give identical results wherever they sit in the batch, counts stay
+    within the reference's N .. N + 3 per level bound, and descriptors of a frame never depend on its neighbours."""
+    w, h, n = 752, 480, 200
+    base = [synth.synth_frame(500 + i, w, h) for i in range(4)]
+    idx = np.random.default_rng(1).integers(0, 4, n)
+    idx[:4] = [0, 1, 2, 3]
+    imgs = np.stack([base[i] for i in idx])
+    ex = ORB(1000, max_batch=128)                          # 200 frames through a 128-frame arena: 64 + 64, then 64 + 8
+    res = ex.extract_batch(imgs)
+    oex = oracle.Extractor(1000)
+    want = [oex.extract(b) for b in base]
+    for f in range(n):
+        k, d = res[f]
+        ok, od = want[idx[f]]
+        assert len(k) == len(ok) and 1000 <= len(k) <= 1000 + 3 * 8, "frame %d: %d keypoints" % (f, len(k))
+        assert np.array_equal(np.ascontiguousarray(k).view(np.uint8), np.ascontiguousarray(ok).view(np.uint8)), "frame %d" % f
+        assert np.array_equal(d, od), "frame %d" % f

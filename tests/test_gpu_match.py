@@ -336,3 +336,34 @@ def test_hamming_top2_csr(oracle):
     if lens[3] >= 6:
         assert g["best_idx"][3] == 109 and g["best_dist"][3] == 0
     assert np.all(g["best_idx"][lens == 0] == -1) and np.all(g["best_dist"][lens == 0] == 256)
+
+
+def test_top2_merge_device_equals_host(oracle):
+    """orb_top2_merge_device (the kernel that follows the NCCL all-gather in bench.py) against the host merge and the
+    single-database oracle, incl. ties on equal distance across shards and empty shards."""
+    import torch
+    from orb_slam_2_ros_b200 import DescriptorDB, top2_merge, top2_merge_device
+    from orb_slam_2_ros_b200._lib import TOP2_DTYPE
+    total, nq = 12000, 300
+    db = synth.synth_descriptors(5, 0, total)
+    db[7000] = db[10]; db[11999] = db[10]                       # duplicates across shards: lowest global index wins
+    q, _, _ = synth.synth_queries(5, total, nq)
+    q[0] = db[10]
+    cuts = [0, 4000, 4000, 9000, total]                         # one empty shard
+    parts = []
+    for s in range(4):
+        sh = DescriptorDB(max(cuts[s + 1] - cuts[s], 1), index_base=cuts[s])
+        sh.add(db[cuts[s]:cuts[s + 1]])
+        parts.append(sh.query_top2(q))
+        sh.close()
+    parts = np.stack(parts)
+    host = top2_merge(parts)
+    d_parts = torch.from_numpy(parts.view(np.uint8).reshape(4, nq, TOP2_DTYPE.itemsize).copy()).cuda()
+    d_out = torch.zeros((nq, TOP2_DTYPE.itemsize), dtype=torch.uint8, device="cuda")
+    top2_merge_device(d_parts.data_ptr(), 4, nq, d_out.data_ptr(), 0, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    dev = d_out.cpu().numpy().view(TOP2_DTYPE).reshape(nq)
+    for f in ("best_dist", "second_dist", "best_idx", "second_idx"):
+        assert np.array_equal(dev[f], host[f]), f
+    _same_top2(dev, oracle.hamming_top2(q, db))
+    assert dev["best_idx"][0] == 10 and dev["second_idx"][0] == 7000
