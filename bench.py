@@ -459,7 +459,7 @@ def main():
                          "frac_vs_popc8_roofline": kern_cps / popc8_peak if popc8_peak else None,
                          "register_only_popc8_compare_per_s": cmp8_rate, "register_only_compare_per_s": cmp_rate,
                          "kernel": "hamming_top2_kernel", "avg_launch_ms": s_ms / max(calls, 1)},
-            "gpu_launches": int(hl),
+            "gpu_launches": int(hl) + (hsteps if world > 1 else 0),   # search + split-merge kernels (+ the cross-shard merge)
         }
 
     sampler.join(timeout=2.0)
