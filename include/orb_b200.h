@@ -90,6 +90,17 @@ int orb_extract_batch(orb_ctx* ctx, const uint8_t* imgs, int nframes, int w, int
  * GPU-resident caller (and bench.py's device-resident leg) uses.  nframes <= max_batch. */
 int orb_extract_batch_device(orb_ctx* ctx, const uint8_t* d_imgs, int nframes, int w, int h, size_t row_stride,
                              size_t frame_stride, orb_kp* d_kps, uint8_t* d_desc32, int cap, int32_t* d_n_out);
+/* Colour input: Tracking::GrabImage* converts the camera image with cvtColor(.., CV_RGB2GRAY /
+ * CV_BGR2GRAY / CV_RGBA2GRAY / CV_BGRA2GRAY) before the extractor sees it (Tracking.cc:181-204, 223-234, 253-264).  These
+ * entry points take the interleaved 8-bit colour image and fuse that conversion into the level-0 pyramid copy
+ * (OpenCV 4.13.0 arithmetic: (B*3735 + G*19235 + R*9798 + 16384) >> 15).  row_stride / frame_stride are in bytes. */
+enum { ORB_PIX_GRAY8 = 0, ORB_PIX_BGR8 = 1, ORB_PIX_RGB8 = 2, ORB_PIX_BGRA8 = 3, ORB_PIX_RGBA8 = 4 };
+int orb_extract_batch_pix(orb_ctx* ctx, const uint8_t* imgs, int pixel_format, int nframes, int w, int h, size_t row_stride,
+                          size_t frame_stride, orb_kp* kps, uint8_t* desc32, int cap, int32_t* n_out);
+int orb_extract_batch_device_pix(orb_ctx* ctx, const uint8_t* d_imgs, int pixel_format, int nframes, int w, int h,
+                                 size_t row_stride, size_t frame_stride, orb_kp* d_kps, uint8_t* d_desc32, int cap,
+                                 int32_t* d_n_out);
+
 /* stream plumbing: adopt an external cudaStream_t (e.g. torch's current stream) / wait for the context */
 int orb_set_stream(orb_ctx* ctx, void* cuda_stream);
 int orb_sync(orb_ctx* ctx);

@@ -73,6 +73,8 @@ void orc_border_reflect101(const uint8_t* src, int w, int h, int sstride, uint8_
                            int dstride);
 int orc_fast9_16(const uint8_t* img, int w, int h, int stride, int threshold, int nms, orc_kp* out, int cap);
 void orc_gaussian7x7_s2(const uint8_t* src, int w, int h, int sstride, uint8_t* dst, int dstride);
+/* cvtColor(.., *2GRAY) on 8-bit interleaved BGR / RGB / BGRA / RGBA (channels = 3 | 4, rgb_order = red first) */
+void orc_cvt_gray(const uint8_t* src, int w, int h, int stride, int channels, int rgb_order, uint8_t* dst, int dstride);
 float orc_fast_atan2(float y, float x);
 int orc_cv_round_f(float v);
 float orc_ic_angle(const uint8_t* center, int stride);

@@ -69,6 +69,7 @@ def lib():
         L.orc_border_reflect101.argtypes = [vp, i32, i32, i32, vp, i32, i32]
         L.orc_fast9_16.argtypes = [vp, i32, i32, i32, i32, i32, vp, i32]
         L.orc_gaussian7x7_s2.argtypes = [vp, i32, i32, i32, vp, i32]
+        L.orc_cvt_gray.argtypes = [vp, i32, i32, i32, i32, i32, vp, i32]
         L.orc_fast_atan2.restype = f32
         L.orc_fast_atan2.argtypes = [f32, f32]
         L.orc_cv_round_f.argtypes = [f32]
@@ -202,6 +203,15 @@ def gaussian_blur(src):
     h, w = src.shape
     dst = np.zeros((h, w), np.uint8)
     lib().orc_gaussian7x7_s2(_p(src), w, h, src.strides[0], _p(dst), w)
+    return dst
+
+
+def cvt_gray(img, rgb=False):
+    """cvtColor(img, BGR2GRAY / RGB2GRAY / BGRA2GRAY / RGBA2GRAY) with OpenCV 4.13.0 arithmetic; img: uint8 (h, w, 3|4)."""
+    img = _u8(img)
+    h, w, ch = img.shape
+    dst = np.zeros((h, w), np.uint8)
+    lib().orc_cvt_gray(_p(img), w, h, img.strides[0], ch, int(rgb), _p(dst), w)
     return dst
 
 

@@ -698,4 +698,18 @@ int orc__nlevels(void* p) { return ((Extractor*)p)->nlevels; }
 float orc__scale(void* p, int l) { return ((Extractor*)p)->scale[l]; }
 float orc__inv_scale(void* p, int l) { return ((Extractor*)p)->inv_scale[l]; }
 
+/* cvtColor(src, dst, CV_BGR2GRAY / CV_RGB2GRAY / CV_BGRA2GRAY / CV_RGBA2GRAY) on CV_8U, the conversion Tracking::GrabImage*
+ * applies before the extractor (Tracking.cc:181-204, 223-234, 253-264).  OpenCV 4.13.0 arithmetic (checked against the cv2
+ * wheel by tests/test_oracle_vs_cv2.py): gray = (B*3735 + G*19235 + R*9798 + (1 << 14)) >> 15. */
+void orc_cvt_gray(const uint8_t* src, int w, int h, int stride, int channels, int rgb_order, uint8_t* dst, int dstride) {
+    for (int y = 0; y < h; ++y) {
+        const uint8_t* s = src + (size_t)y * stride;
+        uint8_t* d = dst + (size_t)y * dstride;
+        for (int x = 0; x < w; ++x, s += channels) {
+            const int b = rgb_order ? s[2] : s[0], g = s[1], r = rgb_order ? s[0] : s[2];
+            d[x] = (uint8_t)((b * 3735 + g * 19235 + r * 9798 + (1 << 14)) >> 15);
+        }
+    }
+}
+
 }  // extern "C"

@@ -10,6 +10,8 @@ LIB_PATH = os.path.join(_HERE, "lib", "liborb_b200.so")
 
 ORB_OK, ORB_ERR_INVALID, ORB_ERR_CUDA, ORB_ERR_CAPACITY, ORB_ERR_NO_DEVICE, ORB_ERR_TOO_SMALL = 0, -1, -2, -3, -4, -5
 
+PIX_GRAY8, PIX_BGR8, PIX_RGB8, PIX_BGRA8, PIX_RGBA8 = 0, 1, 2, 3, 4
+
 KP_DTYPE = np.dtype(
     [("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
      ("octave", "<i4"), ("class_id", "<i4")]
@@ -32,7 +34,7 @@ class OrbError(RuntimeError):
 # every symbol include/orb_b200.h declares (tests check that the .so exports all of them)
 EXPORTS = [
     "orb_last_error", "orb_device_count", "orb_version", "orb_create", "orb_destroy", "orb_get_tables",
-    "orb_max_keypoints", "orb_extract", "orb_extract_batch", "orb_extract_batch_device", "orb_set_stream", "orb_sync",
+    "orb_max_keypoints", "orb_extract", "orb_extract_batch", "orb_extract_batch_device", "orb_extract_batch_pix", "orb_extract_batch_device_pix", "orb_set_stream", "orb_sync",
     "orb_launch_count", "orb_profile_enable", "orb_profile_read", "orb_level_dims", "orb_pyramid_level", "orb_debug_blurred", "orb_debug_raw_corners",
     "orb_debug_tie_counts", "orb_hamming_top2", "orb_hamming_top2_csr", "orb_db_create", "orb_db_destroy", "orb_db_add", "orb_db_add_device",
     "orb_db_size", "orb_db_set_stream", "orb_db_query_top2", "orb_db_query_top2_device", "orb_db_launch_count", "orb_db_profile_enable", "orb_db_profile_read",
@@ -60,6 +62,8 @@ def lib():
     L.orb_extract.argtypes = [vp, vp, i32, i32, sz, vp, vp, i32, C.POINTER(i32)]
     L.orb_extract_batch.argtypes = [vp, vp, i32, i32, i32, sz, sz, vp, vp, i32, vp]
     L.orb_extract_batch_device.argtypes = [vp, vp, i32, i32, i32, sz, sz, vp, vp, i32, vp]
+    L.orb_extract_batch_pix.argtypes = [vp, vp, i32, i32, i32, i32, sz, sz, vp, vp, i32, vp]
+    L.orb_extract_batch_device_pix.argtypes = [vp, vp, i32, i32, i32, i32, sz, sz, vp, vp, i32, vp]
     L.orb_set_stream.argtypes = [vp, vp]
     L.orb_sync.argtypes = [vp]
     L.orb_launch_count.argtypes = [vp]

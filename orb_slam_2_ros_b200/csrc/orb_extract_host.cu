@@ -305,8 +305,8 @@ int ensure_outputs(orb_ctx* c, int dcap, bool need_host_mirror) {
     return ORB_OK;
 }
 
-int ensure_input_staging(orb_ctx* c, bool need_host_mirror) {
-    const size_t in_bytes = (size_t)c->max_batch * c->g.w * c->g.h;
+int ensure_input_staging(orb_ctx* c, bool need_host_mirror, int channels) {
+    const size_t in_bytes = (size_t)c->max_batch * c->g.w * c->g.h * channels;
     if (c->in_bytes < in_bytes) {
         ORB_CUDA(cudaStreamSynchronize(c->stream));
         cudaFree(c->d_in); c->d_in = nullptr;
@@ -533,10 +533,16 @@ int orb_profile_read(orb_ctx* c, double* stage_ms, int64_t* calls, int64_t* fram
 
 int orb_extract_batch_device(orb_ctx* c, const uint8_t* d_imgs, int nframes, int w, int h, size_t row_stride,
                              size_t frame_stride, orb_kp* d_kps, uint8_t* d_desc, int cap, int32_t* d_n_out) {
+    return orb_extract_batch_device_pix(c, d_imgs, ORB_PIX_GRAY8, nframes, w, h, row_stride, frame_stride, d_kps, d_desc, cap, d_n_out);
+}
+
+int orb_extract_batch_device_pix(orb_ctx* c, const uint8_t* d_imgs, int fmt, int nframes, int w, int h, size_t row_stride,
+                                 size_t frame_stride, orb_kp* d_kps, uint8_t* d_desc, int cap, int32_t* d_n_out) {
     if (!c || !d_imgs || !d_kps || !d_desc || !d_n_out || nframes < 0 || cap <= 0) return ORB_ERR_INVALID;
+    if (fmt < ORB_PIX_GRAY8 || fmt > ORB_PIX_RGBA8) return ORB_ERR_INVALID;
     if (nframes == 0 || w <= 0 || h <= 0) return ORB_OK;  // empty image => silent return (ORBextractor.cc:1086)
     if (nframes > c->max_batch) { orb_set_error("nframes %d > max_batch %d", nframes, c->max_batch); return ORB_ERR_CAPACITY; }
-    if (row_stride < (size_t)w) return ORB_ERR_INVALID;
+    if (row_stride < (size_t)w * orb_pix_channels(fmt)) return ORB_ERR_INVALID;
     int rc = ensure_device(c);
     if (rc != ORB_OK) return rc;
     rc = build_geometry(c, w, h);
@@ -544,7 +550,7 @@ int orb_extract_batch_device(orb_ctx* c, const uint8_t* d_imgs, int nframes, int
     c->last_frames = nframes;
     // (measured: cutting a resident batch into sub-batches on two streams is SLOWER, 147k -> 130k frames/s at 512
     // frames; the big launches already fill the chip.  Only the host pipeline below alternates streams.)
-    return orb_launch_extract(c, d_imgs, nframes, 0, row_stride, frame_stride, d_kps, d_desc, cap, d_n_out, c->stream);
+    return orb_launch_extract(c, d_imgs, fmt, nframes, 0, row_stride, frame_stride, d_kps, d_desc, cap, d_n_out, c->stream);
 }
 
 // Host buffers in, host buffers out.  The batch is cut into chunks of ORB_PIPE_CHUNK frames that flow through three
@@ -552,21 +558,29 @@ int orb_extract_batch_device(orb_ctx* c, const uint8_t* d_imgs, int nframes, int
 // Pinned caller buffers are used directly; pageable ones go through the context's pinned mirrors.
 int orb_extract_batch(orb_ctx* c, const uint8_t* imgs, int nframes, int w, int h, size_t row_stride, size_t frame_stride,
                       orb_kp* kps, uint8_t* desc, int cap, int32_t* n_out) {
+    return orb_extract_batch_pix(c, imgs, ORB_PIX_GRAY8, nframes, w, h, row_stride, frame_stride, kps, desc, cap, n_out);
+}
+
+int orb_extract_batch_pix(orb_ctx* c, const uint8_t* imgs, int fmt, int nframes, int w, int h, size_t row_stride,
+                          size_t frame_stride, orb_kp* kps, uint8_t* desc, int cap, int32_t* n_out) {
     if (!c || !n_out || nframes < 0 || cap < 0) return ORB_ERR_INVALID;
+    if (fmt < ORB_PIX_GRAY8 || fmt > ORB_PIX_RGBA8) return ORB_ERR_INVALID;
+    const int ch = orb_pix_channels(fmt);
     for (int f = 0; f < nframes; ++f) n_out[f] = 0;
     if (nframes == 0 || !imgs || w <= 0 || h <= 0) return ORB_OK;  // ORBextractor.cc:1086-1087
-    if (!kps || !desc || cap == 0 || row_stride < (size_t)w) return ORB_ERR_INVALID;
+    if (!kps || !desc || cap == 0 || row_stride < (size_t)w * ch) return ORB_ERR_INVALID;
     int rc = ensure_device(c);
     if (rc != ORB_OK) return rc;
     rc = build_geometry(c, w, h);
     if (rc != ORB_OK) return rc;
-    const bool tight = row_stride == (size_t)w && frame_stride == (size_t)w * h;
+    const size_t rbytes = (size_t)w * ch;                 // bytes of one tight row
+    const bool tight = row_stride == rbytes && frame_stride == rbytes * h;
     const bool in_direct = tight && is_pinned(imgs);
     const bool out_direct = is_pinned(kps) && is_pinned(desc);
     const int dcap = std::min(cap, c->g.total_kp_slots);
     rc = ensure_outputs(c, std::max(dcap, c->out_cap), !out_direct);
     if (rc != ORB_OK) return rc;
-    rc = ensure_input_staging(c, !in_direct);
+    rc = ensure_input_staging(c, !in_direct, ch);
     if (rc != ORB_OK) return rc;
     const int ocap = c->out_cap;                        // device row length (>= dcap)
     static const int chunk_frames = [] {               // frames per pipeline chunk (tunable for experiments)
@@ -574,7 +588,7 @@ int orb_extract_batch(orb_ctx* c, const uint8_t* imgs, int nframes, int w, int h
         const int v = e ? atoi(e) : 0;
         return v > 0 ? v : ORB_PIPE_CHUNK;
     }();
-    const size_t fbytes = (size_t)w * h;
+    const size_t fbytes = rbytes * h;
     int status = ORB_OK;
     // the caller's stream (c->stream) may have pending work that produced or still reads our buffers
     ORB_CUDA(cudaStreamSynchronize(c->stream));
@@ -608,8 +622,8 @@ int orb_extract_batch(orb_ctx* c, const uint8_t* imgs, int nframes, int w, int h
                 for (int f = 0; f < F; ++f) {
                     const uint8_t* s1 = src + (size_t)f * frame_stride;
                     uint8_t* d1 = stage + (size_t)f * fbytes;
-                    if (row_stride == (size_t)w) memcpy(d1, s1, fbytes);
-                    else for (int y = 0; y < h; ++y) memcpy(d1 + (size_t)y * w, s1 + (size_t)y * row_stride, w);
+                    if (row_stride == rbytes) memcpy(d1, s1, fbytes);
+                    else for (int y = 0; y < h; ++y) memcpy(d1 + (size_t)y * rbytes, s1 + (size_t)y * row_stride, rbytes);
                 }
                 src = stage;
             }
@@ -620,7 +634,7 @@ int orb_extract_batch(orb_ctx* c, const uint8_t* imgs, int nframes, int w, int h
             // chunk (upper pyramid levels, quadtree) overlap the issue-bound ones of its neighbour ----
             cudaStream_t cs = (k & 1) ? c->st_c2 : c->stream;
             ORB_CUDA(cudaStreamWaitEvent(cs, c->ev_in[slot], 0));
-            rc = orb_launch_extract(c, d_src, F, f0, (size_t)w, fbytes, c->d_kps_out + (size_t)f0 * ocap,
+            rc = orb_launch_extract(c, d_src, fmt, F, f0, rbytes, fbytes, c->d_kps_out + (size_t)f0 * ocap,
                                     c->d_desc_out + (size_t)f0 * ocap * 32, ocap, c->d_n_out + f0, cs);
             if (rc != ORB_OK) return rc;
             ORB_CUDA(cudaEventRecord(c->ev_done[slot], cs));

@@ -486,7 +486,7 @@ extern "C" int orb_debug_sincos_range(int device, unsigned first_bits, long long
 // ======================================================================================================
 // host-side launch sequence of one batch (asynchronous on c->stream)
 // ======================================================================================================
-int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int F, int f0, size_t row_stride, size_t frame_stride,
+int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int pixel_format, int F, int f0, size_t row_stride, size_t frame_stride,
                        orb_kp* d_kps, uint8_t* d_desc, int cap, int* d_n_out, cudaStream_t st) {
     // frames [f0, f0 + F) of the arena: a per-launch copy of the geometry with shifted bases, so the kernels index
     // frames by blockIdx.y alone; d_imgs / d_kps / d_desc / d_n_out already point at the chunk's first frame
@@ -519,7 +519,7 @@ int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int F, int f0, size_t 
     ORB_CUDA(cudaMemsetAsync(d_cc, 0, sizeof(int) * (size_t)F * g.nlevels, st));
     ORB_CUDA(cudaMemsetAsync(d_tie, 0, sizeof(int) * (size_t)F * g.nlevels, st));
     ORB_STAGE_MARK(0, st);
-    { int rc = orb_launch_pyramid(c, g, d_imgs, F, row_stride, frame_stride, st); if (rc != ORB_OK) return rc; }   // K1 interior
+    { int rc = orb_launch_pyramid(c, g, d_imgs, pixel_format, F, row_stride, frame_stride, st); if (rc != ORB_OK) return rc; }   // K1 interior
     ORB_STAGE_MARK(1, st);
     if (aux != st) {
         ORB_CUDA(cudaEventRecord(c->ev_pyr[which], st));

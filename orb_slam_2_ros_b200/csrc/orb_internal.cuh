@@ -166,11 +166,12 @@ struct orb_ctx {
 int orb_profile_harvest(orb_ctx* c, int slot);
 
 // kernels' launchers (orb_extract_kernels.cu)
-int orb_launch_pyramid(orb_ctx* c, const Geometry& g, const uint8_t* d_imgs, int nframes, size_t row_stride,
+int orb_launch_pyramid(orb_ctx* c, const Geometry& g, const uint8_t* d_imgs, int pixel_format, int nframes, size_t row_stride,
                        size_t frame_stride, cudaStream_t st);
+inline int orb_pix_channels(int fmt) { return fmt == ORB_PIX_GRAY8 ? 1 : (fmt == ORB_PIX_BGR8 || fmt == ORB_PIX_RGB8) ? 3 : 4; }
 int orb_launch_border(orb_ctx* c, const Geometry& g, int nframes, cudaStream_t st);
 int orb_launch_fast(orb_ctx* c, const Geometry& g, int* d_corner_count, int nframes, int f0, cudaStream_t st);
 int orb_launch_blur(orb_ctx* c, const Geometry& g, int nframes, cudaStream_t st);
 // frames [f0, f0 + nframes) of the arena; all pointers address the chunk's first frame; asynchronous on st
-int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int nframes, int f0, size_t row_stride, size_t frame_stride,
-                       orb_kp* d_kps, uint8_t* d_desc, int cap, int* d_n_out, cudaStream_t st);
+int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int pixel_format, int nframes, int f0, size_t row_stride,
+                       size_t frame_stride, orb_kp* d_kps, uint8_t* d_desc, int cap, int* d_n_out, cudaStream_t st);

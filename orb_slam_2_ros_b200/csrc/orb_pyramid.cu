@@ -52,6 +52,32 @@ pyr_copy0_kernel(const uint8_t* __restrict__ in, size_t row_stride, size_t frame
     *reinterpret_cast<uint4*>(pyr + L.base + (long long)f * L.frame_stride + L.ioff + y * L.pitch + x) = v;
 }
 
+// ---- level 0 interior from an interleaved colour image: cvtColor(.., *2GRAY) fused into the copy -----------------
+// OpenCV 4.13.0 8-bit arithmetic (pin (i)):  gray = (B*3735 + G*19235 + R*9798 + 16384) >> 15.  One output word (4 px)
+// per thread; CH = 3 or 4 interleaved channels, RGB = the red channel comes first.
+template <int CH, bool RGB>
+__global__ void __launch_bounds__(256)
+pyr_copy0_color_kernel(const uint8_t* __restrict__ in, size_t row_stride, size_t frame_stride, uint8_t* __restrict__ pyr,
+                       const __grid_constant__ Geometry g) {
+    const LevelGeom& L = g.lv[0];
+    const int wpr = (L.w + 3) >> 2;
+    const int item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= wpr * L.h) return;
+    const int y = item / wpr, x = (item - y * wpr) << 2;
+    const int f = blockIdx.y;
+    const uint8_t* src = in + (size_t)f * frame_stride + (size_t)y * row_stride + (size_t)x * CH;
+    unsigned v = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (x + k < L.w) {
+            const unsigned c0 = __ldg(src + k * CH), c1 = __ldg(src + k * CH + 1), c2 = __ldg(src + k * CH + 2);
+            const unsigned b = RGB ? c2 : c0, r = RGB ? c0 : c2;
+            v |= ((b * 3735u + c1 * 19235u + r * 9798u + 16384u) >> 15) << (8 * k);
+        }
+    }
+    *reinterpret_cast<unsigned*>(pyr + L.base + (long long)f * L.frame_stride + L.ioff + y * L.pitch + x) = v;
+}
+
 // ---- fast resize: one output word x ORB_RESIZE_ROWS rows per thread ------------------------------------
 struct ColSel { unsigned sh[4]; bool hi[4]; };   // per column: funnel-shift amount and which word pair holds its taps
 
@@ -217,9 +243,21 @@ pyr_border_kernel(uint8_t* __restrict__ pyr, const __grid_constant__ Geometry g)
 
 }  // namespace
 
-int orb_launch_pyramid(orb_ctx* c, const Geometry& g, const uint8_t* d_imgs, int F, size_t row_stride, size_t frame_stride,
-                       cudaStream_t st) {
-    {
+int orb_launch_pyramid(orb_ctx* c, const Geometry& g, const uint8_t* d_imgs, int pixel_format, int F, size_t row_stride,
+                       size_t frame_stride, cudaStream_t st) {
+    if (pixel_format != ORB_PIX_GRAY8) {
+        const LevelGeom& L = g.lv[0];
+        const int items = ((L.w + 3) >> 2) * L.h;
+        dim3 grd((items + 255) / 256, F);
+        switch (pixel_format) {
+            case ORB_PIX_BGR8: pyr_copy0_color_kernel<3, false><<<grd, 256, 0, st>>>(d_imgs, row_stride, frame_stride, c->d_pyr, g); break;
+            case ORB_PIX_RGB8: pyr_copy0_color_kernel<3, true><<<grd, 256, 0, st>>>(d_imgs, row_stride, frame_stride, c->d_pyr, g); break;
+            case ORB_PIX_BGRA8: pyr_copy0_color_kernel<4, false><<<grd, 256, 0, st>>>(d_imgs, row_stride, frame_stride, c->d_pyr, g); break;
+            case ORB_PIX_RGBA8: pyr_copy0_color_kernel<4, true><<<grd, 256, 0, st>>>(d_imgs, row_stride, frame_stride, c->d_pyr, g); break;
+            default: orb_set_error("unknown pixel format %d", pixel_format); return ORB_ERR_INVALID;
+        }
+        c->launches++;
+    } else {
         const LevelGeom& L = g.lv[0];
         const int items = ((L.w + 15) >> 4) * L.h;
         const bool aligned = ((((uintptr_t)d_imgs) | row_stride | frame_stride) & 15) == 0;

@@ -43,11 +43,22 @@ class ORBextractor:
     def GetScaleSigmaSquares(self): return self.mvLevelSigma2.copy()
     def GetInverseScaleSigmaSquares(self): return self.mvInvLevelSigma2.copy()
 
-    def __call__(self, image, mask=None):
+    def __call__(self, image, mask=None, rgb=False):
         """operator()(image, mask, keypoints, descriptors) — mask is ignored like in the reference
-        (ORBextractor.h:58).  Returns (keypoints: KP_DTYPE[n], descriptors: uint8[n, 32])."""
+        (ORBextractor.h:58).  Returns (keypoints: KP_DTYPE[n], descriptors: uint8[n, 32]).
+        A (h, w, 3|4) uint8 image is the camera frame BEFORE Tracking's cvtColor (Tracking.cc:181-204): the BGR(A) /
+        RGB(A) (rgb=True, like mbRGB) -> gray conversion is fused into the level-0 pyramid copy on the device."""
         if image is None or image.size == 0:
             return np.zeros(0, KP_DTYPE), np.zeros((0, 32), np.uint8)   # ORBextractor.cc:1086-1087
+        if image.dtype == np.uint8 and image.ndim == 3 and image.shape[2] in (3, 4):
+            image = np.ascontiguousarray(image)
+            h, w, ch = image.shape
+            fmt = {(3, False): _lib.PIX_BGR8, (3, True): _lib.PIX_RGB8, (4, False): _lib.PIX_BGRA8, (4, True): _lib.PIX_RGBA8}[(ch, bool(rgb))]
+            cap = self.max_keypoints
+            kps = np.zeros(cap, KP_DTYPE); desc = np.zeros((cap, 32), np.uint8); n = np.zeros(1, np.int32)
+            check(lib().orb_extract_batch_pix(self._h, ptr(image), fmt, 1, w, h, image.strides[0], image.strides[0] * h, ptr(kps),
+                                              ptr(desc), cap, ptr(n)))
+            return kps[:n[0]].copy(), desc[:n[0]].copy()
         if image.dtype != np.uint8 or image.ndim != 2:
             raise TypeError("image must be CV_8UC1 (uint8, 2-D)")       # the reference asserts (ORBextractor.cc:1090)
         if image.strides[1] != 1:

@@ -210,3 +210,19 @@ def test_config4_shape_large_batch_properties(oracle, ORB):
         assert len(k) == len(ok) and 1000 <= len(k) <= 1000 + 3 * 8, "frame %d: %d keypoints" % (f, len(k))
         assert np.array_equal(np.ascontiguousarray(k).view(np.uint8), np.ascontiguousarray(ok).view(np.uint8)), "frame %d" % f
         assert np.array_equal(d, od), "frame %d" % f
+
+
+@pytest.mark.parametrize("ch,rgb", [(3, False), (3, True), (4, False), (4, True)])
+def test_colour_input_fused_cvtcolor(oracle, ORB, ch, rgb):
+    """the camera frame before Tracking's cvtColor goes straight to the extractor; level 0 of the pyramid
+    must equal cvtColor's gray image (OpenCV 4.13.0 arithmetic) and everything downstream the oracle on that gray image."""
+    rng = np.random.default_rng(40 + ch + rgb)
+    gray = synth.synth_frame(60 + ch, 640, 480).astype(np.int32)
+    col = np.stack([np.clip(gray + rng.integers(-25, 26, gray.shape), 0, 255) for _ in range(ch)], 2).astype(np.uint8)
+    want_gray = oracle.cvt_gray(col, rgb)
+    ex = ORB(1000)
+    k, d = ex(col, rgb=rgb)
+    assert np.array_equal(ex.mvImagePyramid[0], want_gray)
+    ok, od = oracle.Extractor(1000).extract(want_gray)
+    assert_kps_equal(k, ok, "colour %d %s" % (ch, rgb))
+    assert np.array_equal(d, od)

@@ -71,3 +71,14 @@ def test_full_pipeline_vs_cv2_harness(oracle):
     for f in k1.dtype.names:
         assert np.array_equal(k1[f].view(np.uint32), k2[f].view(np.uint32)), f
     assert np.array_equal(d1, d2)
+
+
+def test_cvt_gray_vs_cv2(oracle):
+    """cvtColor(.., *2GRAY) of Tracking::GrabImage* (Tracking.cc:181-204): the oracle's integer recipe equals cv2 4.13.0."""
+    import cv2
+    rng = np.random.default_rng(12)
+    for ch, rgb, code in ((3, False, cv2.COLOR_BGR2GRAY), (3, True, cv2.COLOR_RGB2GRAY), (4, False, cv2.COLOR_BGRA2GRAY),
+                          (4, True, cv2.COLOR_RGBA2GRAY)):
+        img = rng.integers(0, 256, (97, 131, ch), dtype=np.uint8)
+        img[:8, :8] = 255; img[8:16, :8] = 0                     # saturated corners
+        assert np.array_equal(oracle.cvt_gray(img, rgb), cv2.cvtColor(img, code)), (ch, rgb)
