@@ -536,6 +536,11 @@ int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int pixel_format, int 
     ORB_STAGE_MARK(2, st);
     {   // K3
         const size_t smem = (size_t)g.max_node_cap * 80;
+        if (smem > 48 * 1024 && !c->qt_attr_set) {   // large nFeatures: opt in to > 48 KB of dynamic shared memory
+            ORB_CUDA(cudaFuncSetAttribute(quadtree_kernel<QT_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            ORB_CUDA(cudaFuncSetAttribute(quadtree_kernel<QT_THREADS_LAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            c->qt_attr_set = true;
+        }
         if (F >= 8)
             quadtree_kernel<QT_THREADS><<<dim3(g.nlevels, F), QT_THREADS, smem, st>>>(c->d_corners, d_cc, c->d_node_of_key, d_kept,
                                                                                        d_kept_count, d_tie, g);

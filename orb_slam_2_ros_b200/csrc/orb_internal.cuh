@@ -146,7 +146,7 @@ struct orb_ctx {
     FastTmaps* d_tmaps = nullptr; // device copy (the TMA unit reads the descriptor from global memory)
     bool use_tma = false;
     uint2* d_mom_tab = nullptr;   // IC_Angle weight table [4 alignments][288 items] (orient_describe_kernel)
-    bool fast_attr_set = false;
+    bool fast_attr_set = false, qt_attr_set = false;
     orb_kp* d_kps_out = nullptr; uint8_t* d_desc_out = nullptr; int* d_n_out = nullptr; int out_cap = 0;
     orb_kp* h_kps = nullptr; uint8_t* h_desc = nullptr; int* h_n = nullptr; uint8_t* h_in = nullptr;  // pinned
     size_t h_in_bytes = 0;

@@ -226,3 +226,31 @@ def test_colour_input_fused_cvtcolor(oracle, ORB, ch, rgb):
     ok, od = oracle.Extractor(1000).extract(want_gray)
     assert_kps_equal(k, ok, "colour %d %s" % (ch, rgb))
     assert np.array_equal(d, od)
+
+
+@pytest.mark.parametrize("nf,sf,nl,ini,mn,w,h", [
+    (1000, 1.5, 5, 20, 7, 640, 480),      # scale factor > 4/3: the generic resize kernel
+    (800, 2.0, 3, 20, 7, 752, 480),       # octave pyramid
+    (1200, 1.1, 10, 25, 10, 640, 480),    # ten shallow levels, other FAST thresholds
+    (5000, 1.2, 8, 20, 7, 1241, 376),     # large quota: quadtree shared memory above 48 KB
+    (300, 1.2, 2, 40, 5, 400, 300),       # few features, wide threshold gap
+    (1000, 1.2, 8, 12, 12, 640, 480),     # iniThFAST == minThFAST (the retry never changes anything)
+])
+def test_other_extractor_parameters(oracle, ORB, nf, sf, nl, ini, mn, w, h):
+    """Parameters outside the TUM / KITTI / EuRoC defaults: every code path that depends on them (generic resize,
+    level count, quotas, thresholds, quadtree capacity) against the oracle."""
+    img = synth.synth_frame(70 + nl, w, h)
+    ex = ORB(nf, sf, nl, ini, mn)
+    oex = oracle.Extractor(nf, sf, nl, ini, mn)
+    k, d = ex(img)
+    ok, od = oex.extract(img)
+    for l in range(nl):
+        assert np.array_equal(ex.pyramid_level_bordered(l), oex.level(l)), "pyramid level %d" % l
+    assert_kps_equal(k, ok, "params %s" % ((nf, sf, nl, ini, mn),))
+    assert np.array_equal(d, od)
+    # the same through the throughput shapes (8-row resize threads, 256-thread quadtree CTAs): a batch of 9 frames
+    exb = ORB(nf, sf, nl, ini, mn, max_batch=9)
+    res = exb.extract_batch(np.stack([img] * 9))
+    for f in (0, 8):
+        assert_kps_equal(res[f][0], ok, "batched frame %d" % f)
+        assert np.array_equal(res[f][1], od)
