@@ -122,7 +122,9 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
     uint8_t* score = fs_smem + FS_TILE_BYTES + FS_CAND_BYTES + FS_SCORED_BYTES;                   // FS_SROWS x FS_PITCH scores
     unsigned long long* outl = reinterpret_cast<unsigned long long*>(fs_smem);                   // pass 3: aliases tile + cand
     __shared__ int s_any[FS_MAXG];
-    __shared__ int s_nscored, s_nout, s_base;
+    __shared__ int s_nscored, s_nout, s_base, s_nempty;
+    __shared__ int s_bpre[FS_MAXG + 1], s_bw0[FS_MAXG], s_bnw[FS_MAXG];   // stage B: per empty cell word-item prefix, first word, words per row
+    __shared__ unsigned s_binv[FS_MAXG], s_bmf[FS_MAXG], s_bml[FS_MAXG];
     __shared__ __align__(8) unsigned long long s_mbar;
 
     const int f = blockIdx.y;
@@ -169,13 +171,11 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
 
     // ---- pass 1: scores.  Evaluated pixels are the shared-memory bytes [sb_lo, sb_hi) of tile rows [3, 3+eh) ----
     const int tmin = g.min_th, tini = g.ini_th;
-    const unsigned tp1 = (unsigned)(tmin + 1) * 0x10001u, ntp1 = ((unsigned)(-(tmin + 1)) & 0xFFFFu) * 0x10001u;
     const int sb_lo = a + 3, sb_hi = a + 3 + ew;
     const int wlo = S.wlo, nw = S.nw, whi = wlo + nw - 1;  // words holding evaluated pixels (<= 64)
     const unsigned inv_nw = S.inv_nw;
-    const unsigned vfirst = 0xFu << (sb_lo & 3), vlast = 0xFu >> (3 - ((sb_hi - 1) & 3));
+    const unsigned vfirst = (0xFu << (sb_lo & 3)) & 0xFu, vlast = 0xFu >> (3 - ((sb_hi - 1) & 3));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int total = eh * nw;                             // <= 60 * 64 words: at most 15 iterations of 256 threads
     auto score_one = [&](int r, int sb) {
         const int sc = fast_score_at(tile + (r + 3) * FS_PITCH + sb);
         if (sc >= tmin) {
@@ -184,13 +184,18 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
             if (o < FS_SCAP) scored[o] = (unsigned short)(r * FS_PITCH + sb);
         }
     };
-    {
+    // One candidate pass over `total` word items (<= 60 * 64: at most 15 iterations of 256 threads); map(k) gives the
+    // item's row, word and valid-pixel mask.  Quick test at threshold th -> per-lane 64-bit candidate mask -> warp-local
+    // compaction -> exact scores.  SKIP: pixels that already have a score (an earlier pass) are not candidates.
+    auto cand_pass = [&](const int total, auto&& map, const int th, const bool skip) {
+        const unsigned tp1 = (unsigned)(th + 1) * 0x10001u, ntp1 = ((unsigned)(-(th + 1)) & 0xFFFFu) * 0x10001u;
         // 1a: quick test, 4 candidate bits per iteration per lane
         unsigned long long cmask = 0ull;
         int it = 0;
         for (int k = threadIdx.x; k < total; k += FS_THREADS, ++it) {
-            const int r = (int)__umulhi((unsigned)k, inv_nw);
-            const int wd = wlo + (k - r * nw);
+            int r, wd;
+            unsigned vm;
+            map(k, r, wd, vm);
             const unsigned* row = reinterpret_cast<const unsigned*>(tile + (r + 3) * FS_PITCH) + wd;   // centre row
             constexpr int P = FS_PITCH / 4;
             const unsigned c = row[0], wl = row[-1], wr = row[1];
@@ -202,8 +207,12 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
             const unsigned r6 = __funnelshift_r(rm[0], rm[1], 16), r10 = __funnelshift_r(rm[-1], rm[0], 16);  // (+2,-2) (-2,-2)
             unsigned m = quick2<0>(c, r0, r8, r4, r12, r2, r10, r6, r14, tp1, ntp1) |
                          (quick2<1>(c, r0, r8, r4, r12, r2, r10, r6, r14, tp1, ntp1) << 2);
-            if (wd == wlo) m &= vfirst;
-            if (wd == whi) m &= vlast;
+            m &= vm;
+            if (skip) {
+                const unsigned sw = reinterpret_cast<const unsigned*>(score + (r + 1) * FS_PITCH)[wd];
+                const unsigned nz = __vcmpne4(sw, 0u);     // 0xFF per pixel that already has a score
+                m &= ~((nz & 1u) | ((nz >> 7) & 2u) | ((nz >> 14) & 4u) | ((nz >> 21) & 8u));
+            }
             cmask |= (unsigned long long)m << (4 * it);
         }
         // warp-level compaction: exclusive prefix of the per-lane counts
@@ -217,22 +226,20 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
         const int wtotal = __shfl_sync(0xffffffffu, incl, 31);
         unsigned short* seg = cand + warp * FS_WCAP;
         if (wtotal <= FS_WCAP) {
-            // every lane walks its iterations (uniform trip count, no divergence) and stores the 0-4 candidates of each
-            // word with predicated writes; o = running position in the warp's segment
+            // every lane appends its own candidates (set bits of its mask) at its prefix offset; at iniThFAST a lane
+            // holds only a few, so walking the set bits is cheaper than a uniform walk over all words
             int o = incl - cnt;
-            int it2 = 0;
-            for (int k = threadIdx.x; k < total; k += FS_THREADS, ++it2) {
-                const unsigned m = (unsigned)(cmask >> (4 * it2)) & 15u;
-                const int r = (int)__umulhi((unsigned)k, inv_nw);
-                const int code = r * FS_PITCH + ((wlo + (k - r * nw)) << 2);
-                if (m & 1u) seg[o] = (unsigned short)code;
-                o += m & 1u;
-                if (m & 2u) seg[o] = (unsigned short)(code + 1);
-                o += (m >> 1) & 1u;
-                if (m & 4u) seg[o] = (unsigned short)(code + 2);
-                o += (m >> 2) & 1u;
-                if (m & 8u) seg[o] = (unsigned short)(code + 3);
-                o += (m >> 3) & 1u;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                unsigned mm = half ? (unsigned)(cmask >> 32) : (unsigned)cmask;
+                while (mm) {
+                    const int bit = __ffs((int)mm) - 1;
+                    mm &= mm - 1u;
+                    int r, wd;
+                    unsigned vm;
+                    map(threadIdx.x + ((bit >> 2) + 8 * half) * FS_THREADS, r, wd, vm);
+                    seg[o++] = (unsigned short)(r * FS_PITCH + (wd << 2) + (bit & 3));
+                }
             }
             __syncwarp();
             // 1b: exact score of the warp's candidates
@@ -241,21 +248,31 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
                 const int r = (int)__umulhi((unsigned)code, 0xFFFFFFFFu / FS_PITCH + 1u);
                 score_one(r, code - r * FS_PITCH);
             }
+            __syncwarp();
         } else {
             // segment overflow (a warp with > 896 candidates): score in place, lane by lane
             while (cmask) {
                 const int bit = __ffsll((long long)cmask) - 1;
                 cmask &= cmask - 1ull;
-                const int k = threadIdx.x + (bit >> 2) * FS_THREADS;
-                const int r = (int)__umulhi((unsigned)k, inv_nw);
-                const int wd = wlo + (k - r * nw);
+                int r, wd;
+                unsigned vm;
+                map(threadIdx.x + (bit >> 2) * FS_THREADS, r, wd, vm);
                 score_one(r, (wd << 2) + (bit & 3));
             }
         }
-    }
+    };
+    // stage A: the whole strip at iniThFAST (a cell that has an NMS maximum >= iniThFAST never needs anything lower)
+    cand_pass(eh * nw,
+              [&](int k, int& r, int& wd, unsigned& vm) {
+                  r = (int)__umulhi((unsigned)k, inv_nw);
+                  wd = wlo + (k - r * nw);
+                  vm = (wd == wlo ? vfirst : 0xFu) & (wd == whi ? vlast : 0xFu);
+              },
+              tini, false);
     __syncthreads();
 
-    // ---- pass 2 / 3: NMS (strict >, neighbours outside the cell's evaluated area count as 0) ----
+    // ---- pass 2: NMS (strict >, neighbours outside the cell's evaluated area count as 0) of the scores >= iniThFAST;
+    //      cells decide their threshold: any NMS maximum >= iniThFAST? ----
     const int wCell = L.wCell;
     const unsigned inv_wc = S.inv_wc;
     auto nms_max = [&](int r, int sb, int sc, int& jj, int& xr) -> bool {
@@ -282,31 +299,20 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
             if (gi < L.corner_cap) corners[L.corner_base + (long long)f * L.corner_cap + gi] = rec;
         }
     };
-    const int nscored = s_nscored;
-    if (nscored <= FS_SCAP) {
-        // dense: one scored corner per thread; bit 15 of the entry remembers "is an NMS maximum"
-        for (int k = threadIdx.x; k < nscored; k += FS_THREADS) {
+    const int n1 = s_nscored;
+    if (n1 <= FS_SCAP) {
+        // dense: one scored corner per thread; bit 15 of the entry remembers "is an NMS maximum" (scores >= iniThFAST
+        // only: a neighbour below iniThFAST cannot suppress them, so later passes never change these flags)
+        for (int k = threadIdx.x; k < n1; k += FS_THREADS) {
             const int code = scored[k];
             const int r = (int)__umulhi((unsigned)code, 0xFFFFFFFFu / FS_PITCH + 1u);
             const int sb = code - r * FS_PITCH;
             const int sc = score[(r + 1) * FS_PITCH + sb];
             int jj, xr;
-            if (nms_max(r, sb, sc, jj, xr)) {
+            if (sc >= tini && nms_max(r, sb, sc, jj, xr)) {
                 scored[k] = (unsigned short)(code | 0x8000);
-                if (sc >= tini) s_any[jj] = 1;
+                s_any[jj] = 1;
             }
-        }
-        __syncthreads();   // also: every read of tile / cand is done, outl may overwrite them
-        for (int k = threadIdx.x; k < nscored; k += FS_THREADS) {
-            const int code = scored[k];
-            if (!(code & 0x8000)) continue;
-            const int r = (int)__umulhi((unsigned)(code & 0x7FFF), 0xFFFFFFFFu / FS_PITCH + 1u);
-            const int sb = (code & 0x7FFF) - r * FS_PITCH;
-            const int sc = score[(r + 1) * FS_PITCH + sb];
-            const int xe = sb - sb_lo;
-            const int jj = (int)__umulhi((unsigned)xe, inv_wc);
-            if (sc < (s_any[jj] ? tini : tmin)) continue;
-            emit(r, sb, sc, jj, xe - jj * wCell);
         }
     } else {
         // scored-list overflow: scan the score tile instead (same result, slower)
@@ -320,7 +326,60 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
                 if (sc >= tini && nms_max(r, (wd << 2) + b, sc, jj, xr)) s_any[jj] = 1;
             }
         }
-        __syncthreads();
+    }
+    __syncthreads();
+
+    // ---- stage B (ORBextractor.cc:846-850): the cells without any maximum >= iniThFAST are searched again at
+    //      minThFAST; their word items are enumerated cell by cell through a small prefix table ----
+    if (threadIdx.x == 0) {
+        int ne = 0, pre = 0;
+        for (int jj = 0; jj < FS_MAXG && jj * wCell < ew; ++jj) {
+            if (s_any[jj]) continue;
+            const int lo = sb_lo + jj * wCell, hi = min(lo + wCell, sb_hi);   // shared-memory bytes of the cell's evaluated columns
+            const int w0 = lo >> 2, n = ((hi - 1) >> 2) - w0 + 1;
+            s_bw0[ne] = w0; s_bnw[ne] = n; s_binv[ne] = 0xFFFFFFFFu / (unsigned)n + 1u;
+            s_bmf[ne] = (0xFu << (lo & 3)) & 0xFu; s_bml[ne] = 0xFu >> (3 - ((hi - 1) & 3));
+            s_bpre[ne] = pre; pre += n * eh; ++ne;
+        }
+        s_bpre[ne] = pre; s_nempty = ne;
+    }
+    __syncthreads();
+    const int nempty = s_nempty;
+    if (nempty > 0 && tmin < tini) {
+        cand_pass(s_bpre[nempty],
+                  [&](int k, int& r, int& wd, unsigned& vm) {
+                      int e = 0;
+                      while (e + 1 < nempty && k >= s_bpre[e + 1]) ++e;
+                      const int kk = k - s_bpre[e], n = s_bnw[e];
+                      r = (int)__umulhi((unsigned)kk, s_binv[e]);
+                      const int cw = kk - r * n;
+                      wd = s_bw0[e] + cw;
+                      vm = (cw == 0 ? s_bmf[e] : 0xFu) & (cw == n - 1 ? s_bml[e] : 0xFu);
+                  },
+                  tmin, true);
+    }
+    __syncthreads();   // also: every read of tile / cand is done, outl may overwrite them
+
+    // ---- pass 3: emit.  Cells with a maximum >= iniThFAST emit their flagged maxima; the others emit every NMS
+    //      maximum >= minThFAST (all of their scores are in the tile after stage B) ----
+    const int nscored = s_nscored;
+    if (nscored <= FS_SCAP) {
+        for (int k = threadIdx.x; k < nscored; k += FS_THREADS) {
+            const int code = scored[k] & 0x7FFF;
+            const bool flagged = (scored[k] & 0x8000) != 0;
+            const int r = (int)__umulhi((unsigned)code, 0xFFFFFFFFu / FS_PITCH + 1u);
+            const int sb = code - r * FS_PITCH;
+            const int sc = score[(r + 1) * FS_PITCH + sb];
+            const int xe = sb - sb_lo;
+            int jj = (int)__umulhi((unsigned)xe, inv_wc), xr = xe - jj * wCell;
+            if (sc >= tini) {
+                if (!flagged) continue;
+            } else {
+                if (s_any[jj] || !nms_max(r, sb, sc, jj, xr)) continue;
+            }
+            emit(r, sb, sc, jj, xr);
+        }
+    } else {
         for (int k = threadIdx.x; k < eh * nw; k += FS_THREADS) {
             const int r = (int)__umulhi((unsigned)k, inv_nw);
             const int wd = wlo + (k - r * nw);

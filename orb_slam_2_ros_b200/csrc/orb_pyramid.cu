@@ -176,8 +176,9 @@ pyr_resize_generic_kernel(uint8_t* __restrict__ pyr, const ResizeTap* __restrict
 
 // ---- the 19-px BORDER_REFLECT_101 frame of every level, one launch ---------------------------------------
 // Two kinds of work items, one thread each:
-//   side  : one bordered row — its 5 left border words (bytes 12..31) and its right border words (the first may
-//           straddle interior | border), each a byte-reversed unaligned window of the reflected interior row
+//   side  : ONE border word of one bordered row (16 thread slots per row: 5 left words = bytes 12..31, up to 6 right
+//           words, the first of which may straddle interior | border); each is a byte-reversed unaligned window of
+//           the reflected interior row, built with one funnel shift + one byte permute, no branches
 //   copy  : 16 bytes (or one trailing word) of a top/bottom bordered row — a plain aligned copy of the reflected row
 // A single reflection suffices (19 < w, h: smaller levels are rejected at geometry build time because the
 // reference's 30-px cell grid does not exist there either).
@@ -186,45 +187,39 @@ __device__ __forceinline__ int reflect1(int i, int n) {
     return i >= n ? 2 * n - 2 - i : i;
 }
 
+#define ORB_BORDER_SLOTS 16
+
 __global__ void __launch_bounds__(256)
 pyr_border_kernel(uint8_t* __restrict__ pyr, const __grid_constant__ Geometry g) {
     const int item = blockIdx.x * blockDim.x + threadIdx.x;
     const int f = blockIdx.y;
-    if (item < g.border_items) {
+    if (item < g.border_items * ORB_BORDER_SLOTS) {
+        const int ritem = item / ORB_BORDER_SLOTS, slot = item % ORB_BORDER_SLOTS;
         int l = 0;
-        while (l + 1 < g.nlevels && item >= g.lv[l + 1].border_base) ++l;
+        while (l + 1 < g.nlevels && ritem >= g.lv[l + 1].border_base) ++l;
         const LevelGeom& L = g.lv[l];
-        const int row = item - L.border_base;                                  // 0 .. h + 37
+        const int row = ritem - L.border_base;                                 // 0 .. h + 37
         uint8_t* img = pyr + L.base + (long long)f * L.frame_stride;
-        const uint8_t* srow = img + L.ioff + reflect1(row - ORB_EDGE, L.h) * L.pitch;
-        const unsigned* sw = reinterpret_cast<const unsigned*>(srow);
+        const unsigned* sw = reinterpret_cast<const unsigned*>(img + L.ioff + reflect1(row - ORB_EDGE, L.h) * L.pitch);
         unsigned* drow = reinterpret_cast<unsigned*>(img + row * L.pitch);
-        // left: border word k (bytes x0 .. x0+3, x0 = -20 + 4k) = reversed interior window [-x0-3, -x0] = bytes 1..4 of
-        // the word pair (4-k, 5-k): gfedcb|abcdefgh.  (Byte 12 of the row is a dead byte.)
-        unsigned prev = sw[5];
-#pragma unroll
-        for (int k = 0; k < 5; ++k) {
-            const unsigned cur = sw[4 - k];
-            drow[(ORB_XOFF - ORB_EDGE) / 4 + k] = __byte_perm(__funnelshift_r(cur, prev, 8), 0u, 0x0123);
-            prev = cur;
-        }
-        // right: words from the one holding interior byte w (may straddle) to the end of the 19-px frame
+        // word `word` of the bordered row holds interior columns x0 .. x0+3 (x0 < 0: left border, x0 + 3 >= w: right).
+        // Reflect-101 of those 4 columns = the byte-reversed window [s0, s0+3] of the interior row:
+        //   left:  s0 = -x0 - 3        (gfedcb|abcdefgh; byte 12 of the row is a dead byte)
+        //   right: s0 = 2w - 5 - x0    (abcdefgh|gfedcba)
         const int first = (ORB_XOFF + L.w) >> 2, end = (ORB_XOFF - ORB_EDGE) / 4 + L.border_words;
-        for (int word = first; word < end; ++word) {
-            const int x0 = 4 * word - ORB_XOFF;
-            unsigned v;
-            if (x0 >= L.w) {
-                const int s0 = 2 * L.w - 5 - x0;                               // mirrored window [s0, s0+3]
-                v = __byte_perm(__funnelshift_r(sw[s0 >> 2], sw[(s0 >> 2) + 1], (s0 & 3) * 8), 0u, 0x0123);
-            } else {
-                v = 0;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) v |= (unsigned)srow[reflect1(x0 + k, L.w)] << (8 * k);
-            }
-            drow[word] = v;
-        }
+        const bool left = slot < 5;
+        const int word = left ? (ORB_XOFF - ORB_EDGE) / 4 + slot : first + slot - 5;
+        if (word >= end) return;
+        const int x0 = 4 * word - ORB_XOFF;
+        const int s0 = left ? -x0 - 3 : 2 * L.w - 5 - x0;
+        const unsigned refl = __byte_perm(__funnelshift_r(sw[s0 >> 2], sw[(s0 >> 2) + 1], (s0 & 3) * 8), 0u, 0x0123);
+        // the straddling word keeps its n = w - x0 interior bytes (taken from the reflected source row: in a top/bottom
+        // row the copy items of this launch do not write the partial word)
+        const int n = left ? 0 : min(max(L.w - x0, 0), 4);
+        const unsigned m = n >= 4 ? 0xFFFFu : ((1u << (4 * n)) - 1u);
+        drow[word] = __byte_perm(sw[max(x0, 0) >> 2], refl, (0x3210u & m) | (0x7654u & ~m));
     } else {
-        int it = item - g.border_items;
+        int it = item - g.border_items * ORB_BORDER_SLOTS;
         if (it >= g.border_copy_items) return;
         int l = 0;
         while (l + 1 < g.nlevels && it >= g.lv[l + 1].copy_base) ++l;
@@ -288,7 +283,7 @@ int orb_launch_pyramid(orb_ctx* c, const Geometry& g, const uint8_t* d_imgs, int
 }
 
 int orb_launch_border(orb_ctx* c, const Geometry& g, int F, cudaStream_t st) {
-    pyr_border_kernel<<<dim3((g.border_items + g.border_copy_items + 255) / 256, F), 256, 0, st>>>(c->d_pyr, g);
+    pyr_border_kernel<<<dim3((g.border_items * ORB_BORDER_SLOTS + g.border_copy_items + 255) / 256, F), 256, 0, st>>>(c->d_pyr, g);
     c->launches++;
     ORB_CUDA(cudaGetLastError());
     return ORB_OK;
