@@ -12,6 +12,7 @@
  *   ORBmatcher::SearchByProjection (Frame/Last) ORBmatcher.cc:45-129, 1330-1472           -> orb_search_by_projection
  *   ORBmatcher::SearchByBoW inner loop          ORBmatcher.cc:196-252                     -> orb_match_bruteforce
  *   Frame::ComputeStereoMatches                 Frame.cc:502-676                          -> orb_stereo_match
+ *   ORBVocabulary::transform / loadFromTextFile DBoW2/TemplatedVocabulary.h:1140-1272, 1351 -> orb_bow_transform*, orb_voc_*
  *
  * INTEGRATION.md shows the C++ shims (ORBextractor.cc / ORBmatcher.cc / Frame.cc replacements) that bind
  * these entry points with the reference's own signatures.
@@ -207,6 +208,40 @@ int orb_match_bruteforce(int device, const uint8_t* desc1, const float* angle1, 
 int orb_stereo_match(orb_ctx* ctx_left, orb_ctx* ctx_right, const orb_kp* kps_l, const uint8_t* desc_l, int nl,
                      const orb_kp* kps_r, const uint8_t* desc_r, int nr, float bf, float b, float* u_right,
                      float* depth, int* nmatches);
+
+/* ---- bag of words: ORBVocabulary = DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB> ------------------------- */
+/* (orb_slam2/include/ORBVocabulary.h:31; Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h)                                */
+typedef struct orb_voc orb_voc;
+/* the in-memory form of loadFromTextFile (TemplatedVocabulary.h:1389-1436): nodes in id order, node 0 = root,
+ * parent[i] < i, children of a node = the nodes naming it as parent, in id order; word ids are given to the leaves
+ * (is_leaf != 0) in id order.  scoring / weighting = DBoW2::ScoringType / WeightingType (BowVector.h:36-53). */
+int orb_voc_create(orb_voc** voc, int device, int k, int L, int scoring, int weighting, int n_nodes, const int32_t* parent,
+                   const uint8_t* is_leaf, const uint8_t* desc32, const double* weight);
+/* TemplatedVocabulary::loadFromTextFile (TemplatedVocabulary.h:1351-1441), the ORBvoc.txt format */
+int orb_voc_load_text(orb_voc** voc, int device, const char* path);
+void orb_voc_destroy(orb_voc* voc);
+int orb_voc_info(orb_voc* voc, int* k, int* L, int* n_nodes, int* n_words, int* scoring, int* weighting);
+/* transform(feature, word_id, weight, &nid, levelsup) for n descriptors (TemplatedVocabulary.h:1231-1272) */
+int orb_bow_transform_features(orb_voc* voc, const uint8_t* desc32, int n, int levelsup, int32_t* word_id, double* weight,
+                               int32_t* node_id);
+int orb_bow_transform_features_device(orb_voc* voc, const uint8_t* d_desc32, int n, int levelsup, int32_t* d_word_id,
+                                      double* d_weight, int32_t* d_node_id, void* cuda_stream);
+/* transform(features, BowVector&, FeatureVector&, levelsup) (TemplatedVocabulary.h:1140-1218) for nframes descriptor
+ * sets at once; frame f = descriptor rows [desc_off[f], desc_off[f+1]) (desc_off[0] == 0, at most 8192 rows per frame).
+ * Outputs use the frames' own row ranges as capacity (o = desc_off[f]):
+ *   BowVector f     = (bow_word[o + j], bow_value[o + j]), j < bow_n[f], ascending word id, normalised as the
+ *                     vocabulary's scoring type demands;
+ *   FeatureVector f = nodes fv_node[o + j], j < fv_n[f], ascending; the features of node j are
+ *                     fv_feat[o + fv_start[o + f + j] .. o + fv_start[o + f + j + 1]) (indices inside the frame, ascending).
+ * Capacities: bow_word / bow_value / fv_node / fv_feat hold desc_off[nframes] entries, fv_start desc_off[nframes] + nframes. */
+int orb_bow_transform(orb_voc* voc, const uint8_t* desc32, const int32_t* desc_off, int nframes, int levelsup, int32_t* bow_n,
+                      int32_t* bow_word, double* bow_value, int32_t* fv_n, int32_t* fv_node, int32_t* fv_start, int32_t* fv_feat);
+/* the same with every pointer on the vocabulary's device, asynchronous on cuda_stream; d_scratch holds 16 bytes per
+ * descriptor; max_frame = the largest frame's row count */
+int orb_bow_transform_device(orb_voc* voc, const uint8_t* d_desc32, const int32_t* d_desc_off, int nframes, int n_total,
+                             int max_frame, int levelsup, void* d_scratch, int32_t* d_bow_n, int32_t* d_bow_word,
+                             double* d_bow_value, int32_t* d_fv_n, int32_t* d_fv_node, int32_t* d_fv_start, int32_t* d_fv_feat,
+                             void* cuda_stream);
 
 #ifdef __cplusplus
 }

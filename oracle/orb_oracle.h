@@ -159,6 +159,22 @@ int orc_stereo_match(void* ex_left, void* ex_right, const orc_kp* kps_l, const u
                      const orc_kp* kps_r, const uint8_t* desc_r, int nr, const orc_stereo_params* prm,
                      float* u_right, float* depth, int32_t* best_sad);
 
+/* ---------------- bag of words (DBoW2 TemplatedVocabulary<FORB>, orb_oracle_bow.cpp) ---------------- */
+/* nodes in id order (0 = root, TemplatedVocabulary.h:1389-1436); children = nodes with that parent in id order */
+void* orc_voc_create(int k, int L, int scoring, int weighting, int n_nodes, const int32_t* parent, const uint8_t* is_leaf,
+                     const uint8_t* desc32, const double* weight);
+void* orc_voc_load_text(const char* path); /* loadFromTextFile, TemplatedVocabulary.h:1351-1441; NULL on failure */
+void orc_voc_destroy(void* voc);
+void orc_voc_info(void* voc, int32_t* k, int32_t* L, int32_t* n_nodes, int32_t* n_words, int32_t* scoring, int32_t* weighting);
+void orc_voc_export(void* voc, int32_t* parent, uint8_t* is_leaf, uint8_t* desc32, double* weight);
+/* transform(feature, id, weight, &nid, levelsup), TemplatedVocabulary.h:1231-1272 */
+void orc_bow_transform_features(void* voc, const uint8_t* desc32, int n, int levelsup, int32_t* word_id, double* weight,
+                                int32_t* node_id);
+/* transform(features, BowVector, FeatureVector, levelsup), TemplatedVocabulary.h:1140-1218 (flat, sorted outputs) */
+void orc_bow_transform(void* voc, const uint8_t* desc32, int n, int levelsup, int32_t* n_bow, int32_t* bow_word,
+                       double* bow_value, int32_t* n_fv, int32_t* fv_node, int32_t* fv_start, int32_t* fv_feat);
+double orc_bow_score_l1(const int32_t* w1, const double* v1, int n1, const int32_t* w2, const double* v2, int n2);
+
 #ifdef __cplusplus
 }
 #endif

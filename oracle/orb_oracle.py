@@ -35,7 +35,7 @@ class StereoParams(C.Structure):
 def build(force=False):
     """Compile the oracle with the committed Makefile (gcc only, a few seconds)."""
     srcs = [os.path.join(_HERE, f) for f in
-            ("orb_oracle_extract.cpp", "orb_oracle_match.cpp", "orb_oracle.h", "orb_pattern_31.inc", "Makefile")]
+            ("orb_oracle_extract.cpp", "orb_oracle_match.cpp", "orb_oracle_bow.cpp", "orb_oracle.h", "orb_pattern_31.inc", "Makefile")]
     if (not force) and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in srcs):
         return _SO
     subprocess.check_call(["make", "-C", _HERE, "-s"])
@@ -87,6 +87,18 @@ def lib():
         L.orc_search_by_projection_ex.argtypes = [C.POINTER(SearchParams), vp, vp, vp, vp, i32, vp, i32] + [vp] * 13
         L.orc_match_bruteforce.argtypes = [vp, vp, i32, vp, vp, i32, i32, f32, i32, vp]
         L.orc_stereo_match.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, C.POINTER(StereoParams), vp, vp, vp]
+        f64 = C.c_double
+        L.orc_voc_create.restype = vp
+        L.orc_voc_create.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp, vp]
+        L.orc_voc_load_text.restype = vp
+        L.orc_voc_load_text.argtypes = [C.c_char_p]
+        L.orc_voc_destroy.argtypes = [vp]
+        L.orc_voc_info.argtypes = [vp] + [C.POINTER(i32)] * 6
+        L.orc_voc_export.argtypes = [vp] * 5
+        L.orc_bow_transform_features.argtypes = [vp, vp, i32, i32, vp, vp, vp]
+        L.orc_bow_transform.argtypes = [vp, vp, i32, i32, C.POINTER(i32), vp, vp, C.POINTER(i32), vp, vp, vp]
+        L.orc_bow_score_l1.restype = f64
+        L.orc_bow_score_l1.argtypes = [vp, vp, i32, vp, vp, i32]
         _lib = L
     return _lib
 
@@ -322,3 +334,59 @@ def stereo_match(ex_left, ex_right, kps_l, desc_l, kps_r, desc_r, bf, b):
     kept = lib().orc_stereo_match(ex_left._h, ex_right._h, _p(kps_l), _p(desc_l), n, _p(kps_r), _p(desc_r), len(kps_r),
                                   C.byref(prm), _p(ur), _p(depth), _p(sad))
     return kept, ur, depth, sad
+
+
+class Vocabulary:
+    """ORBVocabulary (DBoW2 TemplatedVocabulary<FORB>) restated on the CPU."""
+
+    def __init__(self, handle):
+        if not handle:
+            raise ValueError("vocabulary could not be created / loaded")
+        self._h = handle
+        v = [C.c_int32() for _ in range(6)]
+        lib().orc_voc_info(self._h, *[C.byref(x) for x in v])
+        self.k, self.L, self.n_nodes, self.n_words, self.scoring, self.weighting = [int(x.value) for x in v]
+
+    @classmethod
+    def from_arrays(cls, k, L, scoring, weighting, parent, is_leaf, desc, weight):
+        parent = np.ascontiguousarray(parent, np.int32); is_leaf = _u8(is_leaf); desc = _u8(desc)
+        weight = np.ascontiguousarray(weight, np.float64)
+        return cls(lib().orc_voc_create(k, L, scoring, weighting, len(parent), _p(parent), _p(is_leaf), _p(desc), _p(weight)))
+
+    @classmethod
+    def load_text(cls, path):
+        return cls(lib().orc_voc_load_text(os.fsencode(path)))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_voc_destroy(self._h)
+            self._h = None
+
+    def export(self):
+        parent = np.zeros(self.n_nodes, np.int32); leaf = np.zeros(self.n_nodes, np.uint8)
+        desc = np.zeros((self.n_nodes, 32), np.uint8); weight = np.zeros(self.n_nodes, np.float64)
+        lib().orc_voc_export(self._h, _p(parent), _p(leaf), _p(desc), _p(weight))
+        return parent, leaf, desc, weight
+
+    def transform_features(self, desc, levelsup=4):
+        desc = _u8(desc); n = len(desc)
+        word = np.zeros(n, np.int32); weight = np.zeros(n, np.float64); node = np.zeros(n, np.int32)
+        lib().orc_bow_transform_features(self._h, _p(desc), n, levelsup, _p(word), _p(weight), _p(node))
+        return word, weight, node
+
+    def transform(self, desc, levelsup=4):
+        """-> (bow_word, bow_value), (fv_node, fv_start, fv_feat)"""
+        desc = _u8(desc); n = len(desc)
+        bw = np.zeros(n, np.int32); bv = np.zeros(n, np.float64)
+        fn = np.zeros(n, np.int32); fs = np.zeros(n + 1, np.int32); ff = np.zeros(n, np.int32)
+        nb, nf = C.c_int32(), C.c_int32()
+        lib().orc_bow_transform(self._h, _p(desc), n, levelsup, C.byref(nb), _p(bw), _p(bv), C.byref(nf), _p(fn), _p(fs), _p(ff))
+        nb, nf = nb.value, nf.value
+        return (bw[:nb].copy(), bv[:nb].copy()), (fn[:nf].copy(), fs[:nf + 1].copy(), ff[:fs[nf]].copy())
+
+
+def bow_score_l1(a, b):
+    (w1, v1), (w2, v2) = a, b
+    w1 = np.ascontiguousarray(w1, np.int32); w2 = np.ascontiguousarray(w2, np.int32)
+    v1 = np.ascontiguousarray(v1, np.float64); v2 = np.ascontiguousarray(v2, np.float64)
+    return float(lib().orc_bow_score_l1(_p(w1), _p(v1), len(w1), _p(w2), _p(v2), len(w2)))

@@ -39,6 +39,8 @@ EXPORTS = [
     "orb_debug_tie_counts", "orb_hamming_top2", "orb_hamming_top2_csr", "orb_db_create", "orb_db_destroy", "orb_db_add", "orb_db_add_device",
     "orb_db_size", "orb_db_set_stream", "orb_db_query_top2", "orb_db_query_top2_device", "orb_db_launch_count", "orb_db_profile_enable", "orb_db_profile_read",
     "orb_top2_merge", "orb_top2_merge_device", "orb_search_by_projection", "orb_match_bruteforce", "orb_stereo_match",
+    "orb_voc_create", "orb_voc_load_text", "orb_voc_destroy", "orb_voc_info", "orb_bow_transform_features",
+    "orb_bow_transform_features_device", "orb_bow_transform", "orb_bow_transform_device",
 ]
 
 _lib = None
@@ -96,6 +98,16 @@ def lib():
     L.orb_search_by_projection.argtypes = [i32, C.POINTER(SearchParams), vp, vp, vp, i32, vp, i32] + [vp] * 13 + [C.POINTER(i32)]
     L.orb_match_bruteforce.argtypes = [i32, vp, vp, i32, vp, vp, i32, i32, f32, i32, vp, C.POINTER(i32)]
     L.orb_stereo_match.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, f32, f32, vp, vp, C.POINTER(i32)]
+    pi32 = C.POINTER(i32)
+    L.orb_voc_create.argtypes = [C.POINTER(vp), i32, i32, i32, i32, i32, i32, vp, vp, vp, vp]
+    L.orb_voc_load_text.argtypes = [C.POINTER(vp), i32, C.c_char_p]
+    L.orb_voc_destroy.argtypes = [vp]
+    L.orb_voc_destroy.restype = None
+    L.orb_voc_info.argtypes = [vp] + [pi32] * 6
+    L.orb_bow_transform_features.argtypes = [vp, vp, i32, i32, vp, vp, vp]
+    L.orb_bow_transform_features_device.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp]
+    L.orb_bow_transform.argtypes = [vp, vp, vp, i32, i32] + [vp] * 7
+    L.orb_bow_transform_device.argtypes = [vp, vp, vp, i32, i32, i32, i32] + [vp] * 9
     L.orb_debug_sincos_range.argtypes = [i32, C.c_uint32, C.c_longlong, vp, vp]
     L.orb_bench_issue_rate.argtypes = [i32, i32, i32, C.POINTER(C.c_double)]
     _lib = L

@@ -171,3 +171,96 @@ def synth_queries(seed, db_total, nq, n_planted=None, max_flips=40):
     planted = np.full(nq, -1, np.int64)
     planted[:n_planted] = idx
     return q, planted, flips
+
+
+# ---- vocabulary trees (DBoW2 TemplatedVocabulary<FORB>; ORBvoc.txt is not reachable) -------------------
+def synth_vocabulary(seed, k=10, L=6, irregular=False, p_stop=0.0, p_dup=0.02, flips=48):
+    """A k-ary, depth-L vocabulary tree in DBoW2's node numbering (children of a node get consecutive ids when the
+    node is expanded, the tree is expanded level by level here): returns (parent, is_leaf, desc, weight) in node-id
+    order, node 0 = root.  A child's descriptor = its parent's with `flips` random bit flips (so the descent is
+    meaningful), with probability p_dup a copy of its previous sibling (exercises the first-minimum tie rule).
+    irregular: nodes get 2..k children and become leaves early with probability 0.15; p_stop: fraction of words
+    with weight 0 (stopped words).  Weights carry 6 significant digits, like saveToTextFile writes them."""
+    rng = _rng(seed ^ 0x5EED0B0)
+    if not irregular:
+        return _synth_vocabulary_regular(rng, k, L, p_stop, p_dup)
+    parent = [0]
+    depth = [0]
+    descs = [np.zeros(32, np.uint8)]
+    frontier = [0]
+    leaf = [False]
+    for level in range(1, L + 1):
+        nxt = []
+        for p in frontier:
+            nch = int(rng.integers(2, k + 1)) if irregular else k
+            base = rng.integers(0, 256, size=32, dtype=np.uint8) if p == 0 else descs[p]
+            prev = None
+            for c in range(nch):
+                if prev is not None and rng.random() < p_dup:
+                    d = prev.copy()
+                else:
+                    d = base.copy()
+                    bits = rng.choice(256, size=flips if p else 128, replace=False)
+                    np.bitwise_xor.at(d, bits >> 3, (1 << (bits & 7)).astype(np.uint8))
+                nid = len(parent)
+                parent.append(p); depth.append(level); descs.append(d)
+                stop_here = level == L or (irregular and rng.random() < 0.15)
+                leaf.append(stop_here)
+                if not stop_here:
+                    nxt.append(nid)
+                prev = d
+        frontier = nxt
+    n = len(parent)
+    parent = np.asarray(parent, np.int32)
+    is_leaf = np.asarray(leaf, np.uint8)
+    desc = np.stack(descs).astype(np.uint8)
+    weight = np.zeros(n, np.float64)
+    w = rng.uniform(0.5, 12.0, size=n)
+    w = np.asarray([float("%g" % x) for x in w])
+    weight[is_leaf == 1] = w[is_leaf == 1]
+    if p_stop > 0:
+        stop = (rng.random(n) < p_stop) & (is_leaf == 1)
+        weight[stop] = 0.0
+    return parent, is_leaf, desc, weight
+
+
+def _synth_vocabulary_regular(rng, k, L, p_stop, p_dup):
+    """Full k-ary tree, vectorised level by level (the ORBvoc shape k = 10, L = 6 has 1.1 M nodes): a child = its parent
+    with ~25 % of the bits flipped (AND of two random byte planes), or a copy of its previous sibling (p_dup)."""
+    parents, descs = [np.zeros(1, np.int32)], [np.zeros((1, 32), np.uint8)]
+    first = 1
+    prev_ids = np.zeros(1, np.int64)
+    prev_desc = rng.integers(0, 256, size=(1, 32), dtype=np.uint8)
+    for level in range(1, L + 1):
+        m = len(prev_ids)
+        par = np.repeat(prev_ids, k)
+        d = np.repeat(prev_desc, k, axis=0)
+        d ^= rng.integers(0, 256, size=d.shape, dtype=np.uint8) & rng.integers(0, 256, size=d.shape, dtype=np.uint8)
+        dup = (rng.random(m * k) < p_dup) & (np.arange(m * k) % k != 0)
+        idx = np.nonzero(dup)[0]
+        for i in idx:                      # sequential so that runs of duplicates copy the same ancestor
+            d[i] = d[i - 1]
+        ids = first + np.arange(m * k, dtype=np.int64)
+        parents.append(par.astype(np.int32)); descs.append(d)
+        first += m * k
+        prev_ids, prev_desc = ids, d
+    parent = np.concatenate(parents)
+    desc = np.concatenate(descs)
+    n = len(parent)
+    is_leaf = np.zeros(n, np.uint8)
+    is_leaf[n - len(prev_ids):] = 1
+    weight = np.zeros(n, np.float64)
+    w = np.round(rng.uniform(0.5, 12.0, size=len(prev_ids)), 4)
+    if p_stop > 0:
+        w[rng.random(len(prev_ids)) < p_stop] = 0.0
+    weight[n - len(prev_ids):] = w
+    return parent, is_leaf, desc, weight
+
+
+def write_vocabulary_text(path, k, L, scoring, weighting, parent, is_leaf, desc, weight):
+    """The reference's text format (TemplatedVocabulary::saveToTextFile, TemplatedVocabulary.h:1447-1467): header
+    `k L  scoring weighting`, then one line per node 1..n-1: `parent isLeaf d0 .. d31  weight`."""
+    with open(path, "w") as f:
+        f.write("%d %d  %d %d\n" % (k, L, scoring, weighting))
+        for i in range(1, len(parent)):
+            f.write("%d %d %s  %g\n" % (parent[i], 1 if is_leaf[i] else 0, " ".join(str(int(b)) for b in desc[i]), weight[i]))
