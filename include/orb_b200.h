@@ -11,6 +11,7 @@
  *   ORBmatcher::DescriptorDistance + best/2nd   ORBmatcher.cc:1649-1665, 202-227          -> orb_hamming_top2*
  *   ORBmatcher::SearchByProjection (Frame/Last) ORBmatcher.cc:45-129, 1330-1472           -> orb_search_by_projection
  *   ORBmatcher::SearchByBoW inner loop          ORBmatcher.cc:196-252                     -> orb_match_bruteforce
+ *   ORBmatcher::SearchByBoW (both overloads)    ORBmatcher.cc:160-289, 524-657            -> orb_search_by_bow
  *   Frame::ComputeStereoMatches                 Frame.cc:502-676                          -> orb_stereo_match
  *   ORBVocabulary::transform / loadFromTextFile DBoW2/TemplatedVocabulary.h:1140-1272, 1351 -> orb_bow_transform*, orb_voc_*
  *
@@ -201,6 +202,17 @@ int orb_search_by_projection(int device, const orb_search_params* prm, const orb
 int orb_match_bruteforce(int device, const uint8_t* desc1, const float* angle1, int n1, const uint8_t* desc2,
                          const float* angle2, int n2, int th_dist, float nn_ratio, int check_orientation,
                          int32_t* match12, int* nmatches);
+
+/* SearchByBoW over two FeatureVectors (ORBmatcher.cc:160-289 KeyFrame -> Frame: strict = 0, valid2 = NULL;
+ * ORBmatcher.cc:524-657 KeyFrame -> KeyFrame: strict = 1).  Feature vectors in the CSR form orb_bow_transform returns
+ * for one frame: node ids ascending, features of node j = fvX_feat[fvX_start[j] .. fvX_start[j+1]).  valid1[i] / valid2[j]
+ * (NULL = all): the keypoint holds a good map point.  Per shared node the queries are walked in list order, targets
+ * already matched are skipped, a match needs best <= th_dist (strict: <) and best < nn_ratio * second; then the
+ * rotation histogram filter.  match12[n1] = target index or -1, match21[n2] = query index or -1. */
+int orb_search_by_bow(int device, const uint8_t* desc1, const float* angle1, const uint8_t* valid1, int n1, const int32_t* fv1_node,
+                      const int32_t* fv1_start, const int32_t* fv1_feat, int nfv1, const uint8_t* desc2, const float* angle2,
+                      const uint8_t* valid2, int n2, const int32_t* fv2_node, const int32_t* fv2_start, const int32_t* fv2_feat, int nfv2,
+                      int th_dist, int strict, float nn_ratio, int check_orientation, int32_t* match12, int32_t* match21, int* nmatches);
 
 /* ---- stereo (Frame::ComputeStereoMatches, Frame.cc:502-676) ------------------------------------------ */
 /* ctx_left / ctx_right hold the pyramids of the last single-frame extract of the left / right image.

@@ -159,6 +159,12 @@ int orc_stereo_match(void* ex_left, void* ex_right, const orc_kp* kps_l, const u
                      const orc_kp* kps_r, const uint8_t* desc_r, int nr, const orc_stereo_params* prm,
                      float* u_right, float* depth, int32_t* best_sad);
 
+/* SearchByBoW over two FeatureVectors (ORBmatcher.cc:160-289 strict = 0, :524-657 strict = 1); see orb_oracle_match.cpp */
+int orc_search_by_bow(const uint8_t* desc1, const float* angle1, const uint8_t* valid1, int n1, const int32_t* fv1_node,
+                      const int32_t* fv1_start, const int32_t* fv1_feat, int nfv1, const uint8_t* desc2, const float* angle2,
+                      const uint8_t* valid2, int n2, const int32_t* fv2_node, const int32_t* fv2_start, const int32_t* fv2_feat,
+                      int nfv2, int th_dist, int strict, float nn_ratio, int check_orientation, int32_t* match12, int32_t* match21);
+
 /* ---------------- bag of words (DBoW2 TemplatedVocabulary<FORB>, orb_oracle_bow.cpp) ---------------- */
 /* nodes in id order (0 = root, TemplatedVocabulary.h:1389-1436); children = nodes with that parent in id order */
 void* orc_voc_create(int k, int L, int scoring, int weighting, int n_nodes, const int32_t* parent, const uint8_t* is_leaf,

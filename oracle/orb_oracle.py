@@ -88,6 +88,7 @@ def lib():
         L.orc_match_bruteforce.argtypes = [vp, vp, i32, vp, vp, i32, i32, f32, i32, vp]
         L.orc_stereo_match.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, C.POINTER(StereoParams), vp, vp, vp]
         f64 = C.c_double
+        L.orc_search_by_bow.argtypes = [vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, i32, i32, f32, i32, vp, vp]
         L.orc_voc_create.restype = vp
         L.orc_voc_create.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp, vp]
         L.orc_voc_load_text.restype = vp
@@ -390,3 +391,20 @@ def bow_score_l1(a, b):
     w1 = np.ascontiguousarray(w1, np.int32); w2 = np.ascontiguousarray(w2, np.int32)
     v1 = np.ascontiguousarray(v1, np.float64); v2 = np.ascontiguousarray(v2, np.float64)
     return float(lib().orc_bow_score_l1(_p(w1), _p(v1), len(w1), _p(w2), _p(v2), len(w2)))
+
+
+def search_by_bow(desc1, angle1, valid1, fv1, desc2, angle2, valid2, fv2, th_dist=50, strict=False, nn_ratio=0.6,
+                  check_orientation=True):
+    """fvX = (node, start, feat) CSR feature vectors.  -> (match12, match21, nmatches)"""
+    desc1 = _u8(desc1); desc2 = _u8(desc2)
+    n1, n2 = len(desc1), len(desc2)
+    angle1 = np.ascontiguousarray(angle1, np.float32); angle2 = np.ascontiguousarray(angle2, np.float32)
+    valid1 = None if valid1 is None else _u8(valid1)
+    valid2 = None if valid2 is None else _u8(valid2)
+    f1 = [np.ascontiguousarray(x, np.int32) for x in fv1]
+    f2 = [np.ascontiguousarray(x, np.int32) for x in fv2]
+    m12 = np.zeros(n1, np.int32); m21 = np.zeros(n2, np.int32)
+    nm = lib().orc_search_by_bow(_p(desc1), _p(angle1), _p(valid1), n1, _p(f1[0]), _p(f1[1]), _p(f1[2]), len(f1[0]),
+                                 _p(desc2), _p(angle2), _p(valid2), n2, _p(f2[0]), _p(f2[1]), _p(f2[2]), len(f2[0]),
+                                 th_dist, 1 if strict else 0, nn_ratio, 1 if check_orientation else 0, _p(m12), _p(m21))
+    return m12, m21, int(nm)

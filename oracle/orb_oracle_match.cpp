@@ -326,6 +326,63 @@ int orc_match_bruteforce(const uint8_t* desc1, const float* angle1, int n1, cons
     return nmatches;
 }
 
+/* SearchByBoW over FeatureVectors (OM:160-289 KeyFrame -> Frame, strict = 0; OM:524-657 KeyFrame -> KeyFrame, strict = 1).
+ * Feature vectors in CSR form: node ids ascending, features of node j = fvX_feat[fvX_start[j] .. fvX_start[j+1]).
+ * valid1[i]: the query keypoint holds a good map point (OM:196-202 / 562-566); valid2[j] (NULL = all): the target may be
+ * matched at all (OM:580-584, KeyFrame variant only).  A target already matched is skipped (OM:210 / 580).  Accept
+ * best <= th_dist (strict: <, OM:600) and (float)best < ratio * (float)second; rotation histogram on angle1 - angle2 and
+ * three-maxima filter.  match12[n1] = target index or -1; match21[n2] = query index or -1 (the final vpMapPointMatches
+ * of the Frame variant).  Returns nmatches. */
+int orc_search_by_bow(const uint8_t* desc1, const float* angle1, const uint8_t* valid1, int n1, const int32_t* fv1_node,
+                      const int32_t* fv1_start, const int32_t* fv1_feat, int nfv1, const uint8_t* desc2, const float* angle2,
+                      const uint8_t* valid2, int n2, const int32_t* fv2_node, const int32_t* fv2_start, const int32_t* fv2_feat,
+                      int nfv2, int th_dist, int strict, float nn_ratio, int check_orientation, int32_t* match12, int32_t* match21) {
+    for (int i = 0; i < n1; ++i) match12[i] = -1;
+    for (int j = 0; j < n2; ++j) match21[j] = -1;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    int nmatches = 0;
+    int a = 0, b = 0;
+    while (a < nfv1 && b < nfv2) {
+        if (fv1_node[a] == fv2_node[b]) {
+            for (int i1 = fv1_start[a]; i1 < fv1_start[a + 1]; ++i1) {
+                const int idx1 = fv1_feat[i1];
+                if (valid1 && !valid1[idx1]) continue;
+                const uint8_t* d1 = desc1 + (size_t)idx1 * 32;
+                int best1 = 256, bestIdx2 = -1, best2 = 256;
+                for (int i2 = fv2_start[b]; i2 < fv2_start[b + 1]; ++i2) {
+                    const int idx2 = fv2_feat[i2];
+                    if (match21[idx2] >= 0 || (valid2 && !valid2[idx2])) continue;
+                    const int dist = descriptor_distance(d1, desc2 + (size_t)idx2 * 32);
+                    if (dist < best1) { best2 = best1; best1 = dist; bestIdx2 = idx2; }
+                    else if (dist < best2) { best2 = dist; }
+                }
+                if (strict ? (best1 < th_dist) : (best1 <= th_dist)) {
+                    if ((float)best1 < nn_ratio * (float)best2) {
+                        match12[idx1] = bestIdx2;
+                        match21[bestIdx2] = idx1;
+                        if (check_orientation) rotHist[rot_bin(angle1[idx1], angle2[bestIdx2])].push_back(idx1);
+                        nmatches++;
+                    }
+                }
+            }
+            ++a; ++b;
+        } else if (fv1_node[a] < fv2_node[b]) {
+            while (a < nfv1 && fv1_node[a] < fv2_node[b]) ++a;   /* lower_bound */
+        } else {
+            while (b < nfv2 && fv2_node[b] < fv1_node[a]) ++b;
+        }
+    }
+    if (check_orientation) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int h = 0; h < HISTO_LENGTH; ++h) {
+            if (h == ind1 || h == ind2 || h == ind3) continue;
+            for (int idx1 : rotHist[h]) { match21[match12[idx1]] = -1; match12[idx1] = -1; nmatches--; }
+        }
+    }
+    return nmatches;
+}
+
 /* FR:502-676 */
 int orc_stereo_match(void* exL, void* exR, const orc_kp* kpsL, const uint8_t* descL, int N, const orc_kp* kpsR,
                      const uint8_t* descR, int Nr, const orc_stereo_params* prm, float* mvuRight, float* mvDepth,

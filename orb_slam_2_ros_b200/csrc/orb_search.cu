@@ -597,6 +597,85 @@ csr_top2_kernel(const uint8_t* __restrict__ q, int nq, const uint8_t* __restrict
     }
 }
 
+// =============================== SearchByBoW over two FeatureVectors ===============================================
+// (ORBmatcher.cc:160-289 KeyFrame -> Frame, :524-657 KeyFrame -> KeyFrame.)  A keypoint belongs to exactly one
+// vocabulary node, so the "target already matched" state never crosses nodes: ONE WARP PER SHARED NODE walks the
+// node's query features in order (the sequential part), the 32 lanes score the node's free targets in parallel and
+// reduce to best / second with key = dist << 16 | position in the node's list (strict '<': first in list order wins).
+__global__ void __launch_bounds__(256)
+bow_match_kernel(const uint8_t* __restrict__ d1, const uint8_t* __restrict__ valid1, const int* __restrict__ fv1_node,
+                 const int* __restrict__ fv1_start, const int* __restrict__ fv1_feat, int nfv1, const uint8_t* __restrict__ d2,
+                 const uint8_t* __restrict__ valid2, const int* __restrict__ fv2_node, const int* __restrict__ fv2_start,
+                 const int* __restrict__ fv2_feat, int nfv2, int th_dist, int strict, float nn_ratio, int* match12, int* match21) {
+    const int lane = threadIdx.x & 31;
+    const int a = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (a >= nfv1) return;
+    const int node = fv1_node[a];
+    int lo = 0, hi = nfv2;                                   // lower_bound of the node id in the other vector
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (fv2_node[mid] < node) lo = mid + 1; else hi = mid;
+    }
+    if (lo >= nfv2 || fv2_node[lo] != node) return;
+    const int s2 = fv2_start[lo], c2 = fv2_start[lo + 1] - s2;
+    for (int i1 = fv1_start[a]; i1 < fv1_start[a + 1]; ++i1) {
+        const int idx1 = fv1_feat[i1];
+        if (valid1 && !valid1[idx1]) continue;
+        const uint4* dq = reinterpret_cast<const uint4*>(d1 + (size_t)idx1 * 32);
+        unsigned k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
+        for (int p = lane; p < c2; p += 32) {
+            const int idx2 = fv2_feat[s2 + p];
+            if (match21[idx2] >= 0 || (valid2 && !valid2[idx2])) continue;
+            const unsigned k = ((unsigned)dist256(dq, reinterpret_cast<const uint4*>(d2 + (size_t)idx2 * 32)) << 16) | (unsigned)p;
+            k2 = min(k2, max(k, k1));
+            k1 = min(k1, k);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned b1 = __shfl_xor_sync(0xffffffffu, k1, o), b2 = __shfl_xor_sync(0xffffffffu, k2, o);
+            const unsigned l = min(k1, b1), h = max(k1, b1);
+            k2 = min(h, min(k2, b2));
+            k1 = l;
+        }
+        const int best1 = k1 == 0xFFFFFFFFu ? 256 : (int)(k1 >> 16), best2 = k2 == 0xFFFFFFFFu ? 256 : (int)(k2 >> 16);
+        if ((strict ? best1 < th_dist : best1 <= th_dist) && (float)best1 < __fmul_rn(nn_ratio, (float)best2)) {
+            const int idx2 = fv2_feat[s2 + (int)(k1 & 0xFFFFu)];
+            if (lane == 0) { match12[idx1] = idx2; match21[idx2] = idx1; }
+        }
+        __syncwarp();   // the commit is visible to every lane's next scan of match21
+    }
+}
+
+// rotation histogram + three-maxima filter over the finished matches (ORBmatcher.cc:236-247, 268-285): one CTA
+__global__ void __launch_bounds__(1024)
+bow_rot_kernel(const float* __restrict__ angle1, const float* __restrict__ angle2, int n1, int check_ori, int* match12, int* match21,
+               int* nmatches_out) {
+    __shared__ int hist[HISTO_LENGTH];
+    __shared__ int s_n;
+    if (threadIdx.x < HISTO_LENGTH) hist[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    int cnt = 0;
+    for (int i = threadIdx.x; i < n1; i += blockDim.x) {
+        const int m = match12[i];
+        if (m >= 0) { ++cnt; if (check_ori) atomicAdd(&hist[rot_bin(angle1[i], angle2[m])], 1); }
+    }
+    __syncthreads();
+    if (check_ori) {
+        int ind1, ind2, ind3;
+        three_maxima(hist, ind1, ind2, ind3);
+        for (int i = threadIdx.x; i < n1; i += blockDim.x) {
+            const int m = match12[i];
+            if (m < 0) continue;
+            const int bin = rot_bin(angle1[i], angle2[m]);
+            if (bin != ind1 && bin != ind2 && bin != ind3) { match21[m] = -1; match12[i] = -1; --cnt; }
+        }
+    }
+    atomicAdd(&s_n, cnt);
+    __syncthreads();
+    if (threadIdx.x == 0) *nmatches_out = s_n;
+}
+
 // Per-thread, per-device workspace of the host-pointer entry points: one grow-only device slab, one grow-only pinned
 // slab and a private stream.  A call packs all its inputs into the pinned slab, issues ONE H2D copy, the kernels and
 // ONE D2H copy, and synchronises once — no cudaMalloc / cudaFree on the call path.
@@ -808,6 +887,61 @@ int orb_match_bruteforce(int device, const uint8_t* desc1, const float* angle1, 
     ORB_CUDA(cudaMemcpyAsync(H + o_m12, Dv + o_m12, io_bytes - o_m12, cudaMemcpyDeviceToHost, st));
     ORB_CUDA(cudaStreamSynchronize(st));
     memcpy(match12, H + o_m12, 4 * (size_t)n1);
+    *nmatches = *(const int*)(H + o_nm);
+    return ORB_OK;
+}
+
+int orb_search_by_bow(int device, const uint8_t* desc1, const float* angle1, const uint8_t* valid1, int n1, const int32_t* fv1_node,
+                      const int32_t* fv1_start, const int32_t* fv1_feat, int nfv1, const uint8_t* desc2, const float* angle2,
+                      const uint8_t* valid2, int n2, const int32_t* fv2_node, const int32_t* fv2_start, const int32_t* fv2_feat, int nfv2,
+                      int th_dist, int strict, float nn_ratio, int check_orientation, int32_t* match12, int32_t* match21, int* nmatches) {
+    if (n1 < 0 || n2 < 0 || nfv1 < 0 || nfv2 < 0 || !nmatches || (n1 && (!desc1 || !match12)) || (n2 && (!desc2 || !match21))) return ORB_ERR_INVALID;
+    if ((nfv1 && (!fv1_node || !fv1_start || !fv1_feat)) || (nfv2 && (!fv2_node || !fv2_start || !fv2_feat))) return ORB_ERR_INVALID;
+    if (check_orientation && ((n1 && !angle1) || (n2 && !angle2))) return ORB_ERR_INVALID;
+    *nmatches = 0;
+    for (int i = 0; i < n1; ++i) match12[i] = -1;
+    for (int j = 0; j < n2; ++j) match21[j] = -1;
+    if (n1 == 0 || n2 == 0 || nfv1 == 0 || nfv2 == 0) return ORB_OK;
+    const int nf1 = fv1_start[nfv1], nf2 = fv2_start[nfv2];
+    if (nf1 < 0 || nf1 > n1 || nf2 < 0 || nf2 > n2) { orb_set_error("orb_search_by_bow: feature vector larger than the keypoint set"); return ORB_ERR_INVALID; }
+    for (int i = 0; i < nf1; ++i) if (fv1_feat[i] < 0 || fv1_feat[i] >= n1) { orb_set_error("orb_search_by_bow: fv1_feat out of range"); return ORB_ERR_INVALID; }
+    for (int i = 0; i < nf2; ++i) if (fv2_feat[i] < 0 || fv2_feat[i] >= n2) { orb_set_error("orb_search_by_bow: fv2_feat out of range"); return ORB_ERR_INVALID; }
+    for (int j = 0; j < nfv2; ++j) if (fv2_start[j + 1] - fv2_start[j] > 65535) { orb_set_error("orb_search_by_bow: more than 65535 features in one node"); return ORB_ERR_CAPACITY; }
+    if (orb_device_count() <= 0) { orb_set_error("no CUDA device visible: liborb_b200 has no CPU fallback"); return ORB_ERR_NO_DEVICE; }
+    Carver c;
+    const size_t o_d1 = c.take((size_t)32 * n1), o_d2 = c.take((size_t)32 * n2), o_a1 = c.take(4 * (size_t)n1), o_a2 = c.take(4 * (size_t)n2);
+    const size_t o_v1 = c.take(n1), o_v2 = c.take(n2);
+    const size_t o_n1 = c.take(4 * (size_t)nfv1), o_s1 = c.take(4 * ((size_t)nfv1 + 1)), o_f1 = c.take(4 * (size_t)std::max(nf1, 1));
+    const size_t o_n2 = c.take(4 * (size_t)nfv2), o_s2 = c.take(4 * ((size_t)nfv2 + 1)), o_f2 = c.take(4 * (size_t)std::max(nf2, 1));
+    const size_t o_m12 = c.take(4 * (size_t)n1), o_m21 = c.take(4 * (size_t)n2);   // initialised to -1 on the host: part of the upload
+    const size_t in_bytes = c.off;
+    const size_t o_nm = c.take(16);
+    const size_t io_bytes = c.off;
+    Workspace& W = g_ws;
+    int rc = W.prepare(device, io_bytes, io_bytes);
+    if (rc != ORB_OK) return rc;
+    cudaStream_t st = W.st;
+    uint8_t *H = W.h, *Dv = W.d;
+    memcpy(H + o_d1, desc1, (size_t)32 * n1); memcpy(H + o_d2, desc2, (size_t)32 * n2);
+    if (angle1) memcpy(H + o_a1, angle1, 4 * (size_t)n1);
+    if (angle2) memcpy(H + o_a2, angle2, 4 * (size_t)n2);
+    if (valid1) memcpy(H + o_v1, valid1, n1);
+    if (valid2) memcpy(H + o_v2, valid2, n2);
+    memcpy(H + o_n1, fv1_node, 4 * (size_t)nfv1); memcpy(H + o_s1, fv1_start, 4 * ((size_t)nfv1 + 1)); memcpy(H + o_f1, fv1_feat, 4 * (size_t)nf1);
+    memcpy(H + o_n2, fv2_node, 4 * (size_t)nfv2); memcpy(H + o_s2, fv2_start, 4 * ((size_t)nfv2 + 1)); memcpy(H + o_f2, fv2_feat, 4 * (size_t)nf2);
+    memset(H + o_m12, 0xFF, 4 * (size_t)n1); memset(H + o_m21, 0xFF, 4 * (size_t)n2);
+    ORB_CUDA(cudaMemcpyAsync(Dv, H, in_bytes, cudaMemcpyHostToDevice, st));
+    bow_match_kernel<<<(nfv1 + 7) / 8, 256, 0, st>>>(Dv + o_d1, valid1 ? Dv + o_v1 : nullptr, (const int*)(Dv + o_n1), (const int*)(Dv + o_s1),
+                                                     (const int*)(Dv + o_f1), nfv1, Dv + o_d2, valid2 ? Dv + o_v2 : nullptr, (const int*)(Dv + o_n2),
+                                                     (const int*)(Dv + o_s2), (const int*)(Dv + o_f2), nfv2, th_dist, strict, nn_ratio,
+                                                     (int*)(Dv + o_m12), (int*)(Dv + o_m21));
+    bow_rot_kernel<<<1, 1024, 0, st>>>((const float*)(Dv + o_a1), (const float*)(Dv + o_a2), n1, check_orientation, (int*)(Dv + o_m12),
+                                       (int*)(Dv + o_m21), (int*)(Dv + o_nm));
+    ORB_CUDA(cudaGetLastError());
+    ORB_CUDA(cudaMemcpyAsync(H + o_m12, Dv + o_m12, io_bytes - o_m12, cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaStreamSynchronize(st));
+    memcpy(match12, H + o_m12, 4 * (size_t)n1);
+    memcpy(match21, H + o_m21, 4 * (size_t)n2);
     *nmatches = *(const int*)(H + o_nm);
     return ORB_OK;
 }

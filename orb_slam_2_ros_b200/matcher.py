@@ -73,6 +73,21 @@ class ORBmatcher:
         return nm.value, m
 
 
+    def SearchByBoW(self, desc1, angle1, valid1, fv1, desc2, angle2, valid2, fv2, keyframe_pair=False, th_dist=TH_LOW):
+        """ORBmatcher::SearchByBoW: KeyFrame -> Frame (ORBmatcher.cc:160-289; valid2 = None) or, keyframe_pair=True,
+        KeyFrame -> KeyFrame (ORBmatcher.cc:524-657: strict '<' on TH_LOW, targets need a good map point too).
+        fvX = (node, start, feat), the FeatureVector ORBVocabulary.transform returns.  -> nmatches, match12, match21"""
+        desc1, desc2, angle1, angle2 = _b(desc1), _b(desc2), _f(angle1), _f(angle2)
+        valid1, valid2 = _b(valid1), _b(valid2)
+        f1 = [_i(x) for x in fv1]; f2 = [_i(x) for x in fv2]
+        n1, n2 = len(desc1), len(desc2)
+        m12 = np.full(n1, -1, np.int32); m21 = np.full(n2, -1, np.int32); nm = C.c_int32(0)
+        check(lib().orb_search_by_bow(self.device, ptr(desc1), ptr(angle1), ptr(valid1), n1, ptr(f1[0]), ptr(f1[1]), ptr(f1[2]), len(f1[0]),
+                                      ptr(desc2), ptr(angle2), ptr(valid2), n2, ptr(f2[0]), ptr(f2[1]), ptr(f2[2]), len(f2[0]),
+                                      th_dist, 1 if keyframe_pair else 0, self.mfNNratio, int(self.mbCheckOrientation), ptr(m12), ptr(m21),
+                                      C.byref(nm)))
+        return nm.value, m12, m21
+
 def hamming_top2(q, db, device=0):
     """Brute-force best / second-best (ORBmatcher.cc:202-227 update rule) of each query over db (host arrays)."""
     q, db = _b(q), _b(db)

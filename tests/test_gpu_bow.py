@@ -103,3 +103,32 @@ def test_orbvoc_shape_extracted_frame(oracle):
     _same_vectors(gv.transform(desc, 4), ov.transform(desc, 4))
     q = _queries(P, 4000, seed=3)
     _same_vectors(gv.transform(q, 4), ov.transform(q, 4))
+
+
+@pytest.mark.parametrize("keyframe_pair,check_ori,ratio", [(False, True, 0.7), (True, True, 0.75), (False, False, 0.9), (True, False, 0.6)])
+def test_search_by_bow_vs_oracle(oracle, keyframe_pair, check_ori, ratio):
+    """ORBmatcher::SearchByBoW (ORBmatcher.cc:160-289 / 524-657) over the FeatureVectors of two extracted frames."""
+    from orb_slam_2_ros_b200 import ORBextractor, ORBmatcher, ORBVocabulary
+    P = synth.synth_vocabulary(21, k=10, L=5)
+    gv = ORBVocabulary.from_arrays(10, 5, 0, 0, *P)
+    ex = ORBextractor(1000, 1.2, 8, 20, 7)
+    a = synth.synth_frame(4, 640, 480)
+    b = np.roll(a, (2, -3), axis=(0, 1))
+    rng = np.random.default_rng(8)
+    noise = rng.random(b.shape) < 0.02
+    b = np.where(noise, rng.integers(0, 256, b.shape), b).astype(np.uint8)
+    k1, d1 = ex(a)
+    k2, d2 = ex(b)
+    for levelsup in (4, 3, 5):      # 5 = root: one node holding everything
+        (_, fv1), (_, fv2) = gv.transform_batch([d1, d2], levelsup)
+        valid1 = (rng.random(len(d1)) < 0.8).astype(np.uint8)
+        valid2 = (rng.random(len(d2)) < 0.9).astype(np.uint8) if keyframe_pair else None
+        m = ORBmatcher(ratio, check_ori)
+        nm, m12, m21 = m.SearchByBoW(d1, k1["angle"], valid1, fv1, d2, k2["angle"], valid2, fv2, keyframe_pair=keyframe_pair)
+        o12, o21, onm = oracle.search_by_bow(d1, k1["angle"], valid1, fv1, d2, k2["angle"], valid2, fv2, 50, keyframe_pair, ratio, check_ori)
+        assert nm == onm and np.array_equal(m12, o12) and np.array_equal(m21, o21)
+        assert levelsup == 5 or nm > 50
+    # degenerate inputs
+    empty = (np.zeros(0, np.int32), np.zeros(1, np.int32), np.zeros(0, np.int32))
+    nm, m12, m21 = ORBmatcher(0.7, True).SearchByBoW(d1, k1["angle"], None, fv1, d2, k2["angle"], None, empty)
+    assert nm == 0 and (m12 == -1).all() and (m21 == -1).all()

@@ -132,3 +132,21 @@ def test_score_l1(oracle):
     expect = -((abs(0.25 - 0.5) - 0.25 - 0.5) + (abs(0.25 - 0.1) - 0.25 - 0.1)) / 2.0
     assert oracle.bow_score_l1(a, b) == expect
     assert oracle.bow_score_l1(a, a) == 1.0
+
+
+def test_search_by_bow_single_node_equals_bruteforce(oracle):
+    """With one node holding every keypoint, SearchByBoW is the brute-force inner loop (ORBmatcher.cc:196-252)."""
+    rng = np.random.default_rng(3)
+    d2 = rng.integers(0, 256, (300, 32), dtype=np.uint8)
+    d1 = d2[rng.permutation(300)[:200]].copy()
+    d1[:, 0] ^= rng.integers(0, 4, 200, dtype=np.uint8)
+    a1 = rng.uniform(0, 360, 200).astype(np.float32); a2 = rng.uniform(0, 360, 300).astype(np.float32)
+    fv1 = (np.array([7]), np.array([0, 200]), np.arange(200))
+    fv2 = (np.array([7]), np.array([0, 300]), np.arange(300))
+    m12, m21, nm = oracle.search_by_bow(d1, a1, None, fv1, d2, a2, None, fv2, 50, False, 0.6, True)
+    nm2, b12 = oracle.match_bruteforce(d1, a1, d2, a2, 50, 0.6, True)
+    assert nm == nm2 and np.array_equal(m12, b12)
+    assert all(m21[m12[i]] == i for i in range(200) if m12[i] >= 0)
+    # disjoint node ids: nothing is compared
+    fv2b = (np.array([8]), np.array([0, 300]), np.arange(300))
+    assert oracle.search_by_bow(d1, a1, None, fv1, d2, a2, None, fv2b)[2] == 0
