@@ -82,6 +82,30 @@ int ORBmatcher::MatchNode(const uint8_t* desc1, const float* angle1, int n1, con
     return nmatches;
 }
 
+static void flatten(const DBoW2::FeatureVector& fv, std::vector<int32_t>& node, std::vector<int32_t>& start, std::vector<int32_t>& feat) {
+    node.clear(); start.assign(1, 0); feat.clear();
+    for (DBoW2::FeatureVector::const_iterator it = fv.begin(); it != fv.end(); ++it) {
+        node.push_back((int32_t)it->first);
+        feat.insert(feat.end(), it->second.begin(), it->second.end());
+        start.push_back((int32_t)feat.size());
+    }
+}
+
+int ORBmatcher::SearchByBoW(const uint8_t* desc1, const float* angle1, const uint8_t* valid1, int n1, const DBoW2::FeatureVector& fv1,
+                            const uint8_t* desc2, const float* angle2, const uint8_t* valid2, int n2, const DBoW2::FeatureVector& fv2,
+                            bool keyframePair, std::vector<int32_t>& match12, std::vector<int32_t>& match21) const {
+    std::vector<int32_t> n1v, s1v, f1v, n2v, s2v, f2v;
+    flatten(fv1, n1v, s1v, f1v);
+    flatten(fv2, n2v, s2v, f2v);
+    match12.assign(n1, -1);
+    match21.assign(n2, -1);
+    int nmatches = 0;
+    check(orb_search_by_bow(device_, desc1, angle1, valid1, n1, n1v.data(), s1v.data(), f1v.data(), (int)n1v.size(), desc2, angle2, valid2, n2,
+                            n2v.data(), s2v.data(), f2v.data(), (int)n2v.size(), TH_LOW, keyframePair ? 1 : 0, mfNNratio,
+                            mbCheckOrientation ? 1 : 0, match12.data(), match21.data(), &nmatches), "orb_search_by_bow");
+    return nmatches;
+}
+
 int ComputeStereoMatches(ORBextractor& left, ORBextractor& right, const std::vector<cv::KeyPoint>& keysL, const cv::Mat& descL,
                          const std::vector<cv::KeyPoint>& keysR, const cv::Mat& descR, float bf, float b,
                          std::vector<float>& mvuRight, std::vector<float>& mvDepth) {

@@ -8,6 +8,7 @@
 #include <cstdint>
 #include <vector>
 
+#include "ORBVocabulary.h"
 #include "cv_compat.h"
 
 namespace ORB_SLAM2 {
@@ -45,6 +46,13 @@ public:
     // inner loop of SearchByBoW over one vocabulary node (ORBmatcher.cc:196-252)
     int MatchNode(const uint8_t* desc1, const float* angle1, int n1, const uint8_t* desc2, const float* angle2, int n2, int thDist,
                   std::vector<int32_t>& match12) const;
+
+    // SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches) ORBmatcher.cc:160-289 (keyframePair = false, valid2 = NULL) and
+    // SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12)     ORBmatcher.cc:524-657 (keyframePair = true): valid1 / valid2 = the
+    // keypoint holds a good map point; match12[i] = index in set 2 or -1, match21[j] = index in set 1 or -1
+    int SearchByBoW(const uint8_t* desc1, const float* angle1, const uint8_t* valid1, int n1, const DBoW2::FeatureVector& fv1,
+                    const uint8_t* desc2, const float* angle2, const uint8_t* valid2, int n2, const DBoW2::FeatureVector& fv2,
+                    bool keyframePair, std::vector<int32_t>& match12, std::vector<int32_t>& match21) const;
 
     static const int TH_LOW = 50;
     static const int TH_HIGH = 100;

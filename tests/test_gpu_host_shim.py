@@ -68,3 +68,47 @@ def test_cpp_stereo_shim_matches_oracle(oracle, tmp_path):
     assert got["nmatches"] == kept and kept > 100
     assert np.array_equal(got["u_right"].view(np.uint32), ur.view(np.uint32))
     assert np.array_equal(got["depth"].view(np.uint32), depth.view(np.uint32))
+
+
+def test_cpp_vocabulary_and_search_by_bow(oracle, tmp_path):
+    """ORBVocabulary::loadFromTextFile + transform (Frame::ComputeBoW) + ORBmatcher::SearchByBoW through the C++ mirror."""
+    w, h = 640, 480
+    a = synth.synth_frame(31, w, h)
+    b = np.roll(a, (1, 2), axis=(0, 1))
+    P = synth.synth_vocabulary(5, k=10, L=5)
+    voc_path = str(tmp_path / "voc.txt")
+    synth.write_vocabulary_text(voc_path, 10, 5, 0, 0, *P)
+    (tmp_path / "a.raw").write_bytes(a.tobytes()); (tmp_path / "b.raw").write_bytes(b.tobytes())
+    subprocess.check_call([EXE, "bow", voc_path, str(w), str(h), str(tmp_path / "a.raw"), str(tmp_path / "b.raw"), str(tmp_path / "o.bin")])
+    raw = open(tmp_path / "o.bin", "rb").read()
+    off = 0
+
+    def take(dtype, count):
+        nonlocal off
+        x = np.frombuffer(raw, dtype, count, off)
+        off += x.nbytes
+        return x
+    ov = oracle.Vocabulary.load_text(voc_path)
+    ex = oracle.Extractor(1000, 1.2, 8, 20, 7)
+    frames = []
+    for img in (a, b):
+        okps, odesc = ex.extract(img)
+        n = int(take(np.int32, 1)[0]); desc = take(np.uint8, n * 32).reshape(n, 32)
+        assert np.array_equal(desc, odesc)
+        (obw, obv), (ofn, ofs, off_) = ov.transform(odesc, 4)
+        nb = int(take(np.int32, 1)[0])
+        rec = take(np.dtype([("w", "<u4"), ("v", "<f8")]), nb)
+        assert np.array_equal(rec["w"], obw) and np.array_equal(rec["v"].view(np.uint64), obv.view(np.uint64))
+        nf = int(take(np.int32, 1)[0])
+        assert nf == len(ofn)
+        for j in range(nf):
+            node, cnt = take(np.uint32, 1)[0], int(take(np.int32, 1)[0])
+            feats = take(np.uint32, cnt)
+            assert node == ofn[j] and np.array_equal(feats, off_[ofs[j]:ofs[j + 1]])
+        frames.append((okps, odesc, (ofn, ofs, off_)))
+    nm = int(take(np.int32, 1)[0])
+    m12 = take(np.int32, len(frames[0][1])); m21 = take(np.int32, len(frames[1][1]))
+    assert off == len(raw)
+    o12, o21, onm = oracle.search_by_bow(frames[0][1], frames[0][0]["angle"], None, frames[0][2], frames[1][1], frames[1][0]["angle"], None,
+                                         frames[1][2], 50, False, np.float32(0.7), True)
+    assert nm == onm and nm > 100 and np.array_equal(m12, o12) and np.array_equal(m21, o21)
