@@ -12,6 +12,9 @@
  *   ORBmatcher::SearchByProjection (Frame/Last) ORBmatcher.cc:45-129, 1330-1472           -> orb_search_by_projection
  *   ORBmatcher::SearchByBoW inner loop          ORBmatcher.cc:196-252                     -> orb_match_bruteforce
  *   ORBmatcher::SearchByBoW (both overloads)    ORBmatcher.cc:160-289, 524-657            -> orb_search_by_bow
+ *   ORBmatcher::SearchForTriangulation          ORBmatcher.cc:659-825                     -> orb_search_for_triangulation
+ *   ORBmatcher::SearchBySim3                    ORBmatcher.cc:1104-1328                   -> orb_search_by_sim3
+ *   MapPoint::ComputeDistinctiveDescriptors     MapPoint.cc:288-361                       -> orb_distinctive_descriptors
  *   Frame::ComputeStereoMatches                 Frame.cc:502-676                          -> orb_stereo_match
  *   ORBVocabulary::transform / loadFromTextFile DBoW2/TemplatedVocabulary.h:1140-1272, 1351 -> orb_bow_transform*, orb_voc_*
  *
@@ -213,6 +216,36 @@ int orb_search_by_bow(int device, const uint8_t* desc1, const float* angle1, con
                       const int32_t* fv1_start, const int32_t* fv1_feat, int nfv1, const uint8_t* desc2, const float* angle2,
                       const uint8_t* valid2, int n2, const int32_t* fv2_node, const int32_t* fv2_start, const int32_t* fv2_feat, int nfv2,
                       int th_dist, int strict, float nn_ratio, int check_orientation, int32_t* match12, int32_t* match21, int* nmatches);
+
+/* ORBmatcher::SearchForTriangulation (ORBmatcher.cc:659-825) on arrays.  has_mpX[i] != 0: the keypoint already holds a map
+ * point (skipped); u_rightX (NULL = monocular): bStereo = u_right >= 0; F12 row-major 3x3; (ex, ey) = epipole of camera 1 in
+ * image 2 (ORBmatcher.cc:665-673); scale_factors / level_sigma2 = pKF2->mvScaleFactors / mvLevelSigma2 (nlevels entries).
+ * Per shared vocabulary node every query keeps the target with the smallest distance <= TH_LOW that passes the epipole and
+ * epipolar-line gates (CheckDistEpipolarLine, :140-157), the last one in list order on equal distances (:741); no target is
+ * ever marked as taken (the reference never sets vbMatched2); rotation histogram filter.  match12[n1] = vMatches12. */
+int orb_search_for_triangulation(int device, const orb_kp* kps1, const uint8_t* desc1, const uint8_t* has_mp1, const float* u_right1, int n1,
+                                 const int32_t* fv1_node, const int32_t* fv1_start, const int32_t* fv1_feat, int nfv1, const orb_kp* kps2,
+                                 const uint8_t* desc2, const uint8_t* has_mp2, const float* u_right2, int n2, const int32_t* fv2_node,
+                                 const int32_t* fv2_start, const int32_t* fv2_feat, int nfv2, const float* F12, float ex, float ey,
+                                 const float* scale_factors, const float* level_sigma2, int nlevels, int only_stereo, int check_orientation,
+                                 int32_t* match12, int* nmatches);
+
+/* ORBmatcher::SearchBySim3 (ORBmatcher.cc:1104-1328) on arrays.  boundsX = {mnMinX, mnMinY, mnMaxX, mnMaxY} of keyframe X.
+ * q12_*[n1]: the map point of keypoint i of keyframe 1 projected into keyframe 2 — (u, v), radius = th * scale[pred], predicted
+ * level, descriptor; q12_valid[i] = 0 for the entries the reference skips (no / bad / already matched map point, negative
+ * depth, outside the image or the scale-invariance range; NULL = all valid).  q21_*[n2] likewise.  Each direction keeps the
+ * best candidate of GetFeaturesInArea with octave in [pred-1, pred] when its distance <= th_dist (TH_HIGH); match12[i] is set
+ * when both directions agree (:1282-1299). */
+int orb_search_by_sim3(int device, const orb_kp* kps1_un, const uint8_t* desc1, int n1, const float* bounds1, const orb_kp* kps2_un,
+                       const uint8_t* desc2, int n2, const float* bounds2, const float* q12_u, const float* q12_v, const float* q12_radius,
+                       const int32_t* q12_level, const uint8_t* q12_desc, const uint8_t* q12_valid, const float* q21_u, const float* q21_v,
+                       const float* q21_radius, const int32_t* q21_level, const uint8_t* q21_desc, const uint8_t* q21_valid, int th_dist,
+                       int32_t* match12, int* nfound);
+
+/* MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:288-361) for npoints map points at once: the observed descriptors of
+ * point p are rows [off[p], off[p+1]) (off[0] == 0); best_idx[p] = the row (within the point) with the least median distance to
+ * the others, first on ties, -1 without observations; best_desc32 (may be NULL) receives that descriptor. */
+int orb_distinctive_descriptors(int device, const uint8_t* desc32, const int32_t* off, int npoints, int32_t* best_idx, uint8_t* best_desc32);
 
 /* ---- stereo (Frame::ComputeStereoMatches, Frame.cc:502-676) ------------------------------------------ */
 /* ctx_left / ctx_right hold the pyramids of the last single-frame extract of the left / right image.

@@ -165,6 +165,18 @@ int orc_search_by_bow(const uint8_t* desc1, const float* angle1, const uint8_t* 
                       const uint8_t* valid2, int n2, const int32_t* fv2_node, const int32_t* fv2_start, const int32_t* fv2_feat,
                       int nfv2, int th_dist, int strict, float nn_ratio, int check_orientation, int32_t* match12, int32_t* match21);
 
+/* SearchForTriangulation (ORBmatcher.cc:659-825), one direction of SearchBySim3 (:1150-1213) and
+ * MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:288-361) on arrays; see orb_oracle_match.cpp */
+int orc_search_for_triangulation(const orc_kp* kps1, const uint8_t* desc1, const uint8_t* has_mp1, const float* u_right1, int n1,
+                                 const int32_t* fv1_node, const int32_t* fv1_start, const int32_t* fv1_feat, int nfv1,
+                                 const orc_kp* kps2, const uint8_t* desc2, const uint8_t* has_mp2, const float* u_right2, int n2,
+                                 const int32_t* fv2_node, const int32_t* fv2_start, const int32_t* fv2_feat, int nfv2, const float* F12,
+                                 float ex, float ey, const float* scale_factors, const float* level_sigma2, int only_stereo,
+                                 int check_orientation, int32_t* match12);
+void orc_sim3_search_one_way(void* grid, const orc_kp* kps_un, const uint8_t* desc, int nq, const float* q_u, const float* q_v,
+                             const float* q_radius, const int32_t* q_level, const uint8_t* q_desc, const uint8_t* q_valid, int32_t* match);
+void orc_distinctive_descriptors(const uint8_t* desc, const int32_t* off, int npoints, int32_t* best);
+
 /* ---------------- bag of words (DBoW2 TemplatedVocabulary<FORB>, orb_oracle_bow.cpp) ---------------- */
 /* nodes in id order (0 = root, TemplatedVocabulary.h:1389-1436); children = nodes with that parent in id order */
 void* orc_voc_create(int k, int L, int scoring, int weighting, int n_nodes, const int32_t* parent, const uint8_t* is_leaf,

@@ -88,6 +88,11 @@ def lib():
         L.orc_match_bruteforce.argtypes = [vp, vp, i32, vp, vp, i32, i32, f32, i32, vp]
         L.orc_stereo_match.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, C.POINTER(StereoParams), vp, vp, vp]
         f64 = C.c_double
+        L.orc_search_for_triangulation.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, i32, vp, f32, f32, vp, vp, i32, i32, vp]
+        L.orc_sim3_search_one_way.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]
+        L.orc_sim3_search_one_way.restype = None
+        L.orc_distinctive_descriptors.argtypes = [vp, vp, i32, vp]
+        L.orc_distinctive_descriptors.restype = None
         L.orc_search_by_bow.argtypes = [vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, i32, i32, f32, i32, vp, vp]
         L.orc_voc_create.restype = vp
         L.orc_voc_create.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp, vp]
@@ -408,3 +413,55 @@ def search_by_bow(desc1, angle1, valid1, fv1, desc2, angle2, valid2, fv2, th_dis
                                  _p(desc2), _p(angle2), _p(valid2), n2, _p(f2[0]), _p(f2[1]), _p(f2[2]), len(f2[0]),
                                  th_dist, 1 if strict else 0, nn_ratio, 1 if check_orientation else 0, _p(m12), _p(m21))
     return m12, m21, int(nm)
+
+
+def _f32(a):
+    return None if a is None else np.ascontiguousarray(a, np.float32)
+
+
+def search_for_triangulation(kps1, desc1, has_mp1, u_right1, fv1, kps2, desc2, has_mp2, u_right2, fv2, F12, ex, ey,
+                             scale_factors, level_sigma2, only_stereo=False, check_orientation=True):
+    """ORBmatcher::SearchForTriangulation (ORBmatcher.cc:659-825) -> (match12, nmatches)"""
+    kps1 = np.ascontiguousarray(kps1, KP_DTYPE); kps2 = np.ascontiguousarray(kps2, KP_DTYPE)
+    desc1 = _u8(desc1); desc2 = _u8(desc2)
+    has_mp1 = None if has_mp1 is None else _u8(has_mp1); has_mp2 = None if has_mp2 is None else _u8(has_mp2)
+    u_right1, u_right2 = _f32(u_right1), _f32(u_right2)
+    f1 = [np.ascontiguousarray(x, np.int32) for x in fv1]; f2 = [np.ascontiguousarray(x, np.int32) for x in fv2]
+    F12 = _f32(F12).reshape(9); sf = _f32(scale_factors); ls = _f32(level_sigma2)
+    m12 = np.zeros(len(kps1), np.int32)
+    nm = lib().orc_search_for_triangulation(_p(kps1), _p(desc1), _p(has_mp1), _p(u_right1), len(kps1), _p(f1[0]), _p(f1[1]), _p(f1[2]),
+                                            len(f1[0]), _p(kps2), _p(desc2), _p(has_mp2), _p(u_right2), len(kps2), _p(f2[0]), _p(f2[1]),
+                                            _p(f2[2]), len(f2[0]), _p(F12), ex, ey, _p(sf), _p(ls), int(only_stereo),
+                                            int(check_orientation), _p(m12))
+    return m12, int(nm)
+
+
+def sim3_search_one_way(grid, desc, q_u, q_v, q_radius, q_level, q_desc, q_valid=None):
+    nq = len(q_u)
+    desc = _u8(desc); q_desc = _u8(q_desc)
+    q_u, q_v, q_radius = _f32(q_u), _f32(q_v), _f32(q_radius)
+    q_level = np.ascontiguousarray(q_level, np.int32)
+    q_valid = None if q_valid is None else _u8(q_valid)
+    m = np.zeros(nq, np.int32)
+    lib().orc_sim3_search_one_way(grid._h, _p(grid.kps), _p(desc), nq, _p(q_u), _p(q_v), _p(q_radius), _p(q_level), _p(q_desc), _p(q_valid), _p(m))
+    return m
+
+
+def search_by_sim3(grid1, desc1, grid2, desc2, q12, q21):
+    """ORBmatcher::SearchBySim3 (ORBmatcher.cc:1104-1328) on arrays.  q12 = dict(u, v, radius, level, desc, valid): the
+    map points of keyframe 1 projected into keyframe 2 (one entry per keypoint of keyframe 1), q21 the reverse.
+    -> (match12 after the agreement check, nFound)"""
+    m1 = sim3_search_one_way(grid2, desc2, q12["u"], q12["v"], q12["radius"], q12["level"], q12["desc"], q12.get("valid"))
+    m2 = sim3_search_one_way(grid1, desc1, q21["u"], q21["v"], q21["radius"], q21["level"], q21["desc"], q21.get("valid"))
+    out = np.full(len(m1), -1, np.int32)
+    for i1, idx2 in enumerate(m1):          # OM:1282-1299
+        if idx2 >= 0 and m2[idx2] == i1:
+            out[i1] = idx2
+    return out, int((out >= 0).sum())
+
+
+def distinctive_descriptors(desc, off):
+    desc = _u8(desc); off = np.ascontiguousarray(off, np.int32)
+    best = np.zeros(len(off) - 1, np.int32)
+    lib().orc_distinctive_descriptors(_p(desc), _p(off), len(off) - 1, _p(best))
+    return best

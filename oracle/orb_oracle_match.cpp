@@ -383,6 +383,128 @@ int orc_search_by_bow(const uint8_t* desc1, const float* angle1, const uint8_t* 
     return nmatches;
 }
 
+/* SearchForTriangulation (OM:659-825) on arrays.  has_mp[i]: the keypoint already holds a map point (skipped, OM:703-705 /
+ * 726-728); u_right (NULL = monocular): bStereo = u_right[i] >= 0; F12 row-major; (ex, ey) epipole in image 2 (OM:665-673);
+ * scale_factors / level_sigma2 = pKF2->mvScaleFactors / mvLevelSigma2.  NOTE: the reference never sets vbMatched2, so two
+ * queries may pick the same target; candidates are gated `dist > TH_LOW || dist > bestDist` (OM:741), so among equal
+ * distances the LAST gate-passing candidate in list order wins.  match12[n1] = vMatches12.  Returns nmatches. */
+int orc_search_for_triangulation(const orc_kp* kps1, const uint8_t* desc1, const uint8_t* has_mp1, const float* u_right1, int n1,
+                                 const int32_t* fv1_node, const int32_t* fv1_start, const int32_t* fv1_feat, int nfv1,
+                                 const orc_kp* kps2, const uint8_t* desc2, const uint8_t* has_mp2, const float* u_right2, int n2,
+                                 const int32_t* fv2_node, const int32_t* fv2_start, const int32_t* fv2_feat, int nfv2, const float* F12,
+                                 float ex, float ey, const float* scale_factors, const float* level_sigma2, int only_stereo,
+                                 int check_orientation, int32_t* match12) {
+    int nmatches = 0;
+    std::vector<bool> vbMatched2(n2, false);
+    for (int i = 0; i < n1; ++i) match12[i] = -1;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    int a = 0, b = 0;
+    while (a < nfv1 && b < nfv2) {
+        if (fv1_node[a] == fv2_node[b]) {
+            for (int i1 = fv1_start[a]; i1 < fv1_start[a + 1]; ++i1) {
+                const int idx1 = fv1_feat[i1];
+                if (has_mp1 && has_mp1[idx1]) continue;
+                const bool bStereo1 = u_right1 && u_right1[idx1] >= 0;
+                if (only_stereo && !bStereo1) continue;
+                const orc_kp& kp1 = kps1[idx1];
+                const uint8_t* d1 = desc1 + (size_t)idx1 * 32;
+                int bestDist = TH_LOW, bestIdx2 = -1;
+                for (int i2 = fv2_start[b]; i2 < fv2_start[b + 1]; ++i2) {
+                    const int idx2 = fv2_feat[i2];
+                    if (vbMatched2[idx2] || (has_mp2 && has_mp2[idx2])) continue;
+                    const bool bStereo2 = u_right2 && u_right2[idx2] >= 0;
+                    if (only_stereo && !bStereo2) continue;
+                    const int dist = descriptor_distance(d1, desc2 + (size_t)idx2 * 32);
+                    if (dist > TH_LOW || dist > bestDist) continue;
+                    const orc_kp& kp2 = kps2[idx2];
+                    if (!bStereo1 && !bStereo2) {
+                        const float distex = ex - kp2.x, distey = ey - kp2.y;
+                        if (distex * distex + distey * distey < 100 * scale_factors[kp2.octave]) continue;
+                    }
+                    /* CheckDistEpipolarLine, OM:140-157 */
+                    const float la = kp1.x * F12[0] + kp1.y * F12[3] + F12[6];
+                    const float lb = kp1.x * F12[1] + kp1.y * F12[4] + F12[7];
+                    const float lc = kp1.x * F12[2] + kp1.y * F12[5] + F12[8];
+                    const float num = la * kp2.x + lb * kp2.y + lc;
+                    const float den = la * la + lb * lb;
+                    if (den == 0) continue;
+                    const float dsqr = num * num / den;
+                    if (dsqr < 3.84 * level_sigma2[kp2.octave]) { bestIdx2 = idx2; bestDist = dist; }
+                }
+                if (bestIdx2 >= 0) {
+                    match12[idx1] = bestIdx2;
+                    nmatches++;
+                    if (check_orientation) rotHist[rot_bin(kp1.angle, kps2[bestIdx2].angle)].push_back(idx1);
+                }
+            }
+            ++a; ++b;
+        } else if (fv1_node[a] < fv2_node[b]) {
+            while (a < nfv1 && fv1_node[a] < fv2_node[b]) ++a;
+        } else {
+            while (b < nfv2 && fv2_node[b] < fv1_node[a]) ++b;
+        }
+    }
+    if (check_orientation) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int h = 0; h < HISTO_LENGTH; ++h) {
+            if (h == ind1 || h == ind2 || h == ind3) continue;
+            for (int idx1 : rotHist[h]) { match12[idx1] = -1; nmatches--; }
+        }
+    }
+    return nmatches;
+}
+
+/* One direction of SearchBySim3 (OM:1150-1213 / 1216-1279) on arrays: query i = a map point of the other keyframe projected
+ * to (q_u, q_v) with radius th * scale[pred] and predicted level q_level (queries the reference skips have q_valid = 0);
+ * candidates = GetFeaturesInArea(u, v, radius) (KeyFrame.cc:700-739, no level filter), octave in [pred-1, pred], best
+ * distance with strict '<', accepted when <= TH_HIGH.  match[i] = target index or -1. */
+void orc_sim3_search_one_way(void* grid, const orc_kp* kps_un, const uint8_t* desc, int nq, const float* q_u, const float* q_v,
+                             const float* q_radius, const int32_t* q_level, const uint8_t* q_desc, const uint8_t* q_valid, int32_t* match) {
+    std::vector<int32_t> cand;
+    for (int i = 0; i < nq; ++i) {
+        match[i] = -1;
+        if (q_valid && !q_valid[i]) continue;
+        grid_query((Grid*)grid, q_u[i], q_v[i], q_radius[i], -1, -1, cand);
+        int bestDist = INT_MAX, bestIdx = -1;
+        for (int32_t idx : cand) {
+            if (kps_un[idx].octave < q_level[i] - 1 || kps_un[idx].octave > q_level[i]) continue;
+            const int dist = descriptor_distance(q_desc + (size_t)i * 32, desc + (size_t)idx * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+        }
+        if (bestDist <= TH_HIGH) match[i] = bestIdx;
+    }
+}
+
+/* MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:288-361) for npoints map points at once: the observed descriptors of
+ * point p are rows [off[p], off[p+1]); best[p] = index (within the point) of the descriptor with the least median distance
+ * to the others (first on ties), -1 for a point without observations. */
+void orc_distinctive_descriptors(const uint8_t* desc, const int32_t* off, int npoints, int32_t* best) {
+    for (int p = 0; p < npoints; ++p) {
+        const int N = off[p + 1] - off[p];
+        best[p] = -1;
+        if (N <= 0) continue;
+        const uint8_t* d = desc + (size_t)off[p] * 32;
+        std::vector<float> Distances((size_t)N * N);
+        for (int i = 0; i < N; i++) {
+            Distances[(size_t)i * N + i] = 0;
+            for (int j = i + 1; j < N; j++) {
+                const int distij = descriptor_distance(d + (size_t)i * 32, d + (size_t)j * 32);
+                Distances[(size_t)i * N + j] = (float)distij;
+                Distances[(size_t)j * N + i] = (float)distij;
+            }
+        }
+        int BestMedian = INT_MAX, BestIdx = 0;
+        for (int i = 0; i < N; i++) {
+            std::vector<int> vDists(Distances.begin() + (size_t)i * N, Distances.begin() + (size_t)(i + 1) * N);
+            std::sort(vDists.begin(), vDists.end());
+            const int median = vDists[(size_t)(0.5 * (N - 1))];
+            if (median < BestMedian) { BestMedian = median; BestIdx = i; }
+        }
+        best[p] = BestIdx;
+    }
+}
+
 /* FR:502-676 */
 int orc_stereo_match(void* exL, void* exR, const orc_kp* kpsL, const uint8_t* descL, int N, const orc_kp* kpsR,
                      const uint8_t* descR, int Nr, const orc_stereo_params* prm, float* mvuRight, float* mvDepth,

@@ -668,12 +668,136 @@ bow_rot_kernel(const float* __restrict__ angle1, const float* __restrict__ angle
             const int m = match12[i];
             if (m < 0) continue;
             const int bin = rot_bin(angle1[i], angle2[m]);
-            if (bin != ind1 && bin != ind2 && bin != ind3) { match21[m] = -1; match12[i] = -1; --cnt; }
+            if (bin != ind1 && bin != ind2 && bin != ind3) { if (match21) match21[m] = -1; match12[i] = -1; --cnt; }
         }
     }
     atomicAdd(&s_n, cnt);
     __syncthreads();
     if (threadIdx.x == 0) *nmatches_out = s_n;
+}
+
+// =============================== SearchForTriangulation (ORBmatcher.cc:659-825) ===================================
+// No loop-carried state (the reference never sets vbMatched2): one warp per shared node, its query keypoints one after
+// the other, the lanes gate and score the node's targets.  The reference keeps a candidate when `dist <= bestDist` and the
+// epipolar gates pass (OM:741-757), i.e. the minimum distance, LAST in list order on ties: key = dist << 16 | (0xFFFF - pos).
+struct TriFrame {
+    const orb_kp* kps; const uint8_t* desc; const uint8_t* has_mp; const float* u_right;
+    const int *fv_node, *fv_start, *fv_feat; int nfv;
+};
+struct TriParams { float F[9]; float ex, ey; float scale[ORB_MAX_LEVELS]; float sigma2[ORB_MAX_LEVELS]; int nlevels, only_stereo, th_low; };
+
+__global__ void __launch_bounds__(256)
+bow_triangulation_kernel(const TriFrame A, const TriFrame B, const __grid_constant__ TriParams P, int* __restrict__ match12) {
+    const int lane = threadIdx.x & 31;
+    const int a = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (a >= A.nfv) return;
+    const int node = A.fv_node[a];
+    int lo = 0, hi = B.nfv;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (B.fv_node[mid] < node) lo = mid + 1; else hi = mid;
+    }
+    if (lo >= B.nfv || B.fv_node[lo] != node) return;
+    const int s2 = B.fv_start[lo], c2 = B.fv_start[lo + 1] - s2;
+    for (int i1 = A.fv_start[a]; i1 < A.fv_start[a + 1]; ++i1) {
+        const int idx1 = A.fv_feat[i1];
+        if (A.has_mp && A.has_mp[idx1]) continue;                                   // OM:703-705
+        const bool st1 = A.u_right && A.u_right[idx1] >= 0.0f;
+        if (P.only_stereo && !st1) continue;
+        const orb_kp kp1 = A.kps[idx1];
+        // epipolar line l = x1' F12 (OM:143-145), every product and sum rounded separately
+        const float la = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, P.F[0]), __fmul_rn(kp1.y, P.F[3])), P.F[6]);
+        const float lb = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, P.F[1]), __fmul_rn(kp1.y, P.F[4])), P.F[7]);
+        const float lc = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, P.F[2]), __fmul_rn(kp1.y, P.F[5])), P.F[8]);
+        const float den = __fadd_rn(__fmul_rn(la, la), __fmul_rn(lb, lb));
+        const uint4* dq = reinterpret_cast<const uint4*>(A.desc + (size_t)idx1 * 32);
+        unsigned best = 0xFFFFFFFFu;
+        for (int p = lane; p < c2; p += 32) {
+            const int idx2 = B.fv_feat[s2 + p];
+            if (B.has_mp && B.has_mp[idx2]) continue;                               // OM:726-728
+            const bool st2 = B.u_right && B.u_right[idx2] >= 0.0f;
+            if (P.only_stereo && !st2) continue;
+            const int dist = dist256(dq, reinterpret_cast<const uint4*>(B.desc + (size_t)idx2 * 32));
+            if (dist > P.th_low) continue;
+            const orb_kp kp2 = B.kps[idx2];
+            const int oct = min(max(kp2.octave, 0), ORB_MAX_LEVELS - 1);
+            if (!st1 && !st2) {                                                     // too close to the epipole (OM:745-751)
+                const float dx = __fsub_rn(P.ex, kp2.x), dy = __fsub_rn(P.ey, kp2.y);
+                if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < __fmul_rn(100.0f, P.scale[oct])) continue;
+            }
+            const float num = __fadd_rn(__fadd_rn(__fmul_rn(la, kp2.x), __fmul_rn(lb, kp2.y)), lc);
+            if (den == 0.0f) continue;
+            const float dsqr = __fdiv_rn(__fmul_rn(num, num), den);
+            if (!((double)dsqr < __dmul_rn(3.84, (double)P.sigma2[oct]))) continue;   // OM:156
+            best = min(best, ((unsigned)dist << 16) | (unsigned)(0xFFFF - p));
+        }
+        best = warp_min_u32(best);
+        if (lane == 0 && best != 0xFFFFFFFFu) match12[idx1] = B.fv_feat[s2 + (0xFFFF - (int)(best & 0xFFFFu))];
+    }
+}
+
+// =============================== MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:288-361), batched ============
+// One CTA (4 warps) per map point; warp w takes the rows i = w, w+4, ...: the lanes compute the N distances of row i, the
+// median vDists[0.5*(N-1)] is found by rank counting (N <= 32: shuffles) or a 257-bin shared-memory histogram; the point's
+// answer is the row with the smallest median, first on ties (key = median << 16 | i).
+#define DD_WARPS 4
+__global__ void __launch_bounds__(DD_WARPS * 32)
+distinctive_kernel(const uint8_t* __restrict__ desc, const int* __restrict__ off, int* __restrict__ best) {
+    __shared__ int hist[DD_WARPS][264];
+    __shared__ unsigned s_key[DD_WARPS];
+    const int p = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int o0 = off[p], N = off[p + 1] - o0;
+    if (N <= 0) { if (threadIdx.x == 0) best[p] = -1; return; }
+    const int k = (N - 1) >> 1;                                  // (size_t)(0.5 * (N - 1))
+    unsigned mykey = 0xFFFFFFFFu;
+    for (int i = warp; i < N; i += DD_WARPS) {
+        const uint4* di = reinterpret_cast<const uint4*>(desc + (size_t)(o0 + i) * 32);
+        int median;
+        if (N <= 32) {
+            const int d = lane < N ? dist256(di, reinterpret_cast<const uint4*>(desc + (size_t)(o0 + lane) * 32)) : 0x7FFF;
+            int rank = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int dj = __shfl_sync(0xffffffffu, d, j);
+                rank += (dj < d || (dj == d && j < lane)) ? 1 : 0;
+            }
+            const unsigned who = __ballot_sync(0xffffffffu, rank == k && lane < N);
+            median = __shfl_sync(0xffffffffu, d, __ffs(who) - 1);
+        } else {
+            for (int b = lane; b < 264; b += 32) hist[warp][b] = 0;
+            __syncwarp();
+            for (int j = lane; j < N; j += 32) atomicAdd(&hist[warp][dist256(di, reinterpret_cast<const uint4*>(desc + (size_t)(o0 + j) * 32))], 1);
+            __syncwarp();
+            // the k-th smallest = the first bin whose inclusive prefix count exceeds k: 9 bins per lane, warp scan
+            int c[9], tot = 0;
+#pragma unroll
+            for (int b = 0; b < 9; ++b) { c[b] = lane * 9 + b < 257 ? hist[warp][lane * 9 + b] : 0; tot += c[b]; }
+            int incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += y;
+            }
+            int run = incl - tot, mine = 0x7FFF;
+#pragma unroll
+            for (int b = 0; b < 9; ++b) {
+                run += c[b];
+                if (run > k && mine == 0x7FFF) mine = lane * 9 + b;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, o));
+            median = mine;
+            __syncwarp();
+        }
+        mykey = min(mykey, ((unsigned)median << 16) | (unsigned)min(i, 0xFFFF));
+    }
+    if (lane == 0) s_key[warp] = mykey;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned m = s_key[0];
+        for (int w = 1; w < DD_WARPS; ++w) m = min(m, s_key[w]);
+        best[p] = (int)(m & 0xFFFFu);
+    }
 }
 
 // Per-thread, per-device workspace of the host-pointer entry points: one grow-only device slab, one grow-only pinned
@@ -943,6 +1067,147 @@ int orb_search_by_bow(int device, const uint8_t* desc1, const float* angle1, con
     memcpy(match12, H + o_m12, 4 * (size_t)n1);
     memcpy(match21, H + o_m21, 4 * (size_t)n2);
     *nmatches = *(const int*)(H + o_nm);
+    return ORB_OK;
+}
+
+int orb_search_for_triangulation(int device, const orb_kp* kps1, const uint8_t* desc1, const uint8_t* has_mp1, const float* u_right1, int n1,
+                                 const int32_t* fv1_node, const int32_t* fv1_start, const int32_t* fv1_feat, int nfv1, const orb_kp* kps2,
+                                 const uint8_t* desc2, const uint8_t* has_mp2, const float* u_right2, int n2, const int32_t* fv2_node,
+                                 const int32_t* fv2_start, const int32_t* fv2_feat, int nfv2, const float* F12, float ex, float ey,
+                                 const float* scale_factors, const float* level_sigma2, int nlevels, int only_stereo, int check_orientation,
+                                 int32_t* match12, int* nmatches) {
+    if (n1 < 0 || n2 < 0 || nfv1 < 0 || nfv2 < 0 || !nmatches || !F12 || !scale_factors || !level_sigma2) return ORB_ERR_INVALID;
+    if ((n1 && (!kps1 || !desc1 || !match12)) || (n2 && (!kps2 || !desc2))) return ORB_ERR_INVALID;
+    if ((nfv1 && (!fv1_node || !fv1_start || !fv1_feat)) || (nfv2 && (!fv2_node || !fv2_start || !fv2_feat))) return ORB_ERR_INVALID;
+    if (nlevels < 1 || nlevels > ORB_MAX_LEVELS) { orb_set_error("orb_search_for_triangulation: 1..%d levels", ORB_MAX_LEVELS); return ORB_ERR_INVALID; }
+    *nmatches = 0;
+    for (int i = 0; i < n1; ++i) match12[i] = -1;
+    if (n1 == 0 || n2 == 0 || nfv1 == 0 || nfv2 == 0) return ORB_OK;
+    const int nf1 = fv1_start[nfv1], nf2 = fv2_start[nfv2];
+    if (nf1 < 0 || nf1 > n1 || nf2 < 0 || nf2 > n2) { orb_set_error("orb_search_for_triangulation: feature vector larger than the keypoint set"); return ORB_ERR_INVALID; }
+    for (int i = 0; i < nf1; ++i) if (fv1_feat[i] < 0 || fv1_feat[i] >= n1) { orb_set_error("orb_search_for_triangulation: fv1_feat out of range"); return ORB_ERR_INVALID; }
+    for (int i = 0; i < nf2; ++i) if (fv2_feat[i] < 0 || fv2_feat[i] >= n2) { orb_set_error("orb_search_for_triangulation: fv2_feat out of range"); return ORB_ERR_INVALID; }
+    for (int j = 0; j < nfv2; ++j) if (fv2_start[j + 1] - fv2_start[j] > 65535) { orb_set_error("orb_search_for_triangulation: more than 65535 features in one node"); return ORB_ERR_CAPACITY; }
+    for (int j = 0; j < n2; ++j) if (kps2[j].octave < 0 || kps2[j].octave >= nlevels) { orb_set_error("orb_search_for_triangulation: octave out of range"); return ORB_ERR_INVALID; }
+    if (orb_device_count() <= 0) { orb_set_error("no CUDA device visible: liborb_b200 has no CPU fallback"); return ORB_ERR_NO_DEVICE; }
+    Carver c;
+    const size_t o_k1 = c.take(sizeof(orb_kp) * (size_t)n1), o_k2 = c.take(sizeof(orb_kp) * (size_t)n2);
+    const size_t o_d1 = c.take((size_t)32 * n1), o_d2 = c.take((size_t)32 * n2);
+    const size_t o_h1 = c.take(n1), o_h2 = c.take(n2), o_u1 = c.take(4 * (size_t)n1), o_u2 = c.take(4 * (size_t)n2);
+    const size_t o_a1 = c.take(4 * (size_t)n1), o_a2 = c.take(4 * (size_t)n2);     // dense angles for the rotation filter
+    const size_t o_n1 = c.take(4 * (size_t)nfv1), o_s1 = c.take(4 * ((size_t)nfv1 + 1)), o_f1 = c.take(4 * (size_t)std::max(nf1, 1));
+    const size_t o_n2 = c.take(4 * (size_t)nfv2), o_s2 = c.take(4 * ((size_t)nfv2 + 1)), o_f2 = c.take(4 * (size_t)std::max(nf2, 1));
+    const size_t o_m12 = c.take(4 * (size_t)n1);
+    const size_t in_bytes = c.off;
+    const size_t o_nm = c.take(16);
+    const size_t io_bytes = c.off;
+    Workspace& W = g_ws;
+    int rc = W.prepare(device, io_bytes, io_bytes);
+    if (rc != ORB_OK) return rc;
+    cudaStream_t st = W.st;
+    uint8_t *H = W.h, *Dv = W.d;
+    memcpy(H + o_k1, kps1, sizeof(orb_kp) * (size_t)n1); memcpy(H + o_k2, kps2, sizeof(orb_kp) * (size_t)n2);
+    memcpy(H + o_d1, desc1, (size_t)32 * n1); memcpy(H + o_d2, desc2, (size_t)32 * n2);
+    if (has_mp1) memcpy(H + o_h1, has_mp1, n1);
+    if (has_mp2) memcpy(H + o_h2, has_mp2, n2);
+    if (u_right1) memcpy(H + o_u1, u_right1, 4 * (size_t)n1);
+    if (u_right2) memcpy(H + o_u2, u_right2, 4 * (size_t)n2);
+    for (int i = 0; i < n1; ++i) reinterpret_cast<float*>(H + o_a1)[i] = kps1[i].angle;
+    for (int j = 0; j < n2; ++j) reinterpret_cast<float*>(H + o_a2)[j] = kps2[j].angle;
+    memcpy(H + o_n1, fv1_node, 4 * (size_t)nfv1); memcpy(H + o_s1, fv1_start, 4 * ((size_t)nfv1 + 1)); memcpy(H + o_f1, fv1_feat, 4 * (size_t)nf1);
+    memcpy(H + o_n2, fv2_node, 4 * (size_t)nfv2); memcpy(H + o_s2, fv2_start, 4 * ((size_t)nfv2 + 1)); memcpy(H + o_f2, fv2_feat, 4 * (size_t)nf2);
+    memset(H + o_m12, 0xFF, 4 * (size_t)n1);
+    ORB_CUDA(cudaMemcpyAsync(Dv, H, in_bytes, cudaMemcpyHostToDevice, st));
+    TriFrame A{(const orb_kp*)(Dv + o_k1), Dv + o_d1, has_mp1 ? Dv + o_h1 : nullptr, u_right1 ? (const float*)(Dv + o_u1) : nullptr,
+               (const int*)(Dv + o_n1), (const int*)(Dv + o_s1), (const int*)(Dv + o_f1), nfv1};
+    TriFrame B{(const orb_kp*)(Dv + o_k2), Dv + o_d2, has_mp2 ? Dv + o_h2 : nullptr, u_right2 ? (const float*)(Dv + o_u2) : nullptr,
+               (const int*)(Dv + o_n2), (const int*)(Dv + o_s2), (const int*)(Dv + o_f2), nfv2};
+    TriParams P;
+    memset(&P, 0, sizeof(P));
+    memcpy(P.F, F12, sizeof(P.F));
+    P.ex = ex; P.ey = ey; P.nlevels = nlevels; P.only_stereo = only_stereo; P.th_low = 50;   // ORBmatcher::TH_LOW
+    for (int l = 0; l < nlevels; ++l) { P.scale[l] = scale_factors[l]; P.sigma2[l] = level_sigma2[l]; }
+    bow_triangulation_kernel<<<(nfv1 + 7) / 8, 256, 0, st>>>(A, B, P, (int*)(Dv + o_m12));
+    bow_rot_kernel<<<1, 1024, 0, st>>>((const float*)(Dv + o_a1), (const float*)(Dv + o_a2), n1, check_orientation, (int*)(Dv + o_m12), nullptr,
+                                       (int*)(Dv + o_nm));
+    ORB_CUDA(cudaGetLastError());
+    ORB_CUDA(cudaMemcpyAsync(H + o_m12, Dv + o_m12, io_bytes - o_m12, cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaStreamSynchronize(st));
+    memcpy(match12, H + o_m12, 4 * (size_t)n1);
+    *nmatches = *(const int*)(H + o_nm);
+    return ORB_OK;
+}
+
+int orb_search_by_sim3(int device, const orb_kp* kps1_un, const uint8_t* desc1, int n1, const float* bounds1, const orb_kp* kps2_un,
+                       const uint8_t* desc2, int n2, const float* bounds2, const float* q12_u, const float* q12_v, const float* q12_radius,
+                       const int32_t* q12_level, const uint8_t* q12_desc, const uint8_t* q12_valid, const float* q21_u, const float* q21_v,
+                       const float* q21_radius, const int32_t* q21_level, const uint8_t* q21_desc, const uint8_t* q21_valid, int th_dist,
+                       int32_t* match12, int* nfound) {
+    if (n1 < 0 || n2 < 0 || !nfound || !bounds1 || !bounds2) return ORB_ERR_INVALID;
+    if (n1 && (!kps1_un || !desc1 || !q12_u || !q12_v || !q12_radius || !q12_level || !q12_desc || !match12)) return ORB_ERR_INVALID;
+    if (n2 && (!kps2_un || !desc2 || !q21_u || !q21_v || !q21_radius || !q21_level || !q21_desc)) return ORB_ERR_INVALID;
+    *nfound = 0;
+    for (int i = 0; i < n1; ++i) match12[i] = -1;
+    if (n1 == 0 || n2 == 0) return ORB_OK;
+    // Each direction (ORBmatcher.cc:1150-1213, 1216-1279) is a windowed best-only search without any "already matched"
+    // state: the TRACK_LAST walk with no target taken and no query blocking its target (q_obs = 0), octave band
+    // [pred - 1, pred], no rotation histogram.
+    std::vector<int32_t> m1(n1, -1), m2(n2, -1), lo, hi;
+    std::vector<uint8_t> taken, zeros;
+    auto one_way = [&](const orb_kp* kps, const uint8_t* desc, int n, const float* b, int nq, const float* u, const float* v, const float* r,
+                       const int32_t* lvl, const uint8_t* qd, const uint8_t* valid, int32_t* out) -> int {
+        orb_search_params prm;
+        prm.mode = ORB_MODE_TRACK_LAST; prm.th_dist = th_dist; prm.nn_ratio = 1.0f; prm.check_orientation = 0;
+        prm.min_x = b[0]; prm.min_y = b[1]; prm.max_x = b[2]; prm.max_y = b[3];
+        lo.resize(nq); hi.resize(nq);
+        for (int i = 0; i < nq; ++i) { lo[i] = lvl[i] - 1; hi[i] = lvl[i]; }
+        taken.assign(n, 0); zeros.assign(nq, 0);
+        int nm = 0;
+        return orb_search_by_projection(device, &prm, kps, desc, nullptr, n, taken.data(), nq, u, v, r, lo.data(), hi.data(), qd, nullptr, nullptr,
+                                        nullptr, valid, zeros.data(), out, nullptr, &nm);
+    };
+    int rc = one_way(kps2_un, desc2, n2, bounds2, n1, q12_u, q12_v, q12_radius, q12_level, q12_desc, q12_valid, m1.data());
+    if (rc != ORB_OK) return rc;
+    rc = one_way(kps1_un, desc1, n1, bounds1, n2, q21_u, q21_v, q21_radius, q21_level, q21_desc, q21_valid, m2.data());
+    if (rc != ORB_OK) return rc;
+    int found = 0;
+    for (int i1 = 0; i1 < n1; ++i1) {                      // agreement check, ORBmatcher.cc:1282-1299
+        const int idx2 = m1[i1];
+        if (idx2 >= 0 && m2[idx2] == i1) { match12[i1] = idx2; ++found; }
+    }
+    *nfound = found;
+    return ORB_OK;
+}
+
+int orb_distinctive_descriptors(int device, const uint8_t* desc32, const int32_t* off, int npoints, int32_t* best_idx, uint8_t* best_desc32) {
+    if (npoints < 0 || !off || (npoints && !best_idx)) return ORB_ERR_INVALID;
+    if (npoints == 0) return ORB_OK;
+    if (off[0] != 0) { orb_set_error("orb_distinctive_descriptors: off[0] must be 0"); return ORB_ERR_INVALID; }
+    for (int p = 0; p < npoints; ++p) {
+        if (off[p + 1] < off[p]) { orb_set_error("orb_distinctive_descriptors: off must be non-decreasing"); return ORB_ERR_INVALID; }
+        if (off[p + 1] - off[p] > 65535) { orb_set_error("orb_distinctive_descriptors: more than 65535 observations of one point"); return ORB_ERR_CAPACITY; }
+    }
+    const int total = off[npoints];
+    if (total && !desc32) return ORB_ERR_INVALID;
+    if (orb_device_count() <= 0) { orb_set_error("no CUDA device visible: liborb_b200 has no CPU fallback"); return ORB_ERR_NO_DEVICE; }
+    Carver c;
+    const size_t o_d = c.take((size_t)32 * std::max(total, 1)), o_off = c.take(4 * ((size_t)npoints + 1));
+    const size_t in_bytes = c.off;
+    const size_t o_best = c.take(4 * (size_t)npoints);
+    Workspace& W = g_ws;
+    int rc = W.prepare(device, c.off, c.off);
+    if (rc != ORB_OK) return rc;
+    if (total) memcpy(W.h + o_d, desc32, (size_t)32 * total);
+    memcpy(W.h + o_off, off, 4 * ((size_t)npoints + 1));
+    ORB_CUDA(cudaMemcpyAsync(W.d, W.h, in_bytes, cudaMemcpyHostToDevice, W.st));
+    distinctive_kernel<<<npoints, DD_WARPS * 32, 0, W.st>>>(W.d + o_d, (const int*)(W.d + o_off), (int*)(W.d + o_best));
+    ORB_CUDA(cudaGetLastError());
+    ORB_CUDA(cudaMemcpyAsync(W.h + o_best, W.d + o_best, 4 * (size_t)npoints, cudaMemcpyDeviceToHost, W.st));
+    ORB_CUDA(cudaStreamSynchronize(W.st));
+    memcpy(best_idx, W.h + o_best, 4 * (size_t)npoints);
+    if (best_desc32)
+        for (int p = 0; p < npoints; ++p)
+            if (best_idx[p] >= 0) memcpy(best_desc32 + (size_t)p * 32, desc32 + (size_t)(off[p] + best_idx[p]) * 32, 32);
     return ORB_OK;
 }
 

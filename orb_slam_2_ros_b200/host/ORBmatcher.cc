@@ -106,6 +106,45 @@ int ORBmatcher::SearchByBoW(const uint8_t* desc1, const float* angle1, const uin
     return nmatches;
 }
 
+int ORBmatcher::SearchForTriangulation(const KeyFrameView& kf1, const KeyFrameView& kf2, const float F12[9], float ex, float ey,
+                                       const std::vector<float>& scaleFactors2, const std::vector<float>& levelSigma2_2,
+                                       std::vector<std::pair<size_t, size_t> >& vMatchedPairs, bool bOnlyStereo) const {
+    std::vector<int32_t> n1v, s1v, f1v, n2v, s2v, f2v, m12(kf1.N, -1);
+    flatten(*kf1.featVec, n1v, s1v, f1v);
+    flatten(*kf2.featVec, n2v, s2v, f2v);
+    int nmatches = 0;
+    check(orb_search_for_triangulation(device_, reinterpret_cast<const orb_kp*>(kf1.keysUn), kf1.descriptors, kf1.hasMapPoint, kf1.uRight, kf1.N,
+                                       n1v.data(), s1v.data(), f1v.data(), (int)n1v.size(), reinterpret_cast<const orb_kp*>(kf2.keysUn),
+                                       kf2.descriptors, kf2.hasMapPoint, kf2.uRight, kf2.N, n2v.data(), s2v.data(), f2v.data(), (int)n2v.size(),
+                                       F12, ex, ey, scaleFactors2.data(), levelSigma2_2.data(), (int)scaleFactors2.size(), bOnlyStereo ? 1 : 0,
+                                       mbCheckOrientation ? 1 : 0, m12.data(), &nmatches), "orb_search_for_triangulation");
+    vMatchedPairs.clear();                                              // ORBmatcher.cc:812-822
+    vMatchedPairs.reserve(nmatches);
+    for (size_t i = 0; i < m12.size(); ++i)
+        if (m12[i] >= 0) vMatchedPairs.push_back(std::make_pair(i, (size_t)m12[i]));
+    return nmatches;
+}
+
+int ORBmatcher::SearchBySim3(const TargetFrame& kf1, const TargetFrame& kf2, const Queries& q12, const Queries& q21,
+                             std::vector<int32_t>& match12) const {
+    match12.assign(kf1.N, -1);
+    const float b1[4] = {kf1.minX, kf1.minY, kf1.maxX, kf1.maxY}, b2[4] = {kf2.minX, kf2.minY, kf2.maxX, kf2.maxY};
+    int nfound = 0;
+    check(orb_search_by_sim3(device_, reinterpret_cast<const orb_kp*>(kf1.keysUn), kf1.descriptors, kf1.N, b1,
+                             reinterpret_cast<const orb_kp*>(kf2.keysUn), kf2.descriptors, kf2.N, b2, q12.u, q12.v, q12.radius, q12.minLevel,
+                             q12.descriptors, q12.valid, q21.u, q21.v, q21.radius, q21.minLevel, q21.descriptors, q21.valid, TH_HIGH,
+                             match12.data(), &nfound), "orb_search_by_sim3");
+    return nfound;
+}
+
+void ORBmatcher::ComputeDistinctiveDescriptors(const uint8_t* desc, const std::vector<int32_t>& off, std::vector<int32_t>& bestIdx,
+                                               std::vector<uint8_t>& bestDesc, int device) {
+    const int np = off.empty() ? 0 : (int)off.size() - 1;
+    bestIdx.assign(np, -1);
+    bestDesc.assign((size_t)np * 32, 0);
+    check(orb_distinctive_descriptors(device, desc, off.data(), np, bestIdx.data(), bestDesc.data()), "orb_distinctive_descriptors");
+}
+
 int ComputeStereoMatches(ORBextractor& left, ORBextractor& right, const std::vector<cv::KeyPoint>& keysL, const cv::Mat& descL,
                          const std::vector<cv::KeyPoint>& keysR, const cv::Mat& descR, float bf, float b,
                          std::vector<float>& mvuRight, std::vector<float>& mvDepth) {

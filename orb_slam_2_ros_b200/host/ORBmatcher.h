@@ -6,6 +6,7 @@
 #define ORBMATCHER_H
 
 #include <cstdint>
+#include <utility>
 #include <vector>
 
 #include "ORBVocabulary.h"
@@ -53,6 +54,25 @@ public:
     int SearchByBoW(const uint8_t* desc1, const float* angle1, const uint8_t* valid1, int n1, const DBoW2::FeatureVector& fv1,
                     const uint8_t* desc2, const float* angle2, const uint8_t* valid2, int n2, const DBoW2::FeatureVector& fv2,
                     bool keyframePair, std::vector<int32_t>& match12, std::vector<int32_t>& match21) const;
+
+    // SearchForTriangulation(KeyFrame*, KeyFrame*, F12, vMatchedPairs, bOnlyStereo)  ORBmatcher.cc:659-825.  hasMapPoint:
+    // GetMapPoint(idx) != NULL; uRight = mvuRight (NULL: monocular); (ex, ey) = epipole (:665-673)
+    struct KeyFrameView {
+        const cv::KeyPoint* keysUn; const uint8_t* descriptors; const uint8_t* hasMapPoint; const float* uRight; int N;
+        const DBoW2::FeatureVector* featVec;
+    };
+    int SearchForTriangulation(const KeyFrameView& kf1, const KeyFrameView& kf2, const float F12[9], float ex, float ey,
+                               const std::vector<float>& scaleFactors2, const std::vector<float>& levelSigma2_2,
+                               std::vector<std::pair<size_t, size_t> >& vMatchedPairs, bool bOnlyStereo) const;
+    // SearchBySim3(KeyFrame*, KeyFrame*, vpMatches12, s12, R12, t12, th)  ORBmatcher.cc:1104-1328: the caller projects the map
+    // points of each keyframe into the other (the 3x3 float algebra of :1150-1190) and passes the windows as Queries
+    // (minLevel / maxLevel unused: level = predicted octave in Queries::minLevel)
+    int SearchBySim3(const TargetFrame& kf1, const TargetFrame& kf2, const Queries& q12, const Queries& q21,
+                     std::vector<int32_t>& match12) const;
+    // MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:288-361) for many points: observations of point p = rows
+    // [off[p], off[p+1]) of desc; bestDesc = npoints x 32
+    static void ComputeDistinctiveDescriptors(const uint8_t* desc, const std::vector<int32_t>& off, std::vector<int32_t>& bestIdx,
+                                              std::vector<uint8_t>& bestDesc, int device = 0);
 
     static const int TH_LOW = 50;
     static const int TH_HIGH = 100;

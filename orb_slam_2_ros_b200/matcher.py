@@ -88,6 +88,44 @@ class ORBmatcher:
                                       C.byref(nm)))
         return nm.value, m12, m21
 
+    def SearchForTriangulation(self, kps1, desc1, has_mp1, u_right1, fv1, kps2, desc2, has_mp2, u_right2, fv2, F12, ex, ey,
+                               scale_factors, level_sigma2, bOnlyStereo=False):
+        """ORBmatcher::SearchForTriangulation (ORBmatcher.cc:659-825).  -> nmatches, vMatches12 (vMatchedPairs = its
+        non-negative entries in index order, :812-822)"""
+        kps1 = np.ascontiguousarray(kps1, KP_DTYPE); kps2 = np.ascontiguousarray(kps2, KP_DTYPE)
+        desc1, desc2 = _b(desc1), _b(desc2)
+        has_mp1, has_mp2, u_right1, u_right2 = _b(has_mp1), _b(has_mp2), _f(u_right1), _f(u_right2)
+        f1 = [_i(x) for x in fv1]; f2 = [_i(x) for x in fv2]
+        F12 = _f(F12).reshape(9); sf = _f(scale_factors); ls = _f(level_sigma2)
+        m12 = np.full(len(kps1), -1, np.int32); nm = C.c_int32(0)
+        check(lib().orb_search_for_triangulation(self.device, ptr(kps1), ptr(desc1), ptr(has_mp1), ptr(u_right1), len(kps1), ptr(f1[0]), ptr(f1[1]),
+                                                 ptr(f1[2]), len(f1[0]), ptr(kps2), ptr(desc2), ptr(has_mp2), ptr(u_right2), len(kps2), ptr(f2[0]),
+                                                 ptr(f2[1]), ptr(f2[2]), len(f2[0]), ptr(F12), ex, ey, ptr(sf), ptr(ls), len(sf), int(bOnlyStereo),
+                                                 int(self.mbCheckOrientation), ptr(m12), C.byref(nm)))
+        return nm.value, m12
+
+    def SearchBySim3(self, kps1_un, desc1, bounds1, kps2_un, desc2, bounds2, q12, q21, th_dist=TH_HIGH):
+        """ORBmatcher::SearchBySim3 (ORBmatcher.cc:1104-1328).  q12 / q21 = dict(u, v, radius, level, desc[, valid]) with one
+        entry per keypoint of keyframe 1 / 2.  -> nFound, match12"""
+        kps1_un = np.ascontiguousarray(kps1_un, KP_DTYPE); kps2_un = np.ascontiguousarray(kps2_un, KP_DTYPE)
+        desc1, desc2 = _b(desc1), _b(desc2)
+        b1, b2 = _f(bounds1), _f(bounds2)
+        a = [(_f(q["u"]), _f(q["v"]), _f(q["radius"]), _i(q["level"]), _b(q["desc"]), _b(q.get("valid"))) for q in (q12, q21)]
+        m12 = np.full(len(kps1_un), -1, np.int32); nf = C.c_int32(0)
+        check(lib().orb_search_by_sim3(self.device, ptr(kps1_un), ptr(desc1), len(kps1_un), ptr(b1), ptr(kps2_un), ptr(desc2), len(kps2_un), ptr(b2),
+                                       *[ptr(x) for x in a[0]], *[ptr(x) for x in a[1]], th_dist, ptr(m12), C.byref(nf)))
+        return nf.value, m12
+
+
+def distinctive_descriptors(desc, off, device=0):
+    """MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:288-361) for many map points: rows [off[p], off[p+1]) of desc are
+    the observations of point p.  -> (best_idx, best_desc)"""
+    desc = _b(desc); off = _i(off)
+    npts = len(off) - 1
+    best = np.full(npts, -1, np.int32); bd = np.zeros((npts, 32), np.uint8)
+    check(lib().orb_distinctive_descriptors(device, ptr(desc), ptr(off), npts, ptr(best), ptr(bd)))
+    return best, bd
+
 def hamming_top2(q, db, device=0):
     """Brute-force best / second-best (ORBmatcher.cc:202-227 update rule) of each query over db (host arrays)."""
     q, db = _b(q), _b(db)
