@@ -11,7 +11,7 @@ import pytest
 from orb_slam_2_ros_b200 import synth
 
 pytestmark = pytest.mark.gpu
-GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLD = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")) if not os.path.basename(p).startswith("bow_"))
 
 
 def sha(a):
