@@ -211,6 +211,33 @@ def other_configs(device):
     cms_st = _median_ms(stereo_cpu, 3, warm=1)
     out["config3_stereo"] = {"workload": "1241x376 pair, nFeatures=2000: 2 extractions + ComputeStereoMatches, sequential calls",
                              "ms": ms_st, "pairs_per_s": 1e3 / ms_st, "stereo_matches": int(res["n"]), "cpu_oracle_ms_1thread": cms_st}
+    # bag-of-words transform (ORBvoc shape k = 10, L = 6, 1.1 M nodes) + SearchByBoW + SearchForTriangulation
+    from orb_slam_2_ros_b200 import ORBVocabulary
+    P = synth.synth_vocabulary(11, k=10, L=6)
+    voc = ORBVocabulary.from_arrays(10, 6, 0, 0, *P, device=device)
+    ovoc = orb_oracle.Vocabulary.from_arrays(10, 6, 0, 0, *P)
+    ms_bow = _median_ms(lambda: voc.transform(da, 4), 30)
+    cms_bow = _median_ms(lambda: ovoc.transform(da, 4), 5, warm=1)
+    nbatch = 256
+    frames_desc = [da if i % 2 == 0 else db for i in range(nbatch)]
+    ms_bowb = _median_ms(lambda: voc.transform_batch(frames_desc, 4), 5, warm=2)
+    (_, fva), (_, fvb) = voc.transform_batch([da, db], 4)
+    m7 = ORBmatcher(0.7, True, device=device)
+    ms_sbb = _median_ms(lambda: m7.SearchByBoW(da, ka["angle"], None, fva, db, kb["angle"], None, fvb), 30)
+    cms_sbb = _median_ms(lambda: orb_oracle.search_by_bow(da, ka["angle"], None, fva, db, kb["angle"], None, fvb, 50, False, 0.7, True), 5, warm=1)
+    F12 = np.array([[0, 0, -2], [0, 0, -3], [2, 3, 0]], np.float32) * np.float32(0.01)
+    sig2 = (sf * sf).astype(np.float32)
+    ms_tri = _median_ms(lambda: m.SearchForTriangulation(ka, da, None, None, fva, kb, db, None, None, fvb, F12, 1e6, 1e6, sf, sig2), 30)
+    cms_tri = _median_ms(lambda: orb_oracle.search_for_triangulation(ka, da, None, None, fva, kb, db, None, None, fvb, F12, 1e6, 1e6, sf, sig2,
+                                                                     False, True), 5, warm=1)
+    out["bow_and_mapping_matchers"] = {
+        "workload": "synthetic vocabulary k=10 L=6 (%d nodes, ORBvoc shape), %d / %d descriptors of two extracted frames, levelsup 4" % (len(P[0]), len(da), len(db)),
+        "bow_transform_ms": ms_bow, "bow_transform_cpu_oracle_ms_1thread": cms_bow,
+        "bow_transform_batch%d_ms" % nbatch: ms_bowb, "bow_transform_batch_descriptors_per_s": sum(len(d) for d in frames_desc) / (ms_bowb * 1e-3),
+        "search_by_bow_ms": ms_sbb, "search_by_bow_cpu_oracle_ms_1thread": cms_sbb,
+        "search_by_bow_matches": int(m7.SearchByBoW(da, ka["angle"], None, fva, db, kb["angle"], None, fvb)[0]),
+        "search_for_triangulation_ms": ms_tri, "search_for_triangulation_cpu_oracle_ms_1thread": cms_tri,
+        "search_for_triangulation_matches": int(m.SearchForTriangulation(ka, da, None, None, fva, kb, db, None, None, fvb, F12, 1e6, 1e6, sf, sig2)[0])}
     return out
 
 
