@@ -32,8 +32,8 @@ namespace {
 #define FS_ROWS 66         // cell sub-image height <= hCell + 6 <= 66
 #define FS_SROWS 62        // evaluated rows <= 60, plus a zero row above and below
 #define FS_MAXG 8          // 250 / 30
-#define FS_WCAP 896        // candidate entries (u16) per warp segment
-#define FS_SCAP 3072       // scored-corner list entries (u16)
+#define FS_WCAP 448        // candidate entries (u16) per warp segment
+#define FS_SCAP 2048       // scored-corner list entries (u16)
 #define FS_TILE_BYTES (FS_ROWS * FS_PITCH)
 #define FS_CAND_BYTES (FS_WARPS * FS_WCAP * 2)
 #define FS_SCORED_BYTES (FS_SCAP * 2)

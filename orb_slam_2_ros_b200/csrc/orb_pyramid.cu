@@ -88,7 +88,7 @@ __device__ __forceinline__ void hrow4(const unsigned* __restrict__ srow, int wb,
     for (int p = 0; p < 4; ++p) {
         const unsigned lo = cs.hi[p] ? w1 : w0, hi = cs.hi[p] ? w2 : w1;
         const unsigned pair = __funnelshift_r(lo, hi, cs.sh[p]);      // byte0 = S[s], byte1 = S[s+1]
-        h[p] = __dp2a_lo(cc[p], pair, 0u);                            // c0*S[s] + c1*S[s+1]
+        h[p] = __dp2a_lo(cc[p], pair, 0u) >> 4;                       // (c0*S[s] + c1*S[s+1]) >> 4
     }
 }
 
@@ -117,7 +117,7 @@ pyr_resize_fast_kernel(uint8_t* __restrict__ pyr, const ResizeTap* __restrict__ 
     const int y0 = strip * ROWS, y1 = min(y0 + ROWS, L.h);
     const uint2* ytab = reinterpret_cast<const uint2*>(taps + L.ytab);   // ResizeTap = {u16 s0, u16 s1, s16 c0, s16 c1}
     const int ppw = P.pitch >> 2;
-    unsigned h0[4], h1[4];
+    unsigned h0[4], h1[4];                                // horizontal results >> 4 of the two source rows
     int have1 = -1;                                       // source row whose horizontal pass sits in h1
     for (int y = y0; y < y1; ++y) {
         const uint2 ty = __ldg(ytab + y);
@@ -140,8 +140,8 @@ pyr_resize_fast_kernel(uint8_t* __restrict__ pyr, const ResizeTap* __restrict__ 
         unsigned v = 0;
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-            const unsigned o = (__umulhi(b0, h0[p] >> 4) + __umulhi(b1, h1[p] >> 4) + 2u) >> 2;
-            v |= o << (8 * p);                            // 0 <= o <= 255
+            const unsigned o = (__umulhi(b1, h1[p]) + (__umulhi(b0, h0[p]) + 2u)) >> 2;   // 0 <= o <= 255
+            v = __funnelshift_r(v, o, 8);                 // shifts the earlier pixels down, o becomes the top byte
         }
         *reinterpret_cast<unsigned*>(D + y * L.pitch) = v;
     }
