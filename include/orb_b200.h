@@ -14,6 +14,7 @@
  *   ORBmatcher::SearchByBoW (both overloads)    ORBmatcher.cc:160-289, 524-657            -> orb_search_by_bow
  *   ORBmatcher::SearchForTriangulation          ORBmatcher.cc:659-825                     -> orb_search_for_triangulation
  *   ORBmatcher::SearchBySim3                    ORBmatcher.cc:1104-1328                   -> orb_search_by_sim3
+ *   ORBmatcher::Fuse x2 (search half)           ORBmatcher.cc:827-977, 979-1102           -> orb_fuse_search
  *   MapPoint::ComputeDistinctiveDescriptors     MapPoint.cc:288-361                       -> orb_distinctive_descriptors
  *   Frame::ComputeStereoMatches                 Frame.cc:502-676                          -> orb_stereo_match
  *   ORBVocabulary::transform / loadFromTextFile DBoW2/TemplatedVocabulary.h:1140-1272, 1351 -> orb_bow_transform*, orb_voc_*
@@ -241,6 +242,18 @@ int orb_search_by_sim3(int device, const orb_kp* kps1_un, const uint8_t* desc1, 
                        const int32_t* q12_level, const uint8_t* q12_desc, const uint8_t* q12_valid, const float* q21_u, const float* q21_v,
                        const float* q21_radius, const int32_t* q21_level, const uint8_t* q21_desc, const uint8_t* q21_valid, int th_dist,
                        int32_t* match12, int* nfound);
+
+/* The search half of ORBmatcher::Fuse (ORBmatcher.cc:827-977; with inv_level_sigma2 == NULL the Sim3 overload :979-1102) on
+ * arrays: query i = a map point projected into the keyframe — (q_u, q_v), right coordinate q_ur = u - bf * invz, radius =
+ * th * mvScaleFactors[pred], predicted level, descriptor; q_valid[i] = 0 for the points the reference skips before the
+ * search (:846-886).  Candidates = GetFeaturesInArea(u, v, radius) with octave in [pred-1, pred] that pass the reprojection
+ * gate e2 * mvInvLevelSigma2[octave] <= 7.8 (keypoint with mvuRight >= 0, e2 includes er) / <= 5.99 (monocular) (:914-940);
+ * best_idx / best_dist = the first candidate with the smallest distance (-1 / 256 when none).  The caller fuses when
+ * best_dist <= TH_LOW; Replace / AddObservation / AddMapPoint (:955-973) mutate the map and stay on the host. */
+int orb_fuse_search(int device, const orb_kp* kps_un, const uint8_t* desc, const float* u_right, int n, const float* bounds,
+                    const float* inv_level_sigma2, int nlevels, int nq, const float* q_u, const float* q_v, const float* q_ur,
+                    const float* q_radius, const int32_t* q_level, const uint8_t* q_desc, const uint8_t* q_valid, int32_t* best_idx,
+                    int32_t* best_dist);
 
 /* MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:288-361) for npoints map points at once: the observed descriptors of
  * point p are rows [off[p], off[p+1]) (off[0] == 0); best_idx[p] = the row (within the point) with the least median distance to

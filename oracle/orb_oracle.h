@@ -175,6 +175,10 @@ int orc_search_for_triangulation(const orc_kp* kps1, const uint8_t* desc1, const
                                  int check_orientation, int32_t* match12);
 void orc_sim3_search_one_way(void* grid, const orc_kp* kps_un, const uint8_t* desc, int nq, const float* q_u, const float* q_v,
                              const float* q_radius, const int32_t* q_level, const uint8_t* q_desc, const uint8_t* q_valid, int32_t* match);
+/* search half of ORBmatcher::Fuse (ORBmatcher.cc:827-977, 979-1102) */
+void orc_fuse_search(void* grid, const orc_kp* kps_un, const uint8_t* desc, const float* u_right, const float* inv_level_sigma2,
+                     int nq, const float* q_u, const float* q_v, const float* q_ur, const float* q_radius, const int32_t* q_level,
+                     const uint8_t* q_desc, const uint8_t* q_valid, int32_t* best_idx, int32_t* best_dist);
 void orc_distinctive_descriptors(const uint8_t* desc, const int32_t* off, int npoints, int32_t* best);
 
 /* ---------------- bag of words (DBoW2 TemplatedVocabulary<FORB>, orb_oracle_bow.cpp) ---------------- */

@@ -92,6 +92,8 @@ def lib():
         L.orc_sim3_search_one_way.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]
         L.orc_sim3_search_one_way.restype = None
         L.orc_distinctive_descriptors.argtypes = [vp, vp, i32, vp]
+        L.orc_fuse_search.argtypes = [vp, vp, vp, vp, vp, i32] + [vp] * 9
+        L.orc_fuse_search.restype = None
         L.orc_distinctive_descriptors.restype = None
         L.orc_search_by_bow.argtypes = [vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, i32, i32, f32, i32, vp, vp]
         L.orc_voc_create.restype = vp
@@ -465,3 +467,17 @@ def distinctive_descriptors(desc, off):
     best = np.zeros(len(off) - 1, np.int32)
     lib().orc_distinctive_descriptors(_p(desc), _p(off), len(off) - 1, _p(best))
     return best
+
+
+def fuse_search(grid, desc, u_right, inv_level_sigma2, q_u, q_v, q_ur, q_radius, q_level, q_desc, q_valid=None):
+    """search half of ORBmatcher::Fuse -> (best_idx, best_dist)"""
+    nq = len(q_u)
+    desc = _u8(desc); q_desc = _u8(q_desc)
+    u_right = _f32(u_right); inv = _f32(inv_level_sigma2)
+    q_u, q_v, q_ur, q_radius = _f32(q_u), _f32(q_v), _f32(q_ur), _f32(q_radius)
+    q_level = np.ascontiguousarray(q_level, np.int32)
+    q_valid = None if q_valid is None else _u8(q_valid)
+    bi = np.zeros(nq, np.int32); bd = np.zeros(nq, np.int32)
+    lib().orc_fuse_search(grid._h, _p(grid.kps), _p(desc), _p(u_right), _p(inv), nq, _p(q_u), _p(q_v), _p(q_ur), _p(q_radius), _p(q_level),
+                          _p(q_desc), _p(q_valid), _p(bi), _p(bd))
+    return bi, bd

@@ -476,6 +476,43 @@ void orc_sim3_search_one_way(void* grid, const orc_kp* kps_un, const uint8_t* de
     }
 }
 
+/* The search half of ORBmatcher::Fuse (OM:827-977; OM:979-1102 when inv_level_sigma2 == NULL) on arrays: query i = a map
+ * point projected into the keyframe at (q_u, q_v) with right coordinate q_ur, radius th * scale[pred], predicted level;
+ * candidates = GetFeaturesInArea(u, v, radius), octave in [pred-1, pred], reprojection gate e2 * invSigma2 > 7.8 (stereo
+ * keypoint, with er) / > 5.99 (monocular) (OM:914-940), best distance with strict '<'.  best_idx / best_dist receive the
+ * winner (-1 / 256 when none); the caller fuses when best_dist <= TH_LOW (the map mutation stays on the host). */
+void orc_fuse_search(void* grid, const orc_kp* kps_un, const uint8_t* desc, const float* u_right, const float* inv_level_sigma2,
+                     int nq, const float* q_u, const float* q_v, const float* q_ur, const float* q_radius, const int32_t* q_level,
+                     const uint8_t* q_desc, const uint8_t* q_valid, int32_t* best_idx, int32_t* best_dist) {
+    std::vector<int32_t> cand;
+    for (int i = 0; i < nq; ++i) {
+        best_idx[i] = -1; best_dist[i] = 256;
+        if (q_valid && !q_valid[i]) continue;
+        const float u = q_u[i], v = q_v[i];
+        grid_query((Grid*)grid, u, v, q_radius[i], -1, -1, cand);
+        int bestDist = 256, bestIdx = -1;
+        for (int32_t idx : cand) {
+            const orc_kp& kp = kps_un[idx];
+            const int kpLevel = kp.octave;
+            if (kpLevel < q_level[i] - 1 || kpLevel > q_level[i]) continue;
+            if (inv_level_sigma2) {
+                if (u_right && u_right[idx] >= 0) {
+                    const float ex = u - kp.x, ey = v - kp.y, er = q_ur[i] - u_right[idx];
+                    const float e2 = ex * ex + ey * ey + er * er;
+                    if (e2 * inv_level_sigma2[kpLevel] > 7.8) continue;
+                } else {
+                    const float ex = u - kp.x, ey = v - kp.y;
+                    const float e2 = ex * ex + ey * ey;
+                    if (e2 * inv_level_sigma2[kpLevel] > 5.99) continue;
+                }
+            }
+            const int dist = descriptor_distance(q_desc + (size_t)i * 32, desc + (size_t)idx * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+        }
+        best_idx[i] = bestIdx; best_dist[i] = bestDist;
+    }
+}
+
 /* MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:288-361) for npoints map points at once: the observed descriptors of
  * point p are rows [off[p], off[p+1]); best[p] = index (within the point) of the descriptor with the least median distance
  * to the others (first on ties), -1 for a point without observations. */

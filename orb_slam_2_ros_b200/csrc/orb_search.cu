@@ -800,6 +800,70 @@ distinctive_kernel(const uint8_t* __restrict__ desc, const int* __restrict__ off
     }
 }
 
+// =============================== search half of ORBmatcher::Fuse (ORBmatcher.cc:827-977, 979-1102) ================
+// One warp per projected map point.  The sorted item array of grid_build_kernel lists the window's candidates in the
+// reference's visiting order (ix, iy, insertion) at ascending positions, so "first minimum" = min(dist << 16 | position).
+struct FuseArgs {
+    const orb_kp* kps; const uint8_t* desc; const float* u_right; const float* inv_sigma2; int nlevels;
+    int nq; const float *q_u, *q_v, *q_ur, *q_radius; const int* q_level; const uint8_t *q_desc, *q_valid;
+    float min_x, min_y, inv_w, inv_h;
+    const unsigned* items; const int* cell_start;
+    int *best_idx, *best_dist;
+};
+
+__global__ void __launch_bounds__(256)
+fuse_search_kernel(const FuseArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (qi >= a.nq) return;
+    if (lane == 0) { a.best_idx[qi] = -1; a.best_dist[qi] = 256; }
+    if (a.q_valid && !a.q_valid[qi]) return;
+    const float x = a.q_u[qi], y = a.q_v[qi], r = a.q_radius[qi];
+    const int lvl = a.q_level[qi];
+    // KeyFrame::GetFeaturesInArea (KeyFrame.cc:700-739), float arithmetic with every op rounded separately
+    const int nMinCellX = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, a.min_x), r), a.inv_w)));
+    if (nMinCellX >= GRID_COLS) return;
+    const int nMaxCellX = min(GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, a.min_x), r), a.inv_w)));
+    if (nMaxCellX < 0) return;
+    const int nMinCellY = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, a.min_y), r), a.inv_h)));
+    if (nMinCellY >= GRID_ROWS) return;
+    const int nMaxCellY = min(GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, a.min_y), r), a.inv_h)));
+    if (nMaxCellY < 0) return;
+    const uint4* dq = reinterpret_cast<const uint4*>(a.q_desc + (size_t)qi * 32);
+    const float ur = a.q_ur ? a.q_ur[qi] : 0.0f;
+    unsigned best = 0xFFFFFFFFu;
+    for (int ix = nMinCellX; ix <= nMaxCellX; ++ix) {
+        const int s = a.cell_start[ix * GRID_ROWS + nMinCellY], e = a.cell_start[ix * GRID_ROWS + nMaxCellY + 1];
+        for (int p = s + lane; p < e; p += 32) {
+            const int id = (int)(a.items[p] & 0xFFFFu);
+            const orb_kp kp = a.kps[id];
+            const float dx = __fsub_rn(kp.x, x), dy = __fsub_rn(kp.y, y);
+            if (!(fabsf(dx) < r && fabsf(dy) < r)) continue;
+            if (kp.octave < lvl - 1 || kp.octave > lvl) continue;                                   // ORBmatcher.cc:909-910
+            if (a.inv_sigma2) {
+                const float inv = a.inv_sigma2[min(max(kp.octave, 0), a.nlevels - 1)];
+                const float ex = __fsub_rn(x, kp.x), ey = __fsub_rn(y, kp.y);
+                float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+                const float kpr = a.u_right ? a.u_right[id] : -1.0f;
+                if (kpr >= 0.0f) {
+                    const float er = __fsub_rn(ur, kpr);
+                    e2 = __fadd_rn(e2, __fmul_rn(er, er));
+                    if ((double)__fmul_rn(e2, inv) > 7.8) continue;                                  // :914-927
+                } else {
+                    if ((double)__fmul_rn(e2, inv) > 5.99) continue;                                 // :929-939
+                }
+            }
+            const unsigned d = (unsigned)dist256(dq, reinterpret_cast<const uint4*>(a.desc + (size_t)id * 32));
+            best = min(best, (d << 16) | (unsigned)p);
+        }
+    }
+    best = warp_min_u32(best);
+    if (lane == 0 && best != 0xFFFFFFFFu) {
+        a.best_idx[qi] = (int)(a.items[best & 0xFFFFu] & 0xFFFFu);
+        a.best_dist[qi] = (int)(best >> 16);
+    }
+}
+
 // Per-thread, per-device workspace of the host-pointer entry points: one grow-only device slab, one grow-only pinned
 // slab and a private stream.  A call packs all its inputs into the pinned slab, issues ONE H2D copy, the kernels and
 // ONE D2H copy, and synchronises once — no cudaMalloc / cudaFree on the call path.
@@ -1208,6 +1272,61 @@ int orb_distinctive_descriptors(int device, const uint8_t* desc32, const int32_t
     if (best_desc32)
         for (int p = 0; p < npoints; ++p)
             if (best_idx[p] >= 0) memcpy(best_desc32 + (size_t)p * 32, desc32 + (size_t)(off[p] + best_idx[p]) * 32, 32);
+    return ORB_OK;
+}
+
+int orb_fuse_search(int device, const orb_kp* kps_un, const uint8_t* desc, const float* u_right, int n, const float* bounds,
+                    const float* inv_level_sigma2, int nlevels, int nq, const float* q_u, const float* q_v, const float* q_ur,
+                    const float* q_radius, const int32_t* q_level, const uint8_t* q_desc, const uint8_t* q_valid, int32_t* best_idx,
+                    int32_t* best_dist) {
+    if (n < 0 || nq < 0 || !bounds || (nq && (!q_u || !q_v || !q_radius || !q_level || !q_desc || !best_idx || !best_dist))) return ORB_ERR_INVALID;
+    if (n && (!kps_un || !desc)) return ORB_ERR_INVALID;
+    if (inv_level_sigma2 && (nlevels < 1 || nlevels > ORB_MAX_LEVELS)) { orb_set_error("orb_fuse_search: 1..%d levels", ORB_MAX_LEVELS); return ORB_ERR_INVALID; }
+    if (inv_level_sigma2 && u_right && !q_ur) return ORB_ERR_INVALID;
+    for (int i = 0; i < nq; ++i) { best_idx[i] = -1; best_dist[i] = 256; }
+    if (n == 0 || nq == 0) return ORB_OK;
+    if (n > GB_MAX_N) { orb_set_error("orb_fuse_search: more than %d keypoints", GB_MAX_N); return ORB_ERR_CAPACITY; }
+    if (orb_device_count() <= 0) { orb_set_error("no CUDA device visible: liborb_b200 has no CPU fallback"); return ORB_ERR_NO_DEVICE; }
+    int npad = 32;
+    while (npad < n) npad <<= 1;
+    Carver c;
+    const size_t o_kps = c.take(sizeof(orb_kp) * (size_t)n), o_desc = c.take((size_t)32 * n), o_ur = c.take(4 * (size_t)n), o_sig = c.take(4 * ORB_MAX_LEVELS);
+    const size_t o_qu = c.take(4 * (size_t)nq), o_qv = c.take(4 * (size_t)nq), o_qur = c.take(4 * (size_t)nq), o_qr = c.take(4 * (size_t)nq);
+    const size_t o_ql = c.take(4 * (size_t)nq), o_qd = c.take((size_t)32 * nq), o_qval = c.take(nq);
+    const size_t in_bytes = c.off;
+    const size_t o_bi = c.take(4 * (size_t)nq), o_bd = c.take(4 * (size_t)nq);
+    const size_t io_bytes = c.off;
+    const size_t o_items = c.take(4 * (size_t)npad), o_cells = c.take(4 * (GRID_COLS * GRID_ROWS + 1));
+    Workspace& W = g_ws;
+    int rc = W.prepare(device, c.off, io_bytes);
+    if (rc != ORB_OK) return rc;
+    cudaStream_t st = W.st;
+    uint8_t *H = W.h, *Dv = W.d;
+    auto put = [&](size_t off, const void* src, size_t bytes) { if (src) memcpy(H + off, src, bytes); };
+    put(o_kps, kps_un, sizeof(orb_kp) * (size_t)n); put(o_desc, desc, (size_t)32 * n); put(o_ur, u_right, 4 * (size_t)n);
+    put(o_sig, inv_level_sigma2, 4 * (size_t)(inv_level_sigma2 ? nlevels : 0));
+    put(o_qu, q_u, 4 * (size_t)nq); put(o_qv, q_v, 4 * (size_t)nq); put(o_qur, q_ur, 4 * (size_t)nq); put(o_qr, q_radius, 4 * (size_t)nq);
+    put(o_ql, q_level, 4 * (size_t)nq); put(o_qd, q_desc, (size_t)32 * nq); put(o_qval, q_valid, nq);
+    ORB_CUDA(cudaMemcpyAsync(Dv, H, in_bytes, cudaMemcpyHostToDevice, st));
+    FuseArgs a;
+    memset(&a, 0, sizeof(a));
+    a.kps = (const orb_kp*)(Dv + o_kps); a.desc = Dv + o_desc; a.u_right = u_right ? (const float*)(Dv + o_ur) : nullptr;
+    a.inv_sigma2 = inv_level_sigma2 ? (const float*)(Dv + o_sig) : nullptr; a.nlevels = nlevels;
+    a.nq = nq; a.q_u = (const float*)(Dv + o_qu); a.q_v = (const float*)(Dv + o_qv); a.q_ur = q_ur ? (const float*)(Dv + o_qur) : nullptr;
+    a.q_radius = (const float*)(Dv + o_qr); a.q_level = (const int*)(Dv + o_ql); a.q_desc = Dv + o_qd; a.q_valid = q_valid ? Dv + o_qval : nullptr;
+    a.min_x = bounds[0]; a.min_y = bounds[1];
+    a.inv_w = (float)GRID_COLS / (bounds[2] - bounds[0]);   // Frame.cc:162-163 / KeyFrame.cc:43-44
+    a.inv_h = (float)GRID_ROWS / (bounds[3] - bounds[1]);
+    a.items = (const unsigned*)(Dv + o_items); a.cell_start = (const int*)(Dv + o_cells);
+    a.best_idx = (int*)(Dv + o_bi); a.best_dist = (int*)(Dv + o_bd);
+    grid_build_kernel<<<1, 1024, npad * sizeof(unsigned), st>>>(a.kps, n, npad, a.min_x, a.min_y, a.inv_w, a.inv_h, (unsigned*)(Dv + o_items),
+                                                                (int*)(Dv + o_cells));
+    fuse_search_kernel<<<(nq + 7) / 8, 256, 0, st>>>(a);
+    ORB_CUDA(cudaGetLastError());
+    ORB_CUDA(cudaMemcpyAsync(H + o_bi, Dv + o_bi, io_bytes - o_bi, cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaStreamSynchronize(st));
+    memcpy(best_idx, H + o_bi, 4 * (size_t)nq);
+    memcpy(best_dist, H + o_bd, 4 * (size_t)nq);
     return ORB_OK;
 }
 

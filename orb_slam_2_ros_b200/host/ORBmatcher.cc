@@ -137,6 +137,15 @@ int ORBmatcher::SearchBySim3(const TargetFrame& kf1, const TargetFrame& kf2, con
     return nfound;
 }
 
+void ORBmatcher::FuseSearch(const TargetFrame& kf, const float* invLevelSigma2, int nlevels, const Queries& q, std::vector<int32_t>& bestIdx,
+                            std::vector<int32_t>& bestDist) const {
+    bestIdx.assign(q.n, -1);
+    bestDist.assign(q.n, 256);
+    const float b[4] = {kf.minX, kf.minY, kf.maxX, kf.maxY};
+    check(orb_fuse_search(device_, reinterpret_cast<const orb_kp*>(kf.keysUn), kf.descriptors, kf.uRight, kf.N, b, invLevelSigma2, nlevels, q.n,
+                          q.u, q.v, q.uR, q.radius, q.minLevel, q.descriptors, q.valid, bestIdx.data(), bestDist.data()), "orb_fuse_search");
+}
+
 void ORBmatcher::ComputeDistinctiveDescriptors(const uint8_t* desc, const std::vector<int32_t>& off, std::vector<int32_t>& bestIdx,
                                                std::vector<uint8_t>& bestDesc, int device) {
     const int np = off.empty() ? 0 : (int)off.size() - 1;

@@ -69,6 +69,11 @@ public:
     // (minLevel / maxLevel unused: level = predicted octave in Queries::minLevel)
     int SearchBySim3(const TargetFrame& kf1, const TargetFrame& kf2, const Queries& q12, const Queries& q21,
                      std::vector<int32_t>& match12) const;
+    // The search half of Fuse(KeyFrame*, vpMapPoints, th) (ORBmatcher.cc:827-977) and, with invLevelSigma2 == NULL, of
+    // Fuse(KeyFrame*, Scw, vpPoints, th, vpReplacePoint) (:979-1102): q = the projected map points (Queries::uR = u - bf*invz,
+    // Queries::minLevel = predicted level); bestIdx / bestDist per point.  Replace / AddObservation stay with the caller.
+    void FuseSearch(const TargetFrame& kf, const float* invLevelSigma2, int nlevels, const Queries& q, std::vector<int32_t>& bestIdx,
+                    std::vector<int32_t>& bestDist) const;
     // MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:288-361) for many points: observations of point p = rows
     // [off[p], off[p+1]) of desc; bestDesc = npoints x 32
     static void ComputeDistinctiveDescriptors(const uint8_t* desc, const std::vector<int32_t>& off, std::vector<int32_t>& bestIdx,

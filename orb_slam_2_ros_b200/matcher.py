@@ -117,6 +117,19 @@ class ORBmatcher:
         return nf.value, m12
 
 
+    def FuseSearch(self, kps_un, desc, u_right, bounds, inv_level_sigma2, q_u, q_v, q_ur, q_radius, q_level, q_desc, q_valid=None):
+        """The search half of ORBmatcher::Fuse (ORBmatcher.cc:827-977; inv_level_sigma2=None: the Sim3 overload :979-1102).
+        -> (best_idx, best_dist); the reference fuses point i into keypoint best_idx[i] when best_dist[i] <= TH_LOW."""
+        kps_un = np.ascontiguousarray(kps_un, KP_DTYPE)
+        desc, q_desc, q_valid = _b(desc), _b(q_desc), _b(q_valid)
+        u_right, inv, b = _f(u_right), _f(inv_level_sigma2), _f(bounds)
+        q_u, q_v, q_ur, q_radius, q_level = _f(q_u), _f(q_v), _f(q_ur), _f(q_radius), _i(q_level)
+        nq = len(q_u)
+        bi = np.full(nq, -1, np.int32); bd = np.full(nq, 256, np.int32)
+        check(lib().orb_fuse_search(self.device, ptr(kps_un), ptr(desc), ptr(u_right), len(kps_un), ptr(b), ptr(inv), 0 if inv is None else len(inv),
+                                    nq, ptr(q_u), ptr(q_v), ptr(q_ur), ptr(q_radius), ptr(q_level), ptr(q_desc), ptr(q_valid), ptr(bi), ptr(bd)))
+        return bi, bd
+
 def distinctive_descriptors(desc, off, device=0):
     """MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:288-361) for many map points: rows [off[p], off[p+1]) of desc are
     the observations of point p.  -> (best_idx, best_desc)"""

@@ -115,3 +115,28 @@ def test_distinctive_descriptors_vs_oracle(oracle):
     for p_, b in enumerate(best):
         if b >= 0:
             assert np.array_equal(bd[p_], desc[off[p_] + b])
+
+
+@pytest.mark.parametrize("stereo,gate", [(True, True), (False, True), (True, False)])
+def test_fuse_search_vs_oracle(oracle, pair, stereo, gate):
+    """Search half of ORBmatcher::Fuse (ORBmatcher.cc:827-977) / its Sim3 overload (:979-1102, no reprojection gate)."""
+    from orb_slam_2_ros_b200 import ORBmatcher
+    p = pair
+    rng = np.random.default_rng(17)
+    w, h = p["w"], p["h"]
+    bounds = np.array([0, 0, w, h], np.float32)
+    k2, d2, k1, d1 = p["k2"], p["d2"], p["k1"], p["d1"]
+    n1 = len(k1)
+    dy, dx = p["shift"]
+    ur2 = np.where(rng.random(len(k2)) < 0.6, k2["x"] - rng.uniform(2, 40, len(k2)), -1).astype(np.float32) if stereo else None
+    lvl = np.clip(k1["octave"] + rng.integers(-1, 2, n1), 0, 7).astype(np.int32)
+    q_u = (k1["x"] + dx + rng.normal(0, 1.2, n1)).astype(np.float32); q_v = (k1["y"] + dy + rng.normal(0, 1.2, n1)).astype(np.float32)
+    q_ur = (q_u - rng.uniform(2, 40, n1)).astype(np.float32)
+    q_r = (np.float32(3.0) * p["scale"][lvl]).astype(np.float32)
+    valid = (rng.random(n1) < 0.9).astype(np.uint8)
+    inv_sigma2 = (1.0 / (p["scale"] * p["scale"])).astype(np.float32) if gate else None
+    grid = oracle.Grid(k2, 0, 0, w, h)
+    obi, obd = oracle.fuse_search(grid, d2, ur2, inv_sigma2, q_u, q_v, q_ur, q_r, lvl, d1, valid)
+    bi, bd = ORBmatcher().FuseSearch(k2, d2, ur2, bounds, inv_sigma2, q_u, q_v, q_ur, q_r, lvl, d1, valid)
+    assert np.array_equal(bi, obi) and np.array_equal(bd, obd)
+    assert ((bd <= 50) & (bi >= 0)).sum() > 100

@@ -65,3 +65,23 @@ def test_sim3_agreement(oracle):
     q2 = dict(q, valid=(np.arange(n) % 2).astype(np.uint8))
     m12, nf = oracle.search_by_sim3(g, d, g, d, q2, q)
     assert nf == n // 2 and (m12[::2] == -1).all()
+
+
+def test_fuse_search_gates(oracle):
+    k = np.zeros(4, KP_DTYPE)
+    k["x"] = [100, 101, 103, 100]; k["y"] = [100, 100, 100, 100]; k["octave"] = [0, 0, 0, 2]
+    d = np.zeros((4, 32), np.uint8); d[0, 0] = 0x0F; d[1, 0] = 0x01; d[2, 0] = 0x00; d[3, 0] = 0x00
+    g = oracle.Grid(k, 0, 0, 640, 480)
+    inv = np.ones(8, np.float32)
+    q = dict(q_u=np.array([100.0]), q_v=np.array([100.0]), q_ur=np.array([90.0]), q_radius=np.array([5.0]), q_level=np.array([0]),
+             q_desc=np.zeros((1, 32), np.uint8))
+    # keypoint 2 has distance 0 but e2 = 9 > 5.99; keypoint 3 is at the wrong level: keypoint 1 (distance 1) wins
+    bi, bd = oracle.fuse_search(g, d, None, inv, **q)
+    assert bi.tolist() == [1] and bd.tolist() == [1]
+    # without the gate (Sim3 overload) keypoint 2 wins
+    bi, bd = oracle.fuse_search(g, d, None, None, **q)
+    assert bi.tolist() == [2] and bd.tolist() == [0]
+    # stereo keypoints: the right-coordinate error enters e2 (er = 90 - 87 = 3 -> e2 = 1 + 9 = 10 > 7.8 for keypoint 1)
+    ur = np.array([90.0, 87.0, -1.0, -1.0], np.float32)
+    bi, bd = oracle.fuse_search(g, d, ur, inv, **q)
+    assert bi.tolist() == [0] and bd.tolist() == [4]
