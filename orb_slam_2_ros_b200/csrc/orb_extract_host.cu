@@ -34,6 +34,8 @@ inline int cv_round_f(float v) { return (int)lrintf(v); }  // cvRound: half-to-e
 inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 void free_geometry_buffers(orb_ctx* c) {
+    if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+    c->graph_warm_w = c->graph_warm_h = 0; c->graph_warm_fmt = -1;
     cudaFree(c->d_in); cudaFree(c->d_pyr); cudaFree(c->d_blur); cudaFree(c->d_corners); cudaFree(c->d_node_of_key);
     cudaFree(c->d_corner_count); cudaFree(c->d_kept); cudaFree(c->d_kept_count); cudaFree(c->d_taps);
     cudaFree(c->d_wtaps); cudaFree(c->d_strips); cudaFree(c->d_tmaps); cudaFree(c->d_kps_out); cudaFree(c->d_desc_out); cudaFree(c->d_n_out);
@@ -561,6 +563,71 @@ int orb_extract_batch(orb_ctx* c, const uint8_t* imgs, int nframes, int w, int h
     return orb_extract_batch_pix(c, imgs, ORB_PIX_GRAY8, nframes, w, h, row_stride, frame_stride, kps, desc, cap, n_out);
 }
 
+// One frame, pageable (or any) host buffers: copy the image into the pinned staging buffer, launch the captured graph,
+// wait, copy the results out.  Returns 1 when the graph path is not applicable (the caller takes the pipeline path).
+static int extract_one_graph(orb_ctx* c, const uint8_t* img, int fmt, int w, int h, size_t row_stride, orb_kp* kps, uint8_t* desc,
+                             int cap, int32_t* n_out) {
+    if (c->use_graph < 0) { const char* e = getenv("ORB_B200_GRAPH"); c->use_graph = (e && atoi(e) == 0) ? 0 : 1; }
+    if (!c->use_graph || c->profile) return 1;
+    // the first call of a geometry / format runs without a graph: it sets the kernels' attributes and sizes the buffers
+    if (c->graph_warm_w != w || c->graph_warm_h != h || c->graph_warm_fmt != fmt) {
+        c->graph_warm_w = w; c->graph_warm_h = h; c->graph_warm_fmt = fmt;
+        return 1;
+    }
+    const int ch = orb_pix_channels(fmt);
+    const size_t rbytes = (size_t)w * ch, fbytes = rbytes * h;
+    const int dcap = std::min(cap, c->g.total_kp_slots);
+    int rc = ensure_outputs(c, std::max(dcap, c->out_cap), true);
+    if (rc != ORB_OK) return rc;
+    rc = ensure_input_staging(c, true, ch);
+    if (rc != ORB_OK) return rc;
+    const int ocap = c->out_cap, rows = std::min(ocap, cap);
+    const orb_ctx::GraphKey key = {fmt, w, h, rows, ocap, c->d_in, c->h_in, c->h_kps, c->h_desc, c->d_kps_out};
+    if (!c->graph_exec || memcmp(&key, &c->graph_key, sizeof(key)) != 0) {
+        if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+        ORB_CUDA(cudaStreamSynchronize(c->stream));
+        const long long l0 = c->launches;
+        const bool ov = c->overlap;
+        cudaGraph_t graph = nullptr;
+        ORB_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        cudaError_t e = cudaMemcpyAsync(c->d_in, c->h_in, fbytes, cudaMemcpyHostToDevice, c->stream);
+        c->overlap = true;   // inside the graph the two independent chains are parallel branches
+        if (e == cudaSuccess)
+            rc = orb_launch_extract(c, c->d_in, fmt, 1, 0, rbytes, fbytes, c->d_kps_out, c->d_desc_out, ocap, c->d_n_out, c->stream);
+        c->overlap = ov;
+        if (e == cudaSuccess && rc == ORB_OK) e = cudaMemcpyAsync(c->h_n, c->d_n_out, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess && rc == ORB_OK) e = cudaMemcpyAsync(c->h_kps, c->d_kps_out, sizeof(orb_kp) * (size_t)rows, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess && rc == ORB_OK) e = cudaMemcpyAsync(c->h_desc, c->d_desc_out, (size_t)32 * rows, cudaMemcpyDeviceToHost, c->stream);
+        const cudaError_t e2 = cudaStreamEndCapture(c->stream, &graph);
+        if (e != cudaSuccess || e2 != cudaSuccess || rc != ORB_OK || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            c->use_graph = 0;   // capture not possible here: keep using the pipeline path
+            c->launches = l0;
+            return 1;
+        }
+        e = cudaGraphInstantiate(&c->graph_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { cudaGetLastError(); c->graph_exec = nullptr; c->use_graph = 0; c->launches = l0; return 1; }
+        c->graph_launches = c->launches - l0;
+        c->launches = l0;
+        c->graph_key = key;
+    }
+    if (row_stride == rbytes) memcpy(c->h_in, img, fbytes);
+    else for (int y = 0; y < h; ++y) memcpy(c->h_in + (size_t)y * rbytes, img + (size_t)y * row_stride, rbytes);
+    ORB_CUDA(cudaGraphLaunch(c->graph_exec, c->stream));
+    c->launches += c->graph_launches;
+    c->last_frames = 1;
+    ORB_CUDA(cudaStreamSynchronize(c->stream));
+    const int n = c->h_n[0];
+    n_out[0] = n;
+    const int m = std::min(n, rows);
+    memcpy(kps, c->h_kps, sizeof(orb_kp) * (size_t)m);
+    memcpy(desc, c->h_desc, (size_t)32 * m);
+    if (n > cap) { orb_set_error("frame 0 produced %d keypoints, capacity %d", n, cap); return ORB_ERR_CAPACITY; }
+    return ORB_OK;
+}
+
 int orb_extract_batch_pix(orb_ctx* c, const uint8_t* imgs, int fmt, int nframes, int w, int h, size_t row_stride,
                           size_t frame_stride, orb_kp* kps, uint8_t* desc, int cap, int32_t* n_out) {
     if (!c || !n_out || nframes < 0 || cap < 0) return ORB_ERR_INVALID;
@@ -573,6 +640,10 @@ int orb_extract_batch_pix(orb_ctx* c, const uint8_t* imgs, int fmt, int nframes,
     if (rc != ORB_OK) return rc;
     rc = build_geometry(c, w, h);
     if (rc != ORB_OK) return rc;
+    if (nframes == 1) {   // latency path
+        rc = extract_one_graph(c, imgs, fmt, w, h, row_stride, kps, desc, cap, n_out);
+        if (rc != 1) return rc;
+    }
     const size_t rbytes = (size_t)w * ch;                 // bytes of one tight row
     const bool tight = row_stride == rbytes && frame_stride == rbytes * h;
     const bool in_direct = tight && is_pinned(imgs);

@@ -147,6 +147,13 @@ struct orb_ctx {
     bool use_tma = false;
     uint2* d_mom_tab = nullptr;   // IC_Angle weight table [4 alignments][288 items] (orient_describe_kernel)
     bool fast_attr_set = false, qt_attr_set = false;
+    // single-frame latency path: the whole call (H2D from the pinned staging buffer, 13 kernels with the border -> blur
+    // chain next to FAST -> quadtree, D2H into the pinned mirrors) as ONE CUDA graph, re-captured when a key field changes
+    int use_graph = -1;                    // -1: not decided yet (ORB_B200_GRAPH=0 disables)
+    cudaGraphExec_t graph_exec = nullptr;
+    struct GraphKey { int fmt, w, h, rows, ocap; const void *d_in, *h_in, *h_kps, *h_desc, *d_kps; } graph_key = {};
+    int graph_warm_w = 0, graph_warm_h = 0, graph_warm_fmt = -1;   // geometry / format that already ran once without a graph
+    long long graph_launches = 0;          // kernels inside the captured graph
     orb_kp* d_kps_out = nullptr; uint8_t* d_desc_out = nullptr; int* d_n_out = nullptr; int out_cap = 0;
     orb_kp* h_kps = nullptr; uint8_t* h_desc = nullptr; int* h_n = nullptr; uint8_t* h_in = nullptr;  // pinned
     size_t h_in_bytes = 0;
