@@ -661,14 +661,31 @@ int orb_extract_batch_pix(orb_ctx* c, const uint8_t* imgs, int fmt, int nframes,
     }();
     const size_t fbytes = rbytes * h;
     int status = ORB_OK;
+    // ORB_B200_PIPE_TRACE=1: per-chunk timeline (H2D start / end, kernels end, D2H end, ms since the call's start) on stderr
+    static const bool trace = getenv("ORB_B200_PIPE_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    cudaEvent_t t0ev = nullptr;
+    if (trace) { cudaEventCreate(&t0ev); cudaEventRecord(t0ev, c->st_h2d); }
     // the caller's stream (c->stream) may have pending work that produced or still reads our buffers
     ORB_CUDA(cudaStreamSynchronize(c->stream));
     for (int b0 = 0; b0 < nframes; b0 += c->max_batch) {
         const int B = std::min(c->max_batch, nframes - b0);
-        const int nchunks = (B + chunk_frames - 1) / chunk_frames;
+        // chunk schedule: two half-size chunks first (the kernels start after 1/16 of a 512-frame batch has arrived), then
+        // full chunks
+        std::vector<int> cf0, cF;
+        {
+            int f = 0, k = 0;
+            while (f < B) {
+                const int want = (k < 2 && B > chunk_frames) ? std::max(chunk_frames / 2, 1) : chunk_frames;
+                const int F = std::min(want, B - f);
+                cf0.push_back(f); cF.push_back(F);
+                f += F; ++k;
+            }
+        }
+        const int nchunks = (int)cf0.size();
         c->last_frames = B;
         auto finish_chunk = [&](int k) -> int {       // host side of chunk k once its D2H has landed
-            const int f0 = k * chunk_frames, F = std::min(chunk_frames, B - f0);
+            const int f0 = cf0[k], F = cF[k];
             ORB_CUDA(cudaEventSynchronize(c->ev_out[k % ORB_PIPE_SLOTS]));
             for (int f = 0; f < F; ++f) {
                 const int n = c->h_n[f0 + f];
@@ -683,7 +700,7 @@ int orb_extract_batch_pix(orb_ctx* c, const uint8_t* imgs, int fmt, int nframes,
             return ORB_OK;
         };
         for (int k = 0; k < nchunks; ++k) {
-            const int f0 = k * chunk_frames, F = std::min(chunk_frames, B - f0);
+            const int f0 = cf0[k], F = cF[k];
             const int slot = k % ORB_PIPE_SLOTS;
             if (k >= ORB_PIPE_SLOTS) { rc = finish_chunk(k - ORB_PIPE_SLOTS); if (rc != ORB_OK) return rc; }   // frees the slot's events
             // ---- H2D ----
@@ -699,16 +716,21 @@ int orb_extract_batch_pix(orb_ctx* c, const uint8_t* imgs, int fmt, int nframes,
                 src = stage;
             }
             uint8_t* d_src = c->d_in + (size_t)f0 * fbytes;
+            if (trace) { tev.resize(tev.size() + 4); for (int i = 0; i < 4; ++i) cudaEventCreate(&tev[tev.size() - 4 + i]); cudaEventRecord(tev[tev.size() - 4], c->st_h2d); }
             ORB_CUDA(cudaMemcpyAsync(d_src, src, (size_t)F * fbytes, cudaMemcpyHostToDevice, c->st_h2d));
             ORB_CUDA(cudaEventRecord(c->ev_in[slot], c->st_h2d));
+            if (trace) cudaEventRecord(tev[tev.size() - 3], c->st_h2d);
             // ---- kernels: chunks alternate between two compute streams, so the latency-bound small launches of one
             // chunk (upper pyramid levels, quadtree) overlap the issue-bound ones of its neighbour ----
-            cudaStream_t cs = (k & 1) ? c->st_c2 : c->stream;
+            static const int nstreams = [] { const char* e = getenv("ORB_B200_PIPE_STREAMS"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= 4) ? v : 4; }();
+            cudaStream_t css[4] = {c->stream, c->st_c2, c->st_aux[0], c->st_aux[1]};
+            cudaStream_t cs = css[(c->overlap ? (k & 1) : k % nstreams)];
             ORB_CUDA(cudaStreamWaitEvent(cs, c->ev_in[slot], 0));
             rc = orb_launch_extract(c, d_src, fmt, F, f0, rbytes, fbytes, c->d_kps_out + (size_t)f0 * ocap,
                                     c->d_desc_out + (size_t)f0 * ocap * 32, ocap, c->d_n_out + f0, cs);
             if (rc != ORB_OK) return rc;
             ORB_CUDA(cudaEventRecord(c->ev_done[slot], cs));
+            if (trace) cudaEventRecord(tev[tev.size() - 2], cs);
             // ---- D2H ----
             ORB_CUDA(cudaStreamWaitEvent(c->st_d2h, c->ev_done[slot], 0));
             ORB_CUDA(cudaMemcpyAsync(c->h_n + f0, c->d_n_out + f0, sizeof(int) * F, cudaMemcpyDeviceToHost, c->st_d2h));
@@ -725,10 +747,21 @@ int orb_extract_batch_pix(orb_ctx* c, const uint8_t* imgs, int fmt, int nframes,
                                          cudaMemcpyDeviceToHost, c->st_d2h));
             }
             ORB_CUDA(cudaEventRecord(c->ev_out[slot], c->st_d2h));
+            if (trace) cudaEventRecord(tev[tev.size() - 1], c->st_d2h);
         }
         for (int k = std::max(0, nchunks - ORB_PIPE_SLOTS); k < nchunks; ++k) { rc = finish_chunk(k); if (rc != ORB_OK) return rc; }
         ORB_CUDA(cudaStreamSynchronize(c->stream));
         ORB_CUDA(cudaStreamSynchronize(c->st_c2));
+        ORB_CUDA(cudaStreamSynchronize(c->st_aux[0]));
+        ORB_CUDA(cudaStreamSynchronize(c->st_aux[1]));
+    }
+    if (trace) {
+        for (size_t k = 0; k < tev.size() / 4; ++k) {
+            float t[4];
+            for (int i = 0; i < 4; ++i) { cudaEventElapsedTime(&t[i], t0ev, tev[4 * k + i]); cudaEventDestroy(tev[4 * k + i]); }
+            fprintf(stderr, "[pipe] chunk %2zu  h2d %.3f-%.3f  kernels done %.3f  d2h done %.3f ms\n", k, t[0], t[1], t[2], t[3]);
+        }
+        cudaEventDestroy(t0ev);
     }
     return status;
 }

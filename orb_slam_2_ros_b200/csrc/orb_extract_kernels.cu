@@ -66,7 +66,9 @@ quadtree_kernel(const unsigned long long* __restrict__ corners, const int* __res
                 unsigned short* __restrict__ node_of_key, unsigned long long* __restrict__ kept,
                 int* __restrict__ kept_count, int* __restrict__ tie_count, const __grid_constant__ Geometry g) {
     extern __shared__ __align__(16) uint8_t smem[];
-    const int l = blockIdx.x, f = blockIdx.y;
+    // longest first: level 0 holds the most corners and the largest quota, so all frames' level-0 CTAs are dispatched before
+    // any level-1 CTA (x = frame varies fastest) and the short upper-level CTAs fill the tail of the launch
+    const int l = blockIdx.y, f = blockIdx.x;
     const LevelGeom& L = g.lv[l];
     const int cap = g.max_node_cap;
     const int K = min(corner_count[f * g.nlevels + l], L.corner_cap);
@@ -542,10 +544,10 @@ int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int pixel_format, int 
             c->qt_attr_set = true;
         }
         if (F >= 8)
-            quadtree_kernel<QT_THREADS><<<dim3(g.nlevels, F), QT_THREADS, smem, st>>>(c->d_corners, d_cc, c->d_node_of_key, d_kept,
+            quadtree_kernel<QT_THREADS><<<dim3(F, g.nlevels), QT_THREADS, smem, st>>>(c->d_corners, d_cc, c->d_node_of_key, d_kept,
                                                                                        d_kept_count, d_tie, g);
         else
-            quadtree_kernel<QT_THREADS_LAT><<<dim3(g.nlevels, F), QT_THREADS_LAT, smem, st>>>(c->d_corners, d_cc, c->d_node_of_key, d_kept,
+            quadtree_kernel<QT_THREADS_LAT><<<dim3(F, g.nlevels), QT_THREADS_LAT, smem, st>>>(c->d_corners, d_cc, c->d_node_of_key, d_kept,
                                                                                                d_kept_count, d_tie, g);
         c->launches++;
     }

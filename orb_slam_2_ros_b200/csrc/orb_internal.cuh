@@ -18,7 +18,7 @@
 #define ORB_NSTAGES 5      // pyramid, FAST cells, quadtree, blur, orientation+descriptors
 #define ORB_PROF_RING 64
 #define ORB_PROF_EVENTS 10
-#define ORB_PIPE_SLOTS 4   // chunks in flight in the host-buffer pipeline
+#define ORB_PIPE_SLOTS 8   // chunks in flight in the host-buffer pipeline
 #define ORB_PIPE_CHUNK 64  // frames per chunk of the host-buffer pipeline
 
 // thread-local error string ---------------------------------------------------------------------------
