@@ -329,14 +329,17 @@ __device__ __forceinline__ int dp4a_su(unsigned a_signed, unsigned b_unsigned, i
 //   2. warp 0, one LANE per keypoint: fastAtan2 + the double-precision sincos of pin (iii)
 //   3. every warp builds its 4 descriptors (lane = descriptor byte); the 512-point pattern sits in shared memory as
 //      float4 [8][32] so that a warp-wide read is conflict-free (a per-lane index into __constant__ serialises)
+// KPW = keypoints per warp: 4 for throughput (32 per CTA), 1 for the latency shape of a few frames (8 per CTA, 4x the CTAs and
+// a 4x shorter serial chain per warp).
+template <int KPW>
 __global__ void __launch_bounds__(OD_WARPS * 32)
 orient_describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur,
                        const unsigned long long* __restrict__ kept, const int* __restrict__ kept_count,
                        const uint2* __restrict__ mom_tab, orb_kp* __restrict__ kps_out, uint8_t* __restrict__ desc_out,
                        int cap, int* __restrict__ n_out, const __grid_constant__ Geometry g) {
     __shared__ float4 s_pat[8 * 32];
-    __shared__ int s_m[OD_KPB][2];
-    __shared__ float s_ang[OD_KPB], s_a[OD_KPB], s_b[OD_KPB];
+    __shared__ int s_m[(OD_WARPS * KPW)][2];
+    __shared__ float s_ang[(OD_WARPS * KPW)], s_a[(OD_WARPS * KPW)], s_b[(OD_WARPS * KPW)];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int f = blockIdx.y;
     // ---- per-level kept counts: lane l holds level l, inclusive prefix by shuffles ----
@@ -352,7 +355,7 @@ orient_describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restric
         const int tot_all = __shfl_sync(0xffffffffu, cum, ORB_MAX_LEVELS - 1);
         if (lane == 0) n_out[f] = tot_all;
     }
-    if (blockIdx.x * OD_KPB >= total) return;   // uniform per CTA
+    if (blockIdx.x * (OD_WARPS * KPW) >= total) return;   // uniform per CTA
     // pattern: byte `i` of the descriptor uses points 16 i .. 16 i + 15; s_pat[k * 32 + i] = (x0, y0, x1, y1) of bit k
     {
         const int k = threadIdx.x >> 5, i = threadIdx.x & 31;
@@ -360,10 +363,10 @@ orient_describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restric
         s_pat[k * 32 + i] = make_float4((float)p[0], (float)p[1], (float)p[2], (float)p[3]);
     }
     // ---- output index -> (level, index in level) for this warp's 4 keypoints ----
-    int lv[OD_KPW], px[OD_KPW], py[OD_KPW], off[OD_KPW], sc[OD_KPW];
+    int lv[KPW], px[KPW], py[KPW], off[KPW], sc[KPW];
 #pragma unroll
-    for (int q = 0; q < OD_KPW; ++q) {
-        const int o = blockIdx.x * OD_KPB + warp * OD_KPW + q;
+    for (int q = 0; q < KPW; ++q) {
+        const int o = blockIdx.x * (OD_WARPS * KPW) + warp * KPW + q;
         const unsigned below = __ballot_sync(0xffffffffu, lane < g.nlevels && o < cum);   // levels whose prefix exceeds o
         lv[q] = -1; px[q] = py[q] = sc[q] = 0; off[q] = o;
         if (o < total && below) {
@@ -376,7 +379,7 @@ orient_describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restric
     }
     // ---- phase 1: IC_Angle moments (ORBextractor.cc:77-104) ----
 #pragma unroll
-    for (int q = 0; q < OD_KPW; ++q) {
+    for (int q = 0; q < KPW; ++q) {
         int m10 = 0, m01 = 0;
         if (lv[q] >= 0) {
             const LevelGeom& L = g.lv[lv[q]];
@@ -400,11 +403,11 @@ orient_describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restric
             m10 += __shfl_xor_sync(0xffffffffu, m10, o);
             m01 += __shfl_xor_sync(0xffffffffu, m01, o);
         }
-        if (lane == 0) { s_m[warp * OD_KPW + q][0] = m01; s_m[warp * OD_KPW + q][1] = m10; }
+        if (lane == 0) { s_m[warp * KPW + q][0] = m01; s_m[warp * KPW + q][1] = m10; }
     }
     __syncthreads();
     // ---- phase 2: angle and steering coefficients, one lane per keypoint ----
-    if (warp == 0) {
+    if (warp == 0 && lane < OD_WARPS * KPW) {
         const float angle = fast_atan2_deg((float)s_m[lane][0], (float)s_m[lane][1]);
         const float factorPI = (float)(3.1415926535897932384626433832795 / 180.0);  // (float)(CV_PI/180.f)
         const float ang = __fmul_rn(angle, factorPI);
@@ -415,11 +418,11 @@ orient_describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restric
     __syncthreads();
     // ---- phase 3: computeOrbDescriptor (ORBextractor.cc:106-147): lane i builds byte i ----
 #pragma unroll
-    for (int q = 0; q < OD_KPW; ++q) {
+    for (int q = 0; q < KPW; ++q) {
         if (lv[q] < 0) continue;   // warp-uniform
         const int l = lv[q];
         const LevelGeom& L = g.lv[l];
-        const int kq = warp * OD_KPW + q;
+        const int kq = warp * KPW + q;
         const float a = s_a[kq], b = s_b[kq];
         const unsigned bp = (unsigned)L.bpitch;
         // taps are addressed with non-negative 32-bit offsets from the patch window's top-left corner
@@ -555,8 +558,12 @@ int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int pixel_format, int 
     if (aux != st) ORB_CUDA(cudaStreamWaitEvent(st, c->ev_blur[which], 0));
     ORB_STAGE_MARK(4, st);
     {   // K4 + K6
-        orient_describe_kernel<<<dim3((g.total_kp_slots + OD_KPB - 1) / OD_KPB, F), OD_WARPS * 32, 0, st>>>(
-            c->d_pyr, c->d_blur, d_kept, d_kept_count, c->d_mom_tab, d_kps, d_desc, cap, d_n_out, g);
+        if (F >= 8)
+            orient_describe_kernel<OD_KPW><<<dim3((g.total_kp_slots + OD_KPB - 1) / OD_KPB, F), OD_WARPS * 32, 0, st>>>(
+                c->d_pyr, c->d_blur, d_kept, d_kept_count, c->d_mom_tab, d_kps, d_desc, cap, d_n_out, g);
+        else   // latency shape: one keypoint per warp
+            orient_describe_kernel<1><<<dim3((g.total_kp_slots + OD_WARPS - 1) / OD_WARPS, F), OD_WARPS * 32, 0, st>>>(
+                c->d_pyr, c->d_blur, d_kept, d_kept_count, c->d_mom_tab, d_kps, d_desc, cap, d_n_out, g);
         c->launches++;
     }
     ORB_STAGE_MARK(5, st);

@@ -81,9 +81,12 @@ pyr_copy0_color_kernel(const uint8_t* __restrict__ in, size_t row_stride, size_t
 // ---- fast resize: one output word x ORB_RESIZE_ROWS rows per thread ------------------------------------
 struct ColSel { unsigned sh[4]; bool hi[4]; };   // per column: funnel-shift amount and which word pair holds its taps
 
+template <bool LDG>
 __device__ __forceinline__ void hrow4(const unsigned* __restrict__ srow, int wb, const ColSel& cs, const unsigned (&cc)[4],
                                       unsigned (&h)[4]) {
-    const unsigned w0 = __ldg(srow + wb), w1 = __ldg(srow + wb + 1), w2 = __ldg(srow + wb + 2);
+    // LDG = false: the source level was written earlier by this same launch (fused tail levels): coherent loads
+    const unsigned w0 = LDG ? __ldg(srow + wb) : srow[wb], w1 = LDG ? __ldg(srow + wb + 1) : srow[wb + 1],
+                   w2 = LDG ? __ldg(srow + wb + 2) : srow[wb + 2];
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
         const unsigned lo = cs.hi[p] ? w1 : w0, hi = cs.hi[p] ? w2 : w1;
@@ -92,18 +95,14 @@ __device__ __forceinline__ void hrow4(const unsigned* __restrict__ srow, int wb,
     }
 }
 
-template <int ROWS>
-__global__ void __launch_bounds__(256)
-pyr_resize_fast_kernel(uint8_t* __restrict__ pyr, const ResizeTap* __restrict__ taps, const ResizeWord* __restrict__ wtaps,
-                       int level, const __grid_constant__ Geometry g) {
+// one work item = output word wc x rows [strip * ROWS, +ROWS) of frame f, level `level`
+template <int ROWS, bool LDG>
+__device__ __forceinline__ void resize_item(uint8_t* __restrict__ pyr, const ResizeTap* __restrict__ taps,
+                                            const ResizeWord* __restrict__ wtaps, int level, const Geometry& g, int f, int item) {
     const LevelGeom& L = g.lv[level];
     const LevelGeom& P = g.lv[level - 1];
     const int wpr = (L.w + 3) >> 2;
-    const int item = blockIdx.x * blockDim.x + threadIdx.x;
-    const int strips = (L.h + ROWS - 1) / ROWS;
-    if (item >= wpr * strips) return;
     const int strip = item / wpr, wc = item - strip * wpr;
-    const int f = blockIdx.y;
     const ResizeWord t = wtaps[L.xwtab + wc];
     ColSel cs;
 #pragma unroll
@@ -126,13 +125,13 @@ pyr_resize_fast_kernel(uint8_t* __restrict__ pyr, const ResizeTap* __restrict__ 
 #pragma unroll
             for (int p = 0; p < 4; ++p) h0[p] = h1[p];
         } else {
-            hrow4(reinterpret_cast<const unsigned*>(S) + s0 * ppw, t.wb, cs, cc, h0);
+            hrow4<LDG>(reinterpret_cast<const unsigned*>(S) + s0 * ppw, t.wb, cs, cc, h0);
         }
         if (s1 == s0) {
 #pragma unroll
             for (int p = 0; p < 4; ++p) h1[p] = h0[p];
         } else {
-            hrow4(reinterpret_cast<const unsigned*>(S) + s1 * ppw, t.wb, cs, cc, h1);
+            hrow4<LDG>(reinterpret_cast<const unsigned*>(S) + s1 * ppw, t.wb, cs, cc, h1);
         }
         have1 = s1;
         // ((b*(h>>4))>>16) == umulhi(b<<16, h>>4): 0 <= b <= 2048, h>>4 < 2^15
@@ -144,6 +143,38 @@ pyr_resize_fast_kernel(uint8_t* __restrict__ pyr, const ResizeTap* __restrict__ 
             v = __funnelshift_r(v, o, 8);                 // shifts the earlier pixels down, o becomes the top byte
         }
         *reinterpret_cast<unsigned*>(D + y * L.pitch) = v;
+    }
+}
+
+template <int ROWS>
+__global__ void __launch_bounds__(256)
+pyr_resize_fast_kernel(uint8_t* __restrict__ pyr, const ResizeTap* __restrict__ taps, const ResizeWord* __restrict__ wtaps,
+                       int level, const __grid_constant__ Geometry g) {
+    const LevelGeom& L = g.lv[level];
+    const int item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= ((L.w + 3) >> 2) * ((L.h + ROWS - 1) / ROWS)) return;
+    resize_item<ROWS, true>(pyr, taps, wtaps, level, g, blockIdx.y, item);
+}
+
+// ---- fused tail: levels [first, nlevels) of one frame in ONE launch --------------------------------------------------
+// The upper levels are tiny (<= 71 k pixels each at 640x480) and strictly dependent: as separate launches of a small batch
+// each costs a launch gap and a latency-bound wave.  Here a thread-block CLUSTER of 8 CTAs owns one frame, computes a
+// level with all its threads and meets at the hardware cluster barrier (release / acquire at cluster scope) before the
+// next one.  Used for chunks of the host pipeline and the single-frame path; large resident batches keep one launch per level.
+#define PYR_TAIL_CLUSTER 8
+#define PYR_TAIL_THREADS 512
+__global__ void __cluster_dims__(PYR_TAIL_CLUSTER, 1, 1) __launch_bounds__(PYR_TAIL_THREADS)
+pyr_resize_tail_kernel(uint8_t* __restrict__ pyr, const ResizeTap* __restrict__ taps, const ResizeWord* __restrict__ wtaps,
+                       int first_level, const __grid_constant__ Geometry g) {
+    const int f = blockIdx.y;
+    const int tid = blockIdx.x * PYR_TAIL_THREADS + threadIdx.x, nthreads = PYR_TAIL_CLUSTER * PYR_TAIL_THREADS;
+    for (int level = first_level; level < g.nlevels; ++level) {
+        const LevelGeom& L = g.lv[level];
+        const int items = ((L.w + 3) >> 2) * ((L.h + 1) >> 1);
+        for (int item = tid; item < items; item += nthreads) resize_item<2, false>(pyr, taps, wtaps, level, g, f, item);
+        if (level + 1 < g.nlevels) {
+            asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+        }
     }
 }
 
@@ -261,7 +292,16 @@ int orb_launch_pyramid(orb_ctx* c, const Geometry& g, const uint8_t* d_imgs, int
         else pyr_copy0_kernel<false><<<grd, 256, 0, st>>>(d_imgs, row_stride, frame_stride, c->d_pyr, g);
         c->launches++;
     }
-    for (int l = 1; l < g.nlevels; ++l) {
+    // small batches: the levels from the first one with <= 100 k pixels on run as ONE cluster launch (see pyr_resize_tail_kernel)
+    int tail_first = g.nlevels;
+    if (F <= 128) {
+        for (int l = g.nlevels - 1; l >= 2; --l) {
+            if (!g.lv[l].fast_resize || g.lv[l].w * g.lv[l].h > 100000) break;
+            tail_first = l;
+        }
+        if (g.nlevels - tail_first < 2) tail_first = g.nlevels;
+    }
+    for (int l = 1; l < tail_first; ++l) {
         const LevelGeom& L = g.lv[l];
         const int wpr = (L.w + 3) >> 2;
         if (L.fast_resize && F >= 8) {
@@ -276,6 +316,10 @@ int orb_launch_pyramid(orb_ctx* c, const Geometry& g, const uint8_t* d_imgs, int
             const int items = wpr * L.h;
             pyr_resize_generic_kernel<<<dim3((items + 255) / 256, F), 256, 0, st>>>(c->d_pyr, c->d_taps, l, g);
         }
+        c->launches++;
+    }
+    if (tail_first < g.nlevels) {
+        pyr_resize_tail_kernel<<<dim3(PYR_TAIL_CLUSTER, F), PYR_TAIL_THREADS, 0, st>>>(c->d_pyr, c->d_taps, c->d_wtaps, tail_first, g);
         c->launches++;
     }
     ORB_CUDA(cudaGetLastError());
