@@ -81,6 +81,35 @@ def clocks_sampler(stop, out, gpu_index):
     p.kill()
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Pin this rank (and therefore the pinned host buffers it allocates next: first touch) to the host cores next to its
+    GPU.  With 8 ranks on one box every rank otherwise allocates on whichever socket it was started on and half of the
+    H2D traffic crosses the socket interconnect.  Returns the cpulist string, or None when sysfs / nvidia-smi say nothing."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if not bus:
+            return None
+        if len(bus.split(":")[0]) == 8:   # nvidia-smi prints an 8-digit PCI domain, sysfs a 4-digit one
+            bus = bus[4:]
+        with open("/sys/bus/pci/devices/%s/local_cpulist" % bus) as fh:
+            cpulist = fh.read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpulist
+    except (OSError, ValueError, subprocess.SubprocessError):
+        return None
+
+
 def summarize_clocks(rows):
     if not rows:
         return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -310,6 +339,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (the product has no CPU path); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 and os.environ.get("ORB_BENCH_NUMA", "1") != "0" else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -549,7 +579,8 @@ def main():
             "config": {"workload": "ORBextractor 640x480 nFeatures=1000 8 levels 1.2 20/7 (BASELINE config 1), batch of %d frames "
                                    "per GPU per step, synthetic frames with +-%d grey-level noise" % (B, args.noise), "frames_per_step_per_gpu": B, "keypoints_per_step_per_gpu": n_kp,
                        "l2": "inputs larger than L2 (%d MB of frames + %d MB pyramid arena per step)" % (B * W * H >> 20, (B * 1158012) >> 20),
-                       "parallelism": "frames sharded over %d GPU(s), no collective" % world},
+                       "parallelism": "frames sharded over %d GPU(s), no collective" % world,
+                       "host_affinity": ("rank 0 bound to the cpus next to its GPU: %s" % numa_cpus) if numa_cpus else "unbound"},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "roofline": roof,
