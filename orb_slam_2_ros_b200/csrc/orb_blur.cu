@@ -25,31 +25,14 @@ __device__ __forceinline__ void blur_hrow(const unsigned* __restrict__ p, unsign
     h[3] = __dp4a(w1, BLUR_KA, __dp4a(w2, BLUR_KB, 0u));
 }
 
-__global__ void __launch_bounds__(256)
-blur_kernel(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur, const __grid_constant__ Geometry g) {
-    const int item = blockIdx.x * blockDim.x + threadIdx.x;
-    if (item >= g.blur_items) return;
-    int l = 0;
-    while (l + 1 < g.nlevels && item >= g.lv[l + 1].blur_base) ++l;
-    const LevelGeom& L = g.lv[l];
-    const int f = blockIdx.y;
-    const int it = item - L.blur_base;
-    const int strip = it / L.blur_wpr, wc = it - strip * L.blur_wpr;
-    const int y0 = strip * ORB_BLUR_ROWS;
-    const int rows = min(ORB_BLUR_ROWS, L.h - y0);
-    const int pw = L.pitch >> 2;
-    // word holding interior pixels 4wc .. 4wc+3 of row y0 - 3 (rows -3..-1 and h..h+2 are border rows)
-    const unsigned* src = reinterpret_cast<const unsigned*>(pyr + L.base + (long long)f * L.frame_stride + L.ioff) +
-                          (y0 - 3) * pw + wc;
-    unsigned* dst = reinterpret_cast<unsigned*>(blur + L.bbase + (long long)f * L.bframe_stride) + y0 * (L.bpitch >> 2) + wc;
-    const int bpw = L.bpitch >> 2;
-    unsigned win[7][4];   // horizontal sums of the 7 rows around the current output row
+template <bool FULL>
+__device__ __forceinline__ void blur_rows(const unsigned* __restrict__ src, unsigned* __restrict__ dst, long long sstep, long long dstep,
+                                          int rows, unsigned (&win)[7][4]) {
 #pragma unroll
-    for (int j = 0; j < 6; ++j) blur_hrow(src + j * pw, win[j]);
-#pragma unroll
-    for (int r = 0; r < ORB_BLUR_ROWS; ++r) {
-        if (r < rows) {
-            blur_hrow(src + (r + 6) * pw, win[(r + 6) % 7]);
+    for (int r = 0; r < ORB_BLUR_ROWS; ++r, src = reinterpret_cast<const unsigned*>(reinterpret_cast<const char*>(src) + sstep),
+                                         dst = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(dst) + dstep)) {   // running pointers
+        if (FULL || r < rows) {
+            blur_hrow(src, win[(r + 6) % 7]);
             unsigned v = 0;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -57,15 +40,43 @@ blur_kernel(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur, const _
                                      48u * (win[(r + 2) % 7][q] + win[(r + 4) % 7][q]) + 56u * win[(r + 3) % 7][q] + 32768u;
                 v |= (acc >> 16) << (8 * q);
             }
-            dst[r * bpw] = v;   // columns >= w of the last word are padding inside bpitch
+            *dst = v;   // columns >= w of the last word are padding inside bpitch
         }
     }
+}
+
+__global__ void __launch_bounds__(256)
+blur_kernel(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur, const __grid_constant__ Geometry g) {
+    // every level starts at a CTA boundary (blur_base is a multiple of 256): level and pitches are warp-uniform
+    const int cta0 = blockIdx.x * 256;
+    int l = 0;
+    while (l + 1 < g.nlevels && cta0 >= g.lv[l + 1].blur_base) ++l;
+    const LevelGeom& L = g.lv[l];
+    const int f = blockIdx.y;
+    const int it = cta0 - L.blur_base + threadIdx.x;
+    const int strip = it / L.blur_wpr, wc = it - strip * L.blur_wpr;
+    const int y0 = strip * ORB_BLUR_ROWS;
+    if (y0 >= L.h) return;
+    const int rows = min(ORB_BLUR_ROWS, L.h - y0);
+    const int pw = L.pitch >> 2;
+    // word holding interior pixels 4wc .. 4wc+3 of row y0 - 3 (rows -3..-1 and h..h+2 are border rows)
+    const unsigned* src = reinterpret_cast<const unsigned*>(pyr + L.base + (long long)f * L.frame_stride + L.ioff) +
+                          (y0 - 3) * pw + wc;
+    unsigned* dst = reinterpret_cast<unsigned*>(blur + L.bbase + (long long)f * L.bframe_stride) + y0 * (L.bpitch >> 2) + wc;
+    const int bpw = L.bpitch >> 2;
+    const long long sstep = L.pitch, dstep = L.bpitch;   // byte strides, widened once
+    unsigned win[7][4];   // horizontal sums of the 7 rows around the current output row
+#pragma unroll
+    for (int j = 0; j < 6; ++j, src = reinterpret_cast<const unsigned*>(reinterpret_cast<const char*>(src) + sstep)) blur_hrow(src, win[j]);
+    // full strips run without per-row guards, so that the compiler is free to issue the loads of the next rows early
+    if (rows == ORB_BLUR_ROWS) blur_rows<true>(src, dst, sstep, dstep, rows, win);
+    else blur_rows<false>(src, dst, sstep, dstep, rows, win);
 }
 
 }  // namespace
 
 int orb_launch_blur(orb_ctx* c, const Geometry& g, int F, cudaStream_t st) {
-    blur_kernel<<<dim3((g.blur_items + 255) / 256, F), 256, 0, st>>>(c->d_pyr, c->d_blur, g);
+    blur_kernel<<<dim3(g.blur_items / 256, F), 256, 0, st>>>(c->d_pyr, c->d_blur, g);
     c->launches++;
     ORB_CUDA(cudaGetLastError());
     return ORB_OK;

@@ -78,7 +78,7 @@ int build_geometry(orb_ctx* c, int w, int h) {
     free_geometry_buffers(c);
     Geometry& g = c->g;
     memset(&g, 0, sizeof(g));
-    g.nlevels = c->nlevels; g.w = w; g.h = h; g.ini_th = c->ini_th; g.min_th = c->min_th;
+    g.nlevels = c->nlevels; g.w = w; g.h = h; g.ini_th = c->ini_th; g.min_th = c->min_th; g.one = 1;
     const int F = c->max_batch;
     long long pyr_off = 0, blur_off = 0, corner_off = 0;
     int cells = 0, kp_slots = 0, taps = 0, wtaps = 0, max_node_cap = 0, fast_ctas = 0, border_items = 0, copy_items = 0, blur_items = 0;
@@ -156,7 +156,8 @@ int build_geometry(orb_ctx* c, int w, int h) {
         }
         // blur: one thread = one output word x ORB_BLUR_ROWS rows
         L.blur_wpr = (L.w + 3) / 4;
-        L.blur_base = blur_items; blur_items += L.blur_wpr * ((L.h + ORB_BLUR_ROWS - 1) / ORB_BLUR_ROWS);
+        L.blur_base = blur_items;   // a multiple of the CTA size: every CTA of the blur kernel lies inside ONE level (uniform level data)
+        blur_items += (L.blur_wpr * ((L.h + ORB_BLUR_ROWS - 1) / ORB_BLUR_ROWS) + 255) / 256 * 256;
     }
     if (max_node_cap > 65535) { orb_set_error("nfeatures too large"); return ORB_ERR_INVALID; }
     if ((size_t)max_node_cap * 80 > 200 * 1024) { orb_set_error("nfeatures too large for the quadtree kernel"); return ORB_ERR_INVALID; }
@@ -176,13 +177,18 @@ int build_geometry(orb_ctx* c, int w, int h) {
             ResizeWord& rw = h_wtaps[L.xwtab + wc];
             memset(&rw, 0, sizeof(rw));
             rw.wb = xt[4 * wc].s0 >> 2;
+            const int off0 = (int)xt[4 * wc].s0 - 4 * rw.wb;   // 0..3
+            rw.sh0 = 8u * (unsigned)off0;
+            unsigned sel[4] = {0, 0, 0, 0};
             for (int p = 0; p < 4; ++p) {
                 const ResizeTap& t = xt[std::min(4 * wc + p, L.w - 1)];
-                const int off = (int)t.s0 - 4 * rw.wb;
-                if (off < 0 || off > 7) L.fast_resize = 0;
-                rw.off |= (unsigned)(off & 0xFF) << (8 * p);
+                const int rel = (int)t.s0 - 4 * rw.wb - off0;   // left tap relative to column 0's: both taps must lie in 8 bytes
+                if (rel < 0 || rel > 6) L.fast_resize = 0;
+                sel[p] = (unsigned)(rel & 7) | ((unsigned)((rel + 1) & 7) << 4);
                 rw.cc[p] = (unsigned)(unsigned short)t.c0 | ((unsigned)(unsigned short)t.c1 << 16);
             }
+            rw.sel01 = sel[0] | (sel[1] << 8);
+            rw.sel23 = sel[2] | (sel[3] << 8);
         }
     }
 

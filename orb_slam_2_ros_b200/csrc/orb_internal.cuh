@@ -68,6 +68,7 @@ struct LevelGeom {
 struct Geometry {
     int nlevels, w, h;
     int ini_th, min_th;
+    int one;                     // = 1: lets kernels build multipliers (1 << k) that the compiler cannot strength-reduce into ALU-pipe shifts
     int total_cells, total_kp_slots, max_node_cap, max_tile_bytes;
     int fast_ctas, border_items, border_copy_items, blur_items;   // per-frame grid sizes of the strip / border / blur kernels
     long long pyr_frame_total;   // not used for addressing (level-major layout), informational
@@ -80,9 +81,11 @@ struct ResizeTap {  // one destination coordinate of resize(INTER_LINEAR): two s
 };
 struct __align__(16) ResizeWord {  // 4 adjacent destination columns (one output word) of the fast resize path
     int wb;              // index of the first aligned source word
-    unsigned off;        // byte offset (0..7) of each column's left tap inside (word wb, wb+1, wb+2), 8 bits each
+    unsigned sh0;        // 8 * (byte offset 0..3 of column 0's left tap inside word wb): the funnel shift that brings the
+                         // 8 source bytes the word needs into two registers (A, B)
+    unsigned sel01;      // PRMT selector over (A, B): (S[s], S[s+1]) of column 0 in bytes 0-1, of column 1 in bytes 2-3
+    unsigned sel23;      // the same for columns 2 and 3
     unsigned cc[4];      // c0 | c1 << 16 per column (Q11)
-    int pad[2];
 };
 // TMA descriptors of the pyramid levels (dims: row bytes, rows, frames of the arena) for the FAST strip loader
 struct FastTmaps { CUtensorMap m[ORB_MAX_LEVELS]; };

@@ -79,20 +79,33 @@ pyr_copy0_color_kernel(const uint8_t* __restrict__ in, size_t row_stride, size_t
 }
 
 // ---- fast resize: one output word x ORB_RESIZE_ROWS rows per thread ------------------------------------
-struct ColSel { unsigned sh[4]; bool hi[4]; };   // per column: funnel-shift amount and which word pair holds its taps
+// The ALU pipe (LOP3 / SHF / PRMT / SEL / IADD3: 2 warp-instructions per clock per SM, tools/pipe_rates.cu) bounds this
+// kernel, the FMA pipe (IMAD / IDP, also 2 per clock) runs next to it.  So: the 8 tap bytes of the 4 columns come from
+// 2 funnel shifts + 2 PRMT with host-built selectors, and the byte packing of the 4 results is phrased as
+// multiply-adds (mad.lo by 2^16 = insert into the upper half) so that it issues on the FMA pipe.  (Measured: also moving
+// the >> 4 of the horizontal pass to mul.hi overloads the FMA pipe; 38 registers -> 6 CTAs per SM.)
+__device__ __forceinline__ unsigned madhi_u32(unsigned a, unsigned b, unsigned c) {
+    unsigned d;
+    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned madlo_u32(unsigned a, unsigned b, unsigned c) {
+    unsigned d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
 
 template <bool LDG>
-__device__ __forceinline__ void hrow4(const unsigned* __restrict__ srow, int wb, const ColSel& cs, const unsigned (&cc)[4],
-                                      unsigned (&h)[4]) {
+__device__ __forceinline__ void hrow4(const unsigned* __restrict__ srow, const ResizeWord& t, unsigned (&h)[4]) {
     // LDG = false: the source level was written earlier by this same launch (fused tail levels): coherent loads
-    const unsigned w0 = LDG ? __ldg(srow + wb) : srow[wb], w1 = LDG ? __ldg(srow + wb + 1) : srow[wb + 1],
-                   w2 = LDG ? __ldg(srow + wb + 2) : srow[wb + 2];
-#pragma unroll
-    for (int p = 0; p < 4; ++p) {
-        const unsigned lo = cs.hi[p] ? w1 : w0, hi = cs.hi[p] ? w2 : w1;
-        const unsigned pair = __funnelshift_r(lo, hi, cs.sh[p]);      // byte0 = S[s], byte1 = S[s+1]
-        h[p] = __dp2a_lo(cc[p], pair, 0u) >> 4;                       // (c0*S[s] + c1*S[s+1]) >> 4
-    }
+    const unsigned w0 = LDG ? __ldg(srow) : srow[0], w1 = LDG ? __ldg(srow + 1) : srow[1], w2 = LDG ? __ldg(srow + 2) : srow[2];
+    const unsigned A = __funnelshift_r(w0, w1, t.sh0), B = __funnelshift_r(w1, w2, t.sh0);   // 8 source bytes from column 0's left tap
+    const unsigned p01 = __byte_perm(A, B, t.sel01), p23 = __byte_perm(A, B, t.sel23);      // (S[s], S[s+1]) pairs
+    // (c0*S[s] + c1*S[s+1]) >> 4
+    h[0] = __dp2a_lo(t.cc[0], p01, 0u) >> 4;
+    h[1] = __dp2a_hi(t.cc[1], p01, 0u) >> 4;
+    h[2] = __dp2a_lo(t.cc[2], p23, 0u) >> 4;
+    h[3] = __dp2a_hi(t.cc[3], p23, 0u) >> 4;
 }
 
 // one work item = output word wc x rows [strip * ROWS, +ROWS) of frame f, level `level`
@@ -104,14 +117,9 @@ __device__ __forceinline__ void resize_item(uint8_t* __restrict__ pyr, const Res
     const int wpr = (L.w + 3) >> 2;
     const int strip = item / wpr, wc = item - strip * wpr;
     const ResizeWord t = wtaps[L.xwtab + wc];
-    ColSel cs;
-#pragma unroll
-    for (int p = 0; p < 4; ++p) {
-        const unsigned off = (t.off >> (8 * p)) & 0xFFu;              // 0..7
-        cs.sh[p] = (off & 3u) * 8u; cs.hi[p] = off >= 4u;
-    }
-    const unsigned cc[4] = {t.cc[0], t.cc[1], t.cc[2], t.cc[3]};
-    const uint8_t* S = pyr + P.base + (long long)f * P.frame_stride + P.ioff;    // 16-byte aligned
+    // multipliers the compiler cannot see through (it would turn them back into ALU-pipe shifts)
+    const unsigned k16 = (unsigned)g.one << 16, k22 = (unsigned)g.one << 22, k6 = (unsigned)g.one << 6;
+    const unsigned* S = reinterpret_cast<const unsigned*>(pyr + P.base + (long long)f * P.frame_stride + P.ioff) + t.wb;   // 16-byte aligned + wb words
     uint8_t* D = pyr + L.base + (long long)f * L.frame_stride + L.ioff + 4 * wc;
     const int y0 = strip * ROWS, y1 = min(y0 + ROWS, L.h);
     const uint2* ytab = reinterpret_cast<const uint2*>(taps + L.ytab);   // ResizeTap = {u16 s0, u16 s1, s16 c0, s16 c1}
@@ -125,29 +133,29 @@ __device__ __forceinline__ void resize_item(uint8_t* __restrict__ pyr, const Res
 #pragma unroll
             for (int p = 0; p < 4; ++p) h0[p] = h1[p];
         } else {
-            hrow4<LDG>(reinterpret_cast<const unsigned*>(S) + s0 * ppw, t.wb, cs, cc, h0);
+            hrow4<LDG>(S + s0 * ppw, t, h0);
         }
         if (s1 == s0) {
 #pragma unroll
             for (int p = 0; p < 4; ++p) h1[p] = h0[p];
         } else {
-            hrow4<LDG>(reinterpret_cast<const unsigned*>(S) + s1 * ppw, t.wb, cs, cc, h1);
+            hrow4<LDG>(S + s1 * ppw, t, h1);
         }
         have1 = s1;
         // ((b*(h>>4))>>16) == umulhi(b<<16, h>>4): 0 <= b <= 2048, h>>4 < 2^15
         const unsigned b0 = (ty.y & 0xFFFFu) << 16, b1 = ty.y & 0xFFFF0000u;
-        unsigned v = 0;
+        unsigned s[4];                                    // 4 * out + (0..3), 10 bits
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            const unsigned o = (__umulhi(b1, h1[p]) + (__umulhi(b0, h0[p]) + 2u)) >> 2;   // 0 <= o <= 255
-            v = __funnelshift_r(v, o, 8);                 // shifts the earlier pixels down, o becomes the top byte
-        }
-        *reinterpret_cast<unsigned*>(D + y * L.pitch) = v;
+        for (int p = 0; p < 4; ++p) s[p] = madhi_u32(b1, h1[p], madhi_u32(b0, h0[p], 2u));
+        // out = s >> 2, packed: even columns in the 16-bit lanes of E, odd columns (shifted to their byte) in O
+        const unsigned E = madlo_u32(s[2], k16, s[0]);                       // s0 | s2 << 16
+        const unsigned O = madlo_u32(s[3], k22, s[1] * k6);                  // (s1 | s3 << 16) << 6
+        *reinterpret_cast<unsigned*>(D + y * L.pitch) = ((E >> 2) & 0x00FF00FFu) | (O & 0xFF00FF00u);
     }
 }
 
 template <int ROWS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 pyr_resize_fast_kernel(uint8_t* __restrict__ pyr, const ResizeTap* __restrict__ taps, const ResizeWord* __restrict__ wtaps,
                        int level, const __grid_constant__ Geometry g) {
     const LevelGeom& L = g.lv[level];
