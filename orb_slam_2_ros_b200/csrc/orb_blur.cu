@@ -45,7 +45,10 @@ __device__ __forceinline__ void blur_rows(const unsigned* __restrict__ src, unsi
     }
 }
 
-__global__ void __launch_bounds__(256)
+#ifndef BLUR_MINB
+#define BLUR_MINB 4
+#endif
+__global__ void __launch_bounds__(256, BLUR_MINB)
 blur_kernel(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur, const __grid_constant__ Geometry g) {
     // every level starts at a CTA boundary (blur_base is a multiple of 256): level and pitches are warp-uniform
     const int cta0 = blockIdx.x * 256;

@@ -331,8 +331,11 @@ __device__ __forceinline__ int dp4a_su(unsigned a_signed, unsigned b_unsigned, i
 //      float4 [8][32] so that a warp-wide read is conflict-free (a per-lane index into __constant__ serialises)
 // KPW = keypoints per warp: 4 for throughput (32 per CTA), 1 for the latency shape of a few frames (8 per CTA, 4x the CTAs and
 // a 4x shorter serial chain per warp).
+#ifndef OD_MINB
+#define OD_MINB 5
+#endif
 template <int KPW>
-__global__ void __launch_bounds__(OD_WARPS * 32)
+__global__ void __launch_bounds__(OD_WARPS * 32, OD_MINB)
 orient_describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur,
                        const unsigned long long* __restrict__ kept, const int* __restrict__ kept_count,
                        const uint2* __restrict__ mom_tab, orb_kp* __restrict__ kps_out, uint8_t* __restrict__ desc_out,

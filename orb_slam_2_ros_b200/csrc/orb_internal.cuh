@@ -98,8 +98,12 @@ struct __align__(16) FastStrip {   // one CTA of fast_strip_kernel: up to fast_G
     int a, lw, nw, wlo;            // smem byte shift, words loaded per row, words with evaluated pixels, first such word
     unsigned inv_lw, inv_nw, inv_wc, pad;   // ceil(2^32 / x) magic numbers for the index divisions
 };
+#ifndef ORB_BLUR_ROWS
 #define ORB_BLUR_ROWS 16   // output rows per blur thread
+#endif
+#ifndef ORB_RESIZE_ROWS
 #define ORB_RESIZE_ROWS 8  // output rows per resize thread
+#endif
 
 // 64-bit corner record: max() over records picks the reference's winner inside a quadtree node:
 //   hi 32 bits = score << 24 | (0xFFFFFF - order)   order = (cell index << 12 | y_in_cell << 6 | x_in_cell)

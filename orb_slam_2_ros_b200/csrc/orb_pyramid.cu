@@ -154,8 +154,11 @@ __device__ __forceinline__ void resize_item(uint8_t* __restrict__ pyr, const Res
     }
 }
 
+#ifndef RESIZE_MINB
+#define RESIZE_MINB 8
+#endif
 template <int ROWS>
-__global__ void __launch_bounds__(256, 6)
+__global__ void __launch_bounds__(256, RESIZE_MINB)
 pyr_resize_fast_kernel(uint8_t* __restrict__ pyr, const ResizeTap* __restrict__ taps, const ResizeWord* __restrict__ wtaps,
                        int level, const __grid_constant__ Geometry g) {
     const LevelGeom& L = g.lv[level];
