@@ -320,6 +320,7 @@ def main():
     ap.add_argument("--ref-frames", type=int, default=64)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--noise", type=int, default=8, help="+-grey-level noise of the synthetic frames (SURVEY.md §8d: 8)")
+    ap.add_argument("--e2e-callers", type=int, default=2, help="2: also time two extractor instances on two host threads")
     ap.add_argument("--no-hamming", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -434,6 +435,41 @@ def main():
     torch.cuda.synchronize()
     t_e2e = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * B * args.steps / t_e2e
+
+    # ---- the same with TWO extractor instances called from two host threads (the reference's own threading model for
+    #      stereo: two ORBextractor instances on two std::threads, Frame.cc:79-82): the pipeline fill / drain of one call
+    #      (first chunk's H2D before any kernel, last chunk's kernels + D2H after the last copy) overlaps the other's ----
+    e2e2_value = None
+    if args.e2e_callers >= 2:
+        ex2 = ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=local_rank, max_batch=B)
+        t_kps_h2 = torch.zeros((B, cap, KP_DTYPE.itemsize), dtype=torch.uint8).pin_memory()
+        t_desc_h2 = torch.zeros((B, cap, 32), dtype=torch.uint8).pin_memory()
+        kps_h2, desc_h2 = t_kps_h2.numpy(), t_desc_h2.numpy()
+        n_h2 = np.zeros(B, np.int32)
+        callers = [(ex, kps_h, desc_h, n_h), (ex2, kps_h2, desc_h2, n_h2)]
+
+        def run_caller(idx, nsteps):
+            e, k, d, n = callers[idx]
+            for _ in range(nsteps):   # ctypes releases the GIL for the duration of the call
+                check(lib().orb_extract_batch(e._h, h_frames.data_ptr(), B, W, H, W, W * H, ptr(k), ptr(d), cap, ptr(n)))
+
+        def run_both(total_steps):
+            per = [total_steps - total_steps // 2, total_steps // 2]
+            th = [threading.Thread(target=run_caller, args=(i, per[i])) for i in range(2)]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+
+        run_both(2)
+        barrier()
+        t0 = time.perf_counter()
+        run_both(args.steps)
+        torch.cuda.synchronize()
+        t_e2e2 = max_over_ranks(time.perf_counter() - t0)
+        e2e2_value = world * B * args.steps / t_e2e2
+        assert np.array_equal(n_h, n_h2) and np.array_equal(desc_h[0, :int(n_h[0])], desc_h2[0, :int(n_h2[0])])
+        del ex2
     h2d = B * W * H
     d2h = int(n_h.sum()) * (KP_DTYPE.itemsize + 32) + 4 * B
     stop.set()
@@ -581,7 +617,10 @@ def main():
                        "l2": "inputs larger than L2 (%d MB of frames + %d MB pyramid arena per step)" % (B * W * H >> 20, (B * 1158012) >> 20),
                        "parallelism": "frames sharded over %d GPU(s), no collective" % world,
                        "host_affinity": ("rank 0 bound to the cpus next to its GPU: %s" % numa_cpus) if numa_cpus else "unbound"},
-            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "callers": 1, "two_callers_value": e2e2_value,
+                    "note": "value = one caller, one blocking orb_extract_batch per step; two_callers_value = the same steps "
+                            "split over two ORBextractor instances on two host threads (reference threading model, Frame.cc:79-82)"},
             "gpu_launches": int(launches),
             "roofline": roof,
             "cpu_baseline": cpu,
