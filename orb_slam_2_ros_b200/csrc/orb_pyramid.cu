@@ -18,6 +18,10 @@
 // horizontal result of the lower source row is reused as the upper row of the next output row when they coincide.
 #include "orb_internal.cuh"
 
+#ifndef RESIZE_PACK
+#define RESIZE_PACK 2   // how the 4 results of a resize word are packed: 0 = multiply-adds (FMA pipe), 1 / 2 = part of it on the ALU pipe
+#endif
+
 namespace {
 
 __device__ __forceinline__ int reflect101(int i, int n) {
@@ -148,8 +152,16 @@ __device__ __forceinline__ void resize_item(uint8_t* __restrict__ pyr, const Res
 #pragma unroll
         for (int p = 0; p < 4; ++p) s[p] = madhi_u32(b1, h1[p], madhi_u32(b0, h0[p], 2u));
         // out = s >> 2, packed: even columns in the 16-bit lanes of E, odd columns (shifted to their byte) in O
+#if RESIZE_PACK == 0
         const unsigned E = madlo_u32(s[2], k16, s[0]);                       // s0 | s2 << 16
         const unsigned O = madlo_u32(s[3], k22, s[1] * k6);                  // (s1 | s3 << 16) << 6
+#elif RESIZE_PACK == 1
+        const unsigned E = __byte_perm(s[0], s[2], 0x5410);                  // s0 | s2 << 16 (ALU)
+        const unsigned O = madlo_u32(s[3], k22, s[1] * k6);                  // (s1 | s3 << 16) << 6
+#else
+        const unsigned E = __byte_perm(s[0], s[2], 0x5410);                  // s0 | s2 << 16 (ALU)
+        const unsigned O = madlo_u32(s[3], k22, s[1] << 6);                  // (s1 | s3 << 16) << 6
+#endif
         *reinterpret_cast<unsigned*>(D + y * L.pitch) = ((E >> 2) & 0x00FF00FFu) | (O & 0xFF00FF00u);
     }
 }
