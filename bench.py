@@ -343,6 +343,7 @@ def main():
     numa_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 and os.environ.get("ORB_BENCH_NUMA", "1") != "0" else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version banner must not precede the JSON line on stdout
         dist.init_process_group("nccl", device_id=dev)
     if args.warmup < 3:
         args.warmup = 3  # timing rule: W >= 3

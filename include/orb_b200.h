@@ -301,6 +301,27 @@ int orb_bow_transform_device(orb_voc* voc, const uint8_t* d_desc32, const int32_
                              double* d_bow_value, int32_t* d_fv_n, int32_t* d_fv_node, int32_t* d_fv_start, int32_t* d_fv_feat,
                              void* cuda_stream);
 
+/* ---- map file record payloads (reference BoostArchiver.h:46-91, KeyFrame.cc:858-864) --------------
+ * System::SaveMap writes a boost::archive::binary_oarchive with no_header (System.cc:627): primitives are stored raw in
+ * native byte order.  These entry points read / write the two PAYLOADS of that file that feed the GPU descriptor
+ * database — nothing else of the archive (class-id / object-tracking preambles, pointers, the Map graph) is interpreted:
+ *   cv::Mat record     (BoostArchiver.h:61-91):  int32 cols, int32 rows, u64 elemSize, u64 type, rows*cols*elemSize bytes
+ *   cv::KeyPoint record (BoostArchiver.h:46-58): f32 angle, i32 class_id, i32 octave, f32 response, f32 response (the
+ *                       reference serialises `response` twice and never `size`), f32 pt.x, f32 pt.y  = 28 bytes; a
+ *                       loaded KeyPoint therefore has size = 0 (cv::KeyPoint's default) — kept.
+ * Parity: the layout follows the reference's serialize() bodies; no boost is available in this image, so it is not
+ * pinned against a file written by the reference binary. */
+int orb_mat_record_bytes(int rows, int cols, size_t elem_size, size_t* bytes);
+int orb_mat_record_encode(const uint8_t* data, int rows, int cols, size_t elem_size, size_t elem_type, uint8_t* out, size_t cap,
+                          size_t* written);
+/* *data points INTO buf (no copy); consumed = bytes of the record */
+int orb_mat_record_decode(const uint8_t* buf, size_t len, int* rows, int* cols, size_t* elem_size, size_t* elem_type,
+                          const uint8_t** data, size_t* consumed);
+int orb_keypoint_records_encode(const orb_kp* kps, int n, uint8_t* out /* 28 * n bytes */);
+int orb_keypoint_records_decode(const uint8_t* buf, int n, orb_kp* kps);
+/* decode one KeyFrame::mDescriptors record (N x 32, CV_8UC1) and append its rows to the device shard; rows_added = N */
+int orb_db_add_mat_record(orb_db* db, const uint8_t* buf, size_t len, size_t* consumed, int64_t* rows_added);
+
 #ifdef __cplusplus
 }
 #endif

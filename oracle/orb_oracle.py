@@ -481,3 +481,45 @@ def fuse_search(grid, desc, u_right, inv_level_sigma2, q_u, q_v, q_ur, q_radius,
     lib().orc_fuse_search(grid._h, _p(grid.kps), _p(desc), _p(u_right), _p(inv), nq, _p(q_u), _p(q_v), _p(q_ur), _p(q_radius), _p(q_level),
                           _p(q_desc), _p(q_valid), _p(bi), _p(bd))
     return bi, bd
+
+
+# ---- map-file record payloads -----------------------------------------------------------------------
+# Plain `struct` restatement of the reference's serialize() bodies for cv::Mat and cv::KeyPoint
+# (orb_slam2/include/BoostArchiver.h:46-91) inside a boost binary archive opened with no_header (System.cc:627, primitives
+# raw, native endian).  Parity unpinned: no boost in this image, so no file written by the reference binary to compare with.
+def mat_record_encode(mat, elem_type):
+    import struct
+    mat = np.ascontiguousarray(mat)                       # BoostArchiver.h:64-66: clone when not continuous
+    rows, cols = mat.shape
+    es = mat.dtype.itemsize
+    return struct.pack("<iiQQ", cols, rows, es, elem_type) + mat.tobytes()   # :68-75 cols, rows, elem_size, elem_type, data
+
+
+def mat_record_decode(buf, offset=0):
+    import struct
+    cols, rows, es, et = struct.unpack_from("<iiQQ", buf, offset)            # :82-85
+    n = cols * rows * es                                                     # :88
+    data = np.frombuffer(buf, np.uint8, n, offset + 24)
+    return rows, cols, es, et, data, 24 + n
+
+
+def keypoint_records_encode(kps):
+    import struct
+    out = bytearray()
+    for k in kps:   # :49-57: angle, class_id, octave, response, response, pt.x, pt.y (no size)
+        out += struct.pack("<fiiffff", float(k["angle"]), int(k["class_id"]), int(k["octave"]), float(k["response"]),
+                           float(k["response"]), float(k["x"]), float(k["y"]))
+    return bytes(out)
+
+
+def keypoint_records_decode(buf, n, offset=0):
+    import struct
+    from orb_slam_2_ros_b200._lib import KP_DTYPE
+    kps = np.zeros(n, KP_DTYPE)                            # cv::KeyPoint(): size = 0, never restored
+    for i in range(n):
+        a, cid, octv, r1, r2, x, y = struct.unpack_from("<fiiffff", buf, offset + 28 * i)
+        kps[i]["angle"], kps[i]["class_id"], kps[i]["octave"] = a, cid, octv
+        kps[i]["response"] = r1
+        kps[i]["response"] = r2                            # the second `ar & kf.response` overwrites the first
+        kps[i]["x"], kps[i]["y"] = x, y
+    return kps

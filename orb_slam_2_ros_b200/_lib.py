@@ -41,6 +41,8 @@ EXPORTS = [
     "orb_top2_merge", "orb_top2_merge_device", "orb_search_by_projection", "orb_match_bruteforce", "orb_stereo_match",
     "orb_search_by_bow", "orb_search_for_triangulation", "orb_search_by_sim3", "orb_distinctive_descriptors", "orb_fuse_search", "orb_voc_create", "orb_voc_load_text", "orb_voc_destroy", "orb_voc_info", "orb_bow_transform_features",
     "orb_bow_transform_features_device", "orb_bow_transform", "orb_bow_transform_device",
+    "orb_mat_record_bytes", "orb_mat_record_encode", "orb_mat_record_decode", "orb_keypoint_records_encode",
+    "orb_keypoint_records_decode", "orb_db_add_mat_record",
 ]
 
 _lib = None
@@ -115,6 +117,13 @@ def lib():
     L.orb_bow_transform_device.argtypes = [vp, vp, vp, i32, i32, i32, i32] + [vp] * 9
     L.orb_debug_sincos_range.argtypes = [i32, C.c_uint32, C.c_longlong, vp, vp]
     L.orb_bench_issue_rate.argtypes = [i32, i32, i32, C.POINTER(C.c_double)]
+    psz = C.POINTER(C.c_size_t)
+    L.orb_mat_record_bytes.argtypes = [i32, i32, C.c_size_t, psz]
+    L.orb_mat_record_encode.argtypes = [vp, i32, i32, C.c_size_t, C.c_size_t, vp, C.c_size_t, psz]
+    L.orb_mat_record_decode.argtypes = [vp, C.c_size_t, pi32, pi32, psz, psz, C.POINTER(vp), psz]
+    L.orb_keypoint_records_encode.argtypes = [vp, i32, vp]
+    L.orb_keypoint_records_decode.argtypes = [vp, i32, vp]
+    L.orb_db_add_mat_record.argtypes = [vp, vp, C.c_size_t, psz, C.POINTER(C.c_int64)]
     _lib = L
     return L
 
