@@ -677,13 +677,20 @@ int orb_extract_batch_pix(orb_ctx* c, const uint8_t* imgs, int fmt, int nframes,
     for (int b0 = 0; b0 < nframes; b0 += c->max_batch) {
         const int B = std::min(c->max_batch, nframes - b0);
         // chunk schedule: two half-size chunks first (the kernels start after 1/16 of a 512-frame batch has arrived), then
-        // full chunks
+        // full chunks, and the last full chunk's worth of frames as 1/2 + 1/4 + 1/4: the H2D stream is the bottleneck, so
+        // the call ends when the kernels + D2H of the LAST chunk are through — the smaller it is, the shorter that tail
+        static const bool taper = [] { const char* e = getenv("ORB_B200_PIPE_TAPER"); return e && atoi(e) != 0; }();   // measured: no gain (the GPU, not the copy, is the backlog), off by default
         std::vector<int> cf0, cF;
         {
             int f = 0, k = 0;
             while (f < B) {
-                const int want = (k < 2 && B > chunk_frames) ? std::max(chunk_frames / 2, 1) : chunk_frames;
-                const int F = std::min(want, B - f);
+                int want = (k < 2 && B > chunk_frames) ? std::max(chunk_frames / 2, 1) : chunk_frames;
+                const int left = B - f;
+                if (taper && B >= 4 * chunk_frames && chunk_frames >= 32) {
+                    if (left <= chunk_frames / 2) want = std::max(chunk_frames / 4, 1);
+                    else if (left <= chunk_frames) want = chunk_frames / 2;
+                }
+                const int F = std::min(want, left);
                 cf0.push_back(f); cF.push_back(F);
                 f += F; ++k;
             }

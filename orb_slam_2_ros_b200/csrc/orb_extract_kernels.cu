@@ -27,7 +27,9 @@ __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9
 // the size>=N cut, ORBextractor.cc:700-761).  New list = reverse(children in creation order) ++ (old list
 // minus expanded parents), exactly what push_front / erase produce.
 // ======================================================================================================
+#ifndef QT_THREADS
 #define QT_THREADS 256        // throughput shape (many frames in flight)
+#endif
 #define QT_THREADS_LAT 1024   // latency shape (a few frames): 4x the threads for the key passes of the big levels
 
 struct QtNode { short x0, y0, x1, y1; };
@@ -310,7 +312,9 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 }
 
 #define OD_WARPS 8
+#ifndef OD_KPW
 #define OD_KPW 4                       // keypoints per warp
+#endif
 #define OD_KPB (OD_WARPS * OD_KPW)     // keypoints per CTA (== 32: one lane of warp 0 per keypoint in phase 2)
 #define OD_ITEMS 288                   // 31 patch rows x 9 aligned words, padded to 9 x 32 lanes
 #define OD_TAPR 19                     // |tap offset| <= 19 after rotation

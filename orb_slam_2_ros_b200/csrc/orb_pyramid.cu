@@ -184,6 +184,9 @@ pyr_resize_fast_kernel(uint8_t* __restrict__ pyr, const ResizeTap* __restrict__ 
 // each costs a launch gap and a latency-bound wave.  Here a thread-block CLUSTER of 8 CTAs owns one frame, computes a
 // level with all its threads and meets at the hardware cluster barrier (release / acquire at cluster scope) before the
 // next one.  Used for chunks of the host pipeline and the single-frame path; large resident batches keep one launch per level.
+#ifndef PYR_TAIL_MAXF
+#define PYR_TAIL_MAXF 128
+#endif
 #define PYR_TAIL_CLUSTER 8
 #define PYR_TAIL_THREADS 512
 __global__ void __cluster_dims__(PYR_TAIL_CLUSTER, 1, 1) __launch_bounds__(PYR_TAIL_THREADS)
@@ -317,7 +320,7 @@ int orb_launch_pyramid(orb_ctx* c, const Geometry& g, const uint8_t* d_imgs, int
     }
     // small batches: the levels from the first one with <= 100 k pixels on run as ONE cluster launch (see pyr_resize_tail_kernel)
     int tail_first = g.nlevels;
-    if (F <= 128) {
+    if (F <= PYR_TAIL_MAXF) {
         for (int l = g.nlevels - 1; l >= 2; --l) {
             if (!g.lv[l].fast_resize || g.lv[l].w * g.lv[l].h > 100000) break;
             tail_first = l;
