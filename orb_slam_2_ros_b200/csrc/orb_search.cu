@@ -76,6 +76,7 @@ grid_build_kernel(const orb_kp* __restrict__ kps, int n, int npad, float min_x, 
 #define SR_K 8   // unmasked top-K per query kept for the optimistic resolve
 #define SR_CH 1024  // queries staged in shared memory per chunk of the sequential walk
 #define SR_THREADS 256
+#define BF_NONE 0x7FFFFFFF   // owner of a target nobody has taken
 
 struct SearchArgs {
     const orb_kp* kps; const uint8_t* desc; const float* u_right; int n;
@@ -233,12 +234,16 @@ window_resolve_kernel(const SearchArgs a, int mode, int th_dist, float nn_ratio,
                       int* overflow) {
     extern __shared__ __align__(16) uint8_t sr_smem[];
     SrStage& S = *reinterpret_cast<SrStage*>(sr_smem);
-    uint8_t* taken = sr_smem + sizeof(SrStage);   // [n]
+    const bool init = (mode == ORB_MODE_INITIALIZATION);
+    // shared-memory layout: INITIALIZATION = stage | taken[n] | vMatchedDistance[n] | vnMatches21[n];
+    // the other modes (parallel rounds, below) = own_prev[n] | own_new[n] (int) | taken[n]
+    int* own_prev = reinterpret_cast<int*>(sr_smem);
+    int* own_new = own_prev + a.n;
+    uint8_t* taken = init ? sr_smem + sizeof(SrStage) : reinterpret_cast<uint8_t*>(own_new + a.n);   // [n]
     // SearchForInitialization state (ORBmatcher.cc:416-417): vMatchedDistance and vnMatches21, 16 bit each
     const int npad = (a.n + 3) & ~3;
     unsigned short* vmd = reinterpret_cast<unsigned short*>(taken + npad);      // 0xFFFF = INT_MAX
     unsigned short* own = vmd + npad;                                           // 0xFFFF = -1
-    const bool init = (mode == ORB_MODE_INITIALIZATION);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     __shared__ int hist[HISTO_LENGTH];
     __shared__ int s_nmatches;
@@ -254,7 +259,97 @@ window_resolve_kernel(const SearchArgs a, int mode, int th_dist, float nn_ratio,
     }
     const int need = (mode == ORB_MODE_TRACK_LAST) ? 1 : 2;
     int nmatches = 0;
-    for (int q0 = 0; q0 < a.nq; q0 += SR_CH) {
+    if (!init) {
+        // ---- TRACK_LAST / LOCAL_POINTS: the "already matched" rule (ORBmatcher.cc:87-89, 1405-1407) as a parallel
+        // fixed-point iteration (see bf_resolve_kernel): a target is invisible to query qi when it was taken before the
+        // call or is owned by an earlier BLOCKING query; own[t] = min { qi blocking : choice[qi] == t } is rebuilt every
+        // round with atomicMin until no choice changes ----
+        __shared__ int s_changed;
+        for (int qi = threadIdx.x; qi < a.nq; qi += SR_THREADS) { match_of_query[qi] = -1; match_bin[qi] = -1; }
+        for (int i = threadIdx.x; i < a.n; i += SR_THREADS) own_prev[i] = BF_NONE;
+        const int nq_up = (a.nq + 31) & ~31;
+        for (int round = 0; round <= a.nq; ++round) {
+            for (int i = threadIdx.x; i < a.n; i += SR_THREADS) own_new[i] = BF_NONE;
+            if (threadIdx.x == 0) s_changed = 0;
+            __syncthreads();
+            for (int qi = threadIdx.x; qi < nq_up; qi += SR_THREADS) {
+                int d1 = 256, d2 = 256, i1 = -1, i2 = -1, nfree = 0, base = 0;
+                bool fallback = false;
+                if (qi < a.nq) {
+                    base = a.cand_base[qi];
+                    unsigned key[SR_K];
+#pragma unroll
+                    for (int k = 0; k < SR_K; ++k) key[k] = a.topk[(size_t)qi * SR_K + k];
+#pragma unroll
+                    for (int k = 0; k < SR_K; ++k) {
+                        if (key[k] == 0xFFFFFFFFu || nfree >= need) break;
+                        const int id = a.cand_idx[base + (key[k] & 0xFFFFu)];
+                        if (taken[id] != 0 || own_prev[id] < qi) continue;
+                        if (nfree == 0) { d1 = (int)(key[k] >> 16); i1 = id; } else { d2 = (int)(key[k] >> 16); i2 = id; }
+                        ++nfree;
+                    }
+                    fallback = nfree < need && key[SR_K - 1] != 0xFFFFFFFFu;   // truncated list, too many entries taken
+                }
+                unsigned todo = __ballot_sync(0xffffffffu, fallback);
+                while (todo) {   // the warp scans the full candidate list of each such query
+                    const int src = __ffs((int)todo) - 1;
+                    todo &= todo - 1u;
+                    const int fq = __shfl_sync(0xffffffffu, qi, src);
+                    const int cnt = a.cand_count[fq], fbase = a.cand_base[fq];
+                    unsigned a1 = 0xFFFFFFFFu, a2 = 0xFFFFFFFFu;
+                    for (int p = lane; p < cnt; p += 32) {
+                        const unsigned d = a.cand_dist[fbase + p];
+                        if (d >= 256u) continue;
+                        const int id = a.cand_idx[fbase + p];
+                        if (taken[id] != 0 || own_prev[id] < fq) continue;
+                        const unsigned k = (d << 16) | (unsigned)p;
+                        a2 = min(a2, max(k, a1));
+                        a1 = min(a1, k);
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const unsigned b1 = __shfl_xor_sync(0xffffffffu, a1, o), b2 = __shfl_xor_sync(0xffffffffu, a2, o);
+                        const unsigned lo = min(a1, b1), hi = max(a1, b1);
+                        a2 = min(hi, min(a2, b2));
+                        a1 = lo;
+                    }
+                    if (lane == src) {
+                        d1 = d2 = 256; i1 = i2 = -1;
+                        if (a1 != 0xFFFFFFFFu) { d1 = (int)(a1 >> 16); i1 = a.cand_idx[fbase + (a1 & 0xFFFFu)]; }
+                        if (a2 != 0xFFFFFFFFu) { d2 = (int)(a2 >> 16); i2 = a.cand_idx[fbase + (a2 & 0xFFFFu)]; }
+                    }
+                }
+                if (qi < a.nq) {
+                    int c = -1;
+                    if (i1 >= 0 && d1 <= th_dist) {
+                        c = i1;
+                        if (mode == ORB_MODE_LOCAL_POINTS) {
+                            const int o1 = a.kps[i1].octave, bestLevel2 = (d2 < 256 && i2 >= 0) ? a.kps[i2].octave : -1;
+                            if (o1 == bestLevel2 && (float)d1 > __fmul_rn(nn_ratio, (float)d2)) c = -1;   // ORBmatcher.cc:120
+                        }
+                    }
+                    if (c != match_of_query[qi]) { match_of_query[qi] = c; s_changed = 1; }
+                    if (c >= 0 && (!a.q_obs || a.q_obs[qi])) atomicMin(own_new + c, qi);   // only such queries block their target
+                }
+            }
+            __syncthreads();
+            const int changed = s_changed;
+            int* t = own_prev; own_prev = own_new; own_new = t;
+            __syncthreads();
+            if (!changed) break;
+        }
+        // final state: taken, target_query (the LAST query that matched the target, as the sequential overwrite leaves it)
+        for (int i = threadIdx.x; i < a.n; i += SR_THREADS) if (own_prev[i] != BF_NONE) taken[i] = 1;
+        for (int qi = threadIdx.x; qi < a.nq; qi += SR_THREADS) {
+            const int m = match_of_query[qi];
+            if (m >= 0) { atomicMax(target_query + m, qi); nmatches++; }
+        }
+        atomicAdd(&s_nmatches, nmatches);
+        __syncthreads();
+        nmatches = s_nmatches;
+        __syncthreads();
+    }
+    for (int q0 = 0; init && q0 < a.nq; q0 += SR_CH) {
         const int nb = min(SR_CH, a.nq - q0);
         __syncthreads();
         // ---- stage the chunk ----
@@ -342,9 +437,11 @@ window_resolve_kernel(const SearchArgs a, int mode, int th_dist, float nn_ratio,
             }
         }
     }
-    if (threadIdx.x == 0) s_nmatches = nmatches;
-    __syncthreads();
-    nmatches = s_nmatches;
+    if (init) {
+        if (threadIdx.x == 0) s_nmatches = nmatches;
+        __syncthreads();
+        nmatches = s_nmatches;
+    }
     if (init) {
         for (int i = threadIdx.x; i < a.n; i += SR_THREADS) target_query[i] = own[i] == 0xFFFFu ? -1 : (int)own[i];   // vnMatches21
         if (check_ori) {
@@ -453,89 +550,110 @@ bf_rows_kernel(const uint8_t* __restrict__ d1, int n1, const uint8_t* __restrict
     }
 }
 
+// The order-dependent part ("a target taken by an earlier query is invisible to the later ones", ORBmatcher.cc:210) as a
+// parallel FIXED-POINT iteration instead of a sequential walk.  The sequential result is the unique solution of
+//     choice[i] = decide(i, { t : own[t] < i }),   own[t] = min { i : choice[i] == t }
+// (induction over i).  Every round evaluates all queries in parallel against the owners of the previous round and
+// rebuilds `own` with atomicMin; when a round changes no choice the recurrence holds for every i, i.e. the state IS the
+// sequential result.  Query i is final after round i + 1 at the latest, typical inputs converge in 3-6 rounds of a few
+// microseconds (the sequential walk of 1000 queries took 330 us).  The optimistic top-K list answers a query when two of
+// its entries are still visible; otherwise the query's warp scans its whole distance row cooperatively.
+template <bool SMEM>
 __global__ void __launch_bounds__(SR_THREADS)
 bf_resolve_kernel(const unsigned short* __restrict__ D, int dpitch, const unsigned* __restrict__ topk, int n1, int n2,
                   const float* __restrict__ angle1, const float* __restrict__ angle2, int th_dist, float nn_ratio,
-                  int check_ori, int* owner /*[n2]*/, int* match12, signed char* match_bin, int* nmatches_out) {
+                  int check_ori, int* owner /*[n2]*/, int* owner_scratch /*[n2], !SMEM only*/, int* match12, signed char* match_bin,
+                  int* nmatches_out) {
     extern __shared__ __align__(16) uint8_t sr_smem[];
-    SrStage& S = *reinterpret_cast<SrStage*>(sr_smem);
-    unsigned* taken_bits = reinterpret_cast<unsigned*>(sr_smem + sizeof(SrStage));   // [(n2 + 31) / 32] (ORBmatcher.cc:210)
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int* own_prev = SMEM ? reinterpret_cast<int*>(sr_smem) : owner;
+    int* own_new = SMEM ? reinterpret_cast<int*>(sr_smem) + n2 : owner_scratch;
+    const int lane = threadIdx.x & 31;
     __shared__ int hist[HISTO_LENGTH];
-    __shared__ int s_nmatches;
+    __shared__ int s_nmatches, s_changed;
     if (threadIdx.x < HISTO_LENGTH) hist[threadIdx.x] = 0;
     if (threadIdx.x == 0) s_nmatches = 0;
-    for (int j = threadIdx.x; j < n2; j += SR_THREADS) owner[j] = -1;
-    for (int j = threadIdx.x; j < (n2 + 31) / 32; j += SR_THREADS) taken_bits[j] = 0u;
-    int nmatches = 0;
-    for (int i0 = 0; i0 < n1; i0 += SR_CH) {
-        const int nb = min(SR_CH, n1 - i0);
+    for (int j = threadIdx.x; j < n2; j += SR_THREADS) own_prev[j] = BF_NONE;
+    for (int i = threadIdx.x; i < n1; i += SR_THREADS) { match12[i] = -1; match_bin[i] = -1; }
+    const int n1_up = (n1 + 31) & ~31;   // whole warps enter the cooperative fallback
+    for (int round = 0; round <= n1; ++round) {
+        for (int j = threadIdx.x; j < n2; j += SR_THREADS) own_new[j] = BF_NONE;
+        if (threadIdx.x == 0) s_changed = 0;
         __syncthreads();
-        for (int e = threadIdx.x; e < nb * SR_K; e += SR_THREADS) {
-            const int j = e / SR_K, k = e - j * SR_K;
-            const unsigned key = topk[(size_t)(i0 + j) * SR_K + k];
-            S.id[j][k] = (unsigned short)(key == 0xFFFFFFFFu ? 0xFFFFu : (key & 0xFFFFu));
-            S.dist[j][k] = (uint8_t)min(key >> 16, 255u);
-            if (k == SR_K - 1) S.flags[j] = (uint8_t)(key != 0xFFFFFFFFu ? 1 : 0);
-        }
-        for (int j = threadIdx.x; j < nb; j += SR_THREADS) { match12[i0 + j] = -1; match_bin[i0 + j] = -1; }
-        __syncthreads();
-        if (warp == 0) {
-            for (int j = 0; j < nb; ++j) {
-                const int i = i0 + j;
-                // optimistic: the first two untaken entries of the sorted unmasked top-K are the masked best / second
-                int best1 = 256, best2 = 256, bestIdx = -1, nfree = 0;
+        for (int i = threadIdx.x; i < n1_up; i += SR_THREADS) {
+            int best1 = 256, best2 = 256, bestIdx = -1, nfree = 0;
+            bool fallback = false;
+            if (i < n1) {
+                // optimistic: the first two visible entries of the sorted unmasked top-K are the masked best / second
+                unsigned key[SR_K];
+#pragma unroll
+                for (int k = 0; k < SR_K; ++k) key[k] = topk[(size_t)i * SR_K + k];
 #pragma unroll
                 for (int k = 0; k < SR_K; ++k) {
-                    const unsigned id = S.id[j][k];
-                    if (id == 0xFFFFu || nfree >= 2) break;
-                    if ((taken_bits[id >> 5] >> (id & 31)) & 1u) continue;
-                    if (nfree == 0) { best1 = S.dist[j][k]; bestIdx = (int)id; } else best2 = S.dist[j][k];
+                    if (key[k] == 0xFFFFFFFFu || nfree >= 2) break;
+                    const int id = (int)(key[k] & 0xFFFFu);
+                    if ((SMEM ? own_prev[id] : __ldcg(own_prev + id)) < i) continue;   // taken by an earlier query
+                    if (nfree == 0) { best1 = (int)min(key[k] >> 16, 255u); bestIdx = id; } else best2 = (int)min(key[k] >> 16, 255u);
                     ++nfree;
                 }
-                if (nfree < 2 && (S.flags[j] & 1)) {
-                    // fallback: masked scan of the whole row of the distance matrix (8 entries per load)
-                    unsigned a1 = 0xFFFFFFFFu, a2 = 0xFFFFFFFFu;
-                    const uint4* row = reinterpret_cast<const uint4*>(D + (size_t)i * dpitch);
-                    for (int v = lane; v < dpitch / 8; v += 32) {
-                        const uint4 t = row[v];
-                        const unsigned w[4] = {t.x, t.y, t.z, t.w};
+                fallback = nfree < 2 && key[SR_K - 1] != 0xFFFFFFFFu;   // list truncated and too many of its entries taken
+            }
+            // fallback: the lanes of the warp scan the whole row of the distance matrix of each such query (8 entries per load)
+            unsigned todo = __ballot_sync(0xffffffffu, fallback);
+            while (todo) {
+                const int src = __ffs((int)todo) - 1;
+                todo &= todo - 1u;
+                const int fi = __shfl_sync(0xffffffffu, i, src);
+                unsigned a1 = 0xFFFFFFFFu, a2 = 0xFFFFFFFFu;
+                const uint4* row = reinterpret_cast<const uint4*>(D + (size_t)fi * dpitch);
+                for (int v = lane; v < dpitch / 8; v += 32) {
+                    const uint4 t = row[v];
+                    const unsigned w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
-                        for (int h = 0; h < 8; ++h) {
-                            const int jj = v * 8 + h;
-                            if (jj >= n2 || ((taken_bits[jj >> 5] >> (jj & 31)) & 1u)) continue;
-                            const unsigned k = (((w[h >> 1] >> (16 * (h & 1))) & 0xFFFFu) << 16) | (unsigned)jj;
-                            a2 = min(a2, max(k, a1));
-                            a1 = min(a1, k);
-                        }
+                    for (int h = 0; h < 8; ++h) {
+                        const int jj = v * 8 + h;
+                        if (jj >= n2 || (SMEM ? own_prev[jj] : __ldcg(own_prev + jj)) < fi) continue;
+                        const unsigned k = (((w[h >> 1] >> (16 * (h & 1))) & 0xFFFFu) << 16) | (unsigned)jj;
+                        a2 = min(a2, max(k, a1));
+                        a1 = min(a1, k);
                     }
+                }
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        const unsigned b1 = __shfl_xor_sync(0xffffffffu, a1, o), b2 = __shfl_xor_sync(0xffffffffu, a2, o);
-                        const unsigned lo = min(a1, b1), hi = max(a1, b1);
-                        a2 = min(hi, min(a2, b2));
-                        a1 = lo;
-                    }
+                for (int o = 16; o > 0; o >>= 1) {
+                    const unsigned b1 = __shfl_xor_sync(0xffffffffu, a1, o), b2 = __shfl_xor_sync(0xffffffffu, a2, o);
+                    const unsigned lo = min(a1, b1), hi = max(a1, b1);
+                    a2 = min(hi, min(a2, b2));
+                    a1 = lo;
+                }
+                if (lane == src) {
                     best1 = best2 = 256; bestIdx = -1;
                     if (a1 != 0xFFFFFFFFu) { best1 = (int)(a1 >> 16); bestIdx = (int)(a1 & 0xFFFFu); }
                     if (a2 != 0xFFFFFFFFu) best2 = (int)(a2 >> 16);
                 }
-                if (bestIdx < 0 || best1 >= 256) continue;
-                if (best1 <= th_dist && (float)best1 < __fmul_rn(nn_ratio, (float)best2)) {   // ORBmatcher.cc:229-231
-                    if (lane == 0) {
-                        owner[bestIdx] = i;
-                        taken_bits[bestIdx >> 5] |= 1u << (bestIdx & 31);
-                        match12[i] = bestIdx;
-                    }
-                    nmatches++;
-                }
-                __syncwarp();
+            }
+            if (i < n1) {
+                int c = -1;
+                if (bestIdx >= 0 && best1 < 256 && best1 <= th_dist && (float)best1 < __fmul_rn(nn_ratio, (float)best2)) c = bestIdx;   // ORBmatcher.cc:229-231
+                if (c != match12[i]) { match12[i] = c; s_changed = 1; }
+                if (c >= 0) atomicMin(own_new + c, i);
             }
         }
+        __syncthreads();
+        const int changed = s_changed;
+        int* t = own_prev; own_prev = own_new; own_new = t;
+        __syncthreads();
+        if (!changed) break;
     }
-    if (threadIdx.x == 0) s_nmatches = nmatches;
+    // own_prev holds the final owners (every query takes its target: at most one query per target)
+    int nmatches = 0;
+    for (int i = threadIdx.x; i < n1; i += SR_THREADS) nmatches += match12[i] >= 0;
+    for (int j = threadIdx.x; j < n2; j += SR_THREADS) {
+        const int o = SMEM ? own_prev[j] : __ldcg(own_prev + j);
+        owner_scratch[j] = (o == BF_NONE) ? -1 : o;   // the result array the host reads (see the launch)
+    }
+    atomicAdd(&s_nmatches, nmatches);
     __syncthreads();
     nmatches = s_nmatches;
+    int* owner_out = owner_scratch;
     if (check_ori) {
         for (int i = threadIdx.x; i < n1; i += SR_THREADS) {      // rotation histogram (ORBmatcher.cc:236-247), parallel
             const int m = match12[i];
@@ -554,7 +672,7 @@ bf_resolve_kernel(const unsigned short* __restrict__ D, int dpitch, const unsign
         int removed = 0;
         for (int i = threadIdx.x; i < n1; i += SR_THREADS) {
             const int bin = match_bin[i];
-            if (bin >= 0 && bin != ind1 && bin != ind2 && bin != ind3) { owner[match12[i]] = -1; match12[i] = -1; removed++; }
+            if (bin >= 0 && bin != ind1 && bin != ind2 && bin != ind3) { owner_out[match12[i]] = -1; match12[i] = -1; removed++; }
         }
         atomicAdd(&s_nmatches, removed);
         __syncthreads();
@@ -980,10 +1098,11 @@ int orb_search_by_projection(int device, const orb_search_params* prm, const orb
         grid_build_kernel<<<1, 1024, npad * sizeof(unsigned), st>>>(a.kps, n, npad, a.min_x, a.min_y, a.inv_w, a.inv_h,
                                                                     (unsigned*)(Dv + o_items), (int*)(Dv + o_cells));
         window_candidates_kernel<<<(nq + 7) / 8, 256, 0, st>>>(a);
-        const size_t rsmem = sizeof(SrStage) + (size_t)((n + 3) & ~3) * 5;   // stage + taken[n] + vMatchedDistance[n] + vnMatches21[n]
+        // INITIALIZATION: stage + taken[n] + vMatchedDistance[n] + vnMatches21[n]; other modes: two int owner arrays + taken[n]
+        const size_t rsmem = std::max(sizeof(SrStage) + (size_t)((n + 3) & ~3) * 5, (size_t)9 * ((n + 3) & ~3) + 16);
         static thread_local int attr_dev = -1;
         if (attr_dev != device) {
-            ORB_CUDA(cudaFuncSetAttribute(window_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(SrStage) + GB_MAX_N * 5)));
+            ORB_CUDA(cudaFuncSetAttribute(window_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(sizeof(SrStage) + GB_MAX_N * 5, (size_t)9 * GB_MAX_N + 16)));
             attr_dev = device;
         }
         window_resolve_kernel<<<1, SR_THREADS, rsmem, st>>>(a, prm->mode, prm->th_dist, prm->nn_ratio, prm->check_orientation,
@@ -1056,7 +1175,7 @@ int orb_match_bruteforce(int device, const uint8_t* desc1, const float* angle1, 
     const size_t o_m12 = c.take(4 * (size_t)n1), o_nm = c.take(16);
     const size_t io_bytes = c.off;
     const int dpitch = (n2 + 7) & ~7;   // 16-byte aligned rows of the u16 distance matrix
-    const size_t o_D = c.take(2 * (size_t)n1 * dpitch), o_topk = c.take(4 * (size_t)n1 * BF_K), o_owner = c.take(4 * (size_t)n2), o_bin = c.take(n1);
+    const size_t o_D = c.take(2 * (size_t)n1 * dpitch), o_topk = c.take(4 * (size_t)n1 * BF_K), o_owner = c.take(4 * (size_t)n2), o_owner2 = c.take(4 * (size_t)n2), o_bin = c.take(n1);
     Workspace& W = g_ws;
     int rc = W.prepare(device, c.off, io_bytes);
     if (rc != ORB_OK) return rc;
@@ -1067,10 +1186,24 @@ int orb_match_bruteforce(int device, const uint8_t* desc1, const float* angle1, 
     if (angle2) memcpy(H + o_a2, angle2, 4 * (size_t)n2);
     ORB_CUDA(cudaMemcpyAsync(Dv, H, in_bytes, cudaMemcpyHostToDevice, st));
     bf_rows_kernel<<<(n1 + 7) / 8, 256, 0, st>>>(Dv + o_d1, n1, Dv + o_d2, n2, (unsigned short*)(Dv + o_D), dpitch, (unsigned*)(Dv + o_topk));
-    bf_resolve_kernel<<<1, SR_THREADS, sizeof(SrStage) + 4 * (size_t)((n2 + 31) / 32), st>>>((const unsigned short*)(Dv + o_D), dpitch, (const unsigned*)(Dv + o_topk), n1, n2,
-                                                                  (const float*)(Dv + o_a1), (const float*)(Dv + o_a2), th_dist, nn_ratio,
-                                                                  check_orientation, (int*)(Dv + o_owner), (int*)(Dv + o_m12),
-                                                                  (signed char*)(Dv + o_bin), (int*)(Dv + o_nm));
+    {
+        const size_t own_smem = 8 * (size_t)n2;   // two owner arrays in shared memory when they fit, else in the workspace
+        static bool attr_set[64] = {};   // per device
+        if (!attr_set[device & 63]) {
+            ORB_CUDA(cudaFuncSetAttribute(bf_resolve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_set[device & 63] = true;
+        }
+        if (own_smem <= 200 * 1024)
+            bf_resolve_kernel<true><<<1, SR_THREADS, own_smem, st>>>((const unsigned short*)(Dv + o_D), dpitch, (const unsigned*)(Dv + o_topk), n1, n2,
+                                                                     (const float*)(Dv + o_a1), (const float*)(Dv + o_a2), th_dist, nn_ratio, check_orientation,
+                                                                     (int*)(Dv + o_owner), (int*)(Dv + o_owner2), (int*)(Dv + o_m12),
+                                                                     (signed char*)(Dv + o_bin), (int*)(Dv + o_nm));
+        else
+            bf_resolve_kernel<false><<<1, SR_THREADS, 0, st>>>((const unsigned short*)(Dv + o_D), dpitch, (const unsigned*)(Dv + o_topk), n1, n2,
+                                                               (const float*)(Dv + o_a1), (const float*)(Dv + o_a2), th_dist, nn_ratio, check_orientation,
+                                                               (int*)(Dv + o_owner), (int*)(Dv + o_owner2), (int*)(Dv + o_m12),
+                                                               (signed char*)(Dv + o_bin), (int*)(Dv + o_nm));
+    }
     ORB_CUDA(cudaGetLastError());
     ORB_CUDA(cudaMemcpyAsync(H + o_m12, Dv + o_m12, io_bytes - o_m12, cudaMemcpyDeviceToHost, st));
     ORB_CUDA(cudaStreamSynchronize(st));
