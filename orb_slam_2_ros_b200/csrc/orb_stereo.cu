@@ -137,21 +137,34 @@ stereo_median_kernel(int N, float* uRight, float* depth, const int* __restrict__
     const int count = s_count;
     if (count == 0) { if (threadIdx.x == 0) *nkept_out = 0; return; }
     const int target = count / 2;
-    // element of rank `target` in (sad, index) order; the SADs are staged in shared memory (N <= ST_MAX_N), so the
-    // O(N^2) rank count runs at shared-memory bandwidth
+    // VALUE of the element of rank `target` among the kept SADs (vDistIdx[size/2].first after the sort, Frame.cc:663-664):
+    // bitwise radix select over the SADs staged in shared memory, one block-wide count per bit (the SADs are sums of
+    // 121 byte differences, < 2^15, so ~15 rounds of two barriers instead of an O(N^2) rank count)
     extern __shared__ int s_sad[];
-    for (int i = threadIdx.x; i < N; i += blockDim.x) s_sad[i] = sad[i];
+    __shared__ int s_max, s_cnt[2];
+    if (threadIdx.x == 0) { s_max = 0; s_cnt[0] = s_cnt[1] = 0; }
     __syncthreads();
-    for (int i = threadIdx.x; i < N; i += blockDim.x) {
-        const int si = s_sad[i];
-        if (si < 0) continue;
-        int rank = 0;
-        for (int j = 0; j < N; ++j) {
-            const int sj = s_sad[j];
-            rank += (sj >= 0) && (sj < si || (sj == si && j < i));
+    int lmax = 0;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) { const int v = sad[i]; s_sad[i] = v; lmax = max(lmax, v); }
+    atomicMax(&s_max, lmax);
+    __syncthreads();
+    unsigned prefix = 0;
+    int rank = target;
+    for (int bit = 31 - __clz(max(s_max, 1)); bit >= 0; --bit) {
+        int c0 = 0;   // kept SADs that agree with the prefix above `bit` and have a 0 there
+        for (int i = threadIdx.x; i < N; i += blockDim.x) {
+            const int v = s_sad[i];
+            c0 += (v >= 0) && (((unsigned)v >> (bit + 1)) == (prefix >> (bit + 1))) && !(((unsigned)v >> bit) & 1u);
         }
-        if (rank == target) s_median = si;
+        int* cnt = &s_cnt[bit & 1];
+        if (c0) atomicAdd(cnt, c0);
+        __syncthreads();
+        const int total0 = *cnt;
+        if (rank >= total0) { rank -= total0; prefix |= 1u << bit; }
+        if (threadIdx.x == 0) s_cnt[(bit & 1) ^ 1] = 0;   // the other counter is idle now: ready for the next round
+        __syncthreads();
     }
+    if (threadIdx.x == 0) s_median = (int)prefix;
     __syncthreads();
     const float thDist = __fmul_rn(1.5f * 1.4f, (float)s_median);
     int removed = 0;
