@@ -367,3 +367,55 @@ def test_top2_merge_device_equals_host(oracle):
         assert np.array_equal(dev[f], host[f]), f
     _same_top2(dev, oracle.hamming_top2(q, db))
     assert dev["best_idx"][0] == 10 and dev["second_idx"][0] == 7000
+
+
+def _flip_first_bits(desc, j):
+    """a copy of the 32-byte descriptor with its first j bits inverted (Hamming distance j)."""
+    out = desc.copy()
+    bits = np.unpackbits(out, bitorder="little")
+    bits[:j] ^= 1
+    return np.packbits(bits, bitorder="little")
+
+
+@pytest.mark.gpu
+def test_resolve_rounds_long_dependency_chain(oracle):
+    """Adversarial input for the parallel fixed-point resolve: identical queries, targets at distances 0, 1, 2, ...  The
+    sequential rule makes query i take target i (every earlier target is gone), so the dependency chain is as long as the
+    match count and query i only becomes final in round i + 1; beyond 8 taken targets every top-8 list is exhausted and
+    the full-row / full-candidate-list scans run.  Brute force (ratio 0.99: the chain ends where i >= 0.99 (i + 1)) and
+    TRACK_LAST / LOCAL_POINTS projection searches (all targets in every query's window)."""
+    from orb_slam_2_ros_b200 import ORBmatcher
+    from orb_slam_2_ros_b200._lib import KP_DTYPE
+    from orb_slam_2_ros_b200.matcher import MODE_LOCAL_POINTS, MODE_TRACK_LAST
+    rng = np.random.default_rng(5)
+    q0 = rng.integers(0, 256, 32, dtype=np.uint8)
+    n1, n2 = 150, 200
+    d1 = np.repeat(q0[None], n1, 0)
+    d2 = np.stack([_flip_first_bits(q0, j) for j in range(n2)])
+    perm = rng.permutation(n2)                                   # target order must not matter
+    d2p = d2[perm]
+    a1 = np.zeros(n1, np.float32); a2 = np.zeros(n2, np.float32)
+    for ratio, th in ((0.99, 100), (0.9, 100), (1.5, 60)):
+        nm_o, m_o = oracle.match_bruteforce(d1, a1, d2p, a2, th, ratio, True)
+        nm_g, m_g = ORBmatcher(ratio, True).MatchBruteForce(d1, a1, d2p, a2, th)
+        assert nm_g == nm_o and np.array_equal(m_g, m_o)
+        if ratio == 0.99:
+            assert nm_o == 99 and np.array_equal(perm[m_o[:99]], np.arange(99))   # the chain: query i -> distance i
+    # projection searches: all targets within 10 px of every query
+    kb = np.zeros(n2, KP_DTYPE)
+    kb["x"] = 300 + rng.uniform(-10, 10, n2); kb["y"] = 200 + rng.uniform(-10, 10, n2)
+    kb["octave"] = rng.integers(0, 3, n2); kb["size"] = 31; kb["class_id"] = -1
+    bounds = (0.0, 0.0, 640.0, 480.0)
+    grid = oracle.Grid(kb, *bounds)
+    q_u = np.full(n1, 300, np.float32); q_v = np.full(n1, 200, np.float32); q_r = np.full(n1, 40, np.float32)
+    q_min, q_max = np.full(n1, -1, np.int32), np.full(n1, -1, np.int32)
+    q_obs = (np.arange(n1) % 7 != 3).astype(np.uint8)            # some queries do not block their target
+    for mode, omode, ratio in ((MODE_TRACK_LAST, oracle.MODE_TRACK_LAST, 0.9), (MODE_LOCAL_POINTS, oracle.MODE_LOCAL_POINTS, 0.99)):
+        t_o, t_g = np.zeros(n2, np.uint8), np.zeros(n2, np.uint8)
+        t_o[perm[:3]] = 1; t_g[perm[:3]] = 1                     # the three closest targets were taken before the call
+        nm_o, moq_o, tq_o = oracle.search_by_projection(omode, grid, d2p, None, t_o, q_u, q_v, q_r, q_min, q_max, d1, q_angle=a1,
+                                                        q_obs=q_obs, th_dist=100, nn_ratio=ratio, check_orientation=False)
+        nm_g, moq_g, tq_g = ORBmatcher(ratio, False).SearchByProjection(mode, kb, d2p, bounds, t_g, q_u, q_v, q_r, q_min, q_max, d1,
+                                                                      q_angle=a1, q_obs=q_obs, th_dist=100)
+        assert nm_o > 30
+        assert nm_g == nm_o and np.array_equal(moq_g, moq_o) and np.array_equal(tq_g, tq_o) and np.array_equal(t_g, t_o)
