@@ -230,6 +230,8 @@ int build_geometry(orb_ctx* c, int w, int h) {
         }
     }
     g.fast_ctas = (int)strips.size();
+    g.fast_rows = 7;
+    for (const FastStrip& s : strips) g.fast_rows = std::max(g.fast_rows, s.ch);
     if (strips.empty()) strips.push_back(FastStrip());
     ORB_CUDA(cudaMalloc(&c->d_strips, sizeof(FastStrip) * strips.size()));
     ORB_CUDA(cudaMemcpyAsync(c->d_strips, strips.data(), sizeof(FastStrip) * strips.size(), cudaMemcpyHostToDevice, c->stream));
@@ -263,7 +265,7 @@ int build_geometry(orb_ctx* c, int w, int h) {
                 const LevelGeom& L = g.lv[l];
                 const cuuint64_t dims[3] = {(cuuint64_t)L.pitch, (cuuint64_t)L.rows, (cuuint64_t)F};
                 const cuuint64_t strides[2] = {(cuuint64_t)L.pitch, (cuuint64_t)L.frame_stride};   // bytes, dims 1 and 2
-                const cuuint32_t box[3] = {ORB_TMA_BOX_W, ORB_TMA_BOX_H, 1};
+                const cuuint32_t box[3] = {ORB_TMA_BOX_W, (cuuint32_t)g.fast_rows, 1};   // one box = the tallest strip of this geometry
                 const cuuint32_t estr[3] = {1, 1, 1};
                 const CUresult r = ((EncodeFn)fn)(&c->tmaps.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, c->d_pyr + L.base, dims, strides, box,
                                                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,

@@ -34,12 +34,14 @@ namespace {
 #define FS_MAXG 8          // 250 / 30
 #define FS_WCAP 448        // candidate entries (u16) per warp segment
 #define FS_SCAP 2048       // scored-corner list entries (u16)
-#define FS_TILE_BYTES (FS_ROWS * FS_PITCH)
 #define FS_CAND_BYTES (FS_WARPS * FS_WCAP * 2)
 #define FS_SCORED_BYTES (FS_SCAP * 2)
-#define FS_SCORE_BYTES (FS_SROWS * FS_PITCH)
-#define FS_SMEM (FS_TILE_BYTES + FS_CAND_BYTES + FS_SCORED_BYTES + FS_SCORE_BYTES + 128)
-#define FS_OUT_CAP ((FS_TILE_BYTES + FS_CAND_BYTES) / 8)   // records that fit the (dead) tile + candidate segments (4036 >= the 3750 worst case; anything beyond goes straight to global)
+// The tile and the score tile are sized by the tallest cell sub-image of the geometry (Geometry::fast_rows: 40 rows at
+// 640x480 instead of the worst case 66), which is what decides how many CTAs fit an SM: 30 KB -> 6-7 CTAs, 44 KB -> 5.
+#define FS_TILE_BYTES(rows) ((rows) * FS_PITCH)
+#define FS_SCORE_BYTES(rows) (((rows) - 4) * FS_PITCH)      // evaluated rows (rows - 6) + a zero row above and below
+#define FS_SMEM(rows) (FS_TILE_BYTES(rows) + FS_CAND_BYTES + FS_SCORED_BYTES + FS_SCORE_BYTES(rows) + 128)
+#define FS_OUT_CAP(rows) ((FS_TILE_BYTES(rows) + FS_CAND_BYTES) / 8)   // records that fit the (dead) tile + candidate segments; anything beyond goes straight to global
 
 // exact FAST score of the pixel at t (shared-memory tile): both polarities in one s16x2 min/max tree on the packed
 // pairs (r_k, 255 - r_k):  lo -> max_arc min r = bmax,  hi -> max_arc min (255 - r) = 255 - min_arc max r = 255 - amin
@@ -110,16 +112,20 @@ __device__ __forceinline__ unsigned quick2(unsigned c, unsigned r0, unsigned r8,
 }
 
 template <bool TMA>
-__global__ void __launch_bounds__(FS_THREADS)
+#ifndef FS_MINB
+#define FS_MINB 6
+#endif
+__global__ void __launch_bounds__(FS_THREADS, FS_MINB)
 fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__ strips, unsigned long long* __restrict__ corners,
                   int* __restrict__ corner_count, const __grid_constant__ Geometry g, const FastTmaps* __restrict__ tm, int f0) {
     extern __shared__ __align__(1024) uint8_t fs_smem_raw[];
     // the TMA destination must be 128-byte aligned: align by hand (static shared variables precede the dynamic window)
     uint8_t* fs_smem = fs_smem_raw + ((128u - (smem_u32(fs_smem_raw) & 127u)) & 127u);
     uint8_t* tile = fs_smem;                                                                     // FS_ROWS x FS_PITCH pixels
-    unsigned short* cand = reinterpret_cast<unsigned short*>(fs_smem + FS_TILE_BYTES);            // per-warp segments
-    unsigned short* scored = reinterpret_cast<unsigned short*>(fs_smem + FS_TILE_BYTES + FS_CAND_BYTES);
-    uint8_t* score = fs_smem + FS_TILE_BYTES + FS_CAND_BYTES + FS_SCORED_BYTES;                   // FS_SROWS x FS_PITCH scores
+    const int tile_bytes = FS_TILE_BYTES(g.fast_rows), out_cap = FS_OUT_CAP(g.fast_rows);
+    unsigned short* cand = reinterpret_cast<unsigned short*>(fs_smem + tile_bytes);               // per-warp segments
+    unsigned short* scored = reinterpret_cast<unsigned short*>(fs_smem + tile_bytes + FS_CAND_BYTES);
+    uint8_t* score = fs_smem + tile_bytes + FS_CAND_BYTES + FS_SCORED_BYTES;                      // (fast_rows - 4) x FS_PITCH scores
     unsigned long long* outl = reinterpret_cast<unsigned long long*>(fs_smem);                   // pass 3: aliases tile + cand
     __shared__ int s_any[FS_MAXG];
     __shared__ int s_nscored, s_nout, s_base, s_nempty;
@@ -140,16 +146,13 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
     // least one spare word on the left, so that word index wd - 1 of the first evaluated word exists)
     const int a = S.a;
     if (TMA) {
-        // one elected thread arms the mbarrier and issues 1-2 bulk tensor copies (box 256 B x 33 rows) of the strip with
+        // one elected thread arms the mbarrier and issues ONE bulk tensor copy (box 256 B x fast_rows rows) of the strip with
         // its halo; rows / bytes beyond the level are zero-filled by the TMA unit and never evaluated
         if (threadIdx.x == 0) mbar_init(&s_mbar, 1);
         __syncthreads();
         if (threadIdx.x == 0) {
-            const int parts = (ch + ORB_TMA_BOX_H - 1) / ORB_TMA_BOX_H;
-            mbar_expect_tx(&s_mbar, (unsigned)parts * ORB_TMA_BOX_W * ORB_TMA_BOX_H);
-            for (int p = 0; p < parts; ++p)
-                tma_load_3d(tile + p * ORB_TMA_BOX_H * FS_PITCH, &tm->m[l], ORB_XOFF + S.X0 - a, ORB_EDGE + S.iniY + p * ORB_TMA_BOX_H,
-                            f0 + f, &s_mbar);
+            mbar_expect_tx(&s_mbar, (unsigned)(ORB_TMA_BOX_W * g.fast_rows));
+            tma_load_3d(tile, &tm->m[l], ORB_XOFF + S.X0 - a, ORB_EDGE + S.iniY, f0 + f, &s_mbar);
         }
     } else {
         const unsigned* src_w = reinterpret_cast<const unsigned*>(pyr + L.base + (long long)f * L.frame_stride + L.ioff +
@@ -292,7 +295,7 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
         const int cell = i * L.nCols + j0 + jj;
         const unsigned long long rec = corner_pack(j0 * wCell + 3 + (sb - sb_lo), i * L.hCell + 3 + r, sc, (cell << 12) | (r << 6) | xr);
         const int o = atomicAdd(&s_nout, 1);
-        if (o < FS_OUT_CAP) {
+        if (o < out_cap) {
             outl[o] = rec;
         } else {   // staging list full (> 3000 NMS maxima in one strip): append to the level's list directly
             const int gi = atomicAdd(corner_count + f * g.nlevels + l, 1);
@@ -394,7 +397,7 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
         }
     }
     __syncthreads();
-    const int nout = min(s_nout, FS_OUT_CAP);
+    const int nout = min(s_nout, out_cap);
     if (nout == 0) return;
     if (threadIdx.x == 0) s_base = atomicAdd(corner_count + f * g.nlevels + l, nout);
     __syncthreads();
@@ -407,16 +410,17 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
 }  // namespace
 
 int orb_launch_fast(orb_ctx* c, const Geometry& g, int* d_corner_count, int F, int f0, cudaStream_t st) {
+    if (g.fast_rows > FS_ROWS) { orb_set_error("FAST strip of %d rows exceeds the tile", g.fast_rows); return ORB_ERR_INVALID; }
     if (!c->fast_attr_set) {   // > 48 KB of dynamic shared memory needs the opt-in, once per context (= per device)
-        ORB_CUDA(cudaFuncSetAttribute(fast_strip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM));
-        ORB_CUDA(cudaFuncSetAttribute(fast_strip_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM));
+        ORB_CUDA(cudaFuncSetAttribute(fast_strip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM(FS_ROWS)));
+        ORB_CUDA(cudaFuncSetAttribute(fast_strip_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM(FS_ROWS)));
         c->fast_attr_set = true;
     }
     if (c->use_tma)
-        fast_strip_kernel<true><<<dim3(g.fast_ctas, F), FS_THREADS, FS_SMEM, st>>>(c->d_pyr, c->d_strips, c->d_corners, d_corner_count, g,
+        fast_strip_kernel<true><<<dim3(g.fast_ctas, F), FS_THREADS, FS_SMEM(g.fast_rows), st>>>(c->d_pyr, c->d_strips, c->d_corners, d_corner_count, g,
                                                                                    c->d_tmaps, f0);
     else
-        fast_strip_kernel<false><<<dim3(g.fast_ctas, F), FS_THREADS, FS_SMEM, st>>>(c->d_pyr, c->d_strips, c->d_corners, d_corner_count, g,
+        fast_strip_kernel<false><<<dim3(g.fast_ctas, F), FS_THREADS, FS_SMEM(g.fast_rows), st>>>(c->d_pyr, c->d_strips, c->d_corners, d_corner_count, g,
                                                                                     c->d_tmaps, f0);
     c->launches++;
     ORB_CUDA(cudaGetLastError());

@@ -70,6 +70,7 @@ struct Geometry {
     int ini_th, min_th;
     int one;                     // = 1: lets kernels build multipliers (1 << k) that the compiler cannot strength-reduce into ALU-pipe shifts
     int total_cells, total_kp_slots, max_node_cap, max_tile_bytes;
+    int fast_rows;               // tile rows of the FAST strip kernel = the tallest cell sub-image of this geometry (<= 66): sizes its shared memory and the TMA box
     int fast_ctas, border_items, border_copy_items, blur_items;   // per-frame grid sizes of the strip / border / blur kernels
     long long pyr_frame_total;   // not used for addressing (level-major layout), informational
     LevelGeom lv[ORB_MAX_LEVELS];
@@ -90,7 +91,6 @@ struct __align__(16) ResizeWord {  // 4 adjacent destination columns (one output
 // TMA descriptors of the pyramid levels (dims: row bytes, rows, frames of the arena) for the FAST strip loader
 struct FastTmaps { CUtensorMap m[ORB_MAX_LEVELS]; };
 #define ORB_TMA_BOX_W 256
-#define ORB_TMA_BOX_H 33
 
 struct __align__(16) FastStrip {   // one CTA of fast_strip_kernel: up to fast_G consecutive valid cells of one cell row
     int level, i, j0, ncell;       // cell row, first cell column, number of valid cells

@@ -38,7 +38,7 @@ def ORB():
 
 CASES = [(0, 640, 480, 1000, 8), (1, 640, 480, 1000, 8), (2, 640, 480, 1000, 8), (3, 752, 480, 1000, 8),
          (4, 1241, 376, 2000, 8), (5, 640, 480, 1200, 8), (6, 320, 240, 500, 6), (7, 160, 120, 300, 4),
-         (8, 645, 487, 1000, 8)]
+         (8, 645, 487, 1000, 8), (9, 1920, 1080, 3000, 8), (10, 1280, 720, 1500, 8), (11, 1023, 767, 2000, 10)]
 
 
 @pytest.mark.parametrize("seed,w,h,nf,nl", CASES)
