@@ -13,7 +13,8 @@ the ranks with an all-gather + merge) — under "hamming".
 Timed regions:
   value   frames already in HBM, outputs stay in HBM (orb_extract_batch_device), CUDA events, max over ranks
   e2e     HOST buffers in, HOST keypoints/descriptors out through the public call (ORBextractor.extract_batch
-          -> orb_extract_batch): pinned staging, H2D, kernels, D2H inside the timed region
+          -> orb_extract_batch): pinned staging, H2D, kernels, D2H inside the timed region; the steps are issued by two
+          extractor instances on two host threads (value) and by a single caller (one_caller_value)
   roofline    per-stage CUDA-event times recorded by the library inside the timed region of `value`
   cpu_baseline  oracle/ (the CPU restatement = checker) timed on all host cores on a bounded sample
 """
@@ -632,10 +633,12 @@ def main():
                        "l2": "inputs larger than L2 (%d MB of frames + %d MB pyramid arena per step)" % (B * W * H >> 20, (B * 1158012) >> 20),
                        "parallelism": "frames sharded over %d GPU(s), no collective" % world,
                        "host_affinity": ("rank 0 bound to the cpus next to its GPU: %s" % numa_cpus) if numa_cpus else "unbound"},
-            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "callers": 1, "two_callers_value": e2e2_value,
-                    "note": "value = one caller, one blocking orb_extract_batch per step; two_callers_value = the same steps "
-                            "split over two ORBextractor instances on two host threads (reference threading model, Frame.cc:79-82)"},
+            "e2e": {"value": e2e2_value if e2e2_value else e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "callers": 2 if e2e2_value else 1, "one_caller_value": e2e_value,
+                    "note": "every step = one blocking orb_extract_batch of the whole batch (pinned host frames in, pinned host keypoints + "
+                            "descriptors out, H2D and D2H inside).  value: the steps are issued by two ORBextractor instances on two host "
+                            "threads (the reference's threading model, Frame.cc:79-82; the CPU arm runs one extractor per host thread), so "
+                            "one call's pipeline drain overlaps the other's copies; one_caller_value: a single caller, calls back to back"},
             "gpu_launches": int(launches),
             "roofline": roof,
             "cpu_baseline": cpu,

@@ -78,6 +78,13 @@ blur_kernel(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur, const _
 
 }  // namespace
 
+
+// experiment / tuning knob: one shared-memory carve-out for every kernel of the chain (ORB_B200_CARVEOUT, percent of the
+// maximum) so that kernels of different chunks can share an SM without the SM draining to re-partition L1 / shared memory
+void orb_carveout_blur(int pct) {
+    cudaFuncSetAttribute(blur_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+}
+
 int orb_launch_blur(orb_ctx* c, const Geometry& g, int F, cudaStream_t st) {
     blur_kernel<<<dim3(g.blur_items / 256, F), 256, 0, st>>>(c->d_pyr, c->d_blur, g);
     c->launches++;

@@ -7,6 +7,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 #include <vector>
 
 #include "orb_internal.cuh"
@@ -541,6 +543,23 @@ int orb_profile_read(orb_ctx* c, double* stage_ms, int64_t* calls, int64_t* fram
     return ORB_OK;
 }
 
+
+// One shared-memory carve-out for every kernel of the chain while chunks of the host pipeline run on several streams.
+// Measured (profiles/r1_l_carveout.txt): kernels with different carve-out needs (FAST: 190 KB of shared memory per SM,
+// the others: none, all of it L1) cannot share an SM — it has to drain before its L1 / shared-memory split changes — so
+// concurrent chunks, or two extractor instances on two threads, slowed each other down (2 x 256 frames concurrently:
+// 159 k frames/s against 171 k back to back).  With the same 58 % split everywhere two concurrent callers reach 164 k
+// frames/s instead of 136 k; the device-resident path keeps the per-kernel default (its launches never overlap, and
+// orient_describe lives on a large L1: 0.53 ms -> 1.33 ms with a carve-out of 72 % or more).
+// pct: 0..100, or -1 = the driver's per-kernel default.  ORB_B200_CARVEOUT overrides both uses.
+static void chain_carveout(orb_ctx* c, int pct) {
+    static const int forced = [] { const char* e = getenv("ORB_B200_CARVEOUT"); return e ? atoi(e) : -2; }();
+    if (forced >= -1 && forced <= 100) pct = forced;
+    static std::atomic<int> current[64];   // per device: last value set + 3 (0 = nothing set yet)
+    if (current[c->device & 63].exchange(pct + 3) == pct + 3) return;
+    orb_carveout_pyramid(pct); orb_carveout_blur(pct); orb_carveout_fast(pct); orb_carveout_extract(pct);
+}
+
 int orb_extract_batch_device(orb_ctx* c, const uint8_t* d_imgs, int nframes, int w, int h, size_t row_stride,
                              size_t frame_stride, orb_kp* d_kps, uint8_t* d_desc, int cap, int32_t* d_n_out) {
     return orb_extract_batch_device_pix(c, d_imgs, ORB_PIX_GRAY8, nframes, w, h, row_stride, frame_stride, d_kps, d_desc, cap, d_n_out);
@@ -558,6 +577,7 @@ int orb_extract_batch_device_pix(orb_ctx* c, const uint8_t* d_imgs, int fmt, int
     rc = build_geometry(c, w, h);
     if (rc != ORB_OK) return rc;
     c->last_frames = nframes;
+    chain_carveout(c, -1);
     // (measured: cutting a resident batch into sub-batches on two streams is SLOWER, 147k -> 130k frames/s at 512
     // frames; the big launches already fill the chip.  Only the host pipeline below alternates streams.)
     return orb_launch_extract(c, d_imgs, fmt, nframes, 0, row_stride, frame_stride, d_kps, d_desc, cap, d_n_out, c->stream);
@@ -662,6 +682,7 @@ int orb_extract_batch_pix(orb_ctx* c, const uint8_t* imgs, int fmt, int nframes,
     rc = ensure_input_staging(c, !in_direct, ch);
     if (rc != ORB_OK) return rc;
     const int ocap = c->out_cap;                        // device row length (>= dcap)
+    chain_carveout(c, 58);
     static const int chunk_frames = [] {               // frames per pipeline chunk (tunable for experiments)
         const char* e = getenv("ORB_B200_PIPE_CHUNK");
         const int v = e ? atoi(e) : 0;

@@ -498,6 +498,16 @@ extern "C" int orb_debug_sincos_range(int device, unsigned first_bits, long long
 // ======================================================================================================
 // host-side launch sequence of one batch (asynchronous on c->stream)
 // ======================================================================================================
+
+// experiment / tuning knob: one shared-memory carve-out for every kernel of the chain (ORB_B200_CARVEOUT, percent of the
+// maximum) so that kernels of different chunks can share an SM without the SM draining to re-partition L1 / shared memory
+void orb_carveout_extract(int pct) {
+    cudaFuncSetAttribute(quadtree_kernel<QT_THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(quadtree_kernel<QT_THREADS_LAT>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(orient_describe_kernel<OD_KPW>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(orient_describe_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+}
+
 int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int pixel_format, int F, int f0, size_t row_stride, size_t frame_stride,
                        orb_kp* d_kps, uint8_t* d_desc, int cap, int* d_n_out, cudaStream_t st) {
     // frames [f0, f0 + F) of the arena: a per-launch copy of the geometry with shifted bases, so the kernels index

@@ -409,6 +409,14 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
 
 }  // namespace
 
+
+// experiment / tuning knob: one shared-memory carve-out for every kernel of the chain (ORB_B200_CARVEOUT, percent of the
+// maximum) so that kernels of different chunks can share an SM without the SM draining to re-partition L1 / shared memory
+void orb_carveout_fast(int pct) {
+    cudaFuncSetAttribute(fast_strip_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(fast_strip_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+}
+
 int orb_launch_fast(orb_ctx* c, const Geometry& g, int* d_corner_count, int F, int f0, cudaStream_t st) {
     if (g.fast_rows > FS_ROWS) { orb_set_error("FAST strip of %d rows exceeds the tile", g.fast_rows); return ORB_ERR_INVALID; }
     if (!c->fast_attr_set) {   // > 48 KB of dynamic shared memory needs the opt-in, once per context (= per device)

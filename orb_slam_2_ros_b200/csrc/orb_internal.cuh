@@ -184,6 +184,10 @@ int orb_launch_pyramid(orb_ctx* c, const Geometry& g, const uint8_t* d_imgs, int
                        size_t frame_stride, cudaStream_t st);
 inline int orb_pix_channels(int fmt) { return fmt == ORB_PIX_GRAY8 ? 1 : (fmt == ORB_PIX_BGR8 || fmt == ORB_PIX_RGB8) ? 3 : 4; }
 int orb_launch_border(orb_ctx* c, const Geometry& g, int nframes, cudaStream_t st);
+void orb_carveout_pyramid(int pct);
+void orb_carveout_blur(int pct);
+void orb_carveout_fast(int pct);
+void orb_carveout_extract(int pct);
 int orb_launch_fast(orb_ctx* c, const Geometry& g, int* d_corner_count, int nframes, int f0, cudaStream_t st);
 int orb_launch_blur(orb_ctx* c, const Geometry& g, int nframes, cudaStream_t st);
 // frames [f0, f0 + nframes) of the arena; all pointers address the chunk's first frame; asynchronous on st

@@ -295,6 +295,19 @@ pyr_border_kernel(uint8_t* __restrict__ pyr, const __grid_constant__ Geometry g)
 
 }  // namespace
 
+
+// experiment / tuning knob: one shared-memory carve-out for every kernel of the chain (ORB_B200_CARVEOUT, percent of the
+// maximum) so that kernels of different chunks can share an SM without the SM draining to re-partition L1 / shared memory
+void orb_carveout_pyramid(int pct) {
+    cudaFuncSetAttribute(pyr_copy0_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(pyr_copy0_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(pyr_resize_fast_kernel<ORB_RESIZE_ROWS>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(pyr_resize_fast_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(pyr_resize_tail_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(pyr_resize_generic_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(pyr_border_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+}
+
 int orb_launch_pyramid(orb_ctx* c, const Geometry& g, const uint8_t* d_imgs, int pixel_format, int F, size_t row_stride,
                        size_t frame_stride, cudaStream_t st) {
     if (pixel_format != ORB_PIX_GRAY8) {
