@@ -614,6 +614,13 @@ def main():
         roof["stages"] = stages
         roof["step_alg_bytes"] = total_alg
         roof["step_gbs"] = total_alg / (ms_dev / args.steps * 1e-3) / 1e9
+        roof["step_frac"] = roof["step_gbs"] / hbm_peak                    # whole step against the unfused-stage byte model
+        # SURVEY.md §8(d)'s second denominator, the FUSED lower bound: read the image once, write the public bordered pyramid
+        # once, write the outputs (~60 KB of keypoints + descriptors per frame)
+        dims_ = level_dims(W, H)
+        fused = W * H + sum((a + 38) * (b + 38) for a, b in dims_) + n_kp // B * 60
+        roof["step_fused_bound_bytes"] = fused * B
+        roof["step_frac_fused_bound"] = fused * B / (ms_dev / args.steps * 1e-3) / 1e9 / hbm_peak
 
         cpu = None
         if world == 1 and not args.no_cpu:
