@@ -318,6 +318,8 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 #define OD_KPB (OD_WARPS * OD_KPW)     // keypoints per CTA (== 32: one lane of warp 0 per keypoint in phase 2)
 #define OD_ITEMS 288                   // 31 patch rows x 9 aligned words, padded to 9 x 32 lanes
 #define OD_TAPR 19                     // |tap offset| <= 19 after rotation
+#define OD_WPITCH 64                    // bytes per row of the staged tap window: the four 16-byte chunks that can hold columns px-19 .. px+19
+#define OD_WBYTES ((2 * OD_TAPR + 1) * OD_WPITCH)
 
 __device__ __forceinline__ int dp4a_su(unsigned a_signed, unsigned b_unsigned, int c) {
     int d;
@@ -345,6 +347,7 @@ orient_describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restric
                        const uint2* __restrict__ mom_tab, orb_kp* __restrict__ kps_out, uint8_t* __restrict__ desc_out,
                        int cap, int* __restrict__ n_out, const __grid_constant__ Geometry g) {
     __shared__ float4 s_pat[8 * 32];
+    __shared__ __align__(16) uint8_t s_win[OD_WARPS][OD_WBYTES];   // per warp: the blurred tap window of the keypoint in work
     __shared__ int s_m[(OD_WARPS * KPW)][2];
     __shared__ float s_ang[(OD_WARPS * KPW)], s_a[(OD_WARPS * KPW)], s_b[(OD_WARPS * KPW)];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -384,6 +387,28 @@ orient_describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restric
             px[q] = corner_x(rec) + ORB_MINB; py[q] = corner_y(rec) + ORB_MINB;   // ORBextractor.cc:881-882
         }
     }
+    // ---- the 512 descriptor taps of a keypoint touch ~420 different 32-byte sectors when gathered from L1, but the
+    //      (2*19+1)^2 window they live in is only ~80 sectors: the warp copies the window into shared memory with
+    //      16-byte cp.async (5 per lane, rows py-19 .. py+19, the 3-4 aligned chunks that hold columns px-19 .. px+19) and
+    //      gathers from there.  One window per warp (20 KB per CTA): a larger footprint would shrink the L1 that the
+    //      moment / record loads of this kernel live on.  Keypoints lie >= 19 px inside the level (EDGE_THRESHOLD), so
+    //      the window never leaves the blurred level's rows; chunk columns past the row end are padding / the next row. ----
+    auto stage_window = [&](int lq, int x, int y) {
+        const LevelGeom& L = g.lv[lq];
+        const int x0 = x - OD_TAPR, xa = x0 & ~15;
+        const int nch = ((x0 + 2 * OD_TAPR) >> 4) - (xa >> 4) + 1;                 // 3 or 4 chunks per row
+        const uint8_t* src = blur + L.bbase + (long long)f * L.bframe_stride + (long long)(y - OD_TAPR) * L.bpitch + xa;
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_win[warp][0]);
+#pragma unroll
+        for (int j = 0; j < ((2 * OD_TAPR + 1) * 4 + 31) / 32; ++j) {
+            const int item = lane + 32 * j, r = item >> 2, cc = item & 3;
+            if (r < 2 * OD_TAPR + 1 && cc < nch)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + r * OD_WPITCH + cc * 16),
+                             "l"(src + (long long)r * L.bpitch + cc * 16) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (lv[0] >= 0) stage_window(lv[0], px[0], py[0]);   // flies behind phases 1 and 2
     // ---- phase 1: IC_Angle moments (ORBextractor.cc:77-104) ----
 #pragma unroll
     for (int q = 0; q < KPW; ++q) {
@@ -431,10 +456,11 @@ orient_describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restric
         const LevelGeom& L = g.lv[l];
         const int kq = warp * KPW + q;
         const float a = s_a[kq], b = s_b[kq];
-        const unsigned bp = (unsigned)L.bpitch;
-        // taps are addressed with non-negative 32-bit offsets from the patch window's top-left corner
-        const uint8_t* b2 = blur + L.bbase + (long long)f * L.bframe_stride + (py[q] - OD_TAPR) * (int)bp + (px[q] - OD_TAPR);
-        const unsigned centre = OD_TAPR * bp + OD_TAPR;
+        // taps are addressed with non-negative offsets from the staged window's top-left chunk
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        const uint8_t* b2 = &s_win[warp][0];
+        const unsigned centre = OD_TAPR * OD_WPITCH + OD_TAPR + (unsigned)((px[q] - OD_TAPR) & 15);
         unsigned val = 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -443,9 +469,11 @@ orient_describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restric
             const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(pt.x, a), __fmul_rn(pt.y, b)));
             const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(pt.z, b), __fmul_rn(pt.w, a)));
             const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(pt.z, a), __fmul_rn(pt.w, b)));
-            const unsigned t0 = b2[centre + (unsigned)(r0 * (int)bp + c0)], t1 = b2[centre + (unsigned)(r1 * (int)bp + c1)];
+            const unsigned t0 = b2[centre + (unsigned)(r0 * OD_WPITCH + c0)], t1 = b2[centre + (unsigned)(r1 * OD_WPITCH + c1)];
             val |= (unsigned)(t0 < t1) << k;
         }
+        __syncwarp();   // every lane has read the window: the next keypoint's copy may overwrite it
+        if (q + 1 < KPW && lv[(q + 1) % KPW] >= 0) stage_window(lv[(q + 1) % KPW], px[(q + 1) % KPW], py[(q + 1) % KPW]);
         // 32-byte descriptor row: gather 4 lanes' bytes into one word, 8 lanes store 8 words (one 32-B sector)
         unsigned w = val;
         w |= __shfl_down_sync(0xffffffffu, val, 1) << 8;
