@@ -320,10 +320,32 @@ def run_reference(args, rank):
                     "sample": "256 queries x 400000 rows, reference bit-hack DescriptorDistance, %.2f s" % hdt},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_json_line(line)
 
 
 # ---------------------------------------------------------------------------------------------------------
+# The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version banner with printf when
+# NCCL_DEBUG=VERSION is set in the environment), so file descriptor 1 is pointed at stderr for the whole run and the JSON
+# line goes to the saved original.
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json_line(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -340,6 +362,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    protect_stdout()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -653,7 +676,7 @@ def main():
             "other_configs": other_configs(local_rank) if (world == 1 and not args.no_cpu) else None,
             "clocks": summarize_clocks(clk.get("rows")),
         }
-        print(json.dumps(line), flush=True)
+        emit_json_line(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
