@@ -148,13 +148,16 @@ int build_geometry(orb_ctx* c, int w, int h) {
         const int first_w = (ORB_XOFF - ORB_EDGE) / 4;                          // word holding byte 13
         const int end_w = (ORB_XOFF + L.w + ORB_EDGE + 3) / 4;                   // one past the last border word
         L.border_words = end_w - first_w;
+        // every level starts at a CTA boundary of the border kernel (16 rows x 16 slots, resp. 256 copy items per CTA), so the
+        // level of a CTA — and with it every LevelGeom field it reads — is uniform (no divergent constant-bank indexing)
         L.border_base = border_items;
-        border_items += L.h + 2 * ORB_EDGE;
+        border_items += (L.h + 2 * ORB_EDGE + 15) / 16 * 16;
         L.copy_base = copy_items;
         {   // top/bottom row copies: 16-byte vectors + trailing whole words per row
             const int per_row = (L.w >> 4) + ((L.w >> 2) - 4 * (L.w >> 4));
             L.inv_wpr = 0xFFFFFFFFu / (unsigned)std::max(per_row, 1) + 1u;
-            copy_items += 2 * ORB_EDGE * per_row;
+            L.copy_items = 2 * ORB_EDGE * per_row;
+            copy_items += (L.copy_items + 255) / 256 * 256;
         }
         // blur: one thread = one output word x ORB_BLUR_ROWS rows
         L.blur_wpr = (L.w + 3) / 4;

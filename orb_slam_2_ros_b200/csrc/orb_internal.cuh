@@ -58,7 +58,8 @@ struct LevelGeom {
     int fast_cta_base;         // number of FAST CTAs of levels < l (per frame)
     int border_base;           // number of bordered rows (= border-fill warps) of levels < l (per frame)
     int border_words;          // words per bordered row that the border kernel may touch
-    int copy_base;             // number of top/bottom row-copy items (words) of levels < l (per frame)
+    int copy_base;             // number of top/bottom row-copy items (words) of levels < l (per frame), padded to CTAs
+    int copy_items;            // row-copy items of this level
     unsigned inv_wpr;          // ceil(2^32 / copy items per row)
     int blur_base, blur_wpr;   // blur: number of thread items of levels < l; words per row
     float scale;               // mvScaleFactor[l]

@@ -248,14 +248,16 @@ __device__ __forceinline__ int reflect1(int i, int n) {
 
 __global__ void __launch_bounds__(256)
 pyr_border_kernel(uint8_t* __restrict__ pyr, const __grid_constant__ Geometry g) {
-    const int item = blockIdx.x * blockDim.x + threadIdx.x;
+    const int item0 = blockIdx.x * 256;                    // CTA-uniform: a CTA never straddles two levels or the two item kinds
     const int f = blockIdx.y;
-    if (item < g.border_items * ORB_BORDER_SLOTS) {
-        const int ritem = item / ORB_BORDER_SLOTS, slot = item % ORB_BORDER_SLOTS;
+    if (item0 < g.border_items * ORB_BORDER_SLOTS) {
+        const int ritem0 = item0 / ORB_BORDER_SLOTS;
         int l = 0;
-        while (l + 1 < g.nlevels && ritem >= g.lv[l + 1].border_base) ++l;
+        while (l + 1 < g.nlevels && ritem0 >= g.lv[l + 1].border_base) ++l;
         const LevelGeom& L = g.lv[l];
-        const int row = ritem - L.border_base;                                 // 0 .. h + 37
+        const int slot = threadIdx.x % ORB_BORDER_SLOTS;
+        const int row = ritem0 + threadIdx.x / ORB_BORDER_SLOTS - L.border_base;   // 0 .. h + 37 (+ padding rows)
+        if (row >= L.h + 2 * ORB_EDGE) return;
         uint8_t* img = pyr + L.base + (long long)f * L.frame_stride;
         const unsigned* sw = reinterpret_cast<const unsigned*>(img + L.ioff + reflect1(row - ORB_EDGE, L.h) * L.pitch);
         unsigned* drow = reinterpret_cast<unsigned*>(img + row * L.pitch);
@@ -276,12 +278,12 @@ pyr_border_kernel(uint8_t* __restrict__ pyr, const __grid_constant__ Geometry g)
         const unsigned m = n >= 4 ? 0xFFFFu : ((1u << (4 * n)) - 1u);
         drow[word] = __byte_perm(sw[max(x0, 0) >> 2], refl, (0x3210u & m) | (0x7654u & ~m));
     } else {
-        int it = item - g.border_items * ORB_BORDER_SLOTS;
-        if (it >= g.border_copy_items) return;
+        const int it0 = item0 - g.border_items * ORB_BORDER_SLOTS;
         int l = 0;
-        while (l + 1 < g.nlevels && it >= g.lv[l + 1].copy_base) ++l;
+        while (l + 1 < g.nlevels && it0 >= g.lv[l + 1].copy_base) ++l;
         const LevelGeom& L = g.lv[l];
-        it -= L.copy_base;
+        const int it = it0 - L.copy_base + threadIdx.x;
+        if (it >= L.copy_items) return;
         const int nvec = L.w >> 4, nrem = (L.w >> 2) - 4 * nvec, per_row = nvec + nrem;   // 16-byte vectors + trailing words
         const int r = (int)__umulhi((unsigned)it, L.inv_wpr), u = it - r * per_row;
         const int row = r < ORB_EDGE ? r : L.h + r;                            // r in [19, 38) -> rows h+19 .. h+37
@@ -366,7 +368,7 @@ int orb_launch_pyramid(orb_ctx* c, const Geometry& g, const uint8_t* d_imgs, int
 }
 
 int orb_launch_border(orb_ctx* c, const Geometry& g, int F, cudaStream_t st) {
-    pyr_border_kernel<<<dim3((g.border_items * ORB_BORDER_SLOTS + g.border_copy_items + 255) / 256, F), 256, 0, st>>>(c->d_pyr, g);
+    pyr_border_kernel<<<dim3((g.border_items * ORB_BORDER_SLOTS + g.border_copy_items) / 256, F), 256, 0, st>>>(c->d_pyr, g);
     c->launches++;
     ORB_CUDA(cudaGetLastError());
     return ORB_OK;
