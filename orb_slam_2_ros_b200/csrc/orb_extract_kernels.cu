@@ -318,7 +318,9 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 #define OD_KPB (OD_WARPS * OD_KPW)     // keypoints per CTA (== 32: one lane of warp 0 per keypoint in phase 2)
 #define OD_ITEMS 288                   // 31 patch rows x 9 aligned words, padded to 9 x 32 lanes
 #define OD_TAPR 19                     // |tap offset| <= 19 after rotation
-#define OD_WPITCH 64                    // bytes per row of the staged tap window: the four 16-byte chunks that can hold columns px-19 .. px+19
+#ifndef OD_WPITCH
+#define OD_WPITCH 80                    // bytes per row of the staged tap window: four 16-byte chunks hold columns px-19 .. px+19; 80 (not 64) spreads the rows over the banks
+#endif
 #define OD_WBYTES ((2 * OD_TAPR + 1) * OD_WPITCH)
 
 __device__ __forceinline__ int dp4a_su(unsigned a_signed, unsigned b_unsigned, int c) {
