@@ -514,7 +514,6 @@ def keypoint_records_encode(kps):
 
 def keypoint_records_decode(buf, n, offset=0):
     import struct
-    from orb_slam_2_ros_b200._lib import KP_DTYPE
     kps = np.zeros(n, KP_DTYPE)                            # cv::KeyPoint(): size = 0, never restored
     for i in range(n):
         a, cid, octv, r1, r2, x, y = struct.unpack_from("<fiiffff", buf, offset + 28 * i)
