@@ -215,7 +215,23 @@ def other_configs(device):
                                                qmin, qmax, da, q_angle=ka["angle"], th_dist=100, nn_ratio=0.9, check_orientation=True)
     ms_sbp = _median_ms(sbp, 30)
     cms_sbp = _median_ms(sbp_cpu, 5, warm=1)
+    # SearchForInitialization (mono initialisation, ORBmatcher.cc:406-521): level-0 keypoints, 100-px windows
+    prev0 = np.stack([ka["x"], ka["y"]], 1).astype(np.float32)
+
+    def sfi():
+        return m9.SearchForInitialization(ka, da, kb, db, bounds, prev0.copy(), 100)
+    valid0 = (ka["octave"] == 0).astype(np.uint8)
+    zeros0 = np.zeros(len(ka), np.int32)
+
+    def sfi_cpu():
+        return orb_oracle.search_by_projection(orb_oracle.MODE_INITIALIZATION, grid, db, None, np.zeros(len(kb), np.uint8),
+                                               prev0[:, 0].copy(), prev0[:, 1].copy(), np.full(len(ka), 100, np.float32), zeros0, zeros0,
+                                               da, q_angle=ka["angle"], q_valid=valid0, th_dist=50, nn_ratio=0.9, check_orientation=True)
+    ms_sfi = _median_ms(sfi, 30)
+    cms_sfi = _median_ms(sfi_cpu, 5, warm=1)
     out["config2_matching"] = {"workload": "%d x %d descriptors of two extracted frames" % (len(da), len(db)),
+                               "search_for_initialization_ms": ms_sfi, "search_for_initialization_cpu_oracle_ms_1thread": cms_sfi,
+                               "search_for_initialization_matches": int(sfi()[0]),
                                "bruteforce_ratio_rothist_ms": ms_bf, "bruteforce_compares_per_s": len(da) * len(db) / (ms_bf * 1e-3),
                                "bruteforce_cpu_oracle_ms_1thread": cms_bf, "bruteforce_matches": int(m.MatchBruteForce(da, ka["angle"], db, kb["angle"], 50)[0]),
                                "search_by_projection_ms": ms_sbp, "search_by_projection_cpu_oracle_ms_1thread": cms_sbp,

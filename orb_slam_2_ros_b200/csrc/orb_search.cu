@@ -231,7 +231,7 @@ struct SrStage {
 __global__ void __launch_bounds__(SR_THREADS)
 window_resolve_kernel(const SearchArgs a, int mode, int th_dist, float nn_ratio, int check_ori, uint8_t* taken_g,
                       int* match_of_query, int* target_query, signed char* match_bin, int* assigned, int* nmatches_out,
-                      int* overflow) {
+                      int* overflow, int smem_bytes) {
     extern __shared__ __align__(16) uint8_t sr_smem[];
     SrStage& S = *reinterpret_cast<SrStage*>(sr_smem);
     const bool init = (mode == ORB_MODE_INITIALIZATION);
@@ -349,7 +349,132 @@ window_resolve_kernel(const SearchArgs a, int mode, int th_dist, float nn_ratio,
         nmatches = s_nmatches;
         __syncthreads();
     }
-    for (int q0 = 0; init && q0 < a.nq; q0 += SR_CH) {
+    // ---- INITIALIZATION (ORBmatcher.cc:406-521) in parallel rounds.  A target can be taken again by a later query with a
+    // strictly smaller distance (:445, 464-471), so the state of a target is its whole list of takers; the distances of the
+    // successive takers decrease, i.e. vMatchedDistance seen by query qi = min { d_j : j < qi took the target }.  The
+    // sequential result is again the unique solution of choice[qi] = decide(qi, takers before qi): every round rebuilds the
+    // per-target taker lists (up to INIT_C entries, d << 16 | query) from the previous choices and re-evaluates all queries;
+    // a target with more takers than that, or too many targets for the shared-memory lists, falls back to the walk below.
+    bool init_done = false;
+    constexpr int INIT_C = 4;
+    if (init && a.nq < 65535 && (size_t)a.n * (4 * INIT_C + 4) <= (size_t)smem_bytes) {
+        unsigned* lst = reinterpret_cast<unsigned*>(sr_smem);           // [n][INIT_C]
+        int* cnt = reinterpret_cast<int*>(lst + (size_t)a.n * INIT_C);  // [n]
+        __shared__ int s_chg, s_over;
+        __syncthreads();                                                // the set-up loop above wrote arrays these alias
+        for (int qi = threadIdx.x; qi < a.nq; qi += SR_THREADS) { assigned[qi] = -1; match_of_query[qi] = -1; match_bin[qi] = -1; }
+        const int nq_up = (a.nq + 31) & ~31;
+        auto visible = [&](int id, int dist, int qi) -> bool {          // no earlier taker matched the target at least as well
+            const int c = min(cnt[id], INIT_C);
+            for (int e = 0; e < c; ++e) {
+                const unsigned v = lst[id * INIT_C + e];
+                if ((int)(v & 0xFFFFu) < qi && (int)(v >> 16) <= dist) return false;
+            }
+            return true;
+        };
+        bool over = false;
+        for (int round = 0; round <= a.nq; ++round) {
+            for (int i = threadIdx.x; i < a.n; i += SR_THREADS) cnt[i] = 0;
+            if (threadIdx.x == 0) { s_chg = 0; s_over = 0; }
+            __syncthreads();
+            for (int qi = threadIdx.x; qi < a.nq; qi += SR_THREADS) {
+                const int v = assigned[qi];                              // d << 16 | target, or -1
+                if (v >= 0) {
+                    const int slot = atomicAdd(&cnt[v & 0xFFFF], 1);
+                    if (slot < INIT_C) lst[(v & 0xFFFF) * INIT_C + slot] = ((unsigned)(v >> 16) << 16) | (unsigned)qi;
+                    else s_over = 1;
+                }
+            }
+            __syncthreads();
+            if (s_over) { over = true; break; }                           // uniform
+            for (int qi = threadIdx.x; qi < nq_up; qi += SR_THREADS) {
+                int d1 = 256, d2 = 256, i1 = -1, nfree = 0;
+                bool fallback = false;
+                if (qi < a.nq) {
+                    const int base = a.cand_base[qi];
+                    unsigned key[SR_K];
+#pragma unroll
+                    for (int k = 0; k < SR_K; ++k) key[k] = a.topk[(size_t)qi * SR_K + k];
+#pragma unroll
+                    for (int k = 0; k < SR_K; ++k) {
+                        if (key[k] == 0xFFFFFFFFu || nfree >= 2) break;
+                        const int id = a.cand_idx[base + (key[k] & 0xFFFFu)], dist = (int)(key[k] >> 16);
+                        if (!visible(id, dist, qi)) continue;
+                        if (nfree == 0) { d1 = dist; i1 = id; } else d2 = dist;
+                        ++nfree;
+                    }
+                    fallback = nfree < 2 && key[SR_K - 1] != 0xFFFFFFFFu;
+                }
+                unsigned todo = __ballot_sync(0xffffffffu, fallback);
+                while (todo) {   // truncated list with too few visible entries: the warp scans the query's whole candidate list
+                    const int src = __ffs((int)todo) - 1;
+                    todo &= todo - 1u;
+                    const int fq = __shfl_sync(0xffffffffu, qi, src);
+                    const int fcnt = a.cand_count[fq], fbase = a.cand_base[fq];
+                    unsigned a1 = 0xFFFFFFFFu, a2 = 0xFFFFFFFFu;
+                    for (int p = lane; p < fcnt; p += 32) {
+                        const unsigned d = a.cand_dist[fbase + p];
+                        if (d >= 256u) continue;
+                        if (!visible(a.cand_idx[fbase + p], (int)d, fq)) continue;
+                        const unsigned k = (d << 16) | (unsigned)p;
+                        a2 = min(a2, max(k, a1));
+                        a1 = min(a1, k);
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const unsigned b1 = __shfl_xor_sync(0xffffffffu, a1, o), b2 = __shfl_xor_sync(0xffffffffu, a2, o);
+                        const unsigned lo = min(a1, b1), hi = max(a1, b1);
+                        a2 = min(hi, min(a2, b2));
+                        a1 = lo;
+                    }
+                    if (lane == src) {
+                        d1 = d2 = 256; i1 = -1;
+                        if (a1 != 0xFFFFFFFFu) { d1 = (int)(a1 >> 16); i1 = a.cand_idx[fbase + (a1 & 0xFFFFu)]; }
+                        if (a2 != 0xFFFFFFFFu) d2 = (int)(a2 >> 16);
+                    }
+                }
+                if (qi < a.nq) {
+                    int c = -1;
+                    // bestDist <= TH_LOW and bestDist < (float)bestDist2 * mfNNratio, bestDist2 = INT_MAX without a second (ORBmatcher.cc:460-462)
+                    if (i1 >= 0 && d1 <= th_dist && !(d2 < 256 && !((float)d1 < __fmul_rn((float)d2, nn_ratio)))) c = (d1 << 16) | i1;
+                    if (c != assigned[qi]) { assigned[qi] = c; s_chg = 1; }
+                }
+            }
+            __syncthreads();
+            const int changed = s_chg;
+            __syncthreads();
+            if (!changed) break;
+        }
+        if (!over) {
+            // the lists of the last round ARE the final takers: vnMatches21 = the latest taker, one match per taken target
+            for (int i = threadIdx.x; i < a.n; i += SR_THREADS) {
+                const int c = min(cnt[i], INIT_C);
+                int latest = -1;
+                for (int e = 0; e < c; ++e) latest = max(latest, (int)(lst[i * INIT_C + e] & 0xFFFFu));
+                target_query[i] = latest;
+                nmatches += latest >= 0;
+            }
+            __syncthreads();
+            for (int qi = threadIdx.x; qi < a.nq; qi += SR_THREADS) {
+                const int v = assigned[qi];
+                const int id = v >= 0 ? (v & 0xFFFF) : -1;
+                assigned[qi] = id;                                        // every assignment made, stale ones included (rotation histogram)
+                match_of_query[qi] = (id >= 0 && target_query[id] == qi) ? id : -1;
+            }
+            atomicAdd(&s_nmatches, nmatches);
+            __syncthreads();
+            nmatches = s_nmatches;
+            __syncthreads();
+            init_done = true;
+        } else {
+            __syncthreads();
+            nmatches = 0;
+        }
+    }
+    if (init && !init_done) {   // state of the sequential walk (it aliases the lists above)
+        for (int i = threadIdx.x; i < a.n; i += SR_THREADS) { target_query[i] = -1; taken[i] = 0; vmd[i] = 0xFFFFu; own[i] = 0xFFFFu; }
+    }
+    for (int q0 = 0; init && !init_done && q0 < a.nq; q0 += SR_CH) {
         const int nb = min(SR_CH, a.nq - q0);
         __syncthreads();
         // ---- stage the chunk ----
@@ -437,13 +562,13 @@ window_resolve_kernel(const SearchArgs a, int mode, int th_dist, float nn_ratio,
             }
         }
     }
-    if (init) {
+    if (init && !init_done) {
         if (threadIdx.x == 0) s_nmatches = nmatches;
         __syncthreads();
         nmatches = s_nmatches;
     }
     if (init) {
-        for (int i = threadIdx.x; i < a.n; i += SR_THREADS) target_query[i] = own[i] == 0xFFFFu ? -1 : (int)own[i];   // vnMatches21
+        if (!init_done) for (int i = threadIdx.x; i < a.n; i += SR_THREADS) target_query[i] = own[i] == 0xFFFFu ? -1 : (int)own[i];   // vnMatches21
         if (check_ori) {
             // rotation histogram of every assignment made, stale ones included (ORBmatcher.cc:473-482, 488-511)
             for (int qi = threadIdx.x; qi < a.nq; qi += SR_THREADS) {
@@ -1099,7 +1224,10 @@ int orb_search_by_projection(int device, const orb_search_params* prm, const orb
                                                                     (unsigned*)(Dv + o_items), (int*)(Dv + o_cells));
         window_candidates_kernel<<<(nq + 7) / 8, 256, 0, st>>>(a);
         // INITIALIZATION: stage + taken[n] + vMatchedDistance[n] + vnMatches21[n]; other modes: two int owner arrays + taken[n]
-        const size_t rsmem = std::max(sizeof(SrStage) + (size_t)((n + 3) & ~3) * 5, (size_t)9 * ((n + 3) & ~3) + 16);
+        const size_t rsmem_max = std::max(sizeof(SrStage) + GB_MAX_N * 5, (size_t)9 * GB_MAX_N + 16);
+        size_t rsmem = std::max(sizeof(SrStage) + (size_t)((n + 3) & ~3) * 5, (size_t)9 * ((n + 3) & ~3) + 16);
+        if (prm->mode == ORB_MODE_INITIALIZATION)   // taker lists of the parallel rounds: 20 bytes per target when they fit
+            rsmem = std::max(rsmem, std::min((size_t)20 * ((n + 3) & ~3), rsmem_max));
         static thread_local int attr_dev = -1;
         if (attr_dev != device) {
             ORB_CUDA(cudaFuncSetAttribute(window_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(sizeof(SrStage) + GB_MAX_N * 5, (size_t)9 * GB_MAX_N + 16)));
@@ -1107,7 +1235,7 @@ int orb_search_by_projection(int device, const orb_search_params* prm, const orb
         }
         window_resolve_kernel<<<1, SR_THREADS, rsmem, st>>>(a, prm->mode, prm->th_dist, prm->nn_ratio, prm->check_orientation,
                                                             Dv + o_taken, (int*)(Dv + o_moq), (int*)(Dv + o_tq),
-                                                            (signed char*)(Dv + o_bin), (int*)(Dv + o_asg), d_scal + 1, d_scal + 2);
+                                                            (signed char*)(Dv + o_bin), (int*)(Dv + o_asg), d_scal + 1, d_scal + 2, (int)rsmem);
         ORB_CUDA(cudaGetLastError());
         ORB_CUDA(cudaMemcpyAsync(H + o_taken, Dv + o_taken, io_bytes - o_taken, cudaMemcpyDeviceToHost, st));
         ORB_CUDA(cudaStreamSynchronize(st));

@@ -419,3 +419,56 @@ def test_resolve_rounds_long_dependency_chain(oracle):
                                                                       q_angle=a1, q_obs=q_obs, th_dist=100)
         assert nm_o > 30
         assert nm_g == nm_o and np.array_equal(moq_g, moq_o) and np.array_equal(tq_g, tq_o) and np.array_equal(t_g, t_o)
+
+
+@pytest.mark.gpu
+def test_search_for_initialization_steal_chains_in_parallel_rounds(oracle):
+    """SearchForInitialization with 1-4 takers per target in decreasing-distance order (every later taker steals), the
+    regime the parallel rounds resolve with their per-target taker lists; plus a target whose FIFTH taker forces the
+    fallback to the sequential walk."""
+    from orb_slam_2_ros_b200 import ORBmatcher
+    from orb_slam_2_ros_b200._lib import KP_DTYPE
+    rng = np.random.default_rng(31)
+    bounds = (0.0, 0.0, 640.0, 480.0)
+    for max_takers in (4, 5):
+        n2 = 120
+        kb = np.zeros(n2, KP_DTYPE)
+        gx, gy = np.meshgrid(np.arange(12), np.arange(10))
+        kb["x"] = (40 + 48 * gx.ravel()).astype(np.float32); kb["y"] = (30 + 44 * gy.ravel()).astype(np.float32)   # well separated
+        kb["angle"] = rng.uniform(0, 360, n2).astype(np.float32); kb["octave"] = 0
+        db = rng.integers(0, 256, (n2, 32), dtype=np.uint8)
+        takers = rng.integers(1, max_takers + 1, n2)
+        takers[7] = max_takers
+        rows = []
+        for t in range(n2):
+            flips = np.sort(rng.choice(np.arange(1, 30), takers[t], replace=False))[::-1]     # strictly decreasing distances
+            for fl in flips:
+                rows.append((t, int(fl)))
+        order = rng.permutation(len(rows))
+        # keep the per-target order of decreasing distance while interleaving the targets
+        per_t = {t: [r for r in rows if r[0] == t] for t in range(n2)}
+        seq = []
+        for i in order:
+            t = rows[i][0]
+            if per_t[t]:
+                seq.append(per_t[t].pop(0))
+        n1 = len(seq)
+        ka = np.zeros(n1, KP_DTYPE)
+        da = np.zeros((n1, 32), np.uint8)
+        for i, (t, fl) in enumerate(seq):
+            ka["x"][i] = kb["x"][t] + rng.uniform(-3, 3); ka["y"][i] = kb["y"][t] + rng.uniform(-3, 3)
+            ka["angle"][i] = kb["angle"][t]
+            da[i] = _flip_first_bits(db[t], fl)
+        prev = np.stack([ka["x"], ka["y"]], 1).astype(np.float32)
+        grid = oracle.Grid(kb, *bounds)
+        zeros = np.zeros(n1, np.int32)
+        for ori in (False, True):
+            nm_o, m12_o, _ = oracle.search_by_projection(oracle.MODE_INITIALIZATION, grid, db, None, np.zeros(n2, np.uint8), prev[:, 0].copy(),
+                                                         prev[:, 1].copy(), np.full(n1, 20, np.float32), zeros, zeros, da, q_angle=ka["angle"],
+                                                         q_valid=np.ones(n1, np.uint8), th_dist=50, nn_ratio=0.9, check_orientation=ori)
+            nm_g, m12_g = ORBmatcher(0.9, ori).SearchForInitialization(ka, da, kb, db, bounds, prev.copy(), 20)
+            assert nm_g == nm_o and np.array_equal(m12_g, m12_o)
+            if not ori:
+                assert nm_o == n2                                                    # every target ends up owned by its LAST taker
+                last = {t: i for i, (t, fl) in enumerate(seq)}
+                assert all(m12_o[i] == t for t, i in last.items()) and (m12_o >= 0).sum() == n2
