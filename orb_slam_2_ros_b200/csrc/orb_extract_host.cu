@@ -470,6 +470,7 @@ void orb_destroy(orb_ctx* c) {
         if (c->st_h2d) {
             cudaStreamDestroy(c->st_h2d); cudaStreamDestroy(c->st_d2h); cudaStreamDestroy(c->st_c2);
             for (int i = 0; i < 2; ++i) { cudaStreamDestroy(c->st_aux[i]); cudaEventDestroy(c->ev_pyr[i]); cudaEventDestroy(c->ev_blur[i]); }
+            if (c->ev_head) { cudaEventDestroy(c->ev_head); cudaEventDestroy(c->ev_early); }
             for (int i = 0; i < ORB_PIPE_SLOTS; ++i) { cudaEventDestroy(c->ev_in[i]); cudaEventDestroy(c->ev_done[i]); cudaEventDestroy(c->ev_out[i]); }
         }
     }

@@ -66,11 +66,11 @@ template <int NT>
 __global__ void __launch_bounds__(NT)
 quadtree_kernel(const unsigned long long* __restrict__ corners, const int* __restrict__ corner_count,
                 unsigned short* __restrict__ node_of_key, unsigned long long* __restrict__ kept,
-                int* __restrict__ kept_count, int* __restrict__ tie_count, const __grid_constant__ Geometry g) {
+                int* __restrict__ kept_count, int* __restrict__ tie_count, const __grid_constant__ Geometry g, int level0) {
     extern __shared__ __align__(16) uint8_t smem[];
     // longest first: level 0 holds the most corners and the largest quota, so all frames' level-0 CTAs are dispatched before
     // any level-1 CTA (x = frame varies fastest) and the short upper-level CTAs fill the tail of the launch
-    const int l = blockIdx.y, f = blockIdx.x;
+    const int l = blockIdx.y + level0, f = blockIdx.x;   // level0: first level of this launch (the latency path launches two level ranges)
     const LevelGeom& L = g.lv[l];
     const int cap = g.max_node_cap;
     const int K = min(corner_count[f * g.nlevels + l], L.corner_cap);
@@ -570,8 +570,51 @@ int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int pixel_format, int 
 #define ORB_STAGE_MARK(i, s_) do { if (ev) ORB_CUDA(cudaEventRecord(ev[i], s_)); } while (0)
     ORB_CUDA(cudaMemsetAsync(d_cc, 0, sizeof(int) * (size_t)F * g.nlevels, st));
     ORB_CUDA(cudaMemsetAsync(d_tie, 0, sizeof(int) * (size_t)F * g.nlevels, st));
+    // launch of K3 for the levels [l0, l1) on stream s
+    auto launch_quadtree = [&](int l0, int l1, cudaStream_t s) -> int {
+        if (l1 <= l0) return ORB_OK;
+        const size_t smem = (size_t)g.max_node_cap * 80;
+        if (smem > 48 * 1024 && !c->qt_attr_set) {   // large nFeatures: opt in to > 48 KB of dynamic shared memory
+            ORB_CUDA(cudaFuncSetAttribute(quadtree_kernel<QT_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            ORB_CUDA(cudaFuncSetAttribute(quadtree_kernel<QT_THREADS_LAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            c->qt_attr_set = true;
+        }
+        if (F >= 8)
+            quadtree_kernel<QT_THREADS><<<dim3(F, l1 - l0), QT_THREADS, smem, s>>>(c->d_corners, d_cc, c->d_node_of_key, d_kept,
+                                                                                   d_kept_count, d_tie, g, l0);
+        else
+            quadtree_kernel<QT_THREADS_LAT><<<dim3(F, l1 - l0), QT_THREADS_LAT, smem, s>>>(c->d_corners, d_cc, c->d_node_of_key, d_kept,
+                                                                                           d_kept_count, d_tie, g, l0);
+        c->launches++;
+        return ORB_OK;
+    };
     ORB_STAGE_MARK(0, st);
-    { int rc = orb_launch_pyramid(c, g, d_imgs, pixel_format, F, row_stride, frame_stride, st); if (rc != ORB_OK) return rc; }   // K1 interior
+    // Latency shape (a few frames, parallel branches allowed): the upper pyramid levels are one cluster launch of ~20 us
+    // that only the FAST / quadtree work of THOSE levels depends on, so FAST + quadtree of the lower levels run next to it
+    // on a third stream.
+    int tail_first = g.nlevels;
+    bool split = false;
+    static const bool no_split = getenv("ORB_B200_NO_SPLIT") != nullptr;   // A/B knob
+    if (!no_split && aux != st && F < 8 && c->st_aux[1 - which] && pixel_format == ORB_PIX_GRAY8) {
+        orb_launch_pyramid(c, g, d_imgs, pixel_format, F, row_stride, frame_stride, st, -1, &tail_first);   // query only (phase -1 launches nothing)
+        split = tail_first < g.nlevels;
+    }
+    if (split) {
+        cudaStream_t early = c->st_aux[1 - which];
+        if (!c->ev_head) {
+            ORB_CUDA(cudaEventCreateWithFlags(&c->ev_head, cudaEventDisableTiming));
+            ORB_CUDA(cudaEventCreateWithFlags(&c->ev_early, cudaEventDisableTiming));
+        }
+        { int rc = orb_launch_pyramid(c, g, d_imgs, pixel_format, F, row_stride, frame_stride, st, 1, nullptr); if (rc != ORB_OK) return rc; }
+        ORB_CUDA(cudaEventRecord(c->ev_head, st));
+        ORB_CUDA(cudaStreamWaitEvent(early, c->ev_head, 0));
+        { int rc = orb_launch_fast(c, g, d_cc, F, f0, early, 0, tail_first); if (rc != ORB_OK) return rc; }
+        { int rc = launch_quadtree(0, tail_first, early); if (rc != ORB_OK) return rc; }
+        ORB_CUDA(cudaEventRecord(c->ev_early, early));
+        { int rc = orb_launch_pyramid(c, g, d_imgs, pixel_format, F, row_stride, frame_stride, st, 2, nullptr); if (rc != ORB_OK) return rc; }
+    } else {
+        int rc = orb_launch_pyramid(c, g, d_imgs, pixel_format, F, row_stride, frame_stride, st); if (rc != ORB_OK) return rc;   // K1 interior
+    }
     ORB_STAGE_MARK(1, st);
     if (aux != st) {
         ORB_CUDA(cudaEventRecord(c->ev_pyr[which], st));
@@ -584,23 +627,10 @@ int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int pixel_format, int 
     ORB_STAGE_MARK(8, aux);
     if (aux != st) ORB_CUDA(cudaEventRecord(c->ev_blur[which], aux));
     ORB_STAGE_MARK(9, st);
-    { int rc = orb_launch_fast(c, g, d_cc, F, f0, st); if (rc != ORB_OK) return rc; }                               // K2
+    { int rc = orb_launch_fast(c, g, d_cc, F, f0, st, split ? tail_first : 0, g.nlevels); if (rc != ORB_OK) return rc; }   // K2
     ORB_STAGE_MARK(2, st);
-    {   // K3
-        const size_t smem = (size_t)g.max_node_cap * 80;
-        if (smem > 48 * 1024 && !c->qt_attr_set) {   // large nFeatures: opt in to > 48 KB of dynamic shared memory
-            ORB_CUDA(cudaFuncSetAttribute(quadtree_kernel<QT_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            ORB_CUDA(cudaFuncSetAttribute(quadtree_kernel<QT_THREADS_LAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            c->qt_attr_set = true;
-        }
-        if (F >= 8)
-            quadtree_kernel<QT_THREADS><<<dim3(F, g.nlevels), QT_THREADS, smem, st>>>(c->d_corners, d_cc, c->d_node_of_key, d_kept,
-                                                                                       d_kept_count, d_tie, g);
-        else
-            quadtree_kernel<QT_THREADS_LAT><<<dim3(F, g.nlevels), QT_THREADS_LAT, smem, st>>>(c->d_corners, d_cc, c->d_node_of_key, d_kept,
-                                                                                               d_kept_count, d_tie, g);
-        c->launches++;
-    }
+    { int rc = launch_quadtree(split ? tail_first : 0, g.nlevels, st); if (rc != ORB_OK) return rc; }                     // K3
+    if (split) ORB_CUDA(cudaStreamWaitEvent(st, c->ev_early, 0));
     ORB_STAGE_MARK(3, st);
     if (aux != st) ORB_CUDA(cudaStreamWaitEvent(st, c->ev_blur[which], 0));
     ORB_STAGE_MARK(4, st);

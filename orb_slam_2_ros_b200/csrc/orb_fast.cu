@@ -417,18 +417,22 @@ void orb_carveout_fast(int pct) {
     cudaFuncSetAttribute(fast_strip_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
 }
 
-int orb_launch_fast(orb_ctx* c, const Geometry& g, int* d_corner_count, int F, int f0, cudaStream_t st) {
+int orb_launch_fast(orb_ctx* c, const Geometry& g, int* d_corner_count, int F, int f0, cudaStream_t st, int level_begin, int level_end) {
     if (g.fast_rows > FS_ROWS) { orb_set_error("FAST strip of %d rows exceeds the tile", g.fast_rows); return ORB_ERR_INVALID; }
     if (!c->fast_attr_set) {   // > 48 KB of dynamic shared memory needs the opt-in, once per context (= per device)
         ORB_CUDA(cudaFuncSetAttribute(fast_strip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM(FS_ROWS)));
         ORB_CUDA(cudaFuncSetAttribute(fast_strip_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM(FS_ROWS)));
         c->fast_attr_set = true;
     }
+    // strips are stored level by level: a level range is a contiguous range of CTAs
+    level_end = min(level_end, g.nlevels);
+    const int first = g.lv[level_begin].fast_cta_base, last = level_end < g.nlevels ? g.lv[level_end].fast_cta_base : g.fast_ctas;
+    if (last <= first) return ORB_OK;
     if (c->use_tma)
-        fast_strip_kernel<true><<<dim3(g.fast_ctas, F), FS_THREADS, FS_SMEM(g.fast_rows), st>>>(c->d_pyr, c->d_strips, c->d_corners, d_corner_count, g,
+        fast_strip_kernel<true><<<dim3(last - first, F), FS_THREADS, FS_SMEM(g.fast_rows), st>>>(c->d_pyr, c->d_strips + first, c->d_corners, d_corner_count, g,
                                                                                    c->d_tmaps, f0);
     else
-        fast_strip_kernel<false><<<dim3(g.fast_ctas, F), FS_THREADS, FS_SMEM(g.fast_rows), st>>>(c->d_pyr, c->d_strips, c->d_corners, d_corner_count, g,
+        fast_strip_kernel<false><<<dim3(last - first, F), FS_THREADS, FS_SMEM(g.fast_rows), st>>>(c->d_pyr, c->d_strips + first, c->d_corners, d_corner_count, g,
                                                                                     c->d_tmaps, f0);
     c->launches++;
     ORB_CUDA(cudaGetLastError());

@@ -136,6 +136,7 @@ struct orb_ctx {
     cudaStream_t st_h2d = nullptr, st_d2h = nullptr, st_c2 = nullptr;
     cudaStream_t st_aux[2] = {nullptr, nullptr};   // border -> blur chain next to FAST -> quadtree (one per compute stream)
     cudaEvent_t ev_pyr[2] = {}, ev_blur[2] = {};
+    cudaEvent_t ev_head = nullptr, ev_early = nullptr;   // latency path: FAST + quadtree of the lower levels run next to the pyramid's tail launch
     bool overlap = false;
     cudaEvent_t ev_in[ORB_PIPE_SLOTS] = {}, ev_done[ORB_PIPE_SLOTS] = {}, ev_out[ORB_PIPE_SLOTS] = {};
     int last_frames = 0;
@@ -182,14 +183,15 @@ int orb_profile_harvest(orb_ctx* c, int slot);
 
 // kernels' launchers (orb_extract_kernels.cu)
 int orb_launch_pyramid(orb_ctx* c, const Geometry& g, const uint8_t* d_imgs, int pixel_format, int nframes, size_t row_stride,
-                       size_t frame_stride, cudaStream_t st);
+                       size_t frame_stride, cudaStream_t st, int phase = 0, int* tail_first_out = nullptr);
 inline int orb_pix_channels(int fmt) { return fmt == ORB_PIX_GRAY8 ? 1 : (fmt == ORB_PIX_BGR8 || fmt == ORB_PIX_RGB8) ? 3 : 4; }
 int orb_launch_border(orb_ctx* c, const Geometry& g, int nframes, cudaStream_t st);
 void orb_carveout_pyramid(int pct);
 void orb_carveout_blur(int pct);
 void orb_carveout_fast(int pct);
 void orb_carveout_extract(int pct);
-int orb_launch_fast(orb_ctx* c, const Geometry& g, int* d_corner_count, int nframes, int f0, cudaStream_t st);
+int orb_launch_fast(orb_ctx* c, const Geometry& g, int* d_corner_count, int nframes, int f0, cudaStream_t st, int level_begin = 0,
+                    int level_end = ORB_MAX_LEVELS);
 int orb_launch_blur(orb_ctx* c, const Geometry& g, int nframes, cudaStream_t st);
 // frames [f0, f0 + nframes) of the arena; all pointers address the chunk's first frame; asynchronous on st
 int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int pixel_format, int nframes, int f0, size_t row_stride,

@@ -310,8 +310,29 @@ void orb_carveout_pyramid(int pct) {
     cudaFuncSetAttribute(pyr_border_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
 }
 
+// phase 0: the whole chain; 1: everything before the fused tail launch; 2: the fused tail launch only.  *tail_first_out = the
+// first level the tail launch computes (nlevels when there is none).
 int orb_launch_pyramid(orb_ctx* c, const Geometry& g, const uint8_t* d_imgs, int pixel_format, int F, size_t row_stride,
-                       size_t frame_stride, cudaStream_t st) {
+                       size_t frame_stride, cudaStream_t st, int phase, int* tail_first_out) {
+    // small batches: the levels from the first one with <= 100 k pixels on run as ONE cluster launch (see pyr_resize_tail_kernel)
+    int tail_first = g.nlevels;
+    if (F <= PYR_TAIL_MAXF) {
+        for (int l = g.nlevels - 1; l >= 2; --l) {
+            if (!g.lv[l].fast_resize || g.lv[l].w * g.lv[l].h > 100000) break;
+            tail_first = l;
+        }
+        if (g.nlevels - tail_first < 2) tail_first = g.nlevels;
+    }
+    if (tail_first_out) *tail_first_out = tail_first;
+    if (phase < 0) return ORB_OK;   // query only
+    if (phase == 2) {
+        if (tail_first < g.nlevels) {
+            pyr_resize_tail_kernel<<<dim3(PYR_TAIL_CLUSTER, F), PYR_TAIL_THREADS, 0, st>>>(c->d_pyr, c->d_taps, c->d_wtaps, tail_first, g);
+            c->launches++;
+        }
+        ORB_CUDA(cudaGetLastError());
+        return ORB_OK;
+    }
     if (pixel_format != ORB_PIX_GRAY8) {
         const LevelGeom& L = g.lv[0];
         const int items = ((L.w + 3) >> 2) * L.h;
@@ -333,15 +354,6 @@ int orb_launch_pyramid(orb_ctx* c, const Geometry& g, const uint8_t* d_imgs, int
         else pyr_copy0_kernel<false><<<grd, 256, 0, st>>>(d_imgs, row_stride, frame_stride, c->d_pyr, g);
         c->launches++;
     }
-    // small batches: the levels from the first one with <= 100 k pixels on run as ONE cluster launch (see pyr_resize_tail_kernel)
-    int tail_first = g.nlevels;
-    if (F <= PYR_TAIL_MAXF) {
-        for (int l = g.nlevels - 1; l >= 2; --l) {
-            if (!g.lv[l].fast_resize || g.lv[l].w * g.lv[l].h > 100000) break;
-            tail_first = l;
-        }
-        if (g.nlevels - tail_first < 2) tail_first = g.nlevels;
-    }
     for (int l = 1; l < tail_first; ++l) {
         const LevelGeom& L = g.lv[l];
         const int wpr = (L.w + 3) >> 2;
@@ -359,7 +371,7 @@ int orb_launch_pyramid(orb_ctx* c, const Geometry& g, const uint8_t* d_imgs, int
         }
         c->launches++;
     }
-    if (tail_first < g.nlevels) {
+    if (phase == 0 && tail_first < g.nlevels) {
         pyr_resize_tail_kernel<<<dim3(PYR_TAIL_CLUSTER, F), PYR_TAIL_THREADS, 0, st>>>(c->d_pyr, c->d_taps, c->d_wtaps, tail_first, g);
         c->launches++;
     }
