@@ -75,7 +75,9 @@ grid_build_kernel(const orb_kp* __restrict__ kps, int n, int npad, float min_x, 
 
 #define SR_K 8   // unmasked top-K per query kept for the optimistic resolve
 #define SR_CH 1024  // queries staged in shared memory per chunk of the sequential walk
-#define SR_THREADS 256
+#ifndef SR_THREADS
+#define SR_THREADS 1024
+#endif
 #define BF_NONE 0x7FFFFFFF   // owner of a target nobody has taken
 
 struct SearchArgs {
@@ -228,7 +230,7 @@ struct SrStage {
     uint8_t flags[SR_CH];             // bit 0: list truncated (all K entries valid), bit 1: query blocks its target
 };
 
-__global__ void __launch_bounds__(SR_THREADS)
+__global__ void __launch_bounds__(SR_THREADS, 1)
 window_resolve_kernel(const SearchArgs a, int mode, int th_dist, float nn_ratio, int check_ori, uint8_t* taken_g,
                       int* match_of_query, int* target_query, signed char* match_bin, int* assigned, int* nmatches_out,
                       int* overflow, int smem_bytes) {
@@ -684,7 +686,7 @@ bf_rows_kernel(const uint8_t* __restrict__ d1, int n1, const uint8_t* __restrict
 // microseconds (the sequential walk of 1000 queries took 330 us).  The optimistic top-K list answers a query when two of
 // its entries are still visible; otherwise the query's warp scans its whole distance row cooperatively.
 template <bool SMEM>
-__global__ void __launch_bounds__(SR_THREADS)
+__global__ void __launch_bounds__(SR_THREADS, 1)
 bf_resolve_kernel(const unsigned short* __restrict__ D, int dpitch, const unsigned* __restrict__ topk, int n1, int n2,
                   const float* __restrict__ angle1, const float* __restrict__ angle2, int th_dist, float nn_ratio,
                   int check_ori, int* owner /*[n2]*/, int* owner_scratch /*[n2], !SMEM only*/, int* match12, signed char* match_bin,
