@@ -26,12 +26,25 @@ __device__ __forceinline__ int dist256s(const uint4* a, const uint4* b) {
            __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
 }
 
+// per right keypoint, once: the row band [minr, maxr] it is listed under (Frame.cc:519-529), its x and octave, packed in 16 bytes
+// (every left keypoint's warp scans all of them: without this each of the N x Nr visits redid the ceil / floor arithmetic
+// on a 28-byte KeyPoint)
+__global__ void __launch_bounds__(256)
+stereo_rows_kernel(const orb_kp* __restrict__ kpsR, int Nr, const StereoScales sc, uint4* __restrict__ rows) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Nr) return;
+    const orb_kp kpR = kpsR[i];
+    const float r = __fmul_rn(2.0f, sc.scale[kpR.octave]);
+    const int maxr = (int)ceilf(__fadd_rn(kpR.y, r)), minr = (int)floorf(__fsub_rn(kpR.y, r));
+    rows[i] = make_uint4(__float_as_uint(kpR.x), (unsigned)minr, (unsigned)maxr, (unsigned)kpR.octave);
+}
+
 __global__ void __launch_bounds__(256)
 stereo_match_kernel(const uint8_t* __restrict__ pyrL, const uint8_t* __restrict__ pyrR, const orb_kp* __restrict__ kpsL,
                     const uint8_t* __restrict__ descL, int N, const orb_kp* __restrict__ kpsR,
                     const uint8_t* __restrict__ descR, int Nr, float mbf, float mb, const StereoScales sc,
                     float* __restrict__ uRight, float* __restrict__ depth, int* __restrict__ sad,
-                    const __grid_constant__ Geometry g) {
+                    const uint4* __restrict__ rowsR, const __grid_constant__ Geometry g) {
     const int lane = threadIdx.x & 31;
     const int iL = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (iL >= N) return;
@@ -48,12 +61,12 @@ stereo_match_kernel(const uint8_t* __restrict__ pyrL, const uint8_t* __restrict_
     const uint4* dL = reinterpret_cast<const uint4*>(descL + (size_t)iL * 32);
     unsigned best = 0xFFFFFFFFu;
     for (int iR = lane; iR < Nr; iR += 32) {
-        const orb_kp kpR = kpsR[iR];
-        const float r = __fmul_rn(2.0f, sc.scale[kpR.octave]);
-        const int maxr = (int)ceilf(__fadd_rn(kpR.y, r)), minr = (int)floorf(__fsub_rn(kpR.y, r));
-        if (row < minr || row > maxr) continue;
-        if (kpR.octave < levelL - 1 || kpR.octave > levelL + 1) continue;
-        if (kpR.x >= minU && kpR.x <= maxU) {
+        const uint4 q = __ldg(rowsR + iR);               // x | minr | maxr | octave
+        if (row < (int)q.y || row > (int)q.z) continue;
+        const int oc = (int)q.w;
+        if (oc < levelL - 1 || oc > levelL + 1) continue;
+        const float xR = __uint_as_float(q.x);
+        if (xR >= minU && xR <= maxU) {
             const int d = dist256s(dL, reinterpret_cast<const uint4*>(descR + (size_t)iR * 32));
             if (d < TH_HIGH) best = min(best, ((unsigned)d << 16) | (unsigned)iR);
         }
@@ -211,7 +224,7 @@ extern "C" int orb_stereo_match(orb_ctx* cl, orb_ctx* cr, const orb_kp* kps_l, c
     const size_t in_bytes = off;
     const size_t o_ur = take(sizeof(float) * nl), o_dep = take(sizeof(float) * nl), o_nk = take(16);
     const size_t io_bytes = off;
-    const size_t o_sad = take(sizeof(int) * nl);
+    const size_t o_sad = take(sizeof(int) * nl), o_rows = take(sizeof(uint4) * (size_t)nr);
     if (cl->d_scratch_cap < off) {
         ORB_CUDA(cudaStreamSynchronize(st));
         cudaFree(cl->d_scratch); cl->d_scratch = nullptr; cl->d_scratch_cap = 0;
@@ -231,10 +244,12 @@ extern "C" int orb_stereo_match(orb_ctx* cl, orb_ctx* cr, const orb_kp* kps_l, c
     {
         StereoScales sc;
         for (int l = 0; l < ORB_MAX_LEVELS; ++l) { sc.scale[l] = l < cl->nlevels ? cl->scale[l] : 1.f; sc.inv_scale[l] = l < cl->nlevels ? cl->inv_scale[l] : 1.f; }
+        stereo_rows_kernel<<<(nr + 255) / 256, 256, 0, st>>>((const orb_kp*)(D + o_kr), nr, sc, (uint4*)(D + o_rows));
         stereo_match_kernel<<<(nl + 7) / 8, 256, 0, st>>>(cl->d_pyr, cr->d_pyr, (const orb_kp*)(D + o_kl), D + o_dl, nl, (const orb_kp*)(D + o_kr),
-                                                         D + o_dr, nr, bf, b, sc, (float*)(D + o_ur), (float*)(D + o_dep), (int*)(D + o_sad), cl->g);
+                                                         D + o_dr, nr, bf, b, sc, (float*)(D + o_ur), (float*)(D + o_dep), (int*)(D + o_sad),
+                                                         (const uint4*)(D + o_rows), cl->g);
         stereo_median_kernel<<<1, 1024, sizeof(int) * (size_t)nl, st>>>(nl, (float*)(D + o_ur), (float*)(D + o_dep), (const int*)(D + o_sad), (int*)(D + o_nk));
-        cl->launches += 2;
+        cl->launches += 3;
     }
     ORB_CUDA(cudaGetLastError());
     ORB_CUDA(cudaMemcpyAsync(H + o_ur, D + o_ur, io_bytes - o_ur, cudaMemcpyDeviceToHost, st));
