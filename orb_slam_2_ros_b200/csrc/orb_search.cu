@@ -91,6 +91,26 @@ struct SearchArgs {
     unsigned* topk;   // [nq][SR_K] sorted keys (dist << 16 | position in the candidate list), 0xFFFFFFFF = none
 };
 
+
+// the SR_K smallest keys of a warp, given every lane's ascending list best[0..SR_K): SR_K rounds of "warp minimum of the
+// list heads, the owning lane pops" (keys are unique: they carry a position).  Lane k returns the k-th smallest.
+__device__ __forceinline__ unsigned warp_topk_extract(unsigned (&best)[SR_K], int lane) {
+    unsigned mine = 0xFFFFFFFFu;
+#pragma unroll
+    for (int k = 0; k < SR_K; ++k) {
+        unsigned m = best[0];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == k) mine = m;
+        if (best[0] == m && m != 0xFFFFFFFFu) {
+#pragma unroll
+            for (int i = 0; i + 1 < SR_K; ++i) best[i] = best[i + 1];
+            best[SR_K - 1] = 0xFFFFFFFFu;
+        }
+    }
+    return mine;
+}
+
 // ---- one warp per query: GetFeaturesInArea in reference order + distances -----------------------------------
 // pass 0 counts, pass 1 (after the warp reserved its segment) writes (index, distance) in candidate order.
 __global__ void __launch_bounds__(256)
@@ -158,7 +178,7 @@ window_candidates_kernel(const SearchArgs a) {
                     }
                     a.cand_idx[pos] = id;
                     a.cand_dist[pos] = (unsigned short)d;
-                    if (d < 256) insert(((unsigned)d << 16) | (unsigned)(pos - base));
+                    if (d < 256) { const unsigned key = ((unsigned)d << 16) | (unsigned)(pos - base); if (key < best[SR_K - 1]) insert(key); }
                 }
                 written += __popc(m);
             }
@@ -176,18 +196,8 @@ window_candidates_kernel(const SearchArgs a) {
         }
     }
     // warp merge of the per-lane sorted top-K lists
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        unsigned other[SR_K];
-#pragma unroll
-        for (int k = 0; k < SR_K; ++k) other[k] = __shfl_xor_sync(0xffffffffu, best[k], o);
-#pragma unroll
-        for (int k = 0; k < SR_K; ++k) insert(other[k]);
-    }
-    if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < SR_K; ++k) a.topk[(size_t)qi * SR_K + k] = best[k];
-    }
+    const unsigned mine = warp_topk_extract(best, lane);
+    if (lane < SR_K) a.topk[(size_t)qi * SR_K + lane] = mine;
 }
 
 __device__ __forceinline__ unsigned warp_min_u32(unsigned v) {
@@ -661,20 +671,11 @@ bf_rows_kernel(const uint8_t* __restrict__ d1, int n1, const uint8_t* __restrict
     for (int j = lane; j < n2; j += 32) {
         const int d = dist256(dq, reinterpret_cast<const uint4*>(d2 + (size_t)j * 32));
         D[(size_t)i * dpitch + j] = (unsigned short)d;
-        insert(((unsigned)d << 16) | (unsigned)j);
+        const unsigned key = ((unsigned)d << 16) | (unsigned)j;
+        if (key < best[BF_K - 1]) insert(key);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        unsigned other[BF_K];
-#pragma unroll
-        for (int k = 0; k < BF_K; ++k) other[k] = __shfl_xor_sync(0xffffffffu, best[k], o);
-#pragma unroll
-        for (int k = 0; k < BF_K; ++k) insert(other[k]);
-    }
-    if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < BF_K; ++k) topk[(size_t)i * BF_K + k] = best[k];
-    }
+    const unsigned mine = warp_topk_extract(best, lane);
+    if (lane < BF_K) topk[(size_t)i * BF_K + lane] = mine;
 }
 
 // The order-dependent part ("a target taken by an earlier query is invisible to the later ones", ORBmatcher.cc:210) as a
