@@ -374,11 +374,15 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--noise", type=int, default=8, help="+-grey-level noise of the synthetic frames (SURVEY.md §8d: 8)")
     ap.add_argument("--e2e-callers", type=int, default=2, help="2: also time two extractor instances on two host threads")
+    ap.add_argument("--frame-size", default="", help="WxH of the synthetic frames (default 640x480 = the metric's shape; 752x480 = BASELINE config 4)")
     ap.add_argument("--no-hamming", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     protect_stdout()
+    if args.frame_size:
+        global W, H
+        W, H = (int(x) for x in args.frame_size.lower().split("x"))
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -674,8 +678,8 @@ def main():
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "ORBextractor 640x480 nFeatures=1000 8 levels 1.2 20/7 (BASELINE config 1), batch of %d frames "
-                                   "per GPU per step, synthetic frames with +-%d grey-level noise" % (B, args.noise), "frames_per_step_per_gpu": B, "keypoints_per_step_per_gpu": n_kp,
+            "config": {"workload": "ORBextractor %dx%d nFeatures=1000 8 levels 1.2 20/7 (BASELINE config 1), batch of %d frames "
+                                   "per GPU per step, synthetic frames with +-%d grey-level noise" % (W, H, B, args.noise), "frames_per_step_per_gpu": B, "keypoints_per_step_per_gpu": n_kp,
                        "l2": "inputs larger than L2 (%d MB of frames + %d MB pyramid arena per step)" % (B * W * H >> 20, (B * 1158012) >> 20),
                        "parallelism": "frames sharded over %d GPU(s), no collective" % world,
                        "host_affinity": ("rank 0 bound to the cpus next to its GPU: %s" % numa_cpus) if numa_cpus else "unbound"},
