@@ -191,7 +191,8 @@ typedef struct {
  * GetFeaturesInArea (Frame.cc:354-412), descriptor, predicted right coordinate + tolerance (NULL when
  * u_right is NULL), angle for the rotation histogram, q_valid (NULL = all), q_obs (query's map point has
  * Observations()>0, NULL = all).  Outputs: match_of_query[nq] (target index or -1), target_query[n]
- * (final owner of each target = final Frame::mvpMapPoints, may be NULL), *nmatches.
+ * (final owner of each target = final Frame::mvpMapPoints, may be NULL: query index, -1 = untouched, -2 = matched and
+ * then removed by the rotation filter, i.e. the reference leaves NULL there, ORBmatcher.cc:1462-1466), *nmatches.
  */
 int orb_search_by_projection(int device, const orb_search_params* prm, const orb_kp* kps_un, const uint8_t* desc,
                              const float* u_right, int n, uint8_t* taken, int nq, const float* q_u,

@@ -163,7 +163,8 @@ int orc_grid_query(void* g, float x, float y, float r, int minLevel, int maxLeve
 
 /* OM:1330-1472 (TRACK_LAST) and OM:45-129 (LOCAL_POINTS); q_obs[i] = query map point has Observations()>0
  * (only then does its assignment block later queries, OM:1405-1407 / OM:87-89).
- * target_query[n] (out): final owner (query index) of each target keypoint, -1 = none. */
+ * target_query[n] (out): final owner (query index) of each target keypoint, -1 = none, -2 = matched and then removed by
+ * the rotation filter (the reference sets that keypoint's map point to NULL, OM:1462-1466). */
 int orc_search_by_projection_ex(const orc_search_params* prm, void* grid, const orc_kp* kps_un,
                                 const uint8_t* desc, const float* u_right, int n, uint8_t* taken, int nq,
                                 const float* q_u, const float* q_v, const float* q_radius,
@@ -261,7 +262,7 @@ int orc_search_by_projection_ex(const orc_search_params* prm, void* grid, const 
         three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
         for (int b = 0; b < HISTO_LENGTH; ++b) {
             if (b == ind1 || b == ind2 || b == ind3) continue;
-            for (int idx : rotHist[b]) { owner[idx] = -1; nmatches--; }
+            for (int idx : rotHist[b]) { owner[idx] = -2; nmatches--; }   /* OM:1462-1466: NULLed, not "left alone" */
         }
     }
     if (target_query) memcpy(target_query, owner.data(), (size_t)n * 4);
@@ -269,7 +270,7 @@ int orc_search_by_projection_ex(const orc_search_params* prm, void* grid, const 
     for (int i = 0; i < nq; ++i)
         if (match_of_query[i] >= 0 && owner[match_of_query[i]] != i) {
             // removed by the rotation filter, or overwritten by a later query (only when q_obs==0)
-            if (owner[match_of_query[i]] == -1) match_of_query[i] = -1;
+            if (owner[match_of_query[i]] == -2) match_of_query[i] = -1;
         }
     return nmatches;
 }

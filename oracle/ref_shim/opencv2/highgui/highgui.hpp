@@ -1,0 +1,2 @@
+/* OpenCV stand-in (test infrastructure): see cvshim.hpp */
+#include "../../cvshim.hpp"

@@ -630,7 +630,7 @@ window_resolve_kernel(const SearchArgs a, int mode, int th_dist, float nn_ratio,
         for (int qi = threadIdx.x; qi < a.nq; qi += SR_THREADS) {
             const int bin = match_bin[qi];
             if (bin >= 0 && bin != ind1 && bin != ind2 && bin != ind3) {
-                target_query[match_of_query[qi]] = -1;   // ORBmatcher.cc:1462-1466
+                target_query[match_of_query[qi]] = -2;   // ORBmatcher.cc:1462-1466: the reference NULLs the keypoint's map point (also one it held before)
                 removed++;
             }
         }
@@ -640,7 +640,7 @@ window_resolve_kernel(const SearchArgs a, int mode, int th_dist, float nn_ratio,
         // per-query view: a query whose target was nulled loses its match
         for (int qi = threadIdx.x; qi < a.nq; qi += SR_THREADS) {
             const int m = match_of_query[qi];
-            if (m >= 0 && target_query[m] == -1) match_of_query[qi] = -1;
+            if (m >= 0 && target_query[m] == -2) match_of_query[qi] = -1;
         }
     }
     if (threadIdx.x == 0) *nmatches_out = nmatches;

@@ -4,6 +4,9 @@
 #include <stdexcept>
 #include <string>
 
+#include <cstdlib>
+#include <cstring>
+
 #include "../../include/orb_b200.h"
 
 namespace ORB_SLAM2 {
@@ -14,7 +17,9 @@ static void check(int rc, const char* what) {
 
 ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int _iniThFAST, int _minThFAST)
     : nfeatures(_nfeatures), scaleFactor(_scaleFactor), nlevels(_nlevels), iniThFAST(_iniThFAST), minThFAST(_minThFAST) {
-    check(orb_create(&ctx_, nfeatures, _scaleFactor, nlevels, iniThFAST, minThFAST, /*device*/ 0, /*max_batch*/ 1), "orb_create");
+    // the reference constructor has no notion of a device: ORB_B200_DEVICE selects it (default 0)
+    const char* dev = getenv("ORB_B200_DEVICE");
+    check(orb_create(&ctx_, nfeatures, _scaleFactor, nlevels, iniThFAST, minThFAST, dev ? atoi(dev) : 0, /*max_batch*/ 1), "orb_create");
     mvScaleFactor.resize(nlevels); mvInvScaleFactor.resize(nlevels); mvLevelSigma2.resize(nlevels);
     mvInvLevelSigma2.resize(nlevels); mnFeaturesPerLevel.resize(nlevels);
     check(orb_get_tables(ctx_, mvScaleFactor.data(), mvInvScaleFactor.data(), mvLevelSigma2.data(), mvInvLevelSigma2.data(),
@@ -29,6 +34,9 @@ void ORBextractor::operator()(cv::InputArray _image, cv::InputArray /*_mask*/, s
                               cv::OutputArray _descriptors) {
     if (_image.empty()) return;                                  // ORBextractor.cc:1086-1087
     cv::Mat image = _image.getMat();
+    // the reference only asserts CV_8UC1 (ORBextractor.cc:1090, compiled out in Release) and would then read garbage; a
+    // colour or 16-bit Mat here is a caller bug, so fail loudly instead of extracting from misinterpreted bytes
+    if (image.type() != CV_8UC1) throw std::runtime_error("ORBextractor: image must be CV_8UC1 (use orb_extract_batch_pix for colour input)");
     const int cap = orb_max_keypoints(ctx_);
     _keypoints.resize(cap);
     static_assert(sizeof(cv::KeyPoint) == sizeof(orb_kp), "cv::KeyPoint must be 28 bytes");

@@ -1,4 +1,4 @@
-// host_check.cpp — drives the C++ host shims (ORBextractor / ORBmatcher / ComputeStereoMatches) the way Frame.cc does
+// host_check.cpp — drives the C++ host shims (ORBextractor / ORBmatcherArrays / ComputeStereoMatches) the way Frame.cc does
 // and dumps the results for tests/test_gpu_host_shim.py, which compares them with the oracle.
 //   host_check <w> <h> <nfeatures> <nlevels> <left.raw> <out.bin> [<right.raw> <bf> <b>]
 //   host_check bow <voc.txt> <w> <h> <a.raw> <b.raw> <out.bin>   (Frame::ComputeBoW on both frames + SearchByBoW)
@@ -11,7 +11,7 @@
 
 #include "ORBextractor.h"
 #include "ORBVocabulary.h"
-#include "ORBmatcher.h"
+#include "ORBmatcherArrays.h"
 #include <cstring>
 
 using namespace ORB_SLAM2;
@@ -24,7 +24,7 @@ static cv::Mat read_raw(const char* path, int w, int h) {
     return m;
 }
 
-// Frame::ComputeBoW (Frame.cc:428-435) on two extracted frames, then ORBmatcher::SearchByBoW(KeyFrame, Frame) with every
+// Frame::ComputeBoW (Frame.cc:428-435) on two extracted frames, then ORBmatcherArrays::SearchByBoW(KeyFrame, Frame) with every
 // keypoint of the first frame holding a map point.  Dump: per frame int32 n | n x 32 B | int32 nb | nb x (u32 word, f64 value)
 // | int32 nf | per node (u32 node, int32 count, count x u32) ; then int32 nmatches | n1 x int32 match12 | n2 x int32 match21.
 static int bow_main(char** argv) {
@@ -58,7 +58,7 @@ static int bow_main(char** argv) {
     std::vector<float> a[2];
     for (int f = 0; f < 2; ++f) for (size_t i = 0; i < k[f].size(); ++i) a[f].push_back(k[f][i].angle);
     std::vector<int32_t> m12, m21;
-    ORBmatcher matcher(0.7f, true);
+    ORBmatcherArrays matcher(0.7f, true);
     int nm = matcher.SearchByBoW(d[0].data, a[0].data(), nullptr, (int)k[0].size(), fv[0], d[1].data, a[1].data(), nullptr, (int)k[1].size(), fv[1],
                                  false, m12, m21);
     fwrite(&nm, 4, 1, o);

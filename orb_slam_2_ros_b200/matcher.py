@@ -26,9 +26,10 @@ class ORBmatcher:
 
     @staticmethod
     def DescriptorDistance(a, b, device=0):
-        """ORBmatcher.cc:1649-1665.  Computed on the device like everything else (one 1x1 search)."""
-        out = hamming_top2(np.asarray(a, np.uint8).reshape(1, 32), np.asarray(b, np.uint8).reshape(1, 32), device)
-        return int(out["best_dist"][0])
+        """ORBmatcher.cc:1649-1665.  One 256-bit popcount stays on the host (a device round trip per pair would stall
+        MapPoint::ComputeDistinctiveDescriptors' O(N^2) loop, MapPoint.cc:332); the GPU serves the batched entry points."""
+        x = np.bitwise_xor(np.asarray(a, np.uint8).reshape(32), np.asarray(b, np.uint8).reshape(32))
+        return int(np.unpackbits(x).sum())
 
     def SearchByProjection(self, mode, kps_un, desc, bounds, taken, q_u, q_v, q_radius, q_min_level, q_max_level,
                            q_desc, u_right=None, q_ur=None, q_er_max=None, q_angle=None, q_valid=None, q_obs=None,
