@@ -1,0 +1,153 @@
+"""Drop-in parity on the GPU: the reference's own callers (unmodified Frame.cc constructors, Frame::GetFeaturesInArea,
+isInFrustum, ORBmatcher.h signatures) run twice over the same seeded worlds —
+
+  reference arm  oracle/_ref/liborb_ref.so     the reference's unmodified ORBextractor.cc / ORBmatcher.cc / Frame.cc
+  drop-in arm    tests/_build/liborb_dropin.so  this repo's host/ORBextractor.cc, host/ORBmatcher.cc and
+                                               host/Frame_ComputeStereoMatches.cc over liborb_b200.so (CUDA)
+
+— and every observable output must be bit-identical: keypoints, descriptors, bordered pyramid levels, mvuRight / mvDepth,
+Frame::mvpMapPoints after each SearchByProjection overload, vpMatched, vnMatches12 + vbPrevMatched, vMatchedPairs,
+vpMatches12, the map mutation of Fuse.  Both libraries are built in the authoring container (they need /root/reference)
+and shipped prebuilt; the tests skip when they are absent."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(__file__))
+import dropin_scenarios as S  # noqa: E402
+from oracle import orb_ref  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def arms():
+    if not (os.path.exists(orb_ref.REF_SO) and os.path.exists(orb_ref.DROPIN_SO)):
+        pytest.skip("harness libraries not built (need /root/reference at build time)")
+    ref, dut = orb_ref.Harness(orb_ref.REF_SO), orb_ref.Harness(orb_ref.DROPIN_SO)
+    assert ref.arm == "reference" and dut.arm == "b200"
+    ref.L.rh_set_monotonic_alloc(1)   # quadtree ties by creation order: the stated pin (ii), see oracle/ref_shim/mono_alloc.cpp
+    return ref, dut
+
+
+def same(a, b, what):
+    assert a.keys() == b.keys()
+    for k in a:
+        x, y = np.asarray(a[k]), np.asarray(b[k])
+        assert x.shape == y.shape, "%s: %s shape %s vs %s" % (what, k, x.shape, y.shape)
+        assert x.tobytes() == y.tobytes(), "%s: %s differs (%d of %d entries)" % (what, k, int((x != y).sum()) if x.dtype.fields is None else -1, x.size)
+
+
+def both(arms, fn, *a, **k):
+    ref, dut = arms
+    r, d = fn(ref, *a, **k), fn(dut, *a, **k)
+    same(r, d, "%s%s%s" % (fn.__name__, a, k))
+    return r
+
+
+@pytest.mark.parametrize("seed,w,h,nf,nl", [(0, 640, 480, 1000, 8), (3, 752, 480, 1000, 8), (4, 1241, 376, 2000, 8), (6, 320, 240, 500, 6),
+                                             (8, 645, 487, 1000, 8), (11, 1023, 767, 2000, 10)])
+def test_extractor_operator_call(arms, seed, w, h, nf, nl):
+    r = both(arms, S.extraction, seed, w, h, nf, nl)
+    assert len(r["kps"]) >= nf * 0.9
+
+
+def test_constants_and_descriptor_distance(arms):
+    ref, dut = arms
+    assert ref.constants() == dut.constants() == (50, 100, 30)
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        a, b = rng.integers(0, 256, 32, dtype=np.uint8), rng.integers(0, 256, 32, dtype=np.uint8)
+        assert ref.descriptor_distance(a, b) == dut.descriptor_distance(a, b) == int(np.unpackbits(a ^ b).sum())
+    a = rng.integers(0, 256, 32, dtype=np.uint8)
+    assert dut.descriptor_distance(a, a ^ np.uint8(255)) == 256 and dut.descriptor_distance(a, a) == 0
+
+
+@pytest.mark.parametrize("seed", [0, 2, 5])
+def test_stereo_frame_constructor(arms, seed):
+    """Frame(imLeft, imRight, ...): two extractor threads + ComputeStereoMatches (Frame.cc:60-128, 502-676)."""
+    r = both(arms, S.stereo_frame, seed)
+    assert (r["depth"] > 0).sum() > 300
+
+
+def test_stereo_frame_small(arms):
+    both(arms, S.stereo_frame, 1, 640, 240, 800)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_features_in_area_of_extracted_frames(arms, seed):
+    both(arms, S.features_in_area, seed)
+
+
+@pytest.mark.parametrize("mono,th,motion,sf,prefill", [(True, 15, "none", 0.0, False), (True, 7, "none", 0.0, True), (False, 7, "forward", 0.7, True),
+                                                       (False, 7, "backward", 0.7, False), (False, 15, "none", 0.5, True)])
+@pytest.mark.parametrize("seed", [1, 7])
+def test_search_by_projection_last_frame(arms, seed, mono, th, motion, sf, prefill):
+    r = both(arms, S.track_last, seed, mono, th, motion, stereo_fraction=sf, prefill=prefill)
+    assert r["n"] > 100
+
+
+def test_search_by_projection_last_frame_no_orientation(arms):
+    both(arms, S.track_last, 3, True, 15, "none", check_ori=False)
+
+
+@pytest.mark.parametrize("seed,th,sf", [(2, 3.0, 0.5), (4, 1.0, 0.0), (9, 5.0, 0.8)])
+def test_search_local_points(arms, seed, th, sf):
+    r = both(arms, S.local_points, seed, th, stereo_fraction=sf)
+    assert r["n"] > 100
+
+
+@pytest.mark.parametrize("seed,th,orb_dist", [(3, 10.0, 100), (3, 3.0, 64), (5, 10.0, 64), (6, 3.0, 100)])
+def test_search_by_projection_relocalisation(arms, seed, th, orb_dist):
+    """a13: ORBmatcher.cc:1474-1601 — ORBdist threshold, non-empty sAlreadyFound, keypoints holding ANY point are hidden."""
+    r = both(arms, S.reloc, seed, th, orb_dist)
+    assert r["n"] > 50
+    both(arms, S.reloc, seed, th, orb_dist, check_ori=False)
+
+
+@pytest.mark.parametrize("seed,th,scale", [(4, 10, 1.0), (4, 10, 1.7), (8, 4, 0.6)])
+def test_search_by_projection_loop_closure(arms, seed, th, scale):
+    """a14: ORBmatcher.cc:291-404 — Sim3 pose, pre-filled vpMatched, TH_LOW, no rotation histogram."""
+    r = both(arms, S.loop_projection, seed, th, scale)
+    assert r["n"] > 50
+
+
+@pytest.mark.parametrize("seed", [5, 12])
+def test_search_by_bow(arms, seed):
+    assert both(arms, S.bow_kf_frame, seed)["n"] > 100
+    assert both(arms, S.bow_kf_kf, seed)["n"] > 100
+    both(arms, S.bow_kf_frame, seed, nnratio=0.9, check_ori=False)
+
+
+@pytest.mark.parametrize("seed,window", [(6, 100), (2, 30)])
+def test_search_for_initialization(arms, seed, window):
+    assert both(arms, S.initialization, seed, window)["n"] > 50
+
+
+@pytest.mark.parametrize("seed,kw", [(6, {}), (7, dict(stereo_fraction=0.6)), (7, dict(only_stereo=True, stereo_fraction=0.6)), (5, {}),
+                                     (8, dict(check_ori=False))])
+def test_search_for_triangulation(arms, seed, kw):
+    both(arms, S.triangulation, seed, **kw)
+
+
+@pytest.mark.parametrize("seed,s12", [(8, 1.0), (3, 1.3)])
+def test_search_by_sim3(arms, seed, s12):
+    assert both(arms, S.sim3, seed, 7.5, s12)["n"] > 50
+
+
+@pytest.mark.parametrize("seed,sf", [(9, 0.5), (2, 0.0)])
+def test_fuse(arms, seed, sf):
+    assert both(arms, S.fuse, seed, 3.0, sf)["n"] > 50
+
+
+@pytest.mark.parametrize("seed,scale", [(9, 1.0), (1, 2.0)])
+def test_fuse_sim3(arms, seed, scale):
+    assert both(arms, S.fuse_sim3, seed, 4.0, scale)["n"] > 50
+
+
+@pytest.mark.parametrize("seed", [10, 11])
+def test_dense_ties_and_chains(arms, seed):
+    r = both(arms, S.dense_ties, seed)
+    assert r["last_n"] > 500
