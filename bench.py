@@ -125,10 +125,28 @@ def summarize_clocks(rows):
 # ---------------------------------------------------------------------------------------------------------
 # CPU restatement (oracle/) on the host cores: cpu_baseline leg and the --impl reference arm
 # ---------------------------------------------------------------------------------------------------------
-def cpu_extract_throughput(frames, threads, repeat=1):
-    """frames: uint8 [n, H, W]; every thread owns one oracle extractor and takes frames round-robin."""
-    from oracle import orb_oracle
-    exs = [orb_oracle.Extractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH) for _ in range(threads)]
+def cpu_arm():
+    """('reference', harness) when oracle/_ref/liborb_ref.so is there — the reference's own unmodified ORBextractor.cc compiled over
+    the OpenCV stand-in (oracle/Makefile) — else ('port', None): oracle/'s restatement."""
+    try:
+        from oracle import orb_ref
+        if os.path.exists(orb_ref.REF_SO):
+            H = orb_ref.Harness(orb_ref.REF_SO)
+            H.L.rh_set_monotonic_alloc(0)      # plain malloc for the quadtree nodes, as the reference runs
+            return "reference", H
+    except Exception as e:                     # noqa: BLE001
+        sys.stderr.write("oracle/_ref unavailable (%s): timing the oracle port\n" % e)
+    return "port", None
+
+
+def cpu_extract_throughput(frames, threads, repeat=1, harness=None):
+    """frames: uint8 [n, H, W]; every thread owns one CPU extractor (the reference's ORBextractor through the rh_* harness, or
+    the oracle port) and takes frames round-robin."""
+    if harness is not None:
+        exs = [harness.extractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH) for _ in range(threads)]
+    else:
+        from oracle import orb_oracle
+        exs = [orb_oracle.Extractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH) for _ in range(threads)]
     counts = [0] * threads
 
     def work(t):
@@ -144,6 +162,65 @@ def cpu_extract_throughput(frames, threads, repeat=1):
         th.join()
     dt = time.perf_counter() - t0
     return sum(counts) / dt, dt, sum(counts)
+
+
+def cv2_simd_primitive_row(frame, reps=5):
+    """BASELINE.md row B5 (sanity, not the headline): OpenCV's own SIMD kernels (the cv2 4.13.0 wheel, one thread) on the primitive
+    calls ORBextractor makes for one frame — resize + copyMakeBorder per level, one cv::FAST call per 30-px cell at iniThFAST,
+    GaussianBlur per level — driven from Python (the ~800 FAST calls include interpreter overhead).  Shows how far the scalar,
+    bit-exact primitives of the CPU arm are from an optimised OpenCV build.  None when cv2 is not importable."""
+    try:
+        import cv2
+    except Exception:      # noqa: BLE001
+        return None
+    cv2.setNumThreads(1)
+    h, w = frame.shape
+    dims = level_dims(w, h)
+    fast = cv2.FastFeatureDetector_create(INI_TH, True)
+
+    def pyramid():
+        lv = [frame]
+        for (lw, lh) in dims[1:]:
+            lv.append(cv2.resize(lv[-1], (lw, lh), interpolation=cv2.INTER_LINEAR))
+        return [cv2.copyMakeBorder(x, 19, 19, 19, 19, cv2.BORDER_REFLECT_101) for x in lv]
+
+    def cells(bordered):
+        n = 0
+        for b in bordered:
+            H_, W_ = b.shape[0] - 38, b.shape[1] - 38
+            minb, maxx, maxy = 19 + 16, 19 + W_ - 16, 19 + H_ - 16     # ORBextractor.cc:801-817 (minBorder = 16, maxBorder = dim - 16), bordered coordinates
+            ncols, nrows = (maxx - minb) // 30, (maxy - minb) // 30
+            wc, hc = -(-(maxx - minb) // ncols), -(-(maxy - minb) // nrows)
+            for i in range(nrows):
+                y0 = minb + i * hc
+                y1 = min(y0 + hc + 6, maxy)
+                if y0 >= maxy - 3:
+                    continue
+                for j in range(ncols):
+                    x0 = minb + j * wc
+                    x1 = min(x0 + wc + 6, maxx)
+                    if x0 >= maxx - 6:
+                        continue
+                    fast.detect(b[y0:y1, x0:x1])
+                    n += 1
+        return n
+
+    def blur(bordered):
+        for b in bordered:
+            cv2.GaussianBlur(b[19:-19, 19:-19].copy(), (7, 7), 2, None, 2, cv2.BORDER_REFLECT_101)
+
+    def ms(fn, *a):
+        fn(*a)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            r = fn(*a)
+        return (time.perf_counter() - t0) / reps * 1e3, r
+    t_pyr, bordered = ms(pyramid)
+    t_fast, ncell = ms(cells, bordered)
+    t_blur, _ = ms(blur, bordered)
+    return {"pyramid_ms": t_pyr, "fast_cells_ms": t_fast, "fast_calls": ncell, "blur_ms": t_blur, "threads": 1, "cv2": cv2.__version__,
+            "note": "BASELINE.md B5 sanity row: cv2 SIMD kernels called from Python for ONE %dx%d frame (no quadtree / orientation / descriptors); "
+                    "not the baseline" % (w, h)}
 
 
 def cpu_hamming_throughput(q, db, threads):
@@ -302,19 +379,21 @@ def other_configs(device):
 
 
 def run_reference(args, rank):
-    """--impl reference: the reference's CPU path.  Its own translation units need OpenCV C++ headers that this
-    image lacks, so the arm times oracle/'s restatement (kind "port") on all host cores."""
+    """--impl reference: the reference's own CPU implementation of the path on all host cores.  oracle/_ref/liborb_ref.so is
+    the reference's UNMODIFIED ORBextractor.cc compiled from /root/reference over an OpenCV stand-in whose primitives are
+    verified against cv2 4.13.0 (kind "reference"); if that library is missing the arm times oracle/'s restatement (kind "port")."""
     if rank != 0:
         return
     from orb_slam_2_ros_b200 import synth
+    kind, harness = cpu_arm()
     threads = os.cpu_count() or 1
     sample = max(threads, min(args.ref_frames, 4 * threads))
     frames = synth.synth_batch(0, sample, W, H, unique=min(16, sample))
     for _ in range(args.warmup):
-        cpu_extract_throughput(frames[:threads], threads)
+        cpu_extract_throughput(frames[:threads], threads, harness=harness)
     t_total, n_total = 0.0, 0
     for _ in range(args.steps):
-        _fps, dt, n = cpu_extract_throughput(frames, threads)
+        _fps, dt, n = cpu_extract_throughput(frames, threads, harness=harness)
         t_total += dt
         n_total += n
     fps = n_total / t_total
@@ -329,8 +408,10 @@ def run_reference(args, rank):
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": "ORBextractor 640x480 nFeatures=1000 8 levels 1.2 20/7 (BASELINE config 1 shape), "
                                "%d frames per step on %d host threads" % (sample, threads)},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
-                         "sample": "%d synthetic frames per step, one oracle extractor per thread" % sample},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
+                         "sample": "%d synthetic frames per step, one %s per host thread; scalar OpenCV-4.13-exact primitives "
+                                   "(no SIMD: an OpenCV build with SIMD kernels is roughly 2x faster per frame)"
+                                   % (sample, "reference ORBextractor (unmodified ORBextractor.cc, oracle/_ref)" if kind == "reference" else "oracle extractor")},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "hamming": {"metric": "Hamming compares/s", "value": cps, "unit": "compares/s", "cores": threads, "kind": "port",
                     "sample": "256 queries x 400000 rows, reference bit-hack DescriptorDistance, %.2f s" % hdt},
@@ -669,11 +750,16 @@ def main():
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
             sample = frames_np[:max(threads, 16)]
-            fps1, dt1, n1 = cpu_extract_throughput(sample[:threads], threads)      # calibration pass (also warm-up)
+            kind, harness = cpu_arm()
+            fps1, dt1, n1 = cpu_extract_throughput(sample[:threads], threads, harness=harness)      # calibration pass (also warm-up)
             repeat = max(1, int(args.cpu_seconds * fps1 / len(sample)))
-            fps, dt, n = cpu_extract_throughput(sample, threads, repeat=repeat)
-            cpu = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
-                   "sample": "%d extractions of %d distinct synthetic frames in %.1f s, one oracle extractor per thread" % (n, len(sample), dt)}
+            fps, dt, n = cpu_extract_throughput(sample, threads, repeat=repeat, harness=harness)
+            cpu = {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
+                   "sample": "%d extractions of %d distinct synthetic frames in %.1f s, one %s per host thread; scalar OpenCV-4.13-exact "
+                             "primitives (no SIMD: an OpenCV build with SIMD kernels is roughly 2x faster per frame)"
+                             % (n, len(sample), dt, "reference ORBextractor (unmodified ORBextractor.cc, oracle/_ref)" if kind == "reference" else "oracle extractor"),
+                   "per_frame_ms_one_thread": 1e3 * threads / fps,
+                   "cv2_simd_primitives": cv2_simd_primitive_row(frames_np[0])}
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -48,10 +48,13 @@ void FAST(InputArray _image, std::vector<KeyPoint>& keypoints, int threshold, bo
     Mat img = _image.getMat();
     need_u8(img, "FAST of a non-8UC1 Mat");
     static_assert(sizeof(KeyPoint) == sizeof(orc_kp), "KeyPoint layout");
-    const int cap = std::max(1, img.rows * img.cols);
-    keypoints.resize(cap);
-    const int n = orc_fast9_16(img.data, img.cols, img.rows, (int)img.step, threshold, nonmaxSuppression ? 1 : 0, reinterpret_cast<orc_kp*>(keypoints.data()), cap);
-    keypoints.resize(n < 0 ? 0 : n);
+    int cap = 256;
+    for (;;) {   /* orc_fast9_16 returns the full count and writes at most cap entries */
+        keypoints.resize(cap);
+        const int n = orc_fast9_16(img.data, img.cols, img.rows, (int)img.step, threshold, nonmaxSuppression ? 1 : 0, reinterpret_cast<orc_kp*>(keypoints.data()), cap);
+        if (n <= cap) { keypoints.resize(n < 0 ? 0 : n); break; }
+        cap = n;
+    }
 }
 
 }  // namespace cv

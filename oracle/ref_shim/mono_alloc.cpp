@@ -28,35 +28,53 @@
 namespace {
 
 const size_t kNode = sizeof(std::_List_node<ORB_SLAM2::ExtractorNode>);
-const size_t kArena = (size_t)256 << 20;   /* virtual reservation; pages are touched lazily */
+/* one bump region per thread (the stereo Frame constructor runs two extractors on two std::threads, Frame.cc:79-82):
+ * kSlots regions of kSlot bytes inside one virtual reservation; pages are touched lazily */
+const size_t kSlot = (size_t)32 << 20;
+const int kSlots = 128;
 
 char* g_base = nullptr;
-std::atomic<size_t> g_cur{0};
-std::atomic<long> g_live{0};
 std::atomic<int> g_on{1};
 std::atomic<long> g_served{0};
+std::atomic<unsigned char> g_used[kSlots];
+
+struct Slot {
+    int id = -1;
+    size_t cur = 0;
+    long live = 0;
+    ~Slot() { if (id >= 0) g_used[id].store(0, std::memory_order_release); }
+};
+thread_local Slot t_slot;
 
 char* arena() {
     static char* base = [] {
-        void* p = mmap(nullptr, kArena, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+        void* p = mmap(nullptr, kSlot * kSlots, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
         return p == MAP_FAILED ? (char*)nullptr : (char*)p;
     }();
     return base;
 }
 
-inline bool in_arena(void* p) { return g_base && (char*)p >= g_base && (char*)p < g_base + kArena; }
+inline bool in_arena(void* p) { return g_base && (char*)p >= g_base && (char*)p < g_base + kSlot * kSlots; }
 
 void* alloc(size_t n) {
     if (n == kNode && g_on.load(std::memory_order_relaxed)) {
         if (!g_base) g_base = arena();
-        if (g_base) {
-            const size_t off = g_cur.fetch_add(kNode, std::memory_order_relaxed);
-            if (off + kNode <= kArena) {
-                g_live.fetch_add(1, std::memory_order_relaxed);
-                g_served.fetch_add(1, std::memory_order_relaxed);
-                return g_base + off;
+        Slot& s = t_slot;
+        if (g_base && s.id < 0) {
+            for (int i = 0; i < kSlots; ++i) {
+                unsigned char expect = 0;
+                if (g_used[i].compare_exchange_strong(expect, 1)) { s.id = i; s.cur = 0; s.live = 0; break; }
             }
-            std::fprintf(stderr, "mono_alloc: arena exhausted, falling back to malloc (tie order no longer pinned)\n");
+        }
+        if (g_base && s.id >= 0) {
+            if (s.cur + kNode <= kSlot) {
+                void* p = g_base + (size_t)s.id * kSlot + s.cur;
+                s.cur += kNode;
+                s.live++;
+                g_served.fetch_add(1, std::memory_order_relaxed);
+                return p;
+            }
+            std::fprintf(stderr, "mono_alloc: arena slot exhausted, falling back to malloc (tie order no longer pinned)\n");
         }
     }
     void* p = std::malloc(n ? n : 1);
@@ -67,9 +85,10 @@ void* alloc(size_t n) {
 void dealloc(void* p) {
     if (!p) return;
     if (in_arena(p)) {
-        /* all list nodes of a DistributeOctTree call die together when its std::list goes out of scope; once none is
-         * alive (in any thread) the arena starts over */
-        if (g_live.fetch_sub(1, std::memory_order_acq_rel) == 1) g_cur.store(0, std::memory_order_release);
+        /* the list nodes of one DistributeOctTree call are created and destroyed by the same thread and die together when
+         * its std::list goes out of scope; once none of this thread's nodes is alive its region starts over */
+        Slot& s = t_slot;
+        if (s.id >= 0 && (size_t)((char*)p - g_base) / kSlot == (size_t)s.id && --s.live == 0) s.cur = 0;
         return;
     }
     std::free(p);
