@@ -268,6 +268,15 @@ int orb_stereo_match(orb_ctx* ctx_left, orb_ctx* ctx_right, const orb_kp* kps_l,
                      const orb_kp* kps_r, const uint8_t* desc_r, int nr, float bf, float b, float* u_right,
                      float* depth, int* nmatches);
 
+/* The same for npairs stereo pairs at once, device-resident (per-pair batches shard across GPUs like frames):
+ * pair p = frame p of the last orb_extract_batch_device call of each context (their pyramids are still in the arenas);
+ * d_kps_* / d_desc_* / d_n_* are exactly the outputs of those calls ([npairs][cap], [npairs][cap][32], [npairs]).  Outputs
+ * d_u_right / d_depth [npairs][cap] (-1 = no match, also in the unused slots), d_nmatches [npairs].  Asynchronous on the LEFT
+ * context's stream (the right context's stream is joined by an event): no host copy, no host synchronisation. */
+int orb_stereo_match_batch_device(orb_ctx* ctx_left, orb_ctx* ctx_right, int npairs, const orb_kp* d_kps_l, const uint8_t* d_desc_l,
+                                  const int32_t* d_n_l, const orb_kp* d_kps_r, const uint8_t* d_desc_r, const int32_t* d_n_r, int cap,
+                                  float bf, float b, float* d_u_right, float* d_depth, int32_t* d_nmatches);
+
 /* ---- bag of words: ORBVocabulary = DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB> ------------------------- */
 /* (orb_slam2/include/ORBVocabulary.h:31; Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h)                                */
 typedef struct orb_voc orb_voc;

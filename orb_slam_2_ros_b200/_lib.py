@@ -38,7 +38,7 @@ EXPORTS = [
     "orb_launch_count", "orb_profile_enable", "orb_profile_read", "orb_level_dims", "orb_pyramid_level", "orb_debug_blurred", "orb_debug_raw_corners",
     "orb_debug_tie_counts", "orb_hamming_top2", "orb_hamming_top2_csr", "orb_db_create", "orb_db_destroy", "orb_db_add", "orb_db_add_device",
     "orb_db_size", "orb_db_set_stream", "orb_db_query_top2", "orb_db_query_top2_device", "orb_db_launch_count", "orb_db_profile_enable", "orb_db_profile_read",
-    "orb_top2_merge", "orb_top2_merge_device", "orb_search_by_projection", "orb_match_bruteforce", "orb_stereo_match",
+    "orb_top2_merge", "orb_top2_merge_device", "orb_search_by_projection", "orb_match_bruteforce", "orb_stereo_match", "orb_stereo_match_batch_device",
     "orb_search_by_bow", "orb_search_for_triangulation", "orb_search_by_sim3", "orb_distinctive_descriptors", "orb_fuse_search", "orb_voc_create", "orb_voc_load_text", "orb_voc_destroy", "orb_voc_info", "orb_bow_transform_features",
     "orb_bow_transform_features_device", "orb_bow_transform", "orb_bow_transform_device",
     "orb_mat_record_bytes", "orb_mat_record_encode", "orb_mat_record_decode", "orb_keypoint_records_encode",
@@ -100,6 +100,7 @@ def lib():
     L.orb_search_by_projection.argtypes = [i32, C.POINTER(SearchParams), vp, vp, vp, i32, vp, i32] + [vp] * 13 + [C.POINTER(i32)]
     L.orb_match_bruteforce.argtypes = [i32, vp, vp, i32, vp, vp, i32, i32, f32, i32, vp, C.POINTER(i32)]
     L.orb_stereo_match.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, f32, f32, vp, vp, C.POINTER(i32)]
+    L.orb_stereo_match_batch_device.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp, i32, f32, f32, vp, vp, vp]
     pi32 = C.POINTER(i32)
     L.orb_search_for_triangulation.argtypes = [i32, vp, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, i32, vp, f32, f32, vp, vp, i32, i32, i32, vp, pi32]
     L.orb_search_by_sim3.argtypes = [i32, vp, vp, i32, vp, vp, vp, i32, vp] + [vp] * 12 + [i32, vp, pi32]

@@ -29,9 +29,13 @@ __device__ __forceinline__ int dist256s(const uint4* a, const uint4* b) {
 // per right keypoint, once: the row band [minr, maxr] it is listed under (Frame.cc:519-529), its x and octave, packed in 16 bytes
 // (every left keypoint's warp scans all of them: without this each of the N x Nr visits redid the ceil / floor arithmetic
 // on a 28-byte KeyPoint)
+// Batched form: blockIdx.y = stereo pair; n_r (when not NULL) holds the per-pair keypoint counts on the device and the
+// per-pair arrays are `cap` entries apart.
 __global__ void __launch_bounds__(256)
-stereo_rows_kernel(const orb_kp* __restrict__ kpsR, int Nr, const StereoScales sc, uint4* __restrict__ rows) {
+stereo_rows_kernel(const orb_kp* __restrict__ kpsR, int Nr, const StereoScales sc, uint4* __restrict__ rows, const int* __restrict__ n_r, int cap) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int pair = blockIdx.y;
+    if (n_r) { Nr = min(n_r[pair], cap); kpsR += (size_t)pair * cap; rows += (size_t)pair * cap; }
     if (i >= Nr) return;
     const orb_kp kpR = kpsR[i];
     const float r = __fmul_rn(2.0f, sc.scale[kpR.octave]);
@@ -44,10 +48,20 @@ stereo_match_kernel(const uint8_t* __restrict__ pyrL, const uint8_t* __restrict_
                     const uint8_t* __restrict__ descL, int N, const orb_kp* __restrict__ kpsR,
                     const uint8_t* __restrict__ descR, int Nr, float mbf, float mb, const StereoScales sc,
                     float* __restrict__ uRight, float* __restrict__ depth, int* __restrict__ sad,
-                    const uint4* __restrict__ rowsR, const __grid_constant__ Geometry g) {
+                    const uint4* __restrict__ rowsR, const __grid_constant__ Geometry g, const int* __restrict__ n_l,
+                    const int* __restrict__ n_r, int cap) {
     const int lane = threadIdx.x & 31;
     const int iL = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (iL >= N) return;
+    const int pair = blockIdx.y;      // batched form (n_l != NULL): frame `pair` of both pyramid arenas, per-pair arrays `cap` apart
+    if (n_l) {
+        N = min(n_l[pair], cap); Nr = min(n_r[pair], cap);
+        const size_t o = (size_t)pair * cap;
+        kpsL += o; descL += o * 32; kpsR += o; descR += o * 32; uRight += o; depth += o; sad += o; rowsR += o;
+    }
+    if (iL >= N) {
+        if (n_l && iL < cap && lane == 0) { uRight[iL] = -1.0f; depth[iL] = -1.0f; sad[iL] = -1; }   // unused slots of the pair's row
+        return;
+    }
     if (lane == 0) { uRight[iL] = -1.0f; depth[iL] = -1.0f; sad[iL] = -1; }
     const orb_kp kpL = kpsL[iL];
     const int levelL = kpL.octave;
@@ -89,8 +103,8 @@ stereo_match_kernel(const uint8_t* __restrict__ pyrL, const uint8_t* __restrict_
     const float endu = __fadd_rn(__fadd_rn(__fadd_rn(scaleduR0, (float)Lh), (float)w), 1.0f);
     if (iniu < 0 || endu >= (float)G.w) return;
     const int y0 = (int)(scaledvL - w), xl0 = (int)(scaleduL - w), xr0 = (int)(scaleduR0 - w);
-    const uint8_t* PL = pyrL + G.base + G.ioff;  // frame 0 interior
-    const uint8_t* PR = pyrR + G.base + G.ioff;
+    const uint8_t* PL = pyrL + G.base + (long long)pair * G.frame_stride + G.ioff;  // interior of frame `pair` (0 in the single-pair form)
+    const uint8_t* PR = pyrR + G.base + (long long)pair * G.frame_stride + G.ioff;
     const int cL = PL[(long long)(y0 + w) * G.pitch + xl0 + w];
     // each lane owns up to 4 of the 121 patch pixels
     int il[4], py[4], px[4];
@@ -139,8 +153,14 @@ stereo_match_kernel(const uint8_t* __restrict__ pyrL, const uint8_t* __restrict_
 
 // median cut (Frame.cc:662-675): thDist = 1.5f*1.4f*median of the kept SADs, drop everything >= thDist
 __global__ void __launch_bounds__(1024)
-stereo_median_kernel(int N, float* uRight, float* depth, const int* __restrict__ sad, int* nkept_out) {
+stereo_median_kernel(int N, float* uRight, float* depth, const int* __restrict__ sad, int* nkept_out, const int* __restrict__ n_l, int cap) {
     __shared__ int s_count, s_median, s_removed;
+    if (n_l) {   // batched form: one CTA per pair
+        const int pair = blockIdx.x;
+        N = min(n_l[pair], cap);
+        const size_t o = (size_t)pair * cap;
+        uRight += o; depth += o; sad += o; nkept_out += pair;
+    }
     if (threadIdx.x == 0) { s_count = 0; s_median = -1; s_removed = 0; }
     __syncthreads();
     int local = 0;
@@ -244,11 +264,11 @@ extern "C" int orb_stereo_match(orb_ctx* cl, orb_ctx* cr, const orb_kp* kps_l, c
     {
         StereoScales sc;
         for (int l = 0; l < ORB_MAX_LEVELS; ++l) { sc.scale[l] = l < cl->nlevels ? cl->scale[l] : 1.f; sc.inv_scale[l] = l < cl->nlevels ? cl->inv_scale[l] : 1.f; }
-        stereo_rows_kernel<<<(nr + 255) / 256, 256, 0, st>>>((const orb_kp*)(D + o_kr), nr, sc, (uint4*)(D + o_rows));
+        stereo_rows_kernel<<<(nr + 255) / 256, 256, 0, st>>>((const orb_kp*)(D + o_kr), nr, sc, (uint4*)(D + o_rows), nullptr, 0);
         stereo_match_kernel<<<(nl + 7) / 8, 256, 0, st>>>(cl->d_pyr, cr->d_pyr, (const orb_kp*)(D + o_kl), D + o_dl, nl, (const orb_kp*)(D + o_kr),
                                                          D + o_dr, nr, bf, b, sc, (float*)(D + o_ur), (float*)(D + o_dep), (int*)(D + o_sad),
-                                                         (const uint4*)(D + o_rows), cl->g);
-        stereo_median_kernel<<<1, 1024, sizeof(int) * (size_t)nl, st>>>(nl, (float*)(D + o_ur), (float*)(D + o_dep), (const int*)(D + o_sad), (int*)(D + o_nk));
+                                                         (const uint4*)(D + o_rows), cl->g, nullptr, nullptr, 0);
+        stereo_median_kernel<<<1, 1024, sizeof(int) * (size_t)nl, st>>>(nl, (float*)(D + o_ur), (float*)(D + o_dep), (const int*)(D + o_sad), (int*)(D + o_nk), nullptr, 0);
         cl->launches += 3;
     }
     ORB_CUDA(cudaGetLastError());
@@ -260,3 +280,52 @@ extern "C" int orb_stereo_match(orb_ctx* cl, orb_ctx* cr, const orb_kp* kps_l, c
     return ORB_OK;
 }
 
+
+// Batched, device-resident form: pair p = frame p of both contexts' pyramid arenas (the last orb_extract_batch_device call of
+// each), keypoints / descriptors / counts exactly as that call left them on the device.  Asynchronous on the LEFT context's
+// stream; the right context's stream is joined with an event.  No host copy, no host synchronisation.
+extern "C" int orb_stereo_match_batch_device(orb_ctx* cl, orb_ctx* cr, int npairs, const orb_kp* d_kps_l, const uint8_t* d_desc_l,
+                                             const int32_t* d_n_l, const orb_kp* d_kps_r, const uint8_t* d_desc_r, const int32_t* d_n_r,
+                                             int cap, float bf, float b, float* d_u_right, float* d_depth, int32_t* d_nmatches) {
+    if (!cl || !cr || npairs < 0 || cap <= 0 || !d_kps_l || !d_desc_l || !d_n_l || !d_kps_r || !d_desc_r || !d_n_r || !d_u_right || !d_depth ||
+        !d_nmatches)
+        return ORB_ERR_INVALID;
+    if (npairs == 0) return ORB_OK;
+    if (!cl->have_geom || !cr->have_geom || cl->last_frames < npairs || cr->last_frames < npairs) {
+        orb_set_error("orb_stereo_match_batch_device: both contexts must hold %d extracted frames", npairs);
+        return ORB_ERR_INVALID;
+    }
+    if (cl->device != cr->device || cl->g.w != cr->g.w || cl->g.h != cr->g.h || cl->nlevels != cr->nlevels || cl->max_batch != cr->max_batch) {
+        orb_set_error("orb_stereo_match_batch_device: left/right contexts differ in device, image size, levels or max_batch");
+        return ORB_ERR_INVALID;
+    }
+    if (cap > 10000) { orb_set_error("orb_stereo_match_batch_device: more than 10000 keypoints per frame"); return ORB_ERR_CAPACITY; }
+    ORB_CUDA(cudaSetDevice(cl->device));
+    cudaStream_t st = cl->stream;
+    if (cr->stream != st) {   // the right pyramids / keypoints must be complete before the left stream reads them
+        cudaEvent_t ev;
+        ORB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        ORB_CUDA(cudaEventRecord(ev, cr->stream));
+        ORB_CUDA(cudaStreamWaitEvent(st, ev, 0));
+        ORB_CUDA(cudaEventDestroy(ev));
+    }
+    const size_t per = (size_t)npairs * cap;
+    const size_t need = per * (sizeof(int) + sizeof(uint4)) + 512;
+    if (cl->d_scratch_cap < need) {
+        ORB_CUDA(cudaStreamSynchronize(st));
+        cudaFree(cl->d_scratch); cl->d_scratch = nullptr; cl->d_scratch_cap = 0;
+        ORB_CUDA(cudaMalloc(&cl->d_scratch, need));
+        cl->d_scratch_cap = need;
+    }
+    uint4* d_rows = reinterpret_cast<uint4*>(cl->d_scratch);
+    int* d_sad = reinterpret_cast<int*>(cl->d_scratch + ((per * sizeof(uint4) + 255) & ~(size_t)255));
+    StereoScales sc;
+    for (int l = 0; l < ORB_MAX_LEVELS; ++l) { sc.scale[l] = l < cl->nlevels ? cl->scale[l] : 1.f; sc.inv_scale[l] = l < cl->nlevels ? cl->inv_scale[l] : 1.f; }
+    stereo_rows_kernel<<<dim3((cap + 255) / 256, npairs), 256, 0, st>>>(d_kps_r, 0, sc, d_rows, d_n_r, cap);
+    stereo_match_kernel<<<dim3((cap + 7) / 8, npairs), 256, 0, st>>>(cl->d_pyr, cr->d_pyr, d_kps_l, d_desc_l, 0, d_kps_r, d_desc_r, 0, bf, b, sc, d_u_right,
+                                                                    d_depth, d_sad, d_rows, cl->g, d_n_l, d_n_r, cap);
+    stereo_median_kernel<<<npairs, 1024, sizeof(int) * (size_t)cap, st>>>(0, d_u_right, d_depth, d_sad, d_nmatches, d_n_l, cap);
+    cl->launches += 3;
+    ORB_CUDA(cudaGetLastError());
+    return ORB_OK;
+}
