@@ -201,12 +201,37 @@ int orb_search_by_projection(int device, const orb_search_params* prm, const orb
                              const float* q_er_max, const float* q_angle, const uint8_t* q_valid,
                              const uint8_t* q_obs, int32_t* match_of_query, int32_t* target_query, int* nmatches);
 
+/* The same search for npairs (target frame, query set) pairs at once, everything device-resident and asynchronous on
+ * cuda_stream (per-pair matching batches shard across GPUs like frames; BASELINE config 2).  The target
+ * arrays are what orb_extract_batch_device left on the device ([npairs][cap_n] keypoints, [npairs][cap_n][32] descriptors,
+ * [npairs] counts), the query arrays are [npairs][cap_q]; a pointer that may be NULL in orb_search_by_projection may be NULL
+ * here.  Modes TRACK_LAST and LOCAL_POINTS.  d_nmatches[p] = -1 when pair p's candidate arena (160 candidates per query on
+ * average) overflowed: re-run that pair through orb_search_by_projection.  One stream per calling thread. */
+typedef struct {
+    const orb_kp* d_kps_un; const uint8_t* d_desc; const float* d_u_right; const int32_t* d_n; int32_t cap_n;
+    uint8_t* d_taken;                       /* [npairs][cap_n] in/out */
+    const int32_t* d_nq; int32_t cap_q;
+    const float *d_q_u, *d_q_v, *d_q_radius; const int32_t *d_q_min_level, *d_q_max_level; const uint8_t* d_q_desc;
+    const float *d_q_ur, *d_q_er_max, *d_q_angle; const uint8_t *d_q_valid, *d_q_obs;
+    int32_t* d_match_of_query;              /* [npairs][cap_q] */
+    int32_t* d_target_query;                /* [npairs][cap_n] */
+    int32_t* d_nmatches;                    /* [npairs] */
+} orb_search_batch;
+int orb_search_by_projection_batch_device(int device, const orb_search_params* prm, int npairs, const orb_search_batch* batch, void* cuda_stream);
+
 /* SearchByBoW inner loop (ORBmatcher.cc:196-252) over one node holding all keypoints of both frames:
  * queries = frame 1 in order, skip already-matched targets, best <= th_dist and best < ratio*second,
  * rotation histogram + three-maxima filter.  match12[n1] = index in frame 2 or -1. */
 int orb_match_bruteforce(int device, const uint8_t* desc1, const float* angle1, int n1, const uint8_t* desc2,
                          const float* angle2, int n2, int th_dist, float nn_ratio, int check_orientation,
                          int32_t* match12, int* nmatches);
+
+/* orb_match_bruteforce for npairs frame pairs at once, device-resident (the outputs of two orb_extract_batch_device calls:
+ * keypoints carry the angles), asynchronous on cuda_stream.  d_match12 [npairs][cap1] (-1 in the unused slots), d_nmatches
+ * [npairs]. */
+int orb_match_bruteforce_batch_device(int device, int npairs, const orb_kp* d_kps1, const uint8_t* d_desc1, const int32_t* d_n1, int cap1,
+                                      const orb_kp* d_kps2, const uint8_t* d_desc2, const int32_t* d_n2, int cap2, int th_dist, float nn_ratio,
+                                      int check_orientation, int32_t* d_match12, int32_t* d_nmatches, void* cuda_stream);
 
 /* SearchByBoW over two FeatureVectors (ORBmatcher.cc:160-289 KeyFrame -> Frame: strict = 0, valid2 = NULL;
  * ORBmatcher.cc:524-657 KeyFrame -> KeyFrame: strict = 1).  Feature vectors in the CSR form orb_bow_transform returns

@@ -25,6 +25,15 @@ class SearchParams(C.Structure):
                 ("min_x", C.c_float), ("min_y", C.c_float), ("max_x", C.c_float), ("max_y", C.c_float)]
 
 
+class SearchBatch(C.Structure):
+    """orb_search_batch (include/orb_b200.h): device pointers of a batch of (target frame, query set) pairs"""
+    _fields_ = [("d_kps_un", C.c_void_p), ("d_desc", C.c_void_p), ("d_u_right", C.c_void_p), ("d_n", C.c_void_p), ("cap_n", C.c_int32),
+                ("d_taken", C.c_void_p), ("d_nq", C.c_void_p), ("cap_q", C.c_int32),
+                ("d_q_u", C.c_void_p), ("d_q_v", C.c_void_p), ("d_q_radius", C.c_void_p), ("d_q_min_level", C.c_void_p), ("d_q_max_level", C.c_void_p),
+                ("d_q_desc", C.c_void_p), ("d_q_ur", C.c_void_p), ("d_q_er_max", C.c_void_p), ("d_q_angle", C.c_void_p), ("d_q_valid", C.c_void_p),
+                ("d_q_obs", C.c_void_p), ("d_match_of_query", C.c_void_p), ("d_target_query", C.c_void_p), ("d_nmatches", C.c_void_p)]
+
+
 class OrbError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("liborb_b200 error %d: %s" % (code, msg))
@@ -38,7 +47,7 @@ EXPORTS = [
     "orb_launch_count", "orb_profile_enable", "orb_profile_read", "orb_level_dims", "orb_pyramid_level", "orb_debug_blurred", "orb_debug_raw_corners",
     "orb_debug_tie_counts", "orb_hamming_top2", "orb_hamming_top2_csr", "orb_db_create", "orb_db_destroy", "orb_db_add", "orb_db_add_device",
     "orb_db_size", "orb_db_set_stream", "orb_db_query_top2", "orb_db_query_top2_device", "orb_db_launch_count", "orb_db_profile_enable", "orb_db_profile_read",
-    "orb_top2_merge", "orb_top2_merge_device", "orb_search_by_projection", "orb_match_bruteforce", "orb_stereo_match", "orb_stereo_match_batch_device",
+    "orb_top2_merge", "orb_top2_merge_device", "orb_search_by_projection", "orb_match_bruteforce", "orb_stereo_match", "orb_stereo_match_batch_device", "orb_search_by_projection_batch_device", "orb_match_bruteforce_batch_device",
     "orb_search_by_bow", "orb_search_for_triangulation", "orb_search_by_sim3", "orb_distinctive_descriptors", "orb_fuse_search", "orb_voc_create", "orb_voc_load_text", "orb_voc_destroy", "orb_voc_info", "orb_bow_transform_features",
     "orb_bow_transform_features_device", "orb_bow_transform", "orb_bow_transform_device",
     "orb_mat_record_bytes", "orb_mat_record_encode", "orb_mat_record_decode", "orb_keypoint_records_encode",
@@ -100,6 +109,8 @@ def lib():
     L.orb_search_by_projection.argtypes = [i32, C.POINTER(SearchParams), vp, vp, vp, i32, vp, i32] + [vp] * 13 + [C.POINTER(i32)]
     L.orb_match_bruteforce.argtypes = [i32, vp, vp, i32, vp, vp, i32, i32, f32, i32, vp, C.POINTER(i32)]
     L.orb_stereo_match.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, f32, f32, vp, vp, C.POINTER(i32)]
+    L.orb_search_by_projection_batch_device.argtypes = [i32, C.POINTER(SearchParams), i32, C.POINTER(SearchBatch), vp]
+    L.orb_match_bruteforce_batch_device.argtypes = [i32, i32, vp, vp, vp, i32, vp, vp, vp, i32, i32, f32, i32, vp, vp, vp]
     L.orb_stereo_match_batch_device.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp, i32, f32, f32, vp, vp, vp]
     pi32 = C.POINTER(i32)
     L.orb_search_for_triangulation.argtypes = [i32, vp, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, i32, vp, f32, f32, vp, vp, i32, i32, i32, vp, pi32]

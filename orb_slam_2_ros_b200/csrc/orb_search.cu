@@ -32,9 +32,8 @@ __device__ __forceinline__ int dist256(const uint4* a, const uint4* b) {
 
 // ---- grid build: keys (cell << 16 | index) bitonic-sorted in shared memory => per cell ascending index,
 //      which is the insertion order of mGrid[x][y].push_back(i) -----------------------------------------
-__global__ void __launch_bounds__(1024)
-grid_build_kernel(const orb_kp* __restrict__ kps, int n, int npad, float min_x, float min_y, float inv_w, float inv_h,
-                  unsigned* __restrict__ items /*[npad]*/, int* __restrict__ cell_start /*[GRID_COLS*GRID_ROWS+1]*/) {
+__device__ __forceinline__ void grid_build_body(const orb_kp* __restrict__ kps, int n, int npad, float min_x, float min_y, float inv_w, float inv_h,
+                                                unsigned* __restrict__ items /*[npad]*/, int* __restrict__ cell_start /*[GRID_COLS*GRID_ROWS+1]*/) {
     extern __shared__ unsigned skey[];
     for (int i = threadIdx.x; i < npad; i += blockDim.x) {
         unsigned key = 0xFFFFFFFFu;
@@ -113,8 +112,7 @@ __device__ __forceinline__ unsigned warp_topk_extract(unsigned (&best)[SR_K], in
 
 // ---- one warp per query: GetFeaturesInArea in reference order + distances -----------------------------------
 // pass 0 counts, pass 1 (after the warp reserved its segment) writes (index, distance) in candidate order.
-__global__ void __launch_bounds__(256)
-window_candidates_kernel(const SearchArgs a) {
+__device__ __forceinline__ void window_candidates_body(const SearchArgs& a) {
     const int lane = threadIdx.x & 31;
     const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (qi >= a.nq) return;
@@ -240,10 +238,9 @@ struct SrStage {
     uint8_t flags[SR_CH];             // bit 0: list truncated (all K entries valid), bit 1: query blocks its target
 };
 
-__global__ void __launch_bounds__(SR_THREADS, 1)
-window_resolve_kernel(const SearchArgs a, int mode, int th_dist, float nn_ratio, int check_ori, uint8_t* taken_g,
-                      int* match_of_query, int* target_query, signed char* match_bin, int* assigned, int* nmatches_out,
-                      int* overflow, int smem_bytes) {
+__device__ __forceinline__ void window_resolve_body(const SearchArgs& a, int mode, int th_dist, float nn_ratio, int check_ori, uint8_t* taken_g,
+                                                    int* match_of_query, int* target_query, signed char* match_bin, int* assigned, int* nmatches_out,
+                                                    int* overflow, int smem_bytes) {
     extern __shared__ __align__(16) uint8_t sr_smem[];
     SrStage& S = *reinterpret_cast<SrStage*>(sr_smem);
     const bool init = (mode == ORB_MODE_INITIALIZATION);
@@ -650,9 +647,8 @@ window_resolve_kernel(const SearchArgs a, int mode, int th_dist, float nn_ratio,
 #define BF_K SR_K
 
 // one warp per query row: distances to every target (stored, u16) + sorted top-K packed keys (dist<<16 | j)
-__global__ void __launch_bounds__(256)
-bf_rows_kernel(const uint8_t* __restrict__ d1, int n1, const uint8_t* __restrict__ d2, int n2,
-               unsigned short* __restrict__ D, int dpitch, unsigned* __restrict__ topk) {
+__device__ __forceinline__ void bf_rows_body(const uint8_t* __restrict__ d1, int n1, const uint8_t* __restrict__ d2, int n2,
+                                             unsigned short* __restrict__ D, int dpitch, unsigned* __restrict__ topk) {
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= n1) return;
@@ -672,7 +668,7 @@ bf_rows_kernel(const uint8_t* __restrict__ d1, int n1, const uint8_t* __restrict
         const int d = dist256(dq, reinterpret_cast<const uint4*>(d2 + (size_t)j * 32));
         D[(size_t)i * dpitch + j] = (unsigned short)d;
         const unsigned key = ((unsigned)d << 16) | (unsigned)j;
-        if (key < best[BF_K - 1]) insert(key);
+        if (d < 256 && key < best[BF_K - 1]) insert(key);   // a distance of 256 never becomes best or second best (ORBmatcher.cc:217-226: dist < 256 is false)
     }
     const unsigned mine = warp_topk_extract(best, lane);
     if (lane < BF_K) topk[(size_t)i * BF_K + lane] = mine;
@@ -687,11 +683,10 @@ bf_rows_kernel(const uint8_t* __restrict__ d1, int n1, const uint8_t* __restrict
 // microseconds (the sequential walk of 1000 queries took 330 us).  The optimistic top-K list answers a query when two of
 // its entries are still visible; otherwise the query's warp scans its whole distance row cooperatively.
 template <bool SMEM>
-__global__ void __launch_bounds__(SR_THREADS, 1)
-bf_resolve_kernel(const unsigned short* __restrict__ D, int dpitch, const unsigned* __restrict__ topk, int n1, int n2,
-                  const float* __restrict__ angle1, const float* __restrict__ angle2, int th_dist, float nn_ratio,
-                  int check_ori, int* owner /*[n2]*/, int* owner_scratch /*[n2], !SMEM only*/, int* match12, signed char* match_bin,
-                  int* nmatches_out) {
+__device__ __forceinline__ void bf_resolve_body(const unsigned short* __restrict__ D, int dpitch, const unsigned* __restrict__ topk, int n1, int n2,
+                                                const float* __restrict__ angle1, const float* __restrict__ angle2, int th_dist, float nn_ratio,
+                                                int check_ori, int* owner /*[n2]*/, int* owner_scratch /*[n2], !SMEM only*/, int* match12,
+                                                signed char* match_bin, int* nmatches_out) {
     extern __shared__ __align__(16) uint8_t sr_smem[];
     int* own_prev = SMEM ? reinterpret_cast<int*>(sr_smem) : owner;
     int* own_new = SMEM ? reinterpret_cast<int*>(sr_smem) + n2 : owner_scratch;
@@ -720,7 +715,7 @@ bf_resolve_kernel(const unsigned short* __restrict__ D, int dpitch, const unsign
                     if (key[k] == 0xFFFFFFFFu || nfree >= 2) break;
                     const int id = (int)(key[k] & 0xFFFFu);
                     if ((SMEM ? own_prev[id] : __ldcg(own_prev + id)) < i) continue;   // taken by an earlier query
-                    if (nfree == 0) { best1 = (int)min(key[k] >> 16, 255u); bestIdx = id; } else best2 = (int)min(key[k] >> 16, 255u);
+                    if (nfree == 0) { best1 = (int)(key[k] >> 16); bestIdx = id; } else best2 = (int)(key[k] >> 16);
                     ++nfree;
                 }
                 fallback = nfree < 2 && key[SR_K - 1] != 0xFFFFFFFFu;   // list truncated and too many of its entries taken
@@ -740,7 +735,9 @@ bf_resolve_kernel(const unsigned short* __restrict__ D, int dpitch, const unsign
                     for (int h = 0; h < 8; ++h) {
                         const int jj = v * 8 + h;
                         if (jj >= n2 || (SMEM ? own_prev[jj] : __ldcg(own_prev + jj)) < fi) continue;
-                        const unsigned k = (((w[h >> 1] >> (16 * (h & 1))) & 0xFFFFu) << 16) | (unsigned)jj;
+                        const unsigned dd = (w[h >> 1] >> (16 * (h & 1))) & 0xFFFFu;
+                        if (dd >= 256u) continue;                               // invisible to the reference's strict '<' updates
+                        const unsigned k = (dd << 16) | (unsigned)jj;
                         a2 = min(a2, max(k, a1));
                         a1 = min(a1, k);
                     }
@@ -807,6 +804,104 @@ bf_resolve_kernel(const unsigned short* __restrict__ D, int dpitch, const unsign
         nmatches -= s_nmatches;
     }
     if (threadIdx.x == 0) *nmatches_out = nmatches;
+}
+
+// ---- launch forms of the bodies above: one pair (arguments in the kernel parameters) and a batch of pairs -------------
+__global__ void __launch_bounds__(1024)
+grid_build_kernel(const orb_kp* __restrict__ kps, int n, int npad, float min_x, float min_y, float inv_w, float inv_h,
+                  unsigned* __restrict__ items, int* __restrict__ cell_start) {
+    grid_build_body(kps, n, npad, min_x, min_y, inv_w, inv_h, items, cell_start);
+}
+__global__ void __launch_bounds__(256) window_candidates_kernel(const SearchArgs a) { window_candidates_body(a); }
+__global__ void __launch_bounds__(SR_THREADS, 1)
+window_resolve_kernel(const SearchArgs a, int mode, int th_dist, float nn_ratio, int check_ori, uint8_t* taken_g, int* match_of_query,
+                      int* target_query, signed char* match_bin, int* assigned, int* nmatches_out, int* overflow, int smem_bytes) {
+    window_resolve_body(a, mode, th_dist, nn_ratio, check_ori, taken_g, match_of_query, target_query, match_bin, assigned, nmatches_out, overflow,
+                        smem_bytes);
+}
+__global__ void __launch_bounds__(256)
+bf_rows_kernel(const uint8_t* __restrict__ d1, int n1, const uint8_t* __restrict__ d2, int n2, unsigned short* __restrict__ D, int dpitch,
+               unsigned* __restrict__ topk) {
+    bf_rows_body(d1, n1, d2, n2, D, dpitch, topk);
+}
+template <bool SMEM>
+__global__ void __launch_bounds__(SR_THREADS, 1)
+bf_resolve_kernel(const unsigned short* __restrict__ D, int dpitch, const unsigned* __restrict__ topk, int n1, int n2,
+                  const float* __restrict__ angle1, const float* __restrict__ angle2, int th_dist, float nn_ratio, int check_ori, int* owner,
+                  int* owner_scratch, int* match12, signed char* match_bin, int* nmatches_out) {
+    bf_resolve_body<SMEM>(D, dpitch, topk, n1, n2, angle1, angle2, th_dist, nn_ratio, check_ori, owner, owner_scratch, match12, match_bin, nmatches_out);
+}
+
+// Batched forms (per-pair matching shards like frames): blockIdx.y (one-CTA kernels: blockIdx.x) = pair.  The
+// host builds one job per pair with the pair's device pointers; the keypoint / query counts stay on the device (they are
+// outputs of the extractor) and are read here.
+struct WindowJob {
+    SearchArgs a;                       // a.n / a.nq = capacities; the live counts come from n_ptr / nq_ptr
+    const int *n_ptr, *nq_ptr;
+    uint8_t* taken; int* moq; int* tq; signed char* bin; int* asg; int* scal;   // scal: [0] candidate total, [1] nmatches, [2] overflow
+};
+__device__ __forceinline__ SearchArgs job_args(const WindowJob& J) {
+    SearchArgs a = J.a;
+    a.n = min(*J.n_ptr, J.a.n);
+    a.nq = min(*J.nq_ptr, J.a.nq);
+    return a;
+}
+__device__ __forceinline__ int pow2_at_least(int n) { int p = 32; while (p < n) p <<= 1; return p; }
+__global__ void __launch_bounds__(1024) grid_build_batch_kernel(const WindowJob* __restrict__ jobs) {
+    const WindowJob& J = jobs[blockIdx.x];
+    const SearchArgs a = job_args(J);
+    if (threadIdx.x < 4) J.scal[threadIdx.x] = 0;
+    grid_build_body(a.kps, a.n, pow2_at_least(a.n), a.min_x, a.min_y, a.inv_w, a.inv_h, const_cast<unsigned*>(a.items), const_cast<int*>(a.cell_start));
+}
+__global__ void __launch_bounds__(256) window_candidates_batch_kernel(const WindowJob* __restrict__ jobs) {
+    const SearchArgs a = job_args(jobs[blockIdx.y]);
+    window_candidates_body(a);
+}
+__global__ void __launch_bounds__(SR_THREADS, 1)
+window_resolve_batch_kernel(const WindowJob* __restrict__ jobs, int mode, int th_dist, float nn_ratio, int check_ori, int smem_bytes) {
+    const WindowJob& J = jobs[blockIdx.x];
+    const SearchArgs a = job_args(J);
+    // slots beyond the live counts read as "no match"
+    for (int i = a.nq + threadIdx.x; i < J.a.nq; i += SR_THREADS) J.moq[i] = -1;
+    for (int i = a.n + threadIdx.x; i < J.a.n; i += SR_THREADS) J.tq[i] = -1;
+    if (a.n == 0 || a.nq == 0) {
+        for (int i = threadIdx.x; i < a.nq; i += SR_THREADS) J.moq[i] = -1;
+        for (int i = threadIdx.x; i < a.n; i += SR_THREADS) J.tq[i] = -1;
+        if (threadIdx.x == 0) { J.scal[1] = 0; J.scal[2] = 0; }
+        return;
+    }
+    window_resolve_body(a, mode, th_dist, nn_ratio, check_ori, J.taken, J.moq, J.tq, J.bin, J.asg, J.scal + 1, J.scal + 2, smem_bytes);
+}
+
+__global__ void search_batch_finish_kernel(const WindowJob* __restrict__ jobs, int npairs, int* __restrict__ nmatches) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < npairs) nmatches[p] = jobs[p].scal[2] > 0 ? -1 : jobs[p].scal[1];
+}
+
+struct BfJob {
+    const uint8_t *d1, *d2; const orb_kp *k1, *k2; const int *n1_ptr, *n2_ptr; int cap1, cap2;
+    unsigned short* D; int dpitch; unsigned* topk; float *a1, *a2; int *owner, *owner2, *m12; signed char* bin; int* nm;
+};
+__global__ void __launch_bounds__(256) bf_rows_batch_kernel(const BfJob* __restrict__ jobs) {
+    const BfJob& J = jobs[blockIdx.y];
+    const int n1 = min(*J.n1_ptr, J.cap1), n2 = min(*J.n2_ptr, J.cap2);
+    // dense angle arrays for the rotation histogram (the extractor's keypoints are 28-byte records)
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n1) J.a1[t] = J.k1[t].angle;
+    for (int j = t; j < n2; j += gridDim.x * blockDim.x) J.a2[j] = J.k2[j].angle;
+    bf_rows_body(J.d1, n1, J.d2, n2, J.D, J.dpitch, J.topk);
+}
+__global__ void __launch_bounds__(SR_THREADS, 1)
+bf_resolve_batch_kernel(const BfJob* __restrict__ jobs, int th_dist, float nn_ratio, int check_ori) {
+    const BfJob& J = jobs[blockIdx.x];
+    const int n1 = min(*J.n1_ptr, J.cap1), n2 = min(*J.n2_ptr, J.cap2);
+    for (int i = n1 + threadIdx.x; i < J.cap1; i += SR_THREADS) J.m12[i] = -1;
+    if (n1 == 0 || n2 == 0) {
+        for (int i = threadIdx.x; i < n1; i += SR_THREADS) J.m12[i] = -1;
+        if (threadIdx.x == 0) *J.nm = 0;
+        return;
+    }
+    bf_resolve_body<false>(J.D, J.dpitch, J.topk, n1, n2, J.a1, J.a2, th_dist, nn_ratio, check_ori, J.owner, J.owner2, J.m12, J.bin, J.nm);
 }
 
 // ---- best / second-best over explicit candidate lists (CSR): one warp per query ------------------------------
@@ -1594,4 +1689,116 @@ int orb_fuse_search(int device, const orb_kp* kps_un, const uint8_t* desc, const
     return ORB_OK;
 }
 
+
+/* ---- batched, device-resident pair matching (BASELINE config 2) ------------------------------------ */
+int orb_match_bruteforce_batch_device(int device, int npairs, const orb_kp* d_kps1, const uint8_t* d_desc1, const int32_t* d_n1, int cap1,
+                                      const orb_kp* d_kps2, const uint8_t* d_desc2, const int32_t* d_n2, int cap2, int th_dist, float nn_ratio,
+                                      int check_orientation, int32_t* d_match12, int32_t* d_nmatches, void* cuda_stream) {
+    if (npairs < 0 || cap1 <= 0 || cap2 <= 0 || !d_kps1 || !d_desc1 || !d_n1 || !d_kps2 || !d_desc2 || !d_n2 || !d_match12 || !d_nmatches)
+        return ORB_ERR_INVALID;
+    if (npairs == 0) return ORB_OK;
+    if (cap2 > 65535) { orb_set_error("orb_match_bruteforce_batch_device: more than 65535 targets"); return ORB_ERR_CAPACITY; }
+    if (orb_device_count() <= 0) { orb_set_error("no CUDA device visible: liborb_b200 has no CPU fallback"); return ORB_ERR_NO_DEVICE; }
+    const int dpitch = (cap2 + 7) & ~7;
+    Carver c;   // per-pair scratch
+    const size_t o_D = c.take(2 * (size_t)cap1 * dpitch), o_topk = c.take(4 * (size_t)cap1 * BF_K), o_a1 = c.take(4 * (size_t)cap1), o_a2 = c.take(4 * (size_t)cap2);
+    const size_t o_owner = c.take(4 * (size_t)cap2), o_owner2 = c.take(4 * (size_t)cap2), o_bin = c.take(cap1);
+    const size_t per_pair = c.off;
+    const size_t jobs_bytes = ((size_t)npairs * sizeof(BfJob) + 255) & ~(size_t)255;
+    Workspace& W = g_ws;
+    int rc = W.prepare(device, jobs_bytes + per_pair * (size_t)npairs, 256);
+    if (rc != ORB_OK) return rc;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    std::vector<BfJob> jobs(npairs);
+    for (int p = 0; p < npairs; ++p) {
+        uint8_t* S = W.d + jobs_bytes + per_pair * (size_t)p;
+        BfJob& J = jobs[p];
+        J.d1 = d_desc1 + (size_t)p * cap1 * 32; J.d2 = d_desc2 + (size_t)p * cap2 * 32;
+        J.k1 = d_kps1 + (size_t)p * cap1; J.k2 = d_kps2 + (size_t)p * cap2;
+        J.n1_ptr = d_n1 + p; J.n2_ptr = d_n2 + p; J.cap1 = cap1; J.cap2 = cap2;
+        J.D = (unsigned short*)(S + o_D); J.dpitch = dpitch; J.topk = (unsigned*)(S + o_topk); J.a1 = (float*)(S + o_a1); J.a2 = (float*)(S + o_a2);
+        J.owner = (int*)(S + o_owner); J.owner2 = (int*)(S + o_owner2); J.m12 = d_match12 + (size_t)p * cap1; J.bin = (signed char*)(S + o_bin);
+        J.nm = d_nmatches + p;
+    }
+    ORB_CUDA(cudaMemcpyAsync(W.d, jobs.data(), (size_t)npairs * sizeof(BfJob), cudaMemcpyHostToDevice, st));   // pageable source: staged before return
+    const BfJob* d_jobs = (const BfJob*)W.d;
+    bf_rows_batch_kernel<<<dim3((cap1 + 7) / 8, npairs), 256, 0, st>>>(d_jobs);
+    bf_resolve_batch_kernel<<<npairs, SR_THREADS, 0, st>>>(d_jobs, th_dist, nn_ratio, check_orientation);
+    ORB_CUDA(cudaGetLastError());
+    return ORB_OK;
+}
+
+int orb_search_by_projection_batch_device(int device, const orb_search_params* prm, int npairs, const orb_search_batch* b, void* cuda_stream) {
+    if (!prm || !b || npairs < 0 || b->cap_n <= 0 || b->cap_q <= 0) return ORB_ERR_INVALID;
+    if (!b->d_kps_un || !b->d_desc || !b->d_n || !b->d_taken || !b->d_nq || !b->d_q_u || !b->d_q_v || !b->d_q_radius || !b->d_q_min_level ||
+        !b->d_q_max_level || !b->d_q_desc || !b->d_match_of_query || !b->d_target_query || !b->d_nmatches)
+        return ORB_ERR_INVALID;
+    if (b->d_u_right && (!b->d_q_ur || !b->d_q_er_max)) return ORB_ERR_INVALID;
+    if (prm->mode != ORB_MODE_TRACK_LAST && prm->mode != ORB_MODE_LOCAL_POINTS) {
+        orb_set_error("orb_search_by_projection_batch_device: modes TRACK_LAST and LOCAL_POINTS only");
+        return ORB_ERR_INVALID;
+    }
+    if (prm->mode == ORB_MODE_TRACK_LAST && prm->check_orientation && !b->d_q_angle) return ORB_ERR_INVALID;
+    if (npairs == 0) return ORB_OK;
+    const int n = b->cap_n, nq = b->cap_q;
+    if (n > GB_MAX_N) { orb_set_error("orb_search_by_projection_batch_device: more than %d target keypoints", GB_MAX_N); return ORB_ERR_CAPACITY; }
+    if (orb_device_count() <= 0) { orb_set_error("no CUDA device visible: liborb_b200 has no CPU fallback"); return ORB_ERR_NO_DEVICE; }
+    int npad = 32;
+    while (npad < n) npad <<= 1;
+    const int cand_cap = std::max(nq * 160, 4096);
+    Carver c;   // per-pair scratch
+    const size_t o_items = c.take(4 * (size_t)npad), o_cells = c.take(4 * (GRID_COLS * GRID_ROWS + 1));
+    const size_t o_cnt = c.take(4 * (size_t)nq), o_base = c.take(4 * (size_t)nq), o_bin = c.take(nq);
+    const size_t o_topk = c.take(4 * (size_t)nq * SR_K), o_asg = c.take(4 * (size_t)nq), o_scal = c.take(16);
+    const size_t o_cidx = c.take(4 * (size_t)cand_cap), o_cdist = c.take(2 * (size_t)cand_cap);
+    const size_t per_pair = c.off;
+    const size_t jobs_bytes = ((size_t)npairs * sizeof(WindowJob) + 255) & ~(size_t)255;
+    Workspace& W = g_ws;
+    int rc = W.prepare(device, jobs_bytes + per_pair * (size_t)npairs, 256);
+    if (rc != ORB_OK) return rc;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    std::vector<WindowJob> jobs(npairs);
+    for (int p = 0; p < npairs; ++p) {
+        uint8_t* S = W.d + jobs_bytes + per_pair * (size_t)p;
+        WindowJob& J = jobs[p];
+        memset(&J, 0, sizeof(J));
+        SearchArgs& a = J.a;
+        const size_t on = (size_t)p * n, oq = (size_t)p * nq;
+        a.n = n; a.nq = nq;
+        a.kps = b->d_kps_un + on; a.desc = b->d_desc + on * 32; a.u_right = b->d_u_right ? b->d_u_right + on : nullptr;
+        a.q_u = b->d_q_u + oq; a.q_v = b->d_q_v + oq; a.q_radius = b->d_q_radius + oq;
+        a.q_min_level = b->d_q_min_level + oq; a.q_max_level = b->d_q_max_level + oq; a.q_desc = b->d_q_desc + oq * 32;
+        a.q_ur = b->d_q_ur ? b->d_q_ur + oq : nullptr; a.q_er_max = b->d_q_er_max ? b->d_q_er_max + oq : nullptr;
+        a.q_angle = b->d_q_angle ? b->d_q_angle + oq : nullptr;
+        a.q_valid = b->d_q_valid ? b->d_q_valid + oq : nullptr; a.q_obs = b->d_q_obs ? b->d_q_obs + oq : nullptr;
+        a.min_x = prm->min_x; a.min_y = prm->min_y;
+        a.inv_w = (float)GRID_COLS / (prm->max_x - prm->min_x);   // Frame.cc:162-163
+        a.inv_h = (float)GRID_ROWS / (prm->max_y - prm->min_y);
+        int* scal = (int*)(S + o_scal);
+        a.items = (const unsigned*)(S + o_items); a.cell_start = (const int*)(S + o_cells);
+        a.cand_count = (int*)(S + o_cnt); a.cand_base = (int*)(S + o_base); a.cand_total = scal;
+        a.cand_cap = cand_cap; a.cand_idx = (int*)(S + o_cidx); a.cand_dist = (unsigned short*)(S + o_cdist);
+        a.topk = (unsigned*)(S + o_topk);
+        J.n_ptr = b->d_n + p; J.nq_ptr = b->d_nq + p;
+        J.taken = b->d_taken + on; J.moq = b->d_match_of_query + oq; J.tq = b->d_target_query + on;
+        J.bin = (signed char*)(S + o_bin); J.asg = (int*)(S + o_asg); J.scal = scal;
+    }
+    ORB_CUDA(cudaMemcpyAsync(W.d, jobs.data(), (size_t)npairs * sizeof(WindowJob), cudaMemcpyHostToDevice, st));
+    const WindowJob* d_jobs = (const WindowJob*)W.d;
+    const size_t rsmem = std::max(sizeof(SrStage) + (size_t)((n + 3) & ~3) * 5, (size_t)9 * ((n + 3) & ~3) + 16);
+    static thread_local int attr_dev = -1;
+    if (attr_dev != device) {
+        ORB_CUDA(cudaFuncSetAttribute(window_resolve_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)std::max(sizeof(SrStage) + GB_MAX_N * 5, (size_t)9 * GB_MAX_N + 16)));
+        attr_dev = device;
+    }
+    grid_build_batch_kernel<<<npairs, 1024, npad * sizeof(unsigned), st>>>(d_jobs);
+    window_candidates_batch_kernel<<<dim3((nq + 7) / 8, npairs), 256, 0, st>>>(d_jobs);
+    window_resolve_batch_kernel<<<npairs, SR_THREADS, rsmem, st>>>(d_jobs, prm->mode, prm->th_dist, prm->nn_ratio, prm->check_orientation, (int)rsmem);
+    ORB_CUDA(cudaGetLastError());
+    // per-pair status: nmatches = scal[1]; a pair whose candidate arena overflowed reports -1 (re-run it through orb_search_by_projection)
+    search_batch_finish_kernel<<<(npairs + 255) / 256, 256, 0, st>>>(d_jobs, npairs, b->d_nmatches);
+    ORB_CUDA(cudaGetLastError());
+    return ORB_OK;
+}
 }  // extern "C"

@@ -220,3 +220,17 @@ class DescriptorDB:
         a, b, n = C.c_double(0), C.c_double(0), C.c_int64(0)
         check(lib().orb_db_profile_read(self._h, C.byref(a), C.byref(b), C.byref(n), int(reset)))
         return a.value, b.value, n.value
+
+
+def match_bruteforce_batch_device(npairs, d_kps1, d_desc1, d_n1, cap1, d_kps2, d_desc2, d_n2, cap2, d_match12, d_nmatches, th_dist=TH_LOW,
+                                  nn_ratio=0.6, check_orientation=True, device=0, stream=0):
+    """orb_match_bruteforce for a batch of frame pairs, raw device pointers (outputs of two extract_batch_device calls)."""
+    vp = C.c_void_p
+    check(lib().orb_match_bruteforce_batch_device(device, npairs, vp(d_kps1), vp(d_desc1), vp(d_n1), cap1, vp(d_kps2), vp(d_desc2), vp(d_n2), cap2,
+                                                  th_dist, nn_ratio, int(check_orientation), vp(d_match12), vp(d_nmatches), vp(stream)))
+
+
+def search_by_projection_batch_device(mode, npairs, batch, bounds, th_dist=TH_HIGH, nn_ratio=0.9, check_orientation=True, device=0, stream=0):
+    """orb_search_by_projection for a batch of (target frame, query set) pairs; batch = _lib.SearchBatch of device pointers."""
+    prm = SearchParams(mode, th_dist, nn_ratio, int(check_orientation), *map(float, bounds))
+    check(lib().orb_search_by_projection_batch_device(device, C.byref(prm), npairs, C.byref(batch), C.c_void_p(stream)))

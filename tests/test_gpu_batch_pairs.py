@@ -58,3 +58,96 @@ def test_stereo_match_batch_device(oracle, w, h, nf):
         assert np.array_equal(ur[p, :n].view(np.uint32), ur_o.view(np.uint32))
         assert np.array_equal(dep[p, :n].view(np.uint32), dep_o.view(np.uint32))
         assert np.all(ur[p, n:] == -1) and np.all(dep[p, n:] == -1)
+
+
+def _pairs(P, seed0=20):
+    A = np.stack([synth.synth_frame(seed0 + p, 640, 480) for p in range(P)])
+    B = np.stack([synth.shifted_frame(A[p], 3, -2, seed0 + 100 + p) for p in range(P)])
+    return A, B
+
+
+def test_match_bruteforce_batch_device(oracle):
+    """BASELINE config 2, batched: 1000 x 1000 brute force + ratio test + rotation histogram per frame pair."""
+    import torch
+    from orb_slam_2_ros_b200 import ORBextractor
+    from orb_slam_2_ros_b200._lib import KP_DTYPE
+    from orb_slam_2_ros_b200.matcher import match_bruteforce_batch_device
+    P = 4
+    A, B = _pairs(P)
+    exa, exb = ORBextractor(1000, max_batch=P), ORBextractor(1000, max_batch=P)
+    _, ka, da, na, cap = _dev_batch_extract(exa, A)
+    _, kb, db, nb, _ = _dev_batch_extract(exb, B)
+    m12 = torch.full((P, cap), -7, dtype=torch.int32, device="cuda"); nm = torch.zeros(P, dtype=torch.int32, device="cuda")
+    for th, ratio, ori in ((50, 0.6, True), (100, 0.9, False)):
+        match_bruteforce_batch_device(P, ka.data_ptr(), da.data_ptr(), na.data_ptr(), cap, kb.data_ptr(), db.data_ptr(), nb.data_ptr(), cap,
+                                      m12.data_ptr(), nm.data_ptr(), th, ratio, ori, stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        m12h, nmh = m12.cpu().numpy(), nm.cpu().numpy()
+        for p in range(P):
+            n1, n2 = int(na[p]), int(nb[p])
+            k1 = ka[p].cpu().numpy().view(KP_DTYPE).reshape(-1)[:n1]; k2 = kb[p].cpu().numpy().view(KP_DTYPE).reshape(-1)[:n2]
+            d1 = da[p].cpu().numpy()[:n1]; d2 = db[p].cpu().numpy()[:n2]
+            nm_o, m_o = oracle.match_bruteforce(d1, k1["angle"], d2, k2["angle"], th, ratio, ori)
+            assert nm_o > 50
+            assert nmh[p] == nm_o
+            assert np.array_equal(m12h[p, :n1], m_o)
+            assert np.all(m12h[p, n1:] == -1)
+
+
+@pytest.mark.parametrize("mode_name", ["track_last", "local_points"])
+def test_search_by_projection_batch_device(oracle, mode_name):
+    """BASELINE config 2, batched: SearchByProjection windowed matching of frame A's keypoints in frame B, P pairs per call."""
+    import torch
+    from orb_slam_2_ros_b200 import ORBextractor
+    from orb_slam_2_ros_b200._lib import KP_DTYPE, SearchBatch
+    from orb_slam_2_ros_b200.matcher import MODE_LOCAL_POINTS, MODE_TRACK_LAST, search_by_projection_batch_device
+    P = 4
+    A, B = _pairs(P, 40)
+    exa, exb = ORBextractor(1000, max_batch=P), ORBextractor(1000, max_batch=P)
+    _, ka, da, na, cap = _dev_batch_extract(exa, A)
+    _, kb, db, nb, _ = _dev_batch_extract(exb, B)
+    sf = exa.GetScaleFactors()
+    rng = np.random.default_rng(9)
+    kah = ka.cpu().numpy().view(KP_DTYPE).reshape(P, cap)
+    kbh = kb.cpu().numpy().view(KP_DTYPE).reshape(P, cap)
+    nah, nbh = na.cpu().numpy(), nb.cpu().numpy()
+    th = 15.0 if mode_name == "track_last" else 4.0
+    q_u = (kah["x"] + np.float32(3)).astype(np.float32); q_v = (kah["y"] - np.float32(2)).astype(np.float32)
+    octv = np.clip(kah["octave"], 0, 7)
+    q_radius = (np.float32(th) * sf[octv]).astype(np.float32)
+    q_min = (octv - 1).astype(np.int32); q_max = (octv + (1 if mode_name == "track_last" else 0)).astype(np.int32)
+    q_valid = (rng.random((P, cap)) > 0.1).astype(np.uint8)
+    q_obs = (rng.random((P, cap)) > 0.3).astype(np.uint8)
+    u_right = np.where(rng.random((P, cap)) < 0.6, kbh["x"] - rng.uniform(1, 40, (P, cap)), -1).astype(np.float32)
+    q_ur = (q_u - rng.uniform(1, 40, (P, cap))).astype(np.float32)
+    q_er = q_radius.copy()
+    q_angle = kah["angle"].astype(np.float32).copy()
+    taken0 = (rng.random((P, cap)) < 0.05).astype(np.uint8)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    t = dict(q_u=dev(q_u), q_v=dev(q_v), q_radius=dev(q_radius), q_min=dev(q_min), q_max=dev(q_max), q_valid=dev(q_valid), q_obs=dev(q_obs),
+             u_right=dev(u_right), q_ur=dev(q_ur), q_er=dev(q_er), q_angle=dev(q_angle), taken=dev(taken0),
+             moq=torch.full((P, cap), -7, dtype=torch.int32, device="cuda"), tq=torch.full((P, cap), -7, dtype=torch.int32, device="cuda"),
+             nm=torch.zeros(P, dtype=torch.int32, device="cuda"))
+    b = SearchBatch(kb.data_ptr(), db.data_ptr(), t["u_right"].data_ptr(), nb.data_ptr(), cap, t["taken"].data_ptr(), na.data_ptr(), cap,
+                    t["q_u"].data_ptr(), t["q_v"].data_ptr(), t["q_radius"].data_ptr(), t["q_min"].data_ptr(), t["q_max"].data_ptr(), da.data_ptr(),
+                    t["q_ur"].data_ptr(), t["q_er"].data_ptr(), t["q_angle"].data_ptr(), t["q_valid"].data_ptr(), t["q_obs"].data_ptr(),
+                    t["moq"].data_ptr(), t["tq"].data_ptr(), t["nm"].data_ptr())
+    mode = MODE_TRACK_LAST if mode_name == "track_last" else MODE_LOCAL_POINTS
+    omode = oracle.MODE_TRACK_LAST if mode_name == "track_last" else oracle.MODE_LOCAL_POINTS
+    bounds = (0.0, 0.0, 640.0, 480.0)
+    search_by_projection_batch_device(mode, P, b, bounds, 100, 0.8, True, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    moq, tq, nm, taken = t["moq"].cpu().numpy(), t["tq"].cpu().numpy(), t["nm"].cpu().numpy(), t["taken"].cpu().numpy()
+    dah, dbh = da.cpu().numpy(), db.cpu().numpy()
+    for p in range(P):
+        n, nq = int(nbh[p]), int(nah[p])
+        grid = oracle.Grid(kbh[p, :n], *bounds)
+        t_o = taken0[p, :n].copy()
+        nm_o, moq_o, tq_o = oracle.search_by_projection(omode, grid, dbh[p, :n], u_right[p, :n], t_o, q_u[p, :nq], q_v[p, :nq], q_radius[p, :nq],
+                                                        q_min[p, :nq], q_max[p, :nq], dah[p, :nq], q_ur[p, :nq], q_er[p, :nq], q_angle[p, :nq],
+                                                        q_valid[p, :nq], q_obs[p, :nq], th_dist=100, nn_ratio=0.8, check_orientation=True)
+        assert nm_o > 100
+        assert nm[p] == nm_o
+        assert np.array_equal(moq[p, :nq], moq_o) and np.all(moq[p, nq:] == -1)
+        assert np.array_equal(tq[p, :n], tq_o) and np.all(tq[p, n:] == -1)
+        assert np.array_equal(taken[p, :n], t_o)

@@ -472,3 +472,26 @@ def test_search_for_initialization_steal_chains_in_parallel_rounds(oracle):
                 assert nm_o == n2                                                    # every target ends up owned by its LAST taker
                 last = {t: i for i, (t, fl) in enumerate(seq)}
                 assert all(m12_o[i] == t for t, i in last.items()) and (m12_o >= 0).sum() == n2
+
+
+def test_complementary_descriptor_distance_256(oracle):
+    """A distance of 256 (complementary descriptors) never becomes best or second best in the reference (dist < 256 is false,
+    ORBmatcher.cc:217-226), so the ratio test sees second = 256, not 255: with best = 153 and ratio 0.6 that decides the match
+    (153 < 153.6 but not < 153.0).  Top-K fast path and the full-row fallback must agree with the oracle."""
+    from orb_slam_2_ros_b200 import ORBmatcher
+    rng = np.random.default_rng(5)
+    q = rng.integers(0, 256, (1, 32), dtype=np.uint8)
+    near = q.copy()
+    bits = rng.choice(256, 153, replace=False)
+    for bidx in bits:
+        near[0, bidx // 8] ^= np.uint8(1 << (bidx % 8))
+    comp = q ^ np.uint8(255)
+    for targets in (np.concatenate([comp, near]), np.concatenate([near, comp]), np.concatenate([comp] * 12 + [near] + [comp] * 5)):
+        a1, a2 = np.zeros(1, np.float32), np.zeros(len(targets), np.float32)
+        nm_o, m_o = oracle.match_bruteforce(q, a1, targets, a2, 200, 0.6, False)
+        nm_g, m_g = ORBmatcher(0.6, False).MatchBruteForce(q, a1, targets, a2, 200)
+        assert nm_o == 1 and nm_g == nm_o and np.array_equal(m_g, m_o)
+    # all targets complementary: no match at all
+    nm_g, m_g = ORBmatcher(0.6, False).MatchBruteForce(q, np.zeros(1, np.float32), np.concatenate([comp] * 3), np.zeros(3, np.float32), 256)
+    nm_o, m_o = oracle.match_bruteforce(q, np.zeros(1, np.float32), np.concatenate([comp] * 3), np.zeros(3, np.float32), 256, 0.6, False)
+    assert nm_g == nm_o == 0 and np.array_equal(m_g, m_o)
