@@ -458,6 +458,7 @@ def main():
     ap.add_argument("--frame-size", default="", help="WxH of the synthetic frames (default 640x480 = the metric's shape; 752x480 = BASELINE config 4)")
     ap.add_argument("--no-hamming", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-pairs", action="store_true", help="skip the config 2 / 3 pair batches and the config 4 leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     protect_stdout()
@@ -493,7 +494,7 @@ def main():
             entry.build()
         if world > 1:
             dist.barrier()
-    from orb_slam_2_ros_b200 import DescriptorDB, ORBextractor, synth, top2_merge
+    from orb_slam_2_ros_b200 import ORBextractor, synth
     from orb_slam_2_ros_b200._lib import KP_DTYPE, TOP2_DTYPE
 
     def barrier():
@@ -620,24 +621,26 @@ def main():
         rows_total = args.db_rows
         from orb_slam_2_ros_b200.sharding import shard_range
         r0, r1 = shard_range(rows_total, rank, world)
-        db = DescriptorDB(max(r1 - r0, 1), index_base=r0, device=local_rank)
+        # the sharded database is a LIBRARY object: per-shard search, ncclAllGather of the 2000 x 24-byte results and the device merge
+        # run inside liborb_b200.so on the shard's stream (orb_db_query_top2_sharded); only the 128-byte NCCL id travels through torch
+        from orb_slam_2_ros_b200.matcher import ShardedDescriptorDB, shard_unique_id
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if world > 1:
+            if rank == 0:
+                uid.copy_(torch.from_numpy(shard_unique_id()))
+            dist.broadcast(uid, 0)
+        db = ShardedDescriptorDB(max(r1 - r0, 1), r0, rank, world, uid.cpu().numpy() if world > 1 else None, device=local_rank)
         chunk = 1 << 20
         for s in range(r0, r1, chunk):
             db.add(synth.synth_descriptors(DB_SEED, s, min(chunk, r1 - s)))
         q_np, planted, _flips = synth.synth_queries(DB_SEED, rows_total, NQ)
         d_q = torch.from_numpy(q_np).to(dev)
-        d_top = torch.zeros((NQ, TOP2_DTYPE.itemsize), dtype=torch.uint8, device=dev)
-        gathered = torch.zeros((world, NQ, TOP2_DTYPE.itemsize), dtype=torch.uint8, device=dev) if world > 1 else None
         d_merged = torch.zeros((NQ, TOP2_DTYPE.itemsize), dtype=torch.uint8, device=dev)
-        from orb_slam_2_ros_b200 import top2_merge_device
         db.set_stream(stream.cuda_stream)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
         def step_hamming():
-            db.query_top2_device(d_q.data_ptr(), NQ, d_top.data_ptr())
-            if world > 1:
-                dist.all_gather_into_tensor(gathered, d_top)   # 2000 x 24 B per rank over NCCL / NVLink
-                top2_merge_device(gathered.data_ptr(), world, NQ, d_merged.data_ptr(), local_rank, stream.cuda_stream)
+            db.query_top2_device(d_q.data_ptr(), NQ, d_merged.data_ptr())   # exact global top-2 on every rank
 
         for _ in range(args.warmup):
             step_hamming()
@@ -659,13 +662,9 @@ def main():
         s_ms, m_ms, calls = db.profile_read(reset=True)
         db.profile_enable(False)
         hl = db.launch_count() - hl0
-        # result check: merged top-1 of the planted queries must be the planted row
-        parts = gathered.cpu().numpy().view(TOP2_DTYPE).reshape(world, NQ) if world > 1 else \
-            d_top.cpu().numpy().view(TOP2_DTYPE).reshape(1, NQ)
-        merged = top2_merge(parts)
-        if world > 1:   # the device-side merge of the timed step must equal the host merge
-            dm = d_merged.cpu().numpy().view(TOP2_DTYPE).reshape(NQ)
-            assert all(np.array_equal(dm[f], merged[f]) for f in ("best_dist", "second_dist", "best_idx", "second_idx")), "device merge != host merge"
+        # result check: the global top-1 of the planted queries must be the planted row (all four fields of all 2000 queries are
+        # compared with the oracle at full size by tests/test_gpu_config5.py)
+        merged = d_merged.cpu().numpy().view(TOP2_DTYPE).reshape(NQ)
         ok = int((merged["best_idx"][planted >= 0] == planted[planted >= 0]).sum())
         import ctypes
         issue = ctypes.c_double(0)
@@ -675,25 +674,180 @@ def main():
         cmp8_rate = issue.value * 1e9                           # register-only compare with 8 POPC + top-2 update
         check(lib().orb_bench_issue_rate(local_rank, 2, 2000, ctypes.byref(issue)))
         cmp_rate = issue.value * 1e9                            # register-only compare as the kernel does it (carry-save, 4 POPC)
-        popc8_peak = popc_rate / 8.0                            # 8 x popc.b32 per 256-bit compare
-        peak_cmp = max(cmp_rate, popc8_peak)                    # ceiling of the kernel's own instruction mix
+        popc8_peak = popc_rate / 8.0                            # 8 x popc.b32 per 256-bit compare (SURVEY.md §8d's roofline)
+        popc4_peak = popc_rate / 4.0                            # the kernel's carry-save popcount needs 4 POPC per compare: its POPC-pipe bound
         kern_cps = NQ * (r1 - r0) / (s_ms / max(calls, 1) * 1e-3) if s_ms > 0 else 0.0
         ham = {
             "metric": "Hamming compares/s", "value": NQ * rows_total * hsteps / (tot * 1e-3), "unit": "compares/s",
             "scaling": "strong", "steps": hsteps, "ms_per_step": tot / hsteps,
-            "config": {"workload": "%d queries x %d-row descriptor DB sharded over %d GPU(s), top-2 + NCCL all-gather + device merge"
-                                   % (NQ, rows_total, world), "l2": "flushed between timed iterations"},
+            "config": {"workload": "%d queries x %d-row descriptor DB sharded over %d GPU(s): orb_db_query_top2_sharded = per-shard top-2 + "
+                                   "ncclAllGather + device merge inside liborb_b200.so" % (NQ, rows_total, world), "l2": "flushed between timed iterations"},
             "planted_top1_found": "%d/%d" % (ok, int((planted >= 0).sum())),
-            "roofline": {"bound": "int-issue (LOP3 + POPC pipes)", "achieved": kern_cps / 1e9, "peak": peak_cmp / 1e9, "unit": "Gcompare/s",
-                         "frac": kern_cps / peak_cmp if peak_cmp else None,
-                         "peak_source": "register-only issue rate of the kernel's compare + top-2 update on this GPU (carry-save "
-                                        "popcount: 16 LOP3 + 4 POPC per compare; orb_bench_issue_rate kind 2)",
+            "roofline": {"bound": "popc pipe (4 POPC per 256-bit compare after the carry-save tree)", "achieved": kern_cps / 1e9,
+                         "peak": popc4_peak / 1e9, "unit": "Gcompare/s", "frac": kern_cps / popc4_peak if popc4_peak else None,
+                         "peak_source": "POPC issue rate of this GPU measured register-only in this run (orb_bench_issue_rate kind 0) / 4",
                          "popc_per_s": popc_rate, "popc8_roofline_gcompare_s": popc8_peak / 1e9,
                          "frac_vs_popc8_roofline": kern_cps / popc8_peak if popc8_peak else None,
-                         "register_only_popc8_compare_per_s": cmp8_rate, "register_only_compare_per_s": cmp_rate,
+                         "binding_pipe": "ALU pipe (LOP3 XOR + carry-save adders, key packing, top-2 min/max); ncu on this kernel: ALU pipe 87 %, "
+                                         "XU/POPC pipe 69 % (profiles/r1_k_ncu_hamming_pipes.txt)",
+                         "own_instruction_mix_ceiling_gcompare_s": cmp_rate / 1e9, "register_only_popc8_compare_per_s": cmp8_rate,
                          "kernel": "hamming_top2_kernel", "avg_launch_ms": s_ms / max(calls, 1)},
-            "gpu_launches": int(hl) + (hsteps if world > 1 else 0),   # search + split-merge kernels (+ the cross-shard merge)
+            "gpu_launches": int(hl),   # search + split-merge kernels (+ the cross-shard merge kernel when sharded)
         }
+
+    # ---- BASELINE configs 2 and 3 as BATCHES OF PAIRS, device-resident, sharded over the ranks like frames:
+    #      config 2 = two extractions + 1000 x 1000 brute-force match (ratio test, rotation histogram) + SearchByProjection of A's
+    #      keypoints in B per pair; config 3 = two 1241x376 / 2000-feature extractions + Frame::ComputeStereoMatches per pair ----
+    def pairs_legs():
+        from orb_slam_2_ros_b200._lib import SearchBatch
+        from orb_slam_2_ros_b200.matcher import MODE_TRACK_LAST, match_bruteforce_batch_device, search_by_projection_batch_device
+        from orb_slam_2_ros_b200.stereo import ComputeStereoMatchesBatchDevice
+        out = {}
+        steps = max(3, min(args.steps, 5))
+
+        def timed(fn):
+            for _ in range(3):
+                fn()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(steps):
+                fn()
+            b.record(stream)
+            barrier()
+            return max_over_ranks(a.elapsed_time(b)) / steps
+
+        def dev_outputs(P, cap_):
+            return (torch.zeros((P, cap_, KP_DTYPE.itemsize), dtype=torch.uint8, device=dev), torch.zeros((P, cap_, 32), dtype=torch.uint8, device=dev),
+                    torch.zeros(P, dtype=torch.int32, device=dev))
+
+        # ---------------- config 2 ----------------
+        P = 128
+        A = synth.synth_batch(5000 + 1000 * rank, P, 640, 480, unique=16, noise=args.noise)
+        Bf = np.stack([synth.shifted_frame(A[i], 3, -2, 7000 + i) for i in range(16)])
+        Bf = Bf[np.arange(P) % 16]
+        dA, dB = torch.from_numpy(A).to(dev), torch.from_numpy(np.ascontiguousarray(Bf)).to(dev)
+        exa = ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=local_rank, max_batch=P)
+        exb = ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=local_rank, max_batch=P)
+        exa.set_stream(stream.cuda_stream); exb.set_stream(stream.cuda_stream)
+        c2 = exa.max_keypoints
+        ka, da, na = dev_outputs(P, c2)
+        kb, db_, nb = dev_outputs(P, c2)
+
+        def extract2():
+            exa.extract_batch_device(dA.data_ptr(), P, 640, 480, 640, 640 * 480, ka.data_ptr(), da.data_ptr(), c2, na.data_ptr())
+            exb.extract_batch_device(dB.data_ptr(), P, 640, 480, 640, 640 * 480, kb.data_ptr(), db_.data_ptr(), c2, nb.data_ptr())
+        extract2()
+        torch.cuda.synchronize()
+        # the caller's side of SearchByProjection (Tracking projects the last frame's points): A's keypoints shifted by the known motion,
+        # window 15 * scale[octave], octave band +-1 — computed once, the frames are the same every step
+        kf = ka.view(torch.float32).view(P, c2, 7)
+        octv = ka.view(torch.int32).view(P, c2, 7)[..., 5].clamp(0, NLEVELS - 1)
+        sc = torch.from_numpy(exa.GetScaleFactors()).to(dev)
+        q = dict(u=(kf[..., 0] + 3.0).contiguous(), v=(kf[..., 1] - 2.0).contiguous(), r=(15.0 * sc[octv.long()]).contiguous(),
+                 lo=(octv - 1).to(torch.int32).contiguous(), hi=(octv + 1).to(torch.int32).contiguous(), ang=kf[..., 3].contiguous())
+        taken = torch.zeros((P, c2), dtype=torch.uint8, device=dev)
+        moq = torch.zeros((P, c2), dtype=torch.int32, device=dev); tq = torch.zeros_like(moq)
+        nm_s = torch.zeros(P, dtype=torch.int32, device=dev); nm_b = torch.zeros_like(nm_s); m12 = torch.zeros_like(moq)
+        sb = SearchBatch(kb.data_ptr(), db_.data_ptr(), None, nb.data_ptr(), c2, taken.data_ptr(), na.data_ptr(), c2, q["u"].data_ptr(), q["v"].data_ptr(),
+                         q["r"].data_ptr(), q["lo"].data_ptr(), q["hi"].data_ptr(), da.data_ptr(), None, None, q["ang"].data_ptr(), None, None,
+                         moq.data_ptr(), tq.data_ptr(), nm_s.data_ptr())
+
+        def match2():
+            match_bruteforce_batch_device(P, ka.data_ptr(), da.data_ptr(), na.data_ptr(), c2, kb.data_ptr(), db_.data_ptr(), nb.data_ptr(), c2,
+                                          m12.data_ptr(), nm_b.data_ptr(), 50, 0.6, True, device=local_rank, stream=stream.cuda_stream)
+            taken.zero_()
+            search_by_projection_batch_device(MODE_TRACK_LAST, P, sb, (0.0, 0.0, 640.0, 480.0), 100, 0.9, True, device=local_rank, stream=stream.cuda_stream)
+
+        def step2():
+            extract2()
+            match2()
+        ms_all, ms_match = timed(step2), timed(match2)
+        torch.cuda.synchronize()
+        out["config2"] = {"metric": "frame pairs/s: 2 x ORBextractor 640x480 + 1000x1000 brute-force match (ratio 0.6, rot. hist.) + SearchByProjection (th 15)",
+                          "value": world * P / (ms_all * 1e-3), "unit": "pairs/s", "pairs_per_step_per_gpu": P, "ms_per_step": ms_all,
+                          "matching_only_ms_per_step": ms_match, "matching_only_pairs_per_s": world * P / (ms_match * 1e-3), "scaling": "weak",
+                          "bruteforce_matches_per_pair": float(nm_b.float().mean().item()), "projection_matches_per_pair": float(nm_s.float().mean().item()),
+                          "entry_points": "orb_extract_batch_device x2, orb_match_bruteforce_batch_device, orb_search_by_projection_batch_device (device-resident)"}
+        del exa, exb, ka, da, kb, db_, dA, dB
+        # ---------------- config 3 ----------------
+        P3, w3, h3, nf3 = 64, 1241, 376, 2000
+        prs = [synth.synth_stereo_pair(9000 + 100 * rank + i, w3, h3)[:2] for i in range(8)]
+        L = np.stack([prs[i % 8][0] for i in range(P3)]); R = np.stack([prs[i % 8][1] for i in range(P3)])
+        dL, dR = torch.from_numpy(L).to(dev), torch.from_numpy(R).to(dev)
+        exl = ORBextractor(nf3, SCALE, NLEVELS, INI_TH, MIN_TH, device=local_rank, max_batch=P3)
+        exr = ORBextractor(nf3, SCALE, NLEVELS, INI_TH, MIN_TH, device=local_rank, max_batch=P3)
+        exl.set_stream(stream.cuda_stream); exr.set_stream(stream.cuda_stream)
+        c3 = exl.max_keypoints
+        kl, dl, nl = dev_outputs(P3, c3)
+        kr, dr, nr = dev_outputs(P3, c3)
+        ur = torch.zeros((P3, c3), dtype=torch.float32, device=dev); dep = torch.zeros_like(ur)
+        nm3 = torch.zeros(P3, dtype=torch.int32, device=dev)
+        bf3 = float(np.float32(386.1448)); b3 = float(np.float32(386.1448) / np.float32(718.856))
+
+        def stereo_only():
+            ComputeStereoMatchesBatchDevice(exl, exr, P3, kl.data_ptr(), dl.data_ptr(), nl.data_ptr(), kr.data_ptr(), dr.data_ptr(), nr.data_ptr(), c3, bf3, b3,
+                                            ur.data_ptr(), dep.data_ptr(), nm3.data_ptr())
+
+        def step3():
+            exl.extract_batch_device(dL.data_ptr(), P3, w3, h3, w3, w3 * h3, kl.data_ptr(), dl.data_ptr(), c3, nl.data_ptr())
+            exr.extract_batch_device(dR.data_ptr(), P3, w3, h3, w3, w3 * h3, kr.data_ptr(), dr.data_ptr(), c3, nr.data_ptr())
+            stereo_only()
+        ms3, ms3m = timed(step3), timed(stereo_only)
+        torch.cuda.synchronize()
+        out["config3"] = {"metric": "stereo pairs/s: 2 x ORBextractor 1241x376 nFeatures=2000 + Frame::ComputeStereoMatches", "value": world * P3 / (ms3 * 1e-3),
+                          "unit": "pairs/s", "pairs_per_step_per_gpu": P3, "ms_per_step": ms3, "stereo_matching_only_ms_per_step": ms3m,
+                          "stereo_matching_only_pairs_per_s": world * P3 / (ms3m * 1e-3), "scaling": "weak",
+                          "stereo_matches_per_pair": float(nm3.float().mean().item()),
+                          "entry_points": "orb_extract_batch_device x2, orb_stereo_match_batch_device (device-resident)"}
+        return out
+
+    # ---- BASELINE config 4 as specified: 4096 frames of 752x480 STRONG-sharded over the ranks (contiguous blocks of 4096 / N) ----
+    def config4_leg():
+        total, w4, h4 = 4096, 752, 480
+        per = total // world
+        b4 = min(512, per)
+        nb4 = per // b4
+        fr = synth.synth_batch(20000 + 1000 * rank, b4, w4, h4, unique=16, noise=args.noise)
+        hf = torch.from_numpy(fr).pin_memory()
+        df = hf.to(dev)
+        e4 = ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=local_rank, max_batch=b4)
+        e4.set_stream(stream.cuda_stream)
+        c4 = e4.max_keypoints
+        k4 = torch.zeros((b4, c4, KP_DTYPE.itemsize), dtype=torch.uint8, device=dev); d4 = torch.zeros((b4, c4, 32), dtype=torch.uint8, device=dev)
+        n4 = torch.zeros(b4, dtype=torch.int32, device=dev)
+
+        def dev_pass():
+            for _ in range(nb4):
+                e4.extract_batch_device(df.data_ptr(), b4, w4, h4, w4, w4 * h4, k4.data_ptr(), d4.data_ptr(), c4, n4.data_ptr())
+        for _ in range(2):
+            dev_pass()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        dev_pass()
+        b.record(stream)
+        barrier()
+        ms = max_over_ranks(a.elapsed_time(b))
+        kh = torch.zeros((b4, c4, KP_DTYPE.itemsize), dtype=torch.uint8).pin_memory(); dh = torch.zeros((b4, c4, 32), dtype=torch.uint8).pin_memory()
+        nh = np.zeros(b4, np.int32)
+
+        def host_pass():
+            for _ in range(nb4):
+                check(lib().orb_extract_batch(e4._h, hf.data_ptr(), b4, w4, h4, w4, w4 * h4, ptr(kh.numpy()), ptr(dh.numpy()), c4, ptr(nh)))
+        host_pass()
+        barrier()
+        t0 = time.perf_counter()
+        host_pass()
+        torch.cuda.synchronize()
+        te = max_over_ranks(time.perf_counter() - t0)
+        return {"metric": "ORB extract frames/s, 4096 frames of 752x480 (EuRoC shape) sharded over the GPUs", "value": total / (ms * 1e-3), "unit": "frames/s",
+                "scaling": "strong", "frames_total": total, "frames_per_gpu": per, "batch": b4, "ms_total": ms,
+                "e2e": {"value": total / te, "unit": "frames/s", "h2d_bytes": per * w4 * h4, "callers": 1,
+                        "note": "host pinned frames -> host keypoints + descriptors, one caller per rank"}}
+
+    pairs = pairs_legs() if not args.no_pairs else None
+    config4 = config4_leg() if not args.no_pairs else None
 
     sampler.join(timeout=2.0)
     if clk.get("proc"):
@@ -779,6 +933,8 @@ def main():
             "roofline": roof,
             "cpu_baseline": cpu,
             "hamming": ham,
+            "pairs": pairs,
+            "config4": config4,
             "other_configs": other_configs(local_rank) if (world == 1 and not args.no_cpu) else None,
             "clocks": summarize_clocks(clk.get("rows")),
         }

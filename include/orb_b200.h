@@ -166,6 +166,19 @@ int orb_top2_merge(const orb_top2* parts, int nparts, int nq, orb_top2* out);
 /* the same on the device, asynchronous on cuda_stream: the step after ncclAllGather of the per-shard results */
 int orb_top2_merge_device(int device, const orb_top2* d_parts, int nparts, int nq, orb_top2* d_out, void* cuda_stream);
 
+/* Sharded database (BASELINE config 5): one orb_db per rank / GPU holding a contiguous slice of the
+ * rows (index_base = global index of its first row); every rank asks the same queries and receives the exact global answer.
+ * Inside: per-shard search -> ncclAllGather of the nq x 24-byte per-shard results on the shard's stream -> device merge
+ * (best = minimum distance, lowest global index on ties; second = second smallest of the union — each shard's two best
+ * suffice).  NCCL is bound at run time (dlopen of libnccl.so.2); the unique id is created on rank 0 and handed to the
+ * other ranks by whatever transport the host program has (MPI, torch.distributed, a file): 128 bytes.
+ * orb_db_create_sharded is collective (ncclCommInitRank); world == 1 degenerates to orb_db_create. */
+#define ORB_SHARD_ID_BYTES 128
+int orb_shard_unique_id(uint8_t* id128);
+int orb_db_create_sharded(orb_db** db, int device, int64_t capacity_rows, int64_t index_base, int rank, int world, const uint8_t* id128);
+int orb_db_query_top2_sharded(orb_db* db, const uint8_t* d_q, int nq, orb_top2* d_out);          /* device pointers, async */
+int orb_db_query_top2_sharded_host(orb_db* db, const uint8_t* q, int nq, orb_top2* out);          /* host pointers, blocking */
+
 /* ---- windowed search with the sequential "already matched" rule ------------------------------------ */
 enum {
     ORB_MODE_TRACK_LAST = 0,  /* ORBmatcher.cc:1330-1472: best only, <= th_dist, rotation histogram      */
@@ -356,6 +369,14 @@ int orb_keypoint_records_encode(const orb_kp* kps, int n, uint8_t* out /* 28 * n
 int orb_keypoint_records_decode(const uint8_t* buf, int n, orb_kp* kps);
 /* decode one KeyFrame::mDescriptors record (N x 32, CV_8UC1) and append its rows to the device shard; rows_added = N */
 int orb_db_add_mat_record(orb_db* db, const uint8_t* buf, size_t len, size_t* consumed, int64_t* rows_added);
+
+/* ---- diagnostics (used by bench.py and the parity tests; not part of the replaced surface) -----------------------------
+ * orb_bench_issue_rate: register-only issue-rate microbenchmarks on `device`; kind 0: POPC -> *gops = 1e9 popc/s; kind 1:
+ * a 256-bit compare with 8 POPC + the top-2 update -> 1e9 compares/s; kind 2: the same with the search kernel's carry-save
+ * (4 POPC) popcount.  orb_debug_sincos_range: the steering coefficients a = (float)cos, b = (float)sin the descriptor kernel
+ * computes for the n consecutive fp32 angle bit patterns starting at first_bits (parity pin (iii)). */
+int orb_bench_issue_rate(int device, int kind, int iters, double* gops);
+int orb_debug_sincos_range(int device, uint32_t first_bits, long long n, float* a, float* b);
 
 #ifdef __cplusplus
 }

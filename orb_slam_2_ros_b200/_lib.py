@@ -52,6 +52,7 @@ EXPORTS = [
     "orb_bow_transform_features_device", "orb_bow_transform", "orb_bow_transform_device",
     "orb_mat_record_bytes", "orb_mat_record_encode", "orb_mat_record_decode", "orb_keypoint_records_encode",
     "orb_keypoint_records_decode", "orb_db_add_mat_record",
+    "orb_shard_unique_id", "orb_db_create_sharded", "orb_db_query_top2_sharded", "orb_db_query_top2_sharded_host", "orb_bench_issue_rate", "orb_debug_sincos_range",
 ]
 
 _lib = None
@@ -127,6 +128,10 @@ def lib():
     L.orb_bow_transform_features_device.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp]
     L.orb_bow_transform.argtypes = [vp, vp, vp, i32, i32] + [vp] * 7
     L.orb_bow_transform_device.argtypes = [vp, vp, vp, i32, i32, i32, i32] + [vp] * 9
+    L.orb_shard_unique_id.argtypes = [vp]
+    L.orb_db_create_sharded.argtypes = [C.POINTER(vp), i32, i64, i64, i32, i32, vp]
+    L.orb_db_query_top2_sharded.argtypes = [vp, vp, i32, vp]
+    L.orb_db_query_top2_sharded_host.argtypes = [vp, vp, i32, vp]
     L.orb_debug_sincos_range.argtypes = [i32, C.c_uint32, C.c_longlong, vp, vp]
     L.orb_bench_issue_rate.argtypes = [i32, i32, i32, C.POINTER(C.c_double)]
     psz = C.POINTER(C.c_size_t)

@@ -246,6 +246,9 @@ struct orb_db {
     uint2* d_partial = nullptr; size_t partial_elems = 0;
     uint8_t* d_q = nullptr; orb_top2* d_out = nullptr; int q_cap = 0;
     long long launches = 0;
+    // sharded form (orb_db_create_sharded): one shard per rank, per-shard results all-gathered over NCCL and merged on the device
+    void* comm = nullptr; int rank = 0, world = 1;
+    orb_top2* d_part = nullptr; orb_top2* d_all = nullptr; int shard_q_cap = 0;
     // CUDA-event timers of {search kernel, merge kernel}: ring of event triples, harvested lazily
     bool profile = false;
     cudaEvent_t prof_ev[ORB_PROF_RING][3] = {};
@@ -306,6 +309,45 @@ static int db_launch(orb_db* db, const uint8_t* d_q, int nq, orb_top2* d_out) {
     return ORB_OK;
 }
 
+// ---- NCCL, bound at run time ------------------------------------------------------------------------------------------
+// liborb_b200.so must load on hosts without NCCL (single-GPU use, the CPU-only build check), so the five entry points the
+// sharded database needs are resolved with dlopen / dlsym on first use: "libnccl.so.2" — the copy already mapped into the
+// process (e.g. the one PyTorch ships) if there is one, else the system's.  The ABI of these calls is stable across NCCL 2.x.
+#include <dlfcn.h>
+namespace {
+struct NcclId { char internal[128]; };   // ncclUniqueId (NCCL_UNIQUE_ID_BYTES = 128)
+struct NcclApi {
+    int (*GetUniqueId)(NcclId*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int /*ncclDataType_t*/, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+NcclApi* nccl_api() {
+    static NcclApi api = [] {
+        NcclApi a;
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+        if (!h) return a;
+        a.GetUniqueId = (int (*)(NcclId*))dlsym(h, "ncclGetUniqueId");
+        a.CommInitRank = (int (*)(void**, int, NcclId, int))dlsym(h, "ncclCommInitRank");
+        a.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+        a.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(h, "ncclAllGather");
+        a.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+        a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllGather && a.GetErrorString;
+        return a;
+    }();
+    return &api;
+}
+#define ORB_NCCL(call)                                                                                        \
+    do {                                                                                                      \
+        const int _r = (call);                                                                                \
+        if (_r != 0) { orb_set_error("NCCL: %s (%s)", nccl_api()->GetErrorString(_r), #call); return ORB_ERR_CUDA; } \
+    } while (0)
+}  // namespace
+
 extern "C" {
 
 int orb_db_create(orb_db** out, int device, int64_t capacity_rows, int64_t index_base) {
@@ -331,7 +373,8 @@ void orb_db_destroy(orb_db* db) {
     if (!db) return;
     cudaSetDevice(db->device);
     if (db->stream) cudaStreamSynchronize(db->stream);
-    cudaFree(db->d_rows); cudaFree(db->d_partial); cudaFree(db->d_q); cudaFree(db->d_out);
+    cudaFree(db->d_rows); cudaFree(db->d_partial); cudaFree(db->d_q); cudaFree(db->d_out); cudaFree(db->d_part); cudaFree(db->d_all);
+    if (db->comm && nccl_api()->ok) nccl_api()->CommDestroy(db->comm);
     if (db->prof_ev[0][0])
         for (int r = 0; r < ORB_PROF_RING; ++r)
             for (int s = 0; s < 3; ++s) cudaEventDestroy(db->prof_ev[r][s]);
@@ -420,14 +463,89 @@ int orb_db_query_top2(orb_db* db, const uint8_t* q, int nq, orb_top2* out) {
     return ORB_OK;
 }
 
+/* ---- sharded database: one shard per rank / GPU, exact global top-2 (BASELINE config 5) ---------- */
+int orb_shard_unique_id(uint8_t* id128) {
+    if (!id128) return ORB_ERR_INVALID;
+    if (!nccl_api()->ok) { orb_set_error("NCCL (libnccl.so.2) not found: the sharded database needs it"); return ORB_ERR_INVALID; }
+    NcclId id;
+    ORB_NCCL(nccl_api()->GetUniqueId(&id));
+    memcpy(id128, id.internal, 128);
+    return ORB_OK;
+}
+
+int orb_db_create_sharded(orb_db** out, int device, int64_t capacity_rows, int64_t index_base, int rank, int world, const uint8_t* id128) {
+    if (!out || world < 1 || rank < 0 || rank >= world || (world > 1 && !id128)) return ORB_ERR_INVALID;
+    int rc = orb_db_create(out, device, capacity_rows, index_base);
+    if (rc != ORB_OK) return rc;
+    orb_db* db = *out;
+    db->rank = rank; db->world = world;
+    if (world > 1) {
+        if (!nccl_api()->ok) { orb_db_destroy(db); *out = nullptr; orb_set_error("NCCL (libnccl.so.2) not found: the sharded database needs it"); return ORB_ERR_INVALID; }
+        NcclId id;
+        memcpy(id.internal, id128, 128);
+        const int r = nccl_api()->CommInitRank(&db->comm, world, id, rank);   // collective: every rank calls it
+        if (r != 0) { orb_set_error("NCCL: %s (ncclCommInitRank)", nccl_api()->GetErrorString(r)); orb_db_destroy(db); *out = nullptr; return ORB_ERR_CUDA; }
+    }
+    return ORB_OK;
+}
+
+/* every rank passes the same nq queries; d_out on every rank receives the exact global result.  Asynchronous on the shard's stream:
+ * per-shard search -> ncclAllGather of the nq x 24-byte results -> device merge. */
+int orb_db_query_top2_sharded(orb_db* db, const uint8_t* d_q, int nq, orb_top2* d_out) {
+    if (!db || nq < 0 || (nq && (!d_q || !d_out))) return ORB_ERR_INVALID;
+    if (nq == 0) return ORB_OK;
+    ORB_CUDA(cudaSetDevice(db->device));
+    if (db->world == 1) return db_launch(db, d_q, nq, d_out);
+    if (db->shard_q_cap < nq) {
+        ORB_CUDA(cudaStreamSynchronize(db->stream));
+        cudaFree(db->d_part); cudaFree(db->d_all); db->d_part = nullptr; db->d_all = nullptr; db->shard_q_cap = 0;
+        ORB_CUDA(cudaMalloc(&db->d_part, (size_t)nq * sizeof(orb_top2)));
+        ORB_CUDA(cudaMalloc(&db->d_all, (size_t)nq * sizeof(orb_top2) * db->world));
+        db->shard_q_cap = nq;
+    }
+    int rc = db_launch(db, d_q, nq, db->d_part);
+    if (rc != ORB_OK) return rc;
+    ORB_NCCL(nccl_api()->AllGather(db->d_part, db->d_all, (size_t)nq * sizeof(orb_top2), /*ncclChar*/ 0, db->comm, db->stream));
+    top2_merge_kernel<<<(nq + 127) / 128, 128, 0, db->stream>>>(db->d_all, db->world, nq, d_out);
+    db->launches++;
+    ORB_CUDA(cudaGetLastError());
+    return ORB_OK;
+}
+
+/* host-pointer convenience form of the same (blocking) */
+int orb_db_query_top2_sharded_host(orb_db* db, const uint8_t* q, int nq, orb_top2* out) {
+    if (!db || nq < 0 || (nq && (!q || !out))) return ORB_ERR_INVALID;
+    if (nq == 0) return ORB_OK;
+    ORB_CUDA(cudaSetDevice(db->device));
+    if (db->q_cap < nq) {
+        ORB_CUDA(cudaStreamSynchronize(db->stream));
+        cudaFree(db->d_q); cudaFree(db->d_out); db->d_q = nullptr; db->d_out = nullptr;
+        ORB_CUDA(cudaMalloc(&db->d_q, (size_t)nq * 32));
+        ORB_CUDA(cudaMalloc(&db->d_out, (size_t)nq * sizeof(orb_top2)));
+        db->q_cap = nq;
+    }
+    ORB_CUDA(cudaMemcpyAsync(db->d_q, q, (size_t)nq * 32, cudaMemcpyHostToDevice, db->stream));
+    int rc = orb_db_query_top2_sharded(db, db->d_q, nq, db->d_out);
+    if (rc != ORB_OK) return rc;
+    ORB_CUDA(cudaMemcpyAsync(out, db->d_out, (size_t)nq * sizeof(orb_top2), cudaMemcpyDeviceToHost, db->stream));
+    ORB_CUDA(cudaStreamSynchronize(db->stream));
+    return ORB_OK;
+}
+
 int orb_hamming_top2(int device, const uint8_t* q, int nq, const uint8_t* dbrows, int64_t ndb, orb_top2* out) {
     if (nq < 0 || ndb < 0 || (nq && (!q || !out)) || (ndb && !dbrows)) return ORB_ERR_INVALID;
-    orb_db* db = nullptr;
-    int rc = orb_db_create(&db, device, ndb, 0);
-    if (rc != ORB_OK) return rc;
-    rc = orb_db_add(db, dbrows, ndb);
-    if (rc == ORB_OK) rc = orb_db_query_top2(db, q, nq, out);
-    orb_db_destroy(db);
+    // one grow-only database per calling thread and device, reused across calls (no cudaMalloc / cudaFree on the call path)
+    struct Cache { orb_db* db = nullptr; int device = -1; ~Cache() { /* the CUDA context may be gone at thread exit: leak, do not touch it */ } };
+    static thread_local Cache cache;
+    if (cache.db && (cache.device != device || cache.db->cap < ndb)) { orb_db_destroy(cache.db); cache.db = nullptr; }
+    if (!cache.db) {
+        const int rc = orb_db_create(&cache.db, device, std::max<int64_t>(ndb + ndb / 2, 1024), 0);
+        if (rc != ORB_OK) { cache.db = nullptr; return rc; }
+        cache.device = device;
+    }
+    cache.db->n = 0;
+    int rc = orb_db_add(cache.db, dbrows, ndb);
+    if (rc == ORB_OK) rc = orb_db_query_top2(cache.db, q, nq, out);
     return rc;
 }
 

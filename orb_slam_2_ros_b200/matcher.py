@@ -234,3 +234,31 @@ def search_by_projection_batch_device(mode, npairs, batch, bounds, th_dist=TH_HI
     """orb_search_by_projection for a batch of (target frame, query set) pairs; batch = _lib.SearchBatch of device pointers."""
     prm = SearchParams(mode, th_dist, nn_ratio, int(check_orientation), *map(float, bounds))
     check(lib().orb_search_by_projection_batch_device(device, C.byref(prm), npairs, C.byref(batch), C.c_void_p(stream)))
+
+
+def shard_unique_id():
+    """128 bytes identifying one sharded-database communicator: create on rank 0, hand to every rank (any transport)."""
+    buf = np.zeros(128, np.uint8)
+    check(lib().orb_shard_unique_id(ptr(buf)))
+    return buf
+
+
+class ShardedDescriptorDB(DescriptorDB):
+    """BASELINE config 5 as a library object: this rank's contiguous slice of a descriptor database that is sharded over `world`
+    GPUs.  query_top2_device / query_top2 return the exact GLOBAL best / second-best on every rank (per-shard search, NCCL
+    all-gather of the 24-byte results and device merge all happen inside liborb_b200.so on the shard's stream)."""
+
+    def __init__(self, capacity_rows, index_base, rank, world, unique_id, device=0):
+        self._h = C.c_void_p()
+        uid = None if unique_id is None else np.ascontiguousarray(unique_id, np.uint8)
+        check(lib().orb_db_create_sharded(C.byref(self._h), device, capacity_rows, index_base, rank, world, ptr(uid)))
+        self.device, self.index_base, self.rank, self.world = device, index_base, rank, world
+
+    def query_top2_device(self, d_q, nq, d_out):
+        check(lib().orb_db_query_top2_sharded(self._h, C.c_void_p(d_q), nq, C.c_void_p(d_out)))
+
+    def query_top2(self, q):
+        q = _b(q)
+        out = np.zeros(len(q), TOP2_DTYPE)
+        check(lib().orb_db_query_top2_sharded_host(self._h, ptr(q), len(q), ptr(out)))
+        return out
