@@ -1213,20 +1213,22 @@ struct Workspace {
     cudaStream_t st = nullptr;
     uint8_t *d = nullptr, *h = nullptr;
     size_t d_cap = 0, h_cap = 0;
+    std::vector<uint8_t> jobs_on_device;   // batched entry points: the job array currently at the head of the device slab
     ~Workspace() {
         // (the CUDA context may already be gone at thread exit: ignore errors)
         if (device >= 0 && cudaSetDevice(device) == cudaSuccess) { cudaFree(d); cudaFreeHost(h); if (st) cudaStreamDestroy(st); }
     }
-    int prepare(int dev, size_t dbytes, size_t hbytes) {
+    int prepare(int dev, size_t dbytes, size_t hbytes, bool batched = false) {
         ORB_CUDA(cudaSetDevice(dev));
+        if (!batched) jobs_on_device.clear();   // the single-pair entry points overwrite the head of the slab
         if (device != dev) {
             if (device >= 0) { cudaSetDevice(device); cudaFree(d); cudaFreeHost(h); if (st) cudaStreamDestroy(st); cudaSetDevice(dev); }
-            d = h = nullptr; d_cap = h_cap = 0; st = nullptr; device = dev;
+            d = h = nullptr; d_cap = h_cap = 0; st = nullptr; device = dev; jobs_on_device.clear();
             ORB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         }
         if (d_cap < dbytes) {
             ORB_CUDA(cudaStreamSynchronize(st));
-            cudaFree(d); d = nullptr; d_cap = 0;
+            cudaFree(d); d = nullptr; d_cap = 0; jobs_on_device.clear();
             ORB_CUDA(cudaMalloc(&d, dbytes + dbytes / 2));
             d_cap = dbytes + dbytes / 2;
         }
@@ -1240,6 +1242,17 @@ struct Workspace {
     }
 };
 thread_local Workspace g_ws;
+thread_local Workspace g_ws_batch[2];   // batched brute force / batched windowed search: own slabs, so their job arrays stay cached
+
+// Upload a batched call's job array to the head of the device slab unless the identical array is already there: a pipeline that
+// calls with the same buffers every step (the normal case) then issues no copy at all — a pageable-source cudaMemcpyAsync stalls
+// the host until the stream has drained, which serialises launch and execution.
+int upload_jobs(Workspace& W, const void* jobs, size_t bytes, cudaStream_t st) {
+    if (W.jobs_on_device.size() == bytes && memcmp(W.jobs_on_device.data(), jobs, bytes) == 0) return ORB_OK;
+    W.jobs_on_device.assign((const uint8_t*)jobs, (const uint8_t*)jobs + bytes);
+    ORB_CUDA(cudaMemcpyAsync(W.d, jobs, bytes, cudaMemcpyHostToDevice, st));
+    return ORB_OK;
+}
 
 // carve-up helper: the same offsets are valid in the pinned slab (inputs / outputs) and the device slab
 struct Carver {
@@ -1705,8 +1718,8 @@ int orb_match_bruteforce_batch_device(int device, int npairs, const orb_kp* d_kp
     const size_t o_owner = c.take(4 * (size_t)cap2), o_owner2 = c.take(4 * (size_t)cap2), o_bin = c.take(cap1);
     const size_t per_pair = c.off;
     const size_t jobs_bytes = ((size_t)npairs * sizeof(BfJob) + 255) & ~(size_t)255;
-    Workspace& W = g_ws;
-    int rc = W.prepare(device, jobs_bytes + per_pair * (size_t)npairs, 256);
+    Workspace& W = g_ws_batch[0];
+    int rc = W.prepare(device, jobs_bytes + per_pair * (size_t)npairs, 256, true);
     if (rc != ORB_OK) return rc;
     cudaStream_t st = (cudaStream_t)cuda_stream;
     std::vector<BfJob> jobs(npairs);
@@ -1720,7 +1733,8 @@ int orb_match_bruteforce_batch_device(int device, int npairs, const orb_kp* d_kp
         J.owner = (int*)(S + o_owner); J.owner2 = (int*)(S + o_owner2); J.m12 = d_match12 + (size_t)p * cap1; J.bin = (signed char*)(S + o_bin);
         J.nm = d_nmatches + p;
     }
-    ORB_CUDA(cudaMemcpyAsync(W.d, jobs.data(), (size_t)npairs * sizeof(BfJob), cudaMemcpyHostToDevice, st));   // pageable source: staged before return
+    rc = upload_jobs(W, jobs.data(), (size_t)npairs * sizeof(BfJob), st);
+    if (rc != ORB_OK) return rc;
     const BfJob* d_jobs = (const BfJob*)W.d;
     bf_rows_batch_kernel<<<dim3((cap1 + 7) / 8, npairs), 256, 0, st>>>(d_jobs);
     bf_resolve_batch_kernel<<<npairs, SR_THREADS, 0, st>>>(d_jobs, th_dist, nn_ratio, check_orientation);
@@ -1753,8 +1767,8 @@ int orb_search_by_projection_batch_device(int device, const orb_search_params* p
     const size_t o_cidx = c.take(4 * (size_t)cand_cap), o_cdist = c.take(2 * (size_t)cand_cap);
     const size_t per_pair = c.off;
     const size_t jobs_bytes = ((size_t)npairs * sizeof(WindowJob) + 255) & ~(size_t)255;
-    Workspace& W = g_ws;
-    int rc = W.prepare(device, jobs_bytes + per_pair * (size_t)npairs, 256);
+    Workspace& W = g_ws_batch[1];
+    int rc = W.prepare(device, jobs_bytes + per_pair * (size_t)npairs, 256, true);
     if (rc != ORB_OK) return rc;
     cudaStream_t st = (cudaStream_t)cuda_stream;
     std::vector<WindowJob> jobs(npairs);
@@ -1783,7 +1797,8 @@ int orb_search_by_projection_batch_device(int device, const orb_search_params* p
         J.taken = b->d_taken + on; J.moq = b->d_match_of_query + oq; J.tq = b->d_target_query + on;
         J.bin = (signed char*)(S + o_bin); J.asg = (int*)(S + o_asg); J.scal = scal;
     }
-    ORB_CUDA(cudaMemcpyAsync(W.d, jobs.data(), (size_t)npairs * sizeof(WindowJob), cudaMemcpyHostToDevice, st));
+    rc = upload_jobs(W, jobs.data(), (size_t)npairs * sizeof(WindowJob), st);
+    if (rc != ORB_OK) return rc;
     const WindowJob* d_jobs = (const WindowJob*)W.d;
     const size_t rsmem = std::max(sizeof(SrStage) + (size_t)((n + 3) & ~3) * 5, (size_t)9 * ((n + 3) & ~3) + 16);
     static thread_local int attr_dev = -1;
