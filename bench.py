@@ -82,6 +82,27 @@ def clocks_sampler(stop, out, gpu_index):
     p.kill()
 
 
+_CPULIST_CACHE = {}
+
+
+def _gpu_cpulist(gpu_index):
+    if gpu_index in _CPULIST_CACHE:
+        return _CPULIST_CACHE[gpu_index]
+    out = None
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if bus:
+            if len(bus.split(":")[0]) == 8:
+                bus = bus[4:]
+            with open("/sys/bus/pci/devices/%s/local_cpulist" % bus) as fh:
+                out = fh.read().strip()
+    except (OSError, ValueError, subprocess.SubprocessError):
+        out = None
+    _CPULIST_CACHE[gpu_index] = out
+    return out
+
+
 def bind_to_gpu_numa_node(gpu_index):
     """Pin this rank (and therefore the pinned host buffers it allocates next: first touch) to the host cores next to its
     GPU.  With 8 ranks on one box every rank otherwise allocates on whichever socket it was started on and half of the
@@ -105,6 +126,17 @@ def bind_to_gpu_numa_node(gpu_index):
         cpus &= os.sched_getaffinity(0)
         if not cpus:
             return None
+        # ranks whose GPUs hang off the same node share that node's cores: give each its own contiguous slice (>= 4 cores) so that
+        # the caller threads and the driver's copy threads of different ranks do not pile onto the same cores
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        same = [g for g in range(world) if _gpu_cpulist(g) == cpulist] if world > 1 else [gpu_index]
+        if len(same) > 1 and gpu_index in same and os.environ.get("ORB_BENCH_SLICE", "1") != "0":
+            order = sorted(cpus)
+            per = max(4, len(order) // len(same))
+            k = same.index(gpu_index)
+            mine = set(order[(k * per) % len(order):(k * per) % len(order) + per]) or cpus
+            os.sched_setaffinity(0, mine)
+            return "%s (slice %d/%d: %d cores)" % (cpulist, k, len(same), len(mine))
         os.sched_setaffinity(0, cpus)
         return cpulist
     except (OSError, ValueError, subprocess.SubprocessError):
@@ -615,6 +647,41 @@ def main():
     d2h = int(n_h.sum()) * (KP_DTYPE.itemsize + 32) + 4 * B
     stop.set()
 
+    # ---- what the box's host<->device path gives a plain copy loop: the step's own traffic (B frames in, the keypoints + descriptors
+    #      out) as bare cudaMemcpyAsync calls on pinned buffers, 8 chunks each way on two streams, ON ALL RANKS AT THE SAME TIME.
+    #      e2e is reported as a fraction of the frame rate this allows (its ceiling on this box at this N). ----
+    def pcie_probe(reps=6):
+        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        nout = max(d2h, 1 << 20)
+        ho = torch.empty(nout, dtype=torch.uint8).pin_memory()
+        do = torch.empty(nout, dtype=torch.uint8, device=dev)
+        hin = h_frames.view(-1)
+        din = d_frames.view(-1)
+        nin = hin.numel()
+
+        def run(both):
+            torch.cuda.synchronize()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                with torch.cuda.stream(s_in):
+                    c = nin // 8
+                    for k in range(8):
+                        din[k * c:(k + 1) * c].copy_(hin[k * c:(k + 1) * c], non_blocking=True)
+                if both:
+                    with torch.cuda.stream(s_out):
+                        c = nout // 8
+                        for k in range(8):
+                            ho[k * c:(k + 1) * c].copy_(do[k * c:(k + 1) * c], non_blocking=True)
+            torch.cuda.synchronize()
+            return max_over_ranks(time.perf_counter() - t0) / reps
+        run(True)
+        t_in, t_both = run(False), run(True)
+        return {"h2d_gbs_per_gpu": nin / t_in / 1e9, "h2d_gbs_per_gpu_with_d2h": nin / t_both / 1e9, "h2d_gbs_aggregate_with_d2h": world * nin / t_both / 1e9,
+                "frames_per_s_ceiling": world * B / t_both, "bytes_in_per_step": nin, "bytes_out_per_step": nout,
+                "how": "bare cudaMemcpyAsync on pinned buffers, 8 chunks each way, all %d rank(s) simultaneously, slowest rank" % world}
+    probe = pcie_probe()
+
     # ---- Hamming leg: 2000 queries x db_rows rows sharded contiguously over the ranks ----
     ham = None
     if not args.no_hamming:
@@ -925,6 +992,7 @@ def main():
                        "host_affinity": ("rank 0 bound to the cpus next to its GPU: %s" % numa_cpus) if numa_cpus else "unbound"},
             "e2e": {"value": e2e2_value if e2e2_value else e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "callers": 2 if e2e2_value else 1, "one_caller_value": e2e_value,
+                    "copy_probe": probe, "fraction_of_copy_ceiling": (e2e2_value if e2e2_value else e2e_value) / probe["frames_per_s_ceiling"],
                     "note": "every step = one blocking orb_extract_batch of the whole batch (pinned host frames in, pinned host keypoints + "
                             "descriptors out, H2D and D2H inside).  value: the steps are issued by two ORBextractor instances on two host "
                             "threads (the reference's threading model, Frame.cc:79-82; the CPU arm runs one extractor per host thread), so "
