@@ -101,6 +101,15 @@ class Harness:
         L.rh_search_sim3.argtypes = [f32, i32, vp, vp, vp, vp, f32, vp, vp, f32]
         L.rh_fuse.argtypes = [f32, i32, vp, vp, vp, i32, f32]
         L.rh_fuse_sim3.argtypes = [f32, i32, vp, vp, vp, vp, i32, f32, vp]
+        L.rh_voc_load_text.restype = vp
+        L.rh_voc_load_text.argtypes = [C.c_char_p]
+        L.rh_voc_destroy.argtypes = [vp]
+        L.rh_voc_size.argtypes = [vp]
+        L.rh_frame_compute_bow.argtypes = [vp, vp]
+        L.rh_frame_get_bow.argtypes = [vp, vp, vp, i32]
+        L.rh_frame_get_featvec.argtypes = [vp, vp, vp, vp, i32, i32]
+        L.rh_voc_score.restype = C.c_double
+        L.rh_voc_score.argtypes = [vp, vp, vp]
         L.rh_probe_gemm.argtypes = [vp, i32, i32, vp, i32, i32, vp, vp]
         L.rh_probe_norm.restype = C.c_double
         L.rh_probe_norm.argtypes = [vp, i32]
@@ -262,6 +271,17 @@ class Frame:
         node, start, feat = _i32(node), _i32(start), _i32(feat)
         self.H.L.rh_frame_set_featvec(self.h, _p(node), _p(start), _p(feat), len(node))
 
+    def compute_bow(self, voc):
+        """Frame::ComputeBoW with this vocabulary -> (words, values), (node, start, feat)"""
+        self.H.L.rh_frame_compute_bow(self.h, voc.h)
+        n = max(self.N, 1)
+        w, v = np.zeros(n, np.int32), np.zeros(n, np.float64)
+        nb = self.H.L.rh_frame_get_bow(self.h, _p(w), _p(v), n)
+        node, start, feat = np.zeros(n, np.int32), np.zeros(n + 1, np.int32), np.zeros(n, np.int32)
+        nf = self.H.L.rh_frame_get_featvec(self.h, _p(node), _p(start), _p(feat), n, n)
+        assert nb <= n and nf >= 0
+        return (w[:nb].copy(), v[:nb].copy()), (node[:nf].copy(), start[:nf + 1].copy(), feat[:start[nf]].copy())
+
     def set_points(self, pts, idx):
         idx = _i32(idx)
         assert len(idx) == self.N
@@ -275,6 +295,27 @@ class Frame:
     def set_outliers(self, o):
         o = _u8(o)
         self.H.L.rh_frame_set_outliers(self.h, _p(o))
+
+
+class Vocabulary:
+    """ORBVocabulary::loadFromTextFile of one harness library (the reference's DBoW2 template, or this repo's GPU vocabulary)."""
+
+    def __init__(self, H, path):
+        self.H = H
+        self.h = H.L.rh_voc_load_text(path.encode())
+        if not self.h:
+            raise RuntimeError("loadFromTextFile failed: %s" % path)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.H.L.rh_voc_destroy(self.h)
+            self.h = None
+
+    def size(self):
+        return self.H.L.rh_voc_size(self.h)
+
+    def score(self, f1, f2):
+        return self.H.L.rh_voc_score(self.h, f1.h, f2.h)
 
 
 class KeyFrame:

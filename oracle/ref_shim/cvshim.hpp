@@ -379,7 +379,10 @@ public:
     FileNode operator[](const std::string&) const { shim_fail("cv::FileNode"); }
     FileNode operator[](int) const { shim_fail("cv::FileNode"); }
     size_t size() const { return 0; }
-    template <class T> operator T() const { shim_fail("cv::FileNode"); }
+    operator int() const { shim_fail("cv::FileNode"); }
+    operator float() const { shim_fail("cv::FileNode"); }
+    operator double() const { shim_fail("cv::FileNode"); }
+    operator std::string() const { shim_fail("cv::FileNode"); }
     bool empty() const { return true; }
 };
 class FileStorage {

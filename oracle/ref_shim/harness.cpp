@@ -63,6 +63,15 @@ cv::Mat image_from(const uint8_t* img, int w, int h, int stride) {
 
 }  // namespace
 
+/* oracle/_ref only (mono_alloc.cpp): marks the calls during which quadtree list nodes may come from the monotonic arena */
+extern "C" void rh_alloc_scope(int delta) __attribute__((weak));
+namespace {
+struct ExtractScope {
+    ExtractScope() { if (rh_alloc_scope) rh_alloc_scope(+1); }
+    ~ExtractScope() { if (rh_alloc_scope) rh_alloc_scope(-1); }
+};
+}  // namespace
+
 extern "C" {
 
 const char* rh_arm(void) {
@@ -88,7 +97,10 @@ int rh_extract(void* p, const uint8_t* img, int w, int h, int stride, void* kps,
     ORBextractor* ex = (ORBextractor*)p;
     cv::Mat image = image_from(img, w, h, stride), descriptors;
     std::vector<cv::KeyPoint> keys;
-    (*ex)(image, cv::Mat(), keys, descriptors);
+    {
+        ExtractScope scope;
+        (*ex)(image, cv::Mat(), keys, descriptors);
+    }
     const int n = (int)keys.size();
     if (n > cap) return -n;
     if (n) {
@@ -131,12 +143,14 @@ static void* frame_storage(const float* k4, float bf) {
 /* Frame(imGray, timeStamp, extractor, voc, K, distCoef, bf, thDepth)  (Frame.cc:178-236) */
 void* rh_frame_mono(void* ex, const uint8_t* img, int w, int h, int stride, const float* k4, float bf, float th_depth) {
     cv::Mat K = make_K(k4), dist = cv::Mat::zeros(4, 1, CV_32F), im = image_from(img, w, h, stride);
+    ExtractScope scope;
     return new (frame_storage(k4, bf)) Frame(im, 0.0, (ORBextractor*)ex, (ORBVocabulary*)nullptr, K, dist, bf, th_depth);
 }
 /* Frame(imLeft, imRight, ...)  (Frame.cc:60-128): two extractor threads + ComputeStereoMatches */
 void* rh_frame_stereo(void* exl, void* exr, const uint8_t* iml, const uint8_t* imr, int w, int h, int stride, const float* k4, float bf,
                       float th_depth) {
     cv::Mat K = make_K(k4), dist = cv::Mat::zeros(4, 1, CV_32F), l = image_from(iml, w, h, stride), r = image_from(imr, w, h, stride);
+    ExtractScope scope;
     return new (frame_storage(k4, bf)) Frame(l, r, 0.0, (ORBextractor*)exl, (ORBextractor*)exr, (ORBVocabulary*)nullptr, K, dist, bf, th_depth);
 }
 /* a Frame from given (undistorted) keypoints: what the constructors leave behind, without an image.  Scale tables come
@@ -211,6 +225,46 @@ void rh_frame_set_featvec(void* fp, const int32_t* node, const int32_t* start, c
     for (int j = 0; j < nnodes; ++j)
         for (int k = start[j]; k < start[j + 1]; ++k) F->mFeatVec.addFeature((DBoW2::NodeId)node[j], (unsigned)feat[k]);
 }
+
+/* ------------------------------------------------------------ ORBVocabulary --------------------------------------- */
+/* System.cc:  mpVocabulary->loadFromTextFile(strVocFile)  (TemplatedVocabulary.h:1351-1441) */
+void* rh_voc_load_text(const char* path) {
+    ORBVocabulary* v = new ORBVocabulary();
+    if (!v->loadFromTextFile(path)) { delete v; return nullptr; }
+    return v;
+}
+void rh_voc_destroy(void* v) { delete (ORBVocabulary*)v; }
+int rh_voc_size(void* v) { return (int)((ORBVocabulary*)v)->size(); }
+/* Frame::ComputeBoW (Frame.cc:428-435): transform(vCurrentDesc, mBowVec, mFeatVec, 4) */
+void rh_frame_compute_bow(void* fp, void* voc) {
+    Frame* F = (Frame*)fp;
+    F->mpORBvocabulary = (ORBVocabulary*)voc;
+    F->mBowVec.clear();
+    F->mFeatVec.clear();
+    F->ComputeBoW();
+}
+int rh_frame_get_bow(void* fp, int32_t* word, double* value, int cap) {
+    Frame* F = (Frame*)fp;
+    int n = 0;
+    for (DBoW2::BowVector::const_iterator it = F->mBowVec.begin(); it != F->mBowVec.end(); ++it, ++n)
+        if (n < cap) { word[n] = (int32_t)it->first; value[n] = it->second; }
+    return n;
+}
+/* CSR: node ids ascending, start[nnodes + 1], feat; returns the node count (-1 when a capacity is too small) */
+int rh_frame_get_featvec(void* fp, int32_t* node, int32_t* start, int32_t* feat, int cap_nodes, int cap_feat) {
+    Frame* F = (Frame*)fp;
+    int n = 0, m = 0;
+    if (cap_nodes > 0) start[0] = 0;
+    for (DBoW2::FeatureVector::const_iterator it = F->mFeatVec.begin(); it != F->mFeatVec.end(); ++it, ++n) {
+        if (n >= cap_nodes || m + (int)it->second.size() > cap_feat) return -1;
+        node[n] = (int32_t)it->first;
+        for (size_t k = 0; k < it->second.size(); ++k) feat[m++] = (int32_t)it->second[k];
+        start[n + 1] = m;
+    }
+    return n;
+}
+/* KeyFrameDatabase's similarity: mpVoc->score(v1, v2) (L1Scoring::score, ScoringObject.cpp:23-66) */
+double rh_voc_score(void* voc, void* f1, void* f2) { return ((ORBVocabulary*)voc)->score(((Frame*)f1)->mBowVec, ((Frame*)f2)->mBowVec); }
 
 /* ------------------------------------------------------------- MapPoints ------------------------------------------ */
 /* n map points: world position, mean viewing direction, representative descriptor, Observations(), isBad(), the scale

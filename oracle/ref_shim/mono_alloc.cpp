@@ -12,7 +12,8 @@
  * (tests/test_ref_pin.py); with it switched off (rh_set_monotonic_alloc(0): plain malloc) the differences must be
  * confined to the order inside a level and to levels whose cut fell inside a tie group.
  *
- * Linked into liborb_ref.so with -Bsymbolic: only that library's own allocations come here.
+ * Linked into liborb_ref.so with -Bsymbolic: only that library's own allocations come here, and the arena is only used while a
+ * harness call that runs the extractor is in flight (rh_alloc_scope).
  */
 #include <atomic>
 #include <cstddef>
@@ -35,6 +36,7 @@ const int kSlots = 128;
 
 char* g_base = nullptr;
 std::atomic<int> g_on{1};
+std::atomic<int> g_scope{0};   // > 0 while a harness call that runs ORBextractor::operator() is in flight (rh_alloc_scope)
 std::atomic<long> g_served{0};
 std::atomic<unsigned char> g_used[kSlots];
 
@@ -57,7 +59,7 @@ char* arena() {
 inline bool in_arena(void* p) { return g_base && (char*)p >= g_base && (char*)p < g_base + kSlot * kSlots; }
 
 void* alloc(size_t n) {
-    if (n == kNode && g_on.load(std::memory_order_relaxed)) {
+    if (n == kNode && g_on.load(std::memory_order_relaxed) && g_scope.load(std::memory_order_relaxed) > 0) {
         if (!g_base) g_base = arena();
         Slot& s = t_slot;
         if (g_base && s.id < 0) {
@@ -104,6 +106,9 @@ void operator delete(void* p, size_t) noexcept { dealloc(p); }
 void operator delete[](void* p, size_t) noexcept { dealloc(p); }
 
 extern "C" {
+/* The arena only serves allocations made while an extraction is running: a same-sized allocation elsewhere (a std::string
+ * buffer, say) may be released inside libstdc++.so, whose operator delete knows nothing of the arena. */
+void rh_alloc_scope(int delta) { g_scope.fetch_add(delta); }
 void rh_set_monotonic_alloc(int on) { g_on.store(on ? 1 : 0); }
 long rh_monotonic_alloc_served(void) { return g_served.load(); }
 }

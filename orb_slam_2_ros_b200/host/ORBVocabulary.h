@@ -14,6 +14,17 @@
 
 struct orb_voc;
 
+// The header this file replaces pulls in DBoW2/TemplatedVocabulary.h, whose line 36 is a global `using namespace std;` — and the
+// rest of ORB-SLAM2 has come to depend on it (Frame.h:91 `vector<size_t>`, Frame.cc:79 `thread`, ORBmatcher.h:70 `pair<>`, ...).
+// A drop-in replacement has to keep that side effect or those files stop compiling.
+using namespace std;
+
+// DBoW2::BowVector / FeatureVector: the reference's own headers when they are on the include path (a real ORB-SLAM2 tree),
+// else the two std::map subclasses they are (BowVector.h:56, FeatureVector.h:21)
+#if __has_include("Thirdparty/DBoW2/DBoW2/BowVector.h")
+#include "Thirdparty/DBoW2/DBoW2/BowVector.h"
+#include "Thirdparty/DBoW2/DBoW2/FeatureVector.h"
+#else
 namespace DBoW2 {
 typedef unsigned int WordId;
 typedef double WordValue;
@@ -21,6 +32,7 @@ typedef unsigned int NodeId;
 class BowVector : public std::map<WordId, WordValue> {};
 class FeatureVector : public std::map<NodeId, std::vector<unsigned int> > {};
 }  // namespace DBoW2
+#endif
 
 namespace ORB_SLAM2 {
 

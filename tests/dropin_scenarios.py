@@ -354,3 +354,32 @@ def dense_ties(H, seed, n=1500, clusters=40):
     ni, m12, prev2 = m.search_initialization(FA, FB, prev, 60)
     out["init_n"], out["init_m12"], out["init_prev"] = np.int64(ni), m12, prev2
     return out
+
+
+def write_voc_file(path, seed=3, k=8, L=3):
+    """A regular synthetic vocabulary in the reference's text format WITHOUT a trailing newline: the reference's
+    `while(!f.eof())` loader (TemplatedVocabulary.h:1396-1420) would turn the empty string after a final newline into a
+    phantom extra child of the root (INTEGRATION.md pin (v))."""
+    parent, is_leaf, desc, weight = synth.synth_vocabulary(seed, k, L)
+    synth.write_vocabulary_text(path, k, L, 0, 0, parent, is_leaf, desc, weight)
+    txt = open(path).read().rstrip("\n")
+    open(path, "w").write(txt)
+    return parent, is_leaf, desc, weight
+
+
+def bag_of_words(H, seed, voc_path):
+    """ORBVocabulary::loadFromTextFile + Frame::ComputeBoW on two extracted frames + score + SearchByBoW over the REAL
+    feature vectors."""
+    W = World(H, seed)
+    voc = orb_ref.Vocabulary(H, voc_path)
+    (wa, va), fva = W.FA.compute_bow(voc)
+    (wb, vb), fvb = W.FB.compute_bow(voc)
+    out = dict(nwords=np.int64(voc.size()), words_a=wa, values_a=va, node_a=fva[0], start_a=fva[1], feat_a=fva[2],
+               words_b=wb, values_b=vb, node_b=fvb[0], start_b=fvb[1], feat_b=fvb[2], score=np.float64(voc.score(W.FA, W.FB)))
+    rng = np.random.default_rng(seed + 30)
+    W.FA.set_pose(pose())
+    kf = orb_ref.KeyFrame(W.FA)
+    kf.set_points(W.pts, np.where(rng.random(W.FA.N) < 0.85, np.arange(W.FA.N), -1).astype(np.int32))
+    n, m = orb_ref.Matcher(H, 0.75, True).search_bow_kf_frame(kf, W.FB, W.pts)
+    out["bow_n"], out["bow_matches"] = np.int64(n), m
+    return out

@@ -151,3 +151,15 @@ def test_fuse_sim3(arms, seed, scale):
 def test_dense_ties_and_chains(arms, seed):
     r = both(arms, S.dense_ties, seed)
     assert r["last_n"] > 500
+
+
+def test_vocabulary_compute_bow_and_search(arms, tmp_path):
+    """ORBVocabulary (the reference's DBoW2 template vs this repo's GPU vocabulary behind the same class name):
+    loadFromTextFile, Frame::ComputeBoW (BowVector doubles bit for bit, FeatureVector), score, SearchByBoW on the result."""
+    path = str(tmp_path / "voc.txt")
+    S.write_voc_file(path, 3, 8, 3)
+    r = both(arms, S.bag_of_words, 5, path)
+    assert r["nwords"] == 8 ** 3 and len(r["words_a"]) > 100 and r["bow_n"] > 20
+    path2 = str(tmp_path / "voc2.txt")
+    S.write_voc_file(path2, 9, 10, 4)
+    both(arms, S.bag_of_words, 6, path2)

@@ -156,3 +156,19 @@ def test_reference_grid_equals_oracle(H, oracle):
         assert np.array_equal(a, b)
         total += len(a)
     assert total > 1000
+
+
+def test_reference_dbow2_equals_oracle(H, oracle, tmp_path):
+    """The reference's own DBoW2 (TemplatedVocabulary<FORB>: loadFromTextFile + transform through Frame::ComputeBoW) == the
+    oracle's restatement (oracle/orb_oracle_bow.cpp): words, weights (doubles, bit for bit), feature vector."""
+    path = str(tmp_path / "voc.txt")
+    S.write_voc_file(path, 3, 8, 3)
+    r = S.bag_of_words(H, 5, path)
+    ov = oracle.Vocabulary.load_text(path)
+    W = S.World(H, 5)
+    for tag, d in (("a", W.a), ("b", W.b)):
+        (w, v), (node, start, feat) = ov.transform(d["desc"], 4)
+        assert np.array_equal(w, r["words_" + tag])
+        assert np.array_equal(np.asarray(v, np.float64).view(np.uint64), r["values_" + tag].view(np.uint64))
+        assert np.array_equal(node, r["node_" + tag]) and np.array_equal(start, r["start_" + tag]) and np.array_equal(feat, r["feat_" + tag])
+    assert r["bow_n"] > 20

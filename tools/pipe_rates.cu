@@ -2,6 +2,7 @@
 // (sm_100a).  Prints warp-instructions per clock per SM for every op and for a few two-pipe mixes.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/_build/pipe_rates tools/pipe_rates.cu
 #include <cstdio>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #define ITERS 4096
@@ -26,6 +27,12 @@ __device__ __forceinline__ void op(unsigned& a, unsigned& b, unsigned c) {
     else if (OP == 14) { a = __vmaxs2(a, c); b = (b & a) ^ c; }   // VIMNMX.S16x2 + LOP3 pair
     else if (OP == 15) a = __vabsdiffu4(a, c);                    // VABSDIFF4 alone (dependent chain per register)
     else if (OP == 16) a = __dp2a_lo(a, c, b);                    // IDP.2A
+    else if (OP == 17) { __half2 x = *reinterpret_cast<__half2*>(&a), y = *reinterpret_cast<__half2*>(&b); x = __hmax2(x, y); a = *reinterpret_cast<unsigned*>(&x); b += c; }   // HMNMX2 (+ IADD keeps the operand changing)
+    else if (OP == 18) { a = __vmaxs2(a, b); b += c; }            // VIMNMX.S16x2 (+ IADD), same shape as 17
+    else if (OP == 19) { __half2 x = *reinterpret_cast<__half2*>(&a), y = *reinterpret_cast<__half2*>(&b); x = __hmax2(x, y); a = *reinterpret_cast<unsigned*>(&x); b = __vmaxs2(b, c) ; }   // HMNMX2 + VIMNMX.S16x2 pair
+    else if (OP == 20) { a = __vmaxs2(a, b); b = __vmins2(b, c); }   // two VIMNMX.S16x2
+    else if (OP == 21) { __half2 x = *reinterpret_cast<__half2*>(&a), y = *reinterpret_cast<__half2*>(&b), z = *reinterpret_cast<const __half2*>(&c); x = __hmax2(x, y); y = __hmin2(y, z); a = *reinterpret_cast<unsigned*>(&x); b = *reinterpret_cast<unsigned*>(&y); }   // two HMNMX2
+    else if (OP == 22) { __half2 x = *reinterpret_cast<__half2*>(&a), y = *reinterpret_cast<__half2*>(&b); x = __hmax2(x, y); a = *reinterpret_cast<unsigned*>(&x); b = b * c + a; }   // HMNMX2 + IMAD pair
 }
 
 template <int OP>
@@ -70,5 +77,7 @@ int main() {
     run<8>("VIMNMX.S32", 1); run<3>("PRMT", 1); run<6>("SHF.R.W", 1); run<9>("IADD3", 1); run<4>("IMAD", 1); run<5>("IDP.4A", 1);
     run<16>("IDP.2A", 1); run<10>("POPC+IADD", 2); run<11>("LOP3+IMAD", 2); run<12>("VIMNMX.S16x2+IMAD", 2);
     run<13>("VABSDIFF4+IMAD", 2); run<14>("VIMNMX.S16x2+LOP3", 2);
+    run<17>("HMNMX2+IADD", 2); run<18>("VIMNMX.S16x2+IADD", 2); run<19>("HMNMX2+VIMNMX.S16x2", 2); run<20>("2x VIMNMX.S16x2", 2); run<21>("2x HMNMX2", 2);
+    run<22>("HMNMX2+IMAD", 2);
     return 0;
 }
