@@ -110,8 +110,28 @@ def shifted_frame(img, dx, dy, seed, renoise_frac=0.02):
     return np.clip(out, 0, 255).astype(np.uint8)
 
 
-def synth_stereo_pair(seed, w=1241, h=376, dmin=2, dmax=60):
-    """Left frame + right frame warped by a piece-wise constant integer disparity field (right(x) = left(x+d))."""
+def synth_stereo_pair(seed, w=1241, h=376, dmin=2, dmax=60, half_pixel=False):
+    """Left frame + right frame warped by a piece-wise constant integer disparity field (right(x) = left(x+d)).
+    half_pixel (second variant): the scene is rendered at 2x horizontal resolution, the right view is
+    displaced by an ODD number of half pixels and both views are box-filtered down by 2, so that the true disparities are
+    d + 0.5 and the parabola sub-pixel fit of ComputeStereoMatches (Frame.cc:634-641) has something to find."""
+    if half_pixel:
+        wide = synth_frame(seed, 2 * w, h, n_rect=420, n_tri=200)
+        rng = _rng(seed ^ 0x57E2E1)
+        disp2 = np.empty((h, 2 * w), np.int32)                       # disparity in half pixels, odd
+        nby, nbx = 4, 6
+        ys = np.linspace(0, h, nby + 1).astype(int)
+        xs = np.linspace(0, 2 * w, nbx + 1).astype(int)
+        for by in range(nby):
+            for bx in range(nbx):
+                disp2[ys[by]:ys[by + 1], xs[bx]:xs[bx + 1]] = 2 * int(rng.integers(dmin, dmax + 1)) + 1
+        xx = np.clip(np.arange(2 * w)[None, :] + disp2, 0, 2 * w - 1)
+        wide_r = np.take_along_axis(wide, xx, axis=1)
+        down = lambda a: ((a[:, 0::2].astype(np.int32) + a[:, 1::2].astype(np.int32) + 1) >> 1)
+        left = down(wide).astype(np.uint8)
+        nz = rng.integers(-2, 3, size=(h, w))
+        right = np.clip(down(wide_r) + nz, 0, 255).astype(np.uint8)
+        return left, right, disp2[:, 0::2].astype(np.float32) / 2
     left = synth_frame(seed, w, h, n_rect=420, n_tri=200)
     rng = _rng(seed ^ 0x57E2E0)
     right = np.empty_like(left)

@@ -106,10 +106,10 @@ def extraction(H, seed, w, h, nfeatures, nlevels):
     return out
 
 
-def stereo_frame(H, seed, w=1241, h=376, nfeatures=2000):
+def stereo_frame(H, seed, w=1241, h=376, nfeatures=2000, half_pixel=False):
     H.reset_calibration()
     exl, exr = H.extractor(nfeatures, 1.2, 8, 20, 7), H.extractor(nfeatures, 1.2, 8, 20, 7)
-    left, right = synth.synth_stereo_pair(seed, w, h)[:2]
+    left, right = synth.synth_stereo_pair(seed, w, h, half_pixel=half_pixel)[:2]
     F = orb_ref.Frame.stereo(H, exl, exr, left, right, K_KITTI, BF_KITTI)
     d = F.get()
     kr, dr = F.get_right()

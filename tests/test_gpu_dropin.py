@@ -76,6 +76,16 @@ def test_stereo_frame_small(arms):
     both(arms, S.stereo_frame, 1, 640, 240, 800)
 
 
+@pytest.mark.parametrize("seed", [3, 4])
+def test_stereo_frame_half_pixel_disparities(arms, seed):
+    """SURVEY.md §8d C3, second variant: true disparities of d + 0.5 px exercise the parabola sub-pixel fit (Frame.cc:634-641)."""
+    r = both(arms, S.stereo_frame, seed, half_pixel=True)
+    ok = r["depth"] > 0
+    assert ok.sum() > 200
+    frac = np.abs((r["kps"]["x"][ok] - r["u_right"][ok]) % 1.0 - 0.5)
+    assert np.median(frac) < 0.3          # the recovered disparities cluster around the half-pixel offsets
+
+
 @pytest.mark.parametrize("seed", [0, 1])
 def test_features_in_area_of_extracted_frames(arms, seed):
     both(arms, S.features_in_area, seed)

@@ -495,3 +495,34 @@ def test_complementary_descriptor_distance_256(oracle):
     nm_g, m_g = ORBmatcher(0.6, False).MatchBruteForce(q, np.zeros(1, np.float32), np.concatenate([comp] * 3), np.zeros(3, np.float32), 256)
     nm_o, m_o = oracle.match_bruteforce(q, np.zeros(1, np.float32), np.concatenate([comp] * 3), np.zeros(3, np.float32), 256, 0.6, False)
     assert nm_g == nm_o == 0 and np.array_equal(m_g, m_o)
+
+
+@pytest.mark.parametrize("style", ["relocalisation_64", "relocalisation_100", "loop_closure"])
+def test_search_by_projection_reloc_and_loop_parameterisations(oracle, frame_pair, style):
+    """The array-level form of the two remaining SearchByProjection overloads, GPU vs oracle:
+    relocalisation refinement (ORBmatcher.cc:1474-1601): best only <= ORBdist (64 / 100), ANY pre-assigned keypoint hidden
+    (taken = mvpMapPoints[i2] != NULL), a non-empty sAlreadyFound (q_valid), levels [l-1, l+1], no stereo gate, rotation histogram;
+    loop closure (ORBmatcher.cc:291-404): best only <= TH_LOW, pre-filled vpMatched hides keypoints, levels [l-1, l], no histogram.
+    (tests/test_gpu_dropin.py runs the same two overloads through the reference's own signatures against the reference's own code.)"""
+    from orb_slam_2_ros_b200 import ORBmatcher
+    from orb_slam_2_ros_b200.matcher import MODE_TRACK_LAST
+    ka, da, kb, db, sf = frame_pair
+    rng = np.random.default_rng(23)
+    n, nq = len(kb), len(ka)
+    q_u = (ka["x"] + np.float32(3)).astype(np.float32); q_v = (ka["y"] - np.float32(2)).astype(np.float32)
+    loop = style == "loop_closure"
+    th, th_dist, ori = (10.0, 50, False) if loop else ((10.0 if style.endswith("100") else 3.0), int(style.split("_")[1]), True)
+    q_radius = (np.float32(th) * sf[ka["octave"]]).astype(np.float32)
+    q_min, q_max = ka["octave"] - 1, ka["octave"] + (0 if loop else 1)
+    q_valid = (rng.random(nq) > 0.2).astype(np.uint8)            # sAlreadyFound / spAlreadyFound / bad points
+    taken0 = (rng.random(n) < 0.15).astype(np.uint8)             # keypoints that already hold a point
+    bounds = (0.0, 0.0, 640.0, 480.0)
+    t_o, t_g = taken0.copy(), taken0.copy()
+    grid = oracle.Grid(kb, *bounds)
+    nm_o, moq_o, tq_o = oracle.search_by_projection(oracle.MODE_TRACK_LAST, grid, db, None, t_o, q_u, q_v, q_radius, q_min, q_max, da, None, None,
+                                                    ka["angle"], q_valid, None, th_dist=th_dist, nn_ratio=0.9, check_orientation=ori)
+    nm_g, moq_g, tq_g = ORBmatcher(0.9, ori).SearchByProjection(MODE_TRACK_LAST, kb, db, bounds, t_g, q_u, q_v, q_radius, q_min, q_max, da, None, None,
+                                                                None, ka["angle"], q_valid, None, th_dist=th_dist)
+    assert nm_o > 50, "test input produced too few matches (%d)" % nm_o
+    assert nm_g == nm_o and np.array_equal(moq_g, moq_o) and np.array_equal(tq_g, tq_o) and np.array_equal(t_g, t_o)
+    assert not np.any((taken0 == 1) & (tq_g >= 0))               # a hidden keypoint never receives a match

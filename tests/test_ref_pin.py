@@ -127,11 +127,12 @@ def test_shim_float_algebra_matches_cv2(H):
         assert H.L.rh_probe_dot(v.ctypes.data, w.ctypes.data, 3) == float(np.dot(v.astype(np.float64), w.astype(np.float64)))
 
 
-@pytest.mark.parametrize("seed", [0, 2])
-def test_reference_stereo_equals_oracle(H, oracle, seed):
-    """Unmodified Frame::ComputeStereoMatches (through the reference's stereo Frame constructor) == oracle."""
-    r = S.stereo_frame(H, seed)
-    left, right = synth.synth_stereo_pair(seed, 1241, 376)[:2]
+@pytest.mark.parametrize("seed,half", [(0, False), (2, False), (3, True)])
+def test_reference_stereo_equals_oracle(H, oracle, seed, half):
+    """Unmodified Frame::ComputeStereoMatches (through the reference's stereo Frame constructor) == oracle; integer and
+    half-pixel disparity fields."""
+    r = S.stereo_frame(H, seed, half_pixel=half)
+    left, right = synth.synth_stereo_pair(seed, 1241, 376, half_pixel=half)[:2]
     exl, exr = oracle.Extractor(2000, 1.2, 8, 20, 7), oracle.Extractor(2000, 1.2, 8, 20, 7)
     kl, dl = exl.extract(left)
     kr, dr = exr.extract(right)
@@ -172,3 +173,39 @@ def test_reference_dbow2_equals_oracle(H, oracle, tmp_path):
         assert np.array_equal(np.asarray(v, np.float64).view(np.uint64), r["values_" + tag].view(np.uint64))
         assert np.array_equal(node, r["node_" + tag]) and np.array_equal(start, r["start_" + tag]) and np.array_equal(feat, r["feat_" + tag])
     assert r["bow_n"] > 20
+
+
+def test_reference_matchers_equal_oracle(H, oracle):
+    """The matcher routines whose inputs need no projection algebra, reference code vs oracle restatement on the same frames:
+    SearchForInitialization (ORBmatcher.cc:406-521) and both SearchByBoW overloads (:160-289, :524-657)."""
+    # --- SearchForInitialization
+    W = S.World(H, 6, nfeatures=2000)
+    prev = np.stack([W.a["kps_un"]["x"], W.a["kps_un"]["y"]], 1)
+    n_ref, m_ref, prev_ref = orb_ref.Matcher(H, 0.9, True).search_initialization(W.FA, W.FB, prev, 100)
+    grid = oracle.Grid(W.b["kps_un"], *H.bounds())
+    n1 = W.FA.N
+    zeros = np.zeros(n1, np.int32)
+    taken = np.zeros(W.FB.N, np.uint8)
+    n_o, m_o, _ = oracle.search_by_projection(oracle.MODE_INITIALIZATION, grid, W.b["desc"], None, taken, prev[:, 0].copy(), prev[:, 1].copy(),
+                                             np.full(n1, 100, np.float32), zeros, zeros, W.a["desc"], q_angle=W.a["kps_un"]["angle"],
+                                             q_valid=(W.a["kps_un"]["octave"] <= 0).astype(np.uint8), th_dist=50, nn_ratio=0.9, check_orientation=True)
+    assert n_ref > 50 and n_ref == n_o and np.array_equal(m_ref, m_o)
+    # --- SearchByBoW, both overloads, over a synthetic FeatureVector
+    W = S.World(H, 5)
+    rng = np.random.default_rng(21)
+    fva, fvb = W.grid_featvec(W.a), W.grid_featvec(W.b, shift=(3, -2))
+    W.FA.set_featvec(*fva); W.FB.set_featvec(*fvb)
+    W.FA.set_pose(S.pose()); W.FB.set_pose(S.pose())
+    ia = np.where(rng.random(W.FA.N) < 0.8, np.arange(W.FA.N), -1).astype(np.int32)
+    ib = np.where(rng.random(W.FB.N) < 0.8, rng.integers(0, W.pts.n, W.FB.N), -1).astype(np.int32)
+    kf1, kf2 = orb_ref.KeyFrame(W.FA), orb_ref.KeyFrame(W.FB)
+    kf1.set_points(W.pts, ia); kf2.set_points(W.pts, ib, observe=False)
+    good = lambda idx: ((idx >= 0) & (W.bad[np.maximum(idx, 0)] == 0)).astype(np.uint8)
+    n_ref, m_ref = orb_ref.Matcher(H, 0.75, True).search_bow_kf_frame(kf1, W.FB, W.pts)
+    m12, m21, n_o = oracle.search_by_bow(W.a["desc"], W.a["kps_un"]["angle"], good(ia), fva, W.b["desc"], W.b["kps"]["angle"], None, fvb, 50, False, 0.75, True)
+    assert n_ref > 100 and n_ref == n_o
+    assert np.array_equal(m_ref, np.where(m21 >= 0, ia[np.maximum(m21, 0)], -1))
+    n_ref, m_ref = orb_ref.Matcher(H, 0.75, True).search_bow_kf_kf(kf1, kf2, W.pts)
+    m12, m21, n_o = oracle.search_by_bow(W.a["desc"], W.a["kps_un"]["angle"], good(ia), fva, W.b["desc"], W.b["kps_un"]["angle"], good(ib), fvb, 50, True, 0.75, True)
+    assert n_ref > 50 and n_ref == n_o
+    assert np.array_equal(m_ref, np.where(m12 >= 0, ib[np.maximum(m12, 0)], -1))
