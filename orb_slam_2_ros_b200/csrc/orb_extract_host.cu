@@ -40,12 +40,12 @@ void free_geometry_buffers(orb_ctx* c) {
     c->graph_warm_w = c->graph_warm_h = 0; c->graph_warm_fmt = -1;
     cudaFree(c->d_in); cudaFree(c->d_pyr); cudaFree(c->d_blur); cudaFree(c->d_corners); cudaFree(c->d_node_of_key);
     cudaFree(c->d_corner_count); cudaFree(c->d_kept); cudaFree(c->d_kept_count); cudaFree(c->d_taps);
-    cudaFree(c->d_wtaps); cudaFree(c->d_strips); cudaFree(c->d_tmaps); cudaFree(c->d_kps_out); cudaFree(c->d_desc_out); cudaFree(c->d_n_out);
+    cudaFree(c->d_wtaps); cudaFree(c->d_strips); cudaFree(c->d_tmaps); cudaFree(c->d_btmaps); cudaFree(c->d_kps_out); cudaFree(c->d_desc_out); cudaFree(c->d_n_out);
     cudaFreeHost(c->h_kps); cudaFreeHost(c->h_desc); cudaFreeHost(c->h_n); cudaFreeHost(c->h_in);
     c->h_out_cap = 0;
     c->d_in = c->d_pyr = c->d_blur = nullptr; c->d_corners = nullptr; c->d_node_of_key = nullptr;
     c->d_corner_count = c->d_kept_count = nullptr; c->d_kept = nullptr; c->d_taps = nullptr;
-    c->d_wtaps = nullptr; c->d_strips = nullptr; c->d_tmaps = nullptr; c->d_kps_out = nullptr; c->d_desc_out = nullptr; c->d_n_out = nullptr;
+    c->d_wtaps = nullptr; c->d_strips = nullptr; c->d_tmaps = nullptr; c->d_btmaps = nullptr; c->d_kps_out = nullptr; c->d_desc_out = nullptr; c->d_n_out = nullptr;
     c->h_kps = nullptr; c->h_desc = nullptr; c->h_n = nullptr; c->h_in = nullptr;
     c->in_bytes = c->h_in_bytes = 0; c->out_cap = 0;
     c->have_geom = false;
@@ -281,6 +281,25 @@ int build_geometry(orb_ctx* c, int w, int h) {
                 ORB_CUDA(cudaMalloc(&c->d_tmaps, sizeof(FastTmaps)));
                 ORB_CUDA(cudaMemcpyAsync(c->d_tmaps, &c->tmaps, sizeof(FastTmaps), cudaMemcpyHostToDevice, c->stream));
             }
+            // the blurred levels, for the 64 x 39-byte tap window of one keypoint (orient_describe_kernel): rows / bytes past the
+            // level are zero-filled by the TMA unit and never addressed by a tap
+            FastTmaps bt;
+            for (int l = 0; l < g.nlevels && ok; ++l) {
+                const LevelGeom& L = g.lv[l];
+                const cuuint64_t dims[3] = {(cuuint64_t)L.bpitch, (cuuint64_t)L.h, (cuuint64_t)F};
+                const cuuint64_t strides[2] = {(cuuint64_t)L.bpitch, (cuuint64_t)L.bframe_stride};
+                const cuuint32_t box[3] = {ORB_TAP_BOX_W, ORB_TAP_BOX_H, 1};
+                const cuuint32_t estr[3] = {1, 1, 1};
+                const CUresult r = ((EncodeFn)fn)(&bt.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, c->d_blur + L.bbase, dims, strides, box, estr,
+                                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                ok = (r == CUDA_SUCCESS);
+            }
+            if (ok && !getenv("ORB_B200_NO_TAP_TMA")) {
+                ORB_CUDA(cudaMalloc(&c->d_btmaps, sizeof(FastTmaps)));
+                ORB_CUDA(cudaMemcpyAsync(c->d_btmaps, &bt, sizeof(FastTmaps), cudaMemcpyHostToDevice, c->stream));
+                ORB_CUDA(cudaStreamSynchronize(c->stream));   // bt is a local
+            }
             c->use_tma = ok;
         } else {
             cudaGetLastError();
@@ -421,16 +440,18 @@ static int ensure_device(orb_ctx* c) {
         // IC_Angle (ORBextractor.cc:77-104) as word dot products: for patch alignment a, item = row*9 + word holds the
         // signed u-weights of the word's 4 bytes (0 outside the circular patch, umax from :463-478) and the 0/1 mask
         static const int umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
-        std::vector<uint2> tab(4 * 288);
+        // (second word: the row offset v = r - 15 times the mask, as signed bytes, so that m01 is a dot product too).  33 rows of
+        // 9 words: rows 31 and 32 are zero (the kernel walks 11 steps of 3 rows)
+        std::vector<uint2> tab(4 * 297);
         for (int a = 0; a < 4; ++a)
-            for (int item = 0; item < 288; ++item) {
+            for (int item = 0; item < 297; ++item) {
                 const int r = item / 9, wi = item % 9, v = r - ORB_HALF_PATCH;
-                unsigned wu = 0, wm = 0;
+                unsigned wu = 0, wv = 0;
                 for (int b = 0; b < 4; ++b) {
                     const int u = 4 * wi + b - a - ORB_HALF_PATCH;
-                    if (r <= 30 && abs(u) <= umax[abs(v)]) { wu |= (unsigned)(uint8_t)(int8_t)u << (8 * b); wm |= 1u << (8 * b); }
+                    if (r <= 30 && abs(u) <= umax[abs(v)]) { wu |= (unsigned)(uint8_t)(int8_t)u << (8 * b); wv |= (unsigned)(uint8_t)(int8_t)v << (8 * b); }
                 }
-                tab[a * 288 + item] = make_uint2(wu, wm);
+                tab[a * 297 + item] = make_uint2(wu, wv);
             }
         ORB_CUDA(cudaMalloc(&c->d_mom_tab, sizeof(uint2) * tab.size()));
         ORB_CUDA(cudaMemcpy(c->d_mom_tab, tab.data(), sizeof(uint2) * tab.size(), cudaMemcpyHostToDevice));

@@ -316,12 +316,37 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 #define OD_KPW 4                       // keypoints per warp
 #endif
 #define OD_KPB (OD_WARPS * OD_KPW)     // keypoints per CTA (== 32: one lane of warp 0 per keypoint in phase 2)
-#define OD_ITEMS 288                   // 31 patch rows x 9 aligned words, padded to 9 x 32 lanes
+#define OD_ITEMS 297                   // 33 rows x 9 aligned words (31 patch rows + 2 all-zero rows): 11 steps of 27 lanes
 #define OD_TAPR 19                     // |tap offset| <= 19 after rotation
 #ifndef OD_WPITCH
 #define OD_WPITCH 80                    // bytes per row of the staged tap window: four 16-byte chunks hold columns px-19 .. px+19; 80 (not 64) spreads the rows over the banks
 #endif
-#define OD_WBYTES ((2 * OD_TAPR + 1) * OD_WPITCH)
+#define OD_WBYTES ((((2 * OD_TAPR + 1) * OD_WPITCH) + 127) / 128 * 128)   // per-warp window, a multiple of 128 bytes (TMA destination alignment)
+
+// ---- TMA (cp.async.bulk.tensor) + mbarrier plumbing for the tap window ----
+__device__ __forceinline__ unsigned od_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void od_mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(od_smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void od_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(od_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void od_mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "OD_WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra OD_WAIT_DONE;\n"
+        "bra OD_WAIT_LOOP;\n"
+        "OD_WAIT_DONE:\n"
+        "}\n" ::"r"(od_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void od_tma_load_3d(void* dst, const CUtensorMap* map, int x, int y, int z, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(od_smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(od_smem_u32(bar)) : "memory");
+}
 
 __device__ __forceinline__ int dp4a_su(unsigned a_signed, unsigned b_unsigned, int c) {
     int d;
@@ -347,9 +372,13 @@ __global__ void __launch_bounds__(OD_WARPS * 32, OD_MINB)
 orient_describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur,
                        const unsigned long long* __restrict__ kept, const int* __restrict__ kept_count,
                        const uint2* __restrict__ mom_tab, orb_kp* __restrict__ kps_out, uint8_t* __restrict__ desc_out,
-                       int cap, int* __restrict__ n_out, const __grid_constant__ Geometry g) {
+                       int cap, int* __restrict__ n_out, const __grid_constant__ Geometry g, const FastTmaps* __restrict__ btm, int f0) {
     __shared__ float4 s_pat[8 * 32];
-    __shared__ __align__(16) uint8_t s_win[OD_WARPS][OD_WBYTES];   // per warp: the blurred tap window of the keypoint in work
+    __shared__ __align__(128) uint8_t s_win[OD_WARPS][OD_WBYTES];   // per warp: the blurred tap window of the keypoint in work
+    __shared__ __align__(8) unsigned long long s_bar[OD_WARPS];    // TMA form: one mbarrier per warp
+    const bool tma = btm != nullptr;
+    const int wpitch = tma ? ORB_TAP_BOX_W : OD_WPITCH;            // the TMA unit writes the box densely
+    unsigned bar_phase = 0;
     __shared__ int s_m[(OD_WARPS * KPW)][2];
     __shared__ float s_ang[(OD_WARPS * KPW)], s_a[(OD_WARPS * KPW)], s_b[(OD_WARPS * KPW)];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -375,6 +404,7 @@ orient_describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restric
         s_pat[k * 32 + i] = make_float4((float)p[0], (float)p[1], (float)p[2], (float)p[3]);
     }
     // ---- output index -> (level, index in level) for this warp's 4 keypoints ----
+    const int od_row = lane / 9, od_word = lane - 9 * od_row;   // phase 1: this lane's (row within a 3-row step, word) item
     int lv[KPW], px[KPW], py[KPW], off[KPW], sc[KPW];
 #pragma unroll
     for (int q = 0; q < KPW; ++q) {
@@ -395,9 +425,21 @@ orient_describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restric
     //      gathers from there.  One window per warp (20 KB per CTA): a larger footprint would shrink the L1 that the
     //      moment / record loads of this kernel live on.  Keypoints lie >= 19 px inside the level (EDGE_THRESHOLD), so
     //      the window never leaves the blurred level's rows; chunk columns past the row end are padding / the next row. ----
+    if (tma && lane == 0) od_mbar_init(&s_bar[warp], 1);
+    __syncwarp();
     auto stage_window = [&](int lq, int x, int y) {
         const LevelGeom& L = g.lv[lq];
         const int x0 = x - OD_TAPR, xa = x0 & ~15;
+        if (tma) {
+            // ONE bulk tensor copy per keypoint: box 64 bytes x 39 rows from the 16-byte aligned column xa (the TMA unit faults on an
+            // unaligned box start), issued by lane 0, landing on the warp's mbarrier; no LSU wavefronts, no per-lane address math
+            if (lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the lanes' generic reads of the previous window are done (syncwarp)
+                od_mbar_expect_tx(&s_bar[warp], ORB_TAP_BOX_W * ORB_TAP_BOX_H);
+                od_tma_load_3d(&s_win[warp][0], &btm->m[lq], xa, y - OD_TAPR, f0 + f, &s_bar[warp]);
+            }
+            return;
+        }
         const int nch = ((x0 + 2 * OD_TAPR) >> 4) - (xa >> 4) + 1;                 // 3 or 4 chunks per row
         const uint8_t* src = blur + L.bbase + (long long)f * L.bframe_stride + (long long)(y - OD_TAPR) * L.bpitch + xa;
         const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_win[warp][0]);
@@ -420,16 +462,23 @@ orient_describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restric
             const int a = (px[q] - ORB_HALF_PATCH) & 3;                       // alignment of the patch's first column
             const uint8_t* p0 = pyr + L.base + (long long)f * L.frame_stride + L.ioff + (py[q] - ORB_HALF_PATCH) * L.pitch +
                                 (px[q] - ORB_HALF_PATCH - a);                 // 4-byte aligned
-            const uint2* tab = mom_tab + a * OD_ITEMS + lane;
-            const unsigned pw = (unsigned)L.pitch >> 2;
+            // item (row, word): 27 lanes take 3 rows x 9 words per step, 11 steps cover rows 0..32 (the table is zero from row 31
+            // on and those rows are not loaded); a lane keeps its word column and walks down 3 rows per step, so the loop has no
+            // index arithmetic: two loads and two IDP.4A per item (the v factor of m01 sits in the table's second word)
+            if (lane < 27) {
+                const uint2* tab = mom_tab + a * OD_ITEMS + lane;
+                const unsigned pw3 = 3u * ((unsigned)L.pitch >> 2);
+                const unsigned* p = reinterpret_cast<const unsigned*>(p0) + od_row * ((unsigned)L.pitch >> 2) + od_word;
 #pragma unroll
-            for (int j = 0; j < OD_ITEMS / 32; ++j) {
-                const int item = lane + 32 * j;
-                const int r = item / 9, wi = item - 9 * r;                    // rows 0..31 (row 31 has zero weights)
-                const unsigned pix = __ldg(reinterpret_cast<const unsigned*>(p0) + r * pw + wi);
-                const uint2 w = __ldg(tab + 32 * j);
-                m10 = dp4a_su(w.x, pix, m10);                                 // sum u * I
-                m01 += (r - ORB_HALF_PATCH) * (int)__dp4a(w.y, pix, 0u);      // v * sum I over the row's circular extent
+                for (int j = 0; j < 11; ++j) {
+                    if (j < 10 || od_row == 0) {
+                        const unsigned pix = __ldg(p);
+                        const uint2 w = __ldg(tab);
+                        m10 = dp4a_su(w.x, pix, m10);                             // sum u * I
+                        m01 = dp4a_su(w.y, pix, m01);                             // sum v * I (weights v inside the circular extent, else 0)
+                    }
+                    p += pw3; tab += 27;
+                }
             }
         }
 #pragma unroll
@@ -459,10 +508,11 @@ orient_describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restric
         const int kq = warp * KPW + q;
         const float a = s_a[kq], b = s_b[kq];
         // taps are addressed with non-negative offsets from the staged window's top-left chunk
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (tma) { od_mbar_wait(&s_bar[warp], bar_phase); bar_phase ^= 1u; }
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
         const uint8_t* b2 = &s_win[warp][0];
-        const unsigned centre = OD_TAPR * OD_WPITCH + OD_TAPR + (unsigned)((px[q] - OD_TAPR) & 15);
+        const unsigned centre = OD_TAPR * wpitch + OD_TAPR + (unsigned)((px[q] - OD_TAPR) & 15);
         unsigned val = 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -471,7 +521,7 @@ orient_describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restric
             const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(pt.x, a), __fmul_rn(pt.y, b)));
             const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(pt.z, b), __fmul_rn(pt.w, a)));
             const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(pt.z, a), __fmul_rn(pt.w, b)));
-            const unsigned t0 = b2[centre + (unsigned)(r0 * OD_WPITCH + c0)], t1 = b2[centre + (unsigned)(r1 * OD_WPITCH + c1)];
+            const unsigned t0 = b2[centre + (unsigned)(r0 * wpitch + c0)], t1 = b2[centre + (unsigned)(r1 * wpitch + c1)];
             val |= (unsigned)(t0 < t1) << k;
         }
         __syncwarp();   // every lane has read the window: the next keypoint's copy may overwrite it
@@ -637,10 +687,10 @@ int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int pixel_format, int 
     {   // K4 + K6
         if (F >= 8)
             orient_describe_kernel<OD_KPW><<<dim3((g.total_kp_slots + OD_KPB - 1) / OD_KPB, F), OD_WARPS * 32, 0, st>>>(
-                c->d_pyr, c->d_blur, d_kept, d_kept_count, c->d_mom_tab, d_kps, d_desc, cap, d_n_out, g);
+                c->d_pyr, c->d_blur, d_kept, d_kept_count, c->d_mom_tab, d_kps, d_desc, cap, d_n_out, g, c->d_btmaps, f0);
         else   // latency shape: one keypoint per warp
             orient_describe_kernel<1><<<dim3((g.total_kp_slots + OD_WARPS - 1) / OD_WARPS, F), OD_WARPS * 32, 0, st>>>(
-                c->d_pyr, c->d_blur, d_kept, d_kept_count, c->d_mom_tab, d_kps, d_desc, cap, d_n_out, g);
+                c->d_pyr, c->d_blur, d_kept, d_kept_count, c->d_mom_tab, d_kps, d_desc, cap, d_n_out, g, c->d_btmaps, f0);
         c->launches++;
     }
     ORB_STAGE_MARK(5, st);

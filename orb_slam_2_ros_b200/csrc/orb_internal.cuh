@@ -92,6 +92,8 @@ struct __align__(16) ResizeWord {  // 4 adjacent destination columns (one output
 // TMA descriptors of the pyramid levels (dims: row bytes, rows, frames of the arena) for the FAST strip loader
 struct FastTmaps { CUtensorMap m[ORB_MAX_LEVELS]; };
 #define ORB_TMA_BOX_W 256
+#define ORB_TAP_BOX_W 64      // descriptor tap window box: 64 bytes x 39 rows (columns px-19 .. px+19 from a 16-byte aligned start)
+#define ORB_TAP_BOX_H 39
 
 struct __align__(16) FastStrip {   // one CTA of fast_strip_kernel: up to fast_G consecutive valid cells of one cell row
     int level, i, j0, ncell;       // cell row, first cell column, number of valid cells
@@ -153,6 +155,7 @@ struct orb_ctx {
     FastStrip* d_strips = nullptr;
     FastTmaps tmaps;              // valid when use_tma
     FastTmaps* d_tmaps = nullptr; // device copy (the TMA unit reads the descriptor from global memory)
+    FastTmaps* d_btmaps = nullptr; // the same for the BLURRED levels (dims: row bytes, rows, frames): descriptor tap windows (orient_describe_kernel)
     bool use_tma = false;
     uint2* d_mom_tab = nullptr;   // IC_Angle weight table [4 alignments][288 items] (orient_describe_kernel)
     bool fast_attr_set = false, qt_attr_set = false;
