@@ -936,6 +936,15 @@ def main():
             traffic["_source"] = os.path.relpath(tf, ROOT)
         except (IndexError, OSError, KeyError, ValueError):
             pass
+        pipes = {}
+        try:   # ALU / FMA / LSU / issue utilisation per stage from the committed ncu capture (tools/ncu_pipes_json.py): names the binding pipe
+            import glob
+            pf = sorted(glob.glob(os.path.join(ROOT, "profiles", "**", "*_pipes.json"), recursive=True))[-1]
+            pj = json.load(open(pf))
+            pipes = pj["stages"]
+            pipes["_source"] = os.path.relpath(pf, ROOT)
+        except (IndexError, OSError, KeyError, ValueError):
+            pass
         per_call = {k: v / max(prof_calls, 1) for k, v in stage_ms.items()}
         stages = {}
         for k in ("pyramid", "fast_cells", "blur"):
@@ -955,6 +964,12 @@ def main():
             roof = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None,
                     "kernel": dom + " (latency-bound stage; achieved = all stages' algorithmic bytes / step time)",
                     "peak_source": peak_src, "avg_launch_ms": per_call[dom]}
+        for k in stages:
+            if k in pipes:
+                stages[k]["pipes"] = pipes[k]
+        if dom in pipes:
+            roof["binding_pipe"] = {"stage": dom, "utilisation": pipes[dom], "source": pipes.get("_source"),
+                                    "note": "integer stencil: the stage is bounded by instruction issue on the named pipe, not by HBM (DESIGN.md §4)"}
         roof["traffic_source"] = traffic.get("_source")
         roof["stages"] = stages
         roof["step_alg_bytes"] = total_alg

@@ -323,6 +323,7 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 #endif
 #define OD_WBYTES ((((2 * OD_TAPR + 1) * OD_WPITCH) + 127) / 128 * 128)   // per-warp window, a multiple of 128 bytes (TMA destination alignment)
 
+static_assert(ORB_TAP_BOX_W * ORB_TAP_BOX_H <= OD_WBYTES && ORB_TAP_BOX_W % 16 == 0 && ORB_TAP_BOX_W >= 64, "tap window box must fit the per-warp window");
 // ---- TMA (cp.async.bulk.tensor) + mbarrier plumbing for the tap window ----
 __device__ __forceinline__ unsigned od_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void od_mbar_init(unsigned long long* bar, unsigned count) {

@@ -92,7 +92,11 @@ struct __align__(16) ResizeWord {  // 4 adjacent destination columns (one output
 // TMA descriptors of the pyramid levels (dims: row bytes, rows, frames of the arena) for the FAST strip loader
 struct FastTmaps { CUtensorMap m[ORB_MAX_LEVELS]; };
 #define ORB_TMA_BOX_W 256
-#define ORB_TAP_BOX_W 64      // descriptor tap window box: 64 bytes x 39 rows (columns px-19 .. px+19 from a 16-byte aligned start)
+#ifndef ORB_TAP_BOX_W
+#define ORB_TAP_BOX_W 80      // descriptor tap window box: 80 bytes x 39 rows (columns px-19 .. px+19 from a 16-byte aligned start need 54;
+                              // the TMA unit writes rows densely, and a 20-word row pitch spreads the rows over 8 bank offsets where 16 words
+                              // give 2: orient_describe 0.477 -> 0.449 ms per 512 frames)
+#endif
 #define ORB_TAP_BOX_H 39
 
 struct __align__(16) FastStrip {   // one CTA of fast_strip_kernel: up to fast_G consecutive valid cells of one cell row
