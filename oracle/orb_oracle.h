@@ -13,10 +13,12 @@
  *   (ii)  DistributeOctTree equal-size tie-break = (size, creation sequence) instead of the
  *         reference's allocator-dependent (size, heap pointer)  (ORBextractor.cc:615,705-708).
  *   (iii) descriptor steering uses a=(float)cos((double)angle), b=(float)sin((double)angle).
- * PARITY UNPINNED BY THE REFERENCE'S OWN TESTS: the reference ships no tests / golden vectors / fixtures for this path
- *  and its translation units cannot be compiled here (no OpenCV C++ headers), so there is no oracle/_ref.
- * Pin (i) is against the third-party
- * module that owns the arithmetic (OpenCV), and (ii),(iii) are stated choices.
+ * PINNED TO THE REFERENCE'S OWN CODE: the reference ships no tests / golden vectors / fixtures for this path, so
+ * the pin is the reference itself — oracle/_ref/liborb_ref.so is the reference's unmodified ORBextractor.cc / ORBmatcher.cc /
+ * Frame.cc / DBoW2 compiled over the OpenCV stand-in of oracle/ref_shim (oracle/Makefile), and tests/test_ref_pin.py checks
+ * this restatement against it bit for bit (extractor incl. order, stereo, grid, SearchForInitialization, SearchByBoW x2, BoW
+ * transform).  Pin (i) is against the third-party module that owns the arithmetic (OpenCV 4.13.0); (ii) is the reference's
+ * behaviour under a monotonic node allocator (ref_shim/mono_alloc.cpp); (iii) is confirmed by _ref calling this glibc's cosf.
  */
 #ifndef ORB_ORACLE_H
 #define ORB_ORACLE_H

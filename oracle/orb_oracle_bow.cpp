@@ -7,7 +7,7 @@
 // The restatement keeps the reference's containers (std::vector children lists, std::map BowVector / FeatureVector) and
 // its loop order, so tie-breaking (first child with the minimum distance, TemplatedVocabulary.h:1251-1262) and the
 // order of the double-precision additions (BowVector::addWeight in feature order, BowVector::normalize in word order)
-// are the reference's.  PARITY UNPINNED by reference tests (there are none); the vocabulary file ORBvoc.txt is absent
+// are the reference's.  Pinned to the reference's own DBoW2 sources compiled in oracle/_ref (tests/test_ref_pin.py::test_reference_dbow2_equals_oracle); the vocabulary file ORBvoc.txt is absent
 // from the checkout, so tests use synthetic trees written in the reference's text format.
 //
 // Stated pin (iv): when the descent reaches a leaf ABOVE level L - levelsup, the reference leaves *nid unwritten
