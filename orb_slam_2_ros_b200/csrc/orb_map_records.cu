@@ -41,8 +41,20 @@ int orb_mat_record_decode(const uint8_t* buf, size_t len, int* rows, int* cols, 
     uint64_t es, et;
     memcpy(&c, buf, 4); memcpy(&r, buf + 4, 4); memcpy(&es, buf + 8, 8); memcpy(&et, buf + 16, 8);   // load order (:82-85)
     if (c < 0 || r < 0 || es > 64) { orb_set_error("orb_mat_record_decode: implausible header %d x %d x %llu", r, c, (unsigned long long)es); return ORB_ERR_INVALID; }
+    // map files are untrusted input: c, r < 2^31 and es <= 64 could still wrap a 64-bit product, so bound the factors against the
+    // bytes that are actually there before multiplying
+    const size_t avail = len - MAT_HEADER;
+    if (es == 0 ? (false) : (c != 0 && r != 0 && ((size_t)c > avail / (size_t)es || (size_t)r > avail / (size_t)es / (size_t)c))) {
+        orb_set_error("orb_mat_record_decode: truncated payload");
+        return ORB_ERR_INVALID;
+    }
+    {   // elemSize must be the size CV_ELEM_SIZE gives for the stored type (depth in the low 3 bits, channels - 1 above)
+        static const unsigned depth_bytes[8] = {1, 1, 2, 2, 4, 4, 8, 2};
+        const uint64_t want = (uint64_t)depth_bytes[et & 7] * (((et >> 3) & 511) + 1);
+        if (et > 0xFFF || want != es) { orb_set_error("orb_mat_record_decode: elemSize %llu does not match type %llu", (unsigned long long)es, (unsigned long long)et); return ORB_ERR_INVALID; }
+    }
     const size_t payload = (size_t)c * (size_t)r * (size_t)es;
-    if (len - MAT_HEADER < payload) { orb_set_error("orb_mat_record_decode: truncated payload"); return ORB_ERR_INVALID; }
+    if (avail < payload) { orb_set_error("orb_mat_record_decode: truncated payload"); return ORB_ERR_INVALID; }
     if (rows) *rows = r;
     if (cols) *cols = c;
     if (elem_size) *elem_size = (size_t)es;

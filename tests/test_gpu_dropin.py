@@ -173,3 +173,25 @@ def test_vocabulary_compute_bow_and_search(arms, tmp_path):
     path2 = str(tmp_path / "voc2.txt")
     S.write_voc_file(path2, 9, 10, 4)
     both(arms, S.bag_of_words, 6, path2)
+
+
+@pytest.mark.parametrize("w,h,nf", [(752, 480, 1000), (1241, 376, 2000)])
+def test_matchers_at_the_other_config_shapes(arms, w, h, nf):
+    """EuRoC- and KITTI-shape frames through the tracking matchers (image bounds, grid pitch and keypoint counts differ)."""
+    def scenario(H):
+        import numpy as np
+        W = S.World(H, 3, w=w, h=h, nfeatures=nf, K=(458.654, 457.296, w / 2 - 7.3, h / 2 + 8.1))
+        rng = np.random.default_rng(77)
+        W.FA.set_points(W.pts, np.where(rng.random(W.FA.N) < 0.9, np.arange(W.FA.N), -1).astype(np.int32))
+        W.FA.set_outliers(np.zeros(W.FA.N, np.uint8))
+        W.FA.set_pose(S.pose()); W.FB.set_pose(S.pose(0.001, 0.002, -0.002, (0.01, 0.0, 0.01)))
+        n1 = orb_ref.Matcher(H, 0.9, True).search_last_frame(W.FB, W.FA, 15.0, True)
+        out = dict(n1=np.int64(n1), pts1=W.FB.get_points(W.pts), bounds=H.bounds())
+        W.FB.set_points(W.pts, np.full(W.FB.N, -1, np.int32))
+        n2 = orb_ref.Matcher(H, 0.8, True).search_local_points(W.FB, W.pts, rng.permutation(W.pts.n).astype(np.int32), 3.0)
+        out.update(n2=np.int64(n2), pts2=W.FB.get_points(W.pts))
+        return out
+    ref, dut = arms
+    r, d = scenario(ref), scenario(dut)
+    same(r, d, "shape %dx%d" % (w, h))
+    assert r["n1"] > 200 and r["n2"] > 200

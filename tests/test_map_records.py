@@ -89,3 +89,22 @@ def test_db_loads_descriptor_records_from_a_map_stream():
         mr.db_add_mat_record(db_a, mr.encode_mat_record(np.eye(4, dtype=np.float32)))
     with pytest.raises(OrbError):                                       # capacity
         mr.db_add_mat_record(db_a, mr.encode_mat_record(mats[2]))
+
+
+def test_mat_record_decode_rejects_overflowing_and_inconsistent_headers():
+    """Map files are untrusted input: a header whose cols * rows * elemSize wraps 64 bits, or whose elemSize
+    does not match its type, must be rejected instead of describing more data than the buffer holds."""
+    import ctypes as C
+    import struct
+    from orb_slam_2_ros_b200._lib import lib
+    L = lib()
+    L.orb_mat_record_decode.argtypes = [C.c_void_p, C.c_size_t] + [C.c_void_p] * 6
+    def decode(buf):
+        b = (C.c_uint8 * len(buf)).from_buffer_copy(buf)
+        return L.orb_mat_record_decode(b, len(buf), None, None, None, None, None, None)
+    ok = struct.pack("<iiQQ", 32, 2, 1, 0) + bytes(64)
+    assert decode(ok) == 0
+    assert decode(struct.pack("<iiQQ", 2**31 - 1, 2**31 - 1, 64, 6 | (7 << 3)) + bytes(64)) != 0      # product wraps 2^64
+    assert decode(struct.pack("<iiQQ", 2**31 - 1, 2**31 - 1, 4, 5) + bytes(64)) != 0                 # 2^64-ish payload, 64 bytes there
+    assert decode(struct.pack("<iiQQ", 32, 2, 2, 0) + bytes(128)) != 0                               # elemSize 2 for CV_8UC1
+    assert decode(struct.pack("<iiQQ", 32, 3, 1, 0) + bytes(64)) != 0                                # truncated payload
