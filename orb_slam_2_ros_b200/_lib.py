@@ -44,7 +44,7 @@ class OrbError(RuntimeError):
 EXPORTS = [
     "orb_last_error", "orb_device_count", "orb_version", "orb_create", "orb_destroy", "orb_get_tables",
     "orb_max_keypoints", "orb_extract", "orb_extract_batch", "orb_extract_batch_device", "orb_extract_batch_pix", "orb_extract_batch_device_pix", "orb_set_stream", "orb_sync",
-    "orb_launch_count", "orb_profile_enable", "orb_profile_read", "orb_level_dims", "orb_pyramid_level", "orb_debug_blurred", "orb_debug_raw_corners",
+    "orb_launch_count", "orb_profile_enable", "orb_profile_read", "orb_level_dims", "orb_pyramid_level", "orb_pyramid_levels", "orb_debug_blurred", "orb_debug_raw_corners",
     "orb_debug_tie_counts", "orb_hamming_top2", "orb_hamming_top2_csr", "orb_db_create", "orb_db_destroy", "orb_db_add", "orb_db_add_device",
     "orb_db_size", "orb_db_set_stream", "orb_db_query_top2", "orb_db_query_top2_device", "orb_db_launch_count", "orb_db_profile_enable", "orb_db_profile_read",
     "orb_top2_merge", "orb_top2_merge_device", "orb_search_by_projection", "orb_match_bruteforce", "orb_stereo_match", "orb_stereo_match_batch_device", "orb_search_by_projection_batch_device", "orb_match_bruteforce_batch_device",
@@ -86,6 +86,7 @@ def lib():
     L.orb_profile_read.argtypes = [vp, vp, C.POINTER(i64), C.POINTER(i64), i32]
     L.orb_level_dims.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32)]
     L.orb_pyramid_level.argtypes = [vp, i32, i32, vp, sz]
+    L.orb_pyramid_levels.argtypes = [vp, i32, vp, sz, vp, vp, vp]
     L.orb_debug_blurred.argtypes = [vp, i32, i32, vp, sz]
     L.orb_debug_raw_corners.argtypes = [vp, i32, i32, vp, i32, C.POINTER(i32)]
     L.orb_debug_tie_counts.argtypes = [vp, i32, vp]

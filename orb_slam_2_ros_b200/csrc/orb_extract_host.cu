@@ -857,6 +857,30 @@ int orb_pyramid_level(orb_ctx* c, int frame, int level, uint8_t* dst, size_t dst
     return ORB_OK;
 }
 
+/* every level of one frame with ONE synchronisation: level l lands at dst + offset[l] with row stride pitch[l] (the device
+ * layout's own pitch, so each level is one contiguous copy); the interior pixel (0,0) of level l is at
+ * dst + offset[l] + 19 * pitch[l] + 19. */
+int orb_pyramid_levels(orb_ctx* c, int frame, uint8_t* dst, size_t dst_bytes, size_t* offset, size_t* pitch, size_t* needed) {
+    if (!c || !c->have_geom || frame < 0 || frame >= c->last_frames) return ORB_ERR_INVALID;
+    size_t total = 0;
+    for (int l = 0; l < c->nlevels; ++l) total += (size_t)c->g.lv[l].pitch * c->g.lv[l].rows;
+    if (needed) *needed = total;
+    if (!dst) return needed ? ORB_OK : ORB_ERR_INVALID;
+    if (dst_bytes < total || !offset || !pitch) return ORB_ERR_CAPACITY;
+    ORB_CUDA(cudaSetDevice(c->device));
+    size_t off = 0;
+    for (int l = 0; l < c->nlevels; ++l) {
+        const LevelGeom& L = c->g.lv[l];
+        const size_t bytes = (size_t)L.pitch * L.rows;
+        ORB_CUDA(cudaMemcpyAsync(dst + off, c->d_pyr + L.base + (long long)frame * L.frame_stride, bytes, cudaMemcpyDeviceToHost, c->stream));
+        offset[l] = off + (ORB_XOFF - ORB_EDGE);   // first byte of the bordered row 0
+        pitch[l] = (size_t)L.pitch;
+        off += bytes;
+    }
+    ORB_CUDA(cudaStreamSynchronize(c->stream));
+    return ORB_OK;
+}
+
 int orb_debug_blurred(orb_ctx* c, int frame, int level, uint8_t* dst, size_t dst_stride) {
     if (!c || !c->have_geom || !dst || level < 0 || level >= c->nlevels || frame < 0 || frame >= c->last_frames)
         return ORB_ERR_INVALID;

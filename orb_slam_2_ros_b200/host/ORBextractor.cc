@@ -53,13 +53,20 @@ void ORBextractor::operator()(cv::InputArray _image, cv::InputArray /*_mask*/, s
         memcpy(out.data, desc.data, (size_t)n * 32);
     }
     if (download_pyramid_) {
+        // public mvImagePyramid (ORBextractor.h:85): all levels in one pass — 8 asynchronous copies of the device layout into one
+        // host buffer and ONE synchronisation; the Mats are headers over that buffer (step = the device pitch), like the ROI of
+        // the bordered buffer the reference builds (ORBextractor.cc:1161-1165)
+        size_t need = 0;
+        check(orb_pyramid_levels(ctx_, 0, nullptr, 0, nullptr, nullptr, &need), "orb_pyramid_levels");
+        if (pyramid_host_.size() < need) pyramid_host_.resize(need);
+        std::vector<size_t> off(nlevels), pitch(nlevels);
+        check(orb_pyramid_levels(ctx_, 0, pyramid_host_.data(), pyramid_host_.size(), off.data(), pitch.data(), nullptr), "orb_pyramid_levels");
         for (int l = 0; l < nlevels; ++l) {
             int w = 0, h = 0;
             check(orb_level_dims(ctx_, l, &w, &h), "orb_level_dims");
-            bordered_[l].create(h + 38, w + 38, CV_8U);
-            check(orb_pyramid_level(ctx_, 0, l, bordered_[l].data, (size_t)bordered_[l].step), "orb_pyramid_level");
+            bordered_[l] = cv::Mat(h + 38, w + 38, CV_8U, pyramid_host_.data() + off[l], pitch[l]);
 #if defined(ORB_B200_USE_OPENCV) || __has_include(<opencv2/core/core.hpp>)
-            mvImagePyramid[l] = bordered_[l](cv::Rect(19, 19, w, h));   // ORBextractor.cc:1161-1165
+            mvImagePyramid[l] = bordered_[l](cv::Rect(19, 19, w, h));
 #else
             mvImagePyramid[l] = bordered_[l].roi(19, 19, w, h);
 #endif

@@ -52,7 +52,8 @@ protected:
 private:
     orb_ctx* ctx_ = nullptr;
     bool download_pyramid_ = true;
-    std::vector<cv::Mat> bordered_;   // owners of the (w+38) x (h+38) host copies
+    std::vector<cv::Mat> bordered_;   // headers of the bordered levels inside pyramid_host_
+    std::vector<unsigned char> pyramid_host_;   // all levels of the last frame in the device layout (one copy pass per call)
 };
 
 }  // namespace ORB_SLAM2
