@@ -127,9 +127,9 @@ int orb_level_dims(orb_ctx* ctx, int level, int* w, int* h);
 int orb_pyramid_level(orb_ctx* ctx, int frame, int level, uint8_t* dst, size_t dst_stride);
 
 /* All levels of one frame with a single synchronisation (what a host caller that reads mvImagePyramid wants after every
- * operator()): level l is copied as it lies on the device — (h_l + 38) rows of pitch[l] bytes — to dst + ..., and offset[l]
- * is the position of its bordered buffer's first byte, so that  Mat(h_l + 38, w_l + 38, CV_8U, dst + offset[l], pitch[l])  is
- * the bordered level and the ROI (19, 19, w_l, h_l) of it is mvImagePyramid[l].  dst == NULL: only *needed (bytes) is set. */
+ * operator()): the bordered buffer of level l — (h_l + 38) rows of (w_l + 38) bytes, the reference's own layout — is copied to
+ * dst + offset[l], pitch[l] = w_l + 38, so that the ROI (19, 19, w_l, h_l) of Mat(h_l + 38, w_l + 38, CV_8U, dst + offset[l], pitch[l])
+ * is mvImagePyramid[l] with step = w_l + 38 (ORBextractor.cc:1161-1165).  dst == NULL: only *needed (bytes) is set. */
 int orb_pyramid_levels(orb_ctx* ctx, int frame, uint8_t* dst, size_t dst_bytes, size_t* offset, size_t* pitch, size_t* needed);
 
 /* stage taps of the last call, for parity tests (host outputs) */

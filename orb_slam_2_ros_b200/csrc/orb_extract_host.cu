@@ -857,13 +857,12 @@ int orb_pyramid_level(orb_ctx* c, int frame, int level, uint8_t* dst, size_t dst
     return ORB_OK;
 }
 
-/* every level of one frame with ONE synchronisation: level l lands at dst + offset[l] with row stride pitch[l] (the device
- * layout's own pitch, so each level is one contiguous copy); the interior pixel (0,0) of level l is at
- * dst + offset[l] + 19 * pitch[l] + 19. */
+/* every level of one frame with ONE synchronisation: the bordered buffer of level l, (h_l + 38) rows of (w_l + 38) bytes (the
+ * reference's own layout: step = w + 38), lands at dst + offset[l]; pitch[l] = w_l + 38 */
 int orb_pyramid_levels(orb_ctx* c, int frame, uint8_t* dst, size_t dst_bytes, size_t* offset, size_t* pitch, size_t* needed) {
     if (!c || !c->have_geom || frame < 0 || frame >= c->last_frames) return ORB_ERR_INVALID;
     size_t total = 0;
-    for (int l = 0; l < c->nlevels; ++l) total += (size_t)c->g.lv[l].pitch * c->g.lv[l].rows;
+    for (int l = 0; l < c->nlevels; ++l) total += (size_t)(c->g.lv[l].w + 2 * ORB_EDGE) * c->g.lv[l].rows;
     if (needed) *needed = total;
     if (!dst) return needed ? ORB_OK : ORB_ERR_INVALID;
     if (dst_bytes < total || !offset || !pitch) return ORB_ERR_CAPACITY;
@@ -871,11 +870,12 @@ int orb_pyramid_levels(orb_ctx* c, int frame, uint8_t* dst, size_t dst_bytes, si
     size_t off = 0;
     for (int l = 0; l < c->nlevels; ++l) {
         const LevelGeom& L = c->g.lv[l];
-        const size_t bytes = (size_t)L.pitch * L.rows;
-        ORB_CUDA(cudaMemcpyAsync(dst + off, c->d_pyr + L.base + (long long)frame * L.frame_stride, bytes, cudaMemcpyDeviceToHost, c->stream));
-        offset[l] = off + (ORB_XOFF - ORB_EDGE);   // first byte of the bordered row 0
-        pitch[l] = (size_t)L.pitch;
-        off += bytes;
+        const size_t bw = (size_t)L.w + 2 * ORB_EDGE;
+        ORB_CUDA(cudaMemcpy2DAsync(dst + off, bw, c->d_pyr + L.base + (long long)frame * L.frame_stride + (ORB_XOFF - ORB_EDGE), L.pitch, bw, L.rows,
+                                   cudaMemcpyDeviceToHost, c->stream));
+        offset[l] = off;
+        pitch[l] = bw;
+        off += bw * L.rows;
     }
     ORB_CUDA(cudaStreamSynchronize(c->stream));
     return ORB_OK;

@@ -53,9 +53,9 @@ void ORBextractor::operator()(cv::InputArray _image, cv::InputArray /*_mask*/, s
         memcpy(out.data, desc.data, (size_t)n * 32);
     }
     if (download_pyramid_) {
-        // public mvImagePyramid (ORBextractor.h:85): all levels in one pass — 8 asynchronous copies of the device layout into one
-        // host buffer and ONE synchronisation; the Mats are headers over that buffer (step = the device pitch), like the ROI of
-        // the bordered buffer the reference builds (ORBextractor.cc:1161-1165)
+        // public mvImagePyramid (ORBextractor.h:85): all levels in one pass — 8 asynchronous 2-D copies into one host buffer and
+        // ONE synchronisation; the Mats are headers over that buffer: the ROI (step = w + 38) of the bordered buffer, as the
+        // reference builds it (ORBextractor.cc:1161-1165)
         size_t need = 0;
         check(orb_pyramid_levels(ctx_, 0, nullptr, 0, nullptr, nullptr, &need), "orb_pyramid_levels");
         if (pyramid_host_.size() < need) pyramid_host_.resize(need);
