@@ -100,7 +100,15 @@ void orc_grid_destroy(void* g);
 /* GetFeaturesInArea; returns count, writes indices (reference order) */
 int orc_grid_query(void* g, float x, float y, float r, int min_level, int max_level, int32_t* out, int cap);
 
-/* matcher modes for orc_search_by_projection */
+/* matcher modes for orc_search_by_projection.  The two remaining SearchByProjection overloads are parameterisations of
+ * ORC_MODE_TRACK_LAST (the same loop body: window, skip taken, best only, threshold, optional rotation histogram):
+ *   ORBmatcher.cc:1474-1601 (Cur, KF, sAlreadyFound, th, ORBdist): th_dist = ORBdist, q_valid = pMP && !isBad && !sAlreadyFound.count(pMP)
+ *       && inside the image / distance range, levels [l-1, l+1], taken = (mvpMapPoints[i2] != NULL)  (:1543), u_right = NULL,
+ *       q_angle = pKF->mvKeysUn[i].angle, q_obs = all;
+ *   ORBmatcher.cc:291-404 (KF, Scw, vpPoints, vpMatched, th): th_dist = TH_LOW, check_orientation = 0, levels [l-1, l],
+ *       taken = (vpMatched[idx] != NULL)  (:376), q_valid = !isBad && !spAlreadyFound.count(pMP) && the projection gates (:322-357).
+ * tests/test_gpu_match.py::test_search_by_projection_reloc_and_loop_parameterisations runs both against the CUDA path, and
+ * tests/test_gpu_dropin.py runs the reference's own compiled code for these two overloads against the drop-in. */
 enum {
     ORC_MODE_TRACK_LAST = 0,  /* ORBmatcher.cc:1330-1472  (Cur, Last, th, bMono)  best only, <= th_dist, rot-hist */
     ORC_MODE_LOCAL_POINTS = 1, /* ORBmatcher.cc:45-129     (F, vpMapPoints, th) best/second, level ratio test */
