@@ -284,3 +284,56 @@ def write_vocabulary_text(path, k, L, scoring, weighting, parent, is_leaf, desc,
         f.write("%d %d  %d %d\n" % (k, L, scoring, weighting))
         for i in range(1, len(parent)):
             f.write("%d %d %s  %g\n" % (parent[i], 1 if is_leaf[i] else 0, " ".join(str(int(b)) for b in desc[i]), weight[i]))
+
+
+# ---- integer-only, counter-based frame generator: the same function exists in C (tools/synth_int.c) --------
+# No RNG state, no libm, no OpenCV: every random number is splitmix64(seed * 2^32 + counter), so the C and the Python
+# implementation produce byte-identical frames (tests/test_synth_int.py) and a C++ caller can regenerate any test input.
+def _sm64_scalar(x):
+    x = (x + 0x9E3779B97F4A7C15) & _M64
+    z = x
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _M64
+    return z ^ (z >> 31)
+
+
+def synth_frame_int(seed, w=640, h=480, n_rect=380, noise=8):
+    """uint8 (h, w).  Content: low-frequency background (integer bilinear blend of a 6x5 grid), n_rect filled
+    rectangles (corner sources), a dense-texture patch, a perfectly flat patch, a low-contrast patch with steps in (7, 20],
+    +-noise per pixel from a hash of the pixel index."""
+    base = (int(seed) & 0xFFFFFFFF) << 32
+    ctr = [0]
+
+    def rnd(n):                                   # uniform in [0, n)
+        ctr[0] += 1
+        return (_sm64_scalar(base + ctr[0]) >> 11) % n
+    gw, gh = 6, 5
+    coarse = np.array([[40 + rnd(176) for _ in range(gw + 1)] for _ in range(gh + 1)], np.int64)
+    xs = (np.arange(w, dtype=np.int64) * gw * 256) // w
+    ys = (np.arange(h, dtype=np.int64) * gh * 256) // h
+    xi, xf, yi, yf = xs >> 8, xs & 255, ys >> 8, ys & 255
+    top = coarse[yi][:, xi] * (256 - xf)[None, :] + coarse[yi][:, xi + 1] * xf[None, :]
+    bot = coarse[yi + 1][:, xi] * (256 - xf)[None, :] + coarse[yi + 1][:, xi + 1] * xf[None, :]
+    img = ((top * (256 - yf)[:, None] + bot * yf[:, None]) >> 16).astype(np.int64)
+    for _ in range(n_rect):
+        x0, y0, rw, rh, v = rnd(w), rnd(h), 6 + rnd(64), 6 + rnd(64), rnd(256)
+        img[y0:y0 + rh, x0:x0 + rw] = v
+    # dense texture: 4x4 checker blocks of random levels in the top-left sixth
+    tw, th = w // 3, h // 2
+    for by in range(0, th, 4):
+        for bx in range(0, tw, 4):
+            img[by:by + 4, bx:bx + 4] = rnd(256)
+    # perfectly flat patch (bottom-right) and a low-contrast patch (bottom-left) with steps in (7, 20]
+    img[h - h // 4:, w - w // 4:] = 128
+    lx, ly = w // 4, h // 4
+    for by in range(h - ly, h, 12):
+        for bx in range(0, lx, 12):
+            img[by:by + 12, bx:bx + 12] = 100 + ((bx // 12 + by // 12) & 1) * (8 + rnd(13))
+    # noise: hash of (seed, pixel index), uniform in [-noise, +noise]; the flat patch stays flat
+    if noise > 0:
+        with np.errstate(over="ignore"):
+            idx = np.arange(w * h, dtype=np.uint64) + np.uint64((base + (1 << 31)) & _M64)
+            nz = ((_splitmix64(idx) >> np.uint64(11)) % np.uint64(2 * noise + 1)).astype(np.int64).reshape(h, w) - noise
+        nz[h - h // 4:, w - w // 4:] = 0
+        img = img + nz
+    return np.clip(img, 0, 255).astype(np.uint8)
