@@ -151,3 +151,50 @@ def test_search_by_projection_batch_device(oracle, mode_name):
         assert np.array_equal(moq[p, :nq], moq_o) and np.all(moq[p, nq:] == -1)
         assert np.array_equal(tq[p, :n], tq_o) and np.all(tq[p, n:] == -1)
         assert np.array_equal(taken[p, :n], t_o)
+
+
+def test_batch_edge_cases_empty_pairs_and_candidate_overflow(oracle):
+    """A pair without keypoints (count 0 on the device) yields no matches and leaves the other pairs untouched; windows so large
+    that a pair's candidate arena (160 per query on average) overflows report nmatches = -1 for that pair instead of a wrong
+    result."""
+    import torch
+    from orb_slam_2_ros_b200 import ORBextractor
+    from orb_slam_2_ros_b200._lib import KP_DTYPE, SearchBatch
+    from orb_slam_2_ros_b200.matcher import MODE_TRACK_LAST, match_bruteforce_batch_device, search_by_projection_batch_device
+    P = 3
+    A, B = _pairs(P, 60)
+    exa, exb = ORBextractor(1000, max_batch=P), ORBextractor(1000, max_batch=P)
+    _, ka, da, na, cap = _dev_batch_extract(exa, A)
+    _, kb, db, nb, _ = _dev_batch_extract(exb, B)
+    na2, nb2 = na.clone(), nb.clone()
+    na2[1] = 0            # pair 1: no queries
+    nb2[2] = 0            # pair 2: no targets
+    m12 = torch.full((P, cap), -7, dtype=torch.int32, device="cuda"); nm = torch.full((P,), -7, dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    match_bruteforce_batch_device(P, ka.data_ptr(), da.data_ptr(), na2.data_ptr(), cap, kb.data_ptr(), db.data_ptr(), nb2.data_ptr(), cap,
+                                  m12.data_ptr(), nm.data_ptr(), 50, 0.6, True, stream=st)
+    torch.cuda.synchronize()
+    nmh, m = nm.cpu().numpy(), m12.cpu().numpy()
+    assert nmh[1] == 0 and nmh[2] == 0 and np.all(m[1] == -1) and np.all(m[2] == -1)
+    k1 = ka[0].cpu().numpy().view(KP_DTYPE).reshape(-1)[:int(na[0])]; k2 = kb[0].cpu().numpy().view(KP_DTYPE).reshape(-1)[:int(nb[0])]
+    nm_o, m_o = oracle.match_bruteforce(da[0].cpu().numpy()[:len(k1)], k1["angle"], db[0].cpu().numpy()[:len(k2)], k2["angle"], 50, 0.6, True)
+    assert nmh[0] == nm_o and np.array_equal(m[0, :len(k1)], m_o)
+    # windowed search: empty pairs, then absurd windows
+    kah = ka.cpu().numpy().view(KP_DTYPE).reshape(P, cap)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    for radius, expect_overflow in ((15.0, False), (5000.0, True)):
+        q_u, q_v = dev(kah["x"].astype(np.float32)), dev(kah["y"].astype(np.float32))
+        q_r = torch.full((P, cap), radius, dtype=torch.float32, device="cuda")
+        lo = torch.full((P, cap), -1, dtype=torch.int32, device="cuda"); hi = torch.full((P, cap), -1, dtype=torch.int32, device="cuda")
+        ang = dev(kah["angle"].astype(np.float32))
+        taken = torch.zeros((P, cap), dtype=torch.uint8, device="cuda")
+        moq = torch.full((P, cap), -7, dtype=torch.int32, device="cuda"); tq = torch.full((P, cap), -7, dtype=torch.int32, device="cuda")
+        nms = torch.full((P,), -7, dtype=torch.int32, device="cuda")
+        b = SearchBatch(kb.data_ptr(), db.data_ptr(), None, nb2.data_ptr(), cap, taken.data_ptr(), na2.data_ptr(), cap, q_u.data_ptr(), q_v.data_ptr(),
+                        q_r.data_ptr(), lo.data_ptr(), hi.data_ptr(), da.data_ptr(), None, None, ang.data_ptr(), None, None, moq.data_ptr(), tq.data_ptr(),
+                        nms.data_ptr())
+        search_by_projection_batch_device(MODE_TRACK_LAST, P, b, (0.0, 0.0, 640.0, 480.0), 100, 0.9, True, stream=st)
+        torch.cuda.synchronize()
+        n = nms.cpu().numpy()
+        assert n[1] == 0 and n[2] == 0
+        assert (n[0] == -1) if expect_overflow else (n[0] > 100)
