@@ -40,12 +40,12 @@ void free_geometry_buffers(orb_ctx* c) {
     c->graph_warm_w = c->graph_warm_h = 0; c->graph_warm_fmt = -1;
     cudaFree(c->d_in); cudaFree(c->d_pyr); cudaFree(c->d_blur); cudaFree(c->d_corners); cudaFree(c->d_node_of_key);
     cudaFree(c->d_corner_count); cudaFree(c->d_kept); cudaFree(c->d_kept_count); cudaFree(c->d_taps);
-    cudaFree(c->d_wtaps); cudaFree(c->d_strips); cudaFree(c->d_tmaps); cudaFree(c->d_btmaps); cudaFree(c->d_kps_out); cudaFree(c->d_desc_out); cudaFree(c->d_n_out);
+    cudaFree(c->d_wtaps); cudaFree(c->d_rsegs); cudaFree(c->d_strips); cudaFree(c->d_tmaps); cudaFree(c->d_btmaps); cudaFree(c->d_kps_out); cudaFree(c->d_desc_out); cudaFree(c->d_n_out);
     cudaFreeHost(c->h_kps); cudaFreeHost(c->h_desc); cudaFreeHost(c->h_n); cudaFreeHost(c->h_in);
     c->h_out_cap = 0;
     c->d_in = c->d_pyr = c->d_blur = nullptr; c->d_corners = nullptr; c->d_node_of_key = nullptr;
     c->d_corner_count = c->d_kept_count = nullptr; c->d_kept = nullptr; c->d_taps = nullptr;
-    c->d_wtaps = nullptr; c->d_strips = nullptr; c->d_tmaps = nullptr; c->d_btmaps = nullptr; c->d_kps_out = nullptr; c->d_desc_out = nullptr; c->d_n_out = nullptr;
+    c->d_wtaps = nullptr; c->d_rsegs = nullptr; c->d_strips = nullptr; c->d_tmaps = nullptr; c->d_btmaps = nullptr; c->d_kps_out = nullptr; c->d_desc_out = nullptr; c->d_n_out = nullptr;
     c->h_kps = nullptr; c->h_desc = nullptr; c->h_n = nullptr; c->h_in = nullptr;
     c->in_bytes = c->h_in_bytes = 0; c->out_cap = 0;
     c->have_geom = false;
@@ -83,7 +83,7 @@ int build_geometry(orb_ctx* c, int w, int h) {
     g.nlevels = c->nlevels; g.w = w; g.h = h; g.ini_th = c->ini_th; g.min_th = c->min_th; g.one = 1;
     const int F = c->max_batch;
     long long pyr_off = 0, blur_off = 0, corner_off = 0;
-    int cells = 0, kp_slots = 0, taps = 0, wtaps = 0, max_node_cap = 0, fast_ctas = 0, border_items = 0, copy_items = 0, blur_items = 0;
+    int cells = 0, kp_slots = 0, taps = 0, wtaps = 0, max_node_cap = 0, fast_ctas = 0, blur_items = 0;
     for (int l = 0; l < g.nlevels; ++l) {
         LevelGeom& L = g.lv[l];
         L.w = cv_round_f((float)w * c->inv_scale[l]);  // ORBextractor.cc:1159
@@ -136,7 +136,7 @@ int build_geometry(orb_ctx* c, int w, int h) {
         L.kp_base = kp_slots; kp_slots += L.node_cap;
         L.xtab = taps; taps += L.w;
         L.ytab = taps; taps += L.h;
-        L.xwtab = wtaps; wtaps += (L.w + 3) / 4;
+        L.xwtab = wtaps; wtaps += (ORB_XOFF + L.w + ORB_EDGE + 3) / 4 - (ORB_XOFF - ORB_EDGE) / 4;   // one entry per bordered word
         L.scale = c->scale[l];
         L.size = (float)(int)(ORB_PATCH * c->scale[l]);  // ORBextractor.cc:874
         // FAST strips: one CTA = fast_G consecutive cells of one cell row (tile width fast_G * wCell + 6 <= 256)
@@ -144,21 +144,12 @@ int build_geometry(orb_ctx* c, int w, int h) {
         L.fast_groups = (L.nCols + gmax - 1) / gmax;
         L.fast_G = (L.nCols + L.fast_groups - 1) / L.fast_groups;
         L.fast_cta_base = fast_ctas; fast_ctas += L.nRows * L.fast_groups;
-        // border fill: one warp per bordered row (border_items counts rows)
+        // pyramid row items: a bordered row is written as the words from byte 12 (column -20, a dead byte) to the end of the
+        // right border; level 0 is written as 16-byte vectors of the whole pitch
         const int first_w = (ORB_XOFF - ORB_EDGE) / 4;                          // word holding byte 13
         const int end_w = (ORB_XOFF + L.w + ORB_EDGE + 3) / 4;                   // one past the last border word
         L.border_words = end_w - first_w;
-        // every level starts at a CTA boundary of the border kernel (16 rows x 16 slots, resp. 256 copy items per CTA), so the
-        // level of a CTA — and with it every LevelGeom field it reads — is uniform (no divergent constant-bank indexing)
-        L.border_base = border_items;
-        border_items += (L.h + 2 * ORB_EDGE + 15) / 16 * 16;
-        L.copy_base = copy_items;
-        {   // top/bottom row copies: 16-byte vectors + trailing whole words per row
-            const int per_row = (L.w >> 4) + ((L.w >> 2) - 4 * (L.w >> 4));
-            L.inv_wpr = 0xFFFFFFFFu / (unsigned)std::max(per_row, 1) + 1u;
-            L.copy_items = 2 * ORB_EDGE * per_row;
-            copy_items += (L.copy_items + 255) / 256 * 256;
-        }
+        L.inv_wpr = 0xFFFFFFFFu / (unsigned)L.border_words + 1u;
         // blur: one thread = one output word x ORB_BLUR_ROWS rows
         L.blur_wpr = (L.w + 3) / 4;
         L.blur_base = blur_items;   // a multiple of the CTA size: every CTA of the blur kernel lies inside ONE level (uniform level data)
@@ -167,27 +158,44 @@ int build_geometry(orb_ctx* c, int w, int h) {
     if (max_node_cap > 65535) { orb_set_error("nfeatures too large"); return ORB_ERR_INVALID; }
     if ((size_t)max_node_cap * 80 > 200 * 1024) { orb_set_error("nfeatures too large for the quadtree kernel"); return ORB_ERR_INVALID; }
     g.total_cells = cells; g.total_kp_slots = kp_slots; g.max_node_cap = max_node_cap;
-    g.border_items = border_items; g.border_copy_items = copy_items; g.blur_items = blur_items;
+    g.blur_items = blur_items;
+    g.l0_ni = g.lv[0].w >> 4;   // level-0 pass: interior vectors [2, 2 + l0_ni) of a bordered row are plain copies
+    g.l0_border_first = (g.l0_ni * g.lv[0].h + 31) / 32 * 32;
+    g.l0_inv_ni = 0xFFFFFFFFu / (unsigned)std::max(g.l0_ni, 1) + 1u;
+    g.l0_inv_nb = 0xFFFFFFFFu / (unsigned)((g.lv[0].pitch >> 4) - g.l0_ni) + 1u;
     g.pyr_frame_total = pyr_off / F;
     // resize taps: per-column / per-row tables + the packed per-output-word table of the fast path
     std::vector<ResizeTap> h_taps(std::max(taps, 1));
     std::vector<ResizeWord> h_wtaps(std::max(wtaps, 1));
+    std::vector<ResizeSeg> h_rsegs;
     for (int l = 1; l < g.nlevels; ++l) {
         LevelGeom& L = g.lv[l];
         ResizeTap* xt = h_taps.data() + L.xtab;
         make_taps(g.lv[l - 1].w, L.w, false, xt);
         make_taps(g.lv[l - 1].h, L.h, true, h_taps.data() + L.ytab);
         L.fast_resize = 1;
-        for (int wc = 0; wc < (L.w + 3) / 4; ++wc) {
-            ResizeWord& rw = h_wtaps[L.xwtab + wc];
+        // one entry per word of the bordered row: the 4 columns of word bw are x0 .. x0 + 3, x0 = 4 * bw - 20; a border column
+        // takes the taps of the column it reflects (copyMakeBorder(REFLECT_101) of the resized level).  All 8 tap bytes must
+        // lie in the 8 bytes that start at the leftmost tap (true for scale factors <= 4/3, reflected words included).
+        for (int bw = 0; bw < L.border_words; ++bw) {
+            ResizeWord& rw = h_wtaps[L.xwtab + bw];
             memset(&rw, 0, sizeof(rw));
-            rw.wb = xt[4 * wc].s0 >> 2;
-            const int off0 = (int)xt[4 * wc].s0 - 4 * rw.wb;   // 0..3
+            const int x0 = 4 * bw - (ORB_XOFF - 12);
+            int col[4], smin = 1 << 30;
+            for (int p = 0; p < 4; ++p) {
+                int x = x0 + p;
+                x = x < 0 ? -x : x;
+                if (x >= L.w) x = 2 * L.w - 2 - x;
+                col[p] = std::min(std::max(x, 0), L.w - 1);    // bytes beyond the 19-px border (row padding) are dead
+                smin = std::min(smin, (int)xt[col[p]].s0);
+            }
+            rw.wb = smin >> 2;
+            const int off0 = smin - 4 * rw.wb;                 // 0..3
             rw.sh0 = 8u * (unsigned)off0;
             unsigned sel[4] = {0, 0, 0, 0};
             for (int p = 0; p < 4; ++p) {
-                const ResizeTap& t = xt[std::min(4 * wc + p, L.w - 1)];
-                const int rel = (int)t.s0 - 4 * rw.wb - off0;   // left tap relative to column 0's: both taps must lie in 8 bytes
+                const ResizeTap& t = xt[col[p]];
+                const int rel = (int)t.s0 - smin;              // left tap relative to the leftmost one: both taps must lie in 8 bytes
                 if (rel < 0 || rel > 6) L.fast_resize = 0;
                 sel[p] = (unsigned)(rel & 7) | ((unsigned)((rel + 1) & 7) << 4);
                 rw.cc[p] = (unsigned)(unsigned short)t.c0 | ((unsigned)(unsigned short)t.c1 << 16);
@@ -195,6 +203,32 @@ int build_geometry(orb_ctx* c, int w, int h) {
             rw.sel01 = sel[0] | (sel[1] << 8);
             rw.sel23 = sel[2] | (sel[3] << 8);
         }
+        // staged kernel: column segments of <= 256 bordered words; a segment stages the source words [w0, w0 + nbytes / 4) of
+        // every source row its strip touches
+        L.nseg = (L.border_words + 255) / 256;
+        L.seg_threads = (int)round_up((size_t)(L.border_words + L.nseg - 1) / L.nseg, 32);
+        L.seg_base = (int)h_rsegs.size();
+        int max_bytes = 16;
+        for (int sgi = 0; sgi < L.nseg; ++sgi) {
+            ResizeSeg sg;
+            sg.bw0 = sgi * L.seg_threads;
+            sg.nw = std::min(L.seg_threads, L.border_words - sg.bw0);
+            int wmin = 1 << 30, wmax = 0;
+            for (int bw = sg.bw0; bw < sg.bw0 + sg.nw; ++bw) {
+                wmin = std::min(wmin, h_wtaps[L.xwtab + bw].wb);
+                wmax = std::max(wmax, h_wtaps[L.xwtab + bw].wb + 2);
+            }
+            sg.w0 = wmin & ~3;
+            sg.nbytes = (int)round_up((size_t)(wmax + 1 - sg.w0) * 4, 16);
+            max_bytes = std::max(max_bytes, sg.nbytes);
+            h_rsegs.push_back(sg);
+        }
+        int max_rows = 2;
+        const ResizeTap* yt = h_taps.data() + L.ytab;
+        for (int y0 = 0; y0 < L.h; y0 += ORB_RESIZE_ROWS)
+            max_rows = std::max(max_rows, (int)yt[std::min(y0 + ORB_RESIZE_ROWS, L.h) - 1].s1 - (int)yt[y0].s0 + 1);
+        L.stage_bytes = max_rows * max_bytes;
+        if (L.stage_bytes > 200 * 1024) L.fast_resize = 0;
     }
 
     // FAST strips: valid cells only (ORBextractor.cc:822-837 skip rules), everything a CTA needs precomputed
@@ -253,6 +287,9 @@ int build_geometry(orb_ctx* c, int w, int h) {
     ORB_CUDA(cudaMalloc(&c->d_wtaps, sizeof(ResizeWord) * h_wtaps.size()));
     ORB_CUDA(cudaMemcpyAsync(c->d_taps, h_taps.data(), sizeof(ResizeTap) * h_taps.size(), cudaMemcpyHostToDevice, c->stream));
     ORB_CUDA(cudaMemcpyAsync(c->d_wtaps, h_wtaps.data(), sizeof(ResizeWord) * h_wtaps.size(), cudaMemcpyHostToDevice, c->stream));
+    if (h_rsegs.empty()) h_rsegs.push_back(ResizeSeg());
+    ORB_CUDA(cudaMalloc(&c->d_rsegs, sizeof(ResizeSeg) * h_rsegs.size()));
+    ORB_CUDA(cudaMemcpyAsync(c->d_rsegs, h_rsegs.data(), sizeof(ResizeSeg) * h_rsegs.size(), cudaMemcpyHostToDevice, c->stream));
     // TMA descriptors for the FAST strip loader (cuTensorMapEncodeTiled through the runtime's driver entry point: no
     // link dependency on libcuda).  Without them the kernel falls back to its LDG -> STS loader.
     c->use_tma = false;

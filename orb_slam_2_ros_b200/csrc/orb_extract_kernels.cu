@@ -672,8 +672,7 @@ int orb_launch_extract(orb_ctx* c, const uint8_t* d_imgs, int pixel_format, int 
         ORB_CUDA(cudaStreamWaitEvent(aux, c->ev_pyr[which], 0));
     }
     ORB_STAGE_MARK(6, aux);
-    { int rc = orb_launch_border(c, g, F, aux); if (rc != ORB_OK) return rc; }                                      // K1 borders
-    ORB_STAGE_MARK(7, aux);
+    ORB_STAGE_MARK(7, aux);   // (the border pass that used to run here is part of the pyramid kernels now)
     { int rc = orb_launch_blur(c, g, F, aux); if (rc != ORB_OK) return rc; }                                        // K5
     ORB_STAGE_MARK(8, aux);
     if (aux != st) ORB_CUDA(cudaEventRecord(c->ev_blur[which], aux));

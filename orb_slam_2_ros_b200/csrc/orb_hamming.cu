@@ -19,7 +19,12 @@
 namespace {
 
 #define HT_THREADS 256
+#ifndef HT_TILE
 #define HT_TILE 256          // database rows per shared-memory stage (8 KB)
+#endif
+#ifndef HAMMING_CTAS_PER_SM
+#define HAMMING_CTAS_PER_SM 4
+#endif
 #define HT_IDX_BITS 23       // local row index bits in a packed key (split length <= 8M rows)
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -35,6 +40,12 @@ __device__ __forceinline__ unsigned lop3_xor3(unsigned a, unsigned b, unsigned c
 }
 #ifndef HAMMING_VARIANT
 #define HAMMING_VARIANT 0
+#endif
+#ifndef HAMMING_GROUP
+#define HAMMING_GROUP 4      // rows per top-2 update group (1 = update after every row)
+#endif
+#ifndef HAMMING_QPT
+#define HAMMING_QPT 2        // queries per thread when there are enough queries
 #endif
 __device__ __forceinline__ unsigned lop3_maj(unsigned a, unsigned b, unsigned c) {
     unsigned d; asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d;
@@ -59,6 +70,31 @@ __device__ __forceinline__ int hamming256(const uint4& a, const uint4& b, const 
 #endif
 }
 
+// the packed key  dist << 23 | row  straight from the four partial popcounts, as a chain of four multiply-adds with multipliers the
+// compiler cannot turn into shifts (kernel argument m23 = 1 << 23): IMAD runs on the FMA pipe, which this kernel leaves idle,
+// while shift / LEA / OR forms would take ALU-pipe slots, the pipe that binds it
+__device__ __forceinline__ unsigned hamming256_key(const uint4& a, const uint4& b, const unsigned (&q)[8], unsigned row, unsigned m23,
+                                                   unsigned m24, unsigned m25) {
+    const unsigned x0 = a.x ^ q[0], x1 = a.y ^ q[1], x2 = a.z ^ q[2], x3 = a.w ^ q[3];
+    const unsigned x4 = b.x ^ q[4], x5 = b.y ^ q[5], x6 = b.z ^ q[6], x7 = b.w ^ q[7];
+    const unsigned s1 = lop3_xor3(x0, x1, x2), c1 = lop3_maj(x0, x1, x2);
+    const unsigned s2 = lop3_xor3(x3, x4, x5), c2 = lop3_maj(x3, x4, x5);
+    const unsigned s3 = lop3_xor3(s1, s2, x6), c3 = lop3_maj(s1, s2, x6);
+    unsigned k;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(k) : "r"(__popc(s3)), "r"(m23), "r"(row));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(k) : "r"(__popc(x7)), "r"(m23));
+#if HAMMING_VARIANT == 1
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(k) : "r"(__popc(c1)), "r"(m24));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(k) : "r"(__popc(c2)), "r"(m24));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(k) : "r"(__popc(c3)), "r"(m24));
+#else
+    const unsigned t1 = lop3_xor3(c1, c2, c3), f1 = lop3_maj(c1, c2, c3);
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(k) : "r"(__popc(t1)), "r"(m24));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(k) : "r"(__popc(f1)), "r"(m25));
+#endif
+    return k;
+}
+
 // the plain form (8 POPC), kept for the issue-rate microbenchmark that defines the popc roofline
 __device__ __forceinline__ int hamming256_popc8(const uint4& a, const uint4& b, const unsigned (&q)[8]) {
     const int s0 = __popc(a.x ^ q[0]) + __popc(a.y ^ q[1]) + __popc(a.z ^ q[2]);
@@ -66,10 +102,15 @@ __device__ __forceinline__ int hamming256_popc8(const uint4& a, const uint4& b, 
     return s0 + s1 + __popc(b.z ^ q[6]) + __popc(b.w ^ q[7]);
 }
 
+#ifdef HAMMING_MINB
+#define HT_BOUNDS __launch_bounds__(HT_THREADS, HAMMING_MINB)
+#else
+#define HT_BOUNDS __launch_bounds__(HT_THREADS)
+#endif
 template <int QPT>
-__global__ void __launch_bounds__(HT_THREADS)
+__global__ void HT_BOUNDS
 hamming_top2_kernel(const uint4* __restrict__ q, int nq, const uint4* __restrict__ db, long long ndb,
-                    long long rows_per_split, uint2* __restrict__ partial, int nq_pad) {
+                    long long rows_per_split, uint2* __restrict__ partial, int nq_pad, unsigned m23, unsigned m24, unsigned m25) {
     __shared__ uint4 sdb[2][HT_TILE * 2];
     const int tid = threadIdx.x;
     const long long r0 = (long long)blockIdx.x * rows_per_split;
@@ -94,7 +135,7 @@ hamming_top2_kernel(const uint4* __restrict__ q, int nq, const uint4* __restrict
         const long long row0 = r0 + (long long)t * HT_TILE;
         const long long chunks = min((long long)HT_TILE, r1 - row0) * 2;
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < 2 * HT_TILE / HT_THREADS; ++k) {
             const int cidx = tid + k * HT_THREADS;
             if (cidx < chunks) cp_async16(&sdb[buf][cidx], db + row0 * 2 + cidx);
         }
@@ -108,8 +149,41 @@ hamming_top2_kernel(const uint4* __restrict__ q, int nq, const uint4* __restrict
         __syncthreads();
         const int rows = (int)min((long long)HT_TILE, nrows - (long long)t * HT_TILE);
         const unsigned idx0 = (unsigned)(t * HT_TILE);
+#if HAMMING_GROUP > 1
+        // rows in groups of HAMMING_GROUP: the 3-op top-2 update (ALU pipe, the binding one) runs only when the smallest key
+        // of the group beats the thread's current second best — after the first few thousand rows that is rare, and the
+        // common case costs 2 min3/min + 1 compare per group instead of 3 min/max per row.  Same result: keys that do not beat
+        // k2 change neither k1 nor k2, and the update order inside a group is the row order.
+        int r = 0;
+        for (; r + HAMMING_GROUP <= rows; r += HAMMING_GROUP) {
+            unsigned key[QPT][HAMMING_GROUP];
+#pragma unroll
+            for (int u = 0; u < HAMMING_GROUP; ++u) {
+                const uint4 a = sdb[buf][2 * (r + u)], b = sdb[buf][2 * (r + u) + 1];
+#pragma unroll
+                for (int j = 0; j < QPT; ++j)
+                    key[j][u] = hamming256_key(a, b, qw[j], idx0 + r + u, m23, m24, m25);
+            }
+#pragma unroll
+            for (int j = 0; j < QPT; ++j) {
+                unsigned m = key[j][0];
+#pragma unroll
+                for (int u = 1; u + 1 < HAMMING_GROUP; u += 2) m = __vimin3_u32(m, key[j][u], key[j][u + 1]);
+                if ((HAMMING_GROUP & 1) == 0) m = min(m, key[j][HAMMING_GROUP - 1]);
+                if (m < k2[j]) {
+#pragma unroll
+                    for (int u = 0; u < HAMMING_GROUP; ++u) {
+                        k2[j] = min(k2[j], max(key[j][u], k1[j]));
+                        k1[j] = min(k1[j], key[j][u]);
+                    }
+                }
+            }
+        }
+        for (; r < rows; ++r) {
+#else
 #pragma unroll 4
         for (int r = 0; r < rows; ++r) {
+#endif
             const uint4 a = sdb[buf][2 * r], b = sdb[buf][2 * r + 1];
 #pragma unroll
             for (int j = 0; j < QPT; ++j) {
@@ -220,9 +294,10 @@ HammingPlan make_plan(int nq, long long ndb, int sms) {
     HammingPlan p;
     p.qpt = (nq > 148 * HT_THREADS / 2) ? 2 : 1;   // enough queries to fill the chip with 2 per thread?
     if (nq >= 1024) p.qpt = 2;
+    if (nq >= 1024 && HAMMING_QPT == 4) p.qpt = 4;
     const int per_cta = HT_THREADS * p.qpt;
     p.grid_y = (nq + per_cta - 1) / per_cta;
-    const int target_ctas = sms * 4;
+    const int target_ctas = sms * HAMMING_CTAS_PER_SM;
     long long nsplit = std::max<long long>(1, target_ctas / p.grid_y);
     nsplit = std::min<long long>(nsplit, std::max<long long>(1, (ndb + 63) / 64));   // >= 64 rows per split
     long long rps = (ndb + nsplit - 1) / nsplit;
@@ -292,12 +367,15 @@ static int db_launch(orb_db* db, const uint8_t* d_q, int nq, orb_top2* d_out) {
     }
     if (db->n > 0) {
         dim3 grid(p.nsplit, p.grid_y);
-        if (p.qpt == 2)
+        if (p.qpt == 4)
+            hamming_top2_kernel<4><<<grid, HT_THREADS, 0, db->stream>>>((const uint4*)d_q, nq, (const uint4*)db->d_rows, db->n,
+                                                                       p.rows_per_split, db->d_partial, p.nq_pad, 1u << HT_IDX_BITS, 2u << HT_IDX_BITS, 4u << HT_IDX_BITS);
+        else if (p.qpt == 2)
             hamming_top2_kernel<2><<<grid, HT_THREADS, 0, db->stream>>>((const uint4*)d_q, nq, (const uint4*)db->d_rows, db->n,
-                                                                       p.rows_per_split, db->d_partial, p.nq_pad);
+                                                                       p.rows_per_split, db->d_partial, p.nq_pad, 1u << HT_IDX_BITS, 2u << HT_IDX_BITS, 4u << HT_IDX_BITS);
         else
             hamming_top2_kernel<1><<<grid, HT_THREADS, 0, db->stream>>>((const uint4*)d_q, nq, (const uint4*)db->d_rows, db->n,
-                                                                       p.rows_per_split, db->d_partial, p.nq_pad);
+                                                                       p.rows_per_split, db->d_partial, p.nq_pad, 1u << HT_IDX_BITS, 2u << HT_IDX_BITS, 4u << HT_IDX_BITS);
         db->launches++;
     }
     if (ev) ORB_CUDA(cudaEventRecord(ev[1], db->stream));

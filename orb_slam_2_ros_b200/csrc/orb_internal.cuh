@@ -56,11 +56,9 @@ struct LevelGeom {
     int fast_resize;           // 1: every output word's source taps fit 3 aligned source words (scale <= 4/3)
     int fast_G, fast_groups;   // FAST strips: cells per CTA, CTAs per cell row
     int fast_cta_base;         // number of FAST CTAs of levels < l (per frame)
-    int border_base;           // number of bordered rows (= border-fill warps) of levels < l (per frame)
-    int border_words;          // words per bordered row that the border kernel may touch
-    int copy_base;             // number of top/bottom row-copy items (words) of levels < l (per frame), padded to CTAs
-    int copy_items;            // row-copy items of this level
-    unsigned inv_wpr;          // ceil(2^32 / copy items per row)
+    int border_words;          // words per bordered row from byte 12 on: left border | interior | right border (the pyramid kernels' row items)
+    unsigned inv_wpr;          // ceil(2^32 / border_words)
+    int nseg, seg_base, seg_threads, stage_bytes;   // staged pyramid kernel: segments of <= 256 bordered words per row, first ResizeSeg, CTA size, dynamic shared memory
     int blur_base, blur_wpr;   // blur: number of thread items of levels < l; words per row
     float scale;               // mvScaleFactor[l]
     float size;                // (float)(int)(PATCH_SIZE * scale)
@@ -72,7 +70,9 @@ struct Geometry {
     int one;                     // = 1: lets kernels build multipliers (1 << k) that the compiler cannot strength-reduce into ALU-pipe shifts
     int total_cells, total_kp_slots, max_node_cap, max_tile_bytes;
     int fast_rows;               // tile rows of the FAST strip kernel = the tallest cell sub-image of this geometry (<= 66): sizes its shared memory and the TMA box
-    int fast_ctas, border_items, border_copy_items, blur_items;   // per-frame grid sizes of the strip / border / blur kernels
+    int fast_ctas, blur_items;   // per-frame grid sizes of the strip / blur kernels
+    int l0_ni, l0_border_first;  // level-0 pass: 16-byte vectors wholly inside the interior per row; first item of the border vectors (a multiple of 32)
+    unsigned l0_inv_ni, l0_inv_nb;   // ceil(2^32 / l0_ni), ceil(2^32 / (pitch / 16 - l0_ni))
     long long pyr_frame_total;   // not used for addressing (level-major layout), informational
     LevelGeom lv[ORB_MAX_LEVELS];
 };
@@ -88,6 +88,11 @@ struct __align__(16) ResizeWord {  // 4 adjacent destination columns (one output
     unsigned sel01;      // PRMT selector over (A, B): (S[s], S[s+1]) of column 0 in bytes 0-1, of column 1 in bytes 2-3
     unsigned sel23;      // the same for columns 2 and 3
     unsigned cc[4];      // c0 | c1 << 16 per column (Q11)
+};
+struct ResizeSeg {   // one column segment of the staged pyramid kernel
+    int w0;              // first staged source word of a row (a multiple of 4: 16-byte aligned)
+    int nbytes;          // staged bytes per source row (a multiple of 16)
+    int bw0, nw;         // first bordered word, number of words
 };
 // TMA descriptors of the pyramid levels (dims: row bytes, rows, frames of the arena) for the FAST strip loader
 struct FastTmaps { CUtensorMap m[ORB_MAX_LEVELS]; };
@@ -156,6 +161,7 @@ struct orb_ctx {
     int* d_kept_count = nullptr;                        // [max_batch][nlevels]
     ResizeTap* d_taps = nullptr;
     ResizeWord* d_wtaps = nullptr;
+    ResizeSeg* d_rsegs = nullptr;
     FastStrip* d_strips = nullptr;
     FastTmaps tmaps;              // valid when use_tma
     FastTmaps* d_tmaps = nullptr; // device copy (the TMA unit reads the descriptor from global memory)
@@ -192,7 +198,6 @@ int orb_profile_harvest(orb_ctx* c, int slot);
 int orb_launch_pyramid(orb_ctx* c, const Geometry& g, const uint8_t* d_imgs, int pixel_format, int nframes, size_t row_stride,
                        size_t frame_stride, cudaStream_t st, int phase = 0, int* tail_first_out = nullptr);
 inline int orb_pix_channels(int fmt) { return fmt == ORB_PIX_GRAY8 ? 1 : (fmt == ORB_PIX_BGR8 || fmt == ORB_PIX_RGB8) ? 3 : 4; }
-int orb_launch_border(orb_ctx* c, const Geometry& g, int nframes, cudaStream_t st);
 void orb_carveout_pyramid(int pct);
 void orb_carveout_blur(int pct);
 void orb_carveout_fast(int pct);
