@@ -114,7 +114,7 @@ struct __align__(16) FastStrip {   // one CTA of fast_strip_kernel: up to fast_G
 #define ORB_BLUR_ROWS 16   // output rows per blur thread
 #endif
 #ifndef ORB_RESIZE_ROWS
-#define ORB_RESIZE_ROWS 8  // output rows per resize thread
+#define ORB_RESIZE_ROWS 16 // output rows per pyramid-kernel thread (throughput shape)
 #endif
 
 // 64-bit corner record: max() over records picks the reference's winner inside a quadtree node:

@@ -21,6 +21,10 @@
 
 namespace {
 
+#ifndef RESIZE_UNROLL
+#define RESIZE_UNROLL 2   // row pairs per unrolled iteration of the staged kernel's full-strip loop
+#endif
+
 // ---- level 0: the bordered image straight from the caller's frame ----------------------------------------------------
 // One thread = one 32-bit word of a bordered row (words 3 .. 3 + border_words of the row: bytes 12 ..).  Interior words of
 // a 4-byte-aligned gray frame are plain word copies; border words are byte-reversed unaligned windows of the same input
@@ -242,38 +246,90 @@ pyr_level_kernel(uint8_t* __restrict__ pyr, const ResizeTap* __restrict__ taps, 
 // and all threads wait on the mbarrier, then run the same row loop out of shared memory.
 __device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
+// row loop of the staged kernel: everything a row needs besides the pixels comes from ONE LDS.128 of a per-CTA row record
+// {byte offset of the upper staged source row, of the lower one, b0 << 16, b1 << 16}; full strips run fully unrolled
+template <int ROWS, bool MIRROR, bool FULL>
+__device__ __forceinline__ void staged_rows(const unsigned char* __restrict__ sthread, const uint4* __restrict__ s_row, unsigned* __restrict__ Dbase,
+                                            unsigned doff, unsigned dpw, const ResizeWord& t, int y0, int nrows, int h) {
+    unsigned ha[4], hb[4];                                // horizontal results >> 4 of two source rows
+    unsigned tag = 0xFFFFFFFFu;                           // staged row (byte offset) held by the set that was "lower" in the previous output row
+    auto row = [&](int i, unsigned (&up)[4], unsigned (&lo)[4]) {
+        const uint4 r = s_row[i];
+        unsigned w[3];
+        if (r.x != tag) {                                 // first row of the strip, or the source rows advanced by two
+            const unsigned* p = reinterpret_cast<const unsigned*>(sthread + r.x);
+            w[0] = p[0]; w[1] = p[1]; w[2] = p[2];
+            hcalc4(w, t, up);
+        }
+        const unsigned* p = reinterpret_cast<const unsigned*>(sthread + r.y);
+        w[0] = p[0]; w[1] = p[1]; w[2] = p[2];
+        hcalc4(w, t, lo);
+        tag = r.y;
+        unsigned s[4];                                    // 4 * out + (0..3) - 2, 10 bits
+#pragma unroll
+        for (int q = 0; q < 4; ++q) s[q] = __umulhi(r.z, up[q]) + __umulhi(r.w, lo[q]);
+        const unsigned E = __byte_perm(s[0], s[2], 0x5410) + 0x00020002u;   // s0 | s2 << 16, rounding constant for both lanes
+        const unsigned O = __byte_perm(s[1], s[3], 0x5410) + 0x00020002u;   // s1 | s3 << 16
+        unsigned v;
+        asm("lop3.b32 %0, %1, %2, %3, 0xCA;" : "=r"(v) : "r"(0x00FF00FFu), "r"(E >> 2), "r"(O << 6));   // mask ? E >> 2 : O << 6
+        const int y = y0 + i;
+        Dbase[doff + (unsigned)(y + ORB_EDGE) * dpw] = v;
+        if (MIRROR) {
+            if ((unsigned)(y - 1) < (unsigned)ORB_EDGE) Dbase[doff + (unsigned)(ORB_EDGE - y) * dpw] = v;                      // y in [1, 19] -> row 19 - y
+            if ((unsigned)(h - 2 - y) < (unsigned)ORB_EDGE) Dbase[doff + (unsigned)(2 * h + ORB_EDGE - 2 - y) * dpw] = v;       // y in [h-20, h-2] -> row 2h + 17 - y
+        }
+    };
+    if (FULL) {
+        constexpr int kUnroll = RESIZE_UNROLL;
+#pragma unroll kUnroll
+        for (int i = 0; i < ROWS; i += 2) { row(i, ha, hb); row(i + 1, hb, ha); }
+    } else {
+        for (int i = 0; i < nrows; i += 2) {
+            row(i, ha, hb);
+            if (i + 1 < nrows) row(i + 1, hb, ha);
+        }
+    }
+}
+
 template <int ROWS>
 __global__ void __launch_bounds__(256, RESIZE_MINB)
 pyr_level_staged_kernel(uint8_t* __restrict__ pyr, const ResizeTap* __restrict__ taps, const ResizeWord* __restrict__ wtaps,
                         const ResizeSeg* __restrict__ segs, int level, const __grid_constant__ Geometry g) {
     extern __shared__ __align__(128) unsigned char stage_raw[];
-    __shared__ uint2 s_ty[ROWS];
+    __shared__ __align__(16) uint4 s_row[ROWS];
     __shared__ __align__(8) unsigned long long s_mbar;
+    __shared__ unsigned s_span[2];
     const LevelGeom& L = g.lv[level];
     const LevelGeom& P = g.lv[level - 1];
     const int f = blockIdx.y, tid = threadIdx.x;
     const int strip = blockIdx.x / L.nseg, seg = blockIdx.x - strip * L.nseg;
     const ResizeSeg sg = segs[L.seg_base + seg];
-    const int y0 = strip * ROWS, y1 = min(y0 + ROWS, L.h);
+    const int y0 = strip * ROWS, nrows = min(ROWS, L.h - y0);
     const uint2* ytab = reinterpret_cast<const uint2*>(taps + L.ytab);   // ResizeTap = {u16 s0, u16 s1, s16 c0, s16 c1}
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&s_mbar)), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (tid < y1 - y0) s_ty[tid] = __ldg(ytab + y0 + tid);
-    __syncthreads();
-    const unsigned s_first = s_ty[0].x & 0xFFFFu;
-    if (tid == 0) {
-        const unsigned nrows = (s_ty[y1 - y0 - 1].x >> 16) - s_first + 1u;   // source rows s_first .. s1(last row): ascending taps
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&s_mbar)), "r"(nrows * (unsigned)sg.nbytes) : "memory");
+        // source rows s0(first row) .. s1(last row): the taps ascend with y
+        const unsigned s_first = __ldg(ytab + y0).x & 0xFFFFu, s_last = __ldg(ytab + y0 + nrows - 1).x >> 16;
+        const unsigned n = s_last - s_first + 1u;
+        s_span[0] = s_first;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&s_mbar)), "r"(n * (unsigned)sg.nbytes) : "memory");
         const uint8_t* src = pyr + P.base + (long long)f * P.frame_stride + P.ioff + (long long)s_first * P.pitch + 4 * sg.w0;
-        for (unsigned r = 0; r < nrows; ++r)
+        for (unsigned r = 0; r < n; ++r)
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          ::"r"(smem_addr(stage_raw + r * sg.nbytes)), "l"(src + (size_t)r * P.pitch), "r"(sg.nbytes), "r"(smem_addr(&s_mbar)) : "memory");
+    }
+    __syncthreads();
+    if (tid < nrows) {
+        const uint2 ty = __ldg(ytab + y0 + tid);
+        const unsigned s_first = s_span[0];
+        s_row[tid] = make_uint4(((ty.x & 0xFFFFu) - s_first) * (unsigned)sg.nbytes, ((ty.x >> 16) - s_first) * (unsigned)sg.nbytes,
+                                ty.y << 16, ty.y & 0xFFFF0000u);   // ((b*(h>>4))>>16) == umulhi(b<<16, h>>4): 0 <= b <= 2048, h>>4 < 2^15
     }
     const bool active = tid < sg.nw;
     const int bw = sg.bw0 + (active ? tid : 0);
     const ResizeWord t = wtaps[L.xwtab + bw];
+    __syncthreads();
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -285,13 +341,12 @@ pyr_level_staged_kernel(uint8_t* __restrict__ pyr, const ResizeTap* __restrict__
         "}\n" ::"r"(smem_addr(&s_mbar)), "r"(0) : "memory");
     if (!active) return;
     unsigned* Dbase = reinterpret_cast<unsigned*>(pyr + L.base + (long long)f * L.frame_stride);   // bordered row 0
-    const unsigned ppw = (unsigned)sg.nbytes >> 2, dpw = (unsigned)L.pitch >> 2;
-    const unsigned soff = (unsigned)(t.wb - sg.w0) - s_first * ppw;   // staged word of (source row s, word wb + k) = soff + s * ppw + k
-    const unsigned* stage = reinterpret_cast<const unsigned*>(stage_raw);
-    if (y0 <= ORB_EDGE || y1 > L.h - ORB_EDGE - 2)
-        level_rows<ROWS, false, true>(stage, soff, ppw, Dbase, 3u + (unsigned)bw, dpw, s_ty - y0, t, y0, y1, L.h);
-    else
-        level_rows<ROWS, false, false>(stage, soff, ppw, Dbase, 3u + (unsigned)bw, dpw, s_ty - y0, t, y0, y1, L.h);
+    const unsigned dpw = (unsigned)L.pitch >> 2;
+    const unsigned char* sthread = stage_raw + 4 * (t.wb - sg.w0);   // this thread's first staged word of staged row 0
+    const bool mirror = y0 <= ORB_EDGE || y0 + nrows > L.h - ORB_EDGE - 2;
+    if (mirror) staged_rows<ROWS, true, false>(sthread, s_row, Dbase, 3u + (unsigned)bw, dpw, t, y0, nrows, L.h);
+    else if (nrows == ROWS) staged_rows<ROWS, false, true>(sthread, s_row, Dbase, 3u + (unsigned)bw, dpw, t, y0, nrows, L.h);
+    else staged_rows<ROWS, false, false>(sthread, s_row, Dbase, 3u + (unsigned)bw, dpw, t, y0, nrows, L.h);
 }
 
 // ---- fused tail: levels [first, nlevels) of one frame in ONE launch --------------------------------------------------
