@@ -27,6 +27,9 @@
 namespace {
 
 #define FS_THREADS 256
+#ifndef FS_QUICK
+#define FS_QUICK 2         // stage A's quick test: 2 = word pairs on u16 high-byte lanes, 1 = single words on widened s16 lanes
+#endif
 #define FS_WARPS (FS_THREADS / 32)
 #define FS_PITCH 256       // bytes per shared-memory row = one TMA box row: alignment shift (<= 19) + tile (<= 237)
 #define FS_ROWS 66         // cell sub-image height <= hCell + 6 <= 66
@@ -40,7 +43,7 @@ namespace {
 // 640x480 instead of the worst case 66), which is what decides how many CTAs fit an SM: 30 KB -> 6-7 CTAs, 44 KB -> 5.
 #define FS_TILE_BYTES(rows) ((rows) * FS_PITCH)
 #define FS_SCORE_BYTES(rows) (((rows) - 4) * FS_PITCH)      // evaluated rows (rows - 6) + a zero row above and below
-#define FS_SMEM(rows) (FS_TILE_BYTES(rows) + FS_CAND_BYTES + FS_SCORED_BYTES + FS_SCORE_BYTES(rows) + 128)
+#define FS_SMEM(rows) (FS_TILE_BYTES(rows) + FS_CAND_BYTES + FS_SCORED_BYTES + FS_SCORE_BYTES(rows) + 256)   // 128 for the alignment + 128 readable bytes in front of the tile
 #define FS_OUT_CAP(rows) ((FS_TILE_BYTES(rows) + FS_CAND_BYTES) / 8)   // records that fit the (dead) tile + candidate segments; anything beyond goes straight to global
 
 // exact FAST score of the pixel at t (shared-memory tile): both polarities in one s16x2 min/max tree on the packed
@@ -111,6 +114,30 @@ __device__ __forceinline__ unsigned quick2(unsigned c, unsigned r0, unsigned r8,
     return ((bl | dl) ? 1u : 0u) | ((bh | dh) ? 2u : 0u);
 }
 
+// The same test on UNSIGNED 16-bit lanes whose HIGH bytes hold the pixels and whose low bytes are don't-care: u16 order is
+// lexicographic in (pixel, low byte), so the high byte of every min / max is the min / max of the pixels and a raw tile
+// word serves its odd pixels as it is (its even pixels after << 8) — no byte-to-halfword widening (18 PRMT per word in
+// quick2).  With K = t << 8 the comparisons  minmax >= C + K  and  C - K >= maxmin  can only err towards "pass" (the low
+// bytes act below the pixel difference t + 1 the true condition demands): false candidates are scored exactly like any
+// other, a true corner is never lost.  The centre is clamped so that C + K / C - K cannot wrap in a lane (saturated
+// regions would otherwise pass wholesale).  BLO / BHI: the result bits of the low / high lane.
+template <unsigned BLO, unsigned BHI>
+__device__ __forceinline__ unsigned quick_u16(unsigned C, unsigned a0, unsigned a8, unsigned a4, unsigned a12, unsigned a2, unsigned a10,
+                                              unsigned a6, unsigned a14, unsigned K, unsigned NK, unsigned LIMB) {
+    const unsigned minmax = __vminu2(__vimin3_u16x2(__vmaxu2(a0, a8), __vmaxu2(a4, a12), __vmaxu2(a2, a10)), __vmaxu2(a6, a14));
+    const unsigned maxmin = __vmaxu2(__vimax3_u16x2(__vminu2(a0, a8), __vminu2(a4, a12), __vminu2(a2, a10)), __vminu2(a6, a14));
+    bool bh, bl, dh, dl;
+    __vibmax_u16x2(minmax, __vadd2(__vminu2(C, LIMB), K), &bh, &bl);    // minmax >= min(C, 0xFFFF - K) + K
+    __vibmax_u16x2(__vadd2(__vmaxu2(C, K), NK), maxmin, &dh, &dl);      // max(C, K) - K >= maxmin
+    return ((bl | dl) ? BLO : 0u) | ((bh | dh) ? BHI : 0u);
+}
+// 4 candidate bits of one tile word: odd pixels from the raw words, even pixels from the words << 8
+__device__ __forceinline__ unsigned quick_word(unsigned c, unsigned r0, unsigned r8, unsigned r4, unsigned r12, unsigned r2, unsigned r10,
+                                               unsigned r6, unsigned r14, unsigned K, unsigned NK, unsigned LIMB) {
+    return quick_u16<2u, 8u>(c, r0, r8, r4, r12, r2, r10, r6, r14, K, NK, LIMB) |
+           quick_u16<1u, 4u>(c << 8, r0 << 8, r8 << 8, r4 << 8, r12 << 8, r2 << 8, r10 << 8, r6 << 8, r14 << 8, K, NK, LIMB);
+}
+
 template <bool TMA>
 #ifndef FS_MINB
 #define FS_MINB 6
@@ -120,7 +147,7 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
                   int* __restrict__ corner_count, const __grid_constant__ Geometry g, const FastTmaps* __restrict__ tm, int f0) {
     extern __shared__ __align__(1024) uint8_t fs_smem_raw[];
     // the TMA destination must be 128-byte aligned: align by hand (static shared variables precede the dynamic window)
-    uint8_t* fs_smem = fs_smem_raw + ((128u - (smem_u32(fs_smem_raw) & 127u)) & 127u);
+    uint8_t* fs_smem = fs_smem_raw + ((128u - (smem_u32(fs_smem_raw) & 127u)) & 127u) + 128;   // (the pair walk of stage A may read the word left of the tile's first one)
     uint8_t* tile = fs_smem;                                                                     // FS_ROWS x FS_PITCH pixels
     const int tile_bytes = FS_TILE_BYTES(g.fast_rows), out_cap = FS_OUT_CAP(g.fast_rows);
     unsigned short* cand = reinterpret_cast<unsigned short*>(fs_smem + tile_bytes);               // per-warp segments
@@ -132,6 +159,7 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
     __shared__ int s_bpre[FS_MAXG + 1], s_bw0[FS_MAXG], s_bnw[FS_MAXG];   // stage B: per empty cell word-item prefix, first word, words per row
     __shared__ unsigned s_binv[FS_MAXG], s_bmf[FS_MAXG], s_bml[FS_MAXG];
     __shared__ __align__(8) unsigned long long s_mbar;
+    __shared__ uint8_t s_pvm[40];                          // stage A: valid-pixel mask of the word pairs of a row
 
     const int f = blockIdx.y;
     const FastStrip S = strips[blockIdx.x];               // host-precomputed (uniform loads)
@@ -166,6 +194,11 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
         }
     }
     if (threadIdx.x < FS_MAXG) s_any[threadIdx.x] = 0;
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + S.np) {   // valid pixels of pair q: smem bytes [sb_lo, sb_hi) inside [4 * (w0p + 2q), + 8)
+        const int b0 = 4 * (S.w0p + 2 * ((int)threadIdx.x - 64));
+        const int lo = max(S.a + 3 - b0, 0), hi = min(S.a + 3 + (S.tw - 6) - b0, 8);
+        s_pvm[threadIdx.x - 64] = (uint8_t)(hi > lo ? ((1u << hi) - 1u) & ~((1u << lo) - 1u) : 0u);
+    }
     if (threadIdx.x == 0) { s_nscored = 0; s_nout = 0; }
     for (int k = threadIdx.x; k < (eh + 2) * (FS_PITCH / 16); k += FS_THREADS)
         reinterpret_cast<uint4*>(score)[k] = make_uint4(0u, 0u, 0u, 0u);
@@ -185,6 +218,50 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
             score[(r + 1) * FS_PITCH + sb] = (uint8_t)sc;
             const int o = atomicAdd(&s_nscored, 1);
             if (o < FS_SCAP) scored[o] = (unsigned short)(r * FS_PITCH + sb);
+        }
+    };
+    // warp-level compaction of the per-lane candidate masks + exact scores.  decode(bit) -> tile code (row * FS_PITCH + byte) of
+    // candidate bit `bit` of this lane's mask
+    auto compact_score = [&](unsigned long long cmask, auto&& decode) {
+        const int cnt = __popcll(cmask);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        const int wtotal = __shfl_sync(0xffffffffu, incl, 31);
+        unsigned short* seg = cand + warp * FS_WCAP;
+        if (wtotal <= FS_WCAP) {
+            // every lane appends its own candidates (set bits of its mask) at its prefix offset; at iniThFAST a lane
+            // holds only a few, so walking the set bits is cheaper than a uniform walk over all words
+            int o = incl - cnt;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                unsigned mm = half ? (unsigned)(cmask >> 32) : (unsigned)cmask;
+                while (mm) {
+                    const int bit = __ffs((int)mm) - 1;
+                    mm &= mm - 1u;
+                    seg[o++] = (unsigned short)decode(bit + 32 * half);
+                }
+            }
+            __syncwarp();
+            // 1b: exact score of the warp's candidates
+            for (int k = lane; k < wtotal; k += 32) {
+                const int code = seg[k];
+                const int r = (int)__umulhi((unsigned)code, 0xFFFFFFFFu / FS_PITCH + 1u);
+                score_one(r, code - r * FS_PITCH);
+            }
+            __syncwarp();
+        } else {
+            // segment overflow (a warp with > 448 candidates): score in place, lane by lane
+            while (cmask) {
+                const int bit = __ffsll((long long)cmask) - 1;
+                cmask &= cmask - 1ull;
+                const int code = decode(bit);
+                const int r = (int)__umulhi((unsigned)code, 0xFFFFFFFFu / FS_PITCH + 1u);
+                score_one(r, code - r * FS_PITCH);
+            }
         }
     };
     // One candidate pass over `total` word items (<= 60 * 64: at most 15 iterations of 256 threads); map(k) gives the
@@ -218,53 +295,53 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
             }
             cmask |= (unsigned long long)m << (4 * it);
         }
-        // warp-level compaction: exclusive prefix of the per-lane counts
-        const int cnt = __popcll(cmask);
-        int incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int y = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += y;
+        compact_score(cmask, [&](int bit) {
+            int r, wd;
+            unsigned vm;
+            map(threadIdx.x + (bit >> 2) * FS_THREADS, r, wd, vm);
+            return r * FS_PITCH + (wd << 2) + (bit & 3);
+        });
+    };
+    // Stage A's candidate pass over WORD PAIRS (8 pixels of one row per item, <= 8 items per thread): the 18 tile words an
+    // item needs are 11 loads (4 of them LDS.64) and 10 funnel shifts instead of 2 x (11 + 6), and the u16 high-byte form of
+    // the quick test (quick_u16) needs no widening.  Pair q of a row = tile words w0p + 2q, w0p + 2q + 1 (w0p even).
+    auto pair_pass = [&](const int th) {
+        const unsigned K = ((unsigned)th << 8) * 0x10001u, NK = ((0x10000u - ((unsigned)th << 8)) & 0xFFFFu) * 0x10001u, LIMB = 0xFFFFFFFFu - K;
+        const int np = S.np, w0p = S.w0p, total = eh * np;
+        const unsigned inv_np = S.inv_np;
+        unsigned long long cmask = 0ull;
+        int it = 0;
+        for (int k = threadIdx.x; k < total; k += FS_THREADS, ++it) {
+            const int r = (int)__umulhi((unsigned)k, inv_np), q = k - r * np;
+            constexpr int P = FS_PITCH / 4;
+            const unsigned* row = reinterpret_cast<const unsigned*>(tile + (r + 3) * FS_PITCH) + w0p + 2 * q;   // centre row, 8-byte aligned
+            const uint2 c = *reinterpret_cast<const uint2*>(row);
+            const unsigned wl = row[-1], wr = row[2];
+            const uint2 u = *reinterpret_cast<const uint2*>(row + 3 * P), d = *reinterpret_cast<const uint2*>(row - 3 * P);   // (0,+3) (0,-3)
+            const unsigned* rp = row + 2 * P;
+            const unsigned* rm = row - 2 * P;
+            const uint2 pp = *reinterpret_cast<const uint2*>(rp), mm = *reinterpret_cast<const uint2*>(rm);
+            const unsigned pl = rp[-1], pr = rp[2], ml = rm[-1], mr = rm[2];
+            const unsigned pmid = __funnelshift_r(pp.x, pp.y, 16), mmid = __funnelshift_r(mm.x, mm.y, 16);   // (+2,.) of word 0 = (-2,.) of word 1
+            const unsigned m0 = quick_word(c.x, u.x, d.x, __funnelshift_r(c.x, c.y, 24), __funnelshift_r(wl, c.x, 8),           // (+3,0) (-3,0)
+                                           pmid, __funnelshift_r(ml, mm.x, 16),                                                // (+2,+2) (-2,-2)
+                                           mmid, __funnelshift_r(pl, pp.x, 16), K, NK, LIMB);                                  // (+2,-2) (-2,+2)
+            const unsigned m1 = quick_word(c.y, u.y, d.y, __funnelshift_r(c.y, wr, 24), __funnelshift_r(c.x, c.y, 8),
+                                           __funnelshift_r(pp.y, pr, 16), mmid,
+                                           __funnelshift_r(mm.y, mr, 16), pmid, K, NK, LIMB);
+            const unsigned m = (m0 | (m1 << 4)) & s_pvm[q];
+            cmask |= (unsigned long long)m << (8 * it);
         }
-        const int wtotal = __shfl_sync(0xffffffffu, incl, 31);
-        unsigned short* seg = cand + warp * FS_WCAP;
-        if (wtotal <= FS_WCAP) {
-            // every lane appends its own candidates (set bits of its mask) at its prefix offset; at iniThFAST a lane
-            // holds only a few, so walking the set bits is cheaper than a uniform walk over all words
-            int o = incl - cnt;
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                unsigned mm = half ? (unsigned)(cmask >> 32) : (unsigned)cmask;
-                while (mm) {
-                    const int bit = __ffs((int)mm) - 1;
-                    mm &= mm - 1u;
-                    int r, wd;
-                    unsigned vm;
-                    map(threadIdx.x + ((bit >> 2) + 8 * half) * FS_THREADS, r, wd, vm);
-                    seg[o++] = (unsigned short)(r * FS_PITCH + (wd << 2) + (bit & 3));
-                }
-            }
-            __syncwarp();
-            // 1b: exact score of the warp's candidates
-            for (int k = lane; k < wtotal; k += 32) {
-                const int code = seg[k];
-                const int r = (int)__umulhi((unsigned)code, 0xFFFFFFFFu / FS_PITCH + 1u);
-                score_one(r, code - r * FS_PITCH);
-            }
-            __syncwarp();
-        } else {
-            // segment overflow (a warp with > 896 candidates): score in place, lane by lane
-            while (cmask) {
-                const int bit = __ffsll((long long)cmask) - 1;
-                cmask &= cmask - 1ull;
-                int r, wd;
-                unsigned vm;
-                map(threadIdx.x + (bit >> 2) * FS_THREADS, r, wd, vm);
-                score_one(r, (wd << 2) + (bit & 3));
-            }
-        }
+        compact_score(cmask, [&](int bit) {
+            const int k = threadIdx.x + (bit >> 3) * FS_THREADS;
+            const int r = (int)__umulhi((unsigned)k, inv_np), q = k - r * np;
+            return r * FS_PITCH + ((w0p + 2 * q) << 2) + (bit & 7);
+        });
     };
     // stage A: the whole strip at iniThFAST (a cell that has an NMS maximum >= iniThFAST never needs anything lower)
+#if FS_QUICK == 2
+    pair_pass(tini);
+#else
     cand_pass(eh * nw,
               [&](int k, int& r, int& wd, unsigned& vm) {
                   r = (int)__umulhi((unsigned)k, inv_nw);
@@ -272,6 +349,7 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
                   vm = (wd == wlo ? vfirst : 0xFu) & (wd == whi ? vlast : 0xFu);
               },
               tini, false);
+#endif
     __syncthreads();
 
     // ---- pass 2: NMS (strict >, neighbours outside the cell's evaluated area count as 0) of the scores >= iniThFAST;

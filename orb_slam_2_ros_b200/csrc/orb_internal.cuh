@@ -108,7 +108,8 @@ struct __align__(16) FastStrip {   // one CTA of fast_strip_kernel: up to fast_G
     int level, i, j0, ncell;       // cell row, first cell column, number of valid cells
     int iniY, ch, X0, tw;          // cell sub-image rows [iniY, iniY+ch), tile columns [X0, X0+tw) (interior coords)
     int a, lw, nw, wlo;            // smem byte shift, words loaded per row, words with evaluated pixels, first such word
-    unsigned inv_lw, inv_nw, inv_wc, pad;   // ceil(2^32 / x) magic numbers for the index divisions
+    unsigned inv_lw, inv_nw, inv_wc, inv_np;   // ceil(2^32 / x) magic numbers for the index divisions
+    int np, w0p, pad0, pad1;       // stage A walks word PAIRS: pairs per row, first pair's first word (even, <= wlo)
 };
 #ifndef ORB_BLUR_ROWS
 #define ORB_BLUR_ROWS 16   // output rows per blur thread
