@@ -492,8 +492,19 @@ static int ensure_device(orb_ctx* c) {
                 }
                 tab[a * 297 + item] = make_uint2(wu, wv);
             }
-        ORB_CUDA(cudaMalloc(&c->d_mom_tab, sizeof(uint2) * tab.size()));
+        // behind it: the rBRIEF pattern (ORBextractor.cc:150-408) as float4[8][32] = (x0, y0, x1, y1) of bit k of descriptor byte i at
+        // [k * 32 + i] — the layout orient_describe_kernel keeps in shared memory, fetched with one coalesced 16-byte load per thread
+        static const int pattern[1024] = {
+#include "orb_pattern_31.inc"
+        };
+        static_assert(sizeof(uint2) * 4 * 297 % 16 == 0, "the pattern table must start 16-byte aligned");
+        std::vector<float> pat(4 * 256);
+        for (int k = 0; k < 8; ++k)
+            for (int i = 0; i < 32; ++i)
+                for (int e = 0; e < 4; ++e) pat[4 * (k * 32 + i) + e] = (float)pattern[i * 32 + 4 * k + e];
+        ORB_CUDA(cudaMalloc(&c->d_mom_tab, sizeof(uint2) * tab.size() + sizeof(float) * pat.size()));
         ORB_CUDA(cudaMemcpy(c->d_mom_tab, tab.data(), sizeof(uint2) * tab.size(), cudaMemcpyHostToDevice));
+        ORB_CUDA(cudaMemcpy(c->d_mom_tab + tab.size(), pat.data(), sizeof(float) * pat.size(), cudaMemcpyHostToDevice));
     }
     if (!c->st_h2d) {
         ORB_CUDA(cudaStreamCreateWithFlags(&c->st_h2d, cudaStreamNonBlocking));

@@ -14,9 +14,6 @@
 
 namespace {
 
-__constant__ int c_pattern[1024] = {
-#include "orb_pattern_31.inc"
-};
 __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
 
 // ======================================================================================================
@@ -399,11 +396,9 @@ orient_describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restric
     }
     if (blockIdx.x * (OD_WARPS * KPW) >= total) return;   // uniform per CTA
     // pattern: byte `i` of the descriptor uses points 16 i .. 16 i + 15; s_pat[k * 32 + i] = (x0, y0, x1, y1) of bit k
-    {
-        const int k = threadIdx.x >> 5, i = threadIdx.x & 31;
-        const int* p = c_pattern + i * 32 + 4 * k;   // one-off divergent constant reads, 4 per thread
-        s_pat[k * 32 + i] = make_float4((float)p[0], (float)p[1], (float)p[2], (float)p[3]);
-    }
+    // (the table lies behind the moment weights, already in this layout: one coalesced 16-byte load per thread; reading it from
+    // the __constant__ pattern cost 128 serialised constant-cache accesses per warp, 15 % of the kernel's stall samples)
+    s_pat[threadIdx.x] = __ldg(reinterpret_cast<const float4*>(mom_tab + 4 * OD_ITEMS) + threadIdx.x);
     // ---- output index -> (level, index in level) for this warp's 4 keypoints ----
     const int od_row = lane / 9, od_word = lane - 9 * od_row;   // phase 1: this lane's (row within a 3-row step, word) item
     int lv[KPW], px[KPW], py[KPW], off[KPW], sc[KPW];
@@ -469,16 +464,17 @@ orient_describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restric
             if (lane < 27) {
                 const uint2* tab = mom_tab + a * OD_ITEMS + lane;
                 const unsigned pw3 = 3u * ((unsigned)L.pitch >> 2);
-                const unsigned* p = reinterpret_cast<const unsigned*>(p0) + od_row * ((unsigned)L.pitch >> 2) + od_word;
+                const unsigned* pb = reinterpret_cast<const unsigned*>(p0);   // warp-uniform base + 32-bit word offsets
+                unsigned po = od_row * ((unsigned)L.pitch >> 2) + od_word;
 #pragma unroll
                 for (int j = 0; j < 11; ++j) {
                     if (j < 10 || od_row == 0) {
-                        const unsigned pix = __ldg(p);
-                        const uint2 w = __ldg(tab);
+                        const unsigned pix = __ldg(pb + po);
+                        const uint2 w = __ldg(tab + 27 * j);
                         m10 = dp4a_su(w.x, pix, m10);                             // sum u * I
                         m01 = dp4a_su(w.y, pix, m01);                             // sum v * I (weights v inside the circular extent, else 0)
                     }
-                    p += pw3; tab += 27;
+                    po += pw3;
                 }
             }
         }
@@ -513,16 +509,21 @@ orient_describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restric
         else asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
         const uint8_t* b2 = &s_win[warp][0];
-        const unsigned centre = OD_TAPR * wpitch + OD_TAPR + (unsigned)((px[q] - OD_TAPR) & 15);
+        // cvRound (round half to even) of the rotated tap coordinates without a float -> int conversion (F2I runs on the
+        // quarter-rate XU pipe): x + 1.5 * 2^23 rounds x to an integer n in the same mode and leaves 0x4B400000 + n in the
+        // register; the two biases fold into the window offset (unsigned arithmetic modulo 2^32)
+        const float kMagic = 12582912.f;
+        const unsigned kBits = 0x4B400000u;
+        const unsigned centre = OD_TAPR * wpitch + OD_TAPR + (unsigned)((px[q] - OD_TAPR) & 15) - kBits * (unsigned)wpitch - kBits;
         unsigned val = 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const float4 pt = s_pat[k * 32 + lane];
-            const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(pt.x, b), __fmul_rn(pt.y, a)));
-            const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(pt.x, a), __fmul_rn(pt.y, b)));
-            const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(pt.z, b), __fmul_rn(pt.w, a)));
-            const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(pt.z, a), __fmul_rn(pt.w, b)));
-            const unsigned t0 = b2[centre + (unsigned)(r0 * wpitch + c0)], t1 = b2[centre + (unsigned)(r1 * wpitch + c1)];
+            const unsigned r0 = __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(pt.x, b), __fmul_rn(pt.y, a)), kMagic));
+            const unsigned c0 = __float_as_uint(__fadd_rn(__fsub_rn(__fmul_rn(pt.x, a), __fmul_rn(pt.y, b)), kMagic));
+            const unsigned r1 = __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(pt.z, b), __fmul_rn(pt.w, a)), kMagic));
+            const unsigned c1 = __float_as_uint(__fadd_rn(__fsub_rn(__fmul_rn(pt.z, a), __fmul_rn(pt.w, b)), kMagic));
+            const unsigned t0 = b2[centre + r0 * (unsigned)wpitch + c0], t1 = b2[centre + r1 * (unsigned)wpitch + c1];
             val |= (unsigned)(t0 < t1) << k;
         }
         __syncwarp();   // every lane has read the window: the next keypoint's copy may overwrite it
@@ -534,16 +535,18 @@ orient_describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restric
         w |= __shfl_down_sync(0xffffffffu, val, 3) << 24;
         const long long o = (long long)f * cap + off[q];
         if ((lane & 3) == 0) reinterpret_cast<unsigned*>(desc_out + o * 32)[lane >> 2] = w;
-        if (lane == 0) {
-            orb_kp kp;
-            kp.x = (l != 0) ? __fmul_rn((float)px[q], L.scale) : (float)px[q];   // ORBextractor.cc:1139-1145
-            kp.y = (l != 0) ? __fmul_rn((float)py[q], L.scale) : (float)py[q];
-            kp.size = L.size;
-            kp.angle = s_ang[kq];
-            kp.response = (float)sc[q];
-            kp.octave = l;
-            kp.class_id = -1;
-            kps_out[o] = kp;
+        {   // the 7 words of the cv::KeyPoint-compatible record, one per lane (every lane holds the warp-uniform fields)
+            static_assert(sizeof(orb_kp) == 28, "orb_kp is 7 words");
+            const float kx = (l != 0) ? __fmul_rn((float)px[q], L.scale) : (float)px[q];   // ORBextractor.cc:1139-1145
+            const float ky = (l != 0) ? __fmul_rn((float)py[q], L.scale) : (float)py[q];
+            unsigned wv = __float_as_uint(kx);                        // x
+            wv = lane == 1 ? __float_as_uint(ky) : wv;                 // y
+            wv = lane == 2 ? __float_as_uint(L.size) : wv;             // size
+            wv = lane == 3 ? __float_as_uint(s_ang[kq]) : wv;          // angle
+            wv = lane == 4 ? __float_as_uint((float)sc[q]) : wv;       // response
+            wv = lane == 5 ? (unsigned)l : wv;                         // octave
+            wv = lane == 6 ? 0xFFFFFFFFu : wv;                         // class_id = -1
+            if (lane < 7) reinterpret_cast<unsigned*>(kps_out + o)[lane] = wv;
         }
     }
 }
