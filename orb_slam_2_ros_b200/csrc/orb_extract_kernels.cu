@@ -48,8 +48,9 @@ __device__ __forceinline__ int block_exclusive_scan(int* data, int n, int* s_war
         }
         if (lane == 31) s_warp[wid] = x;
         __syncthreads();
-        int woff = 0;
-        for (int k = 0; k < wid; ++k) woff += s_warp[k];
+        // totals of the warps before this one: one load per lane + a warp reduction (redux.sync) instead of a loop over s_warp
+        const int wt = lane < NT / 32 ? s_warp[lane] : 0;
+        const int woff = __reduce_add_sync(0xffffffffu, lane < wid ? wt : 0);
         const int carry = *s_carry;
         if (i < n) data[i] = carry + woff + x - v;
         __syncthreads();
