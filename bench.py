@@ -931,7 +931,7 @@ def main():
         traffic = {}
         try:   # DRAM bytes per frame and stage from the committed `ncu --set full` capture of one bench step
             import glob
-            tf = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))[-1]
+            tf = sorted(glob.glob(os.path.join(ROOT, "profiles", "**", "*_traffic.json"), recursive=True))[-1]
             traffic = {k: v["dram_bytes_per_frame"] * B for k, v in json.load(open(tf))["stages"].items()}
             traffic["_source"] = os.path.relpath(tf, ROOT)
         except (IndexError, OSError, KeyError, ValueError):
