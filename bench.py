@@ -755,8 +755,9 @@ def main():
                          "peak_source": "POPC issue rate of this GPU measured register-only in this run (orb_bench_issue_rate kind 0) / 4",
                          "popc_per_s": popc_rate, "popc8_roofline_gcompare_s": popc8_peak / 1e9,
                          "frac_vs_popc8_roofline": kern_cps / popc8_peak if popc8_peak else None,
-                         "binding_pipe": "ALU pipe (LOP3 XOR + carry-save adders, key packing, top-2 min/max); ncu on this kernel: ALU pipe 87 %, "
-                                         "XU/POPC pipe 69 % (profiles/r1_k_ncu_hamming_pipes.txt)",
+                         "binding_pipe": "ALU pipe (8 LOP3 XOR + 8 LOP3 carry-save adders per compare; the key is packed by IMADs on the FMA pipe "
+                                         "and the top-2 min/max runs once per group of 4 rows) next to the XU/POPC pipe; ncu on this kernel: ALU "
+                                         "pipe 80 %, XU/POPC pipe 76 %, issue slots 66 % (profiles/r2/ncu_hamming_pipes.txt)",
                          "own_instruction_mix_ceiling_gcompare_s": cmp_rate / 1e9, "register_only_popc8_compare_per_s": cmp8_rate,
                          "kernel": "hamming_top2_kernel", "avg_launch_ms": s_ms / max(calls, 1)},
             "gpu_launches": int(hl),   # search + split-merge kernels (+ the cross-shard merge kernel when sharded)

@@ -266,23 +266,38 @@ __global__ void popc_peak_kernel(unsigned* out, int iters, unsigned seed) {
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
 }
-// the compare itself (8 xor + 8 popc + adds + packed top-2 update) with all operands in registers
+// the compare itself with all operands in registers: CSA = false: 8 xor + 8 popc + adds + the 3-op packed top-2 update per row
+// (SURVEY's popc8 form); CSA = true: the search kernel's own mix — carry-save tree + 4 popc, key by multiply-adds, top-2 update
+// per group of HAMMING_GROUP rows
 template <bool CSA>
-__global__ void compare_peak_kernel(unsigned* out, int iters, unsigned seed) {
+__global__ void compare_peak_kernel(unsigned* out, int iters, unsigned seed, unsigned m23, unsigned m24, unsigned m25) {
     unsigned q[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) q[k] = seed * (k + 1) + threadIdx.x * 2654435761u;
     uint4 a = make_uint4(seed, seed ^ 0x1234567u, seed * 3u, seed * 7u), b = make_uint4(~seed, seed * 5u, seed * 9u, seed + 77u);
     unsigned k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
+    constexpr int G = (CSA && HAMMING_GROUP > 1) ? HAMMING_GROUP : 1;
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            // every word of the row changes every iteration (8 extra IADD on the ALU pipe), so no popc is hoisted
-            a.x += 0x9E3779B9u; a.y += a.x; a.z += a.y; a.w += a.z; b.x += a.w; b.y += b.x; b.z += b.y; b.w += b.z;
-            const unsigned dist = CSA ? (unsigned)hamming256(a, b, q) : (unsigned)hamming256_popc8(a, b, q);
-            const unsigned key = (dist << HT_IDX_BITS) | (unsigned)(i * 8 + u);
-            k2 = min(k2, max(key, k1));
-            k1 = min(k1, key);
+        for (int u0 = 0; u0 < 8; u0 += G) {
+            unsigned key[G];
+#pragma unroll
+            for (int u = 0; u < G; ++u) {
+                // every word of the row changes every iteration (8 extra IADD on the ALU pipe), so no popc is hoisted
+                a.x += 0x9E3779B9u; a.y += a.x; a.z += a.y; a.w += a.z; b.x += a.w; b.y += b.x; b.z += b.y; b.w += b.z;
+                key[u] = CSA ? hamming256_key(a, b, q, (unsigned)(i * 8 + u0 + u), m23, m24, m25)
+                             : (((unsigned)hamming256_popc8(a, b, q) << HT_IDX_BITS) | (unsigned)(i * 8 + u0 + u));
+            }
+            unsigned m = key[0];
+#pragma unroll
+            for (int u = 1; u < G; ++u) m = min(m, key[u]);
+            if (G == 1 || m < k2) {
+#pragma unroll
+                for (int u = 0; u < G; ++u) {
+                    k2 = min(k2, max(key[u], k1));
+                    k1 = min(k1, key[u]);
+                }
+            }
         }
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = k1 ^ k2;
@@ -679,8 +694,8 @@ int orb_bench_issue_rate(int device, int kind, int iters, double* gops) {
     for (int rep = 0; rep < 4; ++rep) {
         ORB_CUDA(cudaEventRecord(e0));
         if (kind == 0) popc_peak_kernel<<<blocks, threads>>>(d_out, iters, 12345u + rep);
-        else if (kind == 1) compare_peak_kernel<false><<<blocks, threads>>>(d_out, iters, 12345u + rep);
-        else compare_peak_kernel<true><<<blocks, threads>>>(d_out, iters, 12345u + rep);
+        else if (kind == 1) compare_peak_kernel<false><<<blocks, threads>>>(d_out, iters, 12345u + rep, 1u << HT_IDX_BITS, 2u << HT_IDX_BITS, 4u << HT_IDX_BITS);
+        else compare_peak_kernel<true><<<blocks, threads>>>(d_out, iters, 12345u + rep, 1u << HT_IDX_BITS, 2u << HT_IDX_BITS, 4u << HT_IDX_BITS);
         ORB_CUDA(cudaEventRecord(e1));
         ORB_CUDA(cudaEventSynchronize(e1));
         float ms = 0;

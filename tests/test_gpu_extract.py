@@ -254,3 +254,36 @@ def test_other_extractor_parameters(oracle, ORB, nf, sf, nl, ini, mn, w, h):
     for f in (0, 8):
         assert_kps_equal(res[f][0], ok, "batched frame %d" % f)
         assert np.array_equal(res[f][1], od)
+
+
+@pytest.mark.parametrize("w,h,pad,shift", [(640, 480, 0, 0), (640, 480, 4, 4), (640, 480, 3, 1), (333, 251, 0, 0), (333, 251, 5, 2), (334, 250, 2, 0)])
+def test_device_resident_input_alignments(oracle, ORB, w, h, pad, shift):
+    """orb_extract_batch_device on caller-owned device frames: the level-0 pass reads 16-byte aligned rows as vectors, 4-byte aligned
+    rows as words and anything else byte by byte, and builds the 19-px border from the same rows — all three must give the oracle's
+    bordered level 0 and keypoints (row stride = w + pad, first pixel `shift` bytes into the allocation)."""
+    import torch
+    from orb_slam_2_ros_b200._lib import KP_DTYPE
+    F = 3
+    imgs = synth.synth_batch(300 + w + pad, F, w, h, unique=F)
+    stride = w + pad
+    buf = torch.zeros(shift + F * h * stride + 64, dtype=torch.uint8, device="cuda")
+    view = buf[shift:shift + F * h * stride].view(F, h, stride)
+    view[:, :, :w] = torch.from_numpy(imgs).cuda()
+    ex = ORB(500, max_batch=F)
+    cap = ex.max_keypoints
+    d_kps = torch.zeros((F, cap, KP_DTYPE.itemsize), dtype=torch.uint8, device="cuda")
+    d_desc = torch.zeros((F, cap, 32), dtype=torch.uint8, device="cuda")
+    d_n = torch.zeros(F, dtype=torch.int32, device="cuda")
+    ex.extract_batch_device(buf.data_ptr() + shift, F, w, h, stride, h * stride, d_kps.data_ptr(), d_desc.data_ptr(), cap, d_n.data_ptr())
+    ex.sync()
+    n = d_n.cpu().numpy()
+    oex = oracle.Extractor(500)
+    for f in range(F):
+        ok, od = oex.extract(imgs[f])
+        kps = d_kps[f, :n[f]].cpu().numpy().view(KP_DTYPE).reshape(-1)
+        assert_kps_equal(kps, ok, "frame %d" % f)
+        assert np.array_equal(d_desc[f, :n[f]].cpu().numpy(), od)
+    # frame slot 0 of the arena still holds frame 0's pyramid: compare the bordered levels (the fused border pass)
+    oex.extract(imgs[0])
+    for l in range(8):
+        assert np.array_equal(ex.pyramid_level_bordered(l), oex.level(l)), "bordered level %d" % l
