@@ -821,11 +821,19 @@ def main():
                          q["r"].data_ptr(), q["lo"].data_ptr(), q["hi"].data_ptr(), da.data_ptr(), None, None, q["ang"].data_ptr(), None, None,
                          moq.data_ptr(), tq.data_ptr(), nm_s.data_ptr())
 
+        # the two searches of a pair are independent of each other (both only read the extractor's outputs), so the caller runs them on two
+        # streams: the brute-force resolve step (one CTA per pair, latency-bound) then overlaps the window search's candidate kernel
+        stream_b = torch.cuda.Stream(device=dev)
+
         def match2():
+            stream_b.wait_stream(stream)
             match_bruteforce_batch_device(P, ka.data_ptr(), da.data_ptr(), na.data_ptr(), c2, kb.data_ptr(), db_.data_ptr(), nb.data_ptr(), c2,
                                           m12.data_ptr(), nm_b.data_ptr(), 50, 0.6, True, device=local_rank, stream=stream.cuda_stream)
-            taken.zero_()
-            search_by_projection_batch_device(MODE_TRACK_LAST, P, sb, (0.0, 0.0, 640.0, 480.0), 100, 0.9, True, device=local_rank, stream=stream.cuda_stream)
+            with torch.cuda.stream(stream_b):
+                taken.zero_()
+                search_by_projection_batch_device(MODE_TRACK_LAST, P, sb, (0.0, 0.0, 640.0, 480.0), 100, 0.9, True, device=local_rank,
+                                                  stream=stream_b.cuda_stream)
+            stream.wait_stream(stream_b)
 
         def step2():
             extract2()
@@ -836,7 +844,7 @@ def main():
                           "value": world * P / (ms_all * 1e-3), "unit": "pairs/s", "pairs_per_step_per_gpu": P, "ms_per_step": ms_all,
                           "matching_only_ms_per_step": ms_match, "matching_only_pairs_per_s": world * P / (ms_match * 1e-3), "scaling": "weak",
                           "bruteforce_matches_per_pair": float(nm_b.float().mean().item()), "projection_matches_per_pair": float(nm_s.float().mean().item()),
-                          "entry_points": "orb_extract_batch_device x2, orb_match_bruteforce_batch_device, orb_search_by_projection_batch_device (device-resident)"}
+                          "entry_points": "orb_extract_batch_device x2, orb_match_bruteforce_batch_device || orb_search_by_projection_batch_device on two streams (device-resident)"}
         del exa, exb, ka, da, kb, db_, dA, dB
         # ---------------- config 3 ----------------
         P3, w3, h3, nf3 = 64, 1241, 376, 2000

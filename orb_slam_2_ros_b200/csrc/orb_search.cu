@@ -646,9 +646,9 @@ __device__ __forceinline__ void window_resolve_body(const SearchArgs& a, int mod
 // =============================== brute force with mask (SearchByBoW inner loop) ===============================
 #define BF_K SR_K
 
-// one warp per query row: distances to every target (stored, u16) + sorted top-K packed keys (dist<<16 | j)
+// one warp per query row (latency shape, one pair): sorted top-K packed keys (dist<<16 | j) of the distances to every target
 __device__ __forceinline__ void bf_rows_body(const uint8_t* __restrict__ d1, int n1, const uint8_t* __restrict__ d2, int n2,
-                                             unsigned short* __restrict__ D, int dpitch, unsigned* __restrict__ topk) {
+                                             unsigned* __restrict__ topk) {
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= n1) return;
@@ -666,12 +666,120 @@ __device__ __forceinline__ void bf_rows_body(const uint8_t* __restrict__ d1, int
     };
     for (int j = lane; j < n2; j += 32) {
         const int d = dist256(dq, reinterpret_cast<const uint4*>(d2 + (size_t)j * 32));
-        D[(size_t)i * dpitch + j] = (unsigned short)d;
         const unsigned key = ((unsigned)d << 16) | (unsigned)j;
         if (d < 256 && key < best[BF_K - 1]) insert(key);   // a distance of 256 never becomes best or second best (ORBmatcher.cc:217-226: dist < 256 is false)
     }
     const unsigned mine = warp_topk_extract(best, lane);
     if (lane < BF_K) topk[(size_t)i * BF_K + lane] = mine;
+}
+
+// Throughput shape (batches of pairs): one THREAD per query, the query in registers, the targets streamed through shared memory
+// in tiles and read with broadcast LDS.128 — the map-wide search kernel's structure (orb_hamming.cu): carry-save popcount tree,
+// 4 POPC per compare, key = dist << 16 | j built by multiply-adds on the FMA pipe, the list touched once per group of 4 targets.
+// The warp-per-query body above spends 63 warp-instructions per warp-compare (two 16-byte global loads per lane per compare, 8
+// POPC), this one about 27.
+//   Only distances that can change a decision are listed: a match needs best <= th_dist, and once second-best exceeds
+// track = max { d : th_dist >= nn_ratio * d (fp32) } the ratio test (ORBmatcher.cc:229-231) passes for every admissible best, so
+// the resolve step never needs the exact value of a distance above `track` (nor its index).  The list of a query therefore
+// holds the targets with dist <= track (sorted, at most SR_K; a full list still means "truncated" to the resolve step, which then
+// rescans the row) — on real descriptor sets that is a handful of entries, so the insertion path is rare and the common case of
+// a group is 2 min + 1 compare.  Exactness: bf_resolve_body reads a missing second entry as 256, and 256 decides like any
+// distance above `track`.
+#ifndef BFT_THREADS
+#define BFT_THREADS 128   // queries per CTA: 1000 queries x 128 pairs = 1024 CTAs of 4 warps (256-thread CTAs leave the SMs with 3 or 4 long CTAs each)
+#endif
+#define BFT_TILE 128   // targets per shared-memory tile (4 KB)
+__device__ __forceinline__ unsigned bft_lop3_xor3(unsigned a, unsigned b, unsigned c) {
+    unsigned d; asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d;
+}
+__device__ __forceinline__ unsigned bft_lop3_maj(unsigned a, unsigned b, unsigned c) {
+    unsigned d; asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d;
+}
+__device__ __forceinline__ unsigned bft_key(const uint4& a, const uint4& b, const unsigned (&q)[8], unsigned j, unsigned m16, unsigned m17,
+                                            unsigned m18) {
+    const unsigned x0 = a.x ^ q[0], x1 = a.y ^ q[1], x2 = a.z ^ q[2], x3 = a.w ^ q[3];
+    const unsigned x4 = b.x ^ q[4], x5 = b.y ^ q[5], x6 = b.z ^ q[6], x7 = b.w ^ q[7];
+    const unsigned s1 = bft_lop3_xor3(x0, x1, x2), c1 = bft_lop3_maj(x0, x1, x2);
+    const unsigned s2 = bft_lop3_xor3(x3, x4, x5), c2 = bft_lop3_maj(x3, x4, x5);
+    const unsigned s3 = bft_lop3_xor3(s1, s2, x6), c3 = bft_lop3_maj(s1, s2, x6);
+    const unsigned t1 = bft_lop3_xor3(c1, c2, c3), f1 = bft_lop3_maj(c1, c2, c3);
+    unsigned k;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(k) : "r"(__popc(s3)), "r"(m16), "r"(j));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(k) : "r"(__popc(x7)), "r"(m16));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(k) : "r"(__popc(t1)), "r"(m17));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(k) : "r"(__popc(f1)), "r"(m18));
+    return k;
+}
+__device__ __forceinline__ void bf_rows_tiled_body(const uint8_t* __restrict__ d1, int n1, const uint8_t* __restrict__ d2, int n2,
+                                                   unsigned* __restrict__ topk, unsigned track_key /* (track + 1) << 16 */, unsigned m16,
+                                                   unsigned m17, unsigned m18) {
+    __shared__ uint4 tile[2][BFT_TILE * 2];
+    const int tid = threadIdx.x;
+    const int i = blockIdx.x * BFT_THREADS + tid;
+    unsigned q[8];
+    {
+        uint4 a = make_uint4(0, 0, 0, 0), b = a;
+        if (i < n1) { a = __ldg(reinterpret_cast<const uint4*>(d1) + 2 * (size_t)i); b = __ldg(reinterpret_cast<const uint4*>(d1) + 2 * (size_t)i + 1); }
+        q[0] = a.x; q[1] = a.y; q[2] = a.z; q[3] = a.w; q[4] = b.x; q[5] = b.y; q[6] = b.z; q[7] = b.w;
+    }
+    unsigned best[SR_K];
+#pragma unroll
+    for (int k = 0; k < SR_K; ++k) best[k] = 0xFFFFFFFFu;
+    unsigned lim = track_key;                            // keys >= lim cannot enter the list
+    auto insert = [&](unsigned key) {
+        if (key >= lim) return;
+#pragma unroll
+        for (int k = 0; k < SR_K; ++k) {
+            const unsigned lo = min(best[k], key);
+            key = max(best[k], key);
+            best[k] = lo;
+        }
+        lim = min(track_key, best[SR_K - 1]);
+    };
+    const int ntiles = (n2 + BFT_TILE - 1) / BFT_TILE;
+    auto issue = [&](int t, int buf) {                   // tile t -> 256 chunks of 16 bytes
+        const int chunks = min(BFT_TILE, n2 - t * BFT_TILE) * 2;
+#pragma unroll
+        for (int c = tid; c < BFT_TILE * 2; c += BFT_THREADS) {
+            if (c < chunks) {
+                const unsigned sa = (unsigned)__cvta_generic_to_shared(&tile[buf][c]);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(reinterpret_cast<const uint4*>(d2) + (size_t)t * BFT_TILE * 2 + c));
+            }
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
+    if (ntiles > 0) issue(0, 0);
+    for (int t = 0; t < ntiles; ++t) {
+        const int buf = t & 1;
+        if (t + 1 < ntiles) { issue(t + 1, buf ^ 1); asm volatile("cp.async.wait_group 1;\n" ::); }
+        else asm volatile("cp.async.wait_group 0;\n" ::);
+        __syncthreads();
+        const int rows = min(BFT_TILE, n2 - t * BFT_TILE);
+        const unsigned j0 = (unsigned)(t * BFT_TILE);
+        int r = 0;
+        for (; r + 4 <= rows; r += 4) {
+            unsigned key[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) key[u] = bft_key(tile[buf][2 * (r + u)], tile[buf][2 * (r + u) + 1], q, j0 + r + u, m16, m17, m18);
+            if (min(__vimin3_u32(key[0], key[1], key[2]), key[3]) < lim) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) insert(key[u]);
+            }
+        }
+        for (; r < rows; ++r) insert(bft_key(tile[buf][2 * r], tile[buf][2 * r + 1], q, j0 + r, m16, m17, m18));
+        __syncthreads();
+    }
+    if (i < n1) {
+#pragma unroll
+        for (int k = 0; k < SR_K; ++k) topk[(size_t)i * SR_K + k] = best[k];
+    }
+}
+// the largest second-best distance whose exact value can still matter: (float)best < nn_ratio * (float)second (ORBmatcher.cc:229-231,
+// separately rounded fp32) holds for every best <= th_dist as soon as second > track
+static int bf_track_limit(int th_dist, float nn_ratio) {
+    int b = 0;
+    while (b < 256 && !((float)th_dist < nn_ratio * (float)b)) ++b;   // smallest second-best that passes for best = th_dist
+    return std::min(255, std::max(b - 1, th_dist));
 }
 
 // The order-dependent part ("a target taken by an earlier query is invisible to the later ones", ORBmatcher.cc:210) as a
@@ -683,7 +791,7 @@ __device__ __forceinline__ void bf_rows_body(const uint8_t* __restrict__ d1, int
 // microseconds (the sequential walk of 1000 queries took 330 us).  The optimistic top-K list answers a query when two of
 // its entries are still visible; otherwise the query's warp scans its whole distance row cooperatively.
 template <bool SMEM>
-__device__ __forceinline__ void bf_resolve_body(const unsigned short* __restrict__ D, int dpitch, const unsigned* __restrict__ topk, int n1, int n2,
+__device__ __forceinline__ void bf_resolve_body(const uint8_t* __restrict__ d1, const uint8_t* __restrict__ d2, const unsigned* __restrict__ topk, int n1, int n2,
                                                 const float* __restrict__ angle1, const float* __restrict__ angle2, int th_dist, float nn_ratio,
                                                 int check_ori, int* owner /*[n2]*/, int* owner_scratch /*[n2], !SMEM only*/, int* match12,
                                                 signed char* match_bin, int* nmatches_out) {
@@ -720,27 +828,21 @@ __device__ __forceinline__ void bf_resolve_body(const unsigned short* __restrict
                 }
                 fallback = nfree < 2 && key[SR_K - 1] != 0xFFFFFFFFu;   // list truncated and too many of its entries taken
             }
-            // fallback: the lanes of the warp scan the whole row of the distance matrix of each such query (8 entries per load)
+            // fallback: the lanes of the warp recompute the distances of each such query to all targets
             unsigned todo = __ballot_sync(0xffffffffu, fallback);
             while (todo) {
                 const int src = __ffs((int)todo) - 1;
                 todo &= todo - 1u;
                 const int fi = __shfl_sync(0xffffffffu, i, src);
                 unsigned a1 = 0xFFFFFFFFu, a2 = 0xFFFFFFFFu;
-                const uint4* row = reinterpret_cast<const uint4*>(D + (size_t)fi * dpitch);
-                for (int v = lane; v < dpitch / 8; v += 32) {
-                    const uint4 t = row[v];
-                    const unsigned w[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-                    for (int h = 0; h < 8; ++h) {
-                        const int jj = v * 8 + h;
-                        if (jj >= n2 || (SMEM ? own_prev[jj] : __ldcg(own_prev + jj)) < fi) continue;
-                        const unsigned dd = (w[h >> 1] >> (16 * (h & 1))) & 0xFFFFu;
-                        if (dd >= 256u) continue;                               // invisible to the reference's strict '<' updates
-                        const unsigned k = (dd << 16) | (unsigned)jj;
-                        a2 = min(a2, max(k, a1));
-                        a1 = min(a1, k);
-                    }
+                const uint4* dq = reinterpret_cast<const uint4*>(d1 + (size_t)fi * 32);
+                for (int jj = lane; jj < n2; jj += 32) {
+                    if ((SMEM ? own_prev[jj] : __ldcg(own_prev + jj)) < fi) continue;
+                    const unsigned dd = (unsigned)dist256(dq, reinterpret_cast<const uint4*>(d2 + (size_t)jj * 32));   // recomputed: no distance matrix is kept
+                    if (dd >= 256u) continue;                               // invisible to the reference's strict '<' updates
+                    const unsigned k = (dd << 16) | (unsigned)jj;
+                    a2 = min(a2, max(k, a1));
+                    a1 = min(a1, k);
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
@@ -820,16 +922,15 @@ window_resolve_kernel(const SearchArgs a, int mode, int th_dist, float nn_ratio,
                         smem_bytes);
 }
 __global__ void __launch_bounds__(256)
-bf_rows_kernel(const uint8_t* __restrict__ d1, int n1, const uint8_t* __restrict__ d2, int n2, unsigned short* __restrict__ D, int dpitch,
-               unsigned* __restrict__ topk) {
-    bf_rows_body(d1, n1, d2, n2, D, dpitch, topk);
+bf_rows_kernel(const uint8_t* __restrict__ d1, int n1, const uint8_t* __restrict__ d2, int n2, unsigned* __restrict__ topk) {
+    bf_rows_body(d1, n1, d2, n2, topk);
 }
 template <bool SMEM>
 __global__ void __launch_bounds__(SR_THREADS, 1)
-bf_resolve_kernel(const unsigned short* __restrict__ D, int dpitch, const unsigned* __restrict__ topk, int n1, int n2,
+bf_resolve_kernel(const uint8_t* __restrict__ d1, const uint8_t* __restrict__ d2, const unsigned* __restrict__ topk, int n1, int n2,
                   const float* __restrict__ angle1, const float* __restrict__ angle2, int th_dist, float nn_ratio, int check_ori, int* owner,
                   int* owner_scratch, int* match12, signed char* match_bin, int* nmatches_out) {
-    bf_resolve_body<SMEM>(D, dpitch, topk, n1, n2, angle1, angle2, th_dist, nn_ratio, check_ori, owner, owner_scratch, match12, match_bin, nmatches_out);
+    bf_resolve_body<SMEM>(d1, d2, topk, n1, n2, angle1, angle2, th_dist, nn_ratio, check_ori, owner, owner_scratch, match12, match_bin, nmatches_out);
 }
 
 // Batched forms (per-pair matching shards like frames): blockIdx.y (one-CTA kernels: blockIdx.x) = pair.  The
@@ -880,16 +981,18 @@ __global__ void search_batch_finish_kernel(const WindowJob* __restrict__ jobs, i
 
 struct BfJob {
     const uint8_t *d1, *d2; const orb_kp *k1, *k2; const int *n1_ptr, *n2_ptr; int cap1, cap2;
-    unsigned short* D; int dpitch; unsigned* topk; float *a1, *a2; int *owner, *owner2, *m12; signed char* bin; int* nm;
+    unsigned* topk; float *a1, *a2; int *owner, *owner2, *m12; signed char* bin; int* nm;
 };
-__global__ void __launch_bounds__(256) bf_rows_batch_kernel(const BfJob* __restrict__ jobs) {
+__global__ void __launch_bounds__(BFT_THREADS) bf_rows_batch_kernel(const BfJob* __restrict__ jobs, unsigned track_key, unsigned m16, unsigned m17,
+                                                                    unsigned m18) {
     const BfJob& J = jobs[blockIdx.y];
     const int n1 = min(*J.n1_ptr, J.cap1), n2 = min(*J.n2_ptr, J.cap2);
     // dense angle arrays for the rotation histogram (the extractor's keypoints are 28-byte records)
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n1) J.a1[t] = J.k1[t].angle;
     for (int j = t; j < n2; j += gridDim.x * blockDim.x) J.a2[j] = J.k2[j].angle;
-    bf_rows_body(J.d1, n1, J.d2, n2, J.D, J.dpitch, J.topk);
+    if (blockIdx.x * BFT_THREADS >= n1) return;   // uniform per CTA
+    bf_rows_tiled_body(J.d1, n1, J.d2, n2, J.topk, track_key, m16, m17, m18);
 }
 __global__ void __launch_bounds__(SR_THREADS, 1)
 bf_resolve_batch_kernel(const BfJob* __restrict__ jobs, int th_dist, float nn_ratio, int check_ori) {
@@ -901,7 +1004,7 @@ bf_resolve_batch_kernel(const BfJob* __restrict__ jobs, int th_dist, float nn_ra
         if (threadIdx.x == 0) *J.nm = 0;
         return;
     }
-    bf_resolve_body<false>(J.D, J.dpitch, J.topk, n1, n2, J.a1, J.a2, th_dist, nn_ratio, check_ori, J.owner, J.owner2, J.m12, J.bin, J.nm);
+    bf_resolve_body<false>(J.d1, J.d2, J.topk, n1, n2, J.a1, J.a2, th_dist, nn_ratio, check_ori, J.owner, J.owner2, J.m12, J.bin, J.nm);
 }
 
 // ---- best / second-best over explicit candidate lists (CSR): one warp per query ------------------------------
@@ -1413,8 +1516,7 @@ int orb_match_bruteforce(int device, const uint8_t* desc1, const float* angle1, 
     const size_t in_bytes = c.off;
     const size_t o_m12 = c.take(4 * (size_t)n1), o_nm = c.take(16);
     const size_t io_bytes = c.off;
-    const int dpitch = (n2 + 7) & ~7;   // 16-byte aligned rows of the u16 distance matrix
-    const size_t o_D = c.take(2 * (size_t)n1 * dpitch), o_topk = c.take(4 * (size_t)n1 * BF_K), o_owner = c.take(4 * (size_t)n2), o_owner2 = c.take(4 * (size_t)n2), o_bin = c.take(n1);
+    const size_t o_topk = c.take(4 * (size_t)n1 * BF_K), o_owner = c.take(4 * (size_t)n2), o_owner2 = c.take(4 * (size_t)n2), o_bin = c.take(n1);
     Workspace& W = g_ws;
     int rc = W.prepare(device, c.off, io_bytes);
     if (rc != ORB_OK) return rc;
@@ -1424,7 +1526,7 @@ int orb_match_bruteforce(int device, const uint8_t* desc1, const float* angle1, 
     if (angle1) memcpy(H + o_a1, angle1, 4 * (size_t)n1);
     if (angle2) memcpy(H + o_a2, angle2, 4 * (size_t)n2);
     ORB_CUDA(cudaMemcpyAsync(Dv, H, in_bytes, cudaMemcpyHostToDevice, st));
-    bf_rows_kernel<<<(n1 + 7) / 8, 256, 0, st>>>(Dv + o_d1, n1, Dv + o_d2, n2, (unsigned short*)(Dv + o_D), dpitch, (unsigned*)(Dv + o_topk));
+    bf_rows_kernel<<<(n1 + 7) / 8, 256, 0, st>>>(Dv + o_d1, n1, Dv + o_d2, n2, (unsigned*)(Dv + o_topk));
     {
         const size_t own_smem = 8 * (size_t)n2;   // two owner arrays in shared memory when they fit, else in the workspace
         static bool attr_set[64] = {};   // per device
@@ -1433,12 +1535,12 @@ int orb_match_bruteforce(int device, const uint8_t* desc1, const float* angle1, 
             attr_set[device & 63] = true;
         }
         if (own_smem <= 200 * 1024)
-            bf_resolve_kernel<true><<<1, SR_THREADS, own_smem, st>>>((const unsigned short*)(Dv + o_D), dpitch, (const unsigned*)(Dv + o_topk), n1, n2,
+            bf_resolve_kernel<true><<<1, SR_THREADS, own_smem, st>>>(Dv + o_d1, Dv + o_d2, (const unsigned*)(Dv + o_topk), n1, n2,
                                                                      (const float*)(Dv + o_a1), (const float*)(Dv + o_a2), th_dist, nn_ratio, check_orientation,
                                                                      (int*)(Dv + o_owner), (int*)(Dv + o_owner2), (int*)(Dv + o_m12),
                                                                      (signed char*)(Dv + o_bin), (int*)(Dv + o_nm));
         else
-            bf_resolve_kernel<false><<<1, SR_THREADS, 0, st>>>((const unsigned short*)(Dv + o_D), dpitch, (const unsigned*)(Dv + o_topk), n1, n2,
+            bf_resolve_kernel<false><<<1, SR_THREADS, 0, st>>>(Dv + o_d1, Dv + o_d2, (const unsigned*)(Dv + o_topk), n1, n2,
                                                                (const float*)(Dv + o_a1), (const float*)(Dv + o_a2), th_dist, nn_ratio, check_orientation,
                                                                (int*)(Dv + o_owner), (int*)(Dv + o_owner2), (int*)(Dv + o_m12),
                                                                (signed char*)(Dv + o_bin), (int*)(Dv + o_nm));
@@ -1712,9 +1814,8 @@ int orb_match_bruteforce_batch_device(int device, int npairs, const orb_kp* d_kp
     if (npairs == 0) return ORB_OK;
     if (cap2 > 65535) { orb_set_error("orb_match_bruteforce_batch_device: more than 65535 targets"); return ORB_ERR_CAPACITY; }
     if (orb_device_count() <= 0) { orb_set_error("no CUDA device visible: liborb_b200 has no CPU fallback"); return ORB_ERR_NO_DEVICE; }
-    const int dpitch = (cap2 + 7) & ~7;
     Carver c;   // per-pair scratch
-    const size_t o_D = c.take(2 * (size_t)cap1 * dpitch), o_topk = c.take(4 * (size_t)cap1 * BF_K), o_a1 = c.take(4 * (size_t)cap1), o_a2 = c.take(4 * (size_t)cap2);
+    const size_t o_topk = c.take(4 * (size_t)cap1 * BF_K), o_a1 = c.take(4 * (size_t)cap1), o_a2 = c.take(4 * (size_t)cap2);
     const size_t o_owner = c.take(4 * (size_t)cap2), o_owner2 = c.take(4 * (size_t)cap2), o_bin = c.take(cap1);
     const size_t per_pair = c.off;
     const size_t jobs_bytes = ((size_t)npairs * sizeof(BfJob) + 255) & ~(size_t)255;
@@ -1729,14 +1830,15 @@ int orb_match_bruteforce_batch_device(int device, int npairs, const orb_kp* d_kp
         J.d1 = d_desc1 + (size_t)p * cap1 * 32; J.d2 = d_desc2 + (size_t)p * cap2 * 32;
         J.k1 = d_kps1 + (size_t)p * cap1; J.k2 = d_kps2 + (size_t)p * cap2;
         J.n1_ptr = d_n1 + p; J.n2_ptr = d_n2 + p; J.cap1 = cap1; J.cap2 = cap2;
-        J.D = (unsigned short*)(S + o_D); J.dpitch = dpitch; J.topk = (unsigned*)(S + o_topk); J.a1 = (float*)(S + o_a1); J.a2 = (float*)(S + o_a2);
+        J.topk = (unsigned*)(S + o_topk); J.a1 = (float*)(S + o_a1); J.a2 = (float*)(S + o_a2);
         J.owner = (int*)(S + o_owner); J.owner2 = (int*)(S + o_owner2); J.m12 = d_match12 + (size_t)p * cap1; J.bin = (signed char*)(S + o_bin);
         J.nm = d_nmatches + p;
     }
     rc = upload_jobs(W, jobs.data(), (size_t)npairs * sizeof(BfJob), st);
     if (rc != ORB_OK) return rc;
     const BfJob* d_jobs = (const BfJob*)W.d;
-    bf_rows_batch_kernel<<<dim3((cap1 + 7) / 8, npairs), 256, 0, st>>>(d_jobs);
+    const unsigned track_key = (unsigned)(bf_track_limit(th_dist, nn_ratio) + 1) << 16;
+    bf_rows_batch_kernel<<<dim3((cap1 + BFT_THREADS - 1) / BFT_THREADS, npairs), BFT_THREADS, 0, st>>>(d_jobs, track_key, 1u << 16, 2u << 16, 4u << 16);
     bf_resolve_batch_kernel<<<npairs, SR_THREADS, 0, st>>>(d_jobs, th_dist, nn_ratio, check_orientation);
     ORB_CUDA(cudaGetLastError());
     return ORB_OK;
