@@ -26,21 +26,49 @@ __device__ __forceinline__ int dist256s(const uint4* a, const uint4* b) {
            __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
 }
 
-// per right keypoint, once: the row band [minr, maxr] it is listed under (Frame.cc:519-529), its x and octave, packed in 16 bytes
-// (every left keypoint's warp scans all of them: without this each of the N x Nr visits redid the ceil / floor arithmetic
-// on a 28-byte KeyPoint)
-// Batched form: blockIdx.y = stereo pair; n_r (when not NULL) holds the per-pair keypoint counts on the device and the
-// per-pair arrays are `cap` entries apart.
-__global__ void __launch_bounds__(256)
-stereo_rows_kernel(const orb_kp* __restrict__ kpsR, int Nr, const StereoScales sc, uint4* __restrict__ rows, const int* __restrict__ n_r, int cap) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int pair = blockIdx.y;
+// per right keypoint, once: the row band [minr, maxr] it is listed under (Frame.cc:519-529), its x, octave and index, packed in
+// 16 bytes — and the records SORTED INTO BINS of 16 rows by minr (counting sort, one CTA per pair): the reference looks a left
+// keypoint's candidates up in vRowIndices[row]; here the left keypoint's warp scans the bins whose minr can reach its row
+// ([row - maxband, row], maxband = the tallest band of the geometry) instead of all Nr right keypoints (the first version's
+// N x Nr visits were 45 % of the kernel's instructions).  The order inside a bin is arbitrary: the match is a minimum over
+// (distance, right index) keys, exactly the reference's "first minimum in ascending iR".
+// Batched form: blockIdx.x = stereo pair; n_r (when not NULL) holds the per-pair keypoint counts on the device and the
+// per-pair arrays are `cap` entries apart (bin_start: ST_MAXBINS + 1 per pair).
+#define ST_BIN_SHIFT 4
+#define ST_MAXBINS 640   // image heights up to 10240 rows
+__global__ void __launch_bounds__(1024)
+stereo_rows_kernel(const orb_kp* __restrict__ kpsR, int Nr, const StereoScales sc, uint4* __restrict__ rows, int* __restrict__ bin_start, int nbins,
+                   const int* __restrict__ n_r, int cap) {
+    __shared__ int s_cnt[ST_MAXBINS + 1], s_cur[ST_MAXBINS];
+    const int pair = blockIdx.x;
     if (n_r) { Nr = min(n_r[pair], cap); kpsR += (size_t)pair * cap; rows += (size_t)pair * cap; }
-    if (i >= Nr) return;
-    const orb_kp kpR = kpsR[i];
-    const float r = __fmul_rn(2.0f, sc.scale[kpR.octave]);
-    const int maxr = (int)ceilf(__fadd_rn(kpR.y, r)), minr = (int)floorf(__fsub_rn(kpR.y, r));
-    rows[i] = make_uint4(__float_as_uint(kpR.x), (unsigned)minr, (unsigned)maxr, (unsigned)kpR.octave);
+    bin_start += (size_t)pair * (ST_MAXBINS + 1);
+    for (int b = threadIdx.x; b <= nbins; b += blockDim.x) s_cnt[b] = 0;
+    __syncthreads();
+    auto record = [&](int i, int& bin) {
+        const orb_kp kpR = kpsR[i];
+        const float r = __fmul_rn(2.0f, sc.scale[kpR.octave]);
+        const int maxr = (int)ceilf(__fadd_rn(kpR.y, r)), minr = (int)floorf(__fsub_rn(kpR.y, r));
+        bin = min(max(minr, 0) >> ST_BIN_SHIFT, nbins - 1);
+        return make_uint4(__float_as_uint(kpR.x), (unsigned)minr, (unsigned)maxr, (unsigned)kpR.octave | ((unsigned)i << 8));
+    };
+    for (int i = threadIdx.x; i < Nr; i += blockDim.x) { int bin; record(i, bin); atomicAdd(&s_cnt[bin], 1); }
+    __syncthreads();
+    if (threadIdx.x < 32) {   // exclusive prefix over the bins, one warp
+        int carry = 0;
+        for (int b0 = 0; b0 < nbins; b0 += 32) {
+            const int b = b0 + (int)threadIdx.x;
+            const int v = b < nbins ? s_cnt[b] : 0;
+            int x = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if ((int)threadIdx.x >= o) x += y; }
+            if (b < nbins) { s_cur[b] = carry + x - v; bin_start[b] = carry + x - v; }
+            carry += __shfl_sync(0xffffffffu, x, 31);
+        }
+        if (threadIdx.x == 0) bin_start[nbins] = carry;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < Nr; i += blockDim.x) { int bin; const uint4 rec = record(i, bin); rows[atomicAdd(&s_cur[bin], 1)] = rec; }
 }
 
 __global__ void __launch_bounds__(256)
@@ -48,8 +76,8 @@ stereo_match_kernel(const uint8_t* __restrict__ pyrL, const uint8_t* __restrict_
                     const uint8_t* __restrict__ descL, int N, const orb_kp* __restrict__ kpsR,
                     const uint8_t* __restrict__ descR, int Nr, float mbf, float mb, const StereoScales sc,
                     float* __restrict__ uRight, float* __restrict__ depth, int* __restrict__ sad,
-                    const uint4* __restrict__ rowsR, const __grid_constant__ Geometry g, const int* __restrict__ n_l,
-                    const int* __restrict__ n_r, int cap) {
+                    const uint4* __restrict__ rowsR, const int* __restrict__ bin_start, int nbins, int maxband,
+                    const __grid_constant__ Geometry g, const int* __restrict__ n_l, const int* __restrict__ n_r, int cap) {
     const int lane = threadIdx.x & 31;
     const int iL = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int pair = blockIdx.y;      // batched form (n_l != NULL): frame `pair` of both pyramid arenas, per-pair arrays `cap` apart
@@ -58,6 +86,7 @@ stereo_match_kernel(const uint8_t* __restrict__ pyrL, const uint8_t* __restrict_
         const size_t o = (size_t)pair * cap;
         kpsL += o; descL += o * 32; kpsR += o; descR += o * 32; uRight += o; depth += o; sad += o; rowsR += o;
     }
+    bin_start += (size_t)pair * (ST_MAXBINS + 1);
     if (iL >= N) {
         if (n_l && iL < cap && lane == 0) { uRight[iL] = -1.0f; depth[iL] = -1.0f; sad[iL] = -1; }   // unused slots of the pair's row
         return;
@@ -74,10 +103,14 @@ stereo_match_kernel(const uint8_t* __restrict__ pyrL, const uint8_t* __restrict_
     if (maxU < 0) return;
     const uint4* dL = reinterpret_cast<const uint4*>(descL + (size_t)iL * 32);
     unsigned best = 0xFFFFFFFFu;
-    for (int iR = lane; iR < Nr; iR += 32) {
-        const uint4 q = __ldg(rowsR + iR);               // x | minr | maxr | octave
+    // right keypoints whose band can hold `row`: minr in [row - maxband, row] -> the bins of that range
+    const int b_lo = min(max(row - maxband, 0) >> ST_BIN_SHIFT, nbins - 1), b_hi = min(row >> ST_BIN_SHIFT, nbins - 1);
+    const int p0 = bin_start[b_lo], p1 = bin_start[b_hi + 1];
+    (void)Nr;
+    for (int p = p0 + lane; p < p1; p += 32) {
+        const uint4 q = __ldg(rowsR + p);                // x | minr | maxr | octave + (index << 8)
         if (row < (int)q.y || row > (int)q.z) continue;
-        const int oc = (int)q.w;
+        const int oc = (int)(q.w & 0xFFu), iR = (int)(q.w >> 8);
         if (oc < levelL - 1 || oc > levelL + 1) continue;
         const float xR = __uint_as_float(q.x);
         if (xR >= minU && xR <= maxU) {
@@ -212,6 +245,10 @@ stereo_median_kernel(int N, float* uRight, float* depth, const int* __restrict__
 
 }  // namespace
 
+// bins of 16 rows over the image height; the tallest row band of the geometry: ceil(y + r) - floor(y - r) <= 2r + 2, r = 2 * scale[octave]
+static int stereo_bins(int h) { return ((std::max(h, 1) - 1) >> ST_BIN_SHIFT) + 1; }
+static int stereo_maxband(const orb_ctx* c) { return (int)ceilf(4.0f * c->scale[c->nlevels - 1]) + 2; }
+
 extern "C" int orb_stereo_match(orb_ctx* cl, orb_ctx* cr, const orb_kp* kps_l, const uint8_t* desc_l, int nl,
                                 const orb_kp* kps_r, const uint8_t* desc_r, int nr, float bf, float b, float* u_right,
                                 float* depth, int* nmatches) {
@@ -244,7 +281,7 @@ extern "C" int orb_stereo_match(orb_ctx* cl, orb_ctx* cr, const orb_kp* kps_l, c
     const size_t in_bytes = off;
     const size_t o_ur = take(sizeof(float) * nl), o_dep = take(sizeof(float) * nl), o_nk = take(16);
     const size_t io_bytes = off;
-    const size_t o_sad = take(sizeof(int) * nl), o_rows = take(sizeof(uint4) * (size_t)nr);
+    const size_t o_sad = take(sizeof(int) * nl), o_rows = take(sizeof(uint4) * (size_t)nr), o_bins = take(sizeof(int) * (ST_MAXBINS + 1));
     if (cl->d_scratch_cap < off) {
         ORB_CUDA(cudaStreamSynchronize(st));
         cudaFree(cl->d_scratch); cl->d_scratch = nullptr; cl->d_scratch_cap = 0;
@@ -264,10 +301,12 @@ extern "C" int orb_stereo_match(orb_ctx* cl, orb_ctx* cr, const orb_kp* kps_l, c
     {
         StereoScales sc;
         for (int l = 0; l < ORB_MAX_LEVELS; ++l) { sc.scale[l] = l < cl->nlevels ? cl->scale[l] : 1.f; sc.inv_scale[l] = l < cl->nlevels ? cl->inv_scale[l] : 1.f; }
-        stereo_rows_kernel<<<(nr + 255) / 256, 256, 0, st>>>((const orb_kp*)(D + o_kr), nr, sc, (uint4*)(D + o_rows), nullptr, 0);
+        const int nbins = stereo_bins(cl->g.h), maxband = stereo_maxband(cl);
+        if (nbins > ST_MAXBINS) { orb_set_error("orb_stereo_match: images taller than %d rows are not supported", ST_MAXBINS << ST_BIN_SHIFT); return ORB_ERR_CAPACITY; }
+        stereo_rows_kernel<<<1, 1024, 0, st>>>((const orb_kp*)(D + o_kr), nr, sc, (uint4*)(D + o_rows), (int*)(D + o_bins), nbins, nullptr, 0);
         stereo_match_kernel<<<(nl + 7) / 8, 256, 0, st>>>(cl->d_pyr, cr->d_pyr, (const orb_kp*)(D + o_kl), D + o_dl, nl, (const orb_kp*)(D + o_kr),
                                                          D + o_dr, nr, bf, b, sc, (float*)(D + o_ur), (float*)(D + o_dep), (int*)(D + o_sad),
-                                                         (const uint4*)(D + o_rows), cl->g, nullptr, nullptr, 0);
+                                                         (const uint4*)(D + o_rows), (const int*)(D + o_bins), nbins, maxband, cl->g, nullptr, nullptr, 0);
         stereo_median_kernel<<<1, 1024, sizeof(int) * (size_t)nl, st>>>(nl, (float*)(D + o_ur), (float*)(D + o_dep), (const int*)(D + o_sad), (int*)(D + o_nk), nullptr, 0);
         cl->launches += 3;
     }
@@ -310,7 +349,8 @@ extern "C" int orb_stereo_match_batch_device(orb_ctx* cl, orb_ctx* cr, int npair
         ORB_CUDA(cudaEventDestroy(ev));
     }
     const size_t per = (size_t)npairs * cap;
-    const size_t need = per * (sizeof(int) + sizeof(uint4)) + 512;
+    const size_t bins_bytes = ((size_t)npairs * (ST_MAXBINS + 1) * sizeof(int) + 255) & ~(size_t)255;
+    const size_t need = per * (sizeof(int) + sizeof(uint4)) + 512 + bins_bytes;
     if (cl->d_scratch_cap < need) {
         ORB_CUDA(cudaStreamSynchronize(st));
         cudaFree(cl->d_scratch); cl->d_scratch = nullptr; cl->d_scratch_cap = 0;
@@ -319,11 +359,14 @@ extern "C" int orb_stereo_match_batch_device(orb_ctx* cl, orb_ctx* cr, int npair
     }
     uint4* d_rows = reinterpret_cast<uint4*>(cl->d_scratch);
     int* d_sad = reinterpret_cast<int*>(cl->d_scratch + ((per * sizeof(uint4) + 255) & ~(size_t)255));
+    int* d_bins = reinterpret_cast<int*>(cl->d_scratch + ((per * sizeof(uint4) + 255) & ~(size_t)255) + ((per * sizeof(int) + 255) & ~(size_t)255));
+    const int nbins = stereo_bins(cl->g.h), maxband = stereo_maxband(cl);
+    if (nbins > ST_MAXBINS) { orb_set_error("orb_stereo_match_batch_device: images taller than %d rows are not supported", ST_MAXBINS << ST_BIN_SHIFT); return ORB_ERR_CAPACITY; }
     StereoScales sc;
     for (int l = 0; l < ORB_MAX_LEVELS; ++l) { sc.scale[l] = l < cl->nlevels ? cl->scale[l] : 1.f; sc.inv_scale[l] = l < cl->nlevels ? cl->inv_scale[l] : 1.f; }
-    stereo_rows_kernel<<<dim3((cap + 255) / 256, npairs), 256, 0, st>>>(d_kps_r, 0, sc, d_rows, d_n_r, cap);
+    stereo_rows_kernel<<<npairs, 1024, 0, st>>>(d_kps_r, 0, sc, d_rows, d_bins, nbins, d_n_r, cap);
     stereo_match_kernel<<<dim3((cap + 7) / 8, npairs), 256, 0, st>>>(cl->d_pyr, cr->d_pyr, d_kps_l, d_desc_l, 0, d_kps_r, d_desc_r, 0, bf, b, sc, d_u_right,
-                                                                    d_depth, d_sad, d_rows, cl->g, d_n_l, d_n_r, cap);
+                                                                    d_depth, d_sad, d_rows, d_bins, nbins, maxband, cl->g, d_n_l, d_n_r, cap);
     stereo_median_kernel<<<npairs, 1024, sizeof(int) * (size_t)cap, st>>>(0, d_u_right, d_depth, d_sad, d_nmatches, d_n_l, cap);
     cl->launches += 3;
     ORB_CUDA(cudaGetLastError());

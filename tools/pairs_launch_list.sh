@@ -1,6 +1,6 @@
 #!/bin/bash
 # per-kernel durations of the pair-batch matching kernels (config 2 / 3 legs of bench.py) under ncu: pairs_launch_list.sh out.csv
-ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active --clock-control none -k regex:"bf_|window_|grid_build|stereo_|search_batch" -c 40 --csv --log-file $1 python bench.py --no-hamming --no-cpu --e2e-callers 1 --steps 2 --warmup 1 > /dev/null 2>&1
+ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active --clock-control none -k regex:"bf_|window_|grid_build|stereo_|search_batch" -c ${2:-40} --csv --log-file $1 python bench.py --no-hamming --no-cpu --e2e-callers 1 --steps 2 --warmup 1 > /dev/null 2>&1
 python - "$1" <<PY
 import csv,collections,sys
 rows=[r for r in csv.reader(open(sys.argv[1])) if len(r)>10]
