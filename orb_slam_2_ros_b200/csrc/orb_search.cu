@@ -73,6 +73,7 @@ __device__ __forceinline__ void grid_build_body(const orb_kp* __restrict__ kps, 
 }
 
 #define SR_K 8   // unmasked top-K per query kept for the optimistic resolve
+#define WC_STAGE 160   // candidates of one window staged in shared memory by window_candidates_body (per warp)
 #define SR_CH 1024  // queries staged in shared memory per chunk of the sequential walk
 #ifndef SR_THREADS
 #define SR_THREADS 1024
@@ -97,9 +98,7 @@ __device__ __forceinline__ unsigned warp_topk_extract(unsigned (&best)[SR_K], in
     unsigned mine = 0xFFFFFFFFu;
 #pragma unroll
     for (int k = 0; k < SR_K; ++k) {
-        unsigned m = best[0];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+        const unsigned m = __reduce_min_sync(0xffffffffu, best[0]);   // redux.sync: one instruction instead of 5 shuffles + 5 min
         if (lane == k) mine = m;
         if (best[0] == m && m != 0xFFFFFFFFu) {
 #pragma unroll
@@ -144,6 +143,12 @@ __device__ __forceinline__ void window_candidates_body(const SearchArgs& a) {
             best[k] = lo;
         }
     };
+    // One walk over the window's cells: the candidates (index, distance) are staged in a per-warp shared-memory buffer, the
+    // arena segment is reserved once their number is known, and the staged entries are copied out.  (The first version walked
+    // the cells twice — count, then write — and gathered every keypoint record twice in a latency-bound kernel.)  A window with
+    // more than WC_STAGE candidates takes the second walk after all, writing straight to the arena.
+    __shared__ unsigned s_stage[8][WC_STAGE];
+    unsigned* stage = s_stage[threadIdx.x >> 5];
     for (int pass = 0; pass < 2; ++pass) {
         int written = 0;
         for (int ix = nMinCellX; ix <= nMaxCellX; ++ix) {
@@ -165,8 +170,8 @@ __device__ __forceinline__ void window_candidates_body(const SearchArgs& a) {
                     if (!(fabsf(dx) < r && fabsf(dy) < r)) ok = false;
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, ok);
-                if (pass == 1 && ok) {
-                    const int pos = base + written + __popc(m & ((1u << lane) - 1));
+                const int lpos = written + __popc(m & ((1u << lane) - 1));   // position in candidate order
+                if (ok && (pass == 1 || lpos < WC_STAGE)) {
                     int d = dist256(dq, reinterpret_cast<const uint4*>(a.desc + (size_t)id * 32));
                     // the stereo consistency test of the reference loop (ORBmatcher.cc:91-96, 1409-1415) is folded
                     // into the list: a candidate that fails it gets the sentinel distance 0xFFFF
@@ -174,9 +179,13 @@ __device__ __forceinline__ void window_candidates_body(const SearchArgs& a) {
                         const float er = fabsf(__fsub_rn(a.q_ur[qi], a.u_right[id]));
                         if (er > a.q_er_max[qi]) d = 0xFFFF;
                     }
-                    a.cand_idx[pos] = id;
-                    a.cand_dist[pos] = (unsigned short)d;
-                    if (d < 256) { const unsigned key = ((unsigned)d << 16) | (unsigned)(pos - base); if (key < best[SR_K - 1]) insert(key); }
+                    if (pass == 0) {
+                        stage[lpos] = (unsigned)id | ((unsigned)d << 16);
+                    } else {
+                        a.cand_idx[base + lpos] = id;
+                        a.cand_dist[base + lpos] = (unsigned short)d;
+                    }
+                    if (d < 256) { const unsigned key = ((unsigned)d << 16) | (unsigned)lpos; if (key < best[SR_K - 1]) insert(key); }
                 }
                 written += __popc(m);
             }
@@ -191,6 +200,17 @@ __device__ __forceinline__ void window_candidates_body(const SearchArgs& a) {
                 return;
             }
             if (lane == 0) { a.cand_count[qi] = total; a.cand_base[qi] = base; }
+            if (total <= WC_STAGE) {          // the usual case: copy the staged list out, done
+                __syncwarp();
+                for (int k = lane; k < total; k += 32) {
+                    const unsigned e = stage[k];
+                    a.cand_idx[base + k] = (int)(e & 0xFFFFu);
+                    a.cand_dist[base + k] = (unsigned short)(e >> 16);
+                }
+                break;
+            }
+#pragma unroll
+            for (int k = 0; k < SR_K; ++k) best[k] = 0xFFFFFFFFu;   // the second walk rebuilds the list over all candidates
         }
     }
     // warp merge of the per-lane sorted top-K lists
@@ -198,11 +218,7 @@ __device__ __forceinline__ void window_candidates_body(const SearchArgs& a) {
     if (lane < SR_K) a.topk[(size_t)qi * SR_K + lane] = mine;
 }
 
-__device__ __forceinline__ unsigned warp_min_u32(unsigned v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
+__device__ __forceinline__ unsigned warp_min_u32(unsigned v) { return __reduce_min_sync(0xffffffffu, v); }
 
 __device__ void three_maxima(const int* cnt, int& ind1, int& ind2, int& ind3) {  // ORBmatcher.cc:1603-1644
     int max1 = 0, max2 = 0, max3 = 0;
@@ -994,6 +1010,7 @@ __global__ void __launch_bounds__(BFT_THREADS) bf_rows_batch_kernel(const BfJob*
     if (blockIdx.x * BFT_THREADS >= n1) return;   // uniform per CTA
     bf_rows_tiled_body(J.d1, n1, J.d2, n2, J.topk, track_key, m16, m17, m18);
 }
+template <bool SMEM>
 __global__ void __launch_bounds__(SR_THREADS, 1)
 bf_resolve_batch_kernel(const BfJob* __restrict__ jobs, int th_dist, float nn_ratio, int check_ori) {
     const BfJob& J = jobs[blockIdx.x];
@@ -1004,7 +1021,7 @@ bf_resolve_batch_kernel(const BfJob* __restrict__ jobs, int th_dist, float nn_ra
         if (threadIdx.x == 0) *J.nm = 0;
         return;
     }
-    bf_resolve_body<false>(J.d1, J.d2, J.topk, n1, n2, J.a1, J.a2, th_dist, nn_ratio, check_ori, J.owner, J.owner2, J.m12, J.bin, J.nm);
+    bf_resolve_body<SMEM>(J.d1, J.d2, J.topk, n1, n2, J.a1, J.a2, th_dist, nn_ratio, check_ori, J.owner, J.owner2, J.m12, J.bin, J.nm);
 }
 
 // ---- best / second-best over explicit candidate lists (CSR): one warp per query ------------------------------
@@ -1839,7 +1856,16 @@ int orb_match_bruteforce_batch_device(int device, int npairs, const orb_kp* d_kp
     const BfJob* d_jobs = (const BfJob*)W.d;
     const unsigned track_key = (unsigned)(bf_track_limit(th_dist, nn_ratio) + 1) << 16;
     bf_rows_batch_kernel<<<dim3((cap1 + BFT_THREADS - 1) / BFT_THREADS, npairs), BFT_THREADS, 0, st>>>(d_jobs, track_key, 1u << 16, 2u << 16, 4u << 16);
-    bf_resolve_batch_kernel<<<npairs, SR_THREADS, 0, st>>>(d_jobs, th_dist, nn_ratio, check_orientation);
+    {
+        const size_t own_smem = 8 * (size_t)cap2;   // the two owner arrays of a pair in shared memory when they fit, else in the workspace
+        static bool attr_set[64] = {};   // per device
+        if (!attr_set[device & 63]) {
+            ORB_CUDA(cudaFuncSetAttribute(bf_resolve_batch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_set[device & 63] = true;
+        }
+        if (own_smem <= 200 * 1024) bf_resolve_batch_kernel<true><<<npairs, SR_THREADS, own_smem, st>>>(d_jobs, th_dist, nn_ratio, check_orientation);
+        else bf_resolve_batch_kernel<false><<<npairs, SR_THREADS, 0, st>>>(d_jobs, th_dist, nn_ratio, check_orientation);
+    }
     ORB_CUDA(cudaGetLastError());
     return ORB_OK;
 }
