@@ -118,8 +118,7 @@ stereo_match_kernel(const uint8_t* __restrict__ pyrL, const uint8_t* __restrict_
             if (d < TH_HIGH) best = min(best, ((unsigned)d << 16) | (unsigned)iR);
         }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    best = __reduce_min_sync(0xffffffffu, best);
     if (best == 0xFFFFFFFFu) return;
     const int bestDist = (int)(best >> 16), bestIdxR = (int)(best & 0xFFFFu);
     if (bestDist >= (TH_HIGH + TH_LOW) / 2) return;
@@ -158,8 +157,7 @@ stereo_match_kernel(const uint8_t* __restrict__ pyrL, const uint8_t* __restrict_
             const int p = lane + 32 * k;
             if (p < 121) s += abs(il[k] - ((int)PR[(long long)(y0 + py[k]) * G.pitch + xr0 + inc + px[k]] - cR));
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        s = __reduce_add_sync(0xffffffffu, s);
         if (want_next) { d_at_best_p1 = s; want_next = false; }
         if (s < bestSad) { bestSad = s; bestinc = inc; d_at_best_m1 = d_prev; d_at_best = s; want_next = true; }
         d_prev = s;
