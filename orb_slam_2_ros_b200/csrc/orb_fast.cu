@@ -43,7 +43,8 @@ namespace {
 // 640x480 instead of the worst case 66), which is what decides how many CTAs fit an SM: 30 KB -> 6-7 CTAs, 44 KB -> 5.
 #define FS_TILE_BYTES(rows) ((rows) * FS_PITCH)
 #define FS_SCORE_BYTES(rows) (((rows) - 4) * FS_PITCH)      // evaluated rows (rows - 6) + a zero row above and below
-#define FS_SMEM(rows) (FS_TILE_BYTES(rows) + FS_CAND_BYTES + FS_SCORED_BYTES + FS_SCORE_BYTES(rows) + 256)   // 128 for the alignment + 128 readable bytes in front of the tile
+#define FS_CODE_BYTES (8 * FS_THREADS * 2)                   // stage A: tile code of every (item, thread), for the candidate decode
+#define FS_SMEM(rows) (FS_TILE_BYTES(rows) + FS_CAND_BYTES + FS_SCORED_BYTES + FS_SCORE_BYTES(rows) + FS_CODE_BYTES + 256)   // 128 for the alignment + 128 readable bytes in front of the tile
 #define FS_OUT_CAP(rows) ((FS_TILE_BYTES(rows) + FS_CAND_BYTES) / 8)   // records that fit the (dead) tile + candidate segments; anything beyond goes straight to global
 
 // exact FAST score of the pixel at t (shared-memory tile): both polarities in one s16x2 min/max tree on the packed
@@ -153,6 +154,7 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
     unsigned short* cand = reinterpret_cast<unsigned short*>(fs_smem + tile_bytes);               // per-warp segments
     unsigned short* scored = reinterpret_cast<unsigned short*>(fs_smem + tile_bytes + FS_CAND_BYTES);
     uint8_t* score = fs_smem + tile_bytes + FS_CAND_BYTES + FS_SCORED_BYTES;                      // (fast_rows - 4) x FS_PITCH scores
+    unsigned short* codes = reinterpret_cast<unsigned short*>(score + FS_SCORE_BYTES(g.fast_rows));   // [8][FS_THREADS]
     unsigned long long* outl = reinterpret_cast<unsigned long long*>(fs_smem);                   // pass 3: aliases tile + cand
     __shared__ int s_any[FS_MAXG];
     __shared__ int s_nscored, s_nout, s_base, s_nempty;
@@ -212,12 +214,13 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
     const unsigned inv_nw = S.inv_nw;
     const unsigned vfirst = (0xFu << (sb_lo & 3)) & 0xFu, vlast = 0xFu >> (3 - ((sb_hi - 1) & 3));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    auto score_one = [&](int r, int sb) {
-        const int sc = fast_score_at(tile + (r + 3) * FS_PITCH + sb);
+    // code = r * FS_PITCH + sb addresses the tile (3 rows down: the halo), the score tile (one zero row down) and the list alike
+    auto score_one = [&](int code) {
+        const int sc = fast_score_at(tile + 3 * FS_PITCH + code);
         if (sc >= tmin) {
-            score[(r + 1) * FS_PITCH + sb] = (uint8_t)sc;
+            score[FS_PITCH + code] = (uint8_t)sc;
             const int o = atomicAdd(&s_nscored, 1);
-            if (o < FS_SCAP) scored[o] = (unsigned short)(r * FS_PITCH + sb);
+            if (o < FS_SCAP) scored[o] = (unsigned short)code;
         }
     };
     // warp-level compaction of the per-lane candidate masks + exact scores.  decode(bit) -> tile code (row * FS_PITCH + byte) of
@@ -247,20 +250,14 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
             }
             __syncwarp();
             // 1b: exact score of the warp's candidates
-            for (int k = lane; k < wtotal; k += 32) {
-                const int code = seg[k];
-                const int r = (int)__umulhi((unsigned)code, 0xFFFFFFFFu / FS_PITCH + 1u);
-                score_one(r, code - r * FS_PITCH);
-            }
+            for (int k = lane; k < wtotal; k += 32) score_one(seg[k]);
             __syncwarp();
         } else {
             // segment overflow (a warp with > 448 candidates): score in place, lane by lane
             while (cmask) {
                 const int bit = __ffsll((long long)cmask) - 1;
                 cmask &= cmask - 1ull;
-                const int code = decode(bit);
-                const int r = (int)__umulhi((unsigned)code, 0xFFFFFFFFu / FS_PITCH + 1u);
-                score_one(r, code - r * FS_PITCH);
+                score_one(decode(bit));
             }
         }
     };
@@ -314,7 +311,9 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
         for (int k = threadIdx.x; k < total; k += FS_THREADS, ++it) {
             const int r = (int)__umulhi((unsigned)k, inv_np), q = k - r * np;
             constexpr int P = FS_PITCH / 4;
-            const unsigned* row = reinterpret_cast<const unsigned*>(tile + (r + 3) * FS_PITCH) + w0p + 2 * q;   // centre row, 8-byte aligned
+            const int code0 = r * FS_PITCH + ((w0p + 2 * q) << 2);          // tile code of the item's first pixel, kept for the candidate decode
+            codes[it * FS_THREADS + threadIdx.x] = (unsigned short)code0;
+            const unsigned* row = reinterpret_cast<const unsigned*>(tile + 3 * FS_PITCH + code0);   // centre row, 8-byte aligned
             const uint2 c = *reinterpret_cast<const uint2*>(row);
             const unsigned wl = row[-1], wr = row[2];
             const uint2 u = *reinterpret_cast<const uint2*>(row + 3 * P), d = *reinterpret_cast<const uint2*>(row - 3 * P);   // (0,+3) (0,-3)
@@ -332,11 +331,7 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
             const unsigned m = (m0 | (m1 << 4)) & s_pvm[q];
             cmask |= (unsigned long long)m << (8 * it);
         }
-        compact_score(cmask, [&](int bit) {
-            const int k = threadIdx.x + (bit >> 3) * FS_THREADS;
-            const int r = (int)__umulhi((unsigned)k, inv_np), q = k - r * np;
-            return r * FS_PITCH + ((w0p + 2 * q) << 2) + (bit & 7);
-        });
+        compact_score(cmask, [&](int bit) { return (int)codes[(bit >> 3) * FS_THREADS + threadIdx.x] + (bit & 7); });
     };
     // stage A: the whole strip at iniThFAST (a cell that has an NMS maximum >= iniThFAST never needs anything lower)
 #if FS_QUICK == 2
