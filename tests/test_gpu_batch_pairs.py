@@ -198,3 +198,45 @@ def test_batch_edge_cases_empty_pairs_and_candidate_overflow(oracle):
         n = nms.cpu().numpy()
         assert n[1] == 0 and n[2] == 0
         assert (n[0] == -1) if expect_overflow else (n[0] > 100)
+
+
+@pytest.mark.parametrize("th,ratio", [(50, 0.6), (100, 0.9), (100, 0.75)])
+def test_match_bruteforce_batch_dense_near_duplicates(oracle, th, ratio):
+    """The batched brute-force kernel lists, per query, only the targets whose distance can still change a decision (<= the
+    `track` limit derived from th_dist / nn_ratio) and at most 8 of them.  Descriptor sets made of a few prototypes with a
+    handful of flipped bits give every query dozens of such targets, many of them taken by earlier queries: the list is
+    truncated, the resolve step must fall back to recomputing the row, and the result must still be the oracle's."""
+    import torch
+    from orb_slam_2_ros_b200.matcher import match_bruteforce_batch_device
+    rng = np.random.default_rng(1234 + th)
+    P, cap = 3, 640
+    n1s, n2s = [600, 640, 37], [640, 500, 41]
+    d1 = np.zeros((P, cap, 32), np.uint8); d2 = np.zeros((P, cap, 32), np.uint8)
+    a1 = rng.uniform(0, 360, (P, cap)).astype(np.float32); a2 = (a1 + rng.normal(0, 20, (P, cap))).astype(np.float32) % np.float32(360)
+    for p in range(P):
+        protos = rng.integers(0, 256, (12, 32), dtype=np.uint8)
+        def noisy(n):
+            out = protos[rng.integers(0, 12, n)].copy()
+            bits = np.unpackbits(out, axis=1)
+            for i in range(n):
+                k = int(rng.integers(0, 40))
+                bits[i, rng.choice(256, k, replace=False)] ^= 1
+            return np.packbits(bits, axis=1)
+        d1[p, :n1s[p]] = noisy(n1s[p]); d2[p, :n2s[p]] = noisy(n2s[p])
+    from orb_slam_2_ros_b200._lib import KP_DTYPE
+    k1 = np.zeros((P, cap), KP_DTYPE); k2 = np.zeros((P, cap), KP_DTYPE)
+    k1["angle"] = a1; k2["angle"] = a2
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    tk1, tk2 = dev(k1.view(np.uint8).reshape(P, cap, -1)), dev(k2.view(np.uint8).reshape(P, cap, -1))
+    td1, td2 = dev(d1), dev(d2)
+    tn1, tn2 = dev(np.array(n1s, np.int32)), dev(np.array(n2s, np.int32))
+    m12 = torch.full((P, cap), -7, dtype=torch.int32, device="cuda"); nm = torch.zeros(P, dtype=torch.int32, device="cuda")
+    match_bruteforce_batch_device(P, tk1.data_ptr(), td1.data_ptr(), tn1.data_ptr(), cap, tk2.data_ptr(), td2.data_ptr(), tn2.data_ptr(), cap,
+                                  m12.data_ptr(), nm.data_ptr(), th, ratio, True, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    m, n = m12.cpu().numpy(), nm.cpu().numpy()
+    for p in range(P):
+        nm_o, m_o = oracle.match_bruteforce(d1[p, :n1s[p]], a1[p, :n1s[p]], d2[p, :n2s[p]], a2[p, :n2s[p]], th, ratio, True)
+        assert n[p] == nm_o, (p, n[p], nm_o)
+        assert np.array_equal(m[p, :n1s[p]], m_o)
+        assert np.all(m[p, n1s[p]:] == -1)
