@@ -662,9 +662,10 @@ __device__ __forceinline__ void window_resolve_body(const SearchArgs& a, int mod
 // =============================== brute force with mask (SearchByBoW inner loop) ===============================
 #define BF_K SR_K
 
-// one warp per query row (latency shape, one pair): sorted top-K packed keys (dist<<16 | j) of the distances to every target
+// one warp per query row (latency shape, one pair): distances to every target (stored, u16) + sorted top-K packed keys (dist<<16 | j)
 __device__ __forceinline__ void bf_rows_body(const uint8_t* __restrict__ d1, int n1, const uint8_t* __restrict__ d2, int n2,
-                                             unsigned* __restrict__ topk) {
+                                             unsigned short* __restrict__ D, int dpitch, unsigned* __restrict__ topk,
+                                             unsigned track_key /* see bf_rows_tiled_body */) {
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= n1) return;
@@ -682,8 +683,10 @@ __device__ __forceinline__ void bf_rows_body(const uint8_t* __restrict__ d1, int
     };
     for (int j = lane; j < n2; j += 32) {
         const int d = dist256(dq, reinterpret_cast<const uint4*>(d2 + (size_t)j * 32));
+        D[(size_t)i * dpitch + j] = (unsigned short)d;   // the one-pair form keeps the distance row for the resolve step's fallback scan
         const unsigned key = ((unsigned)d << 16) | (unsigned)j;
-        if (d < 256 && key < best[BF_K - 1]) insert(key);   // a distance of 256 never becomes best or second best (ORBmatcher.cc:217-226: dist < 256 is false)
+        if (key < track_key && key < best[BF_K - 1]) insert(key);   // only distances that can change a decision (track_key <= 256 << 16: a distance of
+                                                                     // 256 never becomes best or second best, ORBmatcher.cc:217-226)
     }
     const unsigned mine = warp_topk_extract(best, lane);
     if (lane < BF_K) topk[(size_t)i * BF_K + lane] = mine;
@@ -807,7 +810,8 @@ static int bf_track_limit(int th_dist, float nn_ratio) {
 // microseconds (the sequential walk of 1000 queries took 330 us).  The optimistic top-K list answers a query when two of
 // its entries are still visible; otherwise the query's warp scans its whole distance row cooperatively.
 template <bool SMEM>
-__device__ __forceinline__ void bf_resolve_body(const uint8_t* __restrict__ d1, const uint8_t* __restrict__ d2, const unsigned* __restrict__ topk, int n1, int n2,
+__device__ __forceinline__ void bf_resolve_body(const uint8_t* __restrict__ d1, const uint8_t* __restrict__ d2, const unsigned short* __restrict__ D, int dpitch,
+                                                const unsigned* __restrict__ topk, int n1, int n2,
                                                 const float* __restrict__ angle1, const float* __restrict__ angle2, int th_dist, float nn_ratio,
                                                 int check_ori, int* owner /*[n2]*/, int* owner_scratch /*[n2], !SMEM only*/, int* match12,
                                                 signed char* match_bin, int* nmatches_out) {
@@ -844,7 +848,7 @@ __device__ __forceinline__ void bf_resolve_body(const uint8_t* __restrict__ d1, 
                 }
                 fallback = nfree < 2 && key[SR_K - 1] != 0xFFFFFFFFu;   // list truncated and too many of its entries taken
             }
-            // fallback: the lanes of the warp recompute the distances of each such query to all targets
+            // fallback: the lanes of the warp scan the distances of each such query to all targets
             unsigned todo = __ballot_sync(0xffffffffu, fallback);
             while (todo) {
                 const int src = __ffs((int)todo) - 1;
@@ -854,7 +858,8 @@ __device__ __forceinline__ void bf_resolve_body(const uint8_t* __restrict__ d1, 
                 const uint4* dq = reinterpret_cast<const uint4*>(d1 + (size_t)fi * 32);
                 for (int jj = lane; jj < n2; jj += 32) {
                     if ((SMEM ? own_prev[jj] : __ldcg(own_prev + jj)) < fi) continue;
-                    const unsigned dd = (unsigned)dist256(dq, reinterpret_cast<const uint4*>(d2 + (size_t)jj * 32));   // recomputed: no distance matrix is kept
+                    // the batched form keeps no distance matrix (2 MB per pair): its fallback recomputes the row
+                    const unsigned dd = D ? (unsigned)D[(size_t)fi * dpitch + jj] : (unsigned)dist256(dq, reinterpret_cast<const uint4*>(d2 + (size_t)jj * 32));
                     if (dd >= 256u) continue;                               // invisible to the reference's strict '<' updates
                     const unsigned k = (dd << 16) | (unsigned)jj;
                     a2 = min(a2, max(k, a1));
@@ -938,15 +943,17 @@ window_resolve_kernel(const SearchArgs a, int mode, int th_dist, float nn_ratio,
                         smem_bytes);
 }
 __global__ void __launch_bounds__(256)
-bf_rows_kernel(const uint8_t* __restrict__ d1, int n1, const uint8_t* __restrict__ d2, int n2, unsigned* __restrict__ topk) {
-    bf_rows_body(d1, n1, d2, n2, topk);
+bf_rows_kernel(const uint8_t* __restrict__ d1, int n1, const uint8_t* __restrict__ d2, int n2, unsigned short* __restrict__ D, int dpitch,
+               unsigned* __restrict__ topk, unsigned track_key) {
+    bf_rows_body(d1, n1, d2, n2, D, dpitch, topk, track_key);
 }
 template <bool SMEM>
 __global__ void __launch_bounds__(SR_THREADS, 1)
-bf_resolve_kernel(const uint8_t* __restrict__ d1, const uint8_t* __restrict__ d2, const unsigned* __restrict__ topk, int n1, int n2,
+bf_resolve_kernel(const uint8_t* __restrict__ d1, const uint8_t* __restrict__ d2, const unsigned short* __restrict__ D, int dpitch,
+                  const unsigned* __restrict__ topk, int n1, int n2,
                   const float* __restrict__ angle1, const float* __restrict__ angle2, int th_dist, float nn_ratio, int check_ori, int* owner,
                   int* owner_scratch, int* match12, signed char* match_bin, int* nmatches_out) {
-    bf_resolve_body<SMEM>(d1, d2, topk, n1, n2, angle1, angle2, th_dist, nn_ratio, check_ori, owner, owner_scratch, match12, match_bin, nmatches_out);
+    bf_resolve_body<SMEM>(d1, d2, D, dpitch, topk, n1, n2, angle1, angle2, th_dist, nn_ratio, check_ori, owner, owner_scratch, match12, match_bin, nmatches_out);
 }
 
 // Batched forms (per-pair matching shards like frames): blockIdx.y (one-CTA kernels: blockIdx.x) = pair.  The
@@ -1021,7 +1028,7 @@ bf_resolve_batch_kernel(const BfJob* __restrict__ jobs, int th_dist, float nn_ra
         if (threadIdx.x == 0) *J.nm = 0;
         return;
     }
-    bf_resolve_body<SMEM>(J.d1, J.d2, J.topk, n1, n2, J.a1, J.a2, th_dist, nn_ratio, check_ori, J.owner, J.owner2, J.m12, J.bin, J.nm);
+    bf_resolve_body<SMEM>(J.d1, J.d2, nullptr, 0, J.topk, n1, n2, J.a1, J.a2, th_dist, nn_ratio, check_ori, J.owner, J.owner2, J.m12, J.bin, J.nm);
 }
 
 // ---- best / second-best over explicit candidate lists (CSR): one warp per query ------------------------------
@@ -1533,7 +1540,8 @@ int orb_match_bruteforce(int device, const uint8_t* desc1, const float* angle1, 
     const size_t in_bytes = c.off;
     const size_t o_m12 = c.take(4 * (size_t)n1), o_nm = c.take(16);
     const size_t io_bytes = c.off;
-    const size_t o_topk = c.take(4 * (size_t)n1 * BF_K), o_owner = c.take(4 * (size_t)n2), o_owner2 = c.take(4 * (size_t)n2), o_bin = c.take(n1);
+    const int dpitch = (n2 + 7) & ~7;   // 16-byte aligned rows of the u16 distance matrix
+    const size_t o_D = c.take(2 * (size_t)n1 * dpitch), o_topk = c.take(4 * (size_t)n1 * BF_K), o_owner = c.take(4 * (size_t)n2), o_owner2 = c.take(4 * (size_t)n2), o_bin = c.take(n1);
     Workspace& W = g_ws;
     int rc = W.prepare(device, c.off, io_bytes);
     if (rc != ORB_OK) return rc;
@@ -1543,7 +1551,8 @@ int orb_match_bruteforce(int device, const uint8_t* desc1, const float* angle1, 
     if (angle1) memcpy(H + o_a1, angle1, 4 * (size_t)n1);
     if (angle2) memcpy(H + o_a2, angle2, 4 * (size_t)n2);
     ORB_CUDA(cudaMemcpyAsync(Dv, H, in_bytes, cudaMemcpyHostToDevice, st));
-    bf_rows_kernel<<<(n1 + 7) / 8, 256, 0, st>>>(Dv + o_d1, n1, Dv + o_d2, n2, (unsigned*)(Dv + o_topk));
+    bf_rows_kernel<<<(n1 + 7) / 8, 256, 0, st>>>(Dv + o_d1, n1, Dv + o_d2, n2, (unsigned short*)(Dv + o_D), dpitch, (unsigned*)(Dv + o_topk),
+                                                 (unsigned)(bf_track_limit(th_dist, nn_ratio) + 1) << 16);   // (unpruned lists: 101 instead of 89 us per call)
     {
         const size_t own_smem = 8 * (size_t)n2;   // two owner arrays in shared memory when they fit, else in the workspace
         static bool attr_set[64] = {};   // per device
@@ -1552,12 +1561,12 @@ int orb_match_bruteforce(int device, const uint8_t* desc1, const float* angle1, 
             attr_set[device & 63] = true;
         }
         if (own_smem <= 200 * 1024)
-            bf_resolve_kernel<true><<<1, SR_THREADS, own_smem, st>>>(Dv + o_d1, Dv + o_d2, (const unsigned*)(Dv + o_topk), n1, n2,
+            bf_resolve_kernel<true><<<1, SR_THREADS, own_smem, st>>>(Dv + o_d1, Dv + o_d2, (const unsigned short*)(Dv + o_D), dpitch, (const unsigned*)(Dv + o_topk), n1, n2,
                                                                      (const float*)(Dv + o_a1), (const float*)(Dv + o_a2), th_dist, nn_ratio, check_orientation,
                                                                      (int*)(Dv + o_owner), (int*)(Dv + o_owner2), (int*)(Dv + o_m12),
                                                                      (signed char*)(Dv + o_bin), (int*)(Dv + o_nm));
         else
-            bf_resolve_kernel<false><<<1, SR_THREADS, 0, st>>>(Dv + o_d1, Dv + o_d2, (const unsigned*)(Dv + o_topk), n1, n2,
+            bf_resolve_kernel<false><<<1, SR_THREADS, 0, st>>>(Dv + o_d1, Dv + o_d2, (const unsigned short*)(Dv + o_D), dpitch, (const unsigned*)(Dv + o_topk), n1, n2,
                                                                (const float*)(Dv + o_a1), (const float*)(Dv + o_a2), th_dist, nn_ratio, check_orientation,
                                                                (int*)(Dv + o_owner), (int*)(Dv + o_owner2), (int*)(Dv + o_m12),
                                                                (signed char*)(Dv + o_bin), (int*)(Dv + o_nm));
