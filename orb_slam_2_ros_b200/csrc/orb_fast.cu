@@ -47,6 +47,10 @@ namespace {
 #define FS_SMEM(rows) (FS_TILE_BYTES(rows) + FS_CAND_BYTES + FS_SCORED_BYTES + FS_SCORE_BYTES(rows) + FS_CODE_BYTES + 256)   // 128 for the alignment + 128 readable bytes in front of the tile
 #define FS_OUT_CAP(rows) ((FS_TILE_BYTES(rows) + FS_CAND_BYTES) / 8)   // records that fit the (dead) tile + candidate segments; anything beyond goes straight to global
 
+// k / d by the host-built magic number inv = floor((2^32 - 1) / d) + 1 (exact for the small k used here); d == 1 has no 32-bit magic
+// number (it would be 2^32), and it does occur: a strip whose last cell is 7 px wide evaluates ONE column there
+__device__ __forceinline__ int fs_div(int k, int d, unsigned inv) { return d == 1 ? k : (int)__umulhi((unsigned)k, inv); }
+
 // exact FAST score of the pixel at t (shared-memory tile): both polarities in one s16x2 min/max tree on the packed
 // pairs (r_k, 255 - r_k):  lo -> max_arc min r = bmax,  hi -> max_arc min (255 - r) = 255 - min_arc max r = 255 - amin
 __device__ __forceinline__ int fast_score_at(const uint8_t* t) {
@@ -309,7 +313,7 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
         unsigned long long cmask = 0ull;
         int it = 0;
         for (int k = threadIdx.x; k < total; k += FS_THREADS, ++it) {
-            const int r = (int)__umulhi((unsigned)k, inv_np), q = k - r * np;
+            const int r = fs_div(k, np, inv_np), q = k - r * np;
             constexpr int P = FS_PITCH / 4;
             const int code0 = r * FS_PITCH + ((w0p + 2 * q) << 2);          // tile code of the item's first pixel, kept for the candidate decode
             codes[it * FS_THREADS + threadIdx.x] = (unsigned short)code0;
@@ -339,7 +343,7 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
 #else
     cand_pass(eh * nw,
               [&](int k, int& r, int& wd, unsigned& vm) {
-                  r = (int)__umulhi((unsigned)k, inv_nw);
+                  r = fs_div(k, nw, inv_nw);
                   wd = wlo + (k - r * nw);
                   vm = (wd == wlo ? vfirst : 0xFu) & (wd == whi ? vlast : 0xFu);
               },
@@ -393,7 +397,7 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
     } else {
         // scored-list overflow: scan the score tile instead (same result, slower)
         for (int k = threadIdx.x; k < eh * nw; k += FS_THREADS) {
-            const int r = (int)__umulhi((unsigned)k, inv_nw);
+            const int r = fs_div(k, nw, inv_nw);
             const int wd = wlo + (k - r * nw);
             const unsigned sw = reinterpret_cast<const unsigned*>(score + (r + 1) * FS_PITCH)[wd];
             for (int b = 0; b < 4; ++b) {
@@ -427,7 +431,7 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
                       int e = 0;
                       while (e + 1 < nempty && k >= s_bpre[e + 1]) ++e;
                       const int kk = k - s_bpre[e], n = s_bnw[e];
-                      r = (int)__umulhi((unsigned)kk, s_binv[e]);
+                      r = fs_div(kk, n, s_binv[e]);
                       const int cw = kk - r * n;
                       wd = s_bw0[e] + cw;
                       vm = (cw == 0 ? s_bmf[e] : 0xFu) & (cw == n - 1 ? s_bml[e] : 0xFu);
@@ -457,7 +461,7 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
         }
     } else {
         for (int k = threadIdx.x; k < eh * nw; k += FS_THREADS) {
-            const int r = (int)__umulhi((unsigned)k, inv_nw);
+            const int r = fs_div(k, nw, inv_nw);
             const int wd = wlo + (k - r * nw);
             const unsigned sw = reinterpret_cast<const unsigned*>(score + (r + 1) * FS_PITCH)[wd];
             for (int b = 0; b < 4; ++b) {

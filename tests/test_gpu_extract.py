@@ -287,3 +287,24 @@ def test_device_resident_input_alignments(oracle, ORB, w, h, pad, shift):
     oex.extract(imgs[0])
     for l in range(8):
         assert np.array_equal(ex.pyramid_level_bordered(l), oex.level(l)), "bordered level %d" % l
+
+
+@pytest.mark.parametrize("w,h,nf", [(1920, 1080, 2000), (645, 487, 800), (333, 251, 400), (1241, 376, 1500), (2600, 300, 1500)])
+def test_batch_throughput_kernels_odd_and_wide_shapes(oracle, ORB, w, h, nf):
+    """Batches of >= 8 frames take the throughput kernels (pyramid levels staged by bulk copies, one CTA per 16 rows x a segment
+    of <= 256 bordered words): wide images need several segments per row, odd sizes end in partial words / partial strips.
+    Every frame of the batch must give the oracle's keypoints and descriptors, frame 0 also its bordered and blurred levels."""
+    F = 9
+    imgs = synth.synth_batch(700 + w, F, w, h, unique=3)
+    ex = ORB(nf, max_batch=F)
+    res = ex.extract_batch(imgs)
+    oex = oracle.Extractor(nf)
+    for f in (1, 4, 8, 0):          # frame 0 last: the oracle then holds frame 0's levels
+        ok, od = oex.extract(imgs[f])
+        assert_kps_equal(res[f][0], ok, "frame %d" % f)
+        assert np.array_equal(res[f][1], od)
+    for l in range(8):
+        assert np.array_equal(ex.pyramid_level_bordered(l), oex.level(l)), "bordered level %d" % l
+        ob = oex.blurred(l)
+        if ob is not None:
+            assert np.array_equal(ex.debug_blurred(l), ob), "blur level %d" % l
