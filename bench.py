@@ -925,6 +925,38 @@ def main():
     pairs = pairs_legs() if not args.no_pairs else None
     config4 = config4_leg() if not args.no_pairs else None
 
+    def content_leg():
+        """The same device-resident step on frames with fewer corner sources (40 rectangles + 20 triangles, +-2 noise instead of
+        260 + 120, +-8): FAST's time follows the number of candidate pixels (the exact scorer, NMS and emission run per candidate),
+        the other stages do not care.  Raw NMS corners of frame 0 (all levels) are reported for both contents."""
+        step_device()
+        barrier()
+        raw_default = sum(len(ex.debug_raw_corners(l)) for l in range(NLEVELS))
+        sparse = synth.synth_batch(500000 + 1000 * rank, B, W, H, unique=16, noise=2, n_rect=40, n_tri=20)
+        d_frames.copy_(torch.from_numpy(sparse))
+        for _ in range(3):
+            step_device()
+        barrier()
+        ex.profile_enable(True)
+        ex.profile_read(reset=True)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        for _ in range(5):
+            step_device()
+        s1.record(stream)
+        barrier()
+        ms = max_over_ranks(s0.elapsed_time(s1)) / 5
+        st, calls, _ = ex.profile_read(reset=True)
+        ex.profile_enable(False)
+        raw_sparse = sum(len(ex.debug_raw_corners(l)) for l in range(NLEVELS))
+        d_frames.copy_(h_frames)
+        return {"workload": "same step, frames with 40 rectangles + 20 triangles and +-2 noise (fewer corner sources)", "ms_per_step": ms,
+                "frames_per_s": world * B / (ms * 1e-3), "stage_ms": {k: v / max(calls, 1) for k, v in st.items()},
+                "raw_nms_corners_frame0": raw_sparse, "raw_nms_corners_frame0_headline_content": raw_default,
+                "keypoints_per_frame": float(d_n.float().mean().item())}
+
+    content = content_leg() if not args.no_pairs else None
+
     sampler.join(timeout=2.0)
     if clk.get("proc"):
         clk["proc"].kill()
@@ -1027,6 +1059,7 @@ def main():
             "hamming": ham,
             "pairs": pairs,
             "config4": config4,
+            "content_sensitivity": content,
             "other_configs": other_configs(local_rank) if (world == 1 and not args.no_cpu) else None,
             "clocks": summarize_clocks(clk.get("rows")),
         }

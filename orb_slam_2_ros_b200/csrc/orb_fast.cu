@@ -219,9 +219,11 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
     const unsigned vfirst = (0xFu << (sb_lo & 3)) & 0xFu, vlast = 0xFu >> (3 - ((sb_hi - 1) & 3));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // code = r * FS_PITCH + sb addresses the tile (3 rows down: the halo), the score tile (one zero row down) and the list alike
-    auto score_one = [&](int code) {
+    // SKIP (stage B): a pixel that already has a score (stage A scored it) is in the list already
+    auto score_one = [&](int code, const bool skip) {
         const int sc = fast_score_at(tile + 3 * FS_PITCH + code);
         if (sc >= tmin) {
+            if (skip && score[FS_PITCH + code] != 0) return;
             score[FS_PITCH + code] = (uint8_t)sc;
             const int o = atomicAdd(&s_nscored, 1);
             if (o < FS_SCAP) scored[o] = (unsigned short)code;
@@ -229,7 +231,7 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
     };
     // warp-level compaction of the per-lane candidate masks + exact scores.  decode(bit) -> tile code (row * FS_PITCH + byte) of
     // candidate bit `bit` of this lane's mask
-    auto compact_score = [&](unsigned long long cmask, auto&& decode) {
+    auto compact_score = [&](unsigned long long cmask, auto&& decode, const bool skip) {
         const int cnt = __popcll(cmask);
         int incl = cnt;
 #pragma unroll
@@ -254,14 +256,14 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
             }
             __syncwarp();
             // 1b: exact score of the warp's candidates
-            for (int k = lane; k < wtotal; k += 32) score_one(seg[k]);
+            for (int k = lane; k < wtotal; k += 32) score_one(seg[k], skip);
             __syncwarp();
         } else {
             // segment overflow (a warp with > 448 candidates): score in place, lane by lane
             while (cmask) {
                 const int bit = __ffsll((long long)cmask) - 1;
                 cmask &= cmask - 1ull;
-                score_one(decode(bit));
+                score_one(decode(bit), skip);
             }
         }
     };
@@ -301,19 +303,21 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
             unsigned vm;
             map(threadIdx.x + (bit >> 2) * FS_THREADS, r, wd, vm);
             return r * FS_PITCH + (wd << 2) + (bit & 3);
-        });
+        }, false);
     };
     // Stage A's candidate pass over WORD PAIRS (8 pixels of one row per item, <= 8 items per thread): the 18 tile words an
     // item needs are 11 loads (4 of them LDS.64) and 10 funnel shifts instead of 2 x (11 + 6), and the u16 high-byte form of
     // the quick test (quick_u16) needs no widening.  Pair q of a row = tile words w0p + 2q, w0p + 2q + 1 (w0p even).
-    auto pair_pass = [&](const int th) {
+    // map(k) gives item k's row, pair and valid-pixel mask; `total` <= eh * pairs per row <= 8 * FS_THREADS
+    auto pair_pass = [&](const int th, const int total, auto&& map, const bool skip) {
         const unsigned K = ((unsigned)th << 8) * 0x10001u, NK = ((0x10000u - ((unsigned)th << 8)) & 0xFFFFu) * 0x10001u, LIMB = 0xFFFFFFFFu - K;
-        const int np = S.np, w0p = S.w0p, total = eh * np;
-        const unsigned inv_np = S.inv_np;
+        const int w0p = S.w0p;
         unsigned long long cmask = 0ull;
         int it = 0;
         for (int k = threadIdx.x; k < total; k += FS_THREADS, ++it) {
-            const int r = fs_div(k, np, inv_np), q = k - r * np;
+            int r, q;
+            unsigned vm;
+            map(k, r, q, vm);
             constexpr int P = FS_PITCH / 4;
             const int code0 = r * FS_PITCH + ((w0p + 2 * q) << 2);          // tile code of the item's first pixel, kept for the candidate decode
             codes[it * FS_THREADS + threadIdx.x] = (unsigned short)code0;
@@ -332,14 +336,24 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
             const unsigned m1 = quick_word(c.y, u.y, d.y, __funnelshift_r(c.y, wr, 24), __funnelshift_r(c.x, c.y, 8),
                                            __funnelshift_r(pp.y, pr, 16), mmid,
                                            __funnelshift_r(mm.y, mr, 16), pmid, K, NK, LIMB);
-            const unsigned m = (m0 | (m1 << 4)) & s_pvm[q];
+            const unsigned m = (m0 | (m1 << 4)) & vm;
             cmask |= (unsigned long long)m << (8 * it);
         }
-        compact_score(cmask, [&](int bit) { return (int)codes[(bit >> 3) * FS_THREADS + threadIdx.x] + (bit & 7); });
+        compact_score(cmask, [&](int bit) { return (int)codes[(bit >> 3) * FS_THREADS + threadIdx.x] + (bit & 7); }, skip);
     };
     // stage A: the whole strip at iniThFAST (a cell that has an NMS maximum >= iniThFAST never needs anything lower)
 #if FS_QUICK == 2
-    pair_pass(tini);
+    {
+        const int np = S.np;
+        const unsigned inv_np = S.inv_np;
+        pair_pass(tini, eh * np,
+                  [&](int k, int& r, int& q, unsigned& vm) {
+                      r = fs_div(k, np, inv_np);
+                      q = k - r * np;
+                      vm = s_pvm[q];
+                  },
+                  false);
+    }
 #else
     cand_pass(eh * nw,
               [&](int k, int& r, int& wd, unsigned& vm) {
@@ -411,6 +425,45 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
 
     // ---- stage B (ORBextractor.cc:846-850): the cells without any maximum >= iniThFAST are searched again at
     //      minThFAST; their word items are enumerated cell by cell through a small prefix table ----
+#if FS_QUICK == 2
+    // (word PAIRS like stage A; runs of adjacent empty cells are enumerated as one range, so that a pair straddling two empty
+    // cells is visited once and the item count stays <= eh * pairs per row; interior cells are wider than a pair, so two
+    // runs never share one)
+    if (threadIdx.x == 0) {
+        int ne = 0, pre = 0, start = -1;
+        const int pb0 = S.w0p << 2;                        // shared-memory byte of pair 0's first pixel (<= sb_lo)
+        for (int jj = 0; jj <= FS_MAXG; ++jj) {
+            const bool cell = jj < FS_MAXG && jj * wCell < ew;
+            const bool empty = cell && !s_any[jj];
+            if (empty && start < 0) start = jj;
+            if (!empty && start >= 0) {                    // cells [start, jj) are empty
+                const int lo = sb_lo + start * wCell, hi = min(sb_lo + jj * wCell, sb_hi);   // shared-memory bytes of the run's evaluated columns
+                const int q0 = (lo - pb0) >> 3, n = ((hi - 1 - pb0) >> 3) - q0 + 1;
+                s_bw0[ne] = q0; s_bnw[ne] = n; s_binv[ne] = 0xFFFFFFFFu / (unsigned)n + 1u;
+                s_bmf[ne] = (0xFFu << ((lo - pb0) & 7)) & 0xFFu; s_bml[ne] = 0xFFu >> (7 - ((hi - 1 - pb0) & 7));
+                s_bpre[ne] = pre; pre += n * eh; ++ne;
+                start = -1;
+            }
+            if (!cell) break;
+        }
+        s_bpre[ne] = pre; s_nempty = ne;
+    }
+    __syncthreads();
+    const int nempty = s_nempty;
+    if (nempty > 0 && tmin < tini) {
+        pair_pass(tmin, s_bpre[nempty],
+                  [&](int k, int& r, int& q, unsigned& vm) {
+                      int e = 0;
+                      while (e + 1 < nempty && k >= s_bpre[e + 1]) ++e;
+                      const int kk = k - s_bpre[e], n = s_bnw[e];
+                      r = fs_div(kk, n, s_binv[e]);
+                      const int cp = kk - r * n;
+                      q = s_bw0[e] + cp;
+                      vm = s_pvm[q] & (cp == 0 ? s_bmf[e] : 0xFFu) & (cp == n - 1 ? s_bml[e] : 0xFFu);
+                  },
+                  true);
+    }
+#else
     if (threadIdx.x == 0) {
         int ne = 0, pre = 0;
         for (int jj = 0; jj < FS_MAXG && jj * wCell < ew; ++jj) {
@@ -438,6 +491,7 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
                   },
                   tmin, true);
     }
+#endif
     __syncthreads();   // also: every read of tile / cand is done, outl may overwrite them
 
     // ---- pass 3: emit.  Cells with a maximum >= iniThFAST emit their flagged maxima; the others emit every NMS

@@ -87,10 +87,10 @@ def synth_frame(seed, w=640, h=480, n_rect=260, n_tri=120, noise=8):
     return np.clip(img, 0, 255).astype(np.uint8)
 
 
-def synth_batch(seed0, n, w=640, h=480, unique=16, noise=8):
+def synth_batch(seed0, n, w=640, h=480, unique=16, noise=8, n_rect=260, n_tri=120):
     """n frames (n, h, w): `unique` generated frames, the rest are circular shifts of those (cheap but all
     distinct), so that a batch does not repeat the same memory image."""
-    base = [synth_frame(seed0 + i, w, h, noise=noise) for i in range(min(unique, n))]
+    base = [synth_frame(seed0 + i, w, h, n_rect=n_rect, n_tri=n_tri, noise=noise) for i in range(min(unique, n))]
     out = np.empty((n, h, w), np.uint8)
     for i in range(n):
         b = base[i % len(base)]
