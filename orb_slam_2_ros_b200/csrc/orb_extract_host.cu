@@ -276,6 +276,14 @@ int build_geometry(orb_ctx* c, int w, int h) {
     if (strips.empty()) strips.push_back(FastStrip());
     ORB_CUDA(cudaMalloc(&c->d_strips, sizeof(FastStrip) * strips.size()));
     ORB_CUDA(cudaMemcpyAsync(c->d_strips, strips.data(), sizeof(FastStrip) * strips.size(), cudaMemcpyHostToDevice, c->stream));
+    if (!c->d_fast_stats) {   // once per context
+        ORB_CUDA(cudaMalloc(&c->d_fast_stats, 128 * sizeof(int)));
+        ORB_CUDA(cudaMemsetAsync(c->d_fast_stats, 0, 128 * sizeof(int), c->stream));
+        ORB_CUDA(cudaHostAlloc(&c->h_fast_stats, 128 * sizeof(int), cudaHostAllocDefault));
+        ORB_CUDA(cudaEventCreateWithFlags(&c->ev_fast_stats, cudaEventDisableTiming));
+        const char* e = getenv("ORB_B200_FAST_DUAL");
+        c->fast_dual_mode = (e && (e[0] == '0' || e[0] == '1') && !e[1]) ? e[0] - '0' : 2;
+    }
 
     c->pyr_bytes = (size_t)pyr_off; c->blur_bytes = (size_t)blur_off; c->corner_elems = (size_t)corner_off;
     ORB_CUDA(cudaMalloc(&c->d_pyr, c->pyr_bytes + 256));
@@ -534,6 +542,8 @@ void orb_destroy(orb_ctx* c) {
         if (c->stream) cudaStreamSynchronize(c->stream);
         free_geometry_buffers(c);
         cudaFree(c->d_mom_tab); cudaFree(c->d_scratch); cudaFreeHost(c->h_scratch);
+        cudaFree(c->d_fast_stats); cudaFreeHost(c->h_fast_stats);
+        if (c->ev_fast_stats) cudaEventDestroy(c->ev_fast_stats);
         if (c->prof_ev[0][0])
             for (int r = 0; r < ORB_PROF_RING; ++r)
                 for (int s = 0; s < ORB_PROF_EVENTS; ++s) cudaEventDestroy(c->prof_ev[r][s]);

@@ -23,6 +23,7 @@
 //           CTA -> coalesced copy into the level's corner list (record = corner_pack(x, y, score, order key)).
 // Capacity overflows (pathological images only) fall back to slower but identical-result paths.
 #include "orb_internal.cuh"
+#include <type_traits>
 
 namespace {
 
@@ -143,13 +144,36 @@ __device__ __forceinline__ unsigned quick_word(unsigned c, unsigned r0, unsigned
            quick_u16<1u, 4u>(c << 8, r0 << 8, r8 << 8, r4 << 8, r12 << 8, r2 << 8, r10 << 8, r6 << 8, r14 << 8, K, NK, LIMB);
 }
 
-template <bool TMA>
+// Both thresholds in one evaluation (FS_DUAL): the margins  tb = minmax - C  (bright) and  td = C - maxmin  (dark), clamped at 0,
+// are compared with K = t << 8 for iniThFAST and for minThFAST.  tq >= K is the same test as quick_u16's (and drops its two
+// wrap-around false positives); the minThFAST bits are only used later, for the cells that turn out empty at iniThFAST, so
+// those cells need no second walk over the tile.
+template <unsigned BLO, unsigned BHI>
+__device__ __forceinline__ unsigned quick_u16_dual(unsigned C, unsigned a0, unsigned a8, unsigned a4, unsigned a12, unsigned a2, unsigned a10,
+                                                   unsigned a6, unsigned a14, unsigned KI, unsigned KM, unsigned& mlow) {
+    const unsigned minmax = __vminu2(__vimin3_u16x2(__vmaxu2(a0, a8), __vmaxu2(a4, a12), __vmaxu2(a2, a10)), __vmaxu2(a6, a14));
+    const unsigned maxmin = __vmaxu2(__vimax3_u16x2(__vminu2(a0, a8), __vminu2(a4, a12), __vminu2(a2, a10)), __vminu2(a6, a14));
+    const unsigned tq = __vmaxu2(__vsub2(__vmaxu2(minmax, C), C), __vsub2(C, __vminu2(C, maxmin)));
+    bool ih, il, mh, ml;
+    __vibmax_u16x2(tq, KI, &ih, &il);                        // tq >= KI
+    __vibmax_u16x2(tq, KM, &mh, &ml);                        // tq >= KM
+    mlow |= (ml ? BLO : 0u) | (mh ? BHI : 0u);
+    return (il ? BLO : 0u) | (ih ? BHI : 0u);
+}
+__device__ __forceinline__ unsigned quick_word_dual(unsigned c, unsigned r0, unsigned r8, unsigned r4, unsigned r12, unsigned r2, unsigned r10,
+                                                    unsigned r6, unsigned r14, unsigned KI, unsigned KM, unsigned& mlow) {
+    return quick_u16_dual<2u, 8u>(c, r0, r8, r4, r12, r2, r10, r6, r14, KI, KM, mlow) |
+           quick_u16_dual<1u, 4u>(c << 8, r0 << 8, r8 << 8, r4 << 8, r12 << 8, r2 << 8, r10 << 8, r6 << 8, r14 << 8, KI, KM, mlow);
+}
+
+template <bool TMA, bool DUAL>
 #ifndef FS_MINB
 #define FS_MINB 6
 #endif
 __global__ void __launch_bounds__(FS_THREADS, FS_MINB)
 fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__ strips, unsigned long long* __restrict__ corners,
-                  int* __restrict__ corner_count, const __grid_constant__ Geometry g, const FastTmaps* __restrict__ tm, int f0) {
+                  int* __restrict__ corner_count, const __grid_constant__ Geometry g, const FastTmaps* __restrict__ tm, int f0,
+                  int* __restrict__ stats) {
     extern __shared__ __align__(1024) uint8_t fs_smem_raw[];
     // the TMA destination must be 128-byte aligned: align by hand (static shared variables precede the dynamic window)
     uint8_t* fs_smem = fs_smem_raw + ((128u - (smem_u32(fs_smem_raw) & 127u)) & 127u) + 128;   // (the pair walk of stage A may read the word left of the tile's first one)
@@ -160,7 +184,7 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
     uint8_t* score = fs_smem + tile_bytes + FS_CAND_BYTES + FS_SCORED_BYTES;                      // (fast_rows - 4) x FS_PITCH scores
     unsigned short* codes = reinterpret_cast<unsigned short*>(score + FS_SCORE_BYTES(g.fast_rows));   // [8][FS_THREADS]
     unsigned long long* outl = reinterpret_cast<unsigned long long*>(fs_smem);                   // pass 3: aliases tile + cand
-    __shared__ int s_any[FS_MAXG];
+    __shared__ int s_any[FS_MAXG + 1];                   // (+1: the pair walk may look one cell beyond the strip)
     __shared__ int s_nscored, s_nout, s_base, s_nempty;
     __shared__ int s_bpre[FS_MAXG + 1], s_bw0[FS_MAXG], s_bnw[FS_MAXG];   // stage B: per empty cell word-item prefix, first word, words per row
     __shared__ unsigned s_binv[FS_MAXG], s_bmf[FS_MAXG], s_bml[FS_MAXG];
@@ -169,6 +193,10 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
 
     const int f = blockIdx.y;
     const FastStrip S = strips[blockIdx.x];               // host-precomputed (uniform loads)
+    // DUAL: stage A evaluates the quick test at iniThFAST and at minThFAST together (+5 % of the kernel) so that cells found empty
+    // at iniThFAST need no second walk over the tile (up to +30 %).  Which one is faster depends on the image content; both give the
+    // same corners.  The host picks the variant per launch from the share of empty cells the previous launches reported in `stats`
+    // (orb_launch_fast).
     const int l = S.level;
     const LevelGeom& L = g.lv[l];
     const int i = S.i, j0 = S.j0;
@@ -199,7 +227,7 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
             reinterpret_cast<unsigned*>(tile + r * FS_PITCH)[wd] = __ldg(src_w + r * gpw + wd);
         }
     }
-    if (threadIdx.x < FS_MAXG) s_any[threadIdx.x] = 0;
+    if (threadIdx.x <= FS_MAXG) s_any[threadIdx.x] = 0;
     if (threadIdx.x >= 64 && threadIdx.x < 64 + S.np) {   // valid pixels of pair q: smem bytes [sb_lo, sb_hi) inside [4 * (w0p + 2q), + 8)
         const int b0 = 4 * (S.w0p + 2 * ((int)threadIdx.x - 64));
         const int lo = max(S.a + 3 - b0, 0), hi = min(S.a + 3 + (S.tw - 6) - b0, 8);
@@ -308,9 +336,14 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
     // Stage A's candidate pass over WORD PAIRS (8 pixels of one row per item, <= 8 items per thread): the 18 tile words an
     // item needs are 11 loads (4 of them LDS.64) and 10 funnel shifts instead of 2 x (11 + 6), and the u16 high-byte form of
     // the quick test (quick_u16) needs no widening.  Pair q of a row = tile words w0p + 2q, w0p + 2q + 1 (w0p even).
+    unsigned long long cmask_low = 0ull;                   // FS_DUAL: this lane's stage-A pixels that pass the quick test at minThFAST but not at iniThFAST
+    (void)cmask_low;
     // map(k) gives item k's row, pair and valid-pixel mask; `total` <= eh * pairs per row <= 8 * FS_THREADS
-    auto pair_pass = [&](const int th, const int total, auto&& map, const bool skip) {
+    auto pair_pass = [&](const int th, const int total, auto&& map, const bool skip, auto both_tag) {
+        constexpr bool both = decltype(both_tag)::value;
         const unsigned K = ((unsigned)th << 8) * 0x10001u, NK = ((0x10000u - ((unsigned)th << 8)) & 0xFFFFu) * 0x10001u, LIMB = 0xFFFFFFFFu - K;
+        const unsigned KM = ((unsigned)tmin << 8) * 0x10001u;
+        (void)NK; (void)LIMB; (void)KM;
         const int w0p = S.w0p;
         unsigned long long cmask = 0ull;
         int it = 0;
@@ -330,13 +363,26 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
             const uint2 pp = *reinterpret_cast<const uint2*>(rp), mm = *reinterpret_cast<const uint2*>(rm);
             const unsigned pl = rp[-1], pr = rp[2], ml = rm[-1], mr = rm[2];
             const unsigned pmid = __funnelshift_r(pp.x, pp.y, 16), mmid = __funnelshift_r(mm.x, mm.y, 16);   // (+2,.) of word 0 = (-2,.) of word 1
+            unsigned m;
+            if constexpr (both) {
+            unsigned l0 = 0u, l1 = 0u;
+            const unsigned m0 = quick_word_dual(c.x, u.x, d.x, __funnelshift_r(c.x, c.y, 24), __funnelshift_r(wl, c.x, 8),      // (+3,0) (-3,0)
+                                                pmid, __funnelshift_r(ml, mm.x, 16),                                           // (+2,+2) (-2,-2)
+                                                mmid, __funnelshift_r(pl, pp.x, 16), K, KM, l0);                               // (+2,-2) (-2,+2)
+            const unsigned m1 = quick_word_dual(c.y, u.y, d.y, __funnelshift_r(c.y, wr, 24), __funnelshift_r(c.x, c.y, 8),
+                                                __funnelshift_r(pp.y, pr, 16), mmid,
+                                                __funnelshift_r(mm.y, mr, 16), pmid, K, KM, l1);
+            m = (m0 | (m1 << 4)) & vm;
+            cmask_low |= (unsigned long long)((l0 | (l1 << 4)) & vm & ~m) << (8 * it);   // passes at minThFAST only
+            } else {
             const unsigned m0 = quick_word(c.x, u.x, d.x, __funnelshift_r(c.x, c.y, 24), __funnelshift_r(wl, c.x, 8),           // (+3,0) (-3,0)
                                            pmid, __funnelshift_r(ml, mm.x, 16),                                                // (+2,+2) (-2,-2)
                                            mmid, __funnelshift_r(pl, pp.x, 16), K, NK, LIMB);                                  // (+2,-2) (-2,+2)
             const unsigned m1 = quick_word(c.y, u.y, d.y, __funnelshift_r(c.y, wr, 24), __funnelshift_r(c.x, c.y, 8),
                                            __funnelshift_r(pp.y, pr, 16), mmid,
                                            __funnelshift_r(mm.y, mr, 16), pmid, K, NK, LIMB);
-            const unsigned m = (m0 | (m1 << 4)) & vm;
+            m = (m0 | (m1 << 4)) & vm;
+            }
             cmask |= (unsigned long long)m << (8 * it);
         }
         compact_score(cmask, [&](int bit) { return (int)codes[(bit >> 3) * FS_THREADS + threadIdx.x] + (bit & 7); }, skip);
@@ -346,13 +392,12 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
     {
         const int np = S.np;
         const unsigned inv_np = S.inv_np;
-        pair_pass(tini, eh * np,
-                  [&](int k, int& r, int& q, unsigned& vm) {
-                      r = fs_div(k, np, inv_np);
-                      q = k - r * np;
-                      vm = s_pvm[q];
-                  },
-                  false);
+        auto rows = [&](int k, int& r, int& q, unsigned& vm) {
+            r = fs_div(k, np, inv_np);
+            q = k - r * np;
+            vm = s_pvm[q];
+        };
+        pair_pass(tini, eh * np, rows, false, std::integral_constant<bool, DUAL>{});
     }
 #else
     cand_pass(eh * nw,
@@ -426,6 +471,31 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
     // ---- stage B (ORBextractor.cc:846-850): the cells without any maximum >= iniThFAST are searched again at
     //      minThFAST; their word items are enumerated cell by cell through a small prefix table ----
 #if FS_QUICK == 2
+    if (stats != nullptr && threadIdx.x == 0) {            // share of empty cells, for the host's choice of the variant
+        int cells = 0, empties = 0;
+        for (int jj = 0; jj < FS_MAXG && jj * wCell < ew; ++jj) { ++cells; empties += s_any[jj] ? 0 : 1; }
+        atomicAdd(stats + 2 * (blockIdx.x & 63), empties);
+        atomicAdd(stats + 2 * (blockIdx.x & 63) + 1, cells);
+    }
+    // (dual: stage A has already run the quick test at minThFAST: keep, of this lane's low-threshold bits, the pixels of the cells
+    // that are empty, and score them; an item's 8 pixels lie in at most two cells)
+    if constexpr (DUAL) {
+        const int total = eh * S.np;
+        unsigned long long keep = 0ull;
+        int it = 0;
+        for (int k = threadIdx.x; k < total; k += FS_THREADS, ++it) {
+            const int b0 = (int)(codes[it * FS_THREADS + threadIdx.x] & (FS_PITCH - 1));   // shared-memory byte of the item's first pixel
+            const int xe = max(b0 - sb_lo, 0);
+            const int jj = (int)__umulhi((unsigned)xe, inv_wc);
+            const int nb = min(max(sb_lo + (jj + 1) * wCell - b0, 0), 8);                  // pixels [0, nb) of the item lie in cell jj, the rest in jj + 1
+            const unsigned lowbits = (1u << nb) - 1u;
+            const unsigned km = (s_any[jj] ? 0u : lowbits) | (s_any[min(jj + 1, FS_MAXG)] ? 0u : (0xFFu & ~lowbits));
+            keep |= (unsigned long long)km << (8 * it);
+        }
+        cmask_low &= keep;
+        if (__syncthreads_or(cmask_low != 0ull))
+            compact_score(cmask_low, [&](int bit) { return (int)codes[(bit >> 3) * FS_THREADS + threadIdx.x] + (bit & 7); }, true);
+    } else {
     // (word PAIRS like stage A; runs of adjacent empty cells are enumerated as one range, so that a pair straddling two empty
     // cells is visited once and the item count stays <= eh * pairs per row; interior cells are wider than a pair, so two
     // runs never share one)
@@ -461,7 +531,8 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
                       q = s_bw0[e] + cp;
                       vm = s_pvm[q] & (cp == 0 ? s_bmf[e] : 0xFFu) & (cp == n - 1 ? s_bml[e] : 0xFFu);
                   },
-                  true);
+                  true, std::false_type{});
+    }
     }
 #else
     if (threadIdx.x == 0) {
@@ -544,28 +615,63 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
 // experiment / tuning knob: one shared-memory carve-out for every kernel of the chain (ORB_B200_CARVEOUT, percent of the
 // maximum) so that kernels of different chunks can share an SM without the SM draining to re-partition L1 / shared memory
 void orb_carveout_fast(int pct) {
-    cudaFuncSetAttribute(fast_strip_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    cudaFuncSetAttribute(fast_strip_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(fast_strip_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(fast_strip_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(fast_strip_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(fast_strip_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
 }
 
 int orb_launch_fast(orb_ctx* c, const Geometry& g, int* d_corner_count, int F, int f0, cudaStream_t st, int level_begin, int level_end) {
     if (g.fast_rows > FS_ROWS) { orb_set_error("FAST strip of %d rows exceeds the tile", g.fast_rows); return ORB_ERR_INVALID; }
     if (!c->fast_attr_set) {   // > 48 KB of dynamic shared memory needs the opt-in, once per context (= per device)
-        ORB_CUDA(cudaFuncSetAttribute(fast_strip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM(FS_ROWS)));
-        ORB_CUDA(cudaFuncSetAttribute(fast_strip_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM(FS_ROWS)));
+        ORB_CUDA(cudaFuncSetAttribute(fast_strip_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM(FS_ROWS)));
+        ORB_CUDA(cudaFuncSetAttribute(fast_strip_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM(FS_ROWS)));
+        ORB_CUDA(cudaFuncSetAttribute(fast_strip_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM(FS_ROWS)));
+        ORB_CUDA(cudaFuncSetAttribute(fast_strip_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM(FS_ROWS)));
         c->fast_attr_set = true;
     }
     // strips are stored level by level: a level range is a contiguous range of CTAs
     level_end = min(level_end, g.nlevels);
     const int first = g.lv[level_begin].fast_cta_base, last = level_end < g.nlevels ? g.lv[level_end].fast_cta_base : g.fast_ctas;
     if (last <= first) return ORB_OK;
-    if (c->use_tma)
-        fast_strip_kernel<true><<<dim3(last - first, F), FS_THREADS, FS_SMEM(g.fast_rows), st>>>(c->d_pyr, c->d_strips + first, c->d_corners, d_corner_count, g,
-                                                                                   c->d_tmaps, f0);
-    else
-        fast_strip_kernel<false><<<dim3(last - first, F), FS_THREADS, FS_SMEM(g.fast_rows), st>>>(c->d_pyr, c->d_strips + first, c->d_corners, d_corner_count, g,
-                                                                                    c->d_tmaps, f0);
+    // Variant choice (fast_dual_mode 2 = by content): every few launches the kernel also reports how many of its cells were empty at
+    // iniThFAST; the counters come back through a pinned buffer and are looked at, without waiting, by a later launch.  Above ~1/4
+    // empty cells the two-threshold variant is faster (hysteresis 0.18 / 0.28).  Nothing of this happens inside a stream capture.
+    int* stats = nullptr;
+    if (c->fast_dual_mode == 2 && c->d_fast_stats) {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(st, &cap);
+        if (cap == cudaStreamCaptureStatusNone) {
+            if (c->fast_stats_pending && cudaEventQuery(c->ev_fast_stats) == cudaSuccess) {
+                long long empties = 0, cells = 0;
+                for (int k = 0; k < 64; ++k) { empties += c->h_fast_stats[2 * k]; cells += c->h_fast_stats[2 * k + 1]; }
+                if (cells > 0) {
+                    const double share = (double)empties / (double)cells;
+                    if (share > 0.28) c->fast_dual_now = true;
+                    else if (share < 0.18) c->fast_dual_now = false;
+                }
+                c->fast_stats_pending = false;
+            }
+            if (!c->fast_stats_pending && (c->fast_launch_no++ & 3) == 0) stats = c->d_fast_stats;
+        }
+    }
+    const bool dual = c->fast_dual_mode == 1 || (c->fast_dual_mode == 2 && c->fast_dual_now);
+    const dim3 grid(last - first, F);
+    const size_t smem = FS_SMEM(g.fast_rows);
+    if (c->use_tma) {
+        if (dual) fast_strip_kernel<true, true><<<grid, FS_THREADS, smem, st>>>(c->d_pyr, c->d_strips + first, c->d_corners, d_corner_count, g, c->d_tmaps, f0, stats);
+        else fast_strip_kernel<true, false><<<grid, FS_THREADS, smem, st>>>(c->d_pyr, c->d_strips + first, c->d_corners, d_corner_count, g, c->d_tmaps, f0, stats);
+    } else {
+        if (dual) fast_strip_kernel<false, true><<<grid, FS_THREADS, smem, st>>>(c->d_pyr, c->d_strips + first, c->d_corners, d_corner_count, g, c->d_tmaps, f0, stats);
+        else fast_strip_kernel<false, false><<<grid, FS_THREADS, smem, st>>>(c->d_pyr, c->d_strips + first, c->d_corners, d_corner_count, g, c->d_tmaps, f0, stats);
+    }
     c->launches++;
     ORB_CUDA(cudaGetLastError());
+    if (stats) {
+        ORB_CUDA(cudaMemcpyAsync(c->h_fast_stats, c->d_fast_stats, 128 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        ORB_CUDA(cudaMemsetAsync(c->d_fast_stats, 0, 128 * sizeof(int), st));
+        ORB_CUDA(cudaEventRecord(c->ev_fast_stats, st));
+        c->fast_stats_pending = true;
+    }
     return ORB_OK;
 }

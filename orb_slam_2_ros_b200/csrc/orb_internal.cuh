@@ -164,6 +164,14 @@ struct orb_ctx {
     ResizeWord* d_wtaps = nullptr;
     ResizeSeg* d_rsegs = nullptr;
     FastStrip* d_strips = nullptr;
+    // FAST variant choice (orb_fast.cu): 0 / 1 = stage A evaluates iniThFAST only / both thresholds, 2 = by the share of empty cells
+    // the kernel reports (ORB_B200_FAST_DUAL; default 2)
+    int fast_dual_mode = 2;
+    bool fast_dual_now = false, fast_stats_pending = false;
+    unsigned fast_launch_no = 0;
+    int* d_fast_stats = nullptr;      // 64 x (empty cells, cells)
+    int* h_fast_stats = nullptr;      // pinned copy
+    cudaEvent_t ev_fast_stats = nullptr;
     FastTmaps tmaps;              // valid when use_tma
     FastTmaps* d_tmaps = nullptr; // device copy (the TMA unit reads the descriptor from global memory)
     FastTmaps* d_btmaps = nullptr; // the same for the BLURRED levels (dims: row bytes, rows, frames): descriptor tap windows (orient_describe_kernel)

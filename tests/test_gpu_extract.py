@@ -308,3 +308,33 @@ def test_batch_throughput_kernels_odd_and_wide_shapes(oracle, ORB, w, h, nf):
         ob = oex.blurred(l)
         if ob is not None:
             assert np.array_equal(ex.debug_blurred(l), ob), "blur level %d" % l
+
+
+@pytest.mark.parametrize("mode", ["0", "1", "2"])
+def test_fast_threshold_modes_give_identical_corners(oracle, ORB, mode, monkeypatch):
+    """The FAST kernel evaluates the quick test at iniThFAST only (0: empty cells are walked again at minThFAST), at both thresholds
+    in one walk (1), or per strip position by the emptiness seen by the previous frame (2, the default): all three must give the
+    oracle's raw corner lists and keypoints — on the headline scene, on a sparse scene (most cells empty at iniThFAST), on flat
+    and low-contrast frames, and when the frames of a batch alternate between dense and sparse (stale hints)."""
+    monkeypatch.setenv("ORB_B200_FAST_DUAL", mode)
+    dense = synth.synth_batch(900, 3, 640, 480, unique=3)
+    sparse = synth.synth_batch(910, 3, 640, 480, unique=3, noise=2, n_rect=40, n_tri=20)
+    flat = np.full((480, 640), 90, np.uint8); flat[200:215, 300:330] = 110      # one low-contrast blob: found at minThFAST only
+    imgs = np.stack([dense[0], sparse[0], flat, dense[1], sparse[1], dense[2], sparse[2], flat, dense[0], sparse[0]])
+    for ini, mn in ((20, 7), (12, 12), (40, 3)):
+        ex = ORB(1000, 1.2, 8, ini, mn, max_batch=len(imgs))
+        oex = oracle.Extractor(1000, 1.2, 8, ini, mn)
+        for rep in range(2):                                # second round: hints left by the last frames of the first
+            res = ex.extract_batch(imgs)
+            for f in (0, 1, 2, 4, 7, 9):
+                ok, od = oex.extract(imgs[f])
+                assert_kps_equal(res[f][0], ok, "mode %s th %d/%d frame %d" % (mode, ini, mn, f))
+                assert np.array_equal(res[f][1], od)
+        for img in (sparse[1], dense[2], flat):            # single frames: raw corner lists level by level
+            k, d = ex(img)
+            ok, od = oex.extract(img)
+            assert_kps_equal(k, ok, "single")
+            for l in range(8):
+                raw, oraw = ex.debug_raw_corners(l), oex.raw_corners(l)
+                oraw = np.stack([oraw["x"], oraw["y"], oraw["response"]], 1) if len(oraw) else np.zeros((0, 3), np.float32)
+                assert np.array_equal(raw, oraw), "raw corners level %d" % l
