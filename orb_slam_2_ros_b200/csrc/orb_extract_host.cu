@@ -264,7 +264,7 @@ int build_geometry(orb_ctx* c, int w, int h) {
                 s.inv_lw = 0xFFFFFFFFu / (unsigned)s.lw + 1u;
                 s.inv_nw = 0xFFFFFFFFu / (unsigned)s.nw + 1u;
                 s.inv_wc = 0xFFFFFFFFu / (unsigned)L.wCell + 1u;
-                s.w0p = s.wlo & ~1; s.np = ((s.wlo + s.nw - 1) >> 1) - (s.w0p >> 1) + 1;
+                s.w0p = s.wlo & ~1; s.np = std::max(2, ((s.wlo + s.nw - 1) >> 1) - (s.w0p >> 1) + 1);   // >= 2: the 32-bit magic number of a division by 1 does not exist (a surplus pair has no valid pixel)
                 s.inv_np = 0xFFFFFFFFu / (unsigned)s.np + 1u;
                 strips.push_back(s);
             }

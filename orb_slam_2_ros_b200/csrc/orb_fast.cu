@@ -166,6 +166,9 @@ __device__ __forceinline__ unsigned quick_word_dual(unsigned c, unsigned r0, uns
            quick_u16_dual<1u, 4u>(c << 8, r0 << 8, r8 << 8, r4 << 8, r12 << 8, r2 << 8, r10 << 8, r6 << 8, r14 << 8, KI, KM, mlow);
 }
 
+#ifndef FS_STAGEB_WORDS
+#define FS_STAGEB_WORDS 0   // 1: the single-threshold variant re-walks the empty cells word by word (s16 lanes) instead of by word pairs
+#endif
 template <bool TMA, bool DUAL>
 #ifndef FS_MINB
 #define FS_MINB 6
@@ -393,7 +396,7 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
         const int np = S.np;
         const unsigned inv_np = S.inv_np;
         auto rows = [&](int k, int& r, int& q, unsigned& vm) {
-            r = fs_div(k, np, inv_np);
+            r = (int)__umulhi((unsigned)k, inv_np);          // np >= 2 (host)
             q = k - r * np;
             vm = s_pvm[q];
         };
@@ -496,6 +499,35 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
         if (__syncthreads_or(cmask_low != 0ull))
             compact_score(cmask_low, [&](int bit) { return (int)codes[(bit >> 3) * FS_THREADS + threadIdx.x] + (bit & 7); }, true);
     } else {
+#if FS_STAGEB_WORDS
+    if (threadIdx.x == 0) {
+        int ne = 0, pre = 0;
+        for (int jj = 0; jj < FS_MAXG && jj * wCell < ew; ++jj) {
+            if (s_any[jj]) continue;
+            const int lo = sb_lo + jj * wCell, hi = min(lo + wCell, sb_hi);   // shared-memory bytes of the cell's evaluated columns
+            const int w0 = lo >> 2, n = ((hi - 1) >> 2) - w0 + 1;
+            s_bw0[ne] = w0; s_bnw[ne] = n; s_binv[ne] = 0xFFFFFFFFu / (unsigned)n + 1u;
+            s_bmf[ne] = (0xFu << (lo & 3)) & 0xFu; s_bml[ne] = 0xFu >> (3 - ((hi - 1) & 3));
+            s_bpre[ne] = pre; pre += n * eh; ++ne;
+        }
+        s_bpre[ne] = pre; s_nempty = ne;
+    }
+    __syncthreads();
+    const int nempty = s_nempty;
+    if (nempty > 0 && tmin < tini) {
+        cand_pass(s_bpre[nempty],
+                  [&](int k, int& r, int& wd, unsigned& vm) {
+                      int e = 0;
+                      while (e + 1 < nempty && k >= s_bpre[e + 1]) ++e;
+                      const int kk = k - s_bpre[e], n = s_bnw[e];
+                      r = fs_div(kk, n, s_binv[e]);
+                      const int cw = kk - r * n;
+                      wd = s_bw0[e] + cw;
+                      vm = (cw == 0 ? s_bmf[e] : 0xFu) & (cw == n - 1 ? s_bml[e] : 0xFu);
+                  },
+                  tmin, true);
+    }
+#else
     // (word PAIRS like stage A; runs of adjacent empty cells are enumerated as one range, so that a pair straddling two empty
     // cells is visited once and the item count stays <= eh * pairs per row; interior cells are wider than a pair, so two
     // runs never share one)
@@ -533,6 +565,7 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
                   },
                   true, std::false_type{});
     }
+#endif
     }
 #else
     if (threadIdx.x == 0) {
