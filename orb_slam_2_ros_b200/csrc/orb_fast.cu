@@ -675,7 +675,9 @@ int orb_launch_fast(orb_ctx* c, const Geometry& g, int* d_corner_count, int F, i
         cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
         cudaStreamIsCapturing(st, &cap);
         if (cap == cudaStreamCaptureStatusNone) {
-            if (c->fast_stats_pending && cudaEventQuery(c->ev_fast_stats) == cudaSuccess) {
+            const cudaError_t ready = c->fast_stats_pending ? cudaEventQuery(c->ev_fast_stats) : cudaErrorNotReady;
+            if (c->fast_stats_pending && ready == cudaErrorNotReady) (void)cudaGetLastError();   // "not ready" is an answer, not a fault of the launch below
+            if (c->fast_stats_pending && ready == cudaSuccess) {
                 long long empties = 0, cells = 0;
                 for (int k = 0; k < 64; ++k) { empties += c->h_fast_stats[2 * k]; cells += c->h_fast_stats[2 * k + 1]; }
                 if (cells > 0) {
