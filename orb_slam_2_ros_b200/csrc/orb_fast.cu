@@ -160,12 +160,31 @@ __device__ __forceinline__ unsigned quick_u16_dual(unsigned C, unsigned a0, unsi
     mlow |= (ml ? BLO : 0u) | (mh ? BHI : 0u);
     return (il ? BLO : 0u) | (ih ? BHI : 0u);
 }
+// one threshold, same margin form: one compare (two predicates) per lane pair instead of a bright and a dark one
+template <unsigned BLO, unsigned BHI>
+__device__ __forceinline__ unsigned quick_u16_margin(unsigned C, unsigned a0, unsigned a8, unsigned a4, unsigned a12, unsigned a2, unsigned a10,
+                                                     unsigned a6, unsigned a14, unsigned K) {
+    const unsigned minmax = __vminu2(__vimin3_u16x2(__vmaxu2(a0, a8), __vmaxu2(a4, a12), __vmaxu2(a2, a10)), __vmaxu2(a6, a14));
+    const unsigned maxmin = __vmaxu2(__vimax3_u16x2(__vminu2(a0, a8), __vminu2(a4, a12), __vminu2(a2, a10)), __vminu2(a6, a14));
+    const unsigned tq = __vmaxu2(__vsub2(__vmaxu2(minmax, C), C), __vsub2(C, __vminu2(C, maxmin)));
+    bool h, l;
+    __vibmax_u16x2(tq, K, &h, &l);                           // tq >= K
+    return (l ? BLO : 0u) | (h ? BHI : 0u);
+}
+__device__ __forceinline__ unsigned quick_word_margin(unsigned c, unsigned r0, unsigned r8, unsigned r4, unsigned r12, unsigned r2, unsigned r10,
+                                                      unsigned r6, unsigned r14, unsigned K) {
+    return quick_u16_margin<2u, 8u>(c, r0, r8, r4, r12, r2, r10, r6, r14, K) |
+           quick_u16_margin<1u, 4u>(c << 8, r0 << 8, r8 << 8, r4 << 8, r12 << 8, r2 << 8, r10 << 8, r6 << 8, r14 << 8, K);
+}
 __device__ __forceinline__ unsigned quick_word_dual(unsigned c, unsigned r0, unsigned r8, unsigned r4, unsigned r12, unsigned r2, unsigned r10,
                                                     unsigned r6, unsigned r14, unsigned KI, unsigned KM, unsigned& mlow) {
     return quick_u16_dual<2u, 8u>(c, r0, r8, r4, r12, r2, r10, r6, r14, KI, KM, mlow) |
            quick_u16_dual<1u, 4u>(c << 8, r0 << 8, r8 << 8, r4 << 8, r12 << 8, r2 << 8, r10 << 8, r6 << 8, r14 << 8, KI, KM, mlow);
 }
 
+#ifndef FS_MARGIN
+#define FS_MARGIN 1         // single-threshold quick test in the margin form (one compare per lane pair) instead of a bright and a dark compare
+#endif
 #ifndef FS_STAGEB_WORDS
 #define FS_STAGEB_WORDS 0   // 1: the single-threshold variant re-walks the empty cells word by word (s16 lanes) instead of by word pairs
 #endif
@@ -378,12 +397,21 @@ fast_strip_kernel(const uint8_t* __restrict__ pyr, const FastStrip* __restrict__
             m = (m0 | (m1 << 4)) & vm;
             cmask_low |= (unsigned long long)((l0 | (l1 << 4)) & vm & ~m) << (8 * it);   // passes at minThFAST only
             } else {
+#if FS_MARGIN
+            const unsigned m0 = quick_word_margin(c.x, u.x, d.x, __funnelshift_r(c.x, c.y, 24), __funnelshift_r(wl, c.x, 8),    // (+3,0) (-3,0)
+                                                  pmid, __funnelshift_r(ml, mm.x, 16),                                         // (+2,+2) (-2,-2)
+                                                  mmid, __funnelshift_r(pl, pp.x, 16), K);                                     // (+2,-2) (-2,+2)
+            const unsigned m1 = quick_word_margin(c.y, u.y, d.y, __funnelshift_r(c.y, wr, 24), __funnelshift_r(c.x, c.y, 8),
+                                                  __funnelshift_r(pp.y, pr, 16), mmid,
+                                                  __funnelshift_r(mm.y, mr, 16), pmid, K);
+#else
             const unsigned m0 = quick_word(c.x, u.x, d.x, __funnelshift_r(c.x, c.y, 24), __funnelshift_r(wl, c.x, 8),           // (+3,0) (-3,0)
                                            pmid, __funnelshift_r(ml, mm.x, 16),                                                // (+2,+2) (-2,-2)
                                            mmid, __funnelshift_r(pl, pp.x, 16), K, NK, LIMB);                                  // (+2,-2) (-2,+2)
             const unsigned m1 = quick_word(c.y, u.y, d.y, __funnelshift_r(c.y, wr, 24), __funnelshift_r(c.x, c.y, 8),
                                            __funnelshift_r(pp.y, pr, 16), mmid,
                                            __funnelshift_r(mm.y, mr, 16), pmid, K, NK, LIMB);
+#endif
             m = (m0 | (m1 << 4)) & vm;
             }
             cmask |= (unsigned long long)m << (8 * it);
