@@ -12,10 +12,15 @@
 //
 // Kernel shape: one CTA = a strip of up to fast_G consecutive cells of one cell row (tile <= 256 x 66 px in shared
 // memory).  Threads work on aligned 32-bit words of 4 pixels:
-//   pass 1a direction-aware quick reject, 2 pixels per instruction on s16x2 lanes (VIMNMX.S16x2): a bright (dark)
-//           9-arc holds one pixel of each antipodal ring pair, so  min over the 4 axis/diagonal pairs of
-//           max(r_k, r_k+8) > c + t  (resp. max of min < c - t) is necessary.  Every lane keeps a 64-bit mask of
-//           its candidates; each WARP compacts its masks once into a private shared-memory segment
+//   pass 1a direction-aware quick reject, 2 pixels per instruction on u16x2 lanes whose high bytes hold the pixels
+//           (VIMNMX.U16x2, word pairs = 8 pixels per item): a bright (dark) 9-arc holds one pixel of each antipodal ring
+//           pair, so  min over the 4 axis/diagonal pairs of max(r_k, r_k+8) > c + t  (resp. max of min < c - t) is
+//           necessary; both are tested at once as  max(minmax - c, c - maxmin) >= t << 8  on the clamped margins.
+//           Every lane keeps a 64-bit mask of its candidates; each WARP compacts its masks once into a private
+//           shared-memory segment.  Stage A = the whole strip at iniThFAST; stage B = the cells that have no NMS maximum
+//           >= iniThFAST, at minThFAST — either a second walk over those cells (template DUAL = false) or from a second
+//           mask stage A built in the same walk (DUAL = true); orb_launch_fast picks the variant from the share of empty
+//           cells the kernel reports
 //   pass 1b exact 16-pixel score of the warp's candidates, all lanes busy; both polarities in one s16x2 tree on
 //           (r, 255 - r) pairs -> u8 score tile + CTA-wide list of scored corners (score >= minThFAST)
 //   pass 2  NMS over the scored list (dense); cells decide their threshold: any NMS maximum >= iniThFAST?
